@@ -1,0 +1,230 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see jmath.h header).  PARITY UNPINNED.
+// C entry points over the CPU restatement, loaded with ctypes by tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference legs.  Nothing in the product links this.
+#include <chrono>
+#include <cstring>
+#include "world.h"
+
+using namespace orc;
+
+static Xf xfFrom12(const float* t) {  // 9 basis floats row-major + 3 origin floats
+    Xf x;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) x.basis.m[r][c] = t[r * 3 + c];
+    x.origin.set(t[9], t[10], t[11]);
+    return x;
+}
+
+extern "C" {
+
+void* orc_create(int mode) {
+    World* w = new World();
+    w->mode = mode;
+    return w;
+}
+void orc_destroy(void* h) { delete (World*)h; }
+void orc_set_brute_force(void* h, int on) { ((World*)h)->bruteForcePairs = on != 0; }
+void orc_set_params(void* h, float breaking, float dbvtMargin, float predictedFrames) {
+    World* w = (World*)h;
+    w->breakingThreshold = breaking;
+    w->dbvtMargin = dbvtMargin;
+    w->predictedFrames = predictedFrames;
+}
+
+int orc_shape_box(void* h, float hx, float hy, float hz) {
+    Shape s;
+    initBox(s, V3(hx, hy, hz));
+    return ((World*)h)->addShape(s);
+}
+int orc_shape_sphere(void* h, float r) {
+    Shape s;
+    initSphere(s, r);
+    return ((World*)h)->addShape(s);
+}
+int orc_shape_hull(void* h, const float* pts, int n) {
+    Shape s;
+    initHull(s, pts, n);
+    return ((World*)h)->addShape(s);
+}
+int orc_shape_plane(void* h, float nx, float ny, float nz, float c) {
+    Shape s;
+    initPlane(s, V3(nx, ny, nz), c);
+    return ((World*)h)->addShape(s);
+}
+int orc_shape_mesh(void* h, const float* verts, int nv, const int* idx, int ntri) {
+    return ((World*)h)->addMesh(verts, nv, idx, ntri);
+}
+int orc_mesh_num_nodes(void* h, int shape) { return (int)((World*)h)->meshes[shape]->bvh.nodes.size(); }
+void orc_mesh_get_nodes(void* h, int shape, void* out16B) {
+    Bvh& b = ((World*)h)->meshes[shape]->bvh;
+    std::memcpy(out16B, b.nodes.data(), b.nodes.size() * sizeof(QNode));
+}
+void orc_mesh_get_quant(void* h, int shape, float* out9) {
+    Bvh& b = ((World*)h)->meshes[shape]->bvh;
+    out9[0] = b.bvhAabbMin.x; out9[1] = b.bvhAabbMin.y; out9[2] = b.bvhAabbMin.z;
+    out9[3] = b.bvhAabbMax.x; out9[4] = b.bvhAabbMax.y; out9[5] = b.bvhAabbMax.z;
+    out9[6] = b.bvhQuantization.x; out9[7] = b.bvhQuantization.y; out9[8] = b.bvhQuantization.z;
+}
+
+int orc_body_create(void* h, int shape, const float* xf12, int group, int mask, int isStatic) {
+    return ((World*)h)->addBody(shape, xfFrom12(xf12), group, mask, isStatic != 0);
+}
+void orc_body_destroy(void* h, int uid) { ((World*)h)->removeBody(uid); }
+int orc_num_bodies(void* h) { return (int)((World*)h)->bodies.size(); }
+
+// xf: n x 12 floats; uids may be NULL (= bodies 1..n)
+void orc_set_transforms(void* h, int n, const int* uids, const float* xf) {
+    World* w = (World*)h;
+    for (int i = 0; i < n; i++) {
+        int uid = uids ? uids[i] : i + 1;
+        w->bodies[uid - 1].xf = xfFrom12(xf + 12 * i);
+    }
+}
+void orc_set_active(void* h, int n, const int* uids, const unsigned char* active) {
+    World* w = (World*)h;
+    for (int i = 0; i < n; i++) {
+        int uid = uids ? uids[i] : i + 1;
+        w->bodies[uid - 1].active = active[i] != 0;
+    }
+}
+void orc_set_material(void* h, int uid, float friction, float restitution) {
+    World* w = (World*)h;
+    w->bodies[uid - 1].friction = friction;
+    w->bodies[uid - 1].restitution = restitution;
+}
+void orc_update_aabbs(void* h) { ((World*)h)->updateAabbs(); }
+void orc_set_aabb(void* h, int uid, const float* mn, const float* mx) {
+    World* w = (World*)h;
+    w->setAabb(w->bodies[uid - 1], V3(mn[0], mn[1], mn[2]), V3(mx[0], mx[1], mx[2]));
+}
+// out: n x 6 floats (effective AABB min xyz, max xyz)
+void orc_get_aabbs(void* h, float* out) {
+    World* w = (World*)h;
+    for (size_t i = 0; i < w->bodies.size(); i++) {
+        const Body& b = w->bodies[i];
+        out[6 * i + 0] = b.effMin.x; out[6 * i + 1] = b.effMin.y; out[6 * i + 2] = b.effMin.z;
+        out[6 * i + 3] = b.effMax.x; out[6 * i + 4] = b.effMax.y; out[6 * i + 5] = b.effMax.z;
+    }
+}
+int orc_calculate_overlapping_pairs(void* h) { return ((World*)h)->calculateOverlappingPairs(); }
+void orc_get_pairs(void* h, int* out) {
+    World* w = (World*)h;
+    for (size_t i = 0; i < w->pairs.size(); i++) {
+        out[2 * i] = w->pairs[i].first;
+        out[2 * i + 1] = w->pairs[i].second;
+    }
+}
+int orc_dispatch_all_pairs(void* h) { return ((World*)h)->dispatchAllPairs(); }
+int orc_num_raw(void* h) { return (int)((World*)h)->raw.size(); }
+// raw record: 5 ints (uid0, uid1, tri, hasContact, method) + iters ; 7 floats (normal, point, depth)
+void orc_get_raw(void* h, int* ints6, float* floats7) {
+    World* w = (World*)h;
+    for (size_t i = 0; i < w->raw.size(); i++) {
+        const RawContact& r = w->raw[i];
+        ints6[6 * i + 0] = r.uid0; ints6[6 * i + 1] = r.uid1; ints6[6 * i + 2] = r.tri;
+        ints6[6 * i + 3] = r.hasContact; ints6[6 * i + 4] = r.method; ints6[6 * i + 5] = r.iters;
+        for (int k = 0; k < 3; k++) { floats7[7 * i + k] = r.normal[k]; floats7[7 * i + 3 + k] = r.point[k]; }
+        floats7[7 * i + 6] = r.depth;
+    }
+}
+// Manifolds in pair order.  Per manifold: ints[4] = (pairUid0, pairUid1, body0, body1), nContacts;
+// per point (4 slots): 16 floats = localA(3) localB(3) worldA(3) worldB(3) normal(3) distance(1),
+// and 7 ints = lifeTime, srcSlot, partId0, partId1, index0, index1, pad; plus friction/restitution floats.
+int orc_get_manifolds(void* h, int cap, int* hdr5, float* pts /*cap*4*18*/, int* pint /*cap*4*6*/) {
+    World* w = (World*)h;
+    int n = 0;
+    for (auto& kv : w->pairState) {
+        if (!kv.second.hasManifold) continue;
+        if (n < cap) {
+            const PersistentManifold& m = kv.second.manifold;
+            hdr5[5 * n + 0] = kv.first.first; hdr5[5 * n + 1] = kv.first.second;
+            hdr5[5 * n + 2] = m.body0; hdr5[5 * n + 3] = m.body1; hdr5[5 * n + 4] = m.cachedPoints;
+            for (int k = 0; k < 4; k++) {
+                const ManifoldPoint& p = m.pointCache[k];
+                float* f = pts + ((size_t)n * 4 + k) * 18;
+                int* ii = pint + ((size_t)n * 4 + k) * 6;
+                if (k >= m.cachedPoints) {
+                    for (int q = 0; q < 18; q++) f[q] = 0;
+                    for (int q = 0; q < 6; q++) ii[q] = 0;
+                    continue;
+                }
+                f[0] = p.localPointA.x; f[1] = p.localPointA.y; f[2] = p.localPointA.z;
+                f[3] = p.localPointB.x; f[4] = p.localPointB.y; f[5] = p.localPointB.z;
+                f[6] = p.positionWorldOnA.x; f[7] = p.positionWorldOnA.y; f[8] = p.positionWorldOnA.z;
+                f[9] = p.positionWorldOnB.x; f[10] = p.positionWorldOnB.y; f[11] = p.positionWorldOnB.z;
+                f[12] = p.normalWorldOnB.x; f[13] = p.normalWorldOnB.y; f[14] = p.normalWorldOnB.z;
+                f[15] = p.distance1; f[16] = p.combinedFriction; f[17] = p.combinedRestitution;
+                ii[0] = p.lifeTime; ii[1] = p.srcSlot; ii[2] = p.partId0; ii[3] = p.partId1;
+                ii[4] = p.index0; ii[5] = p.index1;
+            }
+        }
+        n++;
+    }
+    return n;
+}
+void orc_get_counters(void* h, long* out5) {
+    World* w = (World*)h;
+    out5[0] = w->gjkChecks; out5[1] = w->deepPenetrationChecks; out5[2] = w->addedContacts;
+    out5[3] = w->bvhNodesVisited; out5[4] = w->trianglesTested;
+}
+
+// ---- stand-alone kernels for known-answer tests ------------------------------------------
+// shape AABB for a shape under a transform (no +-threshold)
+void orc_shape_aabb(void* h, int shape, const float* xf12, float* out6) {
+    World* w = (World*)h;
+    V3 mn, mx;
+    shapeGetAabb(w->shapes[shape], xfFrom12(xf12), mn, mx);
+    out6[0] = mn.x; out6[1] = mn.y; out6[2] = mn.z; out6[3] = mx.x; out6[4] = mx.y; out6[5] = mx.z;
+}
+// one GjkPairDetector.getClosestPoints call; out: hasContact, method, iters, degenerate ; normal, point, depth
+void orc_gjk_pair(void* h, int shapeA, const float* xfA, int shapeB, const float* xfB, int* outi4, float* outf7) {
+    World* w = (World*)h;
+    const Shape* a = &w->shapes[shapeA];
+    const Shape* b = &w->shapes[shapeB];
+    float maxd = a->getMargin() + b->getMargin() + w->breakingThreshold;
+    maxd *= maxd;
+    GjkOut out;
+    gjkGetClosestPoints(a, b, xfFrom12(xfA), xfFrom12(xfB), maxd, out);
+    outi4[0] = out.hasContact; outi4[1] = out.lastUsedMethod; outi4[2] = out.curIter; outi4[3] = out.degenerateSimplex;
+    outf7[0] = out.normalOnBInWorld.x; outf7[1] = out.normalOnBInWorld.y; outf7[2] = out.normalOnBInWorld.z;
+    outf7[3] = out.pointInWorld.x; outf7[4] = out.pointInWorld.y; outf7[5] = out.pointInWorld.z;
+    outf7[6] = out.depth;
+}
+// support vertex (with or without margin)
+void orc_support(void* h, int shape, const float* dir, int withMargin, float* out3) {
+    World* w = (World*)h;
+    V3 o;
+    if (withMargin) localGetSupportingVertex(w->shapes[shape], V3(dir[0], dir[1], dir[2]), o);
+    else localGetSupportingVertexWithoutMargin(w->shapes[shape], V3(dir[0], dir[1], dir[2]), o);
+    out3[0] = o.x; out3[1] = o.y; out3[2] = o.z;
+}
+// BVH query: returns number of triangles reported (first cap written)
+int orc_bvh_query(void* h, int shape, const float* mn, const float* mx, int* outTris, int cap) {
+    World* w = (World*)h;
+    int n = 0;
+    w->meshes[shape]->bvh.reportAabbOverlappingNodex(V3(mn[0], mn[1], mn[2]), V3(mx[0], mx[1], mx[2]), [&](int, int tri) {
+        if (n < cap) outTris[n] = tri;
+        n++;
+    });
+    return n;
+}
+// the two trig constants EncloseOrigin's line case needs (np/GjkEpaSolver.java:449-451)
+void orc_epa_constants(float* out2) {
+    float angle = SIMD_2_PI_ / 3.0f;
+    out2[0] = (float)std::sin((double)(angle * 0.5f));
+    out2[1] = (float)std::cos((double)(angle * 0.5f));
+}
+
+// One full collision step timed on this thread (for bench.py's CPU arm): returns seconds.
+double orc_timed_step(void* h, int n, const float* xf, int* npairs, int* nmanifolds) {
+    World* w = (World*)h;
+    auto t0 = std::chrono::steady_clock::now();
+    orc_set_transforms(h, n, nullptr, xf);
+    w->updateAabbs();
+    *npairs = w->calculateOverlappingPairs();
+    *nmanifolds = w->dispatchAllPairs();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"

@@ -1,0 +1,446 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see jmath.h header).  PARITY UNPINNED.
+// world.h — restatement of the per-step collision path
+//   disp/CollisionWorld.java:123-151 performDiscreteCollisionDetection
+//     :231-245 updateAabbs / :195-229 updateSingleAabb
+//     bp/DbvtBroadphase.java:89-228 (as the per-proxy effective-AABB state machine)
+//     bp/SimpleBroadphase.java:81-110 ("tight" mode)
+//     disp/CollisionDispatcher.java:198-257 + disp/DefaultNearCallback.java:39-66
+//     disp/DefaultCollisionConfiguration.java:149-213 (algorithm table)
+//     disp/SphereSphereCollisionAlgorithm.java:73-134, disp/ConvexPlaneCollisionAlgorithm.java:75-136,
+//     disp/ConvexConvexAlgorithm.java:90-139, disp/ConvexConcaveCollisionAlgorithm.java:65-93,
+//     disp/ConvexTriangleCallback.java:83-172
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <vector>
+#include "bvh.h"
+#include "gjk.h"
+#include "jmath.h"
+#include "manifold.h"
+#include "shapes.h"
+
+namespace orc {
+
+enum BroadphaseMode { BP_TIGHT = 0, BP_DBVT = 1 };
+
+struct Body {
+    int shape = -1;
+    Xf xf;
+    int16_t group = 1, mask = -1;
+    int uid = 0;
+    bool isStatic = false;
+    bool active = true;
+    bool alive = true;
+    float friction = 0.5f, restitution = 0.0f;  // disp/CollisionObject.java:95,71
+    // broadphase proxy state
+    V3 effMin, effMax;    // DbvtProxy.aabb (bp/DbvtProxy.java:35) / SimpleBroadphaseProxy min,max
+    V3 leafMin, leafMax;  // proxy.leaf.volume
+    bool inFixed = false; // stage == STAGECOUNT
+    int lastSetStep = -1; // step index of the last setAabb (createProxy counts as one)
+    bool aabbOverflow = false;
+};
+
+struct RawContact {  // one detector result, before ManifoldResult
+    int uid0, uid1;  // the broadphase pair
+    int tri;         // triangle index for mesh pairs, else -1
+    int hasContact;
+    float normal[3], point[3], depth;
+    int method;      // GjkPairDetector.lastUsedMethod, or 10 sphere-sphere, 11 convex-plane
+    int iters;
+};
+
+struct PairState {
+    PersistentManifold manifold;
+    bool hasManifold = false;
+};
+
+struct MeshShapeData {
+    MeshData mesh;
+    Bvh bvh;
+};
+
+struct World {
+    int mode = BP_TIGHT;
+    float breakingThreshold = 0.02f;  // BulletGlobals.java:63
+    float dbvtMargin = 0.05f;         // bp/DbvtBroadphase.java:35
+    float predictedFrames = 2.0f;     // bp/DbvtBroadphase.java:73
+    bool bruteForcePairs = false;     // O(N^2) pair enumeration instead of sort-and-sweep
+    std::vector<Shape> shapes;
+    std::vector<std::unique_ptr<MeshShapeData>> meshes;  // indexed by shape id (null for non-mesh)
+    std::vector<Body> bodies;  // index = uid-1
+    int step = 0;
+    std::vector<std::pair<int, int>> pairs;  // sorted (uid0<uid1)
+    std::map<std::pair<int, int>, PairState> pairState;
+    std::vector<RawContact> raw;
+    // counters
+    long gjkChecks = 0, deepPenetrationChecks = 0, addedContacts = 0, bvhNodesVisited = 0, trianglesTested = 0;
+
+    int addShape(const Shape& s) {
+        shapes.push_back(s);
+        meshes.emplace_back(nullptr);
+        return (int)shapes.size() - 1;
+    }
+    int addMesh(const float* verts, int nv, const int* idx, int ntri) {
+        std::unique_ptr<MeshShapeData> md(new MeshShapeData());
+        md->mesh.verts.assign(verts, verts + 3 * nv);
+        md->mesh.idx.assign(idx, idx + 3 * ntri);
+        // sh/StridingMeshInterface.java calculateAabbBruteForce
+        V3 mn(1e30f, 1e30f, 1e30f), mx(-1e30f, -1e30f, -1e30f);
+        for (int t = 0; t < ntri; t++) {
+            V3 tri[3];
+            md->mesh.getTriangle(t, tri);
+            for (int k = 0; k < 3; k++) {
+                mn.x = jminf(mn.x, tri[k].x); mn.y = jminf(mn.y, tri[k].y); mn.z = jminf(mn.z, tri[k].z);
+                mx.x = jmaxf(mx.x, tri[k].x); mx.y = jmaxf(mx.y, tri[k].y); mx.z = jmaxf(mx.z, tri[k].z);
+            }
+        }
+        md->bvh.build(md->mesh, mn, mx);
+        Shape s;
+        s.type = SH_MESH;
+        s.collisionMargin = 0.0f;  // sh/ConcaveShape.java:35
+        // sh/TriangleMeshShape.java:79-93 recalcLocalAabb: extreme vertex coordinate per axis +- margin
+        for (int i = 0; i < 3; i++) {
+            s.localAabbMax.setc(i, mx.get(i) + s.collisionMargin);
+            s.localAabbMin.setc(i, mn.get(i) - s.collisionMargin);
+        }
+        s.bvh = &md->bvh;
+        shapes.push_back(s);
+        meshes.push_back(std::move(md));
+        return (int)shapes.size() - 1;
+    }
+
+    // disp/CollisionWorld.java:102-121 addCollisionObject + bp/DbvtBroadphase.java:173-182 createProxy
+    int addBody(int shape, const Xf& xf, int group, int mask, bool isStatic) {
+        Body b;
+        b.shape = shape;
+        b.xf.set(xf);
+        b.group = (int16_t)group;
+        b.mask = (int16_t)mask;
+        b.isStatic = isStatic;
+        b.uid = (int)bodies.size() + 1;  // ++gid
+        shapeGetAabb(shapes[shape], b.xf, b.effMin, b.effMax);  // no +-threshold at creation
+        b.leafMin = b.effMin; b.leafMax = b.effMax;
+        b.inFixed = false;
+        b.lastSetStep = step;
+        bodies.push_back(b);
+        return b.uid;
+    }
+    void removeBody(int uid) { bodies[uid - 1].alive = false; }
+
+    static bool intersect(const V3& amin, const V3& amax, const V3& bmin, const V3& bmax) {  // bp/DbvtAabbMm.java:209-212
+        return (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
+               (amin.z <= bmax.z) && (amax.z >= bmin.z);
+    }
+
+    // BroadphaseInterface.setAabb
+    void setAabb(Body& b, const V3& mn, const V3& mx) {
+        if (mode == BP_TIGHT) {  // bp/SimpleBroadphase.java:112-116
+            b.effMin = mn; b.effMax = mx;
+            b.lastSetStep = step;
+            return;
+        }
+        // bp/DbvtBroadphase.java:196-228
+        V3 amin = mn, amax = mx;
+        if (b.inFixed) {
+            b.leafMin = amin; b.leafMax = amax;
+            b.inFixed = false;
+        } else {
+            if (intersect(b.leafMin, b.leafMax, amin, amax)) {
+                V3 delta; delta.set(mn).add(mx);
+                delta.scl(0.5f);
+                V3 center; center.set(b.effMin).add(b.effMax); center.scl(0.5f);  // bp/DbvtAabbMm.java:66-70
+                delta.sub(center);
+                delta.scl(predictedFrames);
+                // bp/Dbvt.java:157-169 update(leaf, volume, velocity, margin): volume expanded IN PLACE
+                bool contain = (b.leafMin.x <= amin.x) && (b.leafMin.y <= amin.y) && (b.leafMin.z <= amin.z) &&
+                               (b.leafMax.x >= amax.x) && (b.leafMax.y >= amax.y) && (b.leafMax.z >= amax.z);
+                if (!contain) {
+                    V3 e(dbvtMargin, dbvtMargin, dbvtMargin);
+                    amin.sub(e); amax.add(e);  // Expand
+                    if (delta.x > 0) amax.x += delta.x; else amin.x += delta.x;  // SignedExpand
+                    if (delta.y > 0) amax.y += delta.y; else amin.y += delta.y;
+                    if (delta.z > 0) amax.z += delta.z; else amin.z += delta.z;
+                    b.leafMin = amin; b.leafMax = amax;
+                }
+            } else {
+                b.leafMin = amin; b.leafMax = amax;  // teleporting
+            }
+        }
+        b.effMin = amin; b.effMax = amax;  // proxy.aabb.set(aabb) — aliasing quirk
+        b.lastSetStep = step;
+    }
+
+    // disp/CollisionWorld.java:231-245 / :195-229
+    void updateAabbs() {
+        for (Body& b : bodies) {
+            if (!b.alive || !b.active) continue;
+            V3 mn, mx;
+            shapeGetAabb(shapes[b.shape], b.xf, mn, mx);
+            V3 ct(breakingThreshold, breakingThreshold, breakingThreshold);
+            mn.sub(ct);
+            mx.add(ct);
+            V3 tmp; tmp.set(mx).sub(mn);
+            if (b.isStatic || (tmp.len2() < 1e12f)) {
+                setAabb(b, mn, mx);
+            } else {
+                b.aabbOverflow = true;  // reference sets DISABLE_SIMULATION
+                b.active = false;
+            }
+        }
+    }
+
+    bool filter(const Body& a, const Body& b) const {  // bp/HashedOverlappingPairCache.java:179-188
+        bool collides = (a.group & b.mask) != 0;
+        collides = collides && (b.group & a.mask) != 0;
+        return collides;
+    }
+
+    // BroadphaseInterface.calculateOverlappingPairs: resulting pair set
+    int calculateOverlappingPairs() {
+        if (mode == BP_DBVT) {
+            // bp/DbvtBroadphase.java:96-111: proxies not updated during this step (but updated the step
+            // before) move to the fixed set; eff is kept, leaf volume becomes eff.
+            for (Body& b : bodies) {
+                if (!b.alive) continue;
+                if (!b.inFixed && b.lastSetStep < step) {
+                    b.inFixed = true;
+                    b.leafMin = b.effMin; b.leafMax = b.effMax;
+                }
+            }
+        }
+        pairs.clear();
+        std::vector<int> order;
+        for (size_t i = 0; i < bodies.size(); i++)
+            if (bodies[i].alive) order.push_back((int)i);
+        if (bruteForcePairs) {
+            for (size_t a = 0; a < order.size(); a++)
+                for (size_t c = a + 1; c < order.size(); c++) {
+                    const Body& A = bodies[order[a]];
+                    const Body& B = bodies[order[c]];
+                    if (filter(A, B) && intersect(A.effMin, A.effMax, B.effMin, B.effMax))
+                        pairs.push_back(std::make_pair(A.uid, B.uid));
+                }
+        } else {
+            std::sort(order.begin(), order.end(), [&](int a, int c) {
+                if (bodies[a].effMin.x != bodies[c].effMin.x) return bodies[a].effMin.x < bodies[c].effMin.x;
+                return a < c;
+            });
+            for (size_t a = 0; a < order.size(); a++) {
+                const Body& A = bodies[order[a]];
+                for (size_t c = a + 1; c < order.size(); c++) {
+                    const Body& B = bodies[order[c]];
+                    if (B.effMin.x > A.effMax.x) break;
+                    if (filter(A, B) && intersect(A.effMin, A.effMax, B.effMin, B.effMax))
+                        pairs.push_back(std::make_pair(std::min(A.uid, B.uid), std::max(A.uid, B.uid)));
+                }
+            }
+        }
+        std::sort(pairs.begin(), pairs.end());
+        step++;
+        return (int)pairs.size();
+    }
+
+    // ---- narrowphase ------------------------------------------------------------------
+    void initResult(ManifoldResult& r, const Body& b0, const Body& b1) {  // disp/ManifoldResult.java:70-75
+        r.body0 = b0.uid; r.body1 = b1.uid;
+        r.rootTransA.set(b0.xf); r.rootTransB.set(b1.xf);
+        r.friction0 = b0.friction; r.friction1 = b1.friction;
+        r.restitution0 = b0.restitution; r.restitution1 = b1.restitution;
+        r.partId0 = r.partId1 = r.index0 = r.index1 = 0;
+    }
+
+    void convexConvex(const Shape* s0, const Shape* s1, const Body& b0, const Body& b1, ManifoldResult& res,
+                      bool ownManifold, int tri) {  // disp/ConvexConvexAlgorithm.java:90-139
+        float maxd = s0->getMargin() + s1->getMargin() + res.manifoldPtr->breakingThreshold;
+        maxd *= maxd;
+        GjkOut out;
+        gjkChecks++;
+        gjkGetClosestPoints(s0, s1, b0.xf, b1.xf, maxd, out);
+        deepPenetrationChecks += out.deepPenetrationChecks;
+        RawContact rc;
+        rc.uid0 = res.body0; rc.uid1 = res.body1; rc.tri = tri;
+        rc.hasContact = out.hasContact ? 1 : 0;
+        rc.normal[0] = out.normalOnBInWorld.x; rc.normal[1] = out.normalOnBInWorld.y; rc.normal[2] = out.normalOnBInWorld.z;
+        rc.point[0] = out.pointInWorld.x; rc.point[1] = out.pointInWorld.y; rc.point[2] = out.pointInWorld.z;
+        rc.depth = out.depth; rc.method = out.lastUsedMethod; rc.iters = out.curIter;
+        raw.push_back(rc);
+        if (out.hasContact) res.addContactPoint(out.normalOnBInWorld, out.pointInWorld, out.depth);
+        if (ownManifold) res.refreshContactPoints();
+    }
+
+    void sphereSphere(const Shape* s0, const Shape* s1, const Body& b0, const Body& b1, ManifoldResult& res) {
+        // disp/SphereSphereCollisionAlgorithm.java:73-134
+        V3 diff; diff.set(b0.xf.origin).sub(b1.xf.origin);
+        float len = diff.len();
+        float radius0 = s0->implicitDims.x * s0->localScaling.x;
+        float radius1 = s1->implicitDims.x * s1->localScaling.x;
+        RawContact rc;
+        rc.uid0 = b0.uid; rc.uid1 = b1.uid; rc.tri = -1; rc.method = 10; rc.iters = 0;
+        rc.hasContact = 0; rc.depth = 0;
+        for (int k = 0; k < 3; k++) rc.normal[k] = rc.point[k] = 0;
+        if (len > (radius0 + radius1)) {
+            raw.push_back(rc);
+            res.refreshContactPoints();
+            return;
+        }
+        float dist = len - (radius0 + radius1);
+        V3 normalOnSurfaceB(1, 0, 0);
+        if (len > FLT_EPSILON_) normalOnSurfaceB.set(diff).scl(1.0f / len);
+        V3 tmp, pos1;
+        tmp.set(normalOnSurfaceB).scl(radius1);
+        pos1.set(b1.xf.origin).add(tmp);
+        rc.hasContact = 1;
+        rc.normal[0] = normalOnSurfaceB.x; rc.normal[1] = normalOnSurfaceB.y; rc.normal[2] = normalOnSurfaceB.z;
+        rc.point[0] = pos1.x; rc.point[1] = pos1.y; rc.point[2] = pos1.z;
+        rc.depth = dist;
+        raw.push_back(rc);
+        res.addContactPoint(normalOnSurfaceB, pos1, dist);
+        res.refreshContactPoints();
+    }
+
+    void convexPlane(const Shape* cs, const Shape* ps, const Body& convexObj, const Body& planeObj, ManifoldResult& res) {
+        // disp/ConvexPlaneCollisionAlgorithm.java:75-136
+        V3 planeNormal = ps->planeNormal;
+        float planeConstant = ps->planeConstant;
+        Xf planeInConvex; planeInConvex.set(convexObj.xf);
+        planeInConvex.inverse();
+        planeInConvex.mul(planeObj.xf);
+        Xf convexInPlaneTrans; convexInPlaneTrans.set(planeObj.xf);
+        convexInPlaneTrans.inverse();
+        convexInPlaneTrans.mul(convexObj.xf);
+        V3 tmp; tmp.set(planeNormal).scl(-1.0f);
+        v3mul(tmp, planeInConvex.basis);
+        V3 vtx;
+        localGetSupportingVertex(*cs, tmp, vtx);
+        V3 vtxInPlane = vtx;
+        convexInPlaneTrans.transform(vtxInPlane);
+        float distance = (planeNormal.dot(vtxInPlane) - planeConstant);
+        V3 vtxInPlaneProjected;
+        tmp.set(planeNormal).scl(distance);
+        vtxInPlaneProjected.set(vtxInPlane).sub(tmp);
+        V3 vtxInPlaneWorld = vtxInPlaneProjected;
+        planeObj.xf.transform(vtxInPlaneWorld);
+        bool hasCollision = distance < res.manifoldPtr->breakingThreshold;
+        RawContact rc;
+        rc.uid0 = res.body0; rc.uid1 = res.body1; rc.tri = -1; rc.method = 11; rc.iters = 0;
+        rc.hasContact = hasCollision ? 1 : 0;
+        V3 normalOnSurfaceB = planeNormal;
+        v3mul(normalOnSurfaceB, planeObj.xf.basis);
+        rc.normal[0] = normalOnSurfaceB.x; rc.normal[1] = normalOnSurfaceB.y; rc.normal[2] = normalOnSurfaceB.z;
+        rc.point[0] = vtxInPlaneWorld.x; rc.point[1] = vtxInPlaneWorld.y; rc.point[2] = vtxInPlaneWorld.z;
+        rc.depth = distance;
+        raw.push_back(rc);
+        if (hasCollision) res.addContactPoint(normalOnSurfaceB, vtxInPlaneWorld, distance);
+        if (res.manifoldPtr->cachedPoints != 0) res.refreshContactPoints();
+    }
+
+    void convexConcave(const Shape* cs, const Shape* ms, const Body& convexBody, const Body& triBody, ManifoldResult& res) {
+        // disp/ConvexConcaveCollisionAlgorithm.java:65-93 + disp/ConvexTriangleCallback.java:83-172
+        float collisionMarginTriangle = ms->getMargin();
+        Xf convexInTriangleSpace; convexInTriangleSpace.set(triBody.xf);
+        convexInTriangleSpace.inverse();
+        convexInTriangleSpace.mul(convexBody.xf);
+        V3 aabbMin, aabbMax;
+        shapeGetAabb(*cs, convexInTriangleSpace, aabbMin, aabbMax);
+        V3 extra(collisionMarginTriangle, collisionMarginTriangle, collisionMarginTriangle);
+        aabbMax.add(extra);
+        aabbMin.sub(extra);
+        const MeshShapeData* md = meshes[triBody.shape].get();
+        int visited = 0;
+        md->bvh.reportAabbOverlappingNodex(aabbMin, aabbMax, [&](int part, int triIndex) {
+            // sh/BvhTriangleMeshShape.java:265-278 processNode -> ConvexTriangleCallback.processTriangle
+            Shape tm;
+            tm.type = SH_TRIANGLE;
+            md->mesh.getTriangle(triIndex, tm.tri);
+            tm.collisionMargin = collisionMarginTriangle;
+            res.partId0 = -1; res.index0 = -1; res.partId1 = part; res.index1 = triIndex;  // :164
+            trianglesTested++;
+            // findAlgorithm(convexBody, triBody, sharedManifold): convex-convex with ownManifold=false
+            convexConvexTri(cs, &tm, convexBody, triBody, res, triIndex);
+        }, &visited);
+        bvhNodesVisited += visited;
+        res.refreshContactPoints();
+    }
+    // ConvexConvexAlgorithm.processCollision(convexBody, triBody, ..., resultOut) with shared manifold:
+    // the raw record is tagged with the broadphase pair (resultOut bodies), transforms are convex/tri.
+    void convexConvexTri(const Shape* cs, const Shape* tm, const Body& bc, const Body& bt, ManifoldResult& res, int tri) {
+        float maxd = cs->getMargin() + tm->getMargin() + res.manifoldPtr->breakingThreshold;
+        maxd *= maxd;
+        GjkOut out;
+        gjkChecks++;
+        gjkGetClosestPoints(cs, tm, bc.xf, bt.xf, maxd, out);
+        deepPenetrationChecks += out.deepPenetrationChecks;
+        RawContact rc;
+        rc.uid0 = res.body0; rc.uid1 = res.body1; rc.tri = tri;
+        rc.hasContact = out.hasContact ? 1 : 0;
+        rc.normal[0] = out.normalOnBInWorld.x; rc.normal[1] = out.normalOnBInWorld.y; rc.normal[2] = out.normalOnBInWorld.z;
+        rc.point[0] = out.pointInWorld.x; rc.point[1] = out.pointInWorld.y; rc.point[2] = out.pointInWorld.z;
+        rc.depth = out.depth; rc.method = out.lastUsedMethod; rc.iters = out.curIter;
+        raw.push_back(rc);
+        if (out.hasContact) res.addContactPoint(out.normalOnBInWorld, out.pointInWorld, out.depth);
+    }
+
+    // Dispatcher.dispatchAllCollisionPairs over the current pair set.  Returns number of manifolds.
+    int dispatchAllPairs() {
+        raw.clear();
+        // pairs that left the cache lose their algorithm + manifold (bp/HashedOverlappingPairCache.java:129-174
+        // cleanOverlappingPair -> algorithm.destroy -> releaseManifold)
+        {
+            std::map<std::pair<int, int>, PairState> keep;
+            for (auto& p : pairs) {
+                auto it = pairState.find(p);
+                if (it != pairState.end()) keep.insert(*it);
+            }
+            pairState.swap(keep);
+        }
+        int before = 0;
+        for (auto& p : pairs) {
+            const Body& b0 = bodies[p.first - 1];
+            const Body& b1 = bodies[p.second - 1];
+            // disp/CollisionDispatcher.java:198-223 needsCollision
+            if (!b0.active && !b1.active) continue;
+            const Shape* s0 = &shapes[b0.shape];
+            const Shape* s1 = &shapes[b1.shape];
+            PairState& ps = pairState[p];
+            ManifoldResult res;
+            initResult(res, b0, b1);
+            res.manifoldPtr = &ps.manifold;
+            ps.manifold.breakingThreshold = breakingThreshold;
+            for (int k = 0; k < 4; k++) ps.manifold.pointCache[k].srcSlot = (k < ps.manifold.cachedPoints) ? k : -1;
+            before = res.addedContacts;
+            // disp/DefaultCollisionConfiguration.java:149-213
+            if (s0->type == SH_SPHERE && s1->type == SH_SPHERE) {
+                if (!ps.hasManifold) { ps.hasManifold = true; ps.manifold.body0 = b0.uid; ps.manifold.body1 = b1.uid; }
+                sphereSphere(s0, s1, b0, b1, res);
+            } else if (s0->isConvex() && s1->type == SH_PLANE) {
+                if (!ps.hasManifold) { ps.hasManifold = true; ps.manifold.body0 = b0.uid; ps.manifold.body1 = b1.uid; }
+                convexPlane(s0, s1, b0, b1, res);
+            } else if (s1->isConvex() && s0->type == SH_PLANE) {
+                if (!ps.hasManifold) { ps.hasManifold = true; ps.manifold.body0 = b1.uid; ps.manifold.body1 = b0.uid; }
+                convexPlane(s1, s0, b1, b0, res);
+            } else if (s0->isConvex() && s1->isConvex()) {
+                if (!ps.hasManifold) { ps.hasManifold = true; ps.manifold.body0 = b0.uid; ps.manifold.body1 = b1.uid; }
+                convexConvex(s0, s1, b0, b1, res, true, -1);
+            } else if (s0->isConvex() && s1->type == SH_MESH) {
+                if (!ps.hasManifold) { ps.hasManifold = true; }
+                ps.manifold.body0 = b0.uid; ps.manifold.body1 = b1.uid;  // setBodies(convexBody, triBody)
+                convexConcave(s0, s1, b0, b1, res);
+            } else if (s1->isConvex() && s0->type == SH_MESH) {
+                if (!ps.hasManifold) { ps.hasManifold = true; }
+                ps.manifold.body0 = b1.uid; ps.manifold.body1 = b0.uid;
+                convexConcave(s1, s0, b1, b0, res);
+            } else {
+                // EmptyAlgorithm: no manifold
+            }
+            addedContacts += res.addedContacts - before;
+        }
+        int n = 0;
+        for (auto& kv : pairState)
+            if (kv.second.hasManifold) n++;
+        return n;
+    }
+};
+
+}  // namespace orc
