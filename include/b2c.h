@@ -1,0 +1,200 @@
+/* b2c.h — C ABI of the B200 collision path (broadphase overlap pairs + narrowphase contacts).
+ *
+ * Drop-in boundary for libgdx-jbullet's per-step collision phase
+ *   CollisionWorld.performDiscreteCollisionDetection
+ *   (reference: src/com/bulletphysics/collision/dispatch/CollisionWorld.java:123-151)
+ * Each entry point below names the reference interface it replaces ("bp/" =
+ * collision/broadphase/, "disp/" = collision/dispatch/, "np/" = collision/narrowphase/,
+ * "sh/" = collision/shapes/).  A Java host binds these with Panama FFM (or a JNI shim);
+ * see INTEGRATION.md.  Plain pointers and sizes only; the caller owns every host buffer and
+ * the library borrows it for the duration of the call.  All functions return 0 on success or
+ * a negative b2c_status; no exception crosses this boundary.  A ctx is thread-confined (one
+ * ctx per world per thread, like the reference's thread-local pools) and owns one CUDA stream.
+ *
+ * There is no CPU fallback: b2c_create fails with B2C_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef B2C_H
+#define B2C_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2c_ctx b2c_ctx;
+
+typedef enum {
+    B2C_OK = 0,
+    B2C_ERR_BAD_ARG = -1,
+    B2C_ERR_BAD_HANDLE = -2,
+    B2C_ERR_CAPACITY = -3, /* a fixed-capacity buffer overflowed; see b2c_last_error_string */
+    B2C_ERR_CUDA = -4,
+    B2C_ERR_STATE = -5
+} b2c_status;
+
+/* Which reference broadphase defines the exact pair set. */
+typedef enum {
+    B2C_BP_TIGHT = 0, /* bp/SimpleBroadphase.java:81-110: overlaps of the AABBs last passed to setAabb */
+    B2C_BP_DBVT = 1   /* bp/DbvtBroadphase.java:89-228: overlaps of the per-proxy effective (possibly fattened) AABB */
+} b2c_broadphase_mode;
+
+/* Shape kinds (subset of bp/BroadphaseNativeType.java on the hot path). */
+typedef enum { B2C_SHAPE_BOX = 0, B2C_SHAPE_SPHERE = 1, B2C_SHAPE_HULL = 2, B2C_SHAPE_PLANE = 4, B2C_SHAPE_MESH = 5 } b2c_shape_kind;
+
+typedef struct {
+    int32_t device;                    /* CUDA device ordinal */
+    int32_t broadphase_mode;           /* b2c_broadphase_mode */
+    int32_t max_bodies;                /* proxy capacity (uids 1..max_bodies) */
+    int32_t max_pairs;                 /* overlapping-pair capacity */
+    int32_t max_shapes;                /* shape table capacity */
+    int32_t max_hull_points;           /* total hull vertices over all hull shapes */
+    int32_t max_mesh_items;            /* (pair, triangle) work items per step for convex-vs-mesh */
+    int32_t num_worlds;                /* >1: batched independent worlds (world id per body) */
+    float contact_breaking_threshold;  /* BulletGlobals.java:63, default 0.02 */
+    float dbvt_margin;                 /* bp/DbvtBroadphase.java:35 DBVT_BP_MARGIN, default 0.05 */
+    float dbvt_predicted_frames;       /* bp/DbvtBroadphase.java:73, default 2 */
+    int32_t reserved[5];
+} b2c_config;
+
+/* Fills cfg with the reference's defaults (thresholds above; capacities for ~128k bodies). */
+void b2c_default_config(b2c_config* cfg);
+
+int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out);
+void b2c_destroy(b2c_ctx* ctx);
+const char* b2c_last_error_string(const b2c_ctx* ctx);
+/* Library-level check usable without a ctx: number of visible sm_100 devices (0 on a CPU box). */
+int32_t b2c_device_count(void);
+
+/* ---- shapes: replace the shape constructors + per-shape parameters the kernels read -------- */
+/* sh/BoxShape.java:46-50  new BoxShape(halfExtents); margin = CONVEX_DISTANCE_MARGIN unless >= 0 given */
+int32_t b2c_shape_register_box(b2c_ctx*, const float half_extents[3], float margin_or_neg, int32_t* shape_out);
+/* sh/SphereShape.java:38-41 */
+int32_t b2c_shape_register_sphere(b2c_ctx*, float radius, int32_t* shape_out);
+/* sh/ConvexHullShape.java:45-53 (points xyz, tightly packed); localScaling (1,1,1) */
+int32_t b2c_shape_register_hull(b2c_ctx*, const float* points_xyz, int32_t num_points, float margin_or_neg, int32_t* shape_out);
+/* sh/StaticPlaneShape.java:45-48 */
+int32_t b2c_shape_register_plane(b2c_ctx*, const float normal[3], float constant, int32_t* shape_out);
+/* sh/BvhTriangleMeshShape.java:68-90 with useQuantizedAabbCompression=true over one
+ * sh/IndexedMesh.java part: vertices with a byte stride, 32-bit indices with a byte stride per
+ * triangle (sh/TriangleIndexVertexArray.java:51-94).  The data is copied; the BVH is built on the host
+ * exactly as sh/OptimizedBvh.java:283-342 and uploaded. */
+int32_t b2c_shape_register_mesh(b2c_ctx*, const void* vertex_base, int32_t num_vertices, int32_t vertex_stride,
+                                const void* index_base, int32_t num_triangles, int32_t index_stride,
+                                const float scaling[3], int32_t* shape_out);
+/* Debug/inspection: copy the quantized BVH (16-byte nodes, sh/QuantizedBvhNodes.java:34-48) */
+int32_t b2c_mesh_get_bvh(b2c_ctx*, int32_t shape, void* nodes16_out, int32_t cap_nodes, int32_t* num_nodes, float quant9_out[9]);
+
+/* ---- proxies: bp/BroadphaseInterface.java:35-39 ------------------------------------------- */
+/* createProxy + CollisionWorld.addCollisionObject (disp/CollisionWorld.java:102-121): the initial
+ * AABB is the shape's AABB under `transform12` (9 row-major basis floats + origin), uid = ++gid
+ * (bp/DbvtBroadphase.java:179).  flags: bit0 = static object.  world = world id for batched worlds. */
+int32_t b2c_proxy_create(b2c_ctx*, int32_t shape, const float transform12[12], int16_t group, int16_t mask,
+                         int32_t flags, int32_t world, int32_t* uid_out);
+/* The same for `n` proxies in one call (a host shim batches World.addRigidBody loops): shapes[n],
+ * transforms as 12 SoA planes of n floats, groups[n], masks[n], flags[n], worlds[n] (NULL = world 0).
+ * uids are assigned consecutively; the first one is returned. */
+int32_t b2c_proxy_create_batch(b2c_ctx*, int32_t n, const int32_t* shapes, const float* planes12, const int16_t* groups,
+                               const int16_t* masks, const int32_t* flags, const int32_t* worlds, int32_t* first_uid_out);
+/* destroyProxy (bp/BroadphaseInterface.java:37): pairs containing it disappear at the next calculate */
+int32_t b2c_proxy_destroy(b2c_ctx*, int32_t uid);
+/* CollisionObject friction / restitution (disp/CollisionObject.java:95,71) used by ManifoldResult */
+int32_t b2c_proxy_set_material(b2c_ctx*, int32_t uid, float friction, float restitution);
+
+/* ---- per-step inputs ---------------------------------------------------------------------- */
+/* World transforms as 12 SoA planes of `n` floats each (m00 m01 m02 m10 ... m22 ox oy oz), plane
+ * stride = n floats; uids NULL means bodies 1..n.  One H2D copy. */
+int32_t b2c_set_transforms(b2c_ctx*, int32_t n, const int32_t* uids, const float* planes12);
+/* CollisionObject.isActive() per body (disp/CollisionObject.java:178-180); 1 = active */
+int32_t b2c_set_activation(b2c_ctx*, int32_t n, const int32_t* uids, const uint8_t* active);
+/* BroadphaseInterface.setAabb (bp/BroadphaseInterface.java:39) in bulk, for hosts that compute
+ * AABBs themselves: minmax6 = 6 SoA planes of n floats (minx miny minz maxx maxy maxz). */
+int32_t b2c_set_aabbs(b2c_ctx*, int32_t n, const int32_t* uids, const float* minmax6);
+
+/* ---- the path ----------------------------------------------------------------------------- */
+/* CollisionWorld.updateAabbs (disp/CollisionWorld.java:231-245): shape AABBs on the device from the
+ * uploaded transforms, +-threshold, overflow guard, then the broadphase's setAabb state machine. */
+int32_t b2c_update_aabbs(b2c_ctx*);
+/* BroadphaseInterface.calculateOverlappingPairs (bp/BroadphaseInterface.java:42) */
+int32_t b2c_calculate_overlapping_pairs(b2c_ctx*, int32_t* num_pairs_out);
+/* OverlappingPairCache.getOverlappingPairArray (bp/OverlappingPairCache.java:36): (uid0<uid1) pairs,
+ * sorted lexicographically; 2 int32 per pair. */
+int32_t b2c_get_pairs(b2c_ctx*, int32_t* pairs_out, int32_t cap_pairs, int32_t* num_pairs_out);
+/* Dispatcher.dispatchAllCollisionPairs (bp/Dispatcher.java:58) with the default near callback and
+ * the default collision configuration's algorithm table. */
+int32_t b2c_dispatch_all_pairs(b2c_ctx*, int32_t* num_manifolds_out, int32_t* num_contacts_added_out);
+/* The whole of performDiscreteCollisionDetection in one call: transforms in (as b2c_set_transforms,
+ * planes12 may be NULL to reuse the resident ones), counts out. */
+int32_t b2c_step(b2c_ctx*, int32_t n, const float* planes12, int32_t* num_pairs_out, int32_t* num_manifolds_out,
+                 int32_t* num_contacts_added_out);
+
+/* ---- results ------------------------------------------------------------------------------ */
+typedef struct {
+    float local_a[3], local_b[3];     /* np/ManifoldPoint.java:38-39 */
+    float world_a[3], world_b[3];     /* positionWorldOnA / positionWorldOnB */
+    float normal_on_b[3];             /* normalWorldOnB */
+    float distance;                   /* distance1 */
+    float combined_friction, combined_restitution;
+    int32_t life_time;
+    int32_t src_slot;                 /* slot of this manifold at the start of the step this point continues; -1 = new */
+    int32_t part_id1, index1;         /* triangle ids for mesh pairs (partId0/index0 are -1 there), else 0 */
+    int32_t pad[2];
+} b2c_manifold_point; /* 96 bytes */
+
+typedef struct {
+    int32_t pair_uid0, pair_uid1;     /* the broadphase pair (uid0 < uid1) */
+    int32_t body0, body1;             /* PersistentManifold.getBody0/1 (np/PersistentManifold.java:161-167) */
+    int32_t num_contacts;             /* getNumContacts */
+    int32_t algorithm;                /* 1 sphere-sphere, 2 convex-plane, 3 convex-convex, 4 convex-concave */
+    int32_t pad[2];
+    b2c_manifold_point points[4];
+} b2c_manifold; /* 416 bytes */
+
+/* Dispatcher.getNumManifolds / getManifoldByIndexInternal (bp/Dispatcher.java:62-64): manifolds in pair
+ * order.  only_touching != 0 skips manifolds with zero contacts. */
+int32_t b2c_get_manifolds(b2c_ctx*, b2c_manifold* out, int32_t cap, int32_t only_touching, int32_t* num_out);
+
+/* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
+ * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
+typedef struct {
+    int32_t uid0, uid1, tri, has_contact;
+    float normal[3], point[3], depth;
+    int32_t method; /* GjkPairDetector.lastUsedMethod (np/GjkPairDetector.java:54); 10 sphere-sphere; 11 convex-plane */
+    int32_t iters;
+    int32_t pad[1];
+} b2c_raw_contact; /* 56 bytes */
+int32_t b2c_get_raw_contacts(b2c_ctx*, b2c_raw_contact* out, int32_t cap, int32_t* num_out);
+
+/* Effective broadphase AABBs (DbvtProxy.aabb / SimpleBroadphaseProxy min,max) for bodies 1..n: n x 6 floats */
+int32_t b2c_get_aabbs(b2c_ctx*, float* minmax_out, int32_t n);
+/* BroadphaseInterface.getBroadphaseAabb (bp/BroadphaseInterface.java:48) */
+int32_t b2c_get_broadphase_aabb(b2c_ctx*, float min_out[3], float max_out[3]);
+
+/* Counters of the last step (mirrors BulletStats.java:41-56 and adds device timings). */
+typedef struct {
+    int32_t num_pairs, num_manifolds, num_contacts_added;
+    int32_t gjk_checks, deep_penetration_checks; /* BulletStats.gNumGjkChecks / gNumDeepPenetrationChecks */
+    int32_t epa_failed, mesh_items, large_proxies;
+    int32_t kernel_launches;          /* kernels launched by the last b2c_step */
+    int32_t grid_rows;
+    float ms_aabb, ms_broadphase, ms_narrowphase, ms_total; /* CUDA-event times of the last b2c_step */
+    int32_t pad[2];
+} b2c_stats;
+int32_t b2c_get_stats(b2c_ctx*, b2c_stats* out);
+
+/* ---- device-resident stepping for measurement and host-free pipelines ---------------------- */
+/* The ctx's CUDA stream (cudaStream_t) so a caller can time with CUDA events on the right stream. */
+void* b2c_stream(b2c_ctx*);
+/* Device pointer to the 12 transform planes (plane stride = max_bodies floats): a caller with its own
+ * device-side integrator writes here and calls b2c_step_device. */
+float* b2c_device_transforms(b2c_ctx*);
+/* Tell the ctx that planes for bodies 1..n were written on the device through b2c_device_transforms. */
+int32_t b2c_transforms_written(b2c_ctx*, int32_t n);
+/* Enqueue one full collision step on the ctx stream using the resident transforms; does not
+ * synchronise and does not copy results to the host.  Counters are read later with b2c_sync_counts. */
+int32_t b2c_step_device(b2c_ctx*);
+int32_t b2c_sync_counts(b2c_ctx*, int32_t* num_pairs_out, int32_t* num_manifolds_out, int32_t* num_contacts_added_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2C_H */

@@ -1,0 +1,1056 @@
+// b2c_api.cu — the C ABI (include/b2c.h) over the CUDA collision path.  Host orchestration only: every
+// per-step computation is a kernel in broadphase.cuh / narrowphase.cuh / radix_sort.cuh; there is no CPU
+// fallback (b2c_create fails without an sm_100 device).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2c.h"
+#include "broadphase.cuh"
+#include "bvh_build.h"
+#include "common.cuh"
+#include "narrowphase.cuh"
+#include "radix_sort.cuh"
+
+using namespace b2c;
+
+namespace {
+
+constexpr int EPA_GRID = 148, EPA_BLOCK = 64;
+
+struct HostMesh {
+    int4* nodes = nullptr;
+    float* verts = nullptr;
+    int* idx = nullptr;
+    HostBvh bvh;
+};
+
+}  // namespace
+
+struct b2c_ctx {
+    b2c_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // shapes
+    std::vector<ShapeDev> hShapes;
+    ShapeDev* dShapes = nullptr;
+    float4* dHullPts = nullptr;
+    int hullPtsUsed = 0;
+    std::vector<HostMesh> meshes;
+    std::vector<MeshDev> hMeshes;
+    MeshDev* dMeshes = nullptr;
+    bool shapesDirty = false;
+    bool hasPlane = false, hasMesh = false;
+
+    // bodies
+    int nBodies = 0;  // slots in use (uids 1..nBodies)
+    BodyArrays B{};
+    std::vector<uint8_t> hFlags;
+    std::vector<int> hShapeOf;
+    float* dStaging = nullptr;   // 12 planes x max_bodies
+    float* hStagingPinned = nullptr;
+    int stagingCount = 0;        // >0: planes uploaded for bodies 1..stagingCount, to be repacked by k_aabb
+    float* dExtAabb = nullptr;   // 6 planes x max_bodies (b2c_set_aabbs)
+    uint8_t* dExtMask = nullptr;
+    bool extPending = false;
+    bool aabbPending = false;
+    int step = 0;
+
+    // broadphase
+    uint64_t* dKeys[2] = {nullptr, nullptr};
+    uint32_t* dVals[2] = {nullptr, nullptr};
+    uint32_t* dSide = nullptr;        // [2]: body sort side, pair sort side
+    float4* dSmin = nullptr;
+    float4* dSmax = nullptr;
+    uint32_t* dSrow = nullptr;
+    uint32_t* dRowStart = nullptr;
+    int maxRows = 0;
+    GridParams* dGrid = nullptr;
+    StepCounters* dCtr = nullptr;
+    StepCounters* hCtrPinned = nullptr;
+    uint64_t* dPairKeys[2] = {nullptr, nullptr};
+    RadixSorter sortBodies, sortPairs;
+    int uidBits = 1;
+
+    // pairs + manifolds (ping-pong across steps)
+    int2* dPairs = nullptr;
+    uint64_t* dSortedKeys[2] = {nullptr, nullptr};
+    uint32_t* dNumPairs[2] = {nullptr, nullptr};
+    b2c_manifold* dManifolds[2] = {nullptr, nullptr};
+    int cur = 0;  // index of this step's pair keys / manifolds
+    bool pairsValid = false;
+
+    // narrowphase
+    b2c_raw_contact* dRaw = nullptr;
+    uint8_t* dBinOf = nullptr;
+    uint32_t* dItems = nullptr;
+    uint32_t* dBinStart = nullptr;
+    uint32_t* dBinCursor = nullptr;
+    EpaItem* dEpaItems = nullptr;
+    uint32_t maxEpa = 0;
+    EpaScratch* dEpaScratch = nullptr;
+    uint32_t* dMeshPair = nullptr;
+    int* dMeshTri = nullptr;
+    b2c_raw_contact* dRawMesh = nullptr;
+    uint32_t* dMeshStart = nullptr;
+    uint32_t* dMeshCount = nullptr;
+
+    // stats
+    b2c_stats stats{};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int launches = 0;
+    int32_t lastPairs = 0, lastManifolds = 0, lastContacts = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            return B2C_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+int bitsFor(uint32_t v) {
+    int b = 1;
+    while ((1ull << b) <= v) b++;
+    return b;
+}
+
+unsigned gridFor(uint32_t n, int block, unsigned cap = 148 * 8) {
+    unsigned g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return g > cap ? cap : g;
+}
+
+int32_t uploadShapes(b2c_ctx* ctx) {
+    if (!ctx->shapesDirty) return B2C_OK;
+    if (!ctx->hShapes.empty())
+        CK(cudaMemcpyAsync(ctx->dShapes, ctx->hShapes.data(), ctx->hShapes.size() * sizeof(ShapeDev), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    if (!ctx->hMeshes.empty())
+        CK(cudaMemcpyAsync(ctx->dMeshes, ctx->hMeshes.data(), ctx->hMeshes.size() * sizeof(MeshDev), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->shapesDirty = false;
+    return B2C_OK;
+}
+
+// host copy of the shape AABB for createProxy (disp/CollisionWorld.java:113-119): computed on the device
+// by a one-thread launch of the same code path, so the bits are identical to the per-step kernel.
+__global__ void k_initial_aabb(BodyArrays B, const ShapeDev* shapes, int i) {
+    Xf t;
+    float4 r0 = B.xf4[3 * (size_t)i], r1 = B.xf4[3 * (size_t)i + 1], r2 = B.xf4[3 * (size_t)i + 2];
+    t.m[0][0] = r0.x; t.m[0][1] = r0.y; t.m[0][2] = r0.z;
+    t.m[1][0] = r1.x; t.m[1][1] = r1.y; t.m[1][2] = r1.z;
+    t.m[2][0] = r2.x; t.m[2][1] = r2.y; t.m[2][2] = r2.z;
+    t.o = mk3(r0.w, r1.w, r2.w);
+    f3 mn, mx;
+    shapeAabb(shapes[B.shape[i]], t, mn, mx);
+    B.effMin[i] = make_float4(mn.x, mn.y, mn.z, 0.f);
+    B.effMax[i] = make_float4(mx.x, mx.y, mx.z, 0.f);
+    B.leafMin[i] = B.effMin[i];
+    B.leafMax[i] = B.effMax[i];
+}
+
+// batched variant used when many proxies are created before the first step
+__global__ void k_initial_aabb_range(BodyArrays B, const ShapeDev* shapes, int first, int count) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    int i = first + k;
+    Xf t;
+    float4 r0 = B.xf4[3 * (size_t)i], r1 = B.xf4[3 * (size_t)i + 1], r2 = B.xf4[3 * (size_t)i + 2];
+    t.m[0][0] = r0.x; t.m[0][1] = r0.y; t.m[0][2] = r0.z;
+    t.m[1][0] = r1.x; t.m[1][1] = r1.y; t.m[1][2] = r1.z;
+    t.m[2][0] = r2.x; t.m[2][1] = r2.y; t.m[2][2] = r2.z;
+    t.o = mk3(r0.w, r1.w, r2.w);
+    f3 mn, mx;
+    shapeAabb(shapes[B.shape[i]], t, mn, mx);
+    B.effMin[i] = make_float4(mn.x, mn.y, mn.z, 0.f);
+    B.effMax[i] = make_float4(mx.x, mx.y, mx.z, 0.f);
+    B.leafMin[i] = B.effMin[i];
+    B.leafMax[i] = B.effMax[i];
+}
+
+__global__ void k_scatter_xf(BodyArrays B, int n, const int* __restrict__ uids, const float* __restrict__ planes) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int i = uids[k] - 1;
+    const float* p = planes + k;
+    size_t s = (size_t)n;
+    B.xf4[3 * (size_t)i] = make_float4(p[0], p[s], p[2 * s], p[9 * s]);
+    B.xf4[3 * (size_t)i + 1] = make_float4(p[3 * s], p[4 * s], p[5 * s], p[10 * s]);
+    B.xf4[3 * (size_t)i + 2] = make_float4(p[6 * s], p[7 * s], p[8 * s], p[11 * s]);
+}
+
+__global__ void k_get_aabbs(BodyArrays B, int n, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = B.effMin[i], b = B.effMax[i];
+    out[6 * (size_t)i + 0] = a.x; out[6 * (size_t)i + 1] = a.y; out[6 * (size_t)i + 2] = a.z;
+    out[6 * (size_t)i + 3] = b.x; out[6 * (size_t)i + 4] = b.y; out[6 * (size_t)i + 5] = b.z;
+}
+
+__global__ void k_clear_np_counters(StepCounters* c) {
+    if (threadIdx.x == 0) {
+        c->contactsAdded = c->gjkChecks = c->deepChecks = c->epaFailed = 0;
+        c->meshItems = c->meshOverflow = c->numManifolds = c->epaCount = 0;
+    }
+    if (threadIdx.x < 16) c->binCount[threadIdx.x] = 0;
+}
+
+// Flush pending AABB work (update from transforms and/or host-supplied AABBs) with one k_aabb launch.
+// forPairs: this launch opens a pair-finding step, so the counters are cleared first and the extent
+// reduction it performs feeds the grid.
+int32_t runAabbKernel(b2c_ctx* ctx, bool forPairs) {
+    int n = ctx->nBodies;
+    if (forPairs) CK(cudaMemsetAsync(ctx->dCtr, 0, sizeof(StepCounters), ctx->stream));
+    if (n == 0) return B2C_OK;
+    int32_t rc = uploadShapes(ctx);
+    if (rc) return rc;
+    const float* staging = ctx->stagingCount > 0 ? ctx->dStaging : nullptr;
+    k_aabb<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->B, ctx->dShapes, n, staging, ctx->cfg.max_bodies, ctx->stagingCount, ctx->extPending ? ctx->dExtAabb : nullptr,
+        ctx->dExtMask, ctx->cfg.max_bodies, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.contact_breaking_threshold,
+        ctx->cfg.dbvt_margin, ctx->cfg.dbvt_predicted_frames, ctx->aabbPending ? 1 : 0, ctx->dCtr);
+    ctx->launches++;
+    ctx->stagingCount = 0;
+    if (ctx->extPending) {
+        CK(cudaMemsetAsync(ctx->dExtMask, 0, (size_t)ctx->cfg.max_bodies, ctx->stream));
+        ctx->extPending = false;
+    }
+    ctx->aabbPending = false;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int32_t enqueueBroadphase(b2c_ctx* ctx) {
+    int n = ctx->nBodies;
+    int32_t rc = runAabbKernel(ctx, true);
+    if (rc) return rc;
+    ctx->cur ^= 1;
+    const int cur = ctx->cur;
+    cudaStream_t s = ctx->stream;
+    if (n == 0) {
+        CK(cudaMemsetAsync(ctx->dNumPairs[cur], 0, sizeof(uint32_t), s));
+        ctx->step++;
+        ctx->pairsValid = true;
+        return B2C_OK;
+    }
+    unsigned nb = (n + 255) / 256;
+    k_bounds<<<nb, 256, 0, s>>>(ctx->B, n, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.num_worlds, ctx->maxRows, ctx->dCtr,
+                                ctx->dGrid);
+    k_keys<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0]);
+    int rowBits = bitsFor((uint32_t)ctx->maxRows + 2u);
+    ctx->sortBodies.launches = 0;
+    ctx->sortBodies.sort<uint64_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nullptr, (uint32_t)n,
+                                         32 + rowBits, ctx->dSide, s);
+    k_gather<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->dSide, ctx->dGrid,
+                                ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart);
+    dim3 sg(nb, 9);
+    k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys[0],
+                               (uint32_t)ctx->cfg.max_pairs, ctx->dCtr);
+    dim3 lg(gridFor((uint32_t)n, 256, 64), 16);
+    k_large<<<lg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
+                               ctx->uidBits, ctx->dPairKeys[0], (uint32_t)ctx->cfg.max_pairs, ctx->dCtr);
+    ctx->sortPairs.launches = 0;
+    ctx->sortPairs.sort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr, &ctx->dCtr->pairCount, 0,
+                                         2 * ctx->uidBits, ctx->dSide + 1, s);
+    k_pairs_unpack<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dSide + 1,
+                                                                              ctx->dCtr, (uint32_t)ctx->cfg.max_pairs, ctx->uidBits,
+                                                                              ctx->dPairs, ctx->dSortedKeys[cur], ctx->dNumPairs[cur]);
+    // manifolds follow their pair into the new list (done here so a step without dispatch keeps them too)
+    k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
+                                                                      ctx->dSortedKeys[cur ^ 1], ctx->dNumPairs[cur ^ 1],
+                                                                      ctx->dManifolds[cur ^ 1], ctx->dManifolds[cur], ctx->uidBits);
+    ctx->launches += 7 + ctx->sortBodies.launches + ctx->sortPairs.launches;
+    CK(cudaGetLastError());
+    ctx->step++;
+    ctx->pairsValid = true;
+    return B2C_OK;
+}
+
+NpArgs makeNpArgs(b2c_ctx* ctx) {
+    NpArgs a;
+    a.pairs = ctx->dPairs;
+    a.numPairs = ctx->dNumPairs[ctx->cur];
+    a.xf4 = ctx->B.xf4;
+    a.shape = ctx->B.shape;
+    a.flags = ctx->B.flags;
+    a.material = ctx->B.material;
+    a.shapes = ctx->dShapes;
+    a.hullPts = ctx->dHullPts;
+    a.meshes = ctx->dMeshes;
+    a.manifolds = ctx->dManifolds[ctx->cur];
+    a.raw = ctx->dRaw;
+    a.binOf = ctx->dBinOf;
+    a.items = ctx->dItems;
+    a.binStart = ctx->dBinStart;
+    a.binCursor = ctx->dBinCursor;
+    a.ctr = ctx->dCtr;
+    a.threshold = ctx->cfg.contact_breaking_threshold;
+    a.maxPairs = (uint32_t)ctx->cfg.max_pairs;
+    return a;
+}
+
+int32_t enqueueNarrowphase(b2c_ctx* ctx) {
+    if (!ctx->pairsValid) {
+        ctx->err = "dispatch_all_pairs before calculate_overlapping_pairs";
+        return B2C_ERR_STATE;
+    }
+    cudaStream_t s = ctx->stream;
+    NpArgs a = makeNpArgs(ctx);
+    GjkArgs g;
+    g.epaItems = ctx->dEpaItems;
+    g.maxEpa = ctx->maxEpa;
+    g.scratch = ctx->dEpaScratch;
+    g.meshPair = ctx->dMeshPair;
+    g.meshTri = ctx->dMeshTri;
+    g.rawMesh = ctx->dRawMesh;
+    g.meshStart = ctx->dMeshStart;
+    g.meshCount = ctx->dMeshCount;
+    g.maxMeshItems = (uint32_t)ctx->cfg.max_mesh_items;
+    const unsigned pg = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
+    k_clear_np_counters<<<1, 32, 0, s>>>(ctx->dCtr);
+    k_classify<<<pg, 256, 0, s>>>(a);
+    k_bin_offsets<<<1, 32, 0, s>>>(a);
+    k_bin_scatter<<<pg, 256, 0, s>>>(a);
+    k_sphere_sphere<<<148 * 4, 256, 0, s>>>(a);
+    ctx->launches += 5;
+    if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, s>>>(a); ctx->launches++; }
+    k_gjk<<<148 * 8, 128, 0, s>>>(a, g);
+    ctx->launches++;
+    if (ctx->hasMesh) {
+        k_mesh_query<<<148 * 4, 128, 0, s>>>(a, g);
+        k_gjk_tri<<<148 * 8, 128, 0, s>>>(a, g);
+        ctx->launches += 2;
+    }
+    k_epa<<<EPA_GRID, EPA_BLOCK, 0, s>>>(a, g);
+    ctx->launches++;
+    if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
+    k_count_manifolds<<<pg, 256, 0, s>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int32_t readCounters(b2c_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->hCtrPinned, ctx->dCtr, sizeof(StepCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const StepCounters& c = *ctx->hCtrPinned;
+    uint32_t np = c.pairCount;
+    ctx->stats.num_pairs = (int32_t)(np < (uint32_t)ctx->cfg.max_pairs ? np : (uint32_t)ctx->cfg.max_pairs);
+    ctx->stats.num_manifolds = (int32_t)c.numManifolds;
+    ctx->stats.num_contacts_added = (int32_t)c.contactsAdded;
+    ctx->stats.gjk_checks = (int32_t)c.gjkChecks;
+    ctx->stats.deep_penetration_checks = (int32_t)c.deepChecks;
+    ctx->stats.epa_failed = (int32_t)(c.epaFailed & 0x3fffffffu);
+    ctx->stats.mesh_items = (int32_t)c.meshItems;
+    ctx->stats.large_proxies = (int32_t)c.largeCount;
+    ctx->lastPairs = ctx->stats.num_pairs;
+    ctx->lastManifolds = ctx->stats.num_manifolds;
+    ctx->lastContacts = ctx->stats.num_contacts_added;
+    if (c.pairOverflow || np > (uint32_t)ctx->cfg.max_pairs) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "overlapping-pair capacity exceeded: need %u, max_pairs %d", np, ctx->cfg.max_pairs);
+        ctx->err = buf;
+        return B2C_ERR_CAPACITY;
+    }
+    if (c.meshOverflow) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "mesh work-item capacity exceeded: need %u, max_mesh_items %d", c.meshItems, ctx->cfg.max_mesh_items);
+        ctx->err = buf;
+        return B2C_ERR_CAPACITY;
+    }
+    if (c.epaFailed >= 0x40000000u) {
+        ctx->err = "penetration-solver work list capacity exceeded";
+        return B2C_ERR_CAPACITY;
+    }
+    return B2C_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b2c_default_config(b2c_config* cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->broadphase_mode = B2C_BP_DBVT;
+    cfg->max_bodies = 131072;
+    cfg->max_pairs = 2 * 1024 * 1024;
+    cfg->max_shapes = 4096;
+    cfg->max_hull_points = 1 << 20;
+    cfg->max_mesh_items = 1 << 20;
+    cfg->num_worlds = 1;
+    cfg->contact_breaking_threshold = 0.02f;
+    cfg->dbvt_margin = 0.05f;
+    cfg->dbvt_predicted_frames = 2.0f;
+}
+
+int32_t b2c_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
+    if (!cfg || !out) return B2C_ERR_BAD_ARG;
+    *out = nullptr;
+    if (cfg->max_bodies < 1 || cfg->max_pairs < 1 || cfg->max_shapes < 1 || cfg->num_worlds < 1) return B2C_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return B2C_ERR_CUDA;  // no device: there is deliberately no CPU path
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) return B2C_ERR_CUDA;
+    b2c_ctx* ctx = new b2c_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    auto fail = [&](int32_t rc) { b2c_destroy(ctx); return rc; };
+#define CKC(call)                                  \
+    do {                                           \
+        if ((call) != cudaSuccess) {               \
+            cudaGetLastError();                    \
+            return fail(B2C_ERR_CUDA);             \
+        }                                          \
+    } while (0)
+    CKC(cudaSetDevice(cfg->device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    const size_t N = (size_t)cfg->max_bodies, P = (size_t)cfg->max_pairs;
+    CKC(dalloc(&ctx->dShapes, (size_t)cfg->max_shapes));
+    CKC(dalloc(&ctx->dHullPts, (size_t)(cfg->max_hull_points > 0 ? cfg->max_hull_points : 1)));
+    CKC(dalloc(&ctx->dMeshes, (size_t)cfg->max_shapes));
+    CKC(dalloc(&ctx->B.xf4, 3 * N));
+    CKC(dalloc(&ctx->B.shape, N));
+    CKC(dalloc(&ctx->B.filt, N));
+    CKC(dalloc(&ctx->B.flags, N));
+    CKC(dalloc(&ctx->B.world, N));
+    CKC(dalloc(&ctx->B.effMin, N));
+    CKC(dalloc(&ctx->B.effMax, N));
+    CKC(dalloc(&ctx->B.leafMin, N));
+    CKC(dalloc(&ctx->B.leafMax, N));
+    CKC(dalloc(&ctx->B.lastSet, N));
+    CKC(dalloc(&ctx->B.material, N));
+    CKC(dalloc(&ctx->dStaging, 12 * N));
+    CKC(cudaMallocHost((void**)&ctx->hStagingPinned, 12 * N * sizeof(float)));
+    CKC(dalloc(&ctx->dExtAabb, 6 * N));
+    CKC(dalloc(&ctx->dExtMask, N));
+    for (int i = 0; i < 2; i++) {
+        CKC(dalloc(&ctx->dKeys[i], N));
+        CKC(dalloc(&ctx->dVals[i], N));
+        CKC(dalloc(&ctx->dPairKeys[i], P));
+        CKC(dalloc(&ctx->dSortedKeys[i], P));
+        CKC(dalloc(&ctx->dNumPairs[i], (size_t)1));
+        CKC(dalloc(&ctx->dManifolds[i], P));
+    }
+    CKC(dalloc(&ctx->dSide, (size_t)2));
+    CKC(dalloc(&ctx->dSmin, N));
+    CKC(dalloc(&ctx->dSmax, N));
+    CKC(dalloc(&ctx->dSrow, N));
+    ctx->maxRows = (int)(2 * N + 64 > (size_t)(64 * cfg->num_worlds) ? 2 * N + 64 : (size_t)(64 * cfg->num_worlds));
+    CKC(dalloc(&ctx->dRowStart, (size_t)ctx->maxRows + 8));
+    CKC(dalloc(&ctx->dGrid, (size_t)1));
+    CKC(dalloc(&ctx->dCtr, (size_t)1));
+    CKC(cudaMallocHost((void**)&ctx->hCtrPinned, sizeof(StepCounters)));
+    CKC(ctx->sortBodies.init((uint32_t)N));
+    CKC(ctx->sortPairs.init((uint32_t)P));
+    ctx->uidBits = bitsFor((uint32_t)N + 1u);
+    CKC(dalloc(&ctx->dPairs, P));
+    CKC(dalloc(&ctx->dRaw, P));
+    CKC(dalloc(&ctx->dBinOf, P));
+    CKC(dalloc(&ctx->dItems, P));
+    CKC(dalloc(&ctx->dBinStart, (size_t)32));
+    CKC(dalloc(&ctx->dBinCursor, (size_t)32));
+    ctx->maxEpa = (uint32_t)(P / 4 + 1024);
+    CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
+    CKC(dalloc(&ctx->dEpaScratch, (size_t)EPA_GRID * EPA_BLOCK));
+    const size_t MI = (size_t)(cfg->max_mesh_items > 0 ? cfg->max_mesh_items : 1);
+    CKC(dalloc(&ctx->dMeshPair, MI));
+    CKC(dalloc(&ctx->dMeshTri, MI));
+    CKC(dalloc(&ctx->dRawMesh, MI));
+    CKC(dalloc(&ctx->dMeshStart, P));
+    CKC(dalloc(&ctx->dMeshCount, P));
+    for (int i = 0; i < 5; i++) CKC(cudaEventCreate(&ctx->ev[i]));
+#undef CKC
+    *out = ctx;
+    return B2C_OK;
+}
+
+void b2c_destroy(b2c_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->dShapes); cudaFree(ctx->dHullPts); cudaFree(ctx->dMeshes);
+    for (auto& m : ctx->meshes) { cudaFree(m.nodes); cudaFree(m.verts); cudaFree(m.idx); }
+    cudaFree(ctx->B.xf4); cudaFree(ctx->B.shape); cudaFree(ctx->B.filt); cudaFree(ctx->B.flags); cudaFree(ctx->B.world);
+    cudaFree(ctx->B.effMin); cudaFree(ctx->B.effMax); cudaFree(ctx->B.leafMin); cudaFree(ctx->B.leafMax);
+    cudaFree(ctx->B.lastSet); cudaFree(ctx->B.material);
+    cudaFree(ctx->dStaging); cudaFreeHost(ctx->hStagingPinned); cudaFree(ctx->dExtAabb); cudaFree(ctx->dExtMask);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dPairKeys[i]); cudaFree(ctx->dSortedKeys[i]);
+        cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dManifolds[i]);
+    }
+    cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
+    cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
+    ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinOf); cudaFree(ctx->dItems); cudaFree(ctx->dBinStart);
+    cudaFree(ctx->dBinCursor); cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dMeshPair);
+    cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
+    for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* b2c_last_error_string(const b2c_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+// ---- shapes ------------------------------------------------------------------------------------------
+static int32_t addShape(b2c_ctx* ctx, const ShapeDev& s, int32_t* out) {
+    if ((int)ctx->hShapes.size() >= ctx->cfg.max_shapes) { ctx->err = "shape table full"; return B2C_ERR_CAPACITY; }
+    ctx->hShapes.push_back(s);
+    ctx->shapesDirty = true;
+    if (out) *out = (int32_t)ctx->hShapes.size() - 1;
+    return B2C_OK;
+}
+
+int32_t b2c_shape_register_box(b2c_ctx* ctx, const float he[3], float margin, int32_t* out) {
+    if (!ctx || !he) return B2C_ERR_BAD_ARG;
+    ShapeDev s{};
+    s.type = SH_BOX;
+    s.margin = margin >= 0.f ? margin : 0.04f;  // BulletGlobals.CONVEX_DISTANCE_MARGIN
+    // sh/BoxShape.java:46-50: implicitShapeDimensions = halfExtents * localScaling(1) - margin
+    for (int c = 0; c < 3; c++) s.dims[c] = he[c] * 1.0f - s.margin;
+    return addShape(ctx, s, out);
+}
+int32_t b2c_shape_register_sphere(b2c_ctx* ctx, float radius, int32_t* out) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    ShapeDev s{};
+    s.type = SH_SPHERE;
+    s.dims[0] = radius;
+    s.margin = radius * 1.0f;  // getMargin() = getRadius() = implicit.x * localScaling.x (sh/SphereShape.java:83-97)
+    return addShape(ctx, s, out);
+}
+int32_t b2c_shape_register_hull(b2c_ctx* ctx, const float* pts, int32_t n, float margin, int32_t* out) {
+    if (!ctx || !pts || n < 1) return B2C_ERR_BAD_ARG;
+    if (ctx->hullPtsUsed + n > ctx->cfg.max_hull_points) { ctx->err = "hull point pool full"; return B2C_ERR_CAPACITY; }
+    ShapeDev s{};
+    s.type = SH_HULL;
+    s.margin = margin >= 0.f ? margin : 0.04f;
+    s.pointOffset = ctx->hullPtsUsed;
+    s.numPoints = n;
+    std::vector<float4> packed((size_t)n);
+    // sh/PolyhedralConvexShape.java:177-201 recalcLocalAabb: extreme coordinate of point*scaling(1) +- margin
+    float mx[3] = {0, 0, 0}, mn[3] = {0, 0, 0};
+    float wmx[3] = {-1e30f, -1e30f, -1e30f}, wmn[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = 0; i < n; i++) {
+        float v[3] = {pts[3 * i] * 1.0f, pts[3 * i + 1] * 1.0f, pts[3 * i + 2] * 1.0f};
+        packed[i] = make_float4(v[0], v[1], v[2], 0.f);
+        for (int c = 0; c < 3; c++) {
+            float dpos = v[c], dneg = -v[c];  // dot with +-unit axis reduces to +-coordinate (other terms are *0)
+            dpos = (c == 0 ? 1.0f * v[0] + 0.0f * v[1] + 0.0f * v[2] : (c == 1 ? 0.0f * v[0] + 1.0f * v[1] + 0.0f * v[2] : 0.0f * v[0] + 0.0f * v[1] + 1.0f * v[2]));
+            dneg = (c == 0 ? -1.0f * v[0] + 0.0f * v[1] + 0.0f * v[2] : (c == 1 ? 0.0f * v[0] + -1.0f * v[1] + 0.0f * v[2] : 0.0f * v[0] + 0.0f * v[1] + -1.0f * v[2]));
+            if (dpos > wmx[c]) { wmx[c] = dpos; mx[c] = v[c]; }
+            if (dneg > wmn[c]) { wmn[c] = dneg; mn[c] = v[c]; }
+        }
+    }
+    for (int c = 0; c < 3; c++) { s.aabbMax[c] = mx[c] + s.margin; s.aabbMin[c] = mn[c] - s.margin; }
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpy(ctx->dHullPts + ctx->hullPtsUsed, packed.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    ctx->hullPtsUsed += n;
+    return addShape(ctx, s, out);
+}
+int32_t b2c_shape_register_plane(b2c_ctx* ctx, const float nrm[3], float c, int32_t* out) {
+    if (!ctx || !nrm) return B2C_ERR_BAD_ARG;
+    ShapeDev s{};
+    s.type = SH_PLANE;
+    s.margin = 0.f;  // sh/ConcaveShape.java:35
+    // sh/StaticPlaneShape.java:45-48: planeNormal.set(n).nor()  (libgdx nor(): untouched if len2 is 0 or 1)
+    float l2 = nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2];
+    float k = 1.0f;
+    bool scale = !(l2 == 0.f || l2 == 1.f);
+    if (scale) k = 1.0f / (float)std::sqrt((double)l2);
+    for (int i = 0; i < 3; i++) s.plane[i] = scale ? nrm[i] * k : nrm[i];
+    s.plane[3] = c;
+    ctx->hasPlane = true;
+    return addShape(ctx, s, out);
+}
+int32_t b2c_shape_register_mesh(b2c_ctx* ctx, const void* vbase, int32_t nv, int32_t vstride, const void* ibase, int32_t nt,
+                                int32_t istride, const float scaling[3], int32_t* out) {
+    if (!ctx || !vbase || !ibase || nv < 1 || nt < 1 || vstride < 12 || istride < 12) return B2C_ERR_BAD_ARG;
+    if (nt >= (1 << 21)) { ctx->err = "mesh part exceeds 2^21 triangles (sh/OptimizedBvh.java:65)"; return B2C_ERR_BAD_ARG; }
+    float sc[3] = {1.f, 1.f, 1.f};
+    if (scaling) { sc[0] = scaling[0]; sc[1] = scaling[1]; sc[2] = scaling[2]; }
+    std::vector<float> verts(3 * (size_t)nv);
+    std::vector<int32_t> idx(3 * (size_t)nt);
+    for (int i = 0; i < nv; i++) {
+        const float* p = (const float*)((const char*)vbase + (size_t)i * vstride);
+        for (int c = 0; c < 3; c++) verts[3 * (size_t)i + c] = p[c] * sc[c];  // sh/VertexData.java:50-55
+    }
+    for (int t = 0; t < nt; t++) {
+        const int32_t* p = (const int32_t*)((const char*)ibase + (size_t)t * istride);
+        for (int c = 0; c < 3; c++) {
+            if (p[c] < 0 || p[c] >= nv) { ctx->err = "mesh index out of range"; return B2C_ERR_BAD_ARG; }
+            idx[3 * (size_t)t + c] = p[c];
+        }
+    }
+    HostMesh hm;
+    buildQuantizedBvh(verts.data(), idx.data(), nt, hm.bvh);
+    cudaSetDevice(ctx->device);
+    size_t nn = hm.bvh.nodes.size() / 4;
+    CK(cudaMalloc((void**)&hm.nodes, nn * sizeof(int4)));
+    CK(cudaMalloc((void**)&hm.verts, verts.size() * sizeof(float)));
+    CK(cudaMalloc((void**)&hm.idx, idx.size() * sizeof(int)));
+    CK(cudaMemcpy(hm.nodes, hm.bvh.nodes.data(), nn * sizeof(int4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(hm.verts, verts.data(), verts.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(hm.idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    MeshDev md{};
+    md.nodes = hm.nodes; md.verts = hm.verts; md.idx = hm.idx;
+    md.numNodes = (int)nn; md.numTris = nt;
+    for (int c = 0; c < 3; c++) { md.qmin[c] = hm.bvh.qmin[c]; md.qmax[c] = hm.bvh.qmax[c]; md.quant[c] = hm.bvh.quant[c]; }
+    ShapeDev s{};
+    s.type = SH_MESH;
+    s.margin = 0.f;  // sh/ConcaveShape.java:35
+    for (int c = 0; c < 3; c++) { s.aabbMax[c] = hm.bvh.localMax[c] + s.margin; s.aabbMin[c] = hm.bvh.localMin[c] - s.margin; }
+    s.mesh = (int)ctx->hMeshes.size();
+    ctx->hMeshes.push_back(md);
+    ctx->meshes.push_back(std::move(hm));
+    ctx->hasMesh = true;
+    return addShape(ctx, s, out);
+}
+int32_t b2c_mesh_get_bvh(b2c_ctx* ctx, int32_t shape, void* nodesOut, int32_t cap, int32_t* numNodes, float quant9[9]) {
+    if (!ctx || shape < 0 || shape >= (int)ctx->hShapes.size() || ctx->hShapes[shape].type != SH_MESH) return B2C_ERR_BAD_HANDLE;
+    const HostMesh& hm = ctx->meshes[ctx->hShapes[shape].mesh];
+    int nn = (int)(hm.bvh.nodes.size() / 4);
+    if (numNodes) *numNodes = nn;
+    if (quant9)
+        for (int c = 0; c < 3; c++) { quant9[c] = hm.bvh.qmin[c]; quant9[3 + c] = hm.bvh.qmax[c]; quant9[6 + c] = hm.bvh.quant[c]; }
+    if (nodesOut) {
+        if (cap < nn) return B2C_ERR_CAPACITY;
+        memcpy(nodesOut, hm.bvh.nodes.data(), (size_t)nn * 16);
+    }
+    return B2C_OK;
+}
+
+// ---- proxies -----------------------------------------------------------------------------------------
+int32_t b2c_proxy_create(b2c_ctx* ctx, int32_t shape, const float t[12], int16_t group, int16_t mask, int32_t flags, int32_t world,
+                         int32_t* uidOut) {
+    if (!ctx || !t) return B2C_ERR_BAD_ARG;
+    if (shape < 0 || shape >= (int)ctx->hShapes.size()) return B2C_ERR_BAD_HANDLE;
+    if (world < 0 || world >= ctx->cfg.num_worlds) return B2C_ERR_BAD_ARG;
+    if (ctx->nBodies >= ctx->cfg.max_bodies) { ctx->err = "proxy capacity exceeded"; return B2C_ERR_CAPACITY; }
+    cudaSetDevice(ctx->device);
+    int i = ctx->nBodies;
+    float4 rows[3] = {make_float4(t[0], t[1], t[2], t[9]), make_float4(t[3], t[4], t[5], t[10]), make_float4(t[6], t[7], t[8], t[11])};
+    uint32_t filt = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
+    uint8_t fl = (uint8_t)(BF_ALIVE | BF_ACTIVE | ((flags & 1) ? BF_STATIC : 0));
+    float2 mat = make_float2(0.5f, 0.0f);  // disp/CollisionObject.java:95 friction, :71 restitution
+    int32_t rc = uploadShapes(ctx);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->B.xf4 + 3 * (size_t)i, rows, sizeof(rows), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.shape + i, &shape, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.filt + i, &filt, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.flags + i, &fl, 1, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.world + i, &world, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.material + i, &mat, sizeof(float2), cudaMemcpyHostToDevice, s));
+    int ls = ctx->step;  // createProxy counts as a setAabb in the current window (bp/DbvtBroadphase.java:177-180)
+    CK(cudaMemcpyAsync(ctx->B.lastSet + i, &ls, sizeof(int), cudaMemcpyHostToDevice, s));
+    k_initial_aabb<<<1, 1, 0, s>>>(ctx->B, ctx->dShapes, i);
+    CK(cudaStreamSynchronize(s));  // host temporaries above go out of scope
+    ctx->hFlags.push_back(fl);
+    ctx->hShapeOf.push_back(shape);
+    ctx->nBodies++;
+    if (uidOut) *uidOut = ctx->nBodies;  // ++gid
+    return B2C_OK;
+}
+
+int32_t b2c_proxy_create_batch(b2c_ctx* ctx, int32_t n, const int32_t* shapes, const float* planes, const int16_t* groups,
+                               const int16_t* masks, const int32_t* flags, const int32_t* worlds, int32_t* firstUid) {
+    if (!ctx || !shapes || !planes || !groups || !masks || n < 0) return B2C_ERR_BAD_ARG;
+    if (ctx->nBodies + n > ctx->cfg.max_bodies) { ctx->err = "proxy capacity exceeded"; return B2C_ERR_CAPACITY; }
+    if (firstUid) *firstUid = ctx->nBodies + 1;
+    if (n == 0) return B2C_OK;
+    for (int k = 0; k < n; k++) {
+        if (shapes[k] < 0 || shapes[k] >= (int)ctx->hShapes.size()) return B2C_ERR_BAD_HANDLE;
+        if (worlds && (worlds[k] < 0 || worlds[k] >= ctx->cfg.num_worlds)) return B2C_ERR_BAD_ARG;
+    }
+    cudaSetDevice(ctx->device);
+    int32_t rc = uploadShapes(ctx);
+    if (rc) return rc;
+    const int first = ctx->nBodies;
+    std::vector<float4> rows(3 * (size_t)n);
+    std::vector<uint32_t> filt((size_t)n);
+    std::vector<uint8_t> fl((size_t)n);
+    std::vector<int> wl((size_t)n, 0), ls((size_t)n, ctx->step);
+    std::vector<float2> mat((size_t)n, make_float2(0.5f, 0.0f));
+    const size_t S = (size_t)n;
+    for (int k = 0; k < n; k++) {
+        const float* p = planes + k;
+        rows[3 * (size_t)k] = make_float4(p[0], p[S], p[2 * S], p[9 * S]);
+        rows[3 * (size_t)k + 1] = make_float4(p[3 * S], p[4 * S], p[5 * S], p[10 * S]);
+        rows[3 * (size_t)k + 2] = make_float4(p[6 * S], p[7 * S], p[8 * S], p[11 * S]);
+        filt[k] = ((uint32_t)(uint16_t)groups[k]) | ((uint32_t)(uint16_t)masks[k] << 16);
+        fl[k] = (uint8_t)(BF_ALIVE | BF_ACTIVE | ((flags && (flags[k] & 1)) ? BF_STATIC : 0));
+        if (worlds) wl[k] = worlds[k];
+    }
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->B.xf4 + 3 * (size_t)first, rows.data(), rows.size() * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.shape + first, shapes, S * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.filt + first, filt.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.flags + first, fl.data(), S, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.world + first, wl.data(), S * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.material + first, mat.data(), S * sizeof(float2), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->B.lastSet + first, ls.data(), S * sizeof(int), cudaMemcpyHostToDevice, s));
+    k_initial_aabb_range<<<(n + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, first, n);
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < n; k++) { ctx->hFlags.push_back(fl[k]); ctx->hShapeOf.push_back(shapes[k]); }
+    ctx->nBodies += n;
+    return B2C_OK;
+}
+
+int32_t b2c_proxy_destroy(b2c_ctx* ctx, int32_t uid) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (uid < 1 || uid > ctx->nBodies || !(ctx->hFlags[uid - 1] & BF_ALIVE)) return B2C_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    ctx->hFlags[uid - 1] = 0;
+    uint8_t z = 0;
+    CK(cudaMemcpyAsync(ctx->B.flags + (uid - 1), &z, 1, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2C_OK;
+}
+
+int32_t b2c_proxy_set_material(b2c_ctx* ctx, int32_t uid, float friction, float restitution) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (uid < 1 || uid > ctx->nBodies) return B2C_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    float2 m = make_float2(friction, restitution);
+    CK(cudaMemcpyAsync(ctx->B.material + (uid - 1), &m, sizeof(m), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2C_OK;
+}
+
+// ---- per-step inputs ---------------------------------------------------------------------------------
+int32_t b2c_set_transforms(b2c_ctx* ctx, int32_t n, const int32_t* uids, const float* planes) {
+    if (!ctx || !planes || n < 0) return B2C_ERR_BAD_ARG;
+    if (n > ctx->nBodies) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    if (!uids) {
+        // 12 planes of n floats -> staging with plane stride max_bodies; repacked into float4 rows by k_aabb
+        CK(cudaMemcpy2DAsync(ctx->dStaging, (size_t)ctx->cfg.max_bodies * sizeof(float), planes, (size_t)n * sizeof(float),
+                             (size_t)n * sizeof(float), 12, cudaMemcpyHostToDevice, s));
+        ctx->stagingCount = n;
+        return B2C_OK;
+    }
+    for (int i = 0; i < n; i++)
+        if (uids[i] < 1 || uids[i] > ctx->nBodies) return B2C_ERR_BAD_HANDLE;
+    if (ctx->stagingCount > 0) {  // an unflushed full upload precedes this partial one: repack it first
+        int32_t rc = runAabbKernel(ctx, false);
+        if (rc) return rc;
+    }
+    int* dU = nullptr;
+    float* dP = nullptr;
+    CK(cudaMalloc((void**)&dU, (size_t)n * sizeof(int)));
+    CK(cudaMalloc((void**)&dP, (size_t)n * 12 * sizeof(float)));
+    CK(cudaMemcpyAsync(dU, uids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dP, planes, (size_t)n * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    k_scatter_xf<<<(n + 255) / 256, 256, 0, s>>>(ctx->B, n, dU, dP);
+    CK(cudaStreamSynchronize(s));
+    cudaFree(dU);
+    cudaFree(dP);
+    return B2C_OK;
+}
+
+int32_t b2c_set_activation(b2c_ctx* ctx, int32_t n, const int32_t* uids, const uint8_t* active) {
+    if (!ctx || !active || n < 0 || n > ctx->cfg.max_bodies) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    // flags live on the host too (alive/static are host decisions); flush any device-side change first
+    if (ctx->aabbPending || ctx->extPending || ctx->stagingCount) {
+        int32_t rc = runAabbKernel(ctx, false);
+        if (rc) return rc;
+    }
+    std::vector<uint8_t> dev((size_t)ctx->nBodies);
+    if (ctx->nBodies) {
+        CK(cudaMemcpyAsync(dev.data(), ctx->B.flags, (size_t)ctx->nBodies, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (int k = 0; k < n; k++) {
+        int uid = uids ? uids[k] : k + 1;
+        if (uid < 1 || uid > ctx->nBodies) return B2C_ERR_BAD_HANDLE;
+        uint8_t f = dev[uid - 1];
+        if (!(f & BF_ALIVE)) continue;
+        f = active[k] ? (uint8_t)(f | BF_ACTIVE) : (uint8_t)(f & ~BF_ACTIVE);
+        dev[uid - 1] = f;
+    }
+    if (ctx->nBodies) {
+        CK(cudaMemcpyAsync(ctx->B.flags, dev.data(), (size_t)ctx->nBodies, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return B2C_OK;
+}
+
+int32_t b2c_set_aabbs(b2c_ctx* ctx, int32_t n, const int32_t* uids, const float* mm) {
+    if (!ctx || !mm || n < 0 || n > ctx->nBodies) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const size_t N = (size_t)ctx->cfg.max_bodies;
+    if (!uids) {
+        CK(cudaMemcpy2DAsync(ctx->dExtAabb, N * sizeof(float), mm, (size_t)n * sizeof(float), (size_t)n * sizeof(float), 6,
+                             cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(ctx->dExtMask, 1, (size_t)n, s));
+    } else {
+        std::vector<float> tmp(6 * N, 0.f);
+        std::vector<uint8_t> mask(N, 0);
+        if (ctx->extPending) {
+            CK(cudaMemcpyAsync(tmp.data(), ctx->dExtAabb, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(mask.data(), ctx->dExtMask, N, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        for (int k = 0; k < n; k++) {
+            int uid = uids[k];
+            if (uid < 1 || uid > ctx->nBodies) return B2C_ERR_BAD_HANDLE;
+            for (int c = 0; c < 6; c++) tmp[c * N + (uid - 1)] = mm[(size_t)c * n + k];
+            mask[uid - 1] = 1;
+        }
+        CK(cudaMemcpyAsync(ctx->dExtAabb, tmp.data(), 6 * N * sizeof(float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->dExtMask, mask.data(), N, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    ctx->extPending = true;
+    return B2C_OK;
+}
+
+// ---- the path ----------------------------------------------------------------------------------------
+int32_t b2c_update_aabbs(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    ctx->aabbPending = true;  // executed by the k_aabb launch that opens calculate_overlapping_pairs (or by a getter)
+    return B2C_OK;
+}
+
+int32_t b2c_calculate_overlapping_pairs(b2c_ctx* ctx, int32_t* numPairs) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    ctx->launches = 0;
+    int32_t rc = enqueueBroadphase(ctx);
+    if (rc) return rc;
+    rc = readCounters(ctx);
+    if (numPairs) *numPairs = ctx->lastPairs;
+    ctx->stats.kernel_launches = ctx->launches;
+    return rc;
+}
+
+int32_t b2c_get_pairs(b2c_ctx* ctx, int32_t* out, int32_t cap, int32_t* numOut) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->dNumPairs[ctx->cur], sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (numOut) *numOut = (int32_t)n;
+    if (!out) return B2C_OK;
+    if ((uint32_t)cap < n) { ctx->err = "pair output buffer too small"; return B2C_ERR_CAPACITY; }
+    if (n) {
+        CK(cudaMemcpyAsync(out, ctx->dPairs, (size_t)n * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return B2C_OK;
+}
+
+int32_t b2c_dispatch_all_pairs(b2c_ctx* ctx, int32_t* numManifolds, int32_t* numContacts) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    int before = ctx->launches;
+    int32_t rc = enqueueNarrowphase(ctx);
+    if (rc) return rc;
+    rc = readCounters(ctx);
+    if (numManifolds) *numManifolds = ctx->lastManifolds;
+    if (numContacts) *numContacts = ctx->lastContacts;
+    ctx->stats.kernel_launches = ctx->launches;
+    (void)before;
+    return rc;
+}
+
+int32_t b2c_transforms_written(b2c_ctx* ctx, int32_t n) {
+    if (!ctx || n < 0 || n > ctx->nBodies) return B2C_ERR_BAD_ARG;
+    ctx->stagingCount = n;
+    return B2C_OK;
+}
+
+int32_t b2c_step_device(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    ctx->launches = 0;
+    ctx->aabbPending = true;
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    int32_t rc = enqueueBroadphase(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[2], s));
+    rc = enqueueNarrowphase(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[3], s));
+    ctx->stats.kernel_launches = ctx->launches;
+    return B2C_OK;
+}
+
+int32_t b2c_sync_counts(b2c_ctx* ctx, int32_t* numPairs, int32_t* numManifolds, int32_t* numContacts) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    int32_t rc = readCounters(ctx);
+    if (numPairs) *numPairs = ctx->lastPairs;
+    if (numManifolds) *numManifolds = ctx->lastManifolds;
+    if (numContacts) *numContacts = ctx->lastContacts;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]) == cudaSuccess) ctx->stats.ms_broadphase = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_narrowphase = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_total = ms;
+    cudaGetLastError();
+    return rc;
+}
+
+int32_t b2c_step(b2c_ctx* ctx, int32_t n, const float* planes, int32_t* numPairs, int32_t* numManifolds, int32_t* numContacts) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (planes) {
+        int32_t rc = b2c_set_transforms(ctx, n, nullptr, planes);
+        if (rc) return rc;
+    }
+    int32_t rc = b2c_step_device(ctx);
+    if (rc) return rc;
+    return b2c_sync_counts(ctx, numPairs, numManifolds, numContacts);
+}
+
+// ---- results -----------------------------------------------------------------------------------------
+int32_t b2c_get_manifolds(b2c_ctx* ctx, b2c_manifold* out, int32_t cap, int32_t onlyTouching, int32_t* numOut) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->dNumPairs[ctx->cur], sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<b2c_manifold> all(n);
+    if (n) {
+        CK(cudaMemcpyAsync(all.data(), ctx->dManifolds[ctx->cur], (size_t)n * sizeof(b2c_manifold), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    int32_t k = 0;
+    for (uint32_t p = 0; p < n; p++) {
+        const b2c_manifold& m = all[p];
+        if (m.algorithm == 0) continue;
+        if (onlyTouching && m.num_contacts == 0) continue;
+        if (out && k < cap) {
+            out[k] = m;
+            for (int q = m.num_contacts; q < 4; q++) memset(&out[k].points[q], 0, sizeof(b2c_manifold_point));
+        }
+        k++;
+    }
+    if (numOut) *numOut = k;
+    if (out && k > cap) { ctx->err = "manifold output buffer too small"; return B2C_ERR_CAPACITY; }
+    return B2C_OK;
+}
+
+int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, int32_t* numOut) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->dNumPairs[ctx->cur], sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<b2c_raw_contact> raw(n);
+    std::vector<uint32_t> ms(n), mc(n);
+    if (n) {
+        CK(cudaMemcpyAsync(raw.data(), ctx->dRaw, (size_t)n * sizeof(b2c_raw_contact), cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->hasMesh) {
+            CK(cudaMemcpyAsync(ms.data(), ctx->dMeshStart, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(mc.data(), ctx->dMeshCount, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    uint32_t nItems = 0;
+    std::vector<b2c_raw_contact> rawMesh;
+    if (ctx->hasMesh) {
+        nItems = ctx->hCtrPinned->meshItems;
+        if (nItems > (uint32_t)ctx->cfg.max_mesh_items) nItems = 0;
+        rawMesh.resize(nItems);
+        if (nItems) {
+            CK(cudaMemcpyAsync(rawMesh.data(), ctx->dRawMesh, (size_t)nItems * sizeof(b2c_raw_contact), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    int32_t k = 0;
+    for (uint32_t p = 0; p < n; p++) {
+        if (raw[p].has_contact == -1) continue;  // not dispatched
+        if (raw[p].has_contact == -3) {
+            for (uint32_t q = ms[p]; q < ms[p] + mc[p] && q < nItems; q++) {
+                if (out && k < cap) out[k] = rawMesh[q];
+                k++;
+            }
+            continue;
+        }
+        if (out && k < cap) out[k] = raw[p];
+        k++;
+    }
+    if (numOut) *numOut = k;
+    if (out && k > cap) { ctx->err = "raw contact output buffer too small"; return B2C_ERR_CAPACITY; }
+    return B2C_OK;
+}
+
+int32_t b2c_get_aabbs(b2c_ctx* ctx, float* out, int32_t n) {
+    if (!ctx || !out || n < 0 || n > ctx->nBodies) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->aabbPending || ctx->extPending || ctx->stagingCount) {
+        int32_t rc = runAabbKernel(ctx, false);
+        if (rc) return rc;
+    }
+    float* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)n * 6 * sizeof(float)));
+    k_get_aabbs<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->B, n, d);
+    CK(cudaMemcpyAsync(out, d, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return B2C_OK;
+}
+
+int32_t b2c_get_broadphase_aabb(b2c_ctx* ctx, float mn[3], float mx[3]) {
+    if (!ctx || !mn || !mx) return B2C_ERR_BAD_ARG;
+    // bp/SimpleBroadphase.java:118-121 and bp/DbvtBroadphase.java getBroadphaseAabb: unbounded
+    for (int c = 0; c < 3; c++) { mn[c] = -1e30f; mx[c] = 1e30f; }
+    return B2C_OK;
+}
+
+int32_t b2c_get_stats(b2c_ctx* ctx, b2c_stats* out) {
+    if (!ctx || !out) return B2C_ERR_BAD_ARG;
+    *out = ctx->stats;
+    return B2C_OK;
+}
+
+void* b2c_stream(b2c_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+float* b2c_device_transforms(b2c_ctx* ctx) { return ctx ? ctx->dStaging : nullptr; }
+
+}  // extern "C"

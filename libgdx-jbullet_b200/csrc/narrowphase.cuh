@@ -1,0 +1,714 @@
+// narrowphase.cuh — stage 2: per-pair contact generation and the persistent 4-point manifolds.
+//
+// Replaces, for one step:
+//   disp/CollisionDispatcher.java:252-257 dispatchAllCollisionPairs + disp/DefaultNearCallback.java:39-66
+//       + :198-223 needsCollision + disp/DefaultCollisionConfiguration.java:149-213    -> k_carry, k_classify
+//   disp/SphereSphereCollisionAlgorithm.java:73-134                                      -> k_sphere_sphere
+//   disp/ConvexPlaneCollisionAlgorithm.java:75-136                                       -> k_convex_plane
+//   disp/ConvexConvexAlgorithm.java:90-139 + np/GjkPairDetector.java:73-316              -> k_gjk, k_epa
+//   disp/ConvexConcaveCollisionAlgorithm.java:65-93 + disp/ConvexTriangleCallback.java:83-172
+//       + sh/OptimizedBvh.java:709-740,940-997                                           -> k_mesh_query, k_gjk_tri, k_mesh_manifold
+//   disp/ManifoldResult.java:92-191 + np/PersistentManifold.java:83-372                  -> manifoldAdd / manifoldRefresh
+//
+// Pairs are binned by algorithm and shape-type pair so that a warp runs one code path; each pair is one
+// thread (the simplex lives in registers).  Manifolds are one 416-byte record per pair, in pair order,
+// carried from step to step by matching the sorted pair keys.
+#pragma once
+#include "../../include/b2c.h"
+#include "common.cuh"
+#include "epa.cuh"
+#include "gjk.cuh"
+
+namespace b2c {
+
+enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_GJK0 = 3, BIN_MESH = 12, BIN_COUNT = 13 };
+
+struct NpArgs {
+    const int2* pairs;            // sorted (uid0, uid1)
+    uint32_t* numPairs;           // device
+    const float4* xf4;
+    const int* shape;
+    const uint8_t* flags;
+    const float2* material;
+    const ShapeDev* shapes;
+    const float4* hullPts;
+    const MeshDev* meshes;
+    b2c_manifold* manifolds;      // [maxPairs] this step
+    b2c_raw_contact* raw;         // [maxPairs]
+    uint8_t* binOf;               // [maxPairs]
+    uint32_t* items;              // [maxPairs] pair indices grouped by bin
+    uint32_t* binStart;           // [16] device
+    uint32_t* binCursor;          // [16] device
+    StepCounters* ctr;
+    float threshold;
+    uint32_t maxPairs;
+};
+
+// ---- manifold (np/PersistentManifold.java, disp/ManifoldResult.java) ---------------------------------
+__device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(float* p, f3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+// np/PersistentManifold.java:83-156 sortCachedPoints + lm/VectorUtil.java:60-90 closestAxis4
+__device__ __forceinline__ int manifoldSortCachedPoints(const b2c_manifold* m, f3 newLocalA, float newDist) {
+    int maxPenetrationIndex = -1;
+    float maxPenetration = newDist;
+    for (int i = 0; i < 4; i++)
+        if (m->points[i].distance < maxPenetration) { maxPenetrationIndex = i; maxPenetration = m->points[i].distance; }
+    f3 p0 = ld3(m->points[0].local_a), p1 = ld3(m->points[1].local_a), p2 = ld3(m->points[2].local_a), p3 = ld3(m->points[3].local_a);
+    float res0 = 0.f, res1 = 0.f, res2 = 0.f, res3 = 0.f;
+    if (maxPenetrationIndex != 0) res0 = len2_3(crs3(sub3(newLocalA, p1), sub3(p3, p2)));
+    if (maxPenetrationIndex != 1) res1 = len2_3(crs3(sub3(newLocalA, p0), sub3(p3, p2)));
+    if (maxPenetrationIndex != 2) res2 = len2_3(crs3(sub3(newLocalA, p0), sub3(p3, p1)));
+    if (maxPenetrationIndex != 3) res3 = len2_3(crs3(sub3(newLocalA, p0), sub3(p2, p1)));
+    res0 = fabsf(res0); res1 = fabsf(res1); res2 = fabsf(res2); res3 = fabsf(res3);
+    int maxIndex = -1;
+    float maxVal = -1e30f;
+    if (res0 > maxVal) { maxIndex = 0; maxVal = res0; }
+    if (res1 > maxVal) { maxIndex = 1; maxVal = res1; }
+    if (res2 > maxVal) { maxIndex = 2; maxVal = res2; }
+    if (res3 > maxVal) { maxIndex = 3; maxVal = res3; }
+    return maxIndex < 0 ? 0 : maxIndex;
+}
+
+// disp/ManifoldResult.java:92-157 addContactPoint.  rootA/rootB are the transforms of the PAIR's
+// body0/body1 (ManifoldResult.init, :70-75); pairBody0 = uid of the pair's first body.
+__device__ __forceinline__ bool manifoldAdd(b2c_manifold* m, int pairBody0, const Xf& rootA, const Xf& rootB, f3 normal, f3 point,
+                                            float depth, float threshold, float friction, float restitution, int partId1,
+                                            int index1) {
+    if (depth > threshold) return false;
+    bool isSwapped = m->body0 != pairBody0;
+    f3 pointA = add3(scl3(normal, depth), point);
+    f3 localA, localB;
+    if (isSwapped) { localA = invXfPoint(rootB, pointA); localB = invXfPoint(rootA, point); }
+    else { localA = invXfPoint(rootA, pointA); localB = invXfPoint(rootB, point); }
+    // np/PersistentManifold.java:214-233 getCacheEntry
+    float shortest = threshold * threshold;
+    int nearest = -1;
+    int size = m->num_contacts;
+    for (int i = 0; i < size; i++) {
+        f3 d = sub3(ld3(m->points[i].local_a), localA);
+        float dd = dot3(d, d);
+        if (dd < shortest) { shortest = dd; nearest = i; }
+    }
+    int life = 0, src = -1;
+    int idx;
+    if (nearest >= 0) {  // :280-305 replaceContactPoint keeps lifetime (and the solver's cached impulses)
+        idx = nearest;
+        life = m->points[idx].life_time;
+        src = m->points[idx].src_slot;
+    } else {             // :235-257 addManifoldPoint
+        idx = size;
+        if (idx == 4) idx = manifoldSortCachedPoints(m, localA, depth);
+        else m->num_contacts = size + 1;
+    }
+    b2c_manifold_point* p = &m->points[idx];
+    st3(p->local_a, localA); st3(p->local_b, localB);
+    st3(p->world_a, pointA); st3(p->world_b, point);
+    st3(p->normal_on_b, normal);
+    p->distance = depth;
+    p->combined_friction = friction;
+    p->combined_restitution = restitution;
+    p->life_time = life;
+    p->src_slot = src;
+    p->part_id1 = partId1;
+    p->index1 = index1;
+    return true;
+}
+
+// np/PersistentManifold.java:312-372 refreshContactPoints(trA, trB) incl. :259-278 removeContactPoint
+__device__ __forceinline__ void manifoldRefresh(b2c_manifold* m, const Xf& trA, const Xf& trB, float threshold) {
+    for (int i = m->num_contacts - 1; i >= 0; i--) {
+        b2c_manifold_point* p = &m->points[i];
+        f3 wa = xfPoint(trA, ld3(p->local_a));
+        f3 wb = xfPoint(trB, ld3(p->local_b));
+        st3(p->world_a, wa); st3(p->world_b, wb);
+        p->distance = dot3(sub3(wa, wb), ld3(p->normal_on_b));
+        p->life_time++;
+    }
+    for (int i = m->num_contacts - 1; i >= 0; i--) {
+        b2c_manifold_point* p = &m->points[i];
+        bool remove = false;
+        if (!(p->distance <= threshold)) {
+            remove = true;
+        } else {
+            f3 n = ld3(p->normal_on_b);
+            f3 projected = sub3(ld3(p->world_a), scl3(n, p->distance));
+            f3 diff = sub3(ld3(p->world_b), projected);
+            if (dot3(diff, diff) > threshold * threshold) remove = true;
+        }
+        if (remove) {
+            int last = m->num_contacts - 1;
+            if (i != last) {
+                m->points[i] = m->points[last];
+                m->points[last].life_time = 0;
+                m->points[last].src_slot = -1;
+            }
+            m->num_contacts = last;
+        }
+    }
+}
+// disp/ManifoldResult.java:177-191
+__device__ __forceinline__ void resultRefresh(b2c_manifold* m, int pairBody0, const Xf& rootA, const Xf& rootB, float threshold) {
+    if (m->num_contacts == 0) return;
+    if (m->body0 != pairBody0) manifoldRefresh(m, rootB, rootA, threshold);
+    else manifoldRefresh(m, rootA, rootB, threshold);
+}
+// disp/ManifoldResult.java:160-175
+__device__ __forceinline__ float combinedFriction(float f0, float f1) {
+    float f = f0 * f1;
+    if (f < -10.f) f = -10.f;
+    if (f > 10.f) f = 10.f;
+    return f;
+}
+
+// ---- k_carry: bring manifolds over from the previous step by pair key --------------------------------
+// A pair that stayed in the cache keeps its algorithm and manifold (bp/BroadphasePair.java:37-40); a pair
+// that left and came back starts empty (bp/HashedOverlappingPairCache.java:129-174 cleanOverlappingPair).
+__global__ void __launch_bounds__(256)
+k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs, const uint64_t* __restrict__ prevKeys,
+        const uint32_t* __restrict__ prevNum, const b2c_manifold* __restrict__ prevM, b2c_manifold* __restrict__ M, int uidBits) {
+    const uint32_t n = *numPairs, pn = *prevNum;
+    const int lane = threadIdx.x & 31;
+    // one warp per 32 pairs: each lane searches its pair, then the warp copies the 32 records with 16-byte
+    // accesses (26 int4 per record) so the copy is coalesced.
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        uint32_t p = base + lane;
+        int found = -1;
+        uint64_t k = 0;
+        if (p < n) {
+            k = keys[p];
+            uint32_t a = 0, b = pn;
+            while (a < b) {
+                uint32_t mid = (a + b) >> 1;
+                if (prevKeys[mid] < k) a = mid + 1; else b = mid;
+            }
+            if (a < pn && prevKeys[a] == k) found = (int)a;
+        }
+        for (int q = 0; q < 32; q++) {
+            uint32_t pq = base + q;
+            if (pq >= n) break;
+            int fq = __shfl_sync(0xffffffffu, found, q);
+            uint64_t kq = __shfl_sync(0xffffffffu, k, q);
+            int4* dst = reinterpret_cast<int4*>(M + pq);
+            if (fq >= 0) {
+                const int4* src = reinterpret_cast<const int4*>(prevM + fq);
+                int nc = prevM[fq].num_contacts;
+                int words = 2 + 6 * nc;  // header (32 B) + live points (96 B each)
+                if (lane < words) dst[lane] = src[lane];
+            } else if (lane < 2) {
+                int4 h;
+                if (lane == 0) h = make_int4((int)(kq >> uidBits), (int)(kq & ((1ull << uidBits) - 1ull)), 0, 0);
+                else h = make_int4(0, 0, 0, 0);
+                dst[lane] = h;
+            }
+        }
+    }
+}
+
+// ---- k_classify: needsCollision + algorithm table --------------------------------------------------
+__device__ __forceinline__ bool isConvexType(int t) { return t == SH_BOX || t == SH_SPHERE || t == SH_HULL; }
+
+__global__ void __launch_bounds__(256) k_classify(NpArgs a) {
+    const uint32_t n = *a.numPairs;
+    __shared__ uint32_t cnt[BIN_COUNT];
+    if (threadIdx.x < BIN_COUNT) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        uint8_t f0 = a.flags[b0], f1 = a.flags[b1];
+        int bin = BIN_SKIP;
+        // disp/CollisionDispatcher.java:198-223: skip when both are inactive
+        if ((f0 & BF_ACTIVE) || (f1 & BF_ACTIVE)) {
+            int t0 = a.shapes[a.shape[b0]].type, t1 = a.shapes[a.shape[b1]].type;
+            if (t0 == SH_SPHERE && t1 == SH_SPHERE) bin = BIN_SS;
+            else if ((isConvexType(t0) && t1 == SH_PLANE) || (isConvexType(t1) && t0 == SH_PLANE)) bin = BIN_CP;
+            else if (isConvexType(t0) && isConvexType(t1)) bin = BIN_GJK0 + t0 * 3 + t1;
+            else if ((isConvexType(t0) && t1 == SH_MESH) || (isConvexType(t1) && t0 == SH_MESH)) bin = BIN_MESH;
+        }
+        a.binOf[p] = (uint8_t)bin;
+        a.raw[p].has_contact = -1;  // not processed
+        atomicAdd(&cnt[bin], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < BIN_COUNT && cnt[threadIdx.x]) atomicAdd(&a.ctr->binCount[threadIdx.x], cnt[threadIdx.x]);
+}
+__global__ void k_bin_offsets(NpArgs a) {
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < BIN_COUNT; b++) {
+            a.binStart[b] = run;
+            a.binCursor[b] = run;
+            run += a.ctr->binCount[b];
+        }
+        a.binStart[BIN_COUNT] = run;
+    }
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(NpArgs a) {
+    const uint32_t n = *a.numPairs;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        int bin = a.binOf[p];
+        if (bin == BIN_SKIP) continue;
+        uint32_t pos = atomicAdd(&a.binCursor[bin], 1u);
+        a.items[pos] = p;
+    }
+}
+
+__device__ __forceinline__ void writeRaw(b2c_raw_contact* r, int2 pr, int tri, int has, f3 n, f3 pt, float depth, int method,
+                                         int iters) {
+    r->uid0 = pr.x; r->uid1 = pr.y; r->tri = tri; r->has_contact = has;
+    r->normal[0] = n.x; r->normal[1] = n.y; r->normal[2] = n.z;
+    r->point[0] = pt.x; r->point[1] = pt.y; r->point[2] = pt.z;
+    r->depth = depth; r->method = method; r->iters = iters; r->pad[0] = 0;
+}
+
+// ---- sphere-sphere (disp/SphereSphereCollisionAlgorithm.java:73-134) ---------------------------------
+__global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
+    const uint32_t s = a.binStart[BIN_SS], e = a.binStart[BIN_SS + 1];
+    uint32_t added = 0;
+    for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
+        uint32_t p = a.items[it];
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+        float r0 = a.shapes[a.shape[b0]].dims[0], r1 = a.shapes[a.shape[b1]].dims[0];
+        b2c_manifold* m = a.manifolds + p;
+        if (m->algorithm == 0) { m->algorithm = 1; m->body0 = pr.x; m->body1 = pr.y; }
+        for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+        f3 diff = sub3(t0.o, t1.o);
+        float len = len3(diff);
+        if (len > (r0 + r1)) {
+            writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, 10, 0);
+            resultRefresh(m, pr.x, t0, t1, a.threshold);
+            continue;
+        }
+        float dist = len - (r0 + r1);
+        f3 n = mk3(1.f, 0.f, 0.f);
+        if (len > B2C_FLT_EPSILON) n = scl3(diff, 1.f / len);
+        f3 pos1 = add3(t1.o, scl3(n, r1));
+        writeRaw(a.raw + p, pr, -1, 1, n, pos1, dist, 10, 0);
+        float2 m0 = a.material[b0], m1 = a.material[b1];
+        if (manifoldAdd(m, pr.x, t0, t1, n, pos1, dist, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
+        resultRefresh(m, pr.x, t0, t1, a.threshold);
+    }
+    if (added) atomicAdd(&a.ctr->contactsAdded, added);
+}
+
+// ---- convex-plane (disp/ConvexPlaneCollisionAlgorithm.java:75-136) -----------------------------------
+__device__ __forceinline__ AnyS makeAnyS(const ShapeDev& s, const float4* hullPts) {
+    AnyS r;
+    r.type = s.type;
+    r.h = mk3(s.dims[0], s.dims[1], s.dims[2]);
+    r.ta = r.tb = r.tc = mk3(0.f, 0.f, 0.f);
+    r.pts = hullPts + s.pointOffset;
+    r.n = s.numPoints;
+    r.margin = s.margin;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
+    const uint32_t s = a.binStart[BIN_CP], e = a.binStart[BIN_CP + 1];
+    uint32_t added = 0;
+    for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
+        uint32_t p = a.items[it];
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
+        bool swapped = (s0.type == SH_PLANE);  // planeConvexCF: convex is body1
+        int bc = swapped ? b1 : b0, bp = swapped ? b0 : b1;
+        const ShapeDev& cs = swapped ? s1 : s0;
+        const ShapeDev& ps = swapped ? s0 : s1;
+        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+        const Xf& tc = swapped ? t1 : t0;
+        const Xf& tp = swapped ? t0 : t1;
+        b2c_manifold* m = a.manifolds + p;
+        if (m->algorithm == 0) { m->algorithm = 2; m->body0 = bc + 1; m->body1 = bp + 1; }
+        for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+        f3 planeNormal = mk3(ps.plane[0], ps.plane[1], ps.plane[2]);
+        float planeConstant = ps.plane[3];
+        Xf planeInConvex = invMul(tc, tp);
+        Xf convexInPlane = invMul(tp, tc);
+        f3 dir = mulMV(planeInConvex.m, neg3(planeNormal));
+        AnyS shp = makeAnyS(cs, a.hullPts);
+        f3 vtx = shp.supportMargin(dir);
+        f3 vtxInPlane = xfPoint(convexInPlane, vtx);
+        float distance = dot3(planeNormal, vtxInPlane) - planeConstant;
+        f3 projected = sub3(vtxInPlane, scl3(planeNormal, distance));
+        f3 world = xfPoint(tp, projected);
+        bool has = distance < a.threshold;
+        f3 nW = mulMV(tp.m, planeNormal);
+        writeRaw(a.raw + p, pr, -1, has ? 1 : 0, nW, world, distance, 11, 0);
+        if (has) {
+            float2 m0 = a.material[b0], m1 = a.material[b1];
+            if (manifoldAdd(m, pr.x, t0, t1, nW, world, distance, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
+        }
+        if (m->num_contacts != 0) resultRefresh(m, pr.x, t0, t1, a.threshold);
+    }
+    if (added) atomicAdd(&a.ctr->contactsAdded, added);
+}
+
+// ---- GJK bins + EPA --------------------------------------------------------------------------------
+struct EpaItem {        // a pair (or pair/triangle) whose detector asked for the penetration solver
+    uint32_t pair;      // pair index
+    int meshItem;       // index into the mesh item arrays, or -1
+    GjkResult g;
+};
+
+struct GjkArgs {
+    EpaItem* epaItems;
+    uint32_t maxEpa;
+    EpaScratch* scratch;     // [epaThreads]
+    // mesh work items
+    uint32_t* meshPair;      // [maxMeshItems] pair index
+    int* meshTri;            // [maxMeshItems] triangle index
+    b2c_raw_contact* rawMesh;  // [maxMeshItems]
+    uint32_t* meshStart;     // [maxPairs] first item of a mesh pair (indexed by pair)
+    uint32_t* meshCount;     // [maxPairs]
+    uint32_t maxMeshItems;
+};
+
+// np/GjkPairDetector.java:284-312 tail once the detector result is final: emits into the manifold.
+__device__ __forceinline__ void finishConvexConvex(const NpArgs& a, uint32_t p, int2 pr, const Xf& t0, const Xf& t1, bool isValid,
+                                                   f3 normalInB, f3 pointOnB, f3 positionOffset, float distance, int method,
+                                                   int iters, uint32_t& added) {
+    b2c_manifold* m = a.manifolds + p;
+    f3 pt = add3(pointOnB, positionOffset);
+    writeRaw(a.raw + p, pr, -1, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0), isValid ? pt : mk3(0, 0, 0),
+             isValid ? distance : 0.f, method, iters);
+    if (isValid) {
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        float2 m0 = a.material[b0], m1 = a.material[b1];
+        if (manifoldAdd(m, pr.x, t0, t1, normalInB, pt, distance, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
+    }
+    resultRefresh(m, pr.x, t0, t1, a.threshold);  // ownManifold (disp/ConvexConvexAlgorithm.java:136-138)
+}
+
+template <class SA, class SB>
+__device__ __forceinline__ void gjkPairBody(const NpArgs& a, const GjkArgs& g, uint32_t p, int2 pr, const SA& A, const SB& B,
+                                            const Xf& t0, const Xf& t1, uint32_t& added, uint32_t& deep) {
+    b2c_manifold* m = a.manifolds + p;
+    if (m->algorithm == 0) { m->algorithm = 3; m->body0 = pr.x; m->body1 = pr.y; }
+    for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+    float maxd = A.margin + B.margin + a.threshold;  // disp/ConvexConvexAlgorithm.java:122-123
+    maxd *= maxd;
+    GjkResult r;
+    gjkClosestPoints(A, B, t0, t1, maxd, r);
+    if (r.needEpa) {
+        deep++;
+        uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
+        if (slot < g.maxEpa) {
+            g.epaItems[slot].pair = p;
+            g.epaItems[slot].meshItem = -1;
+            g.epaItems[slot].g = r;
+            return;
+        }
+        a.ctr->epaFailed = 0x7fffffffu;  // capacity: reported by the host as B2C_ERR_CAPACITY
+    }
+    finishConvexConvex(a, p, pr, t0, t1, r.isValid, r.normalInB, r.pointOnB, r.positionOffset, r.distance, r.lastUsedMethod,
+                       r.curIter, added);
+}
+
+// One kernel for the 8 convex-convex type pairs: the item list is ordered by type pair, so warps are
+// (almost always) uniform in the switch below.
+__global__ void __launch_bounds__(128) k_gjk(NpArgs a, GjkArgs g) {
+    const uint32_t s = a.binStart[BIN_GJK0], e = a.binStart[BIN_GJK0 + 9];
+    uint32_t added = 0, deep = 0, checks = 0;
+    for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
+        uint32_t p = a.items[it];
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
+        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+        checks++;
+        BoxS bx0, bx1; SphereS sp0, sp1; HullS h0, h1;
+        bx0.h = mk3(s0.dims[0], s0.dims[1], s0.dims[2]); bx0.margin = s0.margin;
+        bx1.h = mk3(s1.dims[0], s1.dims[1], s1.dims[2]); bx1.margin = s1.margin;
+        sp0.margin = s0.margin; sp1.margin = s1.margin;
+        h0.pts = a.hullPts + s0.pointOffset; h0.n = s0.numPoints; h0.margin = s0.margin;
+        h1.pts = a.hullPts + s1.pointOffset; h1.n = s1.numPoints; h1.margin = s1.margin;
+        switch (s0.type * 3 + s1.type) {
+        case 0: gjkPairBody(a, g, p, pr, bx0, bx1, t0, t1, added, deep); break;
+        case 1: gjkPairBody(a, g, p, pr, bx0, sp1, t0, t1, added, deep); break;
+        case 2: gjkPairBody(a, g, p, pr, bx0, h1, t0, t1, added, deep); break;
+        case 3: gjkPairBody(a, g, p, pr, sp0, bx1, t0, t1, added, deep); break;
+        case 5: gjkPairBody(a, g, p, pr, sp0, h1, t0, t1, added, deep); break;
+        case 6: gjkPairBody(a, g, p, pr, h0, bx1, t0, t1, added, deep); break;
+        case 7: gjkPairBody(a, g, p, pr, h0, sp1, t0, t1, added, deep); break;
+        case 8: gjkPairBody(a, g, p, pr, h0, h1, t0, t1, added, deep); break;
+        default: break;
+        }
+    }
+    if (added) atomicAdd(&a.ctr->contactsAdded, added);
+    if (deep) atomicAdd(&a.ctr->deepChecks, deep);
+    if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
+}
+
+// ---- convex vs BvhTriangleMeshShape ------------------------------------------------------------------
+// sh/OptimizedBvh.java:1038-1056 quantizeWithClamp (round-to-nearest for both min and max)
+__device__ __forceinline__ void quantizeClamp(const MeshDev& md, f3 pt, uint32_t q[3]) {
+    f3 c = mk3(jminf(jmaxf(pt.x, md.qmin[0]), md.qmax[0]), jminf(jmaxf(pt.y, md.qmin[1]), md.qmax[1]),
+               jminf(jmaxf(pt.z, md.qmin[2]), md.qmax[2]));
+    f3 v = mk3((c.x - md.qmin[0]) * md.quant[0], (c.y - md.qmin[1]) * md.quant[1], (c.z - md.qmin[2]) * md.quant[2]);
+    q[0] = (uint32_t)__float2int_rz(v.x + 0.5f) & 0xFFFFu;
+    q[1] = (uint32_t)__float2int_rz(v.y + 0.5f) & 0xFFFFu;
+    q[2] = (uint32_t)__float2int_rz(v.z + 0.5f) & 0xFFFFu;
+}
+
+// convex shape AABB in mesh space (disp/ConvexTriangleCallback.java:83-106) — same float sequences as
+// the world-space AABBs in broadphase.cuh, restated here to keep this header self-contained.
+__device__ __forceinline__ void convexAabbIn(const ShapeDev& s, const Xf& t, f3& mn, f3& mx) {
+    if (s.type == SH_SPHERE) {
+        f3 e = mk3(s.margin, s.margin, s.margin);
+        mn = sub3(t.o, e);
+        mx = add3(t.o, e);
+        return;
+    }
+    f3 he, c;
+    if (s.type == SH_BOX) {
+        he = mk3(s.dims[0] + s.margin, s.dims[1] + s.margin, s.dims[2] + s.margin);
+        c = t.o;
+    } else {
+        f3 lmin = mk3(s.aabbMin[0], s.aabbMin[1], s.aabbMin[2]), lmax = mk3(s.aabbMax[0], s.aabbMax[1], s.aabbMax[2]);
+        he = scl3(sub3(lmax, lmin), 0.5f);
+        he = mk3(he.x + s.margin, he.y + s.margin, he.z + s.margin);
+        c = xfPoint(t, scl3(add3(lmax, lmin), 0.5f));
+    }
+    f3 ext = mk3(dot3(mk3(fabsf(t.m[0][0]), fabsf(t.m[0][1]), fabsf(t.m[0][2])), he),
+                 dot3(mk3(fabsf(t.m[1][0]), fabsf(t.m[1][1]), fabsf(t.m[1][2])), he),
+                 dot3(mk3(fabsf(t.m[2][0]), fabsf(t.m[2][1]), fabsf(t.m[2][2])), he));
+    mn = sub3(c, ext);
+    mx = add3(c, ext);
+}
+
+// sh/OptimizedBvh.java:940-997 walkStacklessQuantizedTree; calls f(triIndex) for each overlapping leaf in
+// array order (the order the reference folds contacts in).
+template <class F>
+__device__ __forceinline__ uint32_t walkBvh(const MeshDev& md, const uint32_t qmin[3], const uint32_t qmax[3], F f) {
+    int cur = 0;
+    uint32_t visited = 0;
+    const int end = md.numNodes;
+    while (cur < end) {
+        int4 nd = __ldg(md.nodes + cur);
+        visited++;
+        uint32_t nminx = (uint32_t)nd.x & 0xFFFFu, nminy = ((uint32_t)nd.x >> 16) & 0xFFFFu, nminz = (uint32_t)nd.y & 0xFFFFu;
+        uint32_t nmaxx = ((uint32_t)nd.y >> 16) & 0xFFFFu, nmaxy = (uint32_t)nd.z & 0xFFFFu, nmaxz = ((uint32_t)nd.z >> 16) & 0xFFFFu;
+        bool overlap = !(qmin[0] > nmaxx || qmax[0] < nminx) && !(qmin[2] > nmaxz || qmax[2] < nminz) &&
+                       !(qmin[1] > nmaxy || qmax[1] < nminy);
+        bool leaf = nd.w >= 0;
+        if (leaf && overlap) f(nd.w & 0x1FFFFF);  // 21-bit triangle index (sh/QuantizedBvhNodes.java:194-198)
+        if (overlap || leaf) cur++;
+        else cur += -nd.w;
+    }
+    return visited;
+}
+
+__global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
+    const uint32_t s = a.binStart[BIN_MESH], e = a.binStart[BIN_MESH + 1];
+    for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
+        uint32_t p = a.items[it];
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
+        bool swapped = (s0.type == SH_MESH);
+        int bc = swapped ? b1 : b0, bt = swapped ? b0 : b1;
+        const ShapeDev& cs = swapped ? s1 : s0;
+        const ShapeDev& ms = swapped ? s0 : s1;
+        Xf tc = loadXf(a.xf4, bc), tt = loadXf(a.xf4, bt);
+        b2c_manifold* m = a.manifolds + p;
+        m->algorithm = 4;
+        m->body0 = bc + 1; m->body1 = bt + 1;  // manifoldPtr.setBodies(convexBody, triBody)
+        for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+        MeshDev md = a.meshes[ms.mesh];
+        Xf convexInTri = invMul(tt, tc);
+        f3 mn, mx;
+        convexAabbIn(cs, convexInTri, mn, mx);
+        f3 extra = mk3(ms.margin, ms.margin, ms.margin);
+        mx = add3(mx, extra);
+        mn = sub3(mn, extra);
+        uint32_t qmin[3], qmax[3];
+        quantizeClamp(md, mn, qmin);
+        quantizeClamp(md, mx, qmax);
+        uint32_t count = 0;
+        walkBvh(md, qmin, qmax, [&](int) { count++; });
+        uint32_t start = atomicAdd(&a.ctr->meshItems, count);
+        if (start + count > g.maxMeshItems) {
+            a.ctr->meshOverflow = 1;
+            g.meshStart[p] = 0;
+            g.meshCount[p] = 0;
+            continue;
+        }
+        g.meshStart[p] = start;
+        g.meshCount[p] = count;
+        uint32_t k = start;
+        walkBvh(md, qmin, qmax, [&](int tri) { g.meshPair[k] = p; g.meshTri[k] = tri; k++; });
+    }
+}
+
+__device__ __forceinline__ TriS loadTri(const MeshDev& md, int tri, float margin) {
+    TriS t;
+    int i0 = __ldg(md.idx + 3 * tri), i1 = __ldg(md.idx + 3 * tri + 1), i2 = __ldg(md.idx + 3 * tri + 2);
+    t.a = mk3(__ldg(md.verts + 3 * i0), __ldg(md.verts + 3 * i0 + 1), __ldg(md.verts + 3 * i0 + 2));
+    t.b = mk3(__ldg(md.verts + 3 * i1), __ldg(md.verts + 3 * i1 + 1), __ldg(md.verts + 3 * i1 + 2));
+    t.c = mk3(__ldg(md.verts + 3 * i2), __ldg(md.verts + 3 * i2 + 1), __ldg(md.verts + 3 * i2 + 2));
+    t.margin = margin;
+    return t;
+}
+
+// one thread per (pair, triangle): ConvexConvexAlgorithm on (convex, TriangleShape) with the shared manifold
+__global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g) {
+    uint32_t nItems = a.ctr->meshItems < g.maxMeshItems ? a.ctr->meshItems : g.maxMeshItems;
+    if (a.ctr->meshOverflow) nItems = 0;
+    uint32_t deep = 0, checks = 0;
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nItems; it += gridDim.x * blockDim.x) {
+        uint32_t p = g.meshPair[it];
+        int tri = g.meshTri[it];
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
+        bool swapped = (s0.type == SH_MESH);
+        int bc = swapped ? b1 : b0, bt = swapped ? b0 : b1;
+        const ShapeDev& cs = swapped ? s1 : s0;
+        const ShapeDev& ms = swapped ? s0 : s1;
+        Xf tc = loadXf(a.xf4, bc), tt = loadXf(a.xf4, bt);
+        const MeshDev& md = a.meshes[ms.mesh];
+        TriS T = loadTri(md, tri, ms.margin);
+        float maxd = cs.margin + ms.margin + a.threshold;
+        maxd *= maxd;
+        GjkResult r;
+        checks++;
+        if (cs.type == SH_BOX) { BoxS A; A.h = mk3(cs.dims[0], cs.dims[1], cs.dims[2]); A.margin = cs.margin; gjkClosestPoints(A, T, tc, tt, maxd, r); }
+        else if (cs.type == SH_SPHERE) { SphereS A; A.margin = cs.margin; gjkClosestPoints(A, T, tc, tt, maxd, r); }
+        else { HullS A; A.pts = a.hullPts + cs.pointOffset; A.n = cs.numPoints; A.margin = cs.margin; gjkClosestPoints(A, T, tc, tt, maxd, r); }
+        b2c_raw_contact* rw = g.rawMesh + it;
+        if (r.needEpa) {
+            deep++;
+            uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
+            if (slot < g.maxEpa) {
+                g.epaItems[slot].pair = p;
+                g.epaItems[slot].meshItem = (int)it;
+                g.epaItems[slot].g = r;
+                rw->has_contact = -2;  // pending
+                continue;
+            }
+            a.ctr->epaFailed = 0x7fffffffu;
+        }
+        f3 pt = add3(r.pointOnB, r.positionOffset);
+        writeRaw(rw, pr, tri, r.isValid ? 1 : 0, r.isValid ? r.normalInB : mk3(0, 0, 0), r.isValid ? pt : mk3(0, 0, 0),
+                 r.isValid ? r.distance : 0.f, r.lastUsedMethod, r.curIter);
+    }
+    if (deep) atomicAdd(&a.ctr->deepChecks, deep);
+    if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
+}
+
+// EPA bin: finishes np/GjkPairDetector.java:265-303 for the pairs that asked for it.
+__global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
+    uint32_t nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
+    EpaScratch* scratch = g.scratch + (blockIdx.x * blockDim.x + threadIdx.x);
+    uint32_t added = 0, failed = 0;
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nItems; it += gridDim.x * blockDim.x) {
+        EpaItem item = g.epaItems[it];
+        uint32_t p = item.pair;
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
+        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+        AnyS A, B;
+        Xf ta, tb;
+        int tri = -1;
+        if (item.meshItem >= 0) {
+            bool swapped = (s0.type == SH_MESH);
+            const ShapeDev& cs = swapped ? s1 : s0;
+            const ShapeDev& ms = swapped ? s0 : s1;
+            ta = swapped ? t1 : t0;
+            tb = swapped ? t0 : t1;
+            tri = g.meshTri[item.meshItem];
+            TriS T = loadTri(a.meshes[ms.mesh], tri, ms.margin);
+            A = makeAnyS(cs, a.hullPts);
+            B.type = SH_TRIANGLE; B.h = mk3(0, 0, 0); B.ta = T.a; B.tb = T.b; B.tc = T.c; B.pts = nullptr; B.n = 0; B.margin = ms.margin;
+        } else {
+            A = makeAnyS(s0, a.hullPts);
+            B = makeAnyS(s1, a.hullPts);
+            ta = t0; tb = t1;
+        }
+        GjkResult r = item.g;
+        Xf la = ta, lb = tb;
+        la.o = sub3(ta.o, r.positionOffset);
+        lb.o = sub3(tb.o, r.positionOffset);
+        f3 wA, wB;
+        bool epaFail = false;
+        bool ok = epaPenetration(A, B, la, lb, scratch, wA, wB, epaFail);
+        if (epaFail) failed++;
+        bool isValid = r.isValid;
+        float distance = r.distance;
+        f3 pointOnB = r.pointOnB, normalInB = r.normalInB;
+        int method = r.lastUsedMethod;
+        if (ok) {
+            f3 nrm = sub3(wB, wA);
+            float lenSqr = len2_3(nrm);
+            if (lenSqr > (B2C_FLT_EPSILON * B2C_FLT_EPSILON)) {
+                nrm = scl3(nrm, 1.f / jsqrtf(lenSqr));
+                float distance2 = -len3(sub3(wA, wB));
+                if (!isValid || (distance2 < distance)) {
+                    distance = distance2;
+                    pointOnB = wB;
+                    normalInB = nrm;
+                    isValid = true;
+                    method = 3;
+                }
+            } else {
+                method = 4;
+            }
+        } else {
+            method = 5;
+        }
+        if (item.meshItem >= 0) {
+            f3 pt = add3(pointOnB, r.positionOffset);
+            writeRaw(g.rawMesh + item.meshItem, pr, tri, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0),
+                     isValid ? pt : mk3(0, 0, 0), isValid ? distance : 0.f, method, r.curIter);
+        } else {
+            finishConvexConvex(a, p, pr, t0, t1, isValid, normalInB, pointOnB, r.positionOffset, distance, method, r.curIter, added);
+        }
+    }
+    if (added) atomicAdd(&a.ctr->contactsAdded, added);
+    if (failed) atomicAdd(&a.ctr->epaFailed, failed);
+}
+
+// per mesh pair: fold the per-triangle contacts into the shared manifold in BVH order, then one refresh
+// (disp/ConvexTriangleCallback.java:160-169, disp/ConvexConcaveCollisionAlgorithm.java:89)
+__global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
+    const uint32_t s = a.binStart[BIN_MESH], e = a.binStart[BIN_MESH + 1];
+    uint32_t added = 0;
+    for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
+        uint32_t p = a.items[it];
+        int2 pr = a.pairs[p];
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+        b2c_manifold* m = a.manifolds + p;
+        float2 m0 = a.material[b0], m1 = a.material[b1];
+        float fr = combinedFriction(m0.x, m1.x), re = m0.y * m1.y;
+        uint32_t st = g.meshStart[p], cn = g.meshCount[p];
+        for (uint32_t k = st; k < st + cn; k++) {
+            const b2c_raw_contact* r = g.rawMesh + k;
+            if (r->has_contact == 1) {
+                if (manifoldAdd(m, pr.x, t0, t1, mk3(r->normal[0], r->normal[1], r->normal[2]), mk3(r->point[0], r->point[1], r->point[2]),
+                                r->depth, a.threshold, fr, re, 0, r->tri))
+                    added++;
+            }
+        }
+        resultRefresh(m, pr.x, t0, t1, a.threshold);
+        a.raw[p].has_contact = -3;  // raw records of this pair live in the mesh item array
+    }
+    if (added) atomicAdd(&a.ctr->contactsAdded, added);
+}
+
+// number of manifolds = pairs that own an algorithm with a manifold (Dispatcher.getNumManifolds)
+__global__ void __launch_bounds__(256) k_count_manifolds(NpArgs a) {
+    const uint32_t n = *a.numPairs;
+    uint32_t c = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+        if (a.manifolds[p].algorithm != 0) c++;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&a.ctr->numManifolds, c);
+}
+
+}  // namespace b2c

@@ -1,0 +1,299 @@
+// radix_sort.cuh — LSD radix sort for the broadphase (64-bit projected-AABB keys + body index) and
+// for the canonical pair list (64-bit packed (uidA,uidB) keys).
+//
+// Design (sm_100a, HBM/L2-bound integer work, no tensor cores):
+//   * one upfront histogram kernel builds all digit histograms in a single read of the keys;
+//   * one kernel per 8-bit digit ("onesweep"): tiles are taken in ticket order, each tile ranks its
+//     keys with warp-level match-any multisplit, publishes its per-digit counts and resolves its
+//     exclusive prefix by decoupled look-back over the preceding tiles, then scatters through shared
+//     memory so global stores are coalesced runs;
+//   * a digit whose histogram has a single non-empty bin is skipped on the device (no host sync):
+//     every pass kernel derives the current ping-pong side from the skip flags of the passes before it.
+// The sort is stable, which the sweep relies on for its tie-break by sorted position.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2c {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_MAX_PASSES = 8;
+constexpr uint32_t RS_FLAG_AGG = 1u << 30;
+constexpr uint32_t RS_FLAG_INC = 2u << 30;
+constexpr uint32_t RS_VAL_MASK = (1u << 30) - 1;
+
+struct RadixState {
+    uint32_t hist[RS_MAX_PASSES][256];  // after rs_scan: exclusive digit offsets
+    uint32_t skip[RS_MAX_PASSES];       // 1 = digit is constant over all keys, pass is the identity
+    uint32_t ticket[RS_MAX_PASSES];     // dynamic tile ids
+    uint32_t n;                         // number of keys (device-resident so it can come from a counter)
+    uint32_t pad[7];
+};
+
+__global__ void rs_reset(RadixState* st, uint32_t* status, size_t statusWords, const uint32_t* nPtr, uint32_t nConst,
+                         uint32_t nCap) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = i; j < RS_MAX_PASSES * 256; j += stride) (&st->hist[0][0])[j] = 0;
+    if (i < RS_MAX_PASSES) { st->skip[i] = 0; st->ticket[i] = 0; }
+    if (i == 0) {
+        uint32_t n = nPtr ? *nPtr : nConst;
+        st->n = n < nCap ? n : nCap;
+    }
+    for (; i < statusWords; i += stride) status[i] = 0;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist(const K* __restrict__ keys, RadixState* st, int npass) {
+    __shared__ uint32_t sh[RS_MAX_PASSES][256];
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += RS_THREADS) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t n = st->n;
+    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) {
+        K k = keys[i];
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; p++)
+            if (p < npass) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) {
+        uint32_t v = (&sh[0][0])[i];
+        if (v) atomicAdd(&(&st->hist[0][0])[i], v);
+    }
+}
+
+// one block per pass: exclusive scan of the 256 bins, and the skip flag
+__global__ void __launch_bounds__(256) rs_scan(RadixState* st) {
+    __shared__ uint32_t s[256];
+    __shared__ uint32_t anyFull;
+    const int p = blockIdx.x;
+    const uint32_t n = st->n;
+    uint32_t v = st->hist[p][threadIdx.x];
+    if (threadIdx.x == 0) anyFull = 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    if (v == n) anyFull = 1;  // covers n == 0 as well
+    for (int off = 1; off < 256; off <<= 1) {
+        uint32_t t = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    st->hist[p][threadIdx.x] = s[threadIdx.x] - v;
+    if (threadIdx.x == 0) st->skip[p] = anyFull;
+}
+
+__device__ __forceinline__ uint32_t rs_load_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rs_store_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Which ping-pong side holds the data before pass p.
+__device__ __forceinline__ int rs_side_before(const RadixState* st, int p) {
+    int side = 0;
+    for (int q = 0; q < p; q++) side ^= (st->skip[q] ? 0 : 1);
+    return side;
+}
+
+template <typename K, bool HAS_VAL, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_pass(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, RadixState* st, uint32_t* status /*[numTiles][256]*/,
+        int pass) {
+    constexpr int TILE = RS_THREADS * ITEMS;
+    if (st->skip[pass]) return;
+    const uint32_t n = st->n;
+    const uint32_t numTiles = (n + TILE - 1) / TILE;
+    const int side = rs_side_before(st, pass);
+    const K* __restrict__ src = side ? keys1 : keys0;
+    K* __restrict__ dst = side ? keys0 : keys1;
+    const uint32_t* __restrict__ vsrc = side ? vals1 : vals0;
+    uint32_t* __restrict__ vdst = side ? vals0 : vals1;
+
+    __shared__ uint32_t warpCnt[RS_WARPS][256];
+    __shared__ uint32_t digitBase[256];   // global destination of the first key of digit d in this tile
+    __shared__ uint32_t digitLocal[256];  // exclusive scan of tile counts (position inside the sorted tile)
+    __shared__ uint32_t sTile;
+    extern __shared__ __align__(16) unsigned char dynsmem[];
+    K* skeys = reinterpret_cast<K*>(dynsmem);
+    uint32_t* svals = reinterpret_cast<uint32_t*>(dynsmem + sizeof(K) * TILE);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltmask = (1u << lane) - 1u;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTile = atomicAdd(&st->ticket[pass], 1u);
+        for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warpCnt[0][0])[i] = 0;
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if (tile >= numTiles) return;
+        const uint32_t tileStart = tile * TILE;
+
+        K key[ITEMS];
+        uint32_t val[ITEMS];
+        uint32_t rank[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            uint32_t idx = tileStart + warp * (ITEMS * 32) + k * 32 + lane;
+            bool valid = idx < n;
+            key[k] = valid ? src[idx] : (K)0;
+            if (HAS_VAL) val[k] = valid ? vsrc[idx] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            uint32_t idx = tileStart + warp * (ITEMS * 32) + k * 32 + lane;
+            bool valid = idx < n;
+            uint32_t d = (uint32_t)(key[k] >> (8 * pass)) & 255u;
+            uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (0x100u + lane));
+            uint32_t lower = __popc(m & ltmask);
+            uint32_t pre = 0;
+            if (valid && lower == 0) {
+                pre = warpCnt[warp][d];
+                warpCnt[warp][d] = pre + __popc(m);
+            }
+            __syncwarp();
+            pre = __shfl_sync(0xffffffffu, pre, __ffs(m) - 1);
+            rank[k] = pre + lower;
+        }
+        __syncthreads();
+        // per digit: exclusive scan over warps, tile count
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = warpCnt[w][d];
+            warpCnt[w][d] = run;
+            run += c;
+        }
+        const uint32_t tileCount = run;
+        // publish and look back
+        uint32_t* myStatus = status + (size_t)tile * 256 + d;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            rs_store_release(myStatus, tileCount | RS_FLAG_INC);
+        } else {
+            rs_store_release(myStatus, tileCount | RS_FLAG_AGG);
+            int t = (int)tile - 1;
+            while (t >= 0) {
+                uint32_t s = rs_load_acquire(status + (size_t)t * 256 + d);
+                uint32_t f = s & ~RS_VAL_MASK;
+                if (f == 0) continue;  // not yet published; earlier tickets are always running or done
+                excl += s & RS_VAL_MASK;
+                if (f == RS_FLAG_INC) break;
+                t--;
+            }
+            rs_store_release(myStatus, (excl + tileCount) | RS_FLAG_INC);
+        }
+        // exclusive scan of tileCount over digits -> digitLocal
+        digitLocal[d] = tileCount;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            uint32_t tv = d >= off ? digitLocal[d - off] : 0;
+            __syncthreads();
+            digitLocal[d] += tv;
+            __syncthreads();
+        }
+        const uint32_t localExcl = digitLocal[d] - tileCount;
+        __syncthreads();
+        digitLocal[d] = localExcl;
+        digitBase[d] = st->hist[pass][d] + excl - localExcl;
+        __syncthreads();
+        // place keys in tile-sorted order in shared memory
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            uint32_t idx = tileStart + warp * (ITEMS * 32) + k * 32 + lane;
+            if (idx < n) {
+                uint32_t dk = (uint32_t)(key[k] >> (8 * pass)) & 255u;
+                uint32_t lp = digitLocal[dk] + warpCnt[warp][dk] + rank[k];
+                skeys[lp] = key[k];
+                if (HAS_VAL) svals[lp] = val[k];
+            }
+        }
+        __syncthreads();
+        const uint32_t tileN = min((uint32_t)TILE, n - tileStart);
+        for (uint32_t i = threadIdx.x; i < tileN; i += RS_THREADS) {
+            K kk = skeys[i];
+            uint32_t dk = (uint32_t)(kk >> (8 * pass)) & 255u;
+            uint32_t pos = digitBase[dk] + i;
+            dst[pos] = kk;
+            if (HAS_VAL) vdst[pos] = svals[i];
+        }
+    }
+}
+
+// After all passes: which side holds the sorted data (written to *sideOut) — consumers read it on device.
+__global__ void rs_final_side(const RadixState* st, int npass, uint32_t* sideOut) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *sideOut = (uint32_t)rs_side_before(st, npass);
+}
+
+struct RadixSorter {
+    RadixState* st = nullptr;
+    uint32_t* status = nullptr;
+    size_t statusWordsPerPass = 0;
+    uint32_t capacity = 0;
+    int items = 4;
+    int launches = 0;
+
+    static int pickItems(uint32_t cap) { return cap >= 148u * 2u * 4096u ? 16 : 4; }
+
+    cudaError_t init(uint32_t cap) {
+        capacity = cap;
+        items = pickItems(cap);
+        uint32_t tile = RS_THREADS * items;
+        uint32_t numTiles = (cap + tile - 1) / tile + 1;
+        statusWordsPerPass = (size_t)numTiles * 256;
+        cudaError_t e = cudaMalloc(&st, sizeof(RadixState));
+        if (e != cudaSuccess) return e;
+        return cudaMalloc(&status, statusWordsPerPass * RS_MAX_PASSES * sizeof(uint32_t));
+    }
+    void destroy() {
+        cudaFree(st);
+        cudaFree(status);
+        st = nullptr;
+        status = nullptr;
+    }
+
+    // Sort n keys (n read from *nPtr on the device if nPtr != null, else nConst).  keyBits bounds the
+    // significant bits.  The sorted data ends in side *sideOut (0: keys0/vals0, 1: keys1/vals1).
+    template <typename K, bool HAS_VAL>
+    void sort(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, const uint32_t* nPtr, uint32_t nConst, int keyBits,
+              uint32_t* sideOut, cudaStream_t s) {
+        int npass = (keyBits + 7) / 8;
+        if (npass < 1) npass = 1;
+        if (npass > RS_MAX_PASSES) npass = RS_MAX_PASSES;
+        const uint32_t tile = RS_THREADS * items;
+        const uint32_t maxTiles = (capacity + tile - 1) / tile;
+        size_t words = statusWordsPerPass * npass;
+        rs_reset<<<(unsigned)((words + 255) / 256 < 1024 ? (words + 255) / 256 : 1024), 256, 0, s>>>(st, status, words, nPtr,
+                                                                                                     nConst, capacity);
+        uint32_t nUpper = nPtr ? capacity : (nConst < capacity ? nConst : capacity);
+        unsigned hgrid = (nUpper + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
+        if (hgrid < 1) hgrid = 1;
+        if (hgrid > 148 * 4) hgrid = 148 * 4;
+        rs_hist<K><<<hgrid, RS_THREADS, 0, s>>>(keys0, st, npass);
+        rs_scan<<<npass, 256, 0, s>>>(st);
+        unsigned pgrid = (nUpper + tile - 1) / tile;
+        if (pgrid < 1) pgrid = 1;
+        if (pgrid > maxTiles) pgrid = maxTiles ? maxTiles : 1;
+        if (pgrid > 148 * 4) pgrid = 148 * 4;
+        size_t dyn = (sizeof(K) + (HAS_VAL ? 4 : 0)) * tile;
+        for (int p = 0; p < npass; p++) {
+            uint32_t* stp = status + statusWordsPerPass * p;
+            if (items == 16) {
+                cudaFuncSetAttribute(rs_pass<K, HAS_VAL, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+                rs_pass<K, HAS_VAL, 16><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
+            } else {
+                rs_pass<K, HAS_VAL, 4><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
+            }
+        }
+        rs_final_side<<<1, 32, 0, s>>>(st, npass, sideOut);
+        launches += 4 + npass;
+    }
+};
+
+}  // namespace b2c

@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's collision interfaces over the C ABI (include/b2c.h).
+
+The reference is Java and no JVM exists in this image, so this module is the test/bench host: it keeps
+the reference's names, argument meaning and call order for the path
+``CollisionWorld.performDiscreteCollisionDetection`` (disp/CollisionWorld.java:123-151):
+
+* ``GpuCollisionWorld``  ~ disp/CollisionWorld.java (addCollisionObject, updateAabbs,
+  performDiscreteCollisionDetection, getBroadphase, getDispatcher)
+* ``GpuBroadphase``      ~ bp/BroadphaseInterface.java:33-52 (createProxy, destroyProxy, setAabb,
+  calculateOverlappingPairs, getOverlappingPairCache)
+* ``GpuPairCache``       ~ bp/OverlappingPairCache.java:34-54 (getOverlappingPairArray, getNumOverlappingPairs)
+* ``GpuDispatcher``      ~ bp/Dispatcher.java:38-68 (dispatchAllCollisionPairs, getNumManifolds,
+  getManifoldByIndexInternal)
+
+All compute happens in libb2c.so; nothing here touches the oracle and nothing falls back to the CPU.
+The Java shim a maintainer would add (Panama FFM) is in java/ and INTEGRATION.md.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2CError, Config, MANIFOLD_DTYPE, RAW_DTYPE, Stats
+
+TIGHT, DBVT = 0, 1
+DEFAULT_FILTER, STATIC_FILTER, ALL_FILTER = 1, 2, -1  # bp/CollisionFilterGroups.java:33-39
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def transforms_to_planes(xf):
+    """(n,12) row-major basis + origin  ->  12 SoA planes of n floats (the ABI's layout)."""
+    xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(-1, 12)
+    return np.ascontiguousarray(xf.T)
+
+
+class GpuCollisionWorld:
+    def __init__(self, mode=DBVT, max_bodies=131072, max_pairs=2 << 20, num_worlds=1, device=0, max_mesh_items=1 << 20,
+                 max_hull_points=1 << 20, max_shapes=4096, contact_breaking_threshold=0.02):
+        self.L = _lib.load()
+        cfg = Config()
+        self.L.b2c_default_config(C.byref(cfg))
+        cfg.device = device
+        cfg.broadphase_mode = mode
+        cfg.max_bodies = max_bodies
+        cfg.max_pairs = max_pairs
+        cfg.num_worlds = num_worlds
+        cfg.max_mesh_items = max_mesh_items
+        cfg.max_hull_points = max_hull_points
+        cfg.max_shapes = max_shapes
+        cfg.contact_breaking_threshold = contact_breaking_threshold
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.L.b2c_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise B2CError(rc, "b2c_create failed (no sm_100 device? there is no CPU fallback)")
+        self.h = h
+        self.num_bodies = 0
+        self._broadphase = GpuBroadphase(self)
+        self._dispatcher = GpuDispatcher(self)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b2c_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise B2CError(rc, self.L.b2c_last_error_string(self.h).decode())
+
+    # ---- shapes (constructors of sh/*Shape.java) ----
+    def BoxShape(self, half_extents, margin=-1.0):
+        he = np.asarray(half_extents, dtype=np.float32)
+        out = C.c_int32()
+        self._ck(self.L.b2c_shape_register_box(self.h, _vp(he), margin, C.byref(out)))
+        return out.value
+
+    def SphereShape(self, radius):
+        out = C.c_int32()
+        self._ck(self.L.b2c_shape_register_sphere(self.h, radius, C.byref(out)))
+        return out.value
+
+    def ConvexHullShape(self, points, margin=-1.0):
+        p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        out = C.c_int32()
+        self._ck(self.L.b2c_shape_register_hull(self.h, _vp(p), len(p), margin, C.byref(out)))
+        return out.value
+
+    def StaticPlaneShape(self, normal, constant):
+        n = np.asarray(normal, dtype=np.float32)
+        out = C.c_int32()
+        self._ck(self.L.b2c_shape_register_plane(self.h, _vp(n), constant, C.byref(out)))
+        return out.value
+
+    def BvhTriangleMeshShape(self, vertices, indices, scaling=(1.0, 1.0, 1.0)):
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        i = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        s = np.asarray(scaling, dtype=np.float32)
+        out = C.c_int32()
+        self._ck(self.L.b2c_shape_register_mesh(self.h, _vp(v), len(v), 12, _vp(i), len(i), 12, _vp(s), C.byref(out)))
+        return out.value
+
+    def mesh_bvh(self, shape):
+        n = C.c_int32()
+        q = np.zeros(9, dtype=np.float32)
+        self._ck(self.L.b2c_mesh_get_bvh(self.h, shape, None, 0, C.byref(n), _vp(q)))
+        nodes = np.zeros((n.value, 4), dtype=np.int32)
+        self._ck(self.L.b2c_mesh_get_bvh(self.h, shape, _vp(nodes), n.value, C.byref(n), _vp(q)))
+        return nodes, q
+
+    # ---- disp/CollisionWorld.java:98-121 ----
+    def addCollisionObject(self, shape, transform12, group=DEFAULT_FILTER, mask=ALL_FILTER, static=False, world=0):
+        t = np.ascontiguousarray(transform12, dtype=np.float32)
+        out = C.c_int32()
+        self._ck(self.L.b2c_proxy_create(self.h, shape, _vp(t), group, mask, 1 if static else 0, world, C.byref(out)))
+        self.num_bodies = out.value
+        return out.value
+
+    def addCollisionObjects(self, shapes, transforms, groups=None, masks=None, static=None, worlds=None):
+        """Batched addCollisionObject: transforms (n,12)."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32)
+        n = len(shapes)
+        planes = transforms_to_planes(transforms)
+        groups = np.full(n, DEFAULT_FILTER, np.int16) if groups is None else np.ascontiguousarray(groups, dtype=np.int16)
+        masks = np.full(n, ALL_FILTER, np.int16) if masks is None else np.ascontiguousarray(masks, dtype=np.int16)
+        flags = np.zeros(n, np.int32) if static is None else np.ascontiguousarray(static, dtype=np.int32)
+        wl = None if worlds is None else np.ascontiguousarray(worlds, dtype=np.int32)
+        out = C.c_int32()
+        self._ck(self.L.b2c_proxy_create_batch(self.h, n, _vp(shapes), _vp(planes), _vp(groups), _vp(masks), _vp(flags), _vp(wl),
+                                               C.byref(out)))
+        self.num_bodies += n
+        return out.value
+
+    def removeCollisionObject(self, uid):
+        self._ck(self.L.b2c_proxy_destroy(self.h, uid))
+
+    def setMaterial(self, uid, friction, restitution):
+        self._ck(self.L.b2c_proxy_set_material(self.h, uid, friction, restitution))
+
+    # ---- per-step inputs ----
+    def setWorldTransforms(self, transforms, uids=None):
+        planes = transforms_to_planes(transforms)
+        n = planes.shape[1]
+        u = None if uids is None else np.ascontiguousarray(uids, dtype=np.int32)
+        self._ck(self.L.b2c_set_transforms(self.h, n, _vp(u), _vp(planes)))
+
+    def setWorldTransformPlanes(self, planes):
+        """planes: (12,n) float32 C-contiguous (already in the ABI's SoA layout; no host repack)."""
+        assert planes.dtype == np.float32 and planes.flags.c_contiguous and planes.shape[0] == 12
+        self._ck(self.L.b2c_set_transforms(self.h, planes.shape[1], None, _vp(planes)))
+
+    def setActivation(self, active, uids=None):
+        a = np.ascontiguousarray(active, dtype=np.uint8)
+        u = None if uids is None else np.ascontiguousarray(uids, dtype=np.int32)
+        self._ck(self.L.b2c_set_activation(self.h, len(a), _vp(u), _vp(a)))
+
+    # ---- the path ----
+    def updateAabbs(self):  # disp/CollisionWorld.java:231-245
+        self._ck(self.L.b2c_update_aabbs(self.h))
+
+    def getBroadphase(self):
+        return self._broadphase
+
+    def getPairCache(self):
+        return self._broadphase.getOverlappingPairCache()
+
+    def getDispatcher(self):
+        return self._dispatcher
+
+    def performDiscreteCollisionDetection(self):  # disp/CollisionWorld.java:123-151
+        self.updateAabbs()
+        self._broadphase.calculateOverlappingPairs(self._dispatcher)
+        self._dispatcher.dispatchAllCollisionPairs(self._broadphase.getOverlappingPairCache(), None, self._dispatcher)
+
+    def step(self, planes=None):
+        """One fused b2c_step: (pairs, manifolds, contacts added)."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        n = 0 if planes is None else planes.shape[1]
+        self._ck(self.L.b2c_step(self.h, n, _vp(planes), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def step_device(self):
+        self._ck(self.L.b2c_step_device(self.h))
+
+    def sync_counts(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.L.b2c_sync_counts(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def transforms_written(self, n):
+        self._ck(self.L.b2c_transforms_written(self.h, n))
+
+    # ---- results ----
+    def aabbs(self):
+        out = np.zeros((self.num_bodies, 6), dtype=np.float32)
+        if self.num_bodies:
+            self._ck(self.L.b2c_get_aabbs(self.h, _vp(out), self.num_bodies))
+        return out
+
+    def pairs(self):
+        n = C.c_int32()
+        self._ck(self.L.b2c_get_pairs(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 2), dtype=np.int32)
+        if n.value:
+            self._ck(self.L.b2c_get_pairs(self.h, _vp(out), n.value, C.byref(n)))
+        return out
+
+    def manifolds(self, only_touching=False):
+        n = C.c_int32()
+        self._ck(self.L.b2c_get_manifolds(self.h, None, 0, int(only_touching), C.byref(n)))
+        out = np.zeros(n.value, dtype=MANIFOLD_DTYPE)
+        if n.value:
+            self._ck(self.L.b2c_get_manifolds(self.h, _vp(out), n.value, int(only_touching), C.byref(n)))
+        return out
+
+    def raw_contacts(self):
+        n = C.c_int32()
+        self._ck(self.L.b2c_get_raw_contacts(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=RAW_DTYPE)
+        if n.value:
+            self._ck(self.L.b2c_get_raw_contacts(self.h, _vp(out), n.value, C.byref(n)))
+        return out
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.L.b2c_get_stats(self.h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in Stats._fields_ if f[0] != "pad"}
+
+    def stream(self):
+        return self.L.b2c_stream(self.h)
+
+
+class GpuPairCache:
+    """bp/OverlappingPairCache.java:34-54 view over the device pair list."""
+
+    def __init__(self, world):
+        self.w = world
+        self.num = 0
+
+    def getOverlappingPairArray(self):
+        return self.w.pairs()
+
+    def getNumOverlappingPairs(self):
+        return self.num
+
+
+class GpuBroadphase:
+    """bp/BroadphaseInterface.java:33-52."""
+
+    def __init__(self, world):
+        self.w = world
+        self.cache = GpuPairCache(world)
+
+    def createProxy(self, aabbMin, aabbMax, shape, transform12, group, mask, dispatcher=None, multiSapProxy=None, static=False):
+        # the reference passes the shape's AABB; the device recomputes the identical box from shape + transform
+        return self.w.addCollisionObject(shape, transform12, group, mask, static)
+
+    def destroyProxy(self, uid, dispatcher=None):
+        self.w.removeCollisionObject(uid)
+
+    def setAabb(self, uid, aabbMin, aabbMax, dispatcher=None):
+        mm = np.concatenate([np.asarray(aabbMin, np.float32), np.asarray(aabbMax, np.float32)]).reshape(6, 1)
+        u = np.asarray([uid], dtype=np.int32)
+        self.w._ck(self.w.L.b2c_set_aabbs(self.w.h, 1, _vp(u), _vp(np.ascontiguousarray(mm))))
+
+    def setAabbs(self, uids, mins, maxs):
+        mm = np.ascontiguousarray(np.concatenate([np.asarray(mins, np.float32).reshape(-1, 3).T,
+                                                  np.asarray(maxs, np.float32).reshape(-1, 3).T], axis=0))
+        u = None if uids is None else np.ascontiguousarray(uids, dtype=np.int32)
+        self.w._ck(self.w.L.b2c_set_aabbs(self.w.h, mm.shape[1], _vp(u), _vp(mm)))
+
+    def calculateOverlappingPairs(self, dispatcher=None):
+        n = C.c_int32()
+        self.w._ck(self.w.L.b2c_calculate_overlapping_pairs(self.w.h, C.byref(n)))
+        self.cache.num = n.value
+        return n.value
+
+    def getOverlappingPairCache(self):
+        return self.cache
+
+    def getBroadphaseAabb(self):
+        mn, mx = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self.w._ck(self.w.L.b2c_get_broadphase_aabb(self.w.h, _vp(mn), _vp(mx)))
+        return mn, mx
+
+
+class GpuDispatcher:
+    """bp/Dispatcher.java:38-68 (default near callback + default collision configuration)."""
+
+    def __init__(self, world):
+        self.w = world
+        self.num_manifolds = 0
+        self.num_contacts_added = 0
+        self._manifolds = None
+
+    def dispatchAllCollisionPairs(self, pairCache=None, dispatchInfo=None, dispatcher=None):
+        a, b = C.c_int32(), C.c_int32()
+        self.w._ck(self.w.L.b2c_dispatch_all_pairs(self.w.h, C.byref(a), C.byref(b)))
+        self.num_manifolds, self.num_contacts_added = a.value, b.value
+        self._manifolds = None
+
+    def getNumManifolds(self):
+        return self.num_manifolds
+
+    def getManifoldByIndexInternal(self, i):
+        if self._manifolds is None:
+            self._manifolds = self.w.manifolds()
+        return self._manifolds[i]

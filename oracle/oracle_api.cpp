@@ -66,8 +66,8 @@ void orc_mesh_get_quant(void* h, int shape, float* out9) {
     out9[6] = b.bvhQuantization.x; out9[7] = b.bvhQuantization.y; out9[8] = b.bvhQuantization.z;
 }
 
-int orc_body_create(void* h, int shape, const float* xf12, int group, int mask, int isStatic) {
-    return ((World*)h)->addBody(shape, xfFrom12(xf12), group, mask, isStatic != 0);
+int orc_body_create(void* h, int shape, const float* xf12, int group, int mask, int isStatic, int world) {
+    return ((World*)h)->addBody(shape, xfFrom12(xf12), group, mask, isStatic != 0, world);
 }
 void orc_body_destroy(void* h, int uid) { ((World*)h)->removeBody(uid); }
 int orc_num_bodies(void* h) { return (int)((World*)h)->bodies.size(); }

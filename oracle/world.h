@@ -40,6 +40,7 @@ struct Body {
     bool inFixed = false; // stage == STAGECOUNT
     int lastSetStep = -1; // step index of the last setAabb (createProxy counts as one)
     bool aabbOverflow = false;
+    int world = 0;        // batched independent worlds: each is its own CollisionWorld in the reference
 };
 
 struct RawContact {  // one detector result, before ManifoldResult
@@ -112,13 +113,14 @@ struct World {
     }
 
     // disp/CollisionWorld.java:102-121 addCollisionObject + bp/DbvtBroadphase.java:173-182 createProxy
-    int addBody(int shape, const Xf& xf, int group, int mask, bool isStatic) {
+    int addBody(int shape, const Xf& xf, int group, int mask, bool isStatic, int world = 0) {
         Body b;
         b.shape = shape;
         b.xf.set(xf);
         b.group = (int16_t)group;
         b.mask = (int16_t)mask;
         b.isStatic = isStatic;
+        b.world = world;
         b.uid = (int)bodies.size() + 1;  // ++gid
         shapeGetAabb(shapes[shape], b.xf, b.effMin, b.effMax);  // no +-threshold at creation
         b.leafMin = b.effMin; b.leafMax = b.effMax;
@@ -192,6 +194,7 @@ struct World {
     }
 
     bool filter(const Body& a, const Body& b) const {  // bp/HashedOverlappingPairCache.java:179-188
+        if (a.world != b.world) return false;  // separate worlds never share a pair cache
         bool collides = (a.group & b.mask) != 0;
         collides = collides && (b.group & a.mask) != 0;
         return collides;

@@ -43,7 +43,7 @@ def lib():
     L.orc_mesh_num_nodes.argtypes = [C.c_void_p, C.c_int]
     L.orc_mesh_get_nodes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.orc_mesh_get_quant.argtypes = [C.c_void_p, C.c_int, f32p]
-    L.orc_body_create.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int, C.c_int, C.c_int]
+    L.orc_body_create.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_body_destroy.argtypes = [C.c_void_p, C.c_int]
     L.orc_num_bodies.argtypes = [C.c_void_p]
     L.orc_set_transforms.argtypes = [C.c_void_p, C.c_int, C.c_void_p, f32p]
@@ -120,8 +120,9 @@ class OracleWorld:
         return out, q
 
     # bodies
-    def body(self, shape, xf, group=1, mask=-1, static=False):
-        return self.L.orc_body_create(self.h, shape, np.ascontiguousarray(xf, dtype=np.float32), group, mask, int(static))
+    def body(self, shape, xf, group=1, mask=-1, static=False, world=0):
+        return self.L.orc_body_create(self.h, shape, np.ascontiguousarray(xf, dtype=np.float32), int(group), int(mask),
+                                      int(static), int(world))
 
     def destroy_body(self, uid):
         self.L.orc_body_destroy(self.h, uid)
