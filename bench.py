@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — collision-phase benchmark (BASELINE.json: "collision-phase ms/step at 100k bodies; overlap
+pairs/s and contacts/s per GPU").
+
+  python bench.py --gpus N --steps K --warmup W          # our CUDA path
+  python bench.py --impl reference --steps K --warmup W   # the reference algorithm on host cores (CPU oracle port)
+
+A "step" is one performDiscreteCollisionDetection (AABB update + broadphase pairs + narrowphase + manifolds)
+over the C2 workload: 100 000 mixed boxes / spheres / 16-point hulls in a closed bin of 5 static boxes
+(tests/scenes.py:bin_scene, seeded; synthetic transform trace because the solver/integrator are not on the
+path).  N>1: one independent 100k-body world per GPU (worlds never interact -> no data-path collective,
+weak scaling); `value` is whole-job world-steps per second, `ms_per_step` the per-step device time (max over
+ranks).  One JSON line on stdout from rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FRAMES = 8  # distinct transform frames of the trace, traversed back and forth
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_scene(n_bodies, seed):
+    import scenes
+    # 49 x 49 footprint at 0.82 spacing = the 40 x 40 bin of SURVEY §8d C2
+    return scenes.bin_scene(n=n_bodies, seed=seed, footprint=max(4, int(round((n_bodies / 100000.0) ** 0.5 * 49))))
+
+
+def frame_index(step):
+    period = 2 * (FRAMES - 1)
+    k = step % period
+    return k if k < FRAMES else period - k
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(stage, N, P, st, key_passes_body, key_passes_pair, contacts):
+    """Algorithmic bytes one launch group moves.  N proxies, P pairs."""
+    G = st["gjk_checks"]
+    if stage == "aabb":
+        return N * (48 + 4 + 1 + 32)
+    if stage == "bounds_keys":
+        return N * (32 + 1) + N * (32 + 1 + 4 + 12)
+    if stage == "sort_proxies":
+        return N * 8 + key_passes_body * 2 * 12 * N
+    if stage == "gather":
+        return N * (12 + 32 + 4 + 32 + 4)
+    if stage == "sweep":
+        return 9 * N * 4 + N * 32 + 8 * P
+    if stage == "large":
+        return st["large_proxies"] * N * 32
+    if stage == "sort_pairs":
+        return P * 8 + key_passes_pair * 2 * 8 * P
+    if stage == "unpack_carry":
+        return P * (8 + 8 + 8) + 2 * (32 * P + 96 * contacts)
+    if stage == "classify_bin":
+        return P * (8 + 2 * (1 + 4 + 4) + 1 + 4) + P * (1 + 4)
+    if stage == "closed_form":
+        return 0
+    if stage == "gjk_mesh":
+        # pair 8 B + 2 transforms 96 B + 2 shape records 128 B + manifold header r/w 64 B + raw record 56 B
+        return G * (8 + 96 + 128 + 64 + 56) + 96 * contacts * 2
+    if stage == "epa_fold_count":
+        return st["deep_penetration_checks"] * (120 + 96 + 128 + 56) + P * 8
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ngpu = args.gpus
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    pkg = ge.load_package()
+    L = pkg._lib.load()
+    if L.b2c_device_count() < 1:
+        raise SystemExit("no sm_100 device: the CUDA path cannot run and there is no CPU fallback")
+
+    N = args.bodies
+    t0 = time.time()
+    sc = make_scene(N, seed=100 + rank)
+    import scenes
+    gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=args.max_pairs, device=dev)
+    nb = sc.n
+    frames = [np.ascontiguousarray(pkg.transforms_to_planes(sc.transforms(k))) for k in range(FRAMES)]
+    log(f"[rank {rank}] scene built: {nb} proxies in {time.time() - t0:.1f}s")
+
+    stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
+    dframes = []
+    for f in frames:
+        t = torch.from_numpy(f).to(f"cuda:{dev}")
+        dframes.append(t)
+    hframes = [torch.from_numpy(f).pin_memory() for f in frames]
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=f"cuda:{dev}")  # 192 MiB > 126 MB L2
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: `value` ----------------
+    gw.set_profiling(True)
+    step_no = 0
+    for _ in range(args.warmup):
+        gw.setWorldTransformsDevice(nb, dframes[frame_index(step_no)].data_ptr())
+        gw.step_device()
+        gw.sync_counts()
+        step_no += 1
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stage_sum = {}
+    pairs_tot = contacts_tot = manif_tot = 0
+    launches = 0
+    st = None
+    barrier()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(float(k))  # L2 flush between timed iterations (not timed)
+            # inputs already resident in HBM: the frame is a device tensor
+            ev0[k].record(stream)
+        gw.setWorldTransformsDevice(nb, dframes[frame_index(step_no)].data_ptr())
+        gw.step_device()
+        with torch.cuda.stream(stream):
+            ev1[k].record(stream)
+        p, m, c = gw.sync_counts()
+        pairs_tot += p; manif_tot += m; contacts_tot += c
+        st = gw.stats()
+        launches += st["kernel_launches"]
+        for nm, ms in gw.stage_times().items():
+            stage_sum[nm] = stage_sum.get(nm, 0.0) + ms
+        step_no += 1
+    barrier()
+    ms_steps = [ev0[k].elapsed_time(ev1[k]) for k in range(args.steps)]
+    ms_per_step = float(np.mean(ms_steps))
+
+    # ---------------- end-to-end arm through the C ABI with HOST buffers: `e2e` ----------------
+    P_cap = args.max_pairs
+    pairs_host = torch.empty((P_cap, 2), dtype=torch.int32).pin_memory()
+    hdr_host = torch.empty((P_cap, 8), dtype=torch.int32).pin_memory()
+    pts_host = torch.empty((2 * P_cap, 24), dtype=torch.int32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    nP, nH, nPt = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    e2e_ms = []
+    d2h = 0
+    barrier()
+    for k in range(e2e_steps + 2):
+        with torch.cuda.stream(stream):
+            flush.fill_(float(k))
+        torch.cuda.synchronize()
+        t_start = time.perf_counter()
+        gw.setWorldTransformsHostPtr(nb, hframes[frame_index(step_no)].data_ptr())       # H2D of this step's inputs
+        gw.step_device()
+        gw.sync_counts()
+        gw._ck(L.b2c_get_pairs(gw.h, ctypes.c_void_p(pairs_host.data_ptr()), P_cap, ctypes.byref(nP)))   # D2H pair list
+        gw._ck(L.b2c_get_contacts(gw.h, ctypes.c_void_p(hdr_host.data_ptr()), P_cap, ctypes.c_void_p(pts_host.data_ptr()),
+                                  2 * P_cap, ctypes.byref(nH), ctypes.byref(nPt)))        # D2H contact stream
+        t_end = time.perf_counter()
+        step_no += 1
+        if k >= 2:
+            e2e_ms.append((t_end - t_start) * 1e3)
+            d2h = nP.value * 8 + nH.value * 32 + nPt.value * 96 + 128
+    barrier()
+    e2e_ms_per_step = float(np.mean(e2e_ms))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- reduce over ranks ----------------
+    vals = torch.tensor([ms_per_step, e2e_ms_per_step], dtype=torch.float64, device=f"cuda:{dev}")
+    sums = torch.tensor([pairs_tot, contacts_tot, manif_tot, launches], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_max, e2e_max = [float(x) for x in vals.tolist()]
+    pairs_all, contacts_all, manif_all, launches_all = [float(x) for x in sums.tolist()]
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    stage_ms = {k: v / args.steps for k, v in stage_sum.items()}
+    dom = max(stage_ms, key=stage_ms.get)
+    P_avg = pairs_tot / args.steps
+    contacts_live = st["num_manifolds"] and contacts_tot / args.steps
+    body_bits = 32 + int(np.ceil(np.log2(2 * nb + 66)))
+    pair_bits = 2 * int(np.ceil(np.log2(nb + 2)))
+    abytes = {s: algorithmic_bytes(s, nb, P_avg, st, (body_bits + 7) // 8, (pair_bits + 7) // 8, contacts_live) for s in stage_ms}
+    achieved = abytes[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(dom)
+    except Exception:
+        pass
+    out = {
+        "metric": "collision_phase_world_steps_per_s_100k_bodies",
+        "value": ngpu * 1000.0 / ms_max,
+        "unit": "steps/s (one step = full collision phase of a 100k-body world)",
+        "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"C2: {N} mixed boxes/spheres/16-pt hulls in a closed bin of 5 static boxes, single world per GPU, "
+                               "DbvtBroadphase pair semantics, seeded transform trace",
+                   "proxies": nb, "l2": "flushed between timed iterations (192 MiB write)",
+                   "parallelism": "1 world per GPU, no collective" if ngpu > 1 else "1 GPU"},
+        "pairs_per_s": pairs_all / args.steps / (ms_max * 1e-3),
+        "contacts_per_s": contacts_all / args.steps / (ms_max * 1e-3),
+        "pairs_per_step": pairs_all / args.steps / ngpu,
+        "contacts_added_per_step": contacts_all / args.steps / ngpu,
+        "manifolds_per_step": manif_all / args.steps / ngpu,
+        "stage_ms": {k: round(v, 5) for k, v in stage_ms.items()},
+        "gpu_launches": int(launches_all),
+        "e2e": {"value": ngpu * 1000.0 / e2e_max, "unit": "steps/s", "ms_per_step": e2e_max,
+                "h2d_bytes_per_step": nb * 48, "d2h_bytes_per_step": int(d2h),
+                "what": "b2c_set_transforms(pinned host planes) + b2c_step + b2c_get_pairs + b2c_get_contacts into pinned host buffers"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": abytes[dom],
+                     "all_stages_frac": {s: round((abytes[s] / (stage_ms[s] * 1e-3) / 1e9) / peak_gbs, 5) if stage_ms[s] > 0 else 0.0
+                                         for s in stage_ms}},
+        "clocks": clocks,
+    }
+    if ngpu == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(sc, args)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_steps(sc, n_steps, warmup=1):
+    """Time the CPU oracle (a port of the reference's algorithm; single thread like the reference's world)."""
+    import scenes
+    ow = scenes.build_oracle(sc, 1)
+    times, pairs, contacts = [], 0, 0
+    for k in range(warmup + n_steps):
+        xf = sc.transforms(frame_index(k))
+        t, p, m = ow.timed_step(xf)
+        if k >= warmup:
+            times.append(t)
+            pairs = p
+    return times, pairs
+
+
+def cpu_baseline(sc, args):
+    times, pairs = cpu_steps(sc, args.cpu_steps)
+    ms = float(np.mean(times)) * 1e3
+    return {"value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "cores": 1, "kind": "port",
+            "sample": f"{args.cpu_steps} full steps of the same {sc.n}-proxy C2 world after 1 warm-up (oracle/, g++ -O2, "
+                      "single thread: the reference steps one world on one thread)",
+            "pairs": int(pairs), "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc = make_scene(args.bodies, seed=100)
+    steps = max(1, min(args.steps, args.cpu_steps if args.cpu_steps > 0 else 4))
+    times, pairs = cpu_steps(sc, steps, warmup=min(args.warmup, 1))
+    ms = float(np.mean(times)) * 1e3
+    v = 1000.0 / ms
+    out = {
+        "impl": "reference",
+        "metric": "collision_phase_world_steps_per_s_100k_bodies", "value": v,
+        "unit": "steps/s (one step = full collision phase of a 100k-body world)",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: {args.bodies} mixed boxes/spheres/16-pt hulls in a closed bin of 5 static boxes, single world, "
+                               "DbvtBroadphase pair semantics, seeded transform trace", "proxies": sc.n},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 1, "kind": "port",
+                         "sample": f"{steps} full steps of the {sc.n}-proxy C2 world; Java reference not runnable on this box (no JVM): "
+                                   "CPU baseline is the C++ restatement in oracle/"},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bodies", type=int, default=100000)
+    ap.add_argument("--max-pairs", type=int, default=3 << 20)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

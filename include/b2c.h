@@ -153,6 +153,17 @@ typedef struct {
  * order.  only_touching != 0 skips manifolds with zero contacts. */
 int32_t b2c_get_manifolds(b2c_ctx*, b2c_manifold* out, int32_t cap, int32_t only_touching, int32_t* num_out);
 
+/* Compact contact stream for the solver: only manifolds with >= 1 contact, each a 32-byte header plus its
+ * live points (device-side compaction, two exact-size D2H copies).  Order is unspecified; match by uids. */
+typedef struct {
+    int32_t pair_uid0, pair_uid1, body0, body1;
+    int32_t num_contacts, algorithm;
+    int32_t first_point;              /* index of this manifold's first point in the point array */
+    int32_t pair_index;               /* index of the pair in the sorted pair list */
+} b2c_contact_header; /* 32 bytes */
+int32_t b2c_get_contacts(b2c_ctx*, b2c_contact_header* headers_out, int32_t cap_headers, b2c_manifold_point* points_out,
+                         int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
+
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
 typedef struct {
@@ -181,12 +192,22 @@ typedef struct {
 } b2c_stats;
 int32_t b2c_get_stats(b2c_ctx*, b2c_stats* out);
 
+/* Per-stage device times of the last b2c_step/b2c_step_device (CUDA events on the ctx stream around each
+ * kernel group).  Enable with b2c_set_profiling(ctx, 1).  Stage order: see b2c_stage_name. */
+#define B2C_NUM_STAGES 12
+int32_t b2c_set_profiling(b2c_ctx*, int32_t on);
+int32_t b2c_get_stage_times(b2c_ctx*, float ms_out[B2C_NUM_STAGES]);
+const char* b2c_stage_name(int32_t stage);
+
 /* ---- device-resident stepping for measurement and host-free pipelines ---------------------- */
 /* The ctx's CUDA stream (cudaStream_t) so a caller can time with CUDA events on the right stream. */
 void* b2c_stream(b2c_ctx*);
 /* Device pointer to the 12 transform planes (plane stride = max_bodies floats): a caller with its own
  * device-side integrator writes here and calls b2c_step_device. */
 float* b2c_device_transforms(b2c_ctx*);
+/* b2c_set_transforms with a DEVICE pointer (12 planes of n floats, plane stride n): one D2D copy on the ctx
+ * stream, for hosts whose integrator already lives on the GPU. */
+int32_t b2c_set_transforms_device(b2c_ctx*, int32_t n, const float* device_planes12);
 /* Tell the ctx that planes for bodies 1..n were written on the device through b2c_device_transforms. */
 int32_t b2c_transforms_written(b2c_ctx*, int32_t n);
 /* Enqueue one full collision step on the ctx stream using the resident transforms; does not

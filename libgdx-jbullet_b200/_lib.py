@@ -61,8 +61,15 @@ EXPORTS = [
     "b2c_proxy_set_material", "b2c_set_transforms", "b2c_set_activation", "b2c_set_aabbs", "b2c_update_aabbs",
     "b2c_calculate_overlapping_pairs", "b2c_get_pairs", "b2c_dispatch_all_pairs", "b2c_step", "b2c_get_manifolds",
     "b2c_get_raw_contacts", "b2c_get_aabbs", "b2c_get_broadphase_aabb", "b2c_get_stats", "b2c_stream",
-    "b2c_device_transforms", "b2c_transforms_written", "b2c_step_device", "b2c_sync_counts",
+    "b2c_device_transforms", "b2c_transforms_written", "b2c_step_device", "b2c_sync_counts", "b2c_get_contacts",
+    "b2c_set_profiling", "b2c_get_stage_times", "b2c_stage_name", "b2c_set_transforms_device",
 ]
+NUM_STAGES = 12
+CONTACT_HEADER_DTYPE = np.dtype([
+    ("pair_uid0", np.int32), ("pair_uid1", np.int32), ("body0", np.int32), ("body1", np.int32), ("num_contacts", np.int32),
+    ("algorithm", np.int32), ("first_point", np.int32), ("pair_index", np.int32),
+])
+assert CONTACT_HEADER_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -116,5 +123,11 @@ def load():
     L.b2c_transforms_written.argtypes = [vp, i32]
     L.b2c_step_device.argtypes = [vp]
     L.b2c_sync_counts.argtypes = [vp, pi32, pi32, pi32]
+    L.b2c_set_transforms_device.argtypes = [vp, i32, vp]
+    L.b2c_get_contacts.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
+    L.b2c_set_profiling.argtypes = [vp, i32]
+    L.b2c_get_stage_times.argtypes = [vp, vp]
+    L.b2c_stage_name.argtypes = [i32]
+    L.b2c_stage_name.restype = C.c_char_p
     _lib = L
     return L

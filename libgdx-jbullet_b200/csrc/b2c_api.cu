@@ -20,7 +20,7 @@ using namespace b2c;
 
 namespace {
 
-constexpr int EPA_GRID = 148, EPA_BLOCK = 64;
+constexpr int EPA_GRID = 148 * 8, EPA_BLOCK = 64;
 
 struct HostMesh {
     int4* nodes = nullptr;
@@ -88,10 +88,8 @@ struct b2c_ctx {
 
     // narrowphase
     b2c_raw_contact* dRaw = nullptr;
-    uint8_t* dBinOf = nullptr;
-    uint32_t* dItems = nullptr;
-    uint32_t* dBinStart = nullptr;
-    uint32_t* dBinCursor = nullptr;
+    uint32_t* dBinKeys[2] = {nullptr, nullptr};
+    RadixSorter sortBins;
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
     EpaScratch* dEpaScratch = nullptr;
@@ -106,6 +104,15 @@ struct b2c_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int launches = 0;
     int32_t lastPairs = 0, lastManifolds = 0, lastContacts = 0;
+    bool prof = false;
+    cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
+    bool stageValid = false;
+
+    // compact contact stream
+    b2c_contact_header* dContactHdr = nullptr;
+    b2c_manifold_point* dContactPts = nullptr;
+    uint32_t* dContactCounts = nullptr;
+    uint32_t capContactHdr = 0, capContactPts = 0;
 };
 
 namespace {
@@ -239,8 +246,11 @@ int32_t runAabbKernel(b2c_ctx* ctx, bool forPairs) {
     return B2C_OK;
 }
 
+static inline void mark(b2c_ctx* ctx, int k);
+
 int32_t enqueueBroadphase(b2c_ctx* ctx) {
     int n = ctx->nBodies;
+    mark(ctx, 0);
     int32_t rc = runAabbKernel(ctx, true);
     if (rc) return rc;
     ctx->cur ^= 1;
@@ -253,24 +263,31 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
         return B2C_OK;
     }
     unsigned nb = (n + 255) / 256;
+    mark(ctx, 1);
     k_bounds<<<nb, 256, 0, s>>>(ctx->B, n, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.num_worlds, ctx->maxRows, ctx->dCtr,
                                 ctx->dGrid);
     k_keys<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0]);
     int rowBits = bitsFor((uint32_t)ctx->maxRows + 2u);
+    mark(ctx, 2);
     ctx->sortBodies.launches = 0;
     ctx->sortBodies.sort<uint64_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nullptr, (uint32_t)n,
                                          32 + rowBits, ctx->dSide, s);
+    mark(ctx, 3);
     k_gather<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->dSide, ctx->dGrid,
                                 ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart);
     dim3 sg(nb, 9);
+    mark(ctx, 4);
     k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys[0],
                                (uint32_t)ctx->cfg.max_pairs, ctx->dCtr);
     dim3 lg(gridFor((uint32_t)n, 256, 64), 16);
+    mark(ctx, 5);
     k_large<<<lg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
                                ctx->uidBits, ctx->dPairKeys[0], (uint32_t)ctx->cfg.max_pairs, ctx->dCtr);
+    mark(ctx, 6);
     ctx->sortPairs.launches = 0;
     ctx->sortPairs.sort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr, &ctx->dCtr->pairCount, 0,
                                          2 * ctx->uidBits, ctx->dSide + 1, s);
+    mark(ctx, 7);
     k_pairs_unpack<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dSide + 1,
                                                                               ctx->dCtr, (uint32_t)ctx->cfg.max_pairs, ctx->uidBits,
                                                                               ctx->dPairs, ctx->dSortedKeys[cur], ctx->dNumPairs[cur]);
@@ -283,6 +300,10 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     ctx->step++;
     ctx->pairsValid = true;
     return B2C_OK;
+}
+
+static inline void mark(b2c_ctx* ctx, int k) {
+    if (ctx->prof) cudaEventRecord(ctx->stageEv[k], ctx->stream);
 }
 
 NpArgs makeNpArgs(b2c_ctx* ctx) {
@@ -298,10 +319,10 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.meshes = ctx->dMeshes;
     a.manifolds = ctx->dManifolds[ctx->cur];
     a.raw = ctx->dRaw;
-    a.binOf = ctx->dBinOf;
-    a.items = ctx->dItems;
-    a.binStart = ctx->dBinStart;
-    a.binCursor = ctx->dBinCursor;
+    a.binKeys[0] = ctx->dBinKeys[0];
+    a.binKeys[1] = ctx->dBinKeys[1];
+    a.binSide = ctx->dSide + 2;
+    a.binStart = &ctx->sortBins.st->hist[3][0];
     a.ctr = ctx->dCtr;
     a.threshold = ctx->cfg.contact_breaking_threshold;
     a.maxPairs = (uint32_t)ctx->cfg.max_pairs;
@@ -326,13 +347,19 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     g.meshCount = ctx->dMeshCount;
     g.maxMeshItems = (uint32_t)ctx->cfg.max_mesh_items;
     const unsigned pg = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
+    mark(ctx, 8);
     k_clear_np_counters<<<1, 32, 0, s>>>(ctx->dCtr);
     k_classify<<<pg, 256, 0, s>>>(a);
-    k_bin_offsets<<<1, 32, 0, s>>>(a);
-    k_bin_scatter<<<pg, 256, 0, s>>>(a);
+    // stable partition of the pair indices by bin: one radix pass over the bin digit (bits 24-31)
+    ctx->sortBins.launches = 0;
+    ctx->sortBins.sort<uint32_t, false>(ctx->dBinKeys[0], ctx->dBinKeys[1], nullptr, nullptr, ctx->dNumPairs[ctx->cur], 0, 32,
+                                        ctx->dSide + 2, s, 3);
+    ctx->launches += ctx->sortBins.launches - 2;
+    mark(ctx, 9);
     k_sphere_sphere<<<148 * 4, 256, 0, s>>>(a);
     ctx->launches += 5;
     if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, s>>>(a); ctx->launches++; }
+    mark(ctx, 10);
     k_gjk<<<148 * 8, 128, 0, s>>>(a, g);
     ctx->launches++;
     if (ctx->hasMesh) {
@@ -340,11 +367,14 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         k_gjk_tri<<<148 * 8, 128, 0, s>>>(a, g);
         ctx->launches += 2;
     }
+    mark(ctx, 11);
     k_epa<<<EPA_GRID, EPA_BLOCK, 0, s>>>(a, g);
     ctx->launches++;
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
     k_count_manifolds<<<pg, 256, 0, s>>>(a);
     ctx->launches++;
+    mark(ctx, 12);
+    ctx->stageValid = ctx->prof;
     CK(cudaGetLastError());
     return B2C_OK;
 }
@@ -468,7 +498,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         CKC(dalloc(&ctx->dNumPairs[i], (size_t)1));
         CKC(dalloc(&ctx->dManifolds[i], P));
     }
-    CKC(dalloc(&ctx->dSide, (size_t)2));
+    CKC(dalloc(&ctx->dSide, (size_t)4));
     CKC(dalloc(&ctx->dSmin, N));
     CKC(dalloc(&ctx->dSmax, N));
     CKC(dalloc(&ctx->dSrow, N));
@@ -482,10 +512,10 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     ctx->uidBits = bitsFor((uint32_t)N + 1u);
     CKC(dalloc(&ctx->dPairs, P));
     CKC(dalloc(&ctx->dRaw, P));
-    CKC(dalloc(&ctx->dBinOf, P));
-    CKC(dalloc(&ctx->dItems, P));
-    CKC(dalloc(&ctx->dBinStart, (size_t)32));
-    CKC(dalloc(&ctx->dBinCursor, (size_t)32));
+    if (P > (size_t)(1u << 24)) return fail(B2C_ERR_BAD_ARG);  // pair index must fit 24 bits next to the bin byte
+    CKC(dalloc(&ctx->dBinKeys[0], P));
+    CKC(dalloc(&ctx->dBinKeys[1], P));
+    CKC(ctx->sortBins.init((uint32_t)P));
     ctx->maxEpa = (uint32_t)(P / 4 + 1024);
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
     CKC(dalloc(&ctx->dEpaScratch, (size_t)EPA_GRID * EPA_BLOCK));
@@ -496,6 +526,12 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dMeshStart, P));
     CKC(dalloc(&ctx->dMeshCount, P));
     for (int i = 0; i < 5; i++) CKC(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i <= B2C_NUM_STAGES; i++) CKC(cudaEventCreate(&ctx->stageEv[i]));
+    ctx->capContactHdr = (uint32_t)P;
+    ctx->capContactPts = (uint32_t)(2 * P);
+    CKC(dalloc(&ctx->dContactHdr, (size_t)ctx->capContactHdr));
+    CKC(dalloc(&ctx->dContactPts, (size_t)ctx->capContactPts));
+    CKC(dalloc(&ctx->dContactCounts, (size_t)2));
 #undef CKC
     *out = ctx;
     return B2C_OK;
@@ -518,10 +554,12 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinOf); cudaFree(ctx->dItems); cudaFree(ctx->dBinStart);
-    cudaFree(ctx->dBinCursor); cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dMeshPair);
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); ctx->sortBins.destroy();
+    cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
+    cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -896,6 +934,16 @@ int32_t b2c_dispatch_all_pairs(b2c_ctx* ctx, int32_t* numManifolds, int32_t* num
     return rc;
 }
 
+int32_t b2c_set_transforms_device(b2c_ctx* ctx, int32_t n, const float* dPlanes) {
+    if (!ctx || !dPlanes || n < 0 || n > ctx->nBodies) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpy2DAsync(ctx->dStaging, (size_t)ctx->cfg.max_bodies * sizeof(float), dPlanes, (size_t)n * sizeof(float),
+                         (size_t)n * sizeof(float), 12, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->stagingCount = n;
+    return B2C_OK;
+}
+
 int32_t b2c_transforms_written(b2c_ctx* ctx, int32_t n) {
     if (!ctx || n < 0 || n > ctx->nBodies) return B2C_ERR_BAD_ARG;
     ctx->stagingCount = n;
@@ -1048,6 +1096,57 @@ int32_t b2c_get_stats(b2c_ctx* ctx, b2c_stats* out) {
     if (!ctx || !out) return B2C_ERR_BAD_ARG;
     *out = ctx->stats;
     return B2C_OK;
+}
+
+int32_t b2c_get_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b2c_manifold_point* pOut, int32_t capP,
+                         int32_t* nH, int32_t* nP) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    NpArgs a = makeNpArgs(ctx);
+    CK(cudaMemsetAsync(ctx->dContactCounts, 0, 2 * sizeof(uint32_t), s));
+    k_compact_contacts<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(a, ctx->dContactHdr, ctx->dContactPts,
+                                                                                  ctx->capContactHdr, ctx->capContactPts,
+                                                                                  ctx->dContactCounts);
+    uint32_t counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(counts, ctx->dContactCounts, sizeof(counts), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (nH) *nH = (int32_t)counts[0];
+    if (nP) *nP = (int32_t)counts[1];
+    if (counts[0] > ctx->capContactHdr || counts[1] > ctx->capContactPts) { ctx->err = "contact stream capacity exceeded"; return B2C_ERR_CAPACITY; }
+    if (!hOut && !pOut) return B2C_OK;
+    if ((uint32_t)capH < counts[0] || (uint32_t)capP < counts[1]) { ctx->err = "contact output buffers too small"; return B2C_ERR_CAPACITY; }
+    if (hOut && counts[0]) CK(cudaMemcpyAsync(hOut, ctx->dContactHdr, (size_t)counts[0] * sizeof(b2c_contact_header), cudaMemcpyDeviceToHost, s));
+    if (pOut && counts[1]) CK(cudaMemcpyAsync(pOut, ctx->dContactPts, (size_t)counts[1] * sizeof(b2c_manifold_point), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2C_OK;
+}
+
+int32_t b2c_set_profiling(b2c_ctx* ctx, int32_t on) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    ctx->prof = on != 0;
+    ctx->stageValid = false;
+    return B2C_OK;
+}
+
+int32_t b2c_get_stage_times(b2c_ctx* ctx, float ms[B2C_NUM_STAGES]) {
+    if (!ctx || !ms) return B2C_ERR_BAD_ARG;
+    if (!ctx->stageValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < B2C_NUM_STAGES; k++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->stageEv[k], ctx->stageEv[k + 1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; }
+        ms[k] = t;
+    }
+    return B2C_OK;
+}
+
+const char* b2c_stage_name(int32_t k) {
+    static const char* names[B2C_NUM_STAGES] = {"aabb", "bounds_keys", "sort_proxies", "gather", "sweep", "large", "sort_pairs",
+                                                "unpack_carry", "classify_bin", "closed_form", "gjk_mesh", "epa_fold_count"};
+    return (k >= 0 && k < B2C_NUM_STAGES) ? names[k] : "";
 }
 
 void* b2c_stream(b2c_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

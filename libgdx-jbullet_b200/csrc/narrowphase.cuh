@@ -35,10 +35,9 @@ struct NpArgs {
     const MeshDev* meshes;
     b2c_manifold* manifolds;      // [maxPairs] this step
     b2c_raw_contact* raw;         // [maxPairs]
-    uint8_t* binOf;               // [maxPairs]
-    uint32_t* items;              // [maxPairs] pair indices grouped by bin
-    uint32_t* binStart;           // [16] device
-    uint32_t* binCursor;          // [16] device
+    uint32_t* binKeys[2];         // [maxPairs] (bin << 24) | pairIndex, stably partitioned by bin (radix pass)
+    const uint32_t* binSide;      // which of binKeys holds the partitioned list
+    const uint32_t* binStart;     // exclusive bin offsets (the partition's digit histogram); [b+1] = end of bin b
     StepCounters* ctr;
     float threshold;
     uint32_t maxPairs;
@@ -210,9 +209,6 @@ __device__ __forceinline__ bool isConvexType(int t) { return t == SH_BOX || t ==
 
 __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
     const uint32_t n = *a.numPairs;
-    __shared__ uint32_t cnt[BIN_COUNT];
-    if (threadIdx.x < BIN_COUNT) cnt[threadIdx.x] = 0;
-    __syncthreads();
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
@@ -226,32 +222,12 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
             else if (isConvexType(t0) && isConvexType(t1)) bin = BIN_GJK0 + t0 * 3 + t1;
             else if ((isConvexType(t0) && t1 == SH_MESH) || (isConvexType(t1) && t0 == SH_MESH)) bin = BIN_MESH;
         }
-        a.binOf[p] = (uint8_t)bin;
+        a.binKeys[0][p] = ((uint32_t)bin << 24) | p;
         a.raw[p].has_contact = -1;  // not processed
-        atomicAdd(&cnt[bin], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < BIN_COUNT && cnt[threadIdx.x]) atomicAdd(&a.ctr->binCount[threadIdx.x], cnt[threadIdx.x]);
-}
-__global__ void k_bin_offsets(NpArgs a) {
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int b = 0; b < BIN_COUNT; b++) {
-            a.binStart[b] = run;
-            a.binCursor[b] = run;
-            run += a.ctr->binCount[b];
-        }
-        a.binStart[BIN_COUNT] = run;
     }
 }
-__global__ void __launch_bounds__(256) k_bin_scatter(NpArgs a) {
-    const uint32_t n = *a.numPairs;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        int bin = a.binOf[p];
-        if (bin == BIN_SKIP) continue;
-        uint32_t pos = atomicAdd(&a.binCursor[bin], 1u);
-        a.items[pos] = p;
-    }
+__device__ __forceinline__ uint32_t binItem(const NpArgs& a, uint32_t it) {
+    return (*a.binSide ? a.binKeys[1] : a.binKeys[0])[it] & 0xFFFFFFu;
 }
 
 __device__ __forceinline__ void writeRaw(b2c_raw_contact* r, int2 pr, int tri, int has, f3 n, f3 pt, float depth, int method,
@@ -267,14 +243,14 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
     const uint32_t s = a.binStart[BIN_SS], e = a.binStart[BIN_SS + 1];
     uint32_t added = 0;
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
-        uint32_t p = a.items[it];
+        uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
         float r0 = a.shapes[a.shape[b0]].dims[0], r1 = a.shapes[a.shape[b1]].dims[0];
         b2c_manifold* m = a.manifolds + p;
         if (m->algorithm == 0) { m->algorithm = 1; m->body0 = pr.x; m->body1 = pr.y; }
-        for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+        for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
         f3 diff = sub3(t0.o, t1.o);
         float len = len3(diff);
         if (len > (r0 + r1)) {
@@ -310,7 +286,7 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
     const uint32_t s = a.binStart[BIN_CP], e = a.binStart[BIN_CP + 1];
     uint32_t added = 0;
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
-        uint32_t p = a.items[it];
+        uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
         ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
@@ -323,7 +299,7 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
         const Xf& tp = swapped ? t0 : t1;
         b2c_manifold* m = a.manifolds + p;
         if (m->algorithm == 0) { m->algorithm = 2; m->body0 = bc + 1; m->body1 = bp + 1; }
-        for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+        for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
         f3 planeNormal = mk3(ps.plane[0], ps.plane[1], ps.plane[2]);
         float planeConstant = ps.plane[3];
         Xf planeInConvex = invMul(tc, tp);
@@ -388,7 +364,7 @@ __device__ __forceinline__ void gjkPairBody(const NpArgs& a, const GjkArgs& g, u
                                             const Xf& t0, const Xf& t1, uint32_t& added, uint32_t& deep) {
     b2c_manifold* m = a.manifolds + p;
     if (m->algorithm == 0) { m->algorithm = 3; m->body0 = pr.x; m->body1 = pr.y; }
-    for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+    for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
     float maxd = A.margin + B.margin + a.threshold;  // disp/ConvexConvexAlgorithm.java:122-123
     maxd *= maxd;
     GjkResult r;
@@ -414,7 +390,7 @@ __global__ void __launch_bounds__(128) k_gjk(NpArgs a, GjkArgs g) {
     const uint32_t s = a.binStart[BIN_GJK0], e = a.binStart[BIN_GJK0 + 9];
     uint32_t added = 0, deep = 0, checks = 0;
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
-        uint32_t p = a.items[it];
+        uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
         ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
@@ -505,7 +481,7 @@ __device__ __forceinline__ uint32_t walkBvh(const MeshDev& md, const uint32_t qm
 __global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
     const uint32_t s = a.binStart[BIN_MESH], e = a.binStart[BIN_MESH + 1];
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
-        uint32_t p = a.items[it];
+        uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
         ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
@@ -517,7 +493,7 @@ __global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
         b2c_manifold* m = a.manifolds + p;
         m->algorithm = 4;
         m->body0 = bc + 1; m->body1 = bt + 1;  // manifoldPtr.setBodies(convexBody, triBody)
-        for (int k = 0; k < 4; k++) m->points[k].src_slot = k < m->num_contacts ? k : -1;
+        for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
         MeshDev md = a.meshes[ms.mesh];
         Xf convexInTri = invMul(tt, tc);
         f3 mn, mx;
@@ -679,7 +655,7 @@ __global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
     const uint32_t s = a.binStart[BIN_MESH], e = a.binStart[BIN_MESH + 1];
     uint32_t added = 0;
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
-        uint32_t p = a.items[it];
+        uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
@@ -699,6 +675,51 @@ __global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
         a.raw[p].has_contact = -3;  // raw records of this pair live in the mesh item array
     }
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
+}
+
+// Compact the touching manifolds (header + live points) for the D2H contact stream.
+__global__ void __launch_bounds__(256)
+k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, b2c_manifold_point* __restrict__ pts, uint32_t capH,
+                   uint32_t capP, uint32_t* __restrict__ counts /*[2]: headers, points*/) {
+    const uint32_t n = *a.numPairs;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        uint32_t p = base + lane;
+        int nc = 0;
+        if (p < n && a.manifolds[p].algorithm != 0) nc = a.manifolds[p].num_contacts;
+        uint32_t m = __ballot_sync(0xffffffffu, nc > 0);
+        if (m == 0) continue;
+        // warp totals: headers = popc(m), points = sum nc (inclusive scan by shuffles)
+        int incl = nc;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int totalP = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t baseH = 0, baseP = 0;
+        if (lane == 0) {
+            baseH = atomicAdd(&counts[0], (uint32_t)__popc(m));
+            baseP = atomicAdd(&counts[1], (uint32_t)totalP);
+        }
+        baseH = __shfl_sync(0xffffffffu, baseH, 0);
+        baseP = __shfl_sync(0xffffffffu, baseP, 0);
+        if (nc > 0) {
+            uint32_t h = baseH + __popc(m & ((1u << lane) - 1u));
+            uint32_t fp = baseP + (uint32_t)(incl - nc);
+            if (h < capH && fp + nc <= capP) {
+                const b2c_manifold* mf = a.manifolds + p;
+                b2c_contact_header hh;
+                hh.pair_uid0 = mf->pair_uid0; hh.pair_uid1 = mf->pair_uid1; hh.body0 = mf->body0; hh.body1 = mf->body1;
+                hh.num_contacts = nc; hh.algorithm = mf->algorithm; hh.first_point = (int)fp; hh.pair_index = (int)p;
+                hdr[h] = hh;
+                for (int k = 0; k < nc; k++) {
+                    const int4* src = reinterpret_cast<const int4*>(&mf->points[k]);
+                    int4* dst = reinterpret_cast<int4*>(pts + fp + k);
+                    for (int q = 0; q < 6; q++) dst[q] = src[q];
+                }
+            }
+        }
+    }
 }
 
 // number of manifolds = pairs that own an algorithm with a manifold (Dispatcher.getNumManifolds)

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist(const K* __restrict__ keys
 }
 
 // one block per pass: exclusive scan of the 256 bins, and the skip flag
-__global__ void __launch_bounds__(256) rs_scan(RadixState* st) {
+__global__ void __launch_bounds__(256) rs_scan(RadixState* st, int firstPass) {
     __shared__ uint32_t s[256];
     __shared__ uint32_t anyFull;
     const int p = blockIdx.x;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) rs_scan(RadixState* st) {
         __syncthreads();
     }
     st->hist[p][threadIdx.x] = s[threadIdx.x] - v;
-    if (threadIdx.x == 0) st->skip[p] = anyFull;
+    if (threadIdx.x == 0) st->skip[p] = (p < firstPass) ? 1u : anyFull;
 }
 
 __device__ __forceinline__ uint32_t rs_load_acquire(const uint32_t* p) {
@@ -262,7 +262,7 @@ struct RadixSorter {
     // significant bits.  The sorted data ends in side *sideOut (0: keys0/vals0, 1: keys1/vals1).
     template <typename K, bool HAS_VAL>
     void sort(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, const uint32_t* nPtr, uint32_t nConst, int keyBits,
-              uint32_t* sideOut, cudaStream_t s) {
+              uint32_t* sideOut, cudaStream_t s, int firstPass = 0) {
         int npass = (keyBits + 7) / 8;
         if (npass < 1) npass = 1;
         if (npass > RS_MAX_PASSES) npass = RS_MAX_PASSES;
@@ -276,13 +276,13 @@ struct RadixSorter {
         if (hgrid < 1) hgrid = 1;
         if (hgrid > 148 * 4) hgrid = 148 * 4;
         rs_hist<K><<<hgrid, RS_THREADS, 0, s>>>(keys0, st, npass);
-        rs_scan<<<npass, 256, 0, s>>>(st);
+        rs_scan<<<npass, 256, 0, s>>>(st, firstPass);
         unsigned pgrid = (nUpper + tile - 1) / tile;
         if (pgrid < 1) pgrid = 1;
         if (pgrid > maxTiles) pgrid = maxTiles ? maxTiles : 1;
         if (pgrid > 148 * 4) pgrid = 148 * 4;
         size_t dyn = (sizeof(K) + (HAS_VAL ? 4 : 0)) * tile;
-        for (int p = 0; p < npass; p++) {
+        for (int p = firstPass; p < npass; p++) {
             uint32_t* stp = status + statusWordsPerPass * p;
             if (items == 16) {
                 cudaFuncSetAttribute(rs_pass<K, HAS_VAL, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -292,7 +292,7 @@ struct RadixSorter {
             }
         }
         rs_final_side<<<1, 32, 0, s>>>(st, npass, sideOut);
-        launches += 4 + npass;
+        launches += 4 + npass - firstPass;
     }
 };
 

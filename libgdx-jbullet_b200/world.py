@@ -157,6 +157,14 @@ class GpuCollisionWorld:
         assert planes.dtype == np.float32 and planes.flags.c_contiguous and planes.shape[0] == 12
         self._ck(self.L.b2c_set_transforms(self.h, planes.shape[1], None, _vp(planes)))
 
+    def setWorldTransformsDevice(self, n, device_ptr):
+        """12 planes of n floats already on the device (D2D on the ctx stream)."""
+        self._ck(self.L.b2c_set_transforms_device(self.h, n, C.c_void_p(device_ptr)))
+
+    def setWorldTransformsHostPtr(self, n, host_ptr):
+        """12 planes of n floats at a raw (pinned) host address."""
+        self._ck(self.L.b2c_set_transforms(self.h, n, None, C.c_void_p(host_ptr)))
+
     def setActivation(self, active, uids=None):
         a = np.ascontiguousarray(active, dtype=np.uint8)
         u = None if uids is None else np.ascontiguousarray(uids, dtype=np.int32)
@@ -228,6 +236,24 @@ class GpuCollisionWorld:
         if n.value:
             self._ck(self.L.b2c_get_raw_contacts(self.h, _vp(out), n.value, C.byref(n)))
         return out
+
+    def contacts(self):
+        """Compact contact stream: (headers, points) of the touching manifolds (order unspecified)."""
+        nh, npt = C.c_int32(), C.c_int32()
+        self._ck(self.L.b2c_get_contacts(self.h, None, 0, None, 0, C.byref(nh), C.byref(npt)))
+        hdr = np.zeros(nh.value, dtype=_lib.CONTACT_HEADER_DTYPE)
+        pts = np.zeros(npt.value, dtype=_lib.MANIFOLD_DTYPE["points"].base)
+        if nh.value:
+            self._ck(self.L.b2c_get_contacts(self.h, _vp(hdr), nh.value, _vp(pts), npt.value, C.byref(nh), C.byref(npt)))
+        return hdr, pts
+
+    def set_profiling(self, on=True):
+        self._ck(self.L.b2c_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        ms = np.zeros(_lib.NUM_STAGES, dtype=np.float32)
+        self._ck(self.L.b2c_get_stage_times(self.h, _vp(ms)))
+        return {self.L.b2c_stage_name(k).decode(): float(ms[k]) for k in range(_lib.NUM_STAGES)}
 
     def stats(self):
         s = Stats()
