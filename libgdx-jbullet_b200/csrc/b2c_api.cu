@@ -89,6 +89,7 @@ struct b2c_ctx {
     // narrowphase
     b2c_raw_contact* dRaw = nullptr;
     uint32_t* dBinKeys[2] = {nullptr, nullptr};
+    uint32_t* dCursors = nullptr;
     RadixSorter sortBins;
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
@@ -360,16 +361,18 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     ctx->launches += 5;
     if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, s>>>(a); ctx->launches++; }
     mark(ctx, 10);
-    k_gjk<<<148 * 8, 128, 0, s>>>(a, g);
+    CK(cudaMemsetAsync(ctx->dCursors, 0, 4 * sizeof(uint32_t), s));
+    k_gjk<<<148 * 4, 128, 0, s>>>(a, g, ctx->dCursors);
     ctx->launches++;
     if (ctx->hasMesh) {
         k_mesh_query<<<148 * 4, 128, 0, s>>>(a, g);
-        k_gjk_tri<<<148 * 8, 128, 0, s>>>(a, g);
+        k_gjk_tri<<<148 * 4, 128, 0, s>>>(a, g, ctx->dCursors + 1);
         ctx->launches += 2;
     }
     mark(ctx, 11);
     k_epa<<<EPA_GRID, EPA_BLOCK, 0, s>>>(a, g);
-    ctx->launches++;
+    k_manifold_cc<<<148 * 8, 256, 0, s>>>(a);
+    ctx->launches += 2;
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
     k_count_manifolds<<<pg, 256, 0, s>>>(a);
     ctx->launches++;
@@ -516,6 +519,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dBinKeys[0], P));
     CKC(dalloc(&ctx->dBinKeys[1], P));
     CKC(ctx->sortBins.init((uint32_t)P));
+    CKC(dalloc(&ctx->dCursors, (size_t)4));
     ctx->maxEpa = (uint32_t)(P / 4 + 1024);
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
     CKC(dalloc(&ctx->dEpaScratch, (size_t)EPA_GRID * EPA_BLOCK));
@@ -554,7 +558,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); ctx->sortBins.destroy();
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); ctx->sortBins.destroy();
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

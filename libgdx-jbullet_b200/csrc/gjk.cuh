@@ -312,84 +312,95 @@ struct GjkResult {
     bool isValid, needEpa;
 };
 
-// np/GjkPairDetector.java:73-258: everything up to (not including) the penetration-depth call.
-template <class SA, class SB>
-__device__ __forceinline__ void gjkClosestPoints(const SA& A, const SB& B, const Xf& ta, const Xf& tb, float maxDistSq,
-                                                 GjkResult& out) {
-    float distance = 0.f;
-    f3 normalInB = mk3(0.f, 0.f, 0.f);
-    f3 pointOnA = mk3(0.f, 0.f, 0.f), pointOnB = mk3(0.f, 0.f, 0.f);
-    f3 positionOffset = scl3(add3(ta.o, tb.o), 0.5f);
-    Xf la = ta, lb = tb;
-    la.o = sub3(ta.o, positionOffset);
-    lb.o = sub3(tb.o, positionOffset);
-    const float marginA = A.margin, marginB = B.margin;
-    int curIter = 0;
-    f3 axis = mk3(0.f, 1.f, 0.f);  // :102
-    bool isValid = false, checkSimplex = false, checkPenetration = true;
-    int degenerate = 0, lastUsedMethod = -1;
-    float squaredDistance = B2C_SIMD_INFINITY;
-    const float margin = marginA + marginB;
+// np/GjkPairDetector.java:73-258 as a resumable per-lane state machine: begin() is the prologue (:76-117),
+// iterate() is one trip of the for(;;) loop (:132-228) and returns true when the loop ends, finish() is
+// the epilogue up to (not including) the penetration-depth call (:230-264).  Splitting it this way lets a
+// warp keep all 32 lanes inside the same loop body while each lane works on its own pair and refills from
+// the work list as soon as its pair terminates (iteration counts differ wildly between pairs).
+struct GjkLane {
     Simplex S;
-    S.reset();
-    for (;;) {
-        f3 dirA = mulMtV(ta.m, neg3(axis));
-        f3 dirB = mulMtV(tb.m, axis);
-        f3 pW = xfPoint(la, A.support(dirA));
-        f3 qW = xfPoint(lb, B.support(dirB));
+    f3 axis, positionOffset, laO, lbO;
+    float squaredDistance, maxDistSq, marginA, marginB;
+    int curIter, degenerate;
+    bool checkSimplex, checkPenetration;
+
+    __device__ __forceinline__ void begin(const Xf& ta, const Xf& tb, float mA, float mB, float maxd) {
+        positionOffset = scl3(add3(ta.o, tb.o), 0.5f);
+        laO = sub3(ta.o, positionOffset);
+        lbO = sub3(tb.o, positionOffset);
+        marginA = mA; marginB = mB; maxDistSq = maxd;
+        curIter = 0;
+        axis = mk3(0.f, 1.f, 0.f);  // :102
+        checkSimplex = false; checkPenetration = true;
+        degenerate = 0;
+        squaredDistance = B2C_SIMD_INFINITY;
+        S.reset();
+    }
+    __device__ __forceinline__ f3 dirA(const Xf& ta) const { return mulMtV(ta.m, neg3(axis)); }
+    __device__ __forceinline__ f3 dirB(const Xf& tb) const { return mulMtV(tb.m, axis); }
+    // pW / qW: the two support points already mapped through the recentred transforms
+    __device__ __forceinline__ bool iterate(f3 pW, f3 qW) {
         f3 w = sub3(pW, qW);
         float delta = dot3(axis, w);
-        if ((delta > 0.f) && (delta * delta > squaredDistance * maxDistSq)) { checkPenetration = false; break; }
-        if (S.inSimplex(w)) { degenerate = 1; checkSimplex = true; break; }
+        if ((delta > 0.f) && (delta * delta > squaredDistance * maxDistSq)) { checkPenetration = false; return true; }
+        if (S.inSimplex(w)) { degenerate = 1; checkSimplex = true; return true; }
         float f0 = squaredDistance - delta;
         float f1 = squaredDistance * GJK_REL_ERROR2;
         if (f0 <= f1) {
             if (f0 <= 0.f) degenerate = 2;
             checkSimplex = true;
-            break;
+            return true;
         }
         S.addVertex(w, pW, qW);
         bool ok = S.update();
         axis = S.cachedV;
-        if (!ok) { degenerate = 3; checkSimplex = true; break; }
-        if (len2_3(axis) < GJK_REL_ERROR2) { degenerate = 6; checkSimplex = true; break; }
+        if (!ok) { degenerate = 3; checkSimplex = true; return true; }
+        if (len2_3(axis) < GJK_REL_ERROR2) { degenerate = 6; checkSimplex = true; return true; }
         float prev = squaredDistance;
         squaredDistance = len2_3(axis);
-        if (prev - squaredDistance <= B2C_FLT_EPSILON * prev) { checkSimplex = true; break; }  // backup_closest: axis already cachedV
-        if (curIter++ > 1000) break;
-        if (S.n == 4) break;  // fullSimplex; backup_closest is a no-op here too
+        if (prev - squaredDistance <= B2C_FLT_EPSILON * prev) { checkSimplex = true; return true; }  // backup_closest: axis is cachedV
+        if (curIter++ > 1000) return true;
+        if (S.n == 4) return true;  // fullSimplex (backup_closest is a no-op: axis is cachedV)
+        return false;
     }
-    if (checkSimplex) {
-        S.update();  // compute_points (:643-647); no-op unless a vertex was added without update (never)
-        pointOnA = S.cachedP1;
-        pointOnB = S.cachedP2;
-        normalInB = sub3(pointOnA, pointOnB);
-        float lenSqr = len2_3(axis);
-        if (lenSqr < 0.0001f) degenerate = 5;
-        if (lenSqr > B2C_FLT_EPSILON * B2C_FLT_EPSILON) {
-            float rlen = 1.f / jsqrtf(lenSqr);
-            normalInB = scl3(normalInB, rlen);
-            float s = jsqrtf(squaredDistance);
-            pointOnA = sub3(pointOnA, scl3(axis, marginA / s));
-            pointOnB = add3(pointOnB, scl3(axis, marginB / s));
-            distance = ((1.f / rlen) - margin);
-            isValid = true;
-            lastUsedMethod = 1;
-        } else {
-            lastUsedMethod = 2;
+    __device__ __forceinline__ void finish(GjkResult& out) {
+        float distance = 0.f;
+        f3 normalInB = mk3(0.f, 0.f, 0.f);
+        f3 pointOnA = mk3(0.f, 0.f, 0.f), pointOnB = mk3(0.f, 0.f, 0.f);
+        bool isValid = false;
+        int lastUsedMethod = -1;
+        const float margin = marginA + marginB;
+        if (checkSimplex) {
+            pointOnA = S.cachedP1;  // compute_points (:643-647): the cache is current
+            pointOnB = S.cachedP2;
+            normalInB = sub3(pointOnA, pointOnB);
+            float lenSqr = len2_3(axis);
+            if (lenSqr < 0.0001f) degenerate = 5;
+            if (lenSqr > B2C_FLT_EPSILON * B2C_FLT_EPSILON) {
+                float rlen = 1.f / jsqrtf(lenSqr);
+                normalInB = scl3(normalInB, rlen);
+                float s = jsqrtf(squaredDistance);
+                pointOnA = sub3(pointOnA, scl3(axis, marginA / s));
+                pointOnB = add3(pointOnB, scl3(axis, marginB / s));
+                distance = ((1.f / rlen) - margin);
+                isValid = true;
+                lastUsedMethod = 1;
+            } else {
+                lastUsedMethod = 2;
+            }
         }
+        bool catchDegenerate = (degenerate != 0) && ((distance + margin) < 0.01f);
+        out.needEpa = checkPenetration && (!isValid || catchDegenerate);
+        out.isValid = isValid;
+        out.distance = distance;
+        out.pointOnA = pointOnA;
+        out.pointOnB = pointOnB;
+        out.normalInB = normalInB;
+        out.positionOffset = positionOffset;
+        out.lastUsedMethod = lastUsedMethod;
+        out.curIter = curIter;
+        out.degenerate = degenerate;
     }
-    bool catchDegenerate = (degenerate != 0) && ((distance + margin) < 0.01f);
-    out.needEpa = checkPenetration && (!isValid || catchDegenerate);
-    out.isValid = isValid;
-    out.distance = distance;
-    out.pointOnA = pointOnA;
-    out.pointOnB = pointOnB;
-    out.normalInB = normalInB;
-    out.positionOffset = positionOffset;
-    out.lastUsedMethod = lastUsedMethod;
-    out.curIter = curIter;
-    out.degenerate = degenerate;
-}
+};
 
 }  // namespace b2c

@@ -343,80 +343,140 @@ struct GjkArgs {
     uint32_t maxMeshItems;
 };
 
-// np/GjkPairDetector.java:284-312 tail once the detector result is final: emits into the manifold.
-__device__ __forceinline__ void finishConvexConvex(const NpArgs& a, uint32_t p, int2 pr, const Xf& t0, const Xf& t1, bool isValid,
-                                                   f3 normalInB, f3 pointOnB, f3 positionOffset, float distance, int method,
-                                                   int iters, uint32_t& added) {
-    b2c_manifold* m = a.manifolds + p;
-    f3 pt = add3(pointOnB, positionOffset);
-    writeRaw(a.raw + p, pr, -1, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0), isValid ? pt : mk3(0, 0, 0),
-             isValid ? distance : 0.f, method, iters);
-    if (isValid) {
-        int b0 = pr.x - 1, b1 = pr.y - 1;
-        float2 m0 = a.material[b0], m1 = a.material[b1];
-        if (manifoldAdd(m, pr.x, t0, t1, normalInB, pt, distance, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
+// A lane's convex shape, chosen at run time inside ONE code path (the whole bin shares the loop body; only
+// the support mapping switches), so the instruction footprint stays small and every warp runs the same loop.
+struct LaneShape {
+    int type;
+    f3 h;                 // box: implicitShapeDimensions
+    const float4* pts;    // hull
+    int n;
+    __device__ __forceinline__ void load(const ShapeDev& s, const float4* hullPts) {
+        type = s.type;
+        h = mk3(s.dims[0], s.dims[1], s.dims[2]);
+        pts = hullPts + s.pointOffset;
+        n = s.numPoints;
     }
-    resultRefresh(m, pr.x, t0, t1, a.threshold);  // ownManifold (disp/ConvexConvexAlgorithm.java:136-138)
-}
-
-template <class SA, class SB>
-__device__ __forceinline__ void gjkPairBody(const NpArgs& a, const GjkArgs& g, uint32_t p, int2 pr, const SA& A, const SB& B,
-                                            const Xf& t0, const Xf& t1, uint32_t& added, uint32_t& deep) {
-    b2c_manifold* m = a.manifolds + p;
-    if (m->algorithm == 0) { m->algorithm = 3; m->body0 = pr.x; m->body1 = pr.y; }
-    for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
-    float maxd = A.margin + B.margin + a.threshold;  // disp/ConvexConvexAlgorithm.java:122-123
-    maxd *= maxd;
-    GjkResult r;
-    gjkClosestPoints(A, B, t0, t1, maxd, r);
-    if (r.needEpa) {
-        deep++;
-        uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
-        if (slot < g.maxEpa) {
-            g.epaItems[slot].pair = p;
-            g.epaItems[slot].meshItem = -1;
-            g.epaItems[slot].g = r;
-            return;
-        }
-        a.ctr->epaFailed = 0x7fffffffu;  // capacity: reported by the host as B2C_ERR_CAPACITY
+    __device__ __forceinline__ f3 support(f3 v) const {  // localGetSupportingVertexWithoutMargin
+        if (type == SH_BOX) return mk3(fsel(v.x, h.x, -h.x), fsel(v.y, h.y, -h.y), fsel(v.z, h.z, -h.z));
+        if (type == SH_HULL) { HullS hs; hs.pts = pts; hs.n = n; hs.margin = 0.f; return hs.support(v); }
+        return mk3(0.f, 0.f, 0.f);  // sphere
     }
-    finishConvexConvex(a, p, pr, t0, t1, r.isValid, r.normalInB, r.pointOnB, r.positionOffset, r.distance, r.lastUsedMethod,
-                       r.curIter, added);
-}
+};
 
-// One kernel for the 8 convex-convex type pairs: the item list is ordered by type pair, so warps are
-// (almost always) uniform in the switch below.
-__global__ void __launch_bounds__(128) k_gjk(NpArgs a, GjkArgs g) {
-    const uint32_t s = a.binStart[BIN_GJK0], e = a.binStart[BIN_GJK0 + 9];
-    uint32_t added = 0, deep = 0, checks = 0;
-    for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
-        uint32_t p = binItem(a, it);
-        int2 pr = a.pairs[p];
-        int b0 = pr.x - 1, b1 = pr.y - 1;
-        ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
-        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
-        checks++;
-        BoxS bx0, bx1; SphereS sp0, sp1; HullS h0, h1;
-        bx0.h = mk3(s0.dims[0], s0.dims[1], s0.dims[2]); bx0.margin = s0.margin;
-        bx1.h = mk3(s1.dims[0], s1.dims[1], s1.dims[2]); bx1.margin = s1.margin;
-        sp0.margin = s0.margin; sp1.margin = s1.margin;
-        h0.pts = a.hullPts + s0.pointOffset; h0.n = s0.numPoints; h0.margin = s0.margin;
-        h1.pts = a.hullPts + s1.pointOffset; h1.n = s1.numPoints; h1.margin = s1.margin;
-        switch (s0.type * 3 + s1.type) {
-        case 0: gjkPairBody(a, g, p, pr, bx0, bx1, t0, t1, added, deep); break;
-        case 1: gjkPairBody(a, g, p, pr, bx0, sp1, t0, t1, added, deep); break;
-        case 2: gjkPairBody(a, g, p, pr, bx0, h1, t0, t1, added, deep); break;
-        case 3: gjkPairBody(a, g, p, pr, sp0, bx1, t0, t1, added, deep); break;
-        case 5: gjkPairBody(a, g, p, pr, sp0, h1, t0, t1, added, deep); break;
-        case 6: gjkPairBody(a, g, p, pr, h0, bx1, t0, t1, added, deep); break;
-        case 7: gjkPairBody(a, g, p, pr, h0, sp1, t0, t1, added, deep); break;
-        case 8: gjkPairBody(a, g, p, pr, h0, h1, t0, t1, added, deep); break;
-        default: break;
+// Warp-level refill: idle lanes take the next items of [*cursor, end) with one atomic per warp round.
+__device__ __forceinline__ uint32_t takeItems(bool want, uint32_t* cursor, uint32_t end) {
+    uint32_t m = __ballot_sync(0xffffffffu, want);
+    uint32_t idx = 0xffffffffu;
+    if (m) {
+        int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == (__ffs(m) - 1)) base = atomicAdd(cursor, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (want) {
+            idx = base + __popc(m & ((1u << lane) - 1u));
+            if (idx >= end) idx = 0xffffffffu;
         }
     }
-    if (added) atomicAdd(&a.ctr->contactsAdded, added);
+    return idx;
+}
+
+// k_gjk: convex-convex detector for the 8 type pairs of {box, sphere, hull}^2 minus sphere-sphere.
+// Persistent warps; each lane owns one pair at a time and all lanes step through GjkLane::iterate together.
+// Output is the raw detector record (or an EPA work item); manifolds are updated by k_manifold_cc.
+__global__ void __launch_bounds__(128) k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor) {
+    const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
+    const uint32_t count = e0 - s0;
+    uint32_t deep = 0, checks = 0;
+    GjkLane L;
+    LaneShape A, B;
+    Xf ta, tb;
+    uint32_t p = 0;
+    int2 pr = make_int2(0, 0);
+    bool busy = false, more = true;
+    while (true) {
+        const bool want = !busy && more;
+        const uint32_t it = takeItems(want, cursor, count);  // one convergent call site for the whole warp
+        if (want) {
+            if (it == 0xffffffffu) {
+                more = false;
+            } else {
+                p = binItem(a, s0 + it);
+                pr = a.pairs[p];
+                const int b0 = pr.x - 1, b1 = pr.y - 1;
+                const ShapeDev& sa = a.shapes[a.shape[b0]];
+                const ShapeDev& sb = a.shapes[a.shape[b1]];
+                A.load(sa, a.hullPts);
+                B.load(sb, a.hullPts);
+                ta = loadXf(a.xf4, b0);
+                tb = loadXf(a.xf4, b1);
+                float mA = sa.margin, mB = sb.margin;
+                float maxd = mA + mB + a.threshold;  // disp/ConvexConvexAlgorithm.java:122-123
+                L.begin(ta, tb, mA, mB, maxd * maxd);
+                busy = true;
+                checks++;
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        if (busy) {
+            f3 pW = add3(mulMV(ta.m, A.support(L.dirA(ta))), L.laO);
+            f3 qW = add3(mulMV(tb.m, B.support(L.dirB(tb))), L.lbO);
+            if (L.iterate(pW, qW)) {
+                GjkResult r;
+                L.finish(r);
+                busy = false;
+                bool queued = false;
+                if (r.needEpa) {
+                    deep++;
+                    uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
+                    if (slot < g.maxEpa) {
+                        g.epaItems[slot].pair = p;
+                        g.epaItems[slot].meshItem = -1;
+                        g.epaItems[slot].g = r;
+                        a.raw[p].has_contact = -2;  // pending in the penetration bin
+                        queued = true;
+                    } else {
+                        a.ctr->epaFailed = 0x7fffffffu;  // capacity: reported by the host as B2C_ERR_CAPACITY
+                    }
+                }
+                if (!queued) {
+                    f3 pt = add3(r.pointOnB, r.positionOffset);
+                    writeRaw(a.raw + p, pr, -1, r.isValid ? 1 : 0, r.isValid ? r.normalInB : mk3(0, 0, 0), r.isValid ? pt : mk3(0, 0, 0),
+                             r.isValid ? r.distance : 0.f, r.lastUsedMethod, r.curIter);
+                }
+            }
+        }
+    }
     if (deep) atomicAdd(&a.ctr->deepChecks, deep);
     if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
+}
+
+// k_manifold_cc: ConvexConvexAlgorithm's manifold side for every pair of the GJK bins, after the detector
+// (and the penetration bin) have produced the raw record: getNewManifold on first use
+// (disp/ConvexConvexAlgorithm.java:92-96), ManifoldResult.addContactPoint, refreshContactPoints (:136-138).
+__global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
+    const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
+    uint32_t added = 0;
+    for (uint32_t it = s0 + blockIdx.x * blockDim.x + threadIdx.x; it < e0; it += gridDim.x * blockDim.x) {
+        uint32_t p = binItem(a, it);
+        int2 pr = a.pairs[p];
+        b2c_manifold* m = a.manifolds + p;
+        if (m->algorithm == 0) { m->algorithm = 3; m->body0 = pr.x; m->body1 = pr.y; }
+        const int nc = m->num_contacts;
+        const b2c_raw_contact* r = a.raw + p;
+        const bool has = r->has_contact == 1;
+        if (nc == 0 && !has) continue;  // nothing to add, nothing to refresh
+        for (int k = 0; k < nc; k++) m->points[k].src_slot = k;
+        int b0 = pr.x - 1, b1 = pr.y - 1;
+        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+        if (has) {
+            float2 m0 = a.material[b0], m1 = a.material[b1];
+            if (manifoldAdd(m, pr.x, t0, t1, mk3(r->normal[0], r->normal[1], r->normal[2]), mk3(r->point[0], r->point[1], r->point[2]),
+                            r->depth, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0))
+                added++;
+        }
+        resultRefresh(m, pr.x, t0, t1, a.threshold);
+    }
+    if (added) atomicAdd(&a.ctr->contactsAdded, added);
 }
 
 // ---- convex vs BvhTriangleMeshShape ------------------------------------------------------------------
@@ -530,47 +590,78 @@ __device__ __forceinline__ TriS loadTri(const MeshDev& md, int tri, float margin
     return t;
 }
 
-// one thread per (pair, triangle): ConvexConvexAlgorithm on (convex, TriangleShape) with the shared manifold
-__global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g) {
+// k_gjk_tri: one lane per (pair, triangle) item: ConvexConvexAlgorithm on (convex, TriangleShape) with the
+// shared manifold (disp/ConvexTriangleCallback.java:111-172).  Same persistent-lane loop as k_gjk.
+__global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g, uint32_t* cursor) {
     uint32_t nItems = a.ctr->meshItems < g.maxMeshItems ? a.ctr->meshItems : g.maxMeshItems;
     if (a.ctr->meshOverflow) nItems = 0;
     uint32_t deep = 0, checks = 0;
-    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nItems; it += gridDim.x * blockDim.x) {
-        uint32_t p = g.meshPair[it];
-        int tri = g.meshTri[it];
-        int2 pr = a.pairs[p];
-        int b0 = pr.x - 1, b1 = pr.y - 1;
-        ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
-        bool swapped = (s0.type == SH_MESH);
-        int bc = swapped ? b1 : b0, bt = swapped ? b0 : b1;
-        const ShapeDev& cs = swapped ? s1 : s0;
-        const ShapeDev& ms = swapped ? s0 : s1;
-        Xf tc = loadXf(a.xf4, bc), tt = loadXf(a.xf4, bt);
-        const MeshDev& md = a.meshes[ms.mesh];
-        TriS T = loadTri(md, tri, ms.margin);
-        float maxd = cs.margin + ms.margin + a.threshold;
-        maxd *= maxd;
-        GjkResult r;
-        checks++;
-        if (cs.type == SH_BOX) { BoxS A; A.h = mk3(cs.dims[0], cs.dims[1], cs.dims[2]); A.margin = cs.margin; gjkClosestPoints(A, T, tc, tt, maxd, r); }
-        else if (cs.type == SH_SPHERE) { SphereS A; A.margin = cs.margin; gjkClosestPoints(A, T, tc, tt, maxd, r); }
-        else { HullS A; A.pts = a.hullPts + cs.pointOffset; A.n = cs.numPoints; A.margin = cs.margin; gjkClosestPoints(A, T, tc, tt, maxd, r); }
-        b2c_raw_contact* rw = g.rawMesh + it;
-        if (r.needEpa) {
-            deep++;
-            uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
-            if (slot < g.maxEpa) {
-                g.epaItems[slot].pair = p;
-                g.epaItems[slot].meshItem = (int)it;
-                g.epaItems[slot].g = r;
-                rw->has_contact = -2;  // pending
-                continue;
+    GjkLane L;
+    LaneShape A;
+    TriS T;
+    Xf ta, tb;
+    uint32_t p = 0, item = 0;
+    int tri = 0;
+    int2 pr = make_int2(0, 0);
+    bool busy = false, more = true;
+    while (true) {
+        const bool want = !busy && more;
+        const uint32_t it = takeItems(want, cursor, nItems);
+        if (want) {
+            if (it == 0xffffffffu) {
+                more = false;
+            } else {
+                item = it;
+                p = g.meshPair[it];
+                tri = g.meshTri[it];
+                pr = a.pairs[p];
+                const int b0 = pr.x - 1, b1 = pr.y - 1;
+                const ShapeDev& s0 = a.shapes[a.shape[b0]];
+                const ShapeDev& s1 = a.shapes[a.shape[b1]];
+                const bool swapped = (s0.type == SH_MESH);
+                const ShapeDev& cs = swapped ? s1 : s0;
+                const ShapeDev& ms = swapped ? s0 : s1;
+                ta = loadXf(a.xf4, swapped ? b1 : b0);
+                tb = loadXf(a.xf4, swapped ? b0 : b1);
+                A.load(cs, a.hullPts);
+                T = loadTri(a.meshes[ms.mesh], tri, ms.margin);
+                float mA = cs.margin, mB = ms.margin;
+                float maxd = mA + mB + a.threshold;
+                L.begin(ta, tb, mA, mB, maxd * maxd);
+                busy = true;
+                checks++;
             }
-            a.ctr->epaFailed = 0x7fffffffu;
         }
-        f3 pt = add3(r.pointOnB, r.positionOffset);
-        writeRaw(rw, pr, tri, r.isValid ? 1 : 0, r.isValid ? r.normalInB : mk3(0, 0, 0), r.isValid ? pt : mk3(0, 0, 0),
-                 r.isValid ? r.distance : 0.f, r.lastUsedMethod, r.curIter);
+        if (!__any_sync(0xffffffffu, busy)) break;
+        if (busy) {
+            f3 pW = add3(mulMV(ta.m, A.support(L.dirA(ta))), L.laO);
+            f3 qW = add3(mulMV(tb.m, T.support(L.dirB(tb))), L.lbO);
+            if (L.iterate(pW, qW)) {
+                GjkResult r;
+                L.finish(r);
+                busy = false;
+                b2c_raw_contact* rw = g.rawMesh + item;
+                bool queued = false;
+                if (r.needEpa) {
+                    deep++;
+                    uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
+                    if (slot < g.maxEpa) {
+                        g.epaItems[slot].pair = p;
+                        g.epaItems[slot].meshItem = (int)item;
+                        g.epaItems[slot].g = r;
+                        rw->has_contact = -2;  // pending
+                        queued = true;
+                    } else {
+                        a.ctr->epaFailed = 0x7fffffffu;
+                    }
+                }
+                if (!queued) {
+                    f3 pt = add3(r.pointOnB, r.positionOffset);
+                    writeRaw(rw, pr, tri, r.isValid ? 1 : 0, r.isValid ? r.normalInB : mk3(0, 0, 0), r.isValid ? pt : mk3(0, 0, 0),
+                             r.isValid ? r.distance : 0.f, r.lastUsedMethod, r.curIter);
+                }
+            }
+        }
     }
     if (deep) atomicAdd(&a.ctr->deepChecks, deep);
     if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
@@ -580,7 +671,7 @@ __global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g) {
 __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
     uint32_t nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
     EpaScratch* scratch = g.scratch + (blockIdx.x * blockDim.x + threadIdx.x);
-    uint32_t added = 0, failed = 0;
+    uint32_t failed = 0;
     for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nItems; it += gridDim.x * blockDim.x) {
         EpaItem item = g.epaItems[it];
         uint32_t p = item.pair;
@@ -637,15 +728,11 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
         } else {
             method = 5;
         }
-        if (item.meshItem >= 0) {
-            f3 pt = add3(pointOnB, r.positionOffset);
-            writeRaw(g.rawMesh + item.meshItem, pr, tri, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0),
-                     isValid ? pt : mk3(0, 0, 0), isValid ? distance : 0.f, method, r.curIter);
-        } else {
-            finishConvexConvex(a, p, pr, t0, t1, isValid, normalInB, pointOnB, r.positionOffset, distance, method, r.curIter, added);
-        }
+        f3 pt = add3(pointOnB, r.positionOffset);
+        b2c_raw_contact* rw = item.meshItem >= 0 ? g.rawMesh + item.meshItem : a.raw + p;
+        writeRaw(rw, pr, tri, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0), isValid ? pt : mk3(0, 0, 0),
+                 isValid ? distance : 0.f, method, r.curIter);
     }
-    if (added) atomicAdd(&a.ctr->contactsAdded, added);
     if (failed) atomicAdd(&a.ctr->epaFailed, failed);
 }
 
