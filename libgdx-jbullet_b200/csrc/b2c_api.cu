@@ -20,7 +20,8 @@ using namespace b2c;
 
 namespace {
 
-constexpr int EPA_GRID = 148 * 8, EPA_BLOCK = 64;
+constexpr int EPA_GRID = 148 * 16, EPA_BLOCK = 64;   // tier 0 (small pools in local memory)
+constexpr int EPA_GRID2 = 148, EPA_BLOCK2 = 64;        // tier 1 (large pools in global memory)
 
 struct HostMesh {
     int4* nodes = nullptr;
@@ -94,6 +95,8 @@ struct b2c_ctx {
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
     EpaScratch* dEpaScratch = nullptr;
+    uint32_t* dEpaRetry = nullptr;
+    uint32_t maxEpaRetry = 0;
     uint32_t* dMeshPair = nullptr;
     int* dMeshTri = nullptr;
     b2c_raw_contact* dRawMesh = nullptr;
@@ -217,7 +220,7 @@ __global__ void k_get_aabbs(BodyArrays B, int n, float* out) {
 __global__ void k_clear_np_counters(StepCounters* c) {
     if (threadIdx.x == 0) {
         c->contactsAdded = c->gjkChecks = c->deepChecks = c->epaFailed = 0;
-        c->meshItems = c->meshOverflow = c->numManifolds = c->epaCount = 0;
+        c->meshItems = c->meshOverflow = c->numManifolds = c->epaCount = c->epaRetry = 0;
     }
     if (threadIdx.x < 16) c->binCount[threadIdx.x] = 0;
 }
@@ -341,6 +344,8 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     g.epaItems = ctx->dEpaItems;
     g.maxEpa = ctx->maxEpa;
     g.scratch = ctx->dEpaScratch;
+    g.epaRetry = ctx->dEpaRetry;
+    g.maxEpaRetry = ctx->maxEpaRetry;
     g.meshPair = ctx->dMeshPair;
     g.meshTri = ctx->dMeshTri;
     g.rawMesh = ctx->dRawMesh;
@@ -370,9 +375,10 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         ctx->launches += 2;
     }
     mark(ctx, 11);
-    k_epa<<<EPA_GRID, EPA_BLOCK, 0, s>>>(a, g);
+    k_epa<0><<<EPA_GRID, EPA_BLOCK, 0, s>>>(a, g);
+    k_epa<1><<<EPA_GRID2, EPA_BLOCK2, 0, s>>>(a, g);
     k_manifold_cc<<<148 * 8, 256, 0, s>>>(a);
-    ctx->launches += 2;
+    ctx->launches += 3;
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
     k_count_manifolds<<<pg, 256, 0, s>>>(a);
     ctx->launches++;
@@ -522,7 +528,9 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dCursors, (size_t)4));
     ctx->maxEpa = (uint32_t)(P / 4 + 1024);
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
-    CKC(dalloc(&ctx->dEpaScratch, (size_t)EPA_GRID * EPA_BLOCK));
+    CKC(dalloc(&ctx->dEpaScratch, (size_t)EPA_GRID2 * EPA_BLOCK2));
+    ctx->maxEpaRetry = ctx->maxEpa;
+    CKC(dalloc(&ctx->dEpaRetry, (size_t)ctx->maxEpaRetry));
     const size_t MI = (size_t)(cfg->max_mesh_items > 0 ? cfg->max_mesh_items : 1);
     CKC(dalloc(&ctx->dMeshPair, MI));
     CKC(dalloc(&ctx->dMeshTri, MI));
@@ -559,7 +567,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
     cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); ctx->sortBins.destroy();
-    cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dMeshPair);
+    cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);

@@ -151,7 +151,8 @@ struct StepCounters {
     uint32_t binCount[16];
     uint32_t epaCount;
     uint32_t largeCount;
-    uint32_t pad[14];
+    uint32_t epaRetry;
+    uint32_t pad[13];
 };
 
 // monotone float <-> uint key (total order matching float compare for non-NaN; -0 canonicalised to +0)

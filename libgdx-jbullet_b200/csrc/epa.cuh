@@ -24,22 +24,34 @@ constexpr int EPA_MAXIT = 256;           // :113
 constexpr float EPA_INFACE_EPS = 0.01f;  // :114
 constexpr float EPA_ACCURACY = 0.001f;   // :115
 
-struct EpaFace {  // np/GjkEpaSolver.java:515-525, pointers replaced by pool indices (-1 = null)
-    int v[3];
-    int f[3];
-    int e[3];
-    int mark, prev, next;
+// Pools are templated: the common case (a few iterations, < 100 faces) runs out of a small per-thread pool
+// with one-byte links that lives in local memory (hardware-interleaved across the warp, L1-cached); a pair
+// that overflows it is redone by a second kernel with the large pool in global memory.
+template <typename IdxT>
+struct EpaFaceT {  // np/GjkEpaSolver.java:515-525, pointers replaced by pool indices (NIL = null)
     float nx, ny, nz, d;
+    IdxT v[3];
+    IdxT f[3];
+    IdxT prev, next;
+    uint8_t e[3];
+    uint8_t pad;
+    uint16_t mark;
 };
 struct EpaMkv { f3 w, r; };  // :119-127
 
-struct EpaScratch {
-    EpaMkv mkv[EPA_MAXV];
-    EpaFace face[EPA_MAXF];
-    f3 ray[EPA_MAXRAY];
-    int stkF[EPA_MAXSTK];
-    int stkE[EPA_MAXSTK];
+template <typename IdxT, int MAXF, int MAXV, int MAXRAY, int MAXSTK>
+struct EpaScratchT {
+    typedef IdxT Idx;
+    typedef EpaFaceT<IdxT> Face;
+    static constexpr int kMaxF = MAXF, kMaxV = MAXV, kMaxRay = MAXRAY, kMaxStk = MAXSTK;
+    EpaMkv mkv[MAXV];
+    Face face[MAXF];
+    f3 ray[MAXRAY];
+    IdxT stkF[MAXSTK];
+    uint8_t stkE[MAXSTK];
 };
+typedef EpaScratchT<int16_t, EPA_MAXF, EPA_MAXV, EPA_MAXRAY, EPA_MAXSTK> EpaScratch;   // large pool (global memory)
+typedef EpaScratchT<uint8_t, 120, 40, 24, 48> EpaScratchSmall;                         // small pool (local memory)
 
 // A convex shape chosen at run time (the EPA bin is small and mixed, so no template split here).
 struct AnyS {
@@ -62,12 +74,15 @@ struct AnyS {
     }
 };
 
+template <class SC>
 struct EpaCtx {
+    typedef typename SC::Face Face;
+    static constexpr int NIL = -1;
     const AnyS* A;
     const AnyS* B;
     Xf ta, tb;          // localTransA / localTransB (recentred)
     float margin;       // radialmargin + EPA_accuracy (:880)
-    EpaScratch* s;
+    SC* s;
     // GJK part
     EpaMkv simplex[5];
     f3 ray;
@@ -93,7 +108,8 @@ struct EpaCtx {
     __device__ bool fetchSupport() {  // :222-241 (hash chain == list membership)
         for (int i = 0; i < nrays; i++)
             if (eq3bits(s->ray[i], ray)) { --order; return false; }
-        if (nrays < EPA_MAXRAY) s->ray[nrays++] = ray;
+        if (nrays < SC::kMaxRay) s->ray[nrays++] = ray;
+        else overflow = true;
         ++order;
         support(ray, simplex[order]);
         return dot3(ray, simplex[order].w) > 0;
@@ -241,14 +257,17 @@ struct EpaCtx {
     }
 
     // ---- EPA -----------------------------------------------------------------------------------------
+    typedef typename SC::Idx Idx;
+    __device__ __forceinline__ static int rd(Idx x) { return (x == (Idx)-1) ? -1 : (int)x; }  // link -> index, NIL -> -1
+
     __device__ bool setFace(int fi, int a, int b, int c) {  // :604-631
-        EpaFace& f = s->face[fi];
+        Face& f = s->face[fi];
         f3 aw = s->mkv[a].w, bw = s->mkv[b].w, cw = s->mkv[c].w;
         f3 nrm = crs3(sub3(bw, aw), sub3(cw, aw));
         float len = len3(nrm);
         f3 t1 = crs3(aw, bw), t2 = crs3(bw, cw), t3 = crs3(cw, aw);
         bool valid = (dot3(t1, nrm) >= -EPA_INFACE_EPS) && (dot3(t2, nrm) >= -EPA_INFACE_EPS) && (dot3(t3, nrm) >= -EPA_INFACE_EPS);
-        f.v[0] = a; f.v[1] = b; f.v[2] = c;
+        f.v[0] = (Idx)a; f.v[1] = (Idx)b; f.v[2] = (Idx)c;
         f.mark = 0;
         f3 n = scl3(nrm, 1.f / (len > 0.f ? len : B2C_SIMD_INFINITY));
         f.nx = n.x; f.ny = n.y; f.nz = n.z;
@@ -256,61 +275,62 @@ struct EpaCtx {
         return valid;
     }
     __device__ int newFace(int a, int b, int c) {  // :633-647
-        if (nface_alloc >= EPA_MAXF) { overflow = true; return -1; }
+        if (nface_alloc >= SC::kMaxF) { overflow = true; return -1; }
         int pf = nface_alloc++;
-        EpaFace& f = s->face[pf];
-        f.f[0] = f.f[1] = f.f[2] = -1;
+        Face& f = s->face[pf];
+        f.f[0] = f.f[1] = f.f[2] = (Idx)-1;
         f.e[0] = f.e[1] = f.e[2] = 0;
         if (setFace(pf, a, b, c)) {
-            if (root >= 0) s->face[root].prev = pf;
-            f.prev = -1;
-            f.next = root;
+            if (root >= 0) s->face[root].prev = (Idx)pf;
+            f.prev = (Idx)-1;
+            f.next = (Idx)root;
             root = pf;
             ++nfaces;
         } else {
-            f.prev = f.next = -1;
+            f.prev = f.next = (Idx)-1;
         }
         return pf;
     }
     __device__ void detach(int fi) {  // :649-666
-        EpaFace& f = s->face[fi];
-        if (f.prev >= 0 || f.next >= 0) {
+        Face& f = s->face[fi];
+        const int fprev = rd(f.prev), fnext = rd(f.next);
+        if (fprev >= 0 || fnext >= 0) {
             --nfaces;
             if (fi == root) {
-                root = f.next;
-                s->face[root].prev = -1;
+                root = fnext;
+                s->face[root].prev = (Idx)-1;
             } else {
-                if (f.next < 0) {
-                    s->face[f.prev].next = -1;
+                if (fnext < 0) {
+                    s->face[fprev].next = (Idx)-1;
                 } else {
-                    s->face[f.prev].next = f.next;
-                    s->face[f.next].prev = f.prev;
+                    s->face[fprev].next = (Idx)fnext;
+                    s->face[fnext].prev = (Idx)fprev;
                 }
             }
-            f.prev = f.next = -1;
+            f.prev = f.next = (Idx)-1;
         }
     }
     __device__ void link(int f0, int e0, int f1, int e1) {  // :668-673
-        s->face[f0].f[e0] = f1;
-        s->face[f1].e[e1] = e0;
-        s->face[f1].f[e1] = f0;
-        s->face[f0].e[e0] = e1;
+        s->face[f0].f[e0] = (Idx)f1;
+        s->face[f1].e[e1] = (uint8_t)e0;
+        s->face[f1].f[e1] = (Idx)f0;
+        s->face[f0].e[e0] = (uint8_t)e1;
     }
     // :683-706 BuildHorizon, recursion unrolled onto an explicit stack (children pushed in reverse so the
     // visiting order, and with it the cf/ff chaining, is the reference's depth-first order)
     __device__ int buildHorizon(int markid, int w, int f0, int e0, int& cf, int& ff) {
         int ne = 0, sp = 0;
-        s->stkF[sp] = f0; s->stkE[sp] = e0; sp++;
+        s->stkF[sp] = (Idx)f0; s->stkE[sp] = (uint8_t)e0; sp++;
         const f3 ww = s->mkv[w].w;
         while (sp > 0) {
             sp--;
-            int fi = s->stkF[sp], e = s->stkE[sp];
+            int fi = rd(s->stkF[sp]), e = s->stkE[sp];
             if (fi < 0) { overflow = true; continue; }
-            EpaFace& f = s->face[fi];
+            Face& f = s->face[fi];
             if (f.mark == markid) continue;
             int e1 = (e + 1) % 3;
             if ((dot3(mk3(f.nx, f.ny, f.nz), ww) + f.d) > 0) {
-                int nf = newFace(f.v[e1], f.v[e], w);
+                int nf = newFace(rd(f.v[e1]), rd(f.v[e]), w);
                 if (nf < 0) return ne;
                 link(nf, 0, fi, e);
                 if (cf >= 0) link(cf, 1, nf, 2);
@@ -320,8 +340,8 @@ struct EpaCtx {
             } else {
                 int e2 = (e + 2) % 3;
                 detach(fi);
-                f.mark = markid;
-                if (sp + 2 > EPA_MAXSTK) { overflow = true; return ne; }
+                f.mark = (uint16_t)markid;
+                if (sp + 2 > SC::kMaxStk) { overflow = true; return ne; }
                 s->stkF[sp] = f.f[e2]; s->stkE[sp] = f.e[e2]; sp++;
                 s->stkF[sp] = f.f[e1]; s->stkE[sp] = f.e[e1]; sp++;
             }
@@ -329,9 +349,9 @@ struct EpaCtx {
         return ne;
     }
     __device__ f3 getCoordinates(int fi) const {  // :553-587
-        const EpaFace& f = s->face[fi];
+        const Face& f = s->face[fi];
         f3 o = scl3(mk3(f.nx, f.ny, f.nz), -f.d);
-        f3 w0 = s->mkv[f.v[0]].w, w1 = s->mkv[f.v[1]].w, w2 = s->mkv[f.v[2]].w;
+        f3 w0 = s->mkv[rd(f.v[0])].w, w1 = s->mkv[rd(f.v[1])].w, w2 = s->mkv[rd(f.v[2])].w;
         float a0 = len3(crs3(sub3(w0, o), sub3(w1, o)));
         float a1 = len3(crs3(sub3(w1, o), sub3(w2, o)));
         float a2 = len3(crs3(sub3(w2, o), sub3(w0, o)));
@@ -352,7 +372,6 @@ struct EpaCtx {
         root = -1; nfaces = 0; nface_alloc = 0; nmkv = 0;
         int iters = 0;
         epaFailed = false;
-        overflow = false;
         if (encloseOrigin()) {
             int basefaces[6];
             int nfidx = 0, neidx = 0;
@@ -373,11 +392,11 @@ struct EpaCtx {
             int bf = -1;
             {
                 float bd = B2C_SIMD_INFINITY;
-                for (int cf = root; cf >= 0; cf = s->face[cf].next)
+                for (int cf = root; cf >= 0; cf = rd(s->face[cf].next))
                     if (s->face[cf].d < bd) { bd = s->face[cf].d; bf = cf; }
             }
             if (bf < 0) break;
-            if (nmkv >= EPA_MAXV) { overflow = true; break; }
+            if (nmkv >= SC::kMaxV) { overflow = true; break; }
             int w = nmkv++;
             f3 bn = mk3(s->face[bf].nx, s->face[bf].ny, s->face[bf].nz);
             support(neg3(bn), s->mkv[w]);
@@ -386,8 +405,9 @@ struct EpaCtx {
             if (d < -EPA_ACCURACY) {
                 int cf = -1, ff = -1, nf = 0;
                 detach(bf);
-                s->face[bf].mark = ++markid;
-                for (int i = 0; i < 3 && !overflow; ++i) nf += buildHorizon(markid, w, s->face[bf].f[i], s->face[bf].e[i], cf, ff);
+                s->face[bf].mark = (uint16_t)(++markid);
+                for (int i = 0; i < 3 && !overflow; ++i)
+                    nf += buildHorizon(markid, w, rd(s->face[bf].f[i]), s->face[bf].e[i], cf, ff);
                 if (overflow) break;
                 if (nf <= 2) break;
                 link(cf, 1, ff, 2);
@@ -395,14 +415,14 @@ struct EpaCtx {
                 break;
             }
         }
-        if (overflow) { epaFailed = true; return -B2C_SIMD_INFINITY; }
+        if (overflow) return -B2C_SIMD_INFINITY;
         if (bestface >= 0) {
             f3 b = getCoordinates(bestface);
-            const EpaFace& f = s->face[bestface];
+            const Face& f = s->face[bestface];
             depth = jmaxf(0.f, f.d);
             f3 fa[3], fb[3];
             for (int j = 0; j < 3; ++j) {
-                f3 r = s->mkv[f.v[j]].r;
+                f3 r = s->mkv[rd(f.v[j])].r;
                 fa[j] = localSupport(scl3(r, 1.f), 0);
                 fb[j] = localSupport(scl3(r, -1.f), 1);
             }
@@ -418,18 +438,23 @@ struct EpaCtx {
 };
 
 // np/GjkEpaSolver.java:864-911 collide + np/GjkEpaPenetrationDepthSolver.java:41-63 calcPenDepth.
-// Returns true with witnesses when penetrating.
-__device__ __noinline__ bool epaPenetration(const AnyS& A, const AnyS& B, const Xf& la, const Xf& lb, EpaScratch* scratch,
-                                            f3& wOnA, f3& wOnB, bool& epaFailed) {
-    EpaCtx c;
+// Returns true with witnesses when penetrating.  poolOverflow: the pool was too small, nothing is decided.
+template <class SC>
+__device__ __noinline__ bool epaPenetration(const AnyS& A, const AnyS& B, const Xf& la, const Xf& lb, SC* scratch, f3& wOnA,
+                                            f3& wOnB, bool& epaFailed, bool& poolOverflow) {
+    EpaCtx<SC> c;
     c.A = &A; c.B = &B; c.ta = la; c.tb = lb;
     c.margin = 0.f + EPA_ACCURACY;
     c.s = scratch;
+    c.overflow = false;
     epaFailed = false;
+    poolOverflow = false;
     bool collide = c.searchOrigin();
+    if (c.overflow) { poolOverflow = true; return false; }
     if (collide) {
         f3 n0, n1;
         float pd = c.evaluatePD(n0, n1, epaFailed);
+        if (c.overflow) { poolOverflow = true; return false; }
         if (pd > 0) {
             wOnA = n0;
             wOnB = n1;

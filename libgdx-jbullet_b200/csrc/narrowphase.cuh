@@ -333,7 +333,9 @@ struct EpaItem {        // a pair (or pair/triangle) whose detector asked for th
 struct GjkArgs {
     EpaItem* epaItems;
     uint32_t maxEpa;
-    EpaScratch* scratch;     // [epaThreads]
+    uint32_t* epaRetry;      // items whose small pool overflowed
+    uint32_t maxEpaRetry;
+    EpaScratch* scratch;     // [tier-1 threads] large pools
     // mesh work items
     uint32_t* meshPair;      // [maxMeshItems] pair index
     int* meshTri;            // [maxMeshItems] triangle index
@@ -668,11 +670,16 @@ __global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g, uint32_t* 
 }
 
 // EPA bin: finishes np/GjkPairDetector.java:265-303 for the pairs that asked for it.
+// TIER 0: every queued item, small per-thread pool in local memory; items that overflow it are appended to the
+// retry list.  TIER 1: the retry list with the large pool in global memory (pool exhaustion there = EPA failed).
+template <int TIER>
 __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
-    uint32_t nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
-    EpaScratch* scratch = g.scratch + (blockIdx.x * blockDim.x + threadIdx.x);
+    uint32_t nItems;
+    if (TIER == 0) nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
+    else nItems = a.ctr->epaRetry < g.maxEpaRetry ? a.ctr->epaRetry : g.maxEpaRetry;
     uint32_t failed = 0;
-    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nItems; it += gridDim.x * blockDim.x) {
+    for (uint32_t it0 = blockIdx.x * blockDim.x + threadIdx.x; it0 < nItems; it0 += gridDim.x * blockDim.x) {
+        const uint32_t it = TIER == 0 ? it0 : g.epaRetry[it0];
         EpaItem item = g.epaItems[it];
         uint32_t p = item.pair;
         int2 pr = a.pairs[p];
@@ -702,8 +709,21 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
         la.o = sub3(ta.o, r.positionOffset);
         lb.o = sub3(tb.o, r.positionOffset);
         f3 wA, wB;
-        bool epaFail = false;
-        bool ok = epaPenetration(A, B, la, lb, scratch, wA, wB, epaFail);
+        bool epaFail = false, poolOverflow = false;
+        bool ok;
+        if (TIER == 0) {
+            EpaScratchSmall sc;
+            ok = epaPenetration(A, B, la, lb, &sc, wA, wB, epaFail, poolOverflow);
+            if (poolOverflow) {
+                uint32_t slot = atomicAdd(&a.ctr->epaRetry, 1u);
+                if (slot < g.maxEpaRetry) { g.epaRetry[slot] = it; continue; }
+                epaFail = true;  // retry list full: report as failure below
+            }
+        } else {
+            EpaScratch* sc = g.scratch + (blockIdx.x * blockDim.x + threadIdx.x);
+            ok = epaPenetration(A, B, la, lb, sc, wA, wB, epaFail, poolOverflow);
+            if (poolOverflow) epaFail = true;
+        }
         if (epaFail) failed++;
         bool isValid = r.isValid;
         float distance = r.distance;

@@ -9,6 +9,9 @@
 
 namespace orc {
 
+struct EpaDebugStats { long calls = 0, epaIters = 0, epaItersMax = 0, faces = 0, facesMax = 0, gjkIters = 0, gjkItersMax = 0, hist[9][4] = {}; int curType = 0; };
+static EpaDebugStats g_epaStats;
+
 // ---------------------------------------------------------------------------------------
 // np/GjkEpaSolver.java
 // ---------------------------------------------------------------------------------------
@@ -495,11 +498,20 @@ struct GjkEpaSolver {
         gjk.init(wtrs0.basis, wtrs0.origin, shape0, wtrs1.basis, wtrs1.origin, shape1, radialmargin + EPA_accuracy);
         bool col = gjk.SearchOrigin();
         results.gjk_iterations = gjk.iterations + 1;
+        g_epaStats.calls++;
+        g_epaStats.gjkIters += gjk.iterations + 1;
+        if (gjk.iterations + 1 > g_epaStats.gjkItersMax) g_epaStats.gjkItersMax = gjk.iterations + 1;
+        g_epaStats.curType = (shape0->type % 3) * 3 + (shape1->type % 3);
         if (col) {
             EPA epa;
             epa.gjk = &gjk;
             float pd = epa.EvaluatePD();
             results.epa_iterations = epa.iterations + 1;
+            g_epaStats.epaIters += epa.iterations + 1;
+            if (epa.iterations + 1 > g_epaStats.epaItersMax) g_epaStats.epaItersMax = epa.iterations + 1;
+            g_epaStats.faces += (long)epa.facePool.size();
+            if ((long)epa.facePool.size() > g_epaStats.facesMax) g_epaStats.facesMax = (long)epa.facePool.size();
+            { int it = epa.iterations + 1; int b = it <= 4 ? 0 : (it <= 16 ? 1 : (it <= 64 ? 2 : 3)); g_epaStats.hist[g_epaStats.curType][b]++; }
             if (pd > 0) {
                 results.status = 1;
                 results.normal.set(epa.normal);

@@ -168,6 +168,12 @@ void orc_get_counters(void* h, long* out5) {
     out5[3] = w->bvhNodesVisited; out5[4] = w->trianglesTested;
 }
 
+void orc_epa_debug(long* out /*8 + 36*/) {
+    out[0] = g_epaStats.calls; out[1] = g_epaStats.epaIters; out[2] = g_epaStats.epaItersMax; out[3] = g_epaStats.faces;
+    out[4] = g_epaStats.facesMax; out[5] = g_epaStats.gjkIters; out[6] = g_epaStats.gjkItersMax; out[7] = 0;
+    for (int i = 0; i < 9; i++) for (int j = 0; j < 4; j++) out[8 + i * 4 + j] = g_epaStats.hist[i][j];
+}
+
 // ---- stand-alone kernels for known-answer tests ------------------------------------------
 // shape AABB for a shape under a transform (no +-threshold)
 void orc_shape_aabb(void* h, int shape, const float* xf12, float* out6) {
