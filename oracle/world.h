@@ -16,6 +16,7 @@
 #include <memory>
 #include <vector>
 #include "bvh.h"
+#include "dbvt_literal.h"
 #include "gjk.h"
 #include "jmath.h"
 #include "manifold.h"
@@ -23,7 +24,7 @@
 
 namespace orc {
 
-enum BroadphaseMode { BP_TIGHT = 0, BP_DBVT = 1 };
+enum BroadphaseMode { BP_TIGHT = 0, BP_DBVT = 1, BP_DBVT_LITERAL = 2 };  // 2: the reference's tree, literally (dbvt_literal.h)
 
 struct Body {
     int shape = -1;
@@ -40,6 +41,7 @@ struct Body {
     bool inFixed = false; // stage == STAGECOUNT
     int lastSetStep = -1; // step index of the last setAabb (createProxy counts as one)
     bool aabbOverflow = false;
+    LProxy* lit = nullptr; // BP_DBVT_LITERAL proxy
     int world = 0;        // batched independent worlds: each is its own CollisionWorld in the reference
 };
 
@@ -75,6 +77,7 @@ struct World {
     std::vector<std::pair<int, int>> pairs;  // sorted (uid0<uid1)
     std::map<std::pair<int, int>, PairState> pairState;
     std::vector<RawContact> raw;
+    LDbvtBroadphase literal;
     // counters
     long gjkChecks = 0, deepPenetrationChecks = 0, addedContacts = 0, bvhNodesVisited = 0, trianglesTested = 0;
 
@@ -126,10 +129,19 @@ struct World {
         b.leafMin = b.effMin; b.leafMax = b.effMax;
         b.inFixed = false;
         b.lastSetStep = step;
+        if (mode == BP_DBVT_LITERAL) {
+            literal.margin = dbvtMargin;
+            literal.predictedframes = predictedFrames;
+            b.lit = literal.createProxy(b.effMin, b.effMax, group, mask, world);
+        }
         bodies.push_back(b);
         return b.uid;
     }
-    void removeBody(int uid) { bodies[uid - 1].alive = false; }
+    void removeBody(int uid) {
+        Body& b = bodies[uid - 1];
+        if (b.alive && mode == BP_DBVT_LITERAL) literal.destroyProxy(b.lit);
+        b.alive = false;
+    }
 
     static bool intersect(const V3& amin, const V3& amax, const V3& bmin, const V3& bmax) {  // bp/DbvtAabbMm.java:209-212
         return (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
@@ -140,6 +152,12 @@ struct World {
     void setAabb(Body& b, const V3& mn, const V3& mx) {
         if (mode == BP_TIGHT) {  // bp/SimpleBroadphase.java:112-116
             b.effMin = mn; b.effMax = mx;
+            b.lastSetStep = step;
+            return;
+        }
+        if (mode == BP_DBVT_LITERAL) {
+            literal.setAabb(b.lit, mn, mx);
+            b.effMin = b.lit->aabb.mi; b.effMax = b.lit->aabb.mx;
             b.lastSetStep = step;
             return;
         }
@@ -202,6 +220,14 @@ struct World {
 
     // BroadphaseInterface.calculateOverlappingPairs: resulting pair set
     int calculateOverlappingPairs() {
+        if (mode == BP_DBVT_LITERAL) {
+            literal.collide();
+            pairs.clear();
+            for (auto& pr : literal.pairArray) pairs.push_back(std::make_pair(pr.first->uid, pr.second->uid));
+            std::sort(pairs.begin(), pairs.end());
+            step++;
+            return (int)pairs.size();
+        }
         if (mode == BP_DBVT) {
             // bp/DbvtBroadphase.java:96-111: proxies not updated during this step (but updated the step
             // before) move to the fixed set; eff is kept, leaf volume becomes eff.

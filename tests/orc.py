@@ -76,7 +76,7 @@ def xf12(basis=None, origin=(0, 0, 0)):
     return np.concatenate([b.reshape(9), np.asarray(origin, dtype=np.float32)]).astype(np.float32)
 
 
-TIGHT, DBVT = 0, 1
+TIGHT, DBVT, DBVT_LITERAL = 0, 1, 2
 
 
 class OracleWorld:
