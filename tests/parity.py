@@ -118,3 +118,29 @@ def step_and_compare(gw, ow, xf, extent, active=None, check_aabbs=True):
     r.update(m)
     r["pairs"] = int(len(gp))
     return r
+
+
+# ---- golden fixtures (tests/golden/*.npz, produced by tests/golden/make_golden.py from the oracle) -----------
+def golden_cases():
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.CASES, here
+
+
+def compare_gpu_to_golden(gw, sc, gold, steps, extent):
+    """Drive the CUDA world through the trace and compare every step with the stored oracle outputs."""
+    for step in range(steps):
+        gw.setWorldTransforms(sc.transforms(step))
+        gw.updateAabbs()
+        compare_aabbs(gw.aabbs(), gold[f"aabb{step}"])
+        gw.getBroadphase().calculateOverlappingPairs()
+        compare_pairs(gw.pairs(), gold[f"pairs{step}"])
+        gw.getDispatcher().dispatchAllCollisionPairs()
+        oi = np.zeros((len(gold[f"raw_i{step}"]), 6), np.int32)
+        oi[:, :5] = gold[f"raw_i{step}"]
+        compare_raw(gw.raw_contacts(), (oi, gold[f"raw_f{step}"]), extent)
+        compare_manifolds(gw.manifolds(), (gold[f"mf_hdr{step}"], gold[f"mf_pts{step}"], gold[f"mf_int{step}"]), extent)
