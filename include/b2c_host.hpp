@@ -1,0 +1,151 @@
+// b2c_host.hpp — C++ host-side mirror of the reference's collision interfaces over the C ABI (b2c.h).
+//
+// The reference is compiled Java and this image has no JDK, so the host side above the C ABI is written in
+// C++ (and, for the pytest harness, in Python: libgdx-jbullet_b200/world.py).  Class and method names follow
+//   bp/BroadphaseInterface.java:33-52   -> GpuBroadphase
+//   bp/OverlappingPairCache.java:34-54  -> GpuPairCache
+//   bp/Dispatcher.java:38-68            -> GpuDispatcher
+//   disp/CollisionWorld.java:98-245     -> GpuCollisionWorld
+// with the same argument meaning and call order, so a port of a reference test reads the same.  Header-only;
+// link with libb2c.so.  Errors surface as std::runtime_error carrying b2c_last_error_string.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b2c.h"
+
+namespace b2c_host {
+
+struct Vector3 { float x, y, z; };
+struct Transform { float basis[9]; float origin[3]; };  // row-major basis (lm/Transform.java:46-49)
+struct BroadphasePair { int32_t proxy0, proxy1; };      // uids (bp/BroadphasePair.java:37-40)
+
+inline void check(int32_t rc, b2c_ctx* ctx) {
+    if (rc != B2C_OK) throw std::runtime_error("b2c error " + std::to_string(rc) + ": " + b2c_last_error_string(ctx));
+}
+
+class GpuCollisionWorld;
+
+class GpuPairCache {
+public:
+    explicit GpuPairCache(b2c_ctx* c) : ctx(c) {}
+    int getNumOverlappingPairs() const { return num; }
+    const std::vector<BroadphasePair>& getOverlappingPairArray() {
+        int32_t n = 0;
+        check(b2c_get_pairs(ctx, nullptr, 0, &n), ctx);
+        pairs.resize((size_t)n);
+        if (n) check(b2c_get_pairs(ctx, reinterpret_cast<int32_t*>(pairs.data()), n, &n), ctx);
+        return pairs;
+    }
+    int num = 0;
+private:
+    b2c_ctx* ctx;
+    std::vector<BroadphasePair> pairs;
+};
+
+class GpuDispatcher {
+public:
+    explicit GpuDispatcher(b2c_ctx* c) : ctx(c) {}
+    void dispatchAllCollisionPairs(GpuPairCache*, void* /*dispatchInfo*/, GpuDispatcher*) {
+        check(b2c_dispatch_all_pairs(ctx, &numManifolds, &numContactsAdded), ctx);
+        fetched = false;
+    }
+    int getNumManifolds() const { return numManifolds; }
+    const b2c_manifold& getManifoldByIndexInternal(int i) {
+        if (!fetched) {
+            int32_t n = 0;
+            check(b2c_get_manifolds(ctx, nullptr, 0, 0, &n), ctx);
+            manifolds.resize((size_t)n);
+            if (n) check(b2c_get_manifolds(ctx, manifolds.data(), n, 0, &n), ctx);
+            fetched = true;
+        }
+        return manifolds.at((size_t)i);
+    }
+    int32_t numManifolds = 0, numContactsAdded = 0;
+private:
+    b2c_ctx* ctx;
+    std::vector<b2c_manifold> manifolds;
+    bool fetched = false;
+};
+
+class GpuBroadphase {
+public:
+    explicit GpuBroadphase(b2c_ctx* c) : ctx(c), cache(c) {}
+    // setAabb (bp/BroadphaseInterface.java:39) for hosts that compute AABBs themselves
+    void setAabb(int32_t uid, const Vector3& mn, const Vector3& mx, GpuDispatcher* = nullptr) {
+        float mm[6] = {mn.x, mn.y, mn.z, mx.x, mx.y, mx.z};
+        check(b2c_set_aabbs(ctx, 1, &uid, mm), ctx);
+    }
+    void destroyProxy(int32_t uid, GpuDispatcher* = nullptr) { check(b2c_proxy_destroy(ctx, uid), ctx); }
+    void calculateOverlappingPairs(GpuDispatcher* = nullptr) {
+        int32_t n = 0;
+        check(b2c_calculate_overlapping_pairs(ctx, &n), ctx);
+        cache.num = n;
+    }
+    GpuPairCache* getOverlappingPairCache() { return &cache; }
+    void getBroadphaseAabb(Vector3& mn, Vector3& mx) {
+        float a[3], b[3];
+        check(b2c_get_broadphase_aabb(ctx, a, b), ctx);
+        mn = {a[0], a[1], a[2]};
+        mx = {b[0], b[1], b[2]};
+    }
+private:
+    b2c_ctx* ctx;
+    GpuPairCache cache;
+};
+
+class GpuCollisionWorld {
+public:
+    explicit GpuCollisionWorld(const b2c_config& cfg) {
+        int32_t rc = b2c_create(&cfg, &ctx);
+        if (rc != B2C_OK) throw std::runtime_error("b2c_create failed (" + std::to_string(rc) + "): no sm_100 device? there is no CPU fallback");
+        broadphase = new GpuBroadphase(ctx);
+        dispatcher = new GpuDispatcher(ctx);
+    }
+    ~GpuCollisionWorld() { delete broadphase; delete dispatcher; b2c_destroy(ctx); }
+    GpuCollisionWorld(const GpuCollisionWorld&) = delete;
+    GpuCollisionWorld& operator=(const GpuCollisionWorld&) = delete;
+
+    int32_t BoxShape(const Vector3& he) { int32_t s; float h[3] = {he.x, he.y, he.z}; check(b2c_shape_register_box(ctx, h, -1.f, &s), ctx); return s; }
+    int32_t SphereShape(float r) { int32_t s; check(b2c_shape_register_sphere(ctx, r, &s), ctx); return s; }
+    int32_t ConvexHullShape(const std::vector<Vector3>& pts) {
+        int32_t s;
+        check(b2c_shape_register_hull(ctx, &pts[0].x, (int32_t)pts.size(), -1.f, &s), ctx);
+        return s;
+    }
+    int32_t StaticPlaneShape(const Vector3& n, float c) { int32_t s; float v[3] = {n.x, n.y, n.z}; check(b2c_shape_register_plane(ctx, v, c, &s), ctx); return s; }
+
+    // disp/CollisionWorld.java:102-121
+    int32_t addCollisionObject(int32_t shape, const Transform& t, int16_t group = 1, int16_t mask = -1, bool isStatic = false) {
+        int32_t uid = 0;
+        float t12[12];
+        for (int i = 0; i < 9; i++) t12[i] = t.basis[i];
+        for (int i = 0; i < 3; i++) t12[9 + i] = t.origin[i];
+        check(b2c_proxy_create(ctx, shape, t12, group, mask, isStatic ? 1 : 0, 0, &uid), ctx);
+        numBodies = uid;
+        return uid;
+    }
+    void removeCollisionObject(int32_t uid) { check(b2c_proxy_destroy(ctx, uid), ctx); }
+    // transforms of bodies 1..n as the ABI's 12 SoA planes
+    void setWorldTransformPlanes(int32_t n, const float* planes12) { check(b2c_set_transforms(ctx, n, nullptr, planes12), ctx); }
+    void updateAabbs() { check(b2c_update_aabbs(ctx), ctx); }                            // :231-245
+    void performDiscreteCollisionDetection() {                                           // :123-151
+        updateAabbs();
+        broadphase->calculateOverlappingPairs(dispatcher);
+        dispatcher->dispatchAllCollisionPairs(broadphase->getOverlappingPairCache(), nullptr, dispatcher);
+    }
+    GpuBroadphase* getBroadphase() { return broadphase; }
+    GpuPairCache* getPairCache() { return broadphase->getOverlappingPairCache(); }
+    GpuDispatcher* getDispatcher() { return dispatcher; }
+    b2c_ctx* handle() { return ctx; }
+    int32_t numBodies = 0;
+private:
+    b2c_ctx* ctx = nullptr;
+    GpuBroadphase* broadphase = nullptr;
+    GpuDispatcher* dispatcher = nullptr;
+};
+
+}  // namespace b2c_host

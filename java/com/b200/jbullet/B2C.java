@@ -1,0 +1,69 @@
+package com.b200.jbullet;
+
+import java.lang.foreign.*;
+import java.lang.invoke.MethodHandle;
+
+import static java.lang.foreign.ValueLayout.*;
+
+/**
+ * Panama FFM (JDK 22+) binding of include/b2c.h — the thin C-ABI layer of the B200 collision path.
+ * NOT COMPILED IN THIS REPOSITORY'S IMAGE (no JDK): authored against include/b2c.h, see INTEGRATION.md.
+ * Every handle below binds exactly one exported symbol of libb2c.so.
+ */
+final class B2C {
+    static final Linker LINKER = Linker.nativeLinker();
+    static final SymbolLookup LIB = SymbolLookup.libraryLookup(System.getProperty("b2c.library", "libb2c.so"), Arena.global());
+
+    private static MethodHandle h(String name, FunctionDescriptor fd) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
+    }
+
+    // b2c_config: 8 x int32, 3 x float, 5 x int32 reserved (64 bytes)
+    static final StructLayout CONFIG = MemoryLayout.structLayout(
+        JAVA_INT.withName("device"), JAVA_INT.withName("broadphase_mode"), JAVA_INT.withName("max_bodies"),
+        JAVA_INT.withName("max_pairs"), JAVA_INT.withName("max_shapes"), JAVA_INT.withName("max_hull_points"),
+        JAVA_INT.withName("max_mesh_items"), JAVA_INT.withName("num_worlds"),
+        JAVA_FLOAT.withName("contact_breaking_threshold"), JAVA_FLOAT.withName("dbvt_margin"),
+        JAVA_FLOAT.withName("dbvt_predicted_frames"), MemoryLayout.sequenceLayout(5, JAVA_INT).withName("reserved"));
+
+    static final MethodHandle defaultConfig = h("b2c_default_config", FunctionDescriptor.ofVoid(ADDRESS));
+    static final MethodHandle create = h("b2c_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle destroy = h("b2c_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    static final MethodHandle lastError = h("b2c_last_error_string", FunctionDescriptor.of(ADDRESS, ADDRESS));
+    static final MethodHandle shapeBox = h("b2c_shape_register_box", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_FLOAT, ADDRESS));
+    static final MethodHandle shapeSphere = h("b2c_shape_register_sphere", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_FLOAT, ADDRESS));
+    static final MethodHandle shapeHull = h("b2c_shape_register_hull", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_FLOAT, ADDRESS));
+    static final MethodHandle shapePlane = h("b2c_shape_register_plane", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_FLOAT, ADDRESS));
+    static final MethodHandle shapeMesh = h("b2c_shape_register_mesh",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle proxyCreate = h("b2c_proxy_create",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_SHORT, JAVA_SHORT, JAVA_INT, JAVA_INT, ADDRESS));
+    static final MethodHandle proxyDestroy = h("b2c_proxy_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    static final MethodHandle proxySetMaterial = h("b2c_proxy_set_material", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_FLOAT, JAVA_FLOAT));
+    static final MethodHandle setTransforms = h("b2c_set_transforms", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle setActivation = h("b2c_set_activation", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle setAabbs = h("b2c_set_aabbs", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle updateAabbs = h("b2c_update_aabbs", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle calculateOverlappingPairs = h("b2c_calculate_overlapping_pairs", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle getPairs = h("b2c_get_pairs", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+    static final MethodHandle dispatchAllPairs = h("b2c_dispatch_all_pairs", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle step = h("b2c_step", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle getContacts = h("b2c_get_contacts",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle getManifolds = h("b2c_get_manifolds", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
+
+    static void check(int rc, MemorySegment ctx) {
+        if (rc != 0) {
+            String msg;
+            try {
+                msg = ((MemorySegment) lastError.invokeExact(ctx)).reinterpret(256).getString(0);
+            } catch (Throwable t) {
+                msg = "?";
+            }
+            throw new IllegalStateException("b2c error " + rc + ": " + msg);
+        }
+    }
+
+    private B2C() {
+    }
+}
