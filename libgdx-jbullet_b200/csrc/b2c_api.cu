@@ -83,7 +83,9 @@ struct b2c_ctx {
     int2* dPairs = nullptr;
     uint64_t* dSortedKeys[2] = {nullptr, nullptr};
     uint32_t* dNumPairs[2] = {nullptr, nullptr};
-    b2c_manifold* dManifolds[2] = {nullptr, nullptr};
+    ManifoldHdr* dMHdr[2] = {nullptr, nullptr};
+    b2c_manifold_point* dMPts[2] = {nullptr, nullptr};
+    uint32_t* dPairFirst[2] = {nullptr, nullptr};  // first pair index per uid0 (for the next step's carry)
     int cur = 0;  // index of this step's pair keys / manifolds
     bool pairsValid = false;
 
@@ -298,8 +300,11 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     // manifolds follow their pair into the new list (done here so a step without dispatch keeps them too)
     k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
                                                                       ctx->dSortedKeys[cur ^ 1], ctx->dNumPairs[cur ^ 1],
-                                                                      ctx->dManifolds[cur ^ 1], ctx->dManifolds[cur], ctx->uidBits);
-    ctx->launches += 7 + ctx->sortBodies.launches + ctx->sortPairs.launches;
+                                                                      ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
+                                                                      ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits);
+    k_pair_first<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairs, ctx->dNumPairs[cur], ctx->dPairFirst[cur],
+                                                                           (uint32_t)ctx->cfg.max_bodies);
+    ctx->launches += 8 + ctx->sortBodies.launches + ctx->sortPairs.launches;
     CK(cudaGetLastError());
     ctx->step++;
     ctx->pairsValid = true;
@@ -321,7 +326,8 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.shapes = ctx->dShapes;
     a.hullPts = ctx->dHullPts;
     a.meshes = ctx->dMeshes;
-    a.manifolds = ctx->dManifolds[ctx->cur];
+    a.mhdr = ctx->dMHdr[ctx->cur];
+    a.mpts = ctx->dMPts[ctx->cur];
     a.raw = ctx->dRaw;
     a.binKeys[0] = ctx->dBinKeys[0];
     a.binKeys[1] = ctx->dBinKeys[1];
@@ -505,7 +511,9 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         CKC(dalloc(&ctx->dPairKeys[i], P));
         CKC(dalloc(&ctx->dSortedKeys[i], P));
         CKC(dalloc(&ctx->dNumPairs[i], (size_t)1));
-        CKC(dalloc(&ctx->dManifolds[i], P));
+        CKC(dalloc(&ctx->dMHdr[i], P));
+        CKC(dalloc(&ctx->dMPts[i], 4 * P));
+        CKC(dalloc(&ctx->dPairFirst[i], N + 4));
     }
     CKC(dalloc(&ctx->dSide, (size_t)4));
     CKC(dalloc(&ctx->dSmin, N));
@@ -561,7 +569,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dStaging); cudaFreeHost(ctx->hStagingPinned); cudaFree(ctx->dExtAabb); cudaFree(ctx->dExtMask);
     for (int i = 0; i < 2; i++) {
         cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dPairKeys[i]); cudaFree(ctx->dSortedKeys[i]);
-        cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dManifolds[i]);
+        cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dMHdr[i]); cudaFree(ctx->dMPts[i]); cudaFree(ctx->dPairFirst[i]);
     }
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
@@ -1013,19 +1021,24 @@ int32_t b2c_get_manifolds(b2c_ctx* ctx, b2c_manifold* out, int32_t cap, int32_t 
     uint32_t n = 0;
     CK(cudaMemcpyAsync(&n, ctx->dNumPairs[ctx->cur], sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<b2c_manifold> all(n);
+    std::vector<ManifoldHdr> hdr(n);
+    std::vector<b2c_manifold_point> pts(4 * (size_t)n);
     if (n) {
-        CK(cudaMemcpyAsync(all.data(), ctx->dManifolds[ctx->cur], (size_t)n * sizeof(b2c_manifold), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hdr.data(), ctx->dMHdr[ctx->cur], (size_t)n * sizeof(ManifoldHdr), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(pts.data(), ctx->dMPts[ctx->cur], 4 * (size_t)n * sizeof(b2c_manifold_point), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     int32_t k = 0;
     for (uint32_t p = 0; p < n; p++) {
-        const b2c_manifold& m = all[p];
-        if (m.algorithm == 0) continue;
-        if (onlyTouching && m.num_contacts == 0) continue;
+        const ManifoldHdr& h = hdr[p];
+        if (h.algorithm == 0) continue;
+        if (onlyTouching && h.num_contacts == 0) continue;
         if (out && k < cap) {
-            out[k] = m;
-            for (int q = m.num_contacts; q < 4; q++) memset(&out[k].points[q], 0, sizeof(b2c_manifold_point));
+            b2c_manifold& m = out[k];
+            memset(&m, 0, sizeof(m));
+            m.pair_uid0 = h.pair_uid0; m.pair_uid1 = h.pair_uid1; m.body0 = h.body0; m.body1 = h.body1;
+            m.num_contacts = h.num_contacts; m.algorithm = h.algorithm;
+            for (int q = 0; q < h.num_contacts && q < 4; q++) m.points[q] = pts[4 * (size_t)p + q];
         }
         k++;
     }

@@ -376,23 +376,46 @@ __device__ __forceinline__ bool filterPass(uint32_t fa, uint32_t fb) {  // bp/Ha
     return ((fa & 0xffffu) & (fb >> 16)) != 0 && ((fb & 0xffffu) & (fa >> 16)) != 0;
 }
 
-// Warp-aggregated pair append: one atomic per warp per round (ballot + popc + shuffle).
-__device__ __forceinline__ void emitPair(bool hit, uint32_t bodyA, uint32_t bodyB, int uidBits, uint64_t* __restrict__ pairKeys,
-                                         uint32_t maxPairs, StepCounters* ctr) {
-    uint32_t m = __ballot_sync(0xffffffffu, hit);
-    if (m == 0) return;
-    int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == (__ffs(m) - 1)) base = atomicAdd(&ctr->pairCount, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (hit) {
-        uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-        uint32_t ua = bodyA + 1u, ub = bodyB + 1u;  // uid = slot + 1 (bp/DbvtBroadphase.java:179)
-        uint32_t lo = ua < ub ? ua : ub, hi = ua < ub ? ub : ua;  // bp/HashedOverlappingPairCache.java:292-296
-        if (pos < maxPairs) pairKeys[pos] = ((uint64_t)lo << uidBits) | hi;
-        else ctr->pairOverflow = 1;
+// Warp-staged pair append.  A single global counter cannot take one atomic per warp round (same-address
+// atomics serialise in L2: ~300 k of them per step cost more than the sweep itself), so every warp stages its
+// hits in a private shared-memory buffer (ballot + popc for the slot) and flushes 32+ pairs at a time with ONE
+// global atomic and coalesced 8-byte stores.
+constexpr int PAIR_STAGE = 96;  // per-warp staging capacity (flush when > 64 are waiting)
+
+struct PairStager {
+    uint64_t* buf;   // this warp's shared-memory slice
+    int count;       // warp-uniform
+    __device__ __forceinline__ void init(uint64_t* warpBuf) { buf = warpBuf; count = 0; }
+    __device__ __forceinline__ void flush(uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr) {
+        if (count == 0) return;
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->pairCount, (uint32_t)count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int k = lane; k < count; k += 32) {
+            uint32_t pos = base + k;
+            if (pos < maxPairs) pairKeys[pos] = buf[k];
+            else ctr->pairOverflow = 1;
+        }
+        __syncwarp();
+        count = 0;
     }
-}
+    // all 32 lanes call this together
+    __device__ __forceinline__ void push(bool hit, uint32_t bodyA, uint32_t bodyB, int uidBits, uint64_t* __restrict__ pairKeys,
+                                         uint32_t maxPairs, StepCounters* ctr) {
+        uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m == 0) return;
+        if (hit) {
+            int lane = threadIdx.x & 31;
+            uint32_t ua = bodyA + 1u, ub = bodyB + 1u;  // uid = slot + 1 (bp/DbvtBroadphase.java:179)
+            uint32_t lo = ua < ub ? ua : ub, hi = ua < ub ? ub : ua;  // bp/HashedOverlappingPairCache.java:292-296
+            buf[count + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)lo << uidBits) | hi;
+        }
+        count += __popc(m);
+        if (count > PAIR_STAGE - 32) flush(pairKeys, maxPairs, ctr);
+    }
+};
 
 // k_sweep: blockIdx.y selects one of the 9 neighbour rows (dy,dz); each lane owns one sorted proxy i and
 // walks the x-window of that row: lower_bound(min.x_i) then forward while min.x_j <= max.x_i.  The warp
@@ -402,6 +425,9 @@ __global__ void __launch_bounds__(256)
 k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ srow,
         const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
         uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr) {
+    __shared__ uint64_t stage[8][PAIR_STAGE];
+    PairStager st;
+    st.init(stage[threadIdx.x >> 5]);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = blockIdx.y;  // 0..8
     const int dy = nb / 3 - 1, dz = nb % 3 - 1;
@@ -455,8 +481,9 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                 j++;
             }
         }
-        emitPair(hit, __float_as_uint(amin.w), bodyB, uidBits, pairKeys, maxPairs, ctr);
+        st.push(hit, __float_as_uint(amin.w), bodyB, uidBits, pairKeys, maxPairs, ctr);
     }
+    st.flush(pairKeys, maxPairs, ctr);
 }
 
 // k_large: proxies that do not fit the grid (row == nrows) against every proxy of the same world, and
@@ -465,6 +492,9 @@ __global__ void __launch_bounds__(256)
 k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ rowStart,
         const GridParams* __restrict__ grid, const int* __restrict__ world, int numWorlds, int uidBits,
         uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr) {
+    __shared__ uint64_t stage[8][PAIR_STAGE];
+    PairStager st;
+    st.init(stage[threadIdx.x >> 5]);
     const int nrows = grid->nrows, rpw = grid->rowsPerWorld;
     const uint32_t l0 = rowStart[nrows], l1 = rowStart[nrows + 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) ctr->largeCount = l1 - l0;
@@ -491,9 +521,10 @@ k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                       (amin.z <= bmax.z) && (amax.z >= bmin.z) && filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
                 if (hit && numWorlds > 1 && j >= l0) hit = world[bodyB] == world[bodyA];
             }
-            emitPair(hit, bodyA, bodyB, uidBits, pairKeys, maxPairs, ctr);
+            st.push(hit, bodyA, bodyB, uidBits, pairKeys, maxPairs, ctr);
         }
     }
+    st.flush(pairKeys, maxPairs, ctr);
 }
 
 // k_pairs_unpack: sorted packed keys -> (uid0, uid1) int2 list; records the pair count for this step.

@@ -23,6 +23,16 @@ namespace b2c {
 
 enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_GJK0 = 3, BIN_MESH = 12, BIN_COUNT = 13 };
 
+// Device-side split of b2c_manifold: the 32-byte header every kernel streams, and the point slots only the
+// touching pairs read.  The ABI's 416-byte record is assembled when results are copied out.
+struct ManifoldHdr {
+    int pair_uid0, pair_uid1, body0, body1, num_contacts, algorithm, pad0, pad1;
+};
+struct MView {
+    ManifoldHdr* h;
+    b2c_manifold_point* p;
+};
+
 struct NpArgs {
     const int2* pairs;            // sorted (uid0, uid1)
     uint32_t* numPairs;           // device
@@ -33,7 +43,8 @@ struct NpArgs {
     const ShapeDev* shapes;
     const float4* hullPts;
     const MeshDev* meshes;
-    b2c_manifold* manifolds;      // [maxPairs] this step
+    ManifoldHdr* mhdr;            // [maxPairs] this step: 32-byte manifold headers (SoA: streamed by every kernel)
+    b2c_manifold_point* mpts;     // [4*maxPairs] this step: the 4 point slots of each manifold
     b2c_raw_contact* raw;         // [maxPairs]
     uint32_t* binKeys[2];         // [maxPairs] (bin << 24) | pairIndex, stably partitioned by bin (radix pass)
     const uint32_t* binSide;      // which of binKeys holds the partitioned list
@@ -43,17 +54,25 @@ struct NpArgs {
     uint32_t maxPairs;
 };
 
+__device__ __forceinline__ MView mview(const NpArgs& a, uint32_t p) {
+    MView m;
+    m.h = a.mhdr + p;
+    m.p = a.mpts + 4 * (size_t)p;
+    return m;
+}
+
 // ---- manifold (np/PersistentManifold.java, disp/ManifoldResult.java) ---------------------------------
+__device__ __forceinline__ MView mview(const struct NpArgs& a, uint32_t p);
 __device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
 __device__ __forceinline__ void st3(float* p, f3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 
 // np/PersistentManifold.java:83-156 sortCachedPoints + lm/VectorUtil.java:60-90 closestAxis4
-__device__ __forceinline__ int manifoldSortCachedPoints(const b2c_manifold* m, f3 newLocalA, float newDist) {
+__device__ __forceinline__ int manifoldSortCachedPoints(const MView& m, f3 newLocalA, float newDist) {
     int maxPenetrationIndex = -1;
     float maxPenetration = newDist;
     for (int i = 0; i < 4; i++)
-        if (m->points[i].distance < maxPenetration) { maxPenetrationIndex = i; maxPenetration = m->points[i].distance; }
-    f3 p0 = ld3(m->points[0].local_a), p1 = ld3(m->points[1].local_a), p2 = ld3(m->points[2].local_a), p3 = ld3(m->points[3].local_a);
+        if (m.p[i].distance < maxPenetration) { maxPenetrationIndex = i; maxPenetration = m.p[i].distance; }
+    f3 p0 = ld3(m.p[0].local_a), p1 = ld3(m.p[1].local_a), p2 = ld3(m.p[2].local_a), p3 = ld3(m.p[3].local_a);
     float res0 = 0.f, res1 = 0.f, res2 = 0.f, res3 = 0.f;
     if (maxPenetrationIndex != 0) res0 = len2_3(crs3(sub3(newLocalA, p1), sub3(p3, p2)));
     if (maxPenetrationIndex != 1) res1 = len2_3(crs3(sub3(newLocalA, p0), sub3(p3, p2)));
@@ -71,11 +90,11 @@ __device__ __forceinline__ int manifoldSortCachedPoints(const b2c_manifold* m, f
 
 // disp/ManifoldResult.java:92-157 addContactPoint.  rootA/rootB are the transforms of the PAIR's
 // body0/body1 (ManifoldResult.init, :70-75); pairBody0 = uid of the pair's first body.
-__device__ __forceinline__ bool manifoldAdd(b2c_manifold* m, int pairBody0, const Xf& rootA, const Xf& rootB, f3 normal, f3 point,
+__device__ __forceinline__ bool manifoldAdd(const MView& m, int pairBody0, const Xf& rootA, const Xf& rootB, f3 normal, f3 point,
                                             float depth, float threshold, float friction, float restitution, int partId1,
                                             int index1) {
     if (depth > threshold) return false;
-    bool isSwapped = m->body0 != pairBody0;
+    bool isSwapped = m.h->body0 != pairBody0;
     f3 pointA = add3(scl3(normal, depth), point);
     f3 localA, localB;
     if (isSwapped) { localA = invXfPoint(rootB, pointA); localB = invXfPoint(rootA, point); }
@@ -83,9 +102,9 @@ __device__ __forceinline__ bool manifoldAdd(b2c_manifold* m, int pairBody0, cons
     // np/PersistentManifold.java:214-233 getCacheEntry
     float shortest = threshold * threshold;
     int nearest = -1;
-    int size = m->num_contacts;
+    int size = m.h->num_contacts;
     for (int i = 0; i < size; i++) {
-        f3 d = sub3(ld3(m->points[i].local_a), localA);
+        f3 d = sub3(ld3(m.p[i].local_a), localA);
         float dd = dot3(d, d);
         if (dd < shortest) { shortest = dd; nearest = i; }
     }
@@ -93,14 +112,14 @@ __device__ __forceinline__ bool manifoldAdd(b2c_manifold* m, int pairBody0, cons
     int idx;
     if (nearest >= 0) {  // :280-305 replaceContactPoint keeps lifetime (and the solver's cached impulses)
         idx = nearest;
-        life = m->points[idx].life_time;
-        src = m->points[idx].src_slot;
+        life = m.p[idx].life_time;
+        src = m.p[idx].src_slot;
     } else {             // :235-257 addManifoldPoint
         idx = size;
         if (idx == 4) idx = manifoldSortCachedPoints(m, localA, depth);
-        else m->num_contacts = size + 1;
+        else m.h->num_contacts = size + 1;
     }
-    b2c_manifold_point* p = &m->points[idx];
+    b2c_manifold_point* p = &m.p[idx];
     st3(p->local_a, localA); st3(p->local_b, localB);
     st3(p->world_a, pointA); st3(p->world_b, point);
     st3(p->normal_on_b, normal);
@@ -115,17 +134,17 @@ __device__ __forceinline__ bool manifoldAdd(b2c_manifold* m, int pairBody0, cons
 }
 
 // np/PersistentManifold.java:312-372 refreshContactPoints(trA, trB) incl. :259-278 removeContactPoint
-__device__ __forceinline__ void manifoldRefresh(b2c_manifold* m, const Xf& trA, const Xf& trB, float threshold) {
-    for (int i = m->num_contacts - 1; i >= 0; i--) {
-        b2c_manifold_point* p = &m->points[i];
+__device__ __forceinline__ void manifoldRefresh(const MView& m, const Xf& trA, const Xf& trB, float threshold) {
+    for (int i = m.h->num_contacts - 1; i >= 0; i--) {
+        b2c_manifold_point* p = &m.p[i];
         f3 wa = xfPoint(trA, ld3(p->local_a));
         f3 wb = xfPoint(trB, ld3(p->local_b));
         st3(p->world_a, wa); st3(p->world_b, wb);
         p->distance = dot3(sub3(wa, wb), ld3(p->normal_on_b));
         p->life_time++;
     }
-    for (int i = m->num_contacts - 1; i >= 0; i--) {
-        b2c_manifold_point* p = &m->points[i];
+    for (int i = m.h->num_contacts - 1; i >= 0; i--) {
+        b2c_manifold_point* p = &m.p[i];
         bool remove = false;
         if (!(p->distance <= threshold)) {
             remove = true;
@@ -136,20 +155,20 @@ __device__ __forceinline__ void manifoldRefresh(b2c_manifold* m, const Xf& trA, 
             if (dot3(diff, diff) > threshold * threshold) remove = true;
         }
         if (remove) {
-            int last = m->num_contacts - 1;
+            int last = m.h->num_contacts - 1;
             if (i != last) {
-                m->points[i] = m->points[last];
-                m->points[last].life_time = 0;
-                m->points[last].src_slot = -1;
+                m.p[i] = m.p[last];
+                m.p[last].life_time = 0;
+                m.p[last].src_slot = -1;
             }
-            m->num_contacts = last;
+            m.h->num_contacts = last;
         }
     }
 }
 // disp/ManifoldResult.java:177-191
-__device__ __forceinline__ void resultRefresh(b2c_manifold* m, int pairBody0, const Xf& rootA, const Xf& rootB, float threshold) {
-    if (m->num_contacts == 0) return;
-    if (m->body0 != pairBody0) manifoldRefresh(m, rootB, rootA, threshold);
+__device__ __forceinline__ void resultRefresh(const MView& m, int pairBody0, const Xf& rootA, const Xf& rootB, float threshold) {
+    if (m.h->num_contacts == 0) return;
+    if (m.h->body0 != pairBody0) manifoldRefresh(m, rootB, rootA, threshold);
     else manifoldRefresh(m, rootA, rootB, threshold);
 }
 // disp/ManifoldResult.java:160-175
@@ -163,44 +182,60 @@ __device__ __forceinline__ float combinedFriction(float f0, float f1) {
 // ---- k_carry: bring manifolds over from the previous step by pair key --------------------------------
 // A pair that stayed in the cache keeps its algorithm and manifold (bp/BroadphasePair.java:37-40); a pair
 // that left and came back starts empty (bp/HashedOverlappingPairCache.java:129-174 cleanOverlappingPair).
+// prevFirst[uid0] is the first previous pair whose uid0 is >= the given one, so the search is confined to the
+// handful of pairs that share uid0.
 __global__ void __launch_bounds__(256)
 k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs, const uint64_t* __restrict__ prevKeys,
-        const uint32_t* __restrict__ prevNum, const b2c_manifold* __restrict__ prevM, b2c_manifold* __restrict__ M, int uidBits) {
+        const uint32_t* __restrict__ prevNum, const uint32_t* __restrict__ prevFirst, const ManifoldHdr* __restrict__ prevH,
+        const b2c_manifold_point* __restrict__ prevP, ManifoldHdr* __restrict__ H, b2c_manifold_point* __restrict__ P, int uidBits) {
     const uint32_t n = *numPairs, pn = *prevNum;
     const int lane = threadIdx.x & 31;
-    // one warp per 32 pairs: each lane searches its pair, then the warp copies the 32 records with 16-byte
-    // accesses (26 int4 per record) so the copy is coalesced.
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
         uint32_t p = base + lane;
-        int found = -1;
-        uint64_t k = 0;
+        int found = -1, nc = 0;
         if (p < n) {
-            k = keys[p];
-            uint32_t a = 0, b = pn;
+            uint64_t k = keys[p];
+            uint32_t uid0 = (uint32_t)(k >> uidBits);
+            uint32_t a = pn ? prevFirst[uid0] : 0, b = pn ? prevFirst[uid0 + 1] : 0;
             while (a < b) {
                 uint32_t mid = (a + b) >> 1;
                 if (prevKeys[mid] < k) a = mid + 1; else b = mid;
             }
             if (a < pn && prevKeys[a] == k) found = (int)a;
-        }
-        for (int q = 0; q < 32; q++) {
-            uint32_t pq = base + q;
-            if (pq >= n) break;
-            int fq = __shfl_sync(0xffffffffu, found, q);
-            uint64_t kq = __shfl_sync(0xffffffffu, k, q);
-            int4* dst = reinterpret_cast<int4*>(M + pq);
-            if (fq >= 0) {
-                const int4* src = reinterpret_cast<const int4*>(prevM + fq);
-                int nc = prevM[fq].num_contacts;
-                int words = 2 + 6 * nc;  // header (32 B) + live points (96 B each)
-                if (lane < words) dst[lane] = src[lane];
-            } else if (lane < 2) {
-                int4 h;
-                if (lane == 0) h = make_int4((int)(kq >> uidBits), (int)(kq & ((1ull << uidBits) - 1ull)), 0, 0);
-                else h = make_int4(0, 0, 0, 0);
-                dst[lane] = h;
+            int4 h0, h1;
+            if (found >= 0) {
+                const int4* src = reinterpret_cast<const int4*>(prevH + found);
+                h0 = src[0]; h1 = src[1];
+                nc = h1.x;
+            } else {
+                h0 = make_int4((int)uid0, (int)(k & ((1ull << uidBits) - 1ull)), 0, 0);
+                h1 = make_int4(0, 0, 0, 0);
             }
+            int4* dst = reinterpret_cast<int4*>(H + p);   // adjacent lanes -> adjacent 32-byte headers
+            dst[0] = h0; dst[1] = h1;
         }
+        // live points: the warp copies them with 16-byte accesses (6 int4 per point)
+        uint32_t m = __ballot_sync(0xffffffffu, nc > 0);
+        while (m) {
+            int q = __ffs(m) - 1;
+            m &= m - 1;
+            int fq = __shfl_sync(0xffffffffu, found, q);
+            int nq = __shfl_sync(0xffffffffu, nc, q);
+            const int4* src = reinterpret_cast<const int4*>(prevP + 4 * (size_t)fq);
+            int4* dst = reinterpret_cast<int4*>(P + 4 * (size_t)(base + q));
+            if (lane < 6 * nq) dst[lane] = src[lane];
+        }
+    }
+}
+
+// prevFirst table for the NEXT step's k_carry: first[u] = first pair index whose uid0 >= u (u in 0..maxUid+1)
+__global__ void __launch_bounds__(256)
+k_pair_first(const int2* __restrict__ pairs, const uint32_t* __restrict__ numPairs, uint32_t* __restrict__ first, uint32_t maxUid) {
+    const uint32_t n = *numPairs;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += gridDim.x * blockDim.x) {
+        uint32_t cur = p < n ? (uint32_t)pairs[p].x : maxUid + 2u;
+        uint32_t prev = p ? (uint32_t)pairs[p - 1].x + 1u : 0u;
+        for (uint32_t u = prev; u <= cur && u <= maxUid + 1u; u++) first[u] = p;
     }
 }
 
@@ -248,9 +283,9 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
         int b0 = pr.x - 1, b1 = pr.y - 1;
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
         float r0 = a.shapes[a.shape[b0]].dims[0], r1 = a.shapes[a.shape[b1]].dims[0];
-        b2c_manifold* m = a.manifolds + p;
-        if (m->algorithm == 0) { m->algorithm = 1; m->body0 = pr.x; m->body1 = pr.y; }
-        for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
+        MView m = mview(a, p);
+        if (m.h->algorithm == 0) { m.h->algorithm = 1; m.h->body0 = pr.x; m.h->body1 = pr.y; }
+        for (int k = 0; k < m.h->num_contacts; k++) m.p[k].src_slot = k;
         f3 diff = sub3(t0.o, t1.o);
         float len = len3(diff);
         if (len > (r0 + r1)) {
@@ -297,9 +332,9 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
         const Xf& tc = swapped ? t1 : t0;
         const Xf& tp = swapped ? t0 : t1;
-        b2c_manifold* m = a.manifolds + p;
-        if (m->algorithm == 0) { m->algorithm = 2; m->body0 = bc + 1; m->body1 = bp + 1; }
-        for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
+        MView m = mview(a, p);
+        if (m.h->algorithm == 0) { m.h->algorithm = 2; m.h->body0 = bc + 1; m.h->body1 = bp + 1; }
+        for (int k = 0; k < m.h->num_contacts; k++) m.p[k].src_slot = k;
         f3 planeNormal = mk3(ps.plane[0], ps.plane[1], ps.plane[2]);
         float planeConstant = ps.plane[3];
         Xf planeInConvex = invMul(tc, tp);
@@ -318,7 +353,7 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
             float2 m0 = a.material[b0], m1 = a.material[b1];
             if (manifoldAdd(m, pr.x, t0, t1, nW, world, distance, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
         }
-        if (m->num_contacts != 0) resultRefresh(m, pr.x, t0, t1, a.threshold);
+        if (m.h->num_contacts != 0) resultRefresh(m, pr.x, t0, t1, a.threshold);
     }
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
 }
@@ -365,22 +400,39 @@ struct LaneShape {
     }
 };
 
-// Warp-level refill: idle lanes take the next items of [*cursor, end) with one atomic per warp round.
-__device__ __forceinline__ uint32_t takeItems(bool want, uint32_t* cursor, uint32_t end) {
-    uint32_t m = __ballot_sync(0xffffffffu, want);
-    uint32_t idx = 0xffffffffu;
-    if (m) {
-        int lane = threadIdx.x & 31;
-        uint32_t base = 0;
-        if (lane == (__ffs(m) - 1)) base = atomicAdd(cursor, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (want) {
-            idx = base + __popc(m & ((1u << lane) - 1u));
-            if (idx >= end) idx = 0xffffffffu;
+// Warp-level refill: idle lanes take the next items of [0, end).  The warp reserves CHUNK items at a time from
+// the global cursor (one same-address atomic per 32 items instead of one per round) and hands them out locally.
+struct WarpQueue {
+    uint32_t next, limit;  // warp-uniform: the warp's reserved range [next, limit)
+    __device__ __forceinline__ void init() { next = limit = 0; }
+    __device__ __forceinline__ uint32_t take(bool want, uint32_t* cursor, uint32_t end) {
+        constexpr uint32_t CHUNK = 32;
+        const int lane = threadIdx.x & 31;
+        uint32_t m = __ballot_sync(0xffffffffu, want);
+        uint32_t idx = 0xffffffffu;
+        if (m == 0) return idx;
+        uint32_t need = (uint32_t)__popc(m);
+        if (limit - next < need && limit != 0xffffffffu) {
+            // hand out what is left of the old chunk first, then reserve a new one
+            uint32_t have = limit - next;
+            uint32_t rank = __popc(m & ((1u << lane) - 1u));
+            if (want && rank < have) idx = next + rank;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, CHUNK);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (want && rank >= have) idx = base + (rank - have);
+            next = base + (need - have);
+            limit = base + CHUNK;
+            if (base >= end) limit = 0xffffffffu, next = 0xffffffffu;  // list exhausted: stop reserving
+        } else if (limit != 0xffffffffu) {
+            uint32_t rank = __popc(m & ((1u << lane) - 1u));
+            if (want) idx = next + rank;
+            next += need;
         }
+        if (idx != 0xffffffffu && idx >= end) idx = 0xffffffffu;
+        return idx;
     }
-    return idx;
-}
+};
 
 // k_gjk: convex-convex detector for the 8 type pairs of {box, sphere, hull}^2 minus sphere-sphere.
 // Persistent warps; each lane owns one pair at a time and all lanes step through GjkLane::iterate together.
@@ -395,9 +447,11 @@ __global__ void __launch_bounds__(128) k_gjk(NpArgs a, GjkArgs g, uint32_t* curs
     uint32_t p = 0;
     int2 pr = make_int2(0, 0);
     bool busy = false, more = true;
+    WarpQueue wq;
+    wq.init();
     while (true) {
         const bool want = !busy && more;
-        const uint32_t it = takeItems(want, cursor, count);  // one convergent call site for the whole warp
+        const uint32_t it = wq.take(want, cursor, count);  // one convergent call site for the whole warp
         if (want) {
             if (it == 0xffffffffu) {
                 more = false;
@@ -461,13 +515,13 @@ __global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
     for (uint32_t it = s0 + blockIdx.x * blockDim.x + threadIdx.x; it < e0; it += gridDim.x * blockDim.x) {
         uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
-        b2c_manifold* m = a.manifolds + p;
-        if (m->algorithm == 0) { m->algorithm = 3; m->body0 = pr.x; m->body1 = pr.y; }
-        const int nc = m->num_contacts;
+        MView m = mview(a, p);
+        if (m.h->algorithm == 0) { m.h->algorithm = 3; m.h->body0 = pr.x; m.h->body1 = pr.y; }
+        const int nc = m.h->num_contacts;
         const b2c_raw_contact* r = a.raw + p;
         const bool has = r->has_contact == 1;
         if (nc == 0 && !has) continue;  // nothing to add, nothing to refresh
-        for (int k = 0; k < nc; k++) m->points[k].src_slot = k;
+        for (int k = 0; k < nc; k++) m.p[k].src_slot = k;
         int b0 = pr.x - 1, b1 = pr.y - 1;
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
         if (has) {
@@ -552,10 +606,10 @@ __global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
         const ShapeDev& cs = swapped ? s1 : s0;
         const ShapeDev& ms = swapped ? s0 : s1;
         Xf tc = loadXf(a.xf4, bc), tt = loadXf(a.xf4, bt);
-        b2c_manifold* m = a.manifolds + p;
-        m->algorithm = 4;
-        m->body0 = bc + 1; m->body1 = bt + 1;  // manifoldPtr.setBodies(convexBody, triBody)
-        for (int k = 0; k < m->num_contacts; k++) m->points[k].src_slot = k;
+        MView m = mview(a, p);
+        m.h->algorithm = 4;
+        m.h->body0 = bc + 1; m.h->body1 = bt + 1;  // manifoldPtr.setBodies(convexBody, triBody)
+        for (int k = 0; k < m.h->num_contacts; k++) m.p[k].src_slot = k;
         MeshDev md = a.meshes[ms.mesh];
         Xf convexInTri = invMul(tt, tc);
         f3 mn, mx;
@@ -606,9 +660,11 @@ __global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g, uint32_t* 
     int tri = 0;
     int2 pr = make_int2(0, 0);
     bool busy = false, more = true;
+    WarpQueue wq;
+    wq.init();
     while (true) {
         const bool want = !busy && more;
-        const uint32_t it = takeItems(want, cursor, nItems);
+        const uint32_t it = wq.take(want, cursor, nItems);
         if (want) {
             if (it == 0xffffffffu) {
                 more = false;
@@ -766,7 +822,7 @@ __global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
-        b2c_manifold* m = a.manifolds + p;
+        MView m = mview(a, p);
         float2 m0 = a.material[b0], m1 = a.material[b1];
         float fr = combinedFriction(m0.x, m1.x), re = m0.y * m1.y;
         uint32_t st = g.meshStart[p], cn = g.meshCount[p];
@@ -793,7 +849,7 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, b2c_manifold_
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
         uint32_t p = base + lane;
         int nc = 0;
-        if (p < n && a.manifolds[p].algorithm != 0) nc = a.manifolds[p].num_contacts;
+        if (p < n && a.mhdr[p].algorithm != 0) nc = a.mhdr[p].num_contacts;
         uint32_t m = __ballot_sync(0xffffffffu, nc > 0);
         if (m == 0) continue;
         // warp totals: headers = popc(m), points = sum nc (inclusive scan by shuffles)
@@ -814,13 +870,13 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, b2c_manifold_
             uint32_t h = baseH + __popc(m & ((1u << lane) - 1u));
             uint32_t fp = baseP + (uint32_t)(incl - nc);
             if (h < capH && fp + nc <= capP) {
-                const b2c_manifold* mf = a.manifolds + p;
+                const ManifoldHdr* mf = a.mhdr + p;
                 b2c_contact_header hh;
                 hh.pair_uid0 = mf->pair_uid0; hh.pair_uid1 = mf->pair_uid1; hh.body0 = mf->body0; hh.body1 = mf->body1;
                 hh.num_contacts = nc; hh.algorithm = mf->algorithm; hh.first_point = (int)fp; hh.pair_index = (int)p;
                 hdr[h] = hh;
                 for (int k = 0; k < nc; k++) {
-                    const int4* src = reinterpret_cast<const int4*>(&mf->points[k]);
+                    const int4* src = reinterpret_cast<const int4*>(a.mpts + 4 * (size_t)p + k);
                     int4* dst = reinterpret_cast<int4*>(pts + fp + k);
                     for (int q = 0; q < 6; q++) dst[q] = src[q];
                 }
@@ -834,7 +890,7 @@ __global__ void __launch_bounds__(256) k_count_manifolds(NpArgs a) {
     const uint32_t n = *a.numPairs;
     uint32_t c = 0;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-        if (a.manifolds[p].algorithm != 0) c++;
+        if (a.mhdr[p].algorithm != 0) c++;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&a.ctr->numManifolds, c);
 }
