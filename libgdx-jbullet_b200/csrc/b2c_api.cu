@@ -93,6 +93,7 @@ struct b2c_ctx {
     b2c_raw_contact* dRaw = nullptr;
     uint32_t* dBinKeys[2] = {nullptr, nullptr};
     uint32_t* dCursors = nullptr;
+    uint32_t* dSurvivors = nullptr;
     RadixSorter sortBins;
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
@@ -373,8 +374,9 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, s>>>(a); ctx->launches++; }
     mark(ctx, 10);
     CK(cudaMemsetAsync(ctx->dCursors, 0, 4 * sizeof(uint32_t), s));
-    k_gjk<<<148 * 4, 128, 0, s>>>(a, g, ctx->dCursors);
-    ctx->launches++;
+    k_gjk_prefilter<<<148 * 8, 256, 0, s>>>(a, ctx->dSurvivors, ctx->dCursors + 2);
+    k_gjk<<<148 * GJK_MINB, 128, 0, s>>>(a, g, ctx->dCursors, ctx->dSurvivors, ctx->dCursors + 2);
+    ctx->launches += 2;
     if (ctx->hasMesh) {
         k_mesh_query<<<148 * 4, 128, 0, s>>>(a, g);
         k_gjk_tri<<<148 * 4, 128, 0, s>>>(a, g, ctx->dCursors + 1);
@@ -534,6 +536,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dBinKeys[1], P));
     CKC(ctx->sortBins.init((uint32_t)P));
     CKC(dalloc(&ctx->dCursors, (size_t)4));
+    CKC(dalloc(&ctx->dSurvivors, P));
     ctx->maxEpa = (uint32_t)(P / 4 + 1024);
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
     CKC(dalloc(&ctx->dEpaScratch, (size_t)EPA_GRID2 * EPA_BLOCK2));
@@ -574,7 +577,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); ctx->sortBins.destroy();
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -434,12 +434,87 @@ struct WarpQueue {
     }
 };
 
+// k_gjk_prefilter: the first two trips of the GJK loop as straight-line code, one thread per pair, no
+// divergence.  About two thirds of the AABB-overlapping pairs end in trip 2 through the separating-axis early
+// out (np/GjkPairDetector.java:154: delta > 0 && delta^2 > squaredDistance * maximumDistanceSquared); for
+// those the detector result is final here (no contact, lastUsedMethod -1, curIter 1).  Every other pair —
+// including anything unusual in trip 1 — goes to the survivor list and is run from scratch by k_gjk, so this
+// kernel only has to be exact when it says "done".
+__global__ void __launch_bounds__(256) k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict__ survCount) {
+    const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
+    __shared__ uint32_t warpCnt[8];
+    __shared__ uint32_t blockBase;
+    uint32_t checks = 0;
+    for (uint32_t base = s0 + blockIdx.x * blockDim.x; base < e0; base += gridDim.x * blockDim.x) {
+        const uint32_t it = base + threadIdx.x;
+        bool survive = false;
+        uint32_t p = 0;
+        if (it < e0) {
+            p = binItem(a, it);
+            int2 pr = a.pairs[p];
+            const int b0 = pr.x - 1, b1 = pr.y - 1;
+            const ShapeDev& sa = a.shapes[a.shape[b0]];
+            const ShapeDev& sb = a.shapes[a.shape[b1]];
+            LaneShape A, B;
+            A.load(sa, a.hullPts);
+            B.load(sb, a.hullPts);
+            Xf ta = loadXf(a.xf4, b0), tb = loadXf(a.xf4, b1);
+            float maxd = sa.margin + sb.margin + a.threshold;
+            const float maxDistSq = maxd * maxd;
+            f3 positionOffset = scl3(add3(ta.o, tb.o), 0.5f);
+            f3 laO = sub3(ta.o, positionOffset), lbO = sub3(tb.o, positionOffset);
+            // trip 1 (axis (0,1,0), empty simplex)
+            f3 axis = mk3(0.f, 1.f, 0.f);
+            f3 pW = add3(mulMV(ta.m, A.support(mulMtV(ta.m, neg3(axis)))), laO);
+            f3 qW = add3(mulMV(tb.m, B.support(mulMtV(tb.m, axis))), lbO);
+            f3 w = sub3(pW, qW);
+            float delta = dot3(axis, w);
+            float sq = B2C_SIMD_INFINITY;
+            bool normal1 = !((delta > 0.f) && (delta * delta > sq * maxDistSq));
+            normal1 = normal1 && !eq3bits(w, mk3(1e30f, 1e30f, 1e30f));          // inSimplex against lastW
+            normal1 = normal1 && !((sq - delta) <= (sq * GJK_REL_ERROR2));        // f0 <= f1
+            axis = w;                                                             // one-vertex simplex: v = p - q
+            float sq1 = len2_3(axis);
+            normal1 = normal1 && !(sq1 < GJK_REL_ERROR2);
+            normal1 = normal1 && !((sq - sq1) <= B2C_FLT_EPSILON * sq);
+            // trip 2
+            pW = add3(mulMV(ta.m, A.support(mulMtV(ta.m, neg3(axis)))), laO);
+            qW = add3(mulMV(tb.m, B.support(mulMtV(tb.m, axis))), lbO);
+            w = sub3(pW, qW);
+            delta = dot3(axis, w);
+            bool done = normal1 && (delta > 0.f) && (delta * delta > sq1 * maxDistSq);
+            if (done) {
+                writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, -1, 1);
+                checks++;
+            }
+            survive = !done;
+        }
+        // block-aggregated append: one global atomic per block round
+        uint32_t m = __ballot_sync(0xffffffffu, survive);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) warpCnt[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int k = 0; k < 8; k++) { uint32_t c = warpCnt[k]; warpCnt[k] = tot; tot += c; }
+            blockBase = tot ? atomicAdd(survCount, tot) : 0;
+        }
+        __syncthreads();
+        if (survive) survivors[blockBase + warpCnt[warp] + __popc(m & ((1u << lane) - 1u))] = p;
+        __syncthreads();
+    }
+    if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
+}
+
 // k_gjk: convex-convex detector for the 8 type pairs of {box, sphere, hull}^2 minus sphere-sphere.
 // Persistent warps; each lane owns one pair at a time and all lanes step through GjkLane::iterate together.
 // Output is the raw detector record (or an EPA work item); manifolds are updated by k_manifold_cc.
-__global__ void __launch_bounds__(128) k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor) {
-    const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
-    const uint32_t count = e0 - s0;
+#ifndef GJK_MINB
+#define GJK_MINB 4
+#endif
+__global__ void __launch_bounds__(128, GJK_MINB)
+k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ survivors, const uint32_t* __restrict__ survCount) {
+    const uint32_t count = *survCount;
     uint32_t deep = 0, checks = 0;
     GjkLane L;
     LaneShape A, B;
@@ -456,7 +531,7 @@ __global__ void __launch_bounds__(128) k_gjk(NpArgs a, GjkArgs g, uint32_t* curs
             if (it == 0xffffffffu) {
                 more = false;
             } else {
-                p = binItem(a, s0 + it);
+                p = survivors[it];
                 pr = a.pairs[p];
                 const int b0 = pr.x - 1, b1 = pr.y - 1;
                 const ShapeDev& sa = a.shapes[a.shape[b0]];
