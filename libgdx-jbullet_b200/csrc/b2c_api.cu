@@ -64,7 +64,7 @@ struct b2c_ctx {
     int step = 0;
 
     // broadphase
-    uint64_t* dKeys[2] = {nullptr, nullptr};
+    uint32_t* dKeys[2] = {nullptr, nullptr};
     uint32_t* dVals[2] = {nullptr, nullptr};
     uint32_t* dSide = nullptr;        // [2]: body sort side, pair sort side
     float4* dSmin = nullptr;
@@ -91,6 +91,7 @@ struct b2c_ctx {
 
     // narrowphase
     b2c_raw_contact* dRaw = nullptr;
+    int8_t* dRawFlag = nullptr;
     uint32_t* dBinKeys[2] = {nullptr, nullptr};
     uint32_t* dCursors = nullptr;
     uint32_t* dSurvivors = nullptr;
@@ -223,7 +224,7 @@ __global__ void k_get_aabbs(BodyArrays B, int n, float* out) {
 __global__ void k_clear_np_counters(StepCounters* c) {
     if (threadIdx.x == 0) {
         c->contactsAdded = c->gjkChecks = c->deepChecks = c->epaFailed = 0;
-        c->meshItems = c->meshOverflow = c->numManifolds = c->epaCount = c->epaRetry = 0;
+        c->meshItems = c->meshOverflow = c->epaCount = c->epaRetry = 0;
     }
     if (threadIdx.x < 16) c->binCount[threadIdx.x] = 0;
 }
@@ -277,8 +278,8 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     int rowBits = bitsFor((uint32_t)ctx->maxRows + 2u);
     mark(ctx, 2);
     ctx->sortBodies.launches = 0;
-    ctx->sortBodies.sort<uint64_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nullptr, (uint32_t)n,
-                                         32 + rowBits, ctx->dSide, s);
+    ctx->sortBodies.sort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nullptr, (uint32_t)n,
+                                         12 + rowBits, ctx->dSide, s);
     mark(ctx, 3);
     k_gather<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->dSide, ctx->dGrid,
                                 ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart);
@@ -302,7 +303,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
                                                                       ctx->dSortedKeys[cur ^ 1], ctx->dNumPairs[cur ^ 1],
                                                                       ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
-                                                                      ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits);
+                                                                      ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr);
     k_pair_first<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairs, ctx->dNumPairs[cur], ctx->dPairFirst[cur],
                                                                            (uint32_t)ctx->cfg.max_bodies);
     ctx->launches += 8 + ctx->sortBodies.launches + ctx->sortPairs.launches;
@@ -330,6 +331,7 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.mhdr = ctx->dMHdr[ctx->cur];
     a.mpts = ctx->dMPts[ctx->cur];
     a.raw = ctx->dRaw;
+    a.rawFlag = ctx->dRawFlag;
     a.binKeys[0] = ctx->dBinKeys[0];
     a.binKeys[1] = ctx->dBinKeys[1];
     a.binSide = ctx->dSide + 2;
@@ -388,8 +390,6 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     k_manifold_cc<<<148 * 8, 256, 0, s>>>(a);
     ctx->launches += 3;
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
-    k_count_manifolds<<<pg, 256, 0, s>>>(a);
-    ctx->launches++;
     mark(ctx, 12);
     ctx->stageValid = ctx->prof;
     CK(cudaGetLastError());
@@ -522,6 +522,8 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dSmax, N));
     CKC(dalloc(&ctx->dSrow, N));
     ctx->maxRows = (int)(2 * N + 64 > (size_t)(64 * cfg->num_worlds) ? 2 * N + 64 : (size_t)(64 * cfg->num_worlds));
+    if (ctx->maxRows > (1 << 20) - 4) ctx->maxRows = (1 << 20) - 4;  // the row shares a 32-bit key with 12 bits of x
+    if ((long long)cfg->num_worlds * 4 > ctx->maxRows) return fail(B2C_ERR_BAD_ARG);
     CKC(dalloc(&ctx->dRowStart, (size_t)ctx->maxRows + 8));
     CKC(dalloc(&ctx->dGrid, (size_t)1));
     CKC(dalloc(&ctx->dCtr, (size_t)1));
@@ -531,6 +533,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     ctx->uidBits = bitsFor((uint32_t)N + 1u);
     CKC(dalloc(&ctx->dPairs, P));
     CKC(dalloc(&ctx->dRaw, P));
+    CKC(dalloc(&ctx->dRawFlag, P));
     if (P > (size_t)(1u << 24)) return fail(B2C_ERR_BAD_ARG);  // pair index must fit 24 bits next to the bin byte
     CKC(dalloc(&ctx->dBinKeys[0], P));
     CKC(dalloc(&ctx->dBinKeys[1], P));
@@ -577,7 +580,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

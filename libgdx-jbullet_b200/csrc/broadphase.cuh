@@ -7,7 +7,8 @@
 //       radix sort, k_gather, k_sweep, k_large (pair set == all filtered overlaps of the effective AABBs)
 //   bp/HashedOverlappingPairCache.java:179-188,291-296 (filter, uid ordering)           -> inside k_sweep/k_large
 //
-// Layout: 64-bit key = (row << 32) | floatKey(min.x).  row = world*ny*nz + cy*nz + cz is a coarse grid
+// Layout: 32-bit key = (row << 12) | qx, qx = min.x quantised to 12 bits over the gridded proxies' x range (any
+// monotone function of min.x orders the sweep correctly; the overlap test itself uses the original floats).  row = world*ny*nz + cy*nz + cz is a coarse grid
 // cell over the two non-sweep axes (cell >= the largest gridded extent, so overlapping proxies are in
 // adjacent rows); proxies too large for the grid (static planes, meshes, big static boxes) share one
 // extra row and are tested against everything.  After the sort the sweep visits, for every proxy, the
@@ -225,7 +226,7 @@ k_bounds(BodyArrays B, int n, int mode, int step, int numWorlds, int maxRows, St
     const float limitY = __uint_as_float(ctr->extYBits), limitZ = __uint_as_float(ctr->extZBits);
     float cellY = limitY * 1.05f + 1e-6f;
     float cellZ = limitZ * 1.05f + 1e-6f;
-    uint32_t kyMin = 0xffffffffu, kzMin = 0xffffffffu, kyMax = 0u, kzMax = 0u;
+    uint32_t kyMin = 0xffffffffu, kzMin = 0xffffffffu, kyMax = 0u, kzMax = 0u, kxMin = 0xffffffffu, kxMax = 0u;
     if (i < n) {
         uint8_t flags = B.flags[i];
         if (flags & BF_ALIVE) {
@@ -241,6 +242,7 @@ k_bounds(BodyArrays B, int n, int mode, int step, int numWorlds, int maxRows, St
             if (!large) {
                 kyMin = kyMax = floatKey(a.y);
                 kzMin = kzMax = floatKey(a.z);
+                kxMin = kxMax = floatKey(a.x);
             }
         }
     }
@@ -249,23 +251,27 @@ k_bounds(BodyArrays B, int n, int mode, int step, int numWorlds, int maxRows, St
         kzMin = min(kzMin, __shfl_xor_sync(0xffffffffu, kzMin, o));
         kyMax = max(kyMax, __shfl_xor_sync(0xffffffffu, kyMax, o));
         kzMax = max(kzMax, __shfl_xor_sync(0xffffffffu, kzMax, o));
+        kxMin = min(kxMin, __shfl_xor_sync(0xffffffffu, kxMin, o));
+        kxMax = max(kxMax, __shfl_xor_sync(0xffffffffu, kxMax, o));
     }
-    __shared__ uint32_t s[4][8];
+    __shared__ uint32_t s[6][8];
     __shared__ bool isLast;
     if ((threadIdx.x & 31) == 0) {
         int w = threadIdx.x >> 5;
-        s[0][w] = kyMin; s[1][w] = kzMin; s[2][w] = kyMax; s[3][w] = kzMax;
+        s[0][w] = kyMin; s[1][w] = kzMin; s[2][w] = kyMax; s[3][w] = kzMax; s[4][w] = kxMin; s[5][w] = kxMax;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; w++) {
             kyMin = min(kyMin, s[0][w]); kzMin = min(kzMin, s[1][w]);
             kyMax = max(kyMax, s[2][w]); kzMax = max(kzMax, s[3][w]);
+            kxMin = min(kxMin, s[4][w]); kxMax = max(kxMax, s[5][w]);
         }
         if (kyMin != 0xffffffffu) {
             // counters are zero-initialised, so the minima are kept as maxima of the complemented key
             atomicMax(&ctr->minYKey, ~kyMin); atomicMax(&ctr->minZKey, ~kzMin);
             atomicMax(&ctr->maxYKey, kyMax); atomicMax(&ctr->maxZKey, kzMax);
+            atomicMax(&ctr->minXKey, ~kxMin); atomicMax(&ctr->maxXKey, kxMax);
         }
         __threadfence();
         uint32_t t = atomicAdd(&ctr->boundsTicket, 1u);
@@ -298,7 +304,14 @@ k_bounds(BodyArrays B, int n, int mode, int step, int numWorlds, int maxRows, St
         g.ny = ny; g.nz = nz;
         g.rowsPerWorld = ny * nz;
         g.nrows = ny * nz * numWorlds;
-        g.pad[0] = g.pad[1] = 0;
+        {
+            uint32_t xa = ~*(volatile uint32_t*)&ctr->minXKey, xb = *(volatile uint32_t*)&ctr->maxXKey;
+            float x0 = 0.f, x1 = 0.f;
+            if (xa != 0xffffffffu) { x0 = keyFloat(xa); x1 = keyFloat(xb); }
+            float span = x1 - x0;
+            g.x0 = x0;
+            g.invX = (span > 0.f && span < 1e30f) ? 4095.0f / span : 0.f;
+        }
         *grid = g;
     }
 }
@@ -310,10 +323,17 @@ __device__ __forceinline__ int cellOf(float v, float v0, float inv, int ncell) {
     return c < 0 ? 0 : (c >= ncell ? ncell - 1 : c);
 }
 
-// k_keys: 64-bit key and payload for every slot.
+// 12-bit sweep coordinate: monotone in x (float ops are monotone), clamped
+__device__ __forceinline__ uint32_t quantX(float x, float x0, float invX) {
+    float q = floorf((x - x0) * invX);
+    q = q < 0.f ? 0.f : (q > 4095.f ? 4095.f : q);
+    return (q == q) ? (uint32_t)q : 0u;
+}
+
+// k_keys: 32-bit key and payload for every slot.
 __global__ void __launch_bounds__(256)
 k_keys(BodyArrays B, int n, const StepCounters* __restrict__ ctr, const GridParams* __restrict__ grid,
-       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     GridParams g = *grid;
@@ -334,9 +354,9 @@ k_keys(BodyArrays B, int n, const StepCounters* __restrict__ ctr, const GridPara
             int cy = cellOf(a.y, g.y0, g.invCellY, g.ny), cz = cellOf(a.z, g.z0, g.invCellZ, g.nz);
             row = (uint32_t)(B.world[i] * g.rowsPerWorld + cy * g.nz + cz);
         }
-        xk = floatKey(a.x);
+        xk = quantX(a.x, g.x0, g.invX);
     }
-    keys[i] = ((uint64_t)row << 32) | xk;
+    keys[i] = (row << 12) | xk;
     vals[i] = (uint32_t)i;
 }
 
@@ -344,23 +364,23 @@ k_keys(BodyArrays B, int n, const StepCounters* __restrict__ ctr, const GridPara
 //   smin[j] = (min.x, min.y, min.z, bodyIndex) ; smax[j] = (max.x, max.y, max.z, filter)
 // rowStart[r] = first sorted index whose row >= r (rows without proxies get the next row's start).
 __global__ void __launch_bounds__(256)
-k_gather(BodyArrays B, int n, const uint64_t* keysA, const uint64_t* keysB, const uint32_t* valsA, const uint32_t* valsB,
+k_gather(BodyArrays B, int n, const uint32_t* keysA, const uint32_t* keysB, const uint32_t* valsA, const uint32_t* valsB,
          const uint32_t* __restrict__ side, const GridParams* __restrict__ grid, float4* __restrict__ smin,
          float4* __restrict__ smax, uint32_t* __restrict__ srow, uint32_t* __restrict__ rowStart) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    const uint64_t* keys = *side ? keysB : keysA;
+    const uint32_t* keys = *side ? keysB : keysA;
     const uint32_t* vals = *side ? valsB : valsA;
-    uint64_t k = keys[j];
-    uint32_t row = (uint32_t)(k >> 32);
+    uint32_t k = keys[j];
+    uint32_t row = k >> 12;
     uint32_t body = vals[j];
     float4 a = B.effMin[body], b = B.effMax[body];
     a.w = __uint_as_float(body);
     b.w = __uint_as_float(B.filt[body]);
     smin[j] = a;
     smax[j] = b;
-    srow[j] = row;
-    uint32_t prev = j ? (uint32_t)(keys[j - 1] >> 32) : 0xffffffffu;
+    srow[j] = k;  // the whole sorted key: row = k >> 12, qx = k & 4095
+    uint32_t prev = j ? (keys[j - 1] >> 12) : 0xffffffffu;
     const uint32_t lastRow = (uint32_t)grid->nrows + 2u;
     if (j == 0) {
         for (uint32_t r = 0; r <= row; r++) rowStart[r] = 0;
@@ -436,7 +456,8 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
     float4 amin = make_float4(0, 0, 0, 0), amax = amin;
     uint32_t xkI = 0, xkMax = 0;
     if (i < n) {
-        uint32_t row = srow[i];
+        const uint32_t keyI = srow[i];
+        const uint32_t row = keyI >> 12;
         if (row < (uint32_t)nrows) {
             int w = row / rpw, rem = row - w * rpw;
             int cy = rem / nz + dy, cz = rem % nz + dz;
@@ -445,15 +466,15 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                 uint32_t lo = rowStart[r2], hi = rowStart[r2 + 1];
                 amin = __ldg(smin + i);
                 amax = __ldg(smax + i);
-                xkI = floatKey(amin.x);
-                xkMax = floatKey(amax.x);
+                xkI = keyI & 4095u;
+                xkMax = quantX(amax.x, grid->x0, grid->invX);
                 if (nb == 4) {
                     lo = (uint32_t)i + 1u;  // same row: everything after i has min.x >= min.x_i (stable sort)
                 } else {
                     uint32_t a = lo, b = hi;  // lower_bound of min.x_i inside the neighbour row
                     while (a < b) {
                         uint32_t mid = (a + b) >> 1;
-                        if (floatKey(__ldg(&smin[mid].x)) < xkI) a = mid + 1; else b = mid;
+                        if ((__ldg(srow + mid) & 4095u) < xkI) a = mid + 1; else b = mid;
                     }
                     lo = a;
                 }
@@ -465,13 +486,13 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
         bool hit = false;
         uint32_t bodyB = 0;
         if (j < end) {
-            float4 bmin = __ldg(smin + j);
-            uint32_t xkJ = floatKey(bmin.x);
+            uint32_t xkJ = __ldg(srow + j) & 4095u;
             if (xkJ > xkMax) {
                 j = end;  // window closed
             } else {
                 // ties in min.x across rows: only the earlier sorted position emits
                 if (xkJ != xkI || j > (uint32_t)i) {
+                    float4 bmin = __ldg(smin + j);
                     float4 bmax = __ldg(smax + j);
                     hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
                           (amin.z <= bmax.z) && (amax.z >= bmin.z) &&

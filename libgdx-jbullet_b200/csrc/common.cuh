@@ -136,7 +136,7 @@ struct GridParams {
     int rowsPerWorld;      // ny*nz
     int nrows;             // numWorlds*ny*nz ; row nrows = large proxies, row nrows+1 = dead slots
     float cellY, cellZ;
-    int pad[2];
+    float x0, invX;        // sweep-axis quantisation: qx = clamp(floor((min.x - x0) * invX), 0, 4095)
 };
 
 // Per-step device counters (one 128-byte block, cleared by the first kernel of the step).
@@ -152,7 +152,8 @@ struct StepCounters {
     uint32_t epaCount;
     uint32_t largeCount;
     uint32_t epaRetry;
-    uint32_t pad[13];
+    uint32_t minXKey, maxXKey;  // sweep-axis bounds of the gridded proxies (min kept complemented)
+    uint32_t pad[11];
 };
 
 // monotone float <-> uint key (total order matching float compare for non-NaN; -0 canonicalised to +0)

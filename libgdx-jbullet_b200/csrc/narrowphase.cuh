@@ -46,6 +46,7 @@ struct NpArgs {
     ManifoldHdr* mhdr;            // [maxPairs] this step: 32-byte manifold headers (SoA: streamed by every kernel)
     b2c_manifold_point* mpts;     // [4*maxPairs] this step: the 4 point slots of each manifold
     b2c_raw_contact* raw;         // [maxPairs]
+    int8_t* rawFlag;              // [maxPairs] copy of raw[p].has_contact for the kernels that only need the flag
     uint32_t* binKeys[2];         // [maxPairs] (bin << 24) | pairIndex, stably partitioned by bin (radix pass)
     const uint32_t* binSide;      // which of binKeys holds the partitioned list
     const uint32_t* binStart;     // exclusive bin offsets (the partition's digit histogram); [b+1] = end of bin b
@@ -187,12 +188,14 @@ __device__ __forceinline__ float combinedFriction(float f0, float f1) {
 __global__ void __launch_bounds__(256)
 k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs, const uint64_t* __restrict__ prevKeys,
         const uint32_t* __restrict__ prevNum, const uint32_t* __restrict__ prevFirst, const ManifoldHdr* __restrict__ prevH,
-        const b2c_manifold_point* __restrict__ prevP, ManifoldHdr* __restrict__ H, b2c_manifold_point* __restrict__ P, int uidBits) {
+        const b2c_manifold_point* __restrict__ prevP, ManifoldHdr* __restrict__ H, b2c_manifold_point* __restrict__ P, int uidBits,
+        StepCounters* ctr) {
     const uint32_t n = *numPairs, pn = *prevNum;
     const int lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
         uint32_t p = base + lane;
         int found = -1, nc = 0;
+        bool carriedManifold = false;
         if (p < n) {
             uint64_t k = keys[p];
             uint32_t uid0 = (uint32_t)(k >> uidBits);
@@ -207,6 +210,7 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
                 const int4* src = reinterpret_cast<const int4*>(prevH + found);
                 h0 = src[0]; h1 = src[1];
                 nc = h1.x;
+                carriedManifold = h1.y != 0;  // algorithm field: the pair already owns a manifold
             } else {
                 h0 = make_int4((int)uid0, (int)(k & ((1ull << uidBits) - 1ull)), 0, 0);
                 h1 = make_int4(0, 0, 0, 0);
@@ -214,6 +218,8 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
             int4* dst = reinterpret_cast<int4*>(H + p);   // adjacent lanes -> adjacent 32-byte headers
             dst[0] = h0; dst[1] = h1;
         }
+        uint32_t cm = __ballot_sync(0xffffffffu, carriedManifold);
+        if (lane == 0 && cm) atomicAdd(&ctr->numManifolds, (uint32_t)__popc(cm));
         // live points: the warp copies them with 16-byte accesses (6 int4 per point)
         uint32_t m = __ballot_sync(0xffffffffu, nc > 0);
         while (m) {
@@ -276,7 +282,7 @@ __device__ __forceinline__ void writeRaw(b2c_raw_contact* r, int2 pr, int tri, i
 // ---- sphere-sphere (disp/SphereSphereCollisionAlgorithm.java:73-134) ---------------------------------
 __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
     const uint32_t s = a.binStart[BIN_SS], e = a.binStart[BIN_SS + 1];
-    uint32_t added = 0;
+    uint32_t added = 0, created = 0;
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
         uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
         float r0 = a.shapes[a.shape[b0]].dims[0], r1 = a.shapes[a.shape[b1]].dims[0];
         MView m = mview(a, p);
-        if (m.h->algorithm == 0) { m.h->algorithm = 1; m.h->body0 = pr.x; m.h->body1 = pr.y; }
+        if (m.h->algorithm == 0) { m.h->algorithm = 1; m.h->body0 = pr.x; m.h->body1 = pr.y; created++; }
         for (int k = 0; k < m.h->num_contacts; k++) m.p[k].src_slot = k;
         f3 diff = sub3(t0.o, t1.o);
         float len = len3(diff);
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
         if (manifoldAdd(m, pr.x, t0, t1, n, pos1, dist, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
         resultRefresh(m, pr.x, t0, t1, a.threshold);
     }
+    if (created) atomicAdd(&a.ctr->numManifolds, created);
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
 }
 
@@ -319,7 +326,7 @@ __device__ __forceinline__ AnyS makeAnyS(const ShapeDev& s, const float4* hullPt
 
 __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
     const uint32_t s = a.binStart[BIN_CP], e = a.binStart[BIN_CP + 1];
-    uint32_t added = 0;
+    uint32_t added = 0, created = 0;
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
         uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
         const Xf& tc = swapped ? t1 : t0;
         const Xf& tp = swapped ? t0 : t1;
         MView m = mview(a, p);
-        if (m.h->algorithm == 0) { m.h->algorithm = 2; m.h->body0 = bc + 1; m.h->body1 = bp + 1; }
+        if (m.h->algorithm == 0) { m.h->algorithm = 2; m.h->body0 = bc + 1; m.h->body1 = bp + 1; created++; }
         for (int k = 0; k < m.h->num_contacts; k++) m.p[k].src_slot = k;
         f3 planeNormal = mk3(ps.plane[0], ps.plane[1], ps.plane[2]);
         float planeConstant = ps.plane[3];
@@ -355,6 +362,7 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
         }
         if (m.h->num_contacts != 0) resultRefresh(m, pr.x, t0, t1, a.threshold);
     }
+    if (created) atomicAdd(&a.ctr->numManifolds, created);
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
 }
 
@@ -485,6 +493,7 @@ __global__ void __launch_bounds__(256) k_gjk_prefilter(NpArgs a, uint32_t* __res
             bool done = normal1 && (delta > 0.f) && (delta * delta > sq1 * maxDistSq);
             if (done) {
                 writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, -1, 1);
+                a.rawFlag[p] = 0;
                 checks++;
             }
             survive = !done;
@@ -573,6 +582,7 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
                     f3 pt = add3(r.pointOnB, r.positionOffset);
                     writeRaw(a.raw + p, pr, -1, r.isValid ? 1 : 0, r.isValid ? r.normalInB : mk3(0, 0, 0), r.isValid ? pt : mk3(0, 0, 0),
                              r.isValid ? r.distance : 0.f, r.lastUsedMethod, r.curIter);
+                    a.rawFlag[p] = r.isValid ? 1 : 0;
                 }
             }
         }
@@ -586,16 +596,16 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
 // (disp/ConvexConvexAlgorithm.java:92-96), ManifoldResult.addContactPoint, refreshContactPoints (:136-138).
 __global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
     const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
-    uint32_t added = 0;
+    uint32_t added = 0, created = 0;
     for (uint32_t it = s0 + blockIdx.x * blockDim.x + threadIdx.x; it < e0; it += gridDim.x * blockDim.x) {
         uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
         MView m = mview(a, p);
-        if (m.h->algorithm == 0) { m.h->algorithm = 3; m.h->body0 = pr.x; m.h->body1 = pr.y; }
+        if (m.h->algorithm == 0) { m.h->algorithm = 3; m.h->body0 = pr.x; m.h->body1 = pr.y; created++; }
         const int nc = m.h->num_contacts;
-        const b2c_raw_contact* r = a.raw + p;
-        const bool has = r->has_contact == 1;
+        const bool has = a.rawFlag[p] == 1;
         if (nc == 0 && !has) continue;  // nothing to add, nothing to refresh
+        const b2c_raw_contact* r = a.raw + p;
         for (int k = 0; k < nc; k++) m.p[k].src_slot = k;
         int b0 = pr.x - 1, b1 = pr.y - 1;
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
@@ -607,6 +617,7 @@ __global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
         }
         resultRefresh(m, pr.x, t0, t1, a.threshold);
     }
+    if (created) atomicAdd(&a.ctr->numManifolds, created);
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
 }
 
@@ -671,6 +682,7 @@ __device__ __forceinline__ uint32_t walkBvh(const MeshDev& md, const uint32_t qm
 
 __global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
     const uint32_t s = a.binStart[BIN_MESH], e = a.binStart[BIN_MESH + 1];
+    uint32_t created = 0;
     for (uint32_t it = s + blockIdx.x * blockDim.x + threadIdx.x; it < e; it += gridDim.x * blockDim.x) {
         uint32_t p = binItem(a, it);
         int2 pr = a.pairs[p];
@@ -682,6 +694,7 @@ __global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
         const ShapeDev& ms = swapped ? s0 : s1;
         Xf tc = loadXf(a.xf4, bc), tt = loadXf(a.xf4, bt);
         MView m = mview(a, p);
+        if (m.h->algorithm == 0) created++;
         m.h->algorithm = 4;
         m.h->body0 = bc + 1; m.h->body1 = bt + 1;  // manifoldPtr.setBodies(convexBody, triBody)
         for (int k = 0; k < m.h->num_contacts; k++) m.p[k].src_slot = k;
@@ -709,6 +722,7 @@ __global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
         uint32_t k = start;
         walkBvh(md, qmin, qmax, [&](int tri) { g.meshPair[k] = p; g.meshTri[k] = tri; k++; });
     }
+    if (created) atomicAdd(&a.ctr->numManifolds, created);
 }
 
 __device__ __forceinline__ TriS loadTri(const MeshDev& md, int tri, float margin) {
@@ -883,6 +897,7 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
         b2c_raw_contact* rw = item.meshItem >= 0 ? g.rawMesh + item.meshItem : a.raw + p;
         writeRaw(rw, pr, tri, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0), isValid ? pt : mk3(0, 0, 0),
                  isValid ? distance : 0.f, method, r.curIter);
+        if (item.meshItem < 0) a.rawFlag[p] = isValid ? 1 : 0;
     }
     if (failed) atomicAdd(&a.ctr->epaFailed, failed);
 }
@@ -958,16 +973,6 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, b2c_manifold_
             }
         }
     }
-}
-
-// number of manifolds = pairs that own an algorithm with a manifold (Dispatcher.getNumManifolds)
-__global__ void __launch_bounds__(256) k_count_manifolds(NpArgs a) {
-    const uint32_t n = *a.numPairs;
-    uint32_t c = 0;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-        if (a.mhdr[p].algorithm != 0) c++;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&a.ctr->numManifolds, c);
 }
 
 }  // namespace b2c
