@@ -20,8 +20,9 @@ using namespace b2c;
 
 namespace {
 
-constexpr int EPA_GRID = 148 * 16, EPA_BLOCK = 64;   // tier 0 (small pools in local memory)
-constexpr int EPA_GRID2 = 148, EPA_BLOCK2 = 64;        // tier 1 (large pools in global memory)
+constexpr int EPA_GRID = 148 * 2, EPA_BLOCK = 32;      // tier 0: one warp per block, per-lane pools in shared memory (2 blocks/SM)
+constexpr int EPA_GRID3 = 148 * 16, EPA_BLOCK3 = 64;   // tier 2: pools in local memory, throughput variant
+constexpr int EPA_GRID2 = 148, EPA_BLOCK2 = 64;        // tier 1: large pools in global memory
 
 struct HostMesh {
     int4* nodes = nullptr;
@@ -385,10 +386,16 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         ctx->launches += 2;
     }
     mark(ctx, 11);
-    k_epa<0><<<EPA_GRID, EPA_BLOCK, 0, s>>>(a, g);
+    {
+        static_assert(EPA_SMALL_STRIDE % 8 == 4, "lane chunks need an odd word stride");
+        const int smem = EPA_BLOCK * EPA_SMALL_STRIDE;
+        cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_epa<0><<<EPA_GRID, EPA_BLOCK, smem, s>>>(a, g);
+        k_epa<2><<<EPA_GRID3, EPA_BLOCK3, 0, s>>>(a, g);
+    }
     k_epa<1><<<EPA_GRID2, EPA_BLOCK2, 0, s>>>(a, g);
     k_manifold_cc<<<148 * 8, 256, 0, s>>>(a);
-    ctx->launches += 3;
+    ctx->launches += 4;
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
     mark(ctx, 12);
     ctx->stageValid = ctx->prof;

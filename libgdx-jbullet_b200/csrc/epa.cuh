@@ -24,9 +24,9 @@ constexpr int EPA_MAXIT = 256;           // :113
 constexpr float EPA_INFACE_EPS = 0.01f;  // :114
 constexpr float EPA_ACCURACY = 0.001f;   // :115
 
-// Pools are templated: the common case (a few iterations, < 100 faces) runs out of a small per-thread pool
-// with one-byte links that lives in local memory (hardware-interleaved across the warp, L1-cached); a pair
-// that overflows it is redone by a second kernel with the large pool in global memory.
+// Pools are templated: the common case (a few iterations, < 80 faces) runs out of a small per-lane pool with
+// one-byte links in SHARED memory; a pair that overflows it is redone by a second kernel with the large pool in
+// global memory.
 template <typename IdxT>
 struct EpaFaceT {  // np/GjkEpaSolver.java:515-525, pointers replaced by pool indices (NIL = null)
     float nx, ny, nz, d;
@@ -51,7 +51,9 @@ struct EpaScratchT {
     uint8_t stkE[MAXSTK];
 };
 typedef EpaScratchT<int16_t, EPA_MAXF, EPA_MAXV, EPA_MAXRAY, EPA_MAXSTK> EpaScratch;   // large pool (global memory)
-typedef EpaScratchT<uint8_t, 120, 40, 24, 48> EpaScratchSmall;                         // small pool (local memory)
+typedef EpaScratchT<uint8_t, 80, 28, 12, 24> EpaScratchSmall;                          // small pool (shared memory)
+constexpr int EPA_SMALL_STRIDE = (int)sizeof(EpaScratchSmall) + 4;                        // odd word stride between lanes
+typedef EpaScratchT<uint8_t, 120, 40, 24, 48> EpaScratchLocal;                         // medium pool (local memory)
 
 // A convex shape chosen at run time (the EPA bin is small and mixed, so no template split here).
 struct AnyS {

@@ -814,17 +814,32 @@ __global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g, uint32_t* 
     if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
 }
 
-// EPA bin: finishes np/GjkPairDetector.java:265-303 for the pairs that asked for it.
-// TIER 0: every queued item, small per-thread pool in local memory; items that overflow it are appended to the
-// retry list.  TIER 1: the retry list with the large pool in global memory (pool exhaustion there = EPA failed).
+// EPA bin: finishes np/GjkPairDetector.java:265-303 for the pairs that asked for it.  Three variants share the
+// code; which of TIER 0 / TIER 2 does the work is decided ON THE DEVICE from the size of the bin (the other one
+// returns at once), because the two regimes want opposite trade-offs (measured, profiles/):
+//   TIER 0  small bin (<= EPA_SMEM_LANES items): latency matters.  Per-lane pools in SHARED memory (one warp per
+//           block, ~107 KB, two blocks per SM, odd word stride between lanes): an EPA run is a long chain of
+//           dependent small accesses, and in local memory each one is an L1-miss-prone interleaved line.
+//   TIER 2  large bin: throughput matters.  Pools in local memory, 64-thread blocks, ~75 k threads in flight.
+//   TIER 1  retry of the items that overflowed their pool, with the large pool in global memory (pool exhaustion
+//           there = EPA failed, like the reference's EPA_Failed).
+constexpr uint32_t EPA_SMEM_LANES = 148u * 2u * 32u;
+
 template <int TIER>
 __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
     uint32_t nItems;
-    if (TIER == 0) nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
-    else nItems = a.ctr->epaRetry < g.maxEpaRetry ? a.ctr->epaRetry : g.maxEpaRetry;
+    if (TIER != 1) {
+        nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
+        if (TIER == 0 && nItems > EPA_SMEM_LANES) return;
+        if (TIER == 2 && nItems <= EPA_SMEM_LANES) return;
+    } else {
+        nItems = a.ctr->epaRetry < g.maxEpaRetry ? a.ctr->epaRetry : g.maxEpaRetry;
+    }
     uint32_t failed = 0;
-    for (uint32_t it0 = blockIdx.x * blockDim.x + threadIdx.x; it0 < nItems; it0 += gridDim.x * blockDim.x) {
-        const uint32_t it = TIER == 0 ? it0 : g.epaRetry[it0];
+    extern __shared__ __align__(16) unsigned char epaSmem[];
+    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+    for (uint32_t it0 = first; it0 < nItems; it0 += step) {
+        const uint32_t it = TIER != 1 ? it0 : g.epaRetry[it0];
         EpaItem item = g.epaItems[it];
         uint32_t p = item.pair;
         int2 pr = a.pairs[p];
@@ -857,8 +872,13 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
         bool epaFail = false, poolOverflow = false;
         bool ok;
         if (TIER == 0) {
-            EpaScratchSmall sc;
+            EpaScratchSmall* sc = reinterpret_cast<EpaScratchSmall*>(epaSmem + (size_t)threadIdx.x * EPA_SMALL_STRIDE);
+            ok = epaPenetration(A, B, la, lb, sc, wA, wB, epaFail, poolOverflow);
+        } else if (TIER == 2) {
+            EpaScratchLocal sc;
             ok = epaPenetration(A, B, la, lb, &sc, wA, wB, epaFail, poolOverflow);
+        }
+        if (TIER != 1) {
             if (poolOverflow) {
                 uint32_t slot = atomicAdd(&a.ctr->epaRetry, 1u);
                 if (slot < g.maxEpaRetry) { g.epaRetry[slot] = it; continue; }
