@@ -91,41 +91,53 @@ __device__ __forceinline__ bool baryValid(const SubRes& r) {
 
 // np/VoronoiSimplexSolver.java:267-389 with p = origin.  Writes bary[0..2] (and 0 to bary[3]) + used mask;
 // returns the closest point (needed by the tetrahedron case for the squared distance).
+// The reference tests the Voronoi regions one after the other with early returns (A, B, AB, C, AC, BC, face).
+// Here every lane first evaluates all the dot products and region predicates (no branches: lanes of a warp sit
+// in different regions), the region is chosen with the reference's priority, and only the few operations that
+// are specific to a region are branched on.  Each value is produced by the same operations in the same order as
+// in the reference, so the results are bit-identical.
 __device__ __noinline__ f3 closestPtOriginTriangle(f3 a, f3 b, f3 c, float& u0, float& u1, float& u2, uint32_t& used) {
     const f3 p = mk3(0.f, 0.f, 0.f);
-    f3 ab = sub3(b, a), ac = sub3(c, a), ap = sub3(p, a);
-    float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
-    if (d1 <= 0.f && d2 <= 0.f) { used = 1u; u0 = 1.f; u1 = 0.f; u2 = 0.f; return a; }
-    f3 bp = sub3(p, b);
-    float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
-    if (d3 >= 0.f && d4 <= d3) { used = 2u; u0 = 0.f; u1 = 1.f; u2 = 0.f; return b; }
-    float vc = d1 * d4 - d3 * d2;
-    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+    const f3 ab = sub3(b, a), ac = sub3(c, a), ap = sub3(p, a), bp = sub3(p, b), cp = sub3(p, c);
+    const float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    const float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    const float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    const float vc = d1 * d4 - d3 * d2;
+    const float vb = d5 * d2 - d1 * d6;
+    const float va = d3 * d6 - d5 * d4;
+    int region;  // 0 A, 1 B, 2 AB, 3 C, 4 AC, 5 BC, 6 face
+    if (d1 <= 0.f && d2 <= 0.f) region = 0;
+    else if (d3 >= 0.f && d4 <= d3) region = 1;
+    else if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) region = 2;
+    else if (d6 >= 0.f && d5 <= d6) region = 3;
+    else if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) region = 4;
+    else if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) region = 5;
+    else region = 6;
+    f3 r = a;
+    u0 = 1.f; u1 = 0.f; u2 = 0.f; used = 1u;
+    if (region == 1) { r = b; u0 = 0.f; u1 = 1.f; used = 2u; }
+    else if (region == 3) { r = c; u0 = 0.f; u2 = 1.f; used = 4u; }
+    else if (region == 2) {
         float v = d1 / (d1 - d3);
-        used = 3u; u0 = 1.f - v; u1 = v; u2 = 0.f;
-        return mk3(v * ab.x + a.x, v * ab.y + a.y, v * ab.z + a.z);
-    }
-    f3 cp = sub3(p, c);
-    float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
-    if (d6 >= 0.f && d5 <= d6) { used = 4u; u0 = 0.f; u1 = 0.f; u2 = 1.f; return c; }
-    float vb = d5 * d2 - d1 * d6;
-    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+        r = mk3(v * ab.x + a.x, v * ab.y + a.y, v * ab.z + a.z);
+        u0 = 1.f - v; u1 = v; used = 3u;
+    } else if (region == 4) {
         float w = d2 / (d2 - d6);
-        used = 5u; u0 = 1.f - w; u1 = 0.f; u2 = w;
-        return mk3(w * ac.x + a.x, w * ac.y + a.y, w * ac.z + a.z);
-    }
-    float va = d3 * d6 - d5 * d4;
-    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        r = mk3(w * ac.x + a.x, w * ac.y + a.y, w * ac.z + a.z);
+        u0 = 1.f - w; u2 = w; used = 5u;
+    } else if (region == 5) {
         float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
         f3 t = sub3(c, b);
-        used = 6u; u0 = 0.f; u1 = 1.f - w; u2 = w;
-        return mk3(w * t.x + b.x, w * t.y + b.y, w * t.z + b.z);
+        r = mk3(w * t.x + b.x, w * t.y + b.y, w * t.z + b.z);
+        u0 = 0.f; u1 = 1.f - w; u2 = w; used = 6u;
+    } else if (region == 6) {
+        float denom = 1.f / (va + vb + vc);
+        float v = vb * denom, w = vc * denom;
+        f3 t1 = scl3(ab, v), t2 = scl3(ac, w);
+        r = mk3(a.x + t1.x + t2.x, a.y + t1.y + t2.y, a.z + t1.z + t2.z);
+        u0 = 1.f - v - w; u1 = v; u2 = w; used = 7u;
     }
-    float denom = 1.f / (va + vb + vc);
-    float v = vb * denom, w = vc * denom;
-    f3 t1 = scl3(ab, v), t2 = scl3(ac, w);
-    used = 7u; u0 = 1.f - v - w; u1 = v; u2 = w;
-    return mk3(a.x + t1.x + t2.x, a.y + t1.y + t2.y, a.z + t1.z + t2.z);
+    return r;
 }
 
 // np/VoronoiSimplexSolver.java:393-425 with p = origin
@@ -246,37 +258,39 @@ struct Simplex {
                 r.used = 15u;
                 float u0, u1, u2;
                 uint32_t us;
-                if (oABC != 0) {
+                // the four face tests run for every lane of the warp that is in this case (convergent calls);
+                // a face the origin is not outside of simply does not update the best candidate
+                {
                     f3 q = closestPtOriginTriangle(W0, W1, W2, u0, u1, u2, us);
                     float sq = dot3(q, q);  // (q - 0).(q - 0): q - p with p = 0 keeps q bit-for-bit
-                    if (sq < best) {
+                    if (oABC != 0 && sq < best) {
                         best = sq;
                         r.used = (us & 1u) | (us & 2u) | (us & 4u);
                         r.bary[0] = u0; r.bary[1] = u1; r.bary[2] = u2; r.bary[3] = 0.f;
                     }
                 }
-                if (oACD != 0) {
+                {
                     f3 q = closestPtOriginTriangle(W0, W2, W3, u0, u1, u2, us);
                     float sq = dot3(q, q);
-                    if (sq < best) {
+                    if (oACD != 0 && sq < best) {
                         best = sq;
                         r.used = (us & 1u) | ((us & 2u) << 1) | ((us & 4u) << 1);
                         r.bary[0] = u0; r.bary[1] = 0.f; r.bary[2] = u1; r.bary[3] = u2;
                     }
                 }
-                if (oADB != 0) {
+                {
                     f3 q = closestPtOriginTriangle(W0, W3, W1, u0, u1, u2, us);
                     float sq = dot3(q, q);
-                    if (sq < best) {
+                    if (oADB != 0 && sq < best) {
                         best = sq;
                         r.used = (us & 1u) | ((us & 4u) >> 1) | ((us & 2u) << 2);
                         r.bary[0] = u0; r.bary[1] = u2; r.bary[2] = 0.f; r.bary[3] = u1;
                     }
                 }
-                if (oBDC != 0) {
+                {
                     f3 q = closestPtOriginTriangle(W1, W3, W2, u0, u1, u2, us);
                     float sq = dot3(q, q);
-                    if (sq < best) {
+                    if (oBDC != 0 && sq < best) {
                         best = sq;
                         r.used = ((us & 1u) << 1) | (us & 4u) | ((us & 2u) << 2);
                         r.bary[0] = 0.f; r.bary[1] = u0; r.bary[2] = u2; r.bary[3] = u1;
