@@ -34,8 +34,12 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_scene(n_bodies, seed):
+def make_scene(n_bodies, seed, workload="c2", worlds=4096):
     import scenes
+    if workload == "c4":   # independent 64-body dice worlds
+        return scenes.worlds_scene(num_worlds=worlds, seed=seed)
+    if workload == "c5":   # spheres r=0.5 at 40 % packing, one world
+        return scenes.spheres_scene(n=n_bodies, seed=seed)
     # 49 x 49 footprint at 0.82 spacing = the 40 x 40 bin of SURVEY §8d C2
     return scenes.bin_scene(n=n_bodies, seed=seed, footprint=max(4, int(round((n_bodies / 100000.0) ** 0.5 * 49))))
 
@@ -146,11 +150,11 @@ def algorithmic_bytes(stage, N, P, st, key_passes_body, key_passes_pair, contact
     if stage == "aabb":
         return N * (48 + 4 + 1 + 32)
     if stage == "bounds_keys":
-        return N * (32 + 1) + N * (32 + 1 + 4 + 12)
+        return N * (32 + 1) + N * (32 + 1 + 4 + 8)
     if stage == "sort_proxies":
-        return N * 8 + key_passes_body * 2 * 12 * N
+        return N * 4 + key_passes_body * 2 * 8 * N      # 32-bit key (row | qx) + 32-bit payload
     if stage == "gather":
-        return N * (12 + 32 + 4 + 32 + 4)
+        return N * (8 + 32 + 4 + 32 + 4)
     if stage == "sweep":
         return 9 * N * 4 + N * 32 + 8 * P
     if stage == "large":
@@ -192,13 +196,51 @@ def run_ours(args):
 
     N = args.bodies
     t0 = time.time()
-    sc = make_scene(N, seed=100 + rank)
+    wl = args.workload
+    if wl == "c4":
+        # strong scaling: the 4096-world batch is split by world over the ranks (no cross-world pairs, no collective)
+        sc = make_scene(N, seed=100 + rank, workload="c4", worlds=max(1, args.worlds // world))
+    elif wl == "c5":
+        # strong scaling: ONE world, every rank holds all proxies and owns a slice of the sorted-AABB list
+        sc = make_scene(N, seed=100, workload="c5")
+    else:
+        sc = make_scene(N, seed=100 + rank)
     import scenes
-    if args.settle > 0:
+    if args.settle > 0 and wl == "c2":
         sc = settle_scene(pkg, sc, dev, args.max_pairs, args.settle, log if rank == 0 else None)
         sc.vel *= 0.25  # a settled pile creeps; it does not drift
     gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=args.max_pairs, device=dev)
     nb = sc.n
+    partitioned = wl == "c5" and world > 1
+    if partitioned:
+        gw.set_partition(rank, world)
+        mcap = 1 << 18
+        mig = (torch.zeros(mcap, dtype=torch.int64, device=f"cuda:{dev}"), torch.zeros(mcap * 8, dtype=torch.int32, device=f"cuda:{dev}"),
+               torch.zeros(mcap * 96, dtype=torch.int32, device=f"cuda:{dev}"))
+
+    def one_step():
+        """One collision step on the resident transforms; the partitioned world adds the manifold migration."""
+        if not partitioned:
+            gw.step_device()
+            return
+        gw.mgpu_broadphase()
+        c = gw.mgpu_export_departed(mig[0].data_ptr(), mig[1].data_ptr(), mig[2].data_ptr(), mcap)
+        cnt = torch.tensor([c], dtype=torch.int64, device=f"cuda:{dev}")
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        counts = [int(x.item()) for x in allc]
+        m = max(max(counts), 1)
+        outs = [[torch.empty(m * w_, dtype=t.dtype, device=t.device) for _ in range(world)] for t, w_ in zip(mig, (1, 8, 96))]
+        for t, w_, o in zip(mig, (1, 8, 96), outs):
+            dist.all_gather(o, t[: m * w_].contiguous())     # NCCL over NVLink: the departed manifolds of every rank
+        keys = torch.cat([outs[0][r][: counts[r]] for r in range(world)])
+        hdrs = torch.cat([outs[1][r][: counts[r] * 8] for r in range(world)])
+        pts = torch.cat([outs[2][r][: counts[r] * 96] for r in range(world)])
+        torch.cuda.current_stream().synchronize()
+        gw.mgpu_import_arrivals(keys.data_ptr(), hdrs.data_ptr(), pts.data_ptr(), int(sum(counts)))
+        gw.mgpu_narrowphase()
+        one_step.keep = (keys, hdrs, pts)  # keep the buffers alive until the ctx stream has consumed them
+
     frames = [np.ascontiguousarray(pkg.transforms_to_planes(sc.transforms(k))) for k in range(FRAMES)]
     log(f"[rank {rank}] scene built: {nb} proxies in {time.time() - t0:.1f}s")
 
@@ -221,7 +263,7 @@ def run_ours(args):
     step_no = 0
     for _ in range(args.warmup):
         gw.setWorldTransformsDevice(nb, dframes[frame_index(step_no)].data_ptr())
-        gw.step_device()
+        one_step()
         gw.sync_counts()
         step_no += 1
     barrier()
@@ -241,7 +283,7 @@ def run_ours(args):
             # inputs already resident in HBM: the frame is a device tensor
             ev0[k].record(stream)
         gw.setWorldTransformsDevice(nb, dframes[frame_index(step_no)].data_ptr())
-        gw.step_device()
+        one_step()
         with torch.cuda.stream(stream):
             ev1[k].record(stream)
         p, m, c = gw.sync_counts()
@@ -271,7 +313,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         t_start = time.perf_counter()
         gw.setWorldTransformsHostPtr(nb, hframes[frame_index(step_no)].data_ptr())       # H2D of this step's inputs
-        gw.step_device()
+        one_step()
         gw.sync_counts()
         gw._ck(L.b2c_get_pairs(gw.h, ctypes.c_void_p(pairs_host.data_ptr()), P_cap, ctypes.byref(nP)))   # D2H pair list
         gw._ck(L.b2c_get_contacts(gw.h, ctypes.c_void_p(hdr_host.data_ptr()), P_cap, ctypes.c_void_p(pts_host.data_ptr()),
@@ -309,7 +351,7 @@ def run_ours(args):
     dom = max(stage_ms, key=stage_ms.get)
     P_avg = pairs_tot / args.steps
     contacts_live = st["num_manifolds"] and contacts_tot / args.steps
-    body_bits = 32 + int(np.ceil(np.log2(2 * nb + 66)))
+    body_bits = 12 + min(20, int(np.ceil(np.log2(2 * nb + 66))))
     pair_bits = 2 * int(np.ceil(np.log2(nb + 2)))
     abytes = {s: algorithmic_bytes(s, nb, P_avg, st, (body_bits + 7) // 8, (pair_bits + 7) // 8, contacts_live) for s in stage_ms}
     achieved = abytes[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
@@ -319,19 +361,24 @@ def run_ours(args):
         traffic = tr.get(dom)
     except Exception:
         pass
+    strong = wl in ("c4", "c5")
+    wl_name = {"c2": f"C2: {N} mixed boxes/spheres/16-pt hulls in a closed bin of 5 static boxes, single world per GPU, "
+                     "DbvtBroadphase pair semantics, seeded transform trace",
+               "c4": f"C4: {args.worlds} independent 64-body dice worlds, split by world over the GPUs",
+               "c5": f"C5: {N} spheres r=0.5 at 40% packing, ONE world partitioned by sorted-AABB slices over the GPUs, "
+                     "departed manifolds all-gathered with NCCL"}[wl]
     out = {
-        "metric": "collision_phase_world_steps_per_s_100k_bodies",
-        "value": ngpu * 1000.0 / ms_max,
-        "unit": "steps/s (one step = full collision phase of a 100k-body world)",
+        "metric": "collision_phase_world_steps_per_s_100k_bodies" if wl == "c2" else f"collision_phase_steps_per_s_{wl}",
+        "value": (1000.0 / ms_max) if strong else ngpu * 1000.0 / ms_max,
+        "unit": "steps/s (one step = full collision phase of a 100k-body world)" if wl == "c2" else "steps/s (one step = full collision phase of the whole workload)",
         "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"C2: {N} mixed boxes/spheres/16-pt hulls in a closed bin of 5 static boxes, single world per GPU, "
-                               "DbvtBroadphase pair semantics, seeded transform trace",
+        "config": {"workload": wl_name,
                    "snapshot": f"settled ({args.settle} relaxation iterations)" if args.settle > 0 else "raw jittered lattice (deep overlaps)",
                    "deep_penetration_checks_per_step": st["deep_penetration_checks"],
                    "proxies": nb, "l2": "flushed between timed iterations (192 MiB write)",
@@ -343,7 +390,7 @@ def run_ours(args):
         "manifolds_per_step": manif_all / args.steps / ngpu,
         "stage_ms": {k: round(v, 5) for k, v in stage_ms.items()},
         "gpu_launches": int(launches_all),
-        "e2e": {"value": ngpu * 1000.0 / e2e_max, "unit": "steps/s", "ms_per_step": e2e_max,
+        "e2e": {"value": (1000.0 / e2e_max) if strong else ngpu * 1000.0 / e2e_max, "unit": "steps/s", "ms_per_step": e2e_max,
                 "h2d_bytes_per_step": nb * 48, "d2h_bytes_per_step": int(d2h),
                 "what": "b2c_set_transforms(pinned host planes) + b2c_step + b2c_get_pairs + b2c_get_contacts into pinned host buffers"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -353,7 +400,7 @@ def run_ours(args):
                                          for s in stage_ms}},
         "clocks": clocks,
     }
-    if ngpu == 1 and not args.no_cpu:
+    if ngpu == 1 and not args.no_cpu and wl == "c2":
         out["cpu_baseline"] = cpu_baseline(sc, args)
     print(json.dumps(out), flush=True)
     if dist is not None:
@@ -419,6 +466,9 @@ def main():
     ap.add_argument("--max-pairs", type=int, default=3 << 20)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 = BASELINE headline (default); c4 = batched worlds split by world; c5 = one partitioned world")
+    ap.add_argument("--worlds", type=int, default=4096)
     ap.add_argument("--settle", type=int, default=60, help="relaxation iterations for the settled snapshot (0 = raw lattice)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

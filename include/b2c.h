@@ -215,6 +215,23 @@ int32_t b2c_transforms_written(b2c_ctx*, int32_t n);
 int32_t b2c_step_device(b2c_ctx*);
 int32_t b2c_sync_counts(b2c_ctx*, int32_t* num_pairs_out, int32_t* num_manifolds_out, int32_t* num_contacts_added_out);
 
+/* ---- one world partitioned over several GPUs -------------------------------------
+ * Every rank holds all proxies (their state is small) and owns a contiguous slice of the SORTED proxy list: it
+ * emits the pairs whose first member in sweep order lies in its slice (slab partition by sorted-AABB range; reads
+ * beyond the slice are the halo), and runs the narrowphase for exactly those pairs.  The union over ranks is the
+ * single-GPU result.  A pair near a slice boundary can change owner between steps, so its manifold migrates:
+ *   b2c_mgpu_broadphase -> b2c_mgpu_export_departed -> [all-gather over NVLink, e.g. ncclAllGather] ->
+ *   b2c_mgpu_import_arrivals -> b2c_mgpu_narrowphase.
+ * The export/import buffers are DEVICE pointers owned by the caller (so NCCL can use them directly):
+ * keys: uint64[cap]; headers: 32-byte records [cap]; points: b2c_manifold_point[4*cap]. */
+int32_t b2c_set_partition(b2c_ctx*, int32_t rank, int32_t nranks);
+int32_t b2c_mgpu_broadphase(b2c_ctx*);
+int32_t b2c_mgpu_export_departed(b2c_ctx*, uint64_t* keys_dev, void* headers_dev, b2c_manifold_point* points_dev, int32_t cap,
+                                 int32_t* count_out);
+int32_t b2c_mgpu_import_arrivals(b2c_ctx*, const uint64_t* keys_dev, const void* headers_dev, const b2c_manifold_point* points_dev,
+                                 int32_t count);
+int32_t b2c_mgpu_narrowphase(b2c_ctx*);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,7 +62,8 @@ EXPORTS = [
     "b2c_calculate_overlapping_pairs", "b2c_get_pairs", "b2c_dispatch_all_pairs", "b2c_step", "b2c_get_manifolds",
     "b2c_get_raw_contacts", "b2c_get_aabbs", "b2c_get_broadphase_aabb", "b2c_get_stats", "b2c_stream",
     "b2c_device_transforms", "b2c_transforms_written", "b2c_step_device", "b2c_sync_counts", "b2c_get_contacts",
-    "b2c_set_profiling", "b2c_get_stage_times", "b2c_stage_name", "b2c_set_transforms_device",
+    "b2c_set_profiling", "b2c_get_stage_times", "b2c_stage_name", "b2c_set_transforms_device", "b2c_set_partition", "b2c_mgpu_broadphase", "b2c_mgpu_export_departed",
+    "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase",
 ]
 NUM_STAGES = 12
 CONTACT_HEADER_DTYPE = np.dtype([
@@ -124,6 +125,11 @@ def load():
     L.b2c_step_device.argtypes = [vp]
     L.b2c_sync_counts.argtypes = [vp, pi32, pi32, pi32]
     L.b2c_set_transforms_device.argtypes = [vp, i32, vp]
+    L.b2c_set_partition.argtypes = [vp, i32, i32]
+    L.b2c_mgpu_broadphase.argtypes = [vp]
+    L.b2c_mgpu_export_departed.argtypes = [vp, vp, vp, vp, i32, pi32]
+    L.b2c_mgpu_import_arrivals.argtypes = [vp, vp, vp, vp, i32]
+    L.b2c_mgpu_narrowphase.argtypes = [vp]
     L.b2c_get_contacts.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
     L.b2c_set_profiling.argtypes = [vp, i32]
     L.b2c_get_stage_times.argtypes = [vp, vp]

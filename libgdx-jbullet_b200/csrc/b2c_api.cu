@@ -113,6 +113,8 @@ struct b2c_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int launches = 0;
     int32_t lastPairs = 0, lastManifolds = 0, lastContacts = 0;
+    int partRank = 0, partRanks = 1;
+    uint32_t* dExportCount = nullptr;
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
     bool stageValid = false;
@@ -284,14 +286,17 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     mark(ctx, 3);
     k_gather<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->dSide, ctx->dGrid,
                                 ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart);
-    dim3 sg(nb, 9);
+    // this rank's slice of the sorted proxy list (the whole list when the world is not partitioned)
+    const int partLo = (int)((long long)n * ctx->partRank / ctx->partRanks);
+    const int partHi = (int)((long long)n * (ctx->partRank + 1) / ctx->partRanks);
+    dim3 sg((unsigned)((partHi - partLo + 255) / 256 > 0 ? (partHi - partLo + 255) / 256 : 1), 9);
     mark(ctx, 4);
     k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys[0],
-                               (uint32_t)ctx->cfg.max_pairs, ctx->dCtr);
+                               (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi);
     dim3 lg(gridFor((uint32_t)n, 256, 64), 16);
     mark(ctx, 5);
     k_large<<<lg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
-                               ctx->uidBits, ctx->dPairKeys[0], (uint32_t)ctx->cfg.max_pairs, ctx->dCtr);
+                               ctx->uidBits, ctx->dPairKeys[0], (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi, ctx->partRank);
     mark(ctx, 6);
     ctx->sortPairs.launches = 0;
     ctx->sortPairs.sort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr, &ctx->dCtr->pairCount, 0,
@@ -546,6 +551,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dBinKeys[1], P));
     CKC(ctx->sortBins.init((uint32_t)P));
     CKC(dalloc(&ctx->dCursors, (size_t)4));
+    CKC(dalloc(&ctx->dExportCount, (size_t)1));
     CKC(dalloc(&ctx->dSurvivors, P));
     ctx->maxEpa = (uint32_t)(P / 4 + 1024);
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
@@ -587,7 +593,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1185,6 +1191,67 @@ const char* b2c_stage_name(int32_t k) {
     static const char* names[B2C_NUM_STAGES] = {"aabb", "bounds_keys", "sort_proxies", "gather", "sweep", "large", "sort_pairs",
                                                 "unpack_carry", "classify_bin", "closed_form", "gjk_mesh", "epa_fold_count"};
     return (k >= 0 && k < B2C_NUM_STAGES) ? names[k] : "";
+}
+
+int32_t b2c_set_partition(b2c_ctx* ctx, int32_t rank, int32_t nranks) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return B2C_ERR_BAD_ARG;
+    ctx->partRank = rank;
+    ctx->partRanks = nranks;
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_broadphase(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    ctx->launches = 0;
+    ctx->aabbPending = true;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int32_t rc = enqueueBroadphase(ctx);
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    return rc;
+}
+
+int32_t b2c_mgpu_export_departed(b2c_ctx* ctx, uint64_t* keys, void* hdrs, b2c_manifold_point* pts, int32_t cap, int32_t* countOut) {
+    if (!ctx || !keys || !hdrs || !pts || cap < 0 || !countOut) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const int cur = ctx->cur, prev = cur ^ 1;
+    CK(cudaMemsetAsync(ctx->dExportCount, 0, sizeof(uint32_t), s));
+    k_export_departed<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(
+        ctx->dSortedKeys[prev], ctx->dNumPairs[prev], ctx->dMHdr[prev], ctx->dMPts[prev], ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
+        ctx->dPairFirst[cur], ctx->uidBits, keys, (ManifoldHdr*)hdrs, pts, (uint32_t)cap, ctx->dExportCount);
+    ctx->launches++;
+    uint32_t c = 0;
+    CK(cudaMemcpyAsync(&c, ctx->dExportCount, sizeof(c), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *countOut = (int32_t)c;
+    if (c > (uint32_t)cap) { ctx->err = "departed-manifold export buffer too small"; return B2C_ERR_CAPACITY; }
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_import_arrivals(b2c_ctx* ctx, const uint64_t* keys, const void* hdrs, const b2c_manifold_point* pts, int32_t count) {
+    if (!ctx || count < 0 || (count > 0 && (!keys || !hdrs || !pts))) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    if (count == 0) return B2C_OK;
+    cudaSetDevice(ctx->device);
+    const int cur = ctx->cur;
+    k_import_arrivals<<<gridFor((uint32_t)count, 256), 256, 0, ctx->stream>>>(
+        keys, (const ManifoldHdr*)hdrs, pts, (uint32_t)count, ctx->dSortedKeys[cur], ctx->dNumPairs[cur], ctx->dPairFirst[cur],
+        ctx->uidBits, ctx->dMHdr[cur], ctx->dMPts[cur], ctx->dCtr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_narrowphase(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    int32_t rc = enqueueNarrowphase(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->stats.kernel_launches = ctx->launches;
+    return B2C_OK;
 }
 
 void* b2c_stream(b2c_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

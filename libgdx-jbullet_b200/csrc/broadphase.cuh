@@ -444,11 +444,12 @@ struct PairStager {
 __global__ void __launch_bounds__(256)
 k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ srow,
         const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
-        uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr) {
+        uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi) {
     __shared__ uint64_t stage[8][PAIR_STAGE];
     PairStager st;
     st.init(stage[threadIdx.x >> 5]);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + partLo;  // this rank's slice [partLo, partHi) of the sorted list
+    n = n < partHi ? n : partHi;
     const int nb = blockIdx.y;  // 0..8
     const int dy = nb / 3 - 1, dz = nb % 3 - 1;
     const int ny = grid->ny, nz = grid->nz, rpw = grid->rowsPerWorld, nrows = grid->nrows;
@@ -512,7 +513,7 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
 __global__ void __launch_bounds__(256)
 k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ rowStart,
         const GridParams* __restrict__ grid, const int* __restrict__ world, int numWorlds, int uidBits,
-        uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr) {
+        uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi, int partRank) {
     __shared__ uint64_t stage[8][PAIR_STAGE];
     PairStager st;
     st.init(stage[threadIdx.x >> 5]);
@@ -541,6 +542,9 @@ k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                 hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
                       (amin.z <= bmax.z) && (amax.z >= bmin.z) && filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
                 if (hit && numWorlds > 1 && j >= l0) hit = world[bodyB] == world[bodyA];
+                // partitioned world: a (large, gridded) pair belongs to the rank whose slice holds the gridded member;
+                // (large, large) pairs belong to rank 0
+                if (hit) hit = (j >= l0) ? (partRank == 0) : ((int)j >= partLo && (int)j < partHi);
             }
             st.push(hit, bodyA, bodyB, uidBits, pairKeys, maxPairs, ctr);
         }

@@ -245,6 +245,59 @@ k_pair_first(const int2* __restrict__ pairs, const uint32_t* __restrict__ numPai
     }
 }
 
+// ---- one world partitioned over several GPUs: manifolds follow pairs that change owner ------------------
+// Each rank emits the pairs whose first member (in sorted-AABB order) lies in its contiguous range of the
+// sorted proxy list, so a pair near a range boundary can change owner from one step to the next.  Its manifold
+// must follow it: k_export_departed lists last step's manifolds whose pair this rank no longer owns; after an
+// all-gather every rank adopts the ones whose pair it owns now (k_import_arrivals).
+__device__ __forceinline__ int findPairIndex(const uint64_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ first,
+                                             uint64_t k, int uidBits) {
+    if (n == 0) return -1;
+    uint32_t uid0 = (uint32_t)(k >> uidBits);
+    uint32_t a = first[uid0], b = first[uid0 + 1];
+    while (a < b) {
+        uint32_t mid = (a + b) >> 1;
+        if (keys[mid] < k) a = mid + 1; else b = mid;
+    }
+    return (a < n && keys[a] == k) ? (int)a : -1;
+}
+
+__global__ void __launch_bounds__(256)
+k_export_departed(const uint64_t* __restrict__ prevKeys, const uint32_t* __restrict__ prevNum, const ManifoldHdr* __restrict__ prevH,
+                  const b2c_manifold_point* __restrict__ prevP, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs,
+                  const uint32_t* __restrict__ first, int uidBits, uint64_t* __restrict__ outKeys, ManifoldHdr* __restrict__ outH,
+                  b2c_manifold_point* __restrict__ outP, uint32_t cap, uint32_t* __restrict__ outCount) {
+    const uint32_t pn = *prevNum, n = *numPairs;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pn; p += gridDim.x * blockDim.x) {
+        ManifoldHdr h = prevH[p];
+        if (h.algorithm == 0) continue;
+        uint64_t k = prevKeys[p];
+        if (findPairIndex(keys, n, first, k, uidBits) >= 0) continue;  // still ours: k_carry took care of it
+        uint32_t slot = atomicAdd(outCount, 1u);
+        if (slot >= cap) continue;  // the host checks the count against cap
+        outKeys[slot] = k;
+        outH[slot] = h;
+        for (int q = 0; q < h.num_contacts && q < 4; q++) outP[4 * (size_t)slot + q] = prevP[4 * (size_t)p + q];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_import_arrivals(const uint64_t* __restrict__ inKeys, const ManifoldHdr* __restrict__ inH, const b2c_manifold_point* __restrict__ inP,
+                  uint32_t count, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs,
+                  const uint32_t* __restrict__ first, int uidBits, ManifoldHdr* __restrict__ H, b2c_manifold_point* __restrict__ P,
+                  StepCounters* ctr) {
+    const uint32_t n = *numPairs;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += gridDim.x * blockDim.x) {
+        int idx = findPairIndex(keys, n, first, inKeys[s], uidBits);
+        if (idx < 0) continue;  // another rank's pair (or a pair that really vanished)
+        ManifoldHdr h = inH[s];
+        if (H[idx].algorithm != 0) continue;  // our own departed copy cannot come back; defensive
+        H[idx] = h;
+        for (int q = 0; q < h.num_contacts && q < 4; q++) P[4 * (size_t)idx + q] = inP[4 * (size_t)s + q];
+        atomicAdd(&ctr->numManifolds, 1u);
+    }
+}
+
 // ---- k_classify: needsCollision + algorithm table --------------------------------------------------
 __device__ __forceinline__ bool isConvexType(int t) { return t == SH_BOX || t == SH_SPHERE || t == SH_HULL; }
 

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace b2c {
 
@@ -22,6 +23,7 @@ constexpr int RS_MAX_PASSES = 8;
 constexpr uint32_t RS_FLAG_AGG = 1u << 30;
 constexpr uint32_t RS_FLAG_INC = 2u << 30;
 constexpr uint32_t RS_VAL_MASK = (1u << 30) - 1;
+constexpr int RS_LOOKBACK = 16;
 
 struct RadixState {
     uint32_t hist[RS_MAX_PASSES][256];  // after rs_scan: exclusive digit offsets
@@ -87,6 +89,11 @@ __global__ void __launch_bounds__(256) rs_scan(RadixState* st, int firstPass) {
 __device__ __forceinline__ uint32_t rs_load_acquire(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t rs_load_relaxed(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void rs_store_release(uint32_t* p, uint32_t v) {
@@ -178,14 +185,29 @@ rs_pass(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, RadixState* st, ui
             rs_store_release(myStatus, tileCount | RS_FLAG_INC);
         } else {
             rs_store_release(myStatus, tileCount | RS_FLAG_AGG);
+            // Look back over the preceding tiles until one with an inclusive prefix is found.  The walk is the
+            // critical path of a pass (early on only tile 0 is inclusive, so tile t sums t aggregates), so the
+            // statuses are fetched RS_LOOKBACK at a time as independent loads instead of one dependent load per tile.
             int t = (int)tile - 1;
-            while (t >= 0) {
-                uint32_t s = rs_load_acquire(status + (size_t)t * 256 + d);
-                uint32_t f = s & ~RS_VAL_MASK;
-                if (f == 0) continue;  // not yet published; earlier tickets are always running or done
-                excl += s & RS_VAL_MASK;
-                if (f == RS_FLAG_INC) break;
-                t--;
+            bool done = false;
+            while (!done && t >= 0) {
+                uint32_t sv[RS_LOOKBACK];
+#pragma unroll
+                for (int k = 0; k < RS_LOOKBACK; k++)
+                    sv[k] = (t - k >= 0) ? rs_load_relaxed(status + (size_t)(t - k) * 256 + d) : RS_FLAG_INC;
+                int used = 0;
+#pragma unroll
+                for (int k = 0; k < RS_LOOKBACK; k++) {
+                    if (!done && used == k) {
+                        uint32_t f = sv[k] & ~RS_VAL_MASK;
+                        if (f != 0) {  // published (an unpublished one stops the batch; it is re-read next round)
+                            excl += sv[k] & RS_VAL_MASK;
+                            used = k + 1;
+                            if (f == RS_FLAG_INC) done = true;
+                        }
+                    }
+                }
+                t -= used;
             }
             rs_store_release(myStatus, (excl + tileCount) | RS_FLAG_INC);
         }
@@ -239,7 +261,11 @@ struct RadixSorter {
     int items = 4;
     int launches = 0;
 
-    static int pickItems(uint32_t cap) { return cap >= 148u * 2u * 4096u ? 16 : 4; }
+    static int pickItems(uint32_t cap) {
+        const char* e = getenv("B2C_RS_ITEMS");  // tuning knob for experiments
+        if (e) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) return v; }
+        return cap >= 148u * 2u * 4096u ? 16 : 4;
+    }
 
     cudaError_t init(uint32_t cap) {
         capacity = cap;
@@ -287,6 +313,9 @@ struct RadixSorter {
             if (items == 16) {
                 cudaFuncSetAttribute(rs_pass<K, HAS_VAL, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
                 rs_pass<K, HAS_VAL, 16><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
+            } else if (items == 8) {
+                cudaFuncSetAttribute(rs_pass<K, HAS_VAL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+                rs_pass<K, HAS_VAL, 8><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
             } else {
                 rs_pass<K, HAS_VAL, 4><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
             }

@@ -206,6 +206,24 @@ class GpuCollisionWorld:
     def transforms_written(self, n):
         self._ck(self.L.b2c_transforms_written(self.h, n))
 
+    # ---- one world partitioned over several GPUs (include/b2c.h, last section) ----
+    def set_partition(self, rank, nranks):
+        self._ck(self.L.b2c_set_partition(self.h, rank, nranks))
+
+    def mgpu_broadphase(self):
+        self._ck(self.L.b2c_mgpu_broadphase(self.h))
+
+    def mgpu_export_departed(self, keys_ptr, hdr_ptr, pts_ptr, cap):
+        n = C.c_int32()
+        self._ck(self.L.b2c_mgpu_export_departed(self.h, C.c_void_p(keys_ptr), C.c_void_p(hdr_ptr), C.c_void_p(pts_ptr), cap, C.byref(n)))
+        return n.value
+
+    def mgpu_import_arrivals(self, keys_ptr, hdr_ptr, pts_ptr, count):
+        self._ck(self.L.b2c_mgpu_import_arrivals(self.h, C.c_void_p(keys_ptr), C.c_void_p(hdr_ptr), C.c_void_p(pts_ptr), count))
+
+    def mgpu_narrowphase(self):
+        self._ck(self.L.b2c_mgpu_narrowphase(self.h))
+
     # ---- results ----
     def aabbs(self):
         out = np.zeros((self.num_bodies, 6), dtype=np.float32)
