@@ -90,6 +90,23 @@ def settle_scene(pkg, sc, dev, max_pairs, iters, log_fn=None):
     return sc
 
 
+def settled_path(n_bodies, seed, iters):
+    return os.path.join(ROOT, "tests", "golden", f"c2_settled_n{n_bodies}_seed{seed}_it{iters}.npz")
+
+
+def load_settled(sc, n_bodies, seed, iters):
+    """Apply the committed settled snapshot (origins only; made by `bench.py --save-settled` with settle_scene) so
+    that both arms measure the same scene and the reference arm needs no GPU.  Returns False when there is none."""
+    p = settled_path(n_bodies, seed, iters)
+    if not os.path.exists(p):
+        return False
+    z = np.load(p)
+    if z["pos"].shape != sc.base[:, 9:].shape:
+        return False
+    sc.base[:, 9:] = z["pos"]
+    return True
+
+
 def frame_index(step):
     period = 2 * (FRAMES - 1)
     k = step % period
@@ -207,7 +224,11 @@ def run_ours(args):
         sc = make_scene(N, seed=100 + rank)
     import scenes
     if args.settle > 0 and wl == "c2":
-        sc = settle_scene(pkg, sc, dev, args.max_pairs, args.settle, log if rank == 0 else None)
+        if args.save_settled or not load_settled(sc, N, 100 + rank, args.settle):
+            sc = settle_scene(pkg, sc, dev, args.max_pairs, args.settle, log if rank == 0 else None)
+            if args.save_settled and rank == 0:
+                os.makedirs(os.path.dirname(args.save_settled) or ".", exist_ok=True)
+                np.savez_compressed(args.save_settled, pos=sc.base[:, 9:])
         sc.vel *= 0.25  # a settled pile creeps; it does not drift
     gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=args.max_pairs, device=dev)
     nb = sc.n
@@ -282,11 +303,16 @@ def run_ours(args):
             flush.fill_(float(k))  # L2 flush between timed iterations (not timed)
             # inputs already resident in HBM: the frame is a device tensor
             ev0[k].record(stream)
+        if args.profile_step and k == 0:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()   # ncu --profile-from-start off: capture exactly one timed step
         gw.setWorldTransformsDevice(nb, dframes[frame_index(step_no)].data_ptr())
         one_step()
         with torch.cuda.stream(stream):
             ev1[k].record(stream)
         p, m, c = gw.sync_counts()
+        if args.profile_step and k == 0:
+            torch.cuda.profiler.stop()
         pairs_tot += p; manif_tot += m; contacts_tot += c
         st = gw.stats()
         launches += st["kernel_launches"]
@@ -435,6 +461,9 @@ def run_reference(args):
     if rank != 0:
         return
     sc = make_scene(args.bodies, seed=100)
+    settled = args.settle > 0 and load_settled(sc, args.bodies, 100, args.settle)
+    if settled:
+        sc.vel *= 0.25
     steps = max(1, min(args.steps, args.cpu_steps if args.cpu_steps > 0 else 4))
     times, pairs = cpu_steps(sc, steps, warmup=min(args.warmup, 1))
     ms = float(np.mean(times)) * 1e3
@@ -446,7 +475,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C2: {args.bodies} mixed boxes/spheres/16-pt hulls in a closed bin of 5 static boxes, single world, "
-                               "DbvtBroadphase pair semantics, seeded transform trace", "proxies": sc.n},
+                               "DbvtBroadphase pair semantics, seeded transform trace",
+                   "snapshot": f"settled ({args.settle} relaxation iterations)" if settled else "raw jittered lattice (deep overlaps)",
+                   "proxies": sc.n},
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 1, "kind": "port",
                          "sample": f"{steps} full steps of the {sc.n}-proxy C2 world; Java reference not runnable on this box (no JVM): "
                                    "CPU baseline is the C++ restatement in oracle/"},
@@ -469,6 +500,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 = BASELINE headline (default); c4 = batched worlds split by world; c5 = one partitioned world")
     ap.add_argument("--worlds", type=int, default=4096)
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket the first timed step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    ap.add_argument("--save-settled", default="", help="write the settled origins (npz) here; commit it under tests/golden/")
     ap.add_argument("--settle", type=int, default=60, help="relaxation iterations for the settled snapshot (0 = raw lattice)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
