@@ -14,6 +14,7 @@
 #include "bvh_build.h"
 #include "common.cuh"
 #include "narrowphase.cuh"
+#include "pair_rows.cuh"
 #include "radix_sort.cuh"
 
 using namespace b2c;
@@ -76,8 +77,12 @@ struct b2c_ctx {
     GridParams* dGrid = nullptr;
     StepCounters* dCtr = nullptr;
     StepCounters* hCtrPinned = nullptr;
-    uint64_t* dPairKeys[2] = {nullptr, nullptr};
-    RadixSorter sortBodies, sortPairs;
+    uint64_t* dPairKeys = nullptr;    // emitted (slot | uid0 | uid1) keys, emission order
+    uint32_t* dCsr = nullptr;         // uid1 of every pair, grouped by uid0 (pair_rows.cuh)
+    uint32_t* dRowZero = nullptr;     // one block cleared per step: rowCnt[nRows] | scan status[tiles] | RowMisc
+    uint32_t* dBigRows = nullptr;
+    uint32_t nRows = 0, rowTiles = 0;
+    RadixSorter sortBodies;
     int uidBits = 1;
 
     // pairs + manifolds (ping-pong across steps)
@@ -291,28 +296,32 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     const int partHi = (int)((long long)n * (ctx->partRank + 1) / ctx->partRanks);
     dim3 sg((unsigned)((partHi - partLo + 255) / 256 > 0 ? (partHi - partLo + 255) / 256 : 1), 9);
     mark(ctx, 4);
-    k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys[0],
+    uint32_t* rowCnt = ctx->dRowZero;
+    uint32_t* rowStatus = ctx->dRowZero + ctx->nRows;
+    RowMisc* rowMisc = reinterpret_cast<RowMisc*>(ctx->dRowZero + ctx->nRows + ctx->rowTiles);
+    CK(cudaMemsetAsync(ctx->dRowZero, 0, ((size_t)ctx->nRows + ctx->rowTiles) * sizeof(uint32_t) + sizeof(RowMisc), s));
+    k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys, rowCnt,
                                (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi);
     dim3 lg(gridFor((uint32_t)n, 256, 64), 16);
     mark(ctx, 5);
     k_large<<<lg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
-                               ctx->uidBits, ctx->dPairKeys[0], (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi, ctx->partRank);
+                               ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi,
+                               ctx->partRank);
     mark(ctx, 6);
-    ctx->sortPairs.launches = 0;
-    ctx->sortPairs.sort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr, &ctx->dCtr->pairCount, 0,
-                                         2 * ctx->uidBits, ctx->dSide + 1, s);
+    // canonical (uid0, uid1) order: rows keyed by uid0 (pair_rows.cuh); rowStart is also the "first pair of uid0" table
+    uint32_t* rowStart = ctx->dPairFirst[cur];
+    k_row_scan<<<ctx->rowTiles, 256, 0, s>>>(rowCnt, ctx->nRows, rowStart, rowStatus, rowMisc, ctx->dBigRows, ctx->dNumPairs[cur]);
+    k_row_scatter<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys, ctx->dCtr, (uint32_t)ctx->cfg.max_pairs,
+                                                                             ctx->uidBits, rowStart, ctx->dCsr);
+    k_row_sort<<<gridFor(ctx->nRows, 256), 256, 0, s>>>(rowStart, ctx->nRows, ctx->dCsr, ctx->uidBits, ctx->dPairs, ctx->dSortedKeys[cur]);
+    k_row_sort_big<<<148 * 4, 256, 0, s>>>(rowStart, ctx->dBigRows, rowMisc, ctx->dCsr, ctx->uidBits, ctx->dPairs, ctx->dSortedKeys[cur]);
     mark(ctx, 7);
-    k_pairs_unpack<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dSide + 1,
-                                                                              ctx->dCtr, (uint32_t)ctx->cfg.max_pairs, ctx->uidBits,
-                                                                              ctx->dPairs, ctx->dSortedKeys[cur], ctx->dNumPairs[cur]);
     // manifolds follow their pair into the new list (done here so a step without dispatch keeps them too)
     k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
                                                                       ctx->dSortedKeys[cur ^ 1], ctx->dNumPairs[cur ^ 1],
                                                                       ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
                                                                       ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr);
-    k_pair_first<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairs, ctx->dNumPairs[cur], ctx->dPairFirst[cur],
-                                                                           (uint32_t)ctx->cfg.max_bodies);
-    ctx->launches += 8 + ctx->sortBodies.launches + ctx->sortPairs.launches;
+    ctx->launches += 10 + ctx->sortBodies.launches;
     CK(cudaGetLastError());
     ctx->step++;
     ctx->pairsValid = true;
@@ -522,13 +531,19 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     for (int i = 0; i < 2; i++) {
         CKC(dalloc(&ctx->dKeys[i], N));
         CKC(dalloc(&ctx->dVals[i], N));
-        CKC(dalloc(&ctx->dPairKeys[i], P));
         CKC(dalloc(&ctx->dSortedKeys[i], P));
         CKC(dalloc(&ctx->dNumPairs[i], (size_t)1));
         CKC(dalloc(&ctx->dMHdr[i], P));
         CKC(dalloc(&ctx->dMPts[i], 4 * P));
         CKC(dalloc(&ctx->dPairFirst[i], N + 4));
     }
+    if (N + 2 >= (1u << 21)) return fail(B2C_ERR_BAD_ARG);  // emitted pair key = slot | uid0 | uid1 in 3 x uidBits <= 63 bits
+    CKC(dalloc(&ctx->dPairKeys, P));
+    CKC(dalloc(&ctx->dCsr, P));
+    ctx->nRows = (uint32_t)N + 2u;
+    ctx->rowTiles = (ctx->nRows + RSCAN_TILE - 1) / RSCAN_TILE;
+    CKC(dalloc(&ctx->dRowZero, (size_t)ctx->nRows + ctx->rowTiles + sizeof(RowMisc) / sizeof(uint32_t)));
+    CKC(dalloc(&ctx->dBigRows, (size_t)ctx->nRows));
     CKC(dalloc(&ctx->dSide, (size_t)4));
     CKC(dalloc(&ctx->dSmin, N));
     CKC(dalloc(&ctx->dSmax, N));
@@ -541,7 +556,6 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dCtr, (size_t)1));
     CKC(cudaMallocHost((void**)&ctx->hCtrPinned, sizeof(StepCounters)));
     CKC(ctx->sortBodies.init((uint32_t)N));
-    CKC(ctx->sortPairs.init((uint32_t)P));
     ctx->uidBits = bitsFor((uint32_t)N + 1u);
     CKC(dalloc(&ctx->dPairs, P));
     CKC(dalloc(&ctx->dRaw, P));
@@ -587,12 +601,13 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->B.lastSet); cudaFree(ctx->B.material);
     cudaFree(ctx->dStaging); cudaFreeHost(ctx->hStagingPinned); cudaFree(ctx->dExtAabb); cudaFree(ctx->dExtMask);
     for (int i = 0; i < 2; i++) {
-        cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dPairKeys[i]); cudaFree(ctx->dSortedKeys[i]);
+        cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dSortedKeys[i]);
         cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dMHdr[i]); cudaFree(ctx->dMPts[i]); cudaFree(ctx->dPairFirst[i]);
     }
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
-    ctx->sortBodies.destroy(); ctx->sortPairs.destroy();
+    ctx->sortBodies.destroy();
+    cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dRowZero); cudaFree(ctx->dBigRows);
     cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);

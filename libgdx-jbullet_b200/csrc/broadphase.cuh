@@ -403,9 +403,13 @@ __device__ __forceinline__ bool filterPass(uint32_t fa, uint32_t fb) {  // bp/Ha
 constexpr int PAIR_STAGE = 96;  // per-warp staging capacity (flush when > 64 are waiting)
 
 struct PairStager {
-    uint64_t* buf;   // this warp's shared-memory slice
-    int count;       // warp-uniform
-    __device__ __forceinline__ void init(uint64_t* warpBuf) { buf = warpBuf; count = 0; }
+    uint64_t* buf;      // this warp's shared-memory slice
+    uint32_t* rowCnt;   // pairs per uid0 so far this step: the atomicAdd's return value is the pair's slot in its row
+    int count;          // warp-uniform
+    int uidBits;
+    __device__ __forceinline__ void init(uint64_t* warpBuf, uint32_t* rowCounters, int bits) {
+        buf = warpBuf; rowCnt = rowCounters; count = 0; uidBits = bits;
+    }
     __device__ __forceinline__ void flush(uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr) {
         if (count == 0) return;
         const int lane = threadIdx.x & 31;
@@ -415,14 +419,19 @@ struct PairStager {
         __syncwarp();
         for (int k = lane; k < count; k += 32) {
             uint32_t pos = base + k;
-            if (pos < maxPairs) pairKeys[pos] = buf[k];
-            else ctr->pairOverflow = 1;
+            if (pos < maxPairs) {
+                uint64_t key = buf[k];
+                uint32_t slot = atomicAdd(&rowCnt[(uint32_t)(key >> uidBits)], 1u);
+                pairKeys[pos] = key | ((uint64_t)slot << (2 * uidBits));  // pair_rows.cuh: slot | uid0 | uid1
+            } else {
+                ctr->pairOverflow = 1;
+            }
         }
         __syncwarp();
         count = 0;
     }
     // all 32 lanes call this together
-    __device__ __forceinline__ void push(bool hit, uint32_t bodyA, uint32_t bodyB, int uidBits, uint64_t* __restrict__ pairKeys,
+    __device__ __forceinline__ void push(bool hit, uint32_t bodyA, uint32_t bodyB, uint64_t* __restrict__ pairKeys,
                                          uint32_t maxPairs, StepCounters* ctr) {
         uint32_t m = __ballot_sync(0xffffffffu, hit);
         if (m == 0) return;
@@ -444,10 +453,10 @@ struct PairStager {
 __global__ void __launch_bounds__(256)
 k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ srow,
         const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
-        uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi) {
+        uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi) {
     __shared__ uint64_t stage[8][PAIR_STAGE];
     PairStager st;
-    st.init(stage[threadIdx.x >> 5]);
+    st.init(stage[threadIdx.x >> 5], rowCnt, uidBits);
     const int i = blockIdx.x * blockDim.x + threadIdx.x + partLo;  // this rank's slice [partLo, partHi) of the sorted list
     n = n < partHi ? n : partHi;
     const int nb = blockIdx.y;  // 0..8
@@ -503,7 +512,7 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                 j++;
             }
         }
-        st.push(hit, __float_as_uint(amin.w), bodyB, uidBits, pairKeys, maxPairs, ctr);
+        st.push(hit, __float_as_uint(amin.w), bodyB, pairKeys, maxPairs, ctr);
     }
     st.flush(pairKeys, maxPairs, ctr);
 }
@@ -513,10 +522,11 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
 __global__ void __launch_bounds__(256)
 k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ rowStart,
         const GridParams* __restrict__ grid, const int* __restrict__ world, int numWorlds, int uidBits,
-        uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi, int partRank) {
+        uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi,
+        int partRank) {
     __shared__ uint64_t stage[8][PAIR_STAGE];
     PairStager st;
-    st.init(stage[threadIdx.x >> 5]);
+    st.init(stage[threadIdx.x >> 5], rowCnt, uidBits);
     const int nrows = grid->nrows, rpw = grid->rowsPerWorld;
     const uint32_t l0 = rowStart[nrows], l1 = rowStart[nrows + 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) ctr->largeCount = l1 - l0;
@@ -546,25 +556,10 @@ k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                 // (large, large) pairs belong to rank 0
                 if (hit) hit = (j >= l0) ? (partRank == 0) : ((int)j >= partLo && (int)j < partHi);
             }
-            st.push(hit, bodyA, bodyB, uidBits, pairKeys, maxPairs, ctr);
+            st.push(hit, bodyA, bodyB, pairKeys, maxPairs, ctr);
         }
     }
     st.flush(pairKeys, maxPairs, ctr);
-}
-
-// k_pairs_unpack: sorted packed keys -> (uid0, uid1) int2 list; records the pair count for this step.
-__global__ void __launch_bounds__(256)
-k_pairs_unpack(const uint64_t* keysA, const uint64_t* keysB, const uint32_t* __restrict__ side, const StepCounters* ctr,
-               uint32_t maxPairs, int uidBits, int2* __restrict__ pairs, uint64_t* __restrict__ sortedKeys,
-               uint32_t* __restrict__ numPairsOut) {
-    uint32_t n = ctr->pairCount < maxPairs ? ctr->pairCount : maxPairs;
-    const uint64_t* keys = *side ? keysB : keysA;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *numPairsOut = n;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        uint64_t k = keys[p];
-        sortedKeys[p] = k;
-        pairs[p] = make_int2((int)(k >> uidBits), (int)(k & ((1ull << uidBits) - 1ull)));
-    }
 }
 
 }  // namespace b2c

@@ -234,17 +234,6 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
     }
 }
 
-// prevFirst table for the NEXT step's k_carry: first[u] = first pair index whose uid0 >= u (u in 0..maxUid+1)
-__global__ void __launch_bounds__(256)
-k_pair_first(const int2* __restrict__ pairs, const uint32_t* __restrict__ numPairs, uint32_t* __restrict__ first, uint32_t maxUid) {
-    const uint32_t n = *numPairs;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += gridDim.x * blockDim.x) {
-        uint32_t cur = p < n ? (uint32_t)pairs[p].x : maxUid + 2u;
-        uint32_t prev = p ? (uint32_t)pairs[p - 1].x + 1u : 0u;
-        for (uint32_t u = prev; u <= cur && u <= maxUid + 1u; u++) first[u] = p;
-    }
-}
-
 // ---- one world partitioned over several GPUs: manifolds follow pairs that change owner ------------------
 // Each rank emits the pairs whose first member (in sorted-AABB order) lies in its contiguous range of the
 // sorted proxy list, so a pair near a range boundary can change owner from one step to the next.  Its manifold

@@ -59,5 +59,52 @@ def main(path):
         print(f"| {name} | " + " | ".join(vals) + " |")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 2 and sys.argv[2] == "--traffic"):
     main(sys.argv[1])
+
+
+STAGE_OF = [  # kernel-name prefix -> bench.py stage (b2c_stage_name); order of launch inside one step disambiguates the sorts
+    ("k_aabb", "aabb"), ("k_bounds", "bounds_keys"), ("k_keys", "bounds_keys"), ("k_gather", "gather"), ("k_sweep", "sweep"),
+    ("k_large", "large"), ("k_row_", "sort_pairs"), ("k_pairs_unpack", "unpack_carry"), ("k_carry", "unpack_carry"),
+    ("k_pair_first", "unpack_carry"), ("k_classify", "classify_bin"), ("k_sphere_sphere", "closed_form"),
+    ("k_convex_plane", "closed_form"), ("k_gjk", "gjk_mesh"), ("k_mesh_query", "gjk_mesh"), ("k_epa", "epa_fold_count"),
+    ("k_manifold", "epa_fold_count"), ("k_mesh_manifold", "epa_fold_count"),
+]
+
+
+def traffic(path):
+    """Sum dram__bytes_read+write per bench stage over ONE profiled step -> profiles/traffic.json (bytes per launch group)."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    u = dict(zip(hdr, units))
+    out = {}
+    sort_no = 0
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        name = d["Kernel Name"]
+        short = name.replace("void ", "").replace("<unnamed>::", "")
+        stage = None
+        if short.startswith("rs_"):
+            if short.startswith("rs_reset"):
+                sort_no += 1
+            stage = {1: "sort_proxies", 2: "sort_pairs"}.get(sort_no, "classify_bin")
+        else:
+            for pre, st in STAGE_OF:
+                if short.startswith(pre):
+                    stage = st
+                    break
+        if stage is None:
+            continue
+        b = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            f = float(d.get(k, 0) or 0)
+            unit = u.get(k, "").lower()
+            f *= {"byte": 1, "b": 1, "kbyte": 1e3, "kb": 1e3, "mbyte": 1e6, "mb": 1e6, "gbyte": 1e9, "gb": 1e9}.get(unit, 1)
+            b += f
+        out[stage] = out.get(stage, 0.0) + b
+    print(json.dumps({k: round(v) for k, v in out.items()}, indent=1))
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+    traffic(sys.argv[1])
