@@ -177,9 +177,11 @@ def algorithmic_bytes(stage, N, P, st, key_passes_body, key_passes_pair, contact
     if stage == "large":
         return st["large_proxies"] * N * 32
     if stage == "sort_pairs":
-        return P * 8 + key_passes_pair * 2 * 8 * P
+        # pair_rows.cuh: scan of N row counters (r 4N, w 4N), scatter (r 8P, w 4P), row sort (r 4P, w 8P pairs + 8P keys)
+        return 8 * N + P * (8 + 4 + 4 + 16)
     if stage == "unpack_carry":
-        return P * (8 + 8 + 8) + 2 * (32 * P + 96 * contacts)
+        # k_carry: keys + search in last step's keys, header copy r/w, live point copy r/w
+        return P * (8 + 8) + 2 * (32 * P + 96 * contacts)
     if stage == "classify_bin":
         return P * (8 + 2 * (1 + 4 + 4) + 1 + 4) + P * (1 + 4)
     if stage == "closed_form":

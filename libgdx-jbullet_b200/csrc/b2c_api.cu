@@ -38,6 +38,14 @@ struct b2c_ctx {
     b2c_config cfg;
     int device = 0;
     cudaStream_t stream = nullptr;
+    // side streams of the narrowphase (forked from / joined to `stream` with events inside one step):
+    cudaStream_t streamClosed = nullptr;  // sphere-sphere / convex-plane bins, beside the GJK kernels
+    cudaStream_t streamEpa = nullptr;     // penetration bin (few long-latency lanes), beside k_manifold_cc; high priority
+    cudaEvent_t evFork[2] = {nullptr, nullptr}, evJoin[2] = {nullptr, nullptr};
+    bool overlap = true;
+    int epaHint = -1;                     // -1 unknown, 0 small penetration bin (shared-memory tier), 1 large (local-memory tier)
+    bool timeline = false;                // B2C_TIMELINE=1: print where the side-stream kernels ran (debug)
+    cudaEvent_t tl[6] = {};
     std::string err;
 
     // shapes
@@ -386,9 +394,17 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
                                         ctx->dSide + 2, s, 3);
     ctx->launches += ctx->sortBins.launches - 2;
     mark(ctx, 9);
-    k_sphere_sphere<<<148 * 4, 256, 0, s>>>(a);
+    // the closed-form bins touch only their own pairs' records: they run beside the GJK kernels
+    cudaStream_t sc = s;
+    if (ctx->overlap) {
+        sc = ctx->streamClosed;
+        CK(cudaEventRecord(ctx->evFork[0], s));
+        CK(cudaStreamWaitEvent(sc, ctx->evFork[0], 0));
+    }
+    k_sphere_sphere<<<148 * 4, 256, 0, sc>>>(a);
     ctx->launches += 5;
-    if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, s>>>(a); ctx->launches++; }
+    if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, sc>>>(a); ctx->launches++; }
+    if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[0], sc));
     mark(ctx, 10);
     CK(cudaMemsetAsync(ctx->dCursors, 0, 4 * sizeof(uint32_t), s));
     k_gjk_prefilter<<<148 * 8, 256, 0, s>>>(a, ctx->dSurvivors, ctx->dCursors + 2);
@@ -400,16 +416,40 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         ctx->launches += 2;
     }
     mark(ctx, 11);
+    // the penetration bin is a handful of long, latency-bound lanes: it runs on its own (high-priority) stream while
+    // k_manifold_cc streams through the manifolds of all the other pairs
+    cudaStream_t se = s;
+    if (ctx->overlap) {
+        se = ctx->streamEpa;
+        CK(cudaEventRecord(ctx->evFork[1], s));
+        CK(cudaStreamWaitEvent(se, ctx->evFork[1], 0));
+    }
     {
         static_assert(EPA_SMALL_STRIDE % 8 == 4, "lane chunks need an odd word stride");
         const int smem = EPA_BLOCK * EPA_SMALL_STRIDE;
         cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_epa<0><<<EPA_GRID, EPA_BLOCK, smem, s>>>(a, g);
-        k_epa<2><<<EPA_GRID3, EPA_BLOCK3, 0, s>>>(a, g);
+        // blocks of two kernels share an SM only when both run with the same L1/shared split: k_manifold_cc has to ask for
+        // the split the shared-memory EPA pools force, or it would wait for every EPA block to retire
+        if (ctx->overlap) cudaFuncSetAttribute(k_manifold_cc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (ctx->timeline) cudaEventRecord(ctx->tl[0], se);
+        // which variant: the host knows the size of the previous step's bin (when it has read the counters); the kernels
+        // handle any count either way, so a stale hint only costs time.  Without a hint both are launched and the device decides.
+        const int hint = ctx->epaHint;
+        if (hint <= 0) { k_epa<0><<<EPA_GRID, EPA_BLOCK, smem, se>>>(a, g, hint < 0 ? 0 : 1); ctx->launches++; }
+        if (ctx->timeline) cudaEventRecord(ctx->tl[1], se);
+        if (hint != 0) { k_epa<2><<<EPA_GRID3, EPA_BLOCK3, 0, se>>>(a, g, hint < 0 ? 0 : 1); ctx->launches++; }
     }
-    k_epa<1><<<EPA_GRID2, EPA_BLOCK2, 0, s>>>(a, g);
+    k_epa<1><<<EPA_GRID2, EPA_BLOCK2, 0, se>>>(a, g, 0);  // retry tier + the manifolds of the whole bin
+    if (ctx->timeline) cudaEventRecord(ctx->tl[2], se);
+    if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[1], se));
+    if (ctx->timeline) cudaEventRecord(ctx->tl[3], s);
     k_manifold_cc<<<148 * 8, 256, 0, s>>>(a);
-    ctx->launches += 4;
+    if (ctx->timeline) cudaEventRecord(ctx->tl[4], s);
+    ctx->launches += 2;
+    if (ctx->overlap) {
+        CK(cudaStreamWaitEvent(s, ctx->evJoin[1], 0));
+        CK(cudaStreamWaitEvent(s, ctx->evJoin[0], 0));
+    }
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
     mark(ctx, 12);
     ctx->stageValid = ctx->prof;
@@ -427,6 +467,7 @@ int32_t readCounters(b2c_ctx* ctx) {
     ctx->stats.num_contacts_added = (int32_t)c.contactsAdded;
     ctx->stats.gjk_checks = (int32_t)c.gjkChecks;
     ctx->stats.deep_penetration_checks = (int32_t)c.deepChecks;
+    ctx->epaHint = c.epaCount > EPA_SMEM_LANES ? 1 : 0;
     ctx->stats.epa_failed = (int32_t)(c.epaFailed & 0x3fffffffu);
     ctx->stats.mesh_items = (int32_t)c.meshItems;
     ctx->stats.large_proxies = (int32_t)c.largeCount;
@@ -509,6 +550,21 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     } while (0)
     CKC(cudaSetDevice(cfg->device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        int prLo = 0, prHi = 0;
+        CKC(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+        CKC(cudaStreamCreateWithPriority(&ctx->streamClosed, cudaStreamNonBlocking, prLo));
+        CKC(cudaStreamCreateWithPriority(&ctx->streamEpa, cudaStreamNonBlocking, prHi));
+        for (int i = 0; i < 2; i++) {
+            CKC(cudaEventCreateWithFlags(&ctx->evFork[i], cudaEventDisableTiming));
+            CKC(cudaEventCreateWithFlags(&ctx->evJoin[i], cudaEventDisableTiming));
+        }
+        const char* e = getenv("B2C_OVERLAP");  // measurement knob: 0 = everything on one stream
+        ctx->overlap = !(e && e[0] == '0');
+        const char* t = getenv("B2C_TIMELINE");
+        ctx->timeline = t && t[0] == '1';
+        for (int i = 0; i < 6; i++) CKC(cudaEventCreate(&ctx->tl[i]));
+    }
     const size_t N = (size_t)cfg->max_bodies, P = (size_t)cfg->max_pairs;
     CKC(dalloc(&ctx->dShapes, (size_t)cfg->max_shapes));
     CKC(dalloc(&ctx->dHullPts, (size_t)(cfg->max_hull_points > 0 ? cfg->max_hull_points : 1)));
@@ -614,6 +670,12 @@ void b2c_destroy(b2c_ctx* ctx) {
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
+        if (ctx->evJoin[i]) cudaEventDestroy(ctx->evJoin[i]);
+    }
+    if (ctx->streamClosed) cudaStreamDestroy(ctx->streamClosed);
+    if (ctx->streamEpa) cudaStreamDestroy(ctx->streamEpa);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1194,6 +1256,13 @@ int32_t b2c_get_stage_times(b2c_ctx* ctx, float ms[B2C_NUM_STAGES]) {
     if (!ctx->stageValid) return B2C_ERR_STATE;
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->timeline) {
+        float v[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < 5; k++) cudaEventElapsedTime(&v[k], ctx->stageEv[11], ctx->tl[k]);
+        fprintf(stderr, "[b2c timeline, ms after stage 11 start] epa0 %.3f..%.3f  epa-chain end %.3f | manifold_cc %.3f..%.3f\n", v[0], v[1],
+                v[2], v[3], v[4]);
+        cudaGetLastError();
+    }
     for (int k = 0; k < B2C_NUM_STAGES; k++) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, ctx->stageEv[k], ctx->stageEv[k + 1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; }

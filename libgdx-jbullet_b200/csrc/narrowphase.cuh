@@ -615,6 +615,7 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
                         g.epaItems[slot].meshItem = -1;
                         g.epaItems[slot].g = r;
                         a.raw[p].has_contact = -2;  // pending in the penetration bin
+                        a.rawFlag[p] = -2;
                         queued = true;
                     } else {
                         a.ctr->epaFailed = 0x7fffffffu;  // capacity: reported by the host as B2C_ERR_CAPACITY
@@ -633,31 +634,39 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
     if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
 }
 
-// k_manifold_cc: ConvexConvexAlgorithm's manifold side for every pair of the GJK bins, after the detector
-// (and the penetration bin) have produced the raw record: getNewManifold on first use
-// (disp/ConvexConvexAlgorithm.java:92-96), ManifoldResult.addContactPoint, refreshContactPoints (:136-138).
+// ConvexConvexAlgorithm's manifold side for one pair of the GJK bins, after the detector has produced the raw
+// record: getNewManifold on first use (disp/ConvexConvexAlgorithm.java:92-96), ManifoldResult.addContactPoint,
+// refreshContactPoints (:136-138).
+__device__ __forceinline__ void manifoldCcOne(const NpArgs& a, uint32_t p, bool has, uint32_t& added, uint32_t& created) {
+    int2 pr = a.pairs[p];
+    MView m = mview(a, p);
+    if (m.h->algorithm == 0) { m.h->algorithm = 3; m.h->body0 = pr.x; m.h->body1 = pr.y; created++; }
+    const int nc = m.h->num_contacts;
+    if (nc == 0 && !has) return;  // nothing to add, nothing to refresh
+    const b2c_raw_contact* r = a.raw + p;
+    for (int k = 0; k < nc; k++) m.p[k].src_slot = k;
+    int b0 = pr.x - 1, b1 = pr.y - 1;
+    Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+    if (has) {
+        float2 m0 = a.material[b0], m1 = a.material[b1];
+        if (manifoldAdd(m, pr.x, t0, t1, mk3(r->normal[0], r->normal[1], r->normal[2]), mk3(r->point[0], r->point[1], r->point[2]),
+                        r->depth, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0))
+            added++;
+    }
+    resultRefresh(m, pr.x, t0, t1, a.threshold);
+}
+
+// k_manifold_cc: every pair of the GJK bins whose detector finished in k_gjk / k_gjk_prefilter.  Pairs waiting in the
+// penetration bin (rawFlag == -2, set by k_gjk and never touched by k_epa) are left to k_manifold_epa, so this kernel
+// can run concurrently with the EPA kernels on another stream.
 __global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
     const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
     uint32_t added = 0, created = 0;
     for (uint32_t it = s0 + blockIdx.x * blockDim.x + threadIdx.x; it < e0; it += gridDim.x * blockDim.x) {
         uint32_t p = binItem(a, it);
-        int2 pr = a.pairs[p];
-        MView m = mview(a, p);
-        if (m.h->algorithm == 0) { m.h->algorithm = 3; m.h->body0 = pr.x; m.h->body1 = pr.y; created++; }
-        const int nc = m.h->num_contacts;
-        const bool has = a.rawFlag[p] == 1;
-        if (nc == 0 && !has) continue;  // nothing to add, nothing to refresh
-        const b2c_raw_contact* r = a.raw + p;
-        for (int k = 0; k < nc; k++) m.p[k].src_slot = k;
-        int b0 = pr.x - 1, b1 = pr.y - 1;
-        Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
-        if (has) {
-            float2 m0 = a.material[b0], m1 = a.material[b1];
-            if (manifoldAdd(m, pr.x, t0, t1, mk3(r->normal[0], r->normal[1], r->normal[2]), mk3(r->point[0], r->point[1], r->point[2]),
-                            r->depth, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0))
-                added++;
-        }
-        resultRefresh(m, pr.x, t0, t1, a.threshold);
+        const int8_t f = a.rawFlag[p];
+        if (f == -2) continue;
+        manifoldCcOne(a, p, f == 1, added, created);
     }
     if (created) atomicAdd(&a.ctr->numManifolds, created);
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
@@ -867,13 +876,16 @@ __global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g, uint32_t* 
 //           there = EPA failed, like the reference's EPA_Failed).
 constexpr uint32_t EPA_SMEM_LANES = 148u * 2u * 32u;
 
+constexpr uint32_t EPA_RETRY_BIT = 0x80000000u;  // set in EpaItem.pair while the item waits for the retry tier
+
 template <int TIER>
-__global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
+__global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g, int solo) {
     uint32_t nItems;
     if (TIER != 1) {
         nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
-        if (TIER == 0 && nItems > EPA_SMEM_LANES) return;
-        if (TIER == 2 && nItems <= EPA_SMEM_LANES) return;
+        // solo: the host launched only this variant (it knows the size of last step's bin); any count is handled
+        if (!solo && TIER == 0 && nItems > EPA_SMEM_LANES) return;
+        if (!solo && TIER == 2 && nItems <= EPA_SMEM_LANES) return;
     } else {
         nItems = a.ctr->epaRetry < g.maxEpaRetry ? a.ctr->epaRetry : g.maxEpaRetry;
     }
@@ -883,7 +895,7 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
     for (uint32_t it0 = first; it0 < nItems; it0 += step) {
         const uint32_t it = TIER != 1 ? it0 : g.epaRetry[it0];
         EpaItem item = g.epaItems[it];
-        uint32_t p = item.pair;
+        uint32_t p = item.pair & ~EPA_RETRY_BIT;
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
         ShapeDev s0 = a.shapes[a.shape[b0]], s1 = a.shapes[a.shape[b1]];
@@ -923,7 +935,7 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
         if (TIER != 1) {
             if (poolOverflow) {
                 uint32_t slot = atomicAdd(&a.ctr->epaRetry, 1u);
-                if (slot < g.maxEpaRetry) { g.epaRetry[slot] = it; continue; }
+                if (slot < g.maxEpaRetry) { g.epaRetry[slot] = it; g.epaItems[it].pair = p | EPA_RETRY_BIT; continue; }
                 epaFail = true;  // retry list full: report as failure below
             }
         } else {
@@ -959,9 +971,28 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g) {
         b2c_raw_contact* rw = item.meshItem >= 0 ? g.rawMesh + item.meshItem : a.raw + p;
         writeRaw(rw, pr, tri, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0), isValid ? pt : mk3(0, 0, 0),
                  isValid ? distance : 0.f, method, r.curIter);
-        if (item.meshItem < 0) a.rawFlag[p] = isValid ? 1 : 0;
+        if (TIER == 1 && item.meshItem < 0) {  // the retried pair's manifold, by the thread that finished its detector
+            uint32_t added = 0, created = 0;
+            manifoldCcOne(a, p, isValid, added, created);
+            if (created) atomicAdd(&a.ctr->numManifolds, created);
+            if (added) atomicAdd(&a.ctr->contactsAdded, added);
+        }
     }
     if (failed) atomicAdd(&a.ctr->epaFailed, failed);
+    if (TIER == 1) {
+        // manifold side of every convex-convex pair that went through the penetration bin (ConvexConvexAlgorithm,
+        // disp/ConvexConvexAlgorithm.java:92-139); retried items were done above, (pair, triangle) items are folded by
+        // k_mesh_manifold
+        const uint32_t nAll = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
+        uint32_t added = 0, created = 0;
+        for (uint32_t it = first; it < nAll; it += step) {
+            const uint32_t pp = g.epaItems[it].pair;
+            if ((pp & EPA_RETRY_BIT) || g.epaItems[it].meshItem >= 0) continue;
+            manifoldCcOne(a, pp, a.raw[pp].has_contact == 1, added, created);
+        }
+        if (created) atomicAdd(&a.ctr->numManifolds, created);
+        if (added) atomicAdd(&a.ctr->contactsAdded, added);
+    }
 }
 
 // per mesh pair: fold the per-triangle contacts into the shared manifold in BVH order, then one refresh

@@ -56,7 +56,7 @@ def test_algorithmic_bytes_formula():
     import bench
     st = dict(gjk_checks=1000, deep_penetration_checks=10, large_proxies=5)
     assert bench.algorithmic_bytes("sweep", 100, 500, st, 7, 5, 0) == 9 * 100 * 4 + 100 * 32 + 8 * 500
-    assert bench.algorithmic_bytes("sort_pairs", 100, 500, st, 7, 5, 0) == 500 * 8 + 5 * 2 * 8 * 500
+    assert bench.algorithmic_bytes("sort_pairs", 100, 500, st, 7, 5, 0) == 8 * 100 + 500 * (8 + 4 + 4 + 16)
 
 
 def test_reference_arm_runs_and_prints_contract_line():
