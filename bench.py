@@ -235,39 +235,31 @@ def run_ours(args):
     gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=args.max_pairs, device=dev)
     nb = sc.n
     partitioned = wl == "c5" and world > 1
+    stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
     if partitioned:
         gw.set_partition(rank, world)
-        mcap = 1 << 18
-        mig = (torch.zeros(mcap, dtype=torch.int64, device=f"cuda:{dev}"), torch.zeros(mcap * 8, dtype=torch.int32, device=f"cuda:{dev}"),
-               torch.zeros(mcap * 96, dtype=torch.int32, device=f"cuda:{dev}"))
+        mcap = args.migrate_cap
+        slot_bytes = gw.mgpu_slot_bytes(mcap)
+        my_slot = torch.zeros(slot_bytes, dtype=torch.uint8, device=f"cuda:{dev}")
+        all_slots = torch.zeros(slot_bytes * world, dtype=torch.uint8, device=f"cuda:{dev}")
 
     def one_step():
-        """One collision step on the resident transforms; the partitioned world adds the manifold migration."""
+        """One collision step on the resident transforms.  The partitioned world adds the manifold migration: every rank
+        packs the manifolds of the pairs it stopped owning into a fixed-size slot, ONE NCCL all-gather (NVLink) enqueued
+        on the ctx stream right behind the export, and every rank adopts what it owns now.  No host synchronisation."""
         if not partitioned:
             gw.step_device()
             return
         gw.mgpu_broadphase()
-        c = gw.mgpu_export_departed(mig[0].data_ptr(), mig[1].data_ptr(), mig[2].data_ptr(), mcap)
-        cnt = torch.tensor([c], dtype=torch.int64, device=f"cuda:{dev}")
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        counts = [int(x.item()) for x in allc]
-        m = max(max(counts), 1)
-        outs = [[torch.empty(m * w_, dtype=t.dtype, device=t.device) for _ in range(world)] for t, w_ in zip(mig, (1, 8, 96))]
-        for t, w_, o in zip(mig, (1, 8, 96), outs):
-            dist.all_gather(o, t[: m * w_].contiguous())     # NCCL over NVLink: the departed manifolds of every rank
-        keys = torch.cat([outs[0][r][: counts[r]] for r in range(world)])
-        hdrs = torch.cat([outs[1][r][: counts[r] * 8] for r in range(world)])
-        pts = torch.cat([outs[2][r][: counts[r] * 96] for r in range(world)])
-        torch.cuda.current_stream().synchronize()
-        gw.mgpu_import_arrivals(keys.data_ptr(), hdrs.data_ptr(), pts.data_ptr(), int(sum(counts)))
+        gw.mgpu_export_departed_slot(my_slot.data_ptr(), mcap)
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(all_slots, my_slot)
+        gw.mgpu_import_arrival_slots(all_slots.data_ptr(), world, mcap)
         gw.mgpu_narrowphase()
-        one_step.keep = (keys, hdrs, pts)  # keep the buffers alive until the ctx stream has consumed them
 
     frames = [np.ascontiguousarray(pkg.transforms_to_planes(sc.transforms(k))) for k in range(FRAMES)]
     log(f"[rank {rank}] scene built: {nb} proxies in {time.time() - t0:.1f}s")
 
-    stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
     dframes = []
     for f in frames:
         t = torch.from_numpy(f).to(f"cuda:{dev}")
@@ -410,7 +402,10 @@ def run_ours(args):
                    "snapshot": f"settled ({args.settle} relaxation iterations)" if args.settle > 0 else "raw jittered lattice (deep overlaps)",
                    "deep_penetration_checks_per_step": st["deep_penetration_checks"],
                    "proxies": nb, "l2": "flushed between timed iterations (192 MiB write)",
-                   "parallelism": "1 world per GPU, no collective" if ngpu > 1 else "1 GPU"},
+                   "parallelism": ("1 GPU" if ngpu == 1 else
+                                   {"c2": "1 world per GPU, no collective", "c4": f"{args.worlds // world} worlds per GPU, no collective",
+                                    "c5": f"every GPU sorts all proxies, sweeps and dispatches 1/{world} of the sorted list; one "
+                                          f"all-gather of {args.migrate_cap}-manifold migration slots per step"}[wl])},
         "pairs_per_s": pairs_all / args.steps / (ms_max * 1e-3),
         "contacts_per_s": contacts_all / args.steps / (ms_max * 1e-3),
         "pairs_per_step": pairs_all / args.steps / ngpu,
@@ -502,6 +497,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 = BASELINE headline (default); c4 = batched worlds split by world; c5 = one partitioned world")
     ap.add_argument("--worlds", type=int, default=4096)
+    ap.add_argument("--migrate-cap", type=int, default=8192, help="c5, N>1: manifolds per migration slot")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket the first timed step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--save-settled", default="", help="write the settled origins (npz) here; commit it under tests/golden/")

@@ -231,6 +231,14 @@ int32_t b2c_mgpu_export_departed(b2c_ctx*, uint64_t* keys_dev, void* headers_dev
 int32_t b2c_mgpu_import_arrivals(b2c_ctx*, const uint64_t* keys_dev, const void* headers_dev, const b2c_manifold_point* points_dev,
                                  int32_t count);
 int32_t b2c_mgpu_narrowphase(b2c_ctx*);
+/* The same exchange without any host synchronisation, for a fixed-size all-gather (one NCCL call per step, enqueued
+ * right behind the export on the ctx stream): every rank packs its departed manifolds into one SLOT
+ *   { uint32 count, uint32 pad[3], uint64 keys[cap], 32-byte headers[cap], b2c_manifold_point points[4*cap] }
+ * of b2c_mgpu_slot_bytes(cap) bytes; after the all-gather each rank scans all `nslots` slots on the device.  A slot
+ * that would overflow is reported by the next b2c_sync_counts as B2C_ERR_CAPACITY. */
+int64_t b2c_mgpu_slot_bytes(int32_t cap);
+int32_t b2c_mgpu_export_departed_slot(b2c_ctx*, void* slot_dev, int32_t cap);
+int32_t b2c_mgpu_import_arrival_slots(b2c_ctx*, const void* slots_dev, int32_t nslots, int32_t cap);
 
 #ifdef __cplusplus
 }

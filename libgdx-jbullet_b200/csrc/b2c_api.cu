@@ -288,8 +288,8 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     }
     unsigned nb = (n + 255) / 256;
     mark(ctx, 1);
-    k_bounds<<<nb, 256, 0, s>>>(ctx->B, n, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.num_worlds, ctx->maxRows, ctx->dCtr,
-                                ctx->dGrid);
+    k_bounds<<<nb, 256, 0, s>>>(ctx->B, n, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.num_worlds,
+                                ctx->maxRows - ctx->cfg.num_worlds, ctx->dCtr, ctx->dGrid);
     k_keys<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0]);
     int rowBits = bitsFor((uint32_t)ctx->maxRows + 2u);
     mark(ctx, 2);
@@ -310,7 +310,11 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->dRowZero, 0, ((size_t)ctx->nRows + ctx->rowTiles) * sizeof(uint32_t) + sizeof(RowMisc), s));
     k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys, rowCnt,
                                (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi);
-    dim3 lg(gridFor((uint32_t)n, 256, 64), 16);
+    // one block column per large proxy (static planes, meshes, big statics; one floor per world in batched scenes): the
+    // host sizes the grid from the last count it has read, the kernel strides over whatever there is
+    const unsigned perWorld = (unsigned)(n / ctx->cfg.num_worlds + 1);
+    const int lhint = ctx->stats.large_proxies > 16 ? ctx->stats.large_proxies : 16;
+    dim3 lg(gridFor(perWorld, 256, 64), (unsigned)(lhint < 8192 ? lhint : 8192));
     mark(ctx, 5);
     k_large<<<lg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
                                ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi,
@@ -486,6 +490,10 @@ int32_t readCounters(b2c_ctx* ctx) {
         ctx->err = buf;
         return B2C_ERR_CAPACITY;
     }
+    if (c.migrateOverflow) {
+        ctx->err = "partitioned world: manifold migration slot too small";
+        return B2C_ERR_CAPACITY;
+    }
     if (c.epaFailed >= 0x40000000u) {
         ctx->err = "penetration-solver work list capacity exceeded";
         return B2C_ERR_CAPACITY;
@@ -606,7 +614,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dSrow, N));
     ctx->maxRows = (int)(2 * N + 64 > (size_t)(64 * cfg->num_worlds) ? 2 * N + 64 : (size_t)(64 * cfg->num_worlds));
     if (ctx->maxRows > (1 << 20) - 4) ctx->maxRows = (1 << 20) - 4;  // the row shares a 32-bit key with 12 bits of x
-    if ((long long)cfg->num_worlds * 4 > ctx->maxRows) return fail(B2C_ERR_BAD_ARG);
+    if ((long long)cfg->num_worlds * 5 > ctx->maxRows) return fail(B2C_ERR_BAD_ARG);
     CKC(dalloc(&ctx->dRowStart, (size_t)ctx->maxRows + 8));
     CKC(dalloc(&ctx->dGrid, (size_t)1));
     CKC(dalloc(&ctx->dCtr, (size_t)1));
@@ -1323,6 +1331,39 @@ int32_t b2c_mgpu_import_arrivals(b2c_ctx* ctx, const uint64_t* keys, const void*
     k_import_arrivals<<<gridFor((uint32_t)count, 256), 256, 0, ctx->stream>>>(
         keys, (const ManifoldHdr*)hdrs, pts, (uint32_t)count, ctx->dSortedKeys[cur], ctx->dNumPairs[cur], ctx->dPairFirst[cur],
         ctx->uidBits, ctx->dMHdr[cur], ctx->dMPts[cur], ctx->dCtr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int64_t b2c_mgpu_slot_bytes(int32_t cap) { return cap < 0 ? 0 : (int64_t)mgpuSlotBytes((uint32_t)cap); }
+
+int32_t b2c_mgpu_export_departed_slot(b2c_ctx* ctx, void* slot, int32_t cap) {
+    if (!ctx || !slot || cap < 1) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const int cur = ctx->cur, prev = cur ^ 1;
+    unsigned char* b = (unsigned char*)slot;
+    CK(cudaMemsetAsync(b, 0, 16, s));
+    k_export_departed<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(
+        ctx->dSortedKeys[prev], ctx->dNumPairs[prev], ctx->dMHdr[prev], ctx->dMPts[prev], ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
+        ctx->dPairFirst[cur], ctx->uidBits, (uint64_t*)(b + 16), (ManifoldHdr*)(b + 16 + (size_t)cap * 8),
+        (b2c_manifold_point*)(b + 16 + (size_t)cap * (8 + sizeof(ManifoldHdr))), (uint32_t)cap, (uint32_t*)b);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_import_arrival_slots(b2c_ctx* ctx, const void* slots, int32_t nslots, int32_t cap) {
+    if (!ctx || !slots || nslots < 1 || cap < 1) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    const int cur = ctx->cur;
+    dim3 grid(gridFor((uint32_t)cap, 256, 64), (unsigned)nslots);
+    k_import_arrival_slots<<<grid, 256, 0, ctx->stream>>>((const unsigned char*)slots, (uint32_t)nslots, (uint32_t)cap,
+                                                           ctx->dSortedKeys[cur], ctx->dNumPairs[cur], ctx->dPairFirst[cur], ctx->uidBits,
+                                                           ctx->dMHdr[cur], ctx->dMPts[cur], ctx->dCtr);
     ctx->launches++;
     CK(cudaGetLastError());
     return B2C_OK;

@@ -304,6 +304,7 @@ k_bounds(BodyArrays B, int n, int mode, int step, int numWorlds, int maxRows, St
         g.ny = ny; g.nz = nz;
         g.rowsPerWorld = ny * nz;
         g.nrows = ny * nz * numWorlds;
+        g.numWorlds = numWorlds;
         {
             uint32_t xa = ~*(volatile uint32_t*)&ctr->minXKey, xb = *(volatile uint32_t*)&ctr->maxXKey;
             float x0 = 0.f, x1 = 0.f;
@@ -343,13 +344,13 @@ k_keys(BodyArrays B, int n, const StepCounters* __restrict__ ctr, const GridPara
     uint32_t row;
     uint32_t xk = 0;
     if (!(flags & BF_ALIVE)) {
-        row = (uint32_t)g.nrows + 1u;
+        row = (uint32_t)(g.nrows + g.numWorlds);
     } else {
         float4 a = B.effMin[i], b = B.effMax[i];
         float ey = b.y - a.y, ez = b.z - a.z;
         bool large = !(ey <= limitY) || !(ez <= limitZ) || !(fabsf(a.y) < 1e29f) || !(fabsf(a.z) < 1e29f) || !(fabsf(a.x) < 1e29f);
         if (large) {
-            row = (uint32_t)g.nrows;
+            row = (uint32_t)(g.nrows + B.world[i]);  // one row of large proxies per world
         } else {
             int cy = cellOf(a.y, g.y0, g.invCellY, g.ny), cz = cellOf(a.z, g.z0, g.invCellZ, g.nz);
             row = (uint32_t)(B.world[i] * g.rowsPerWorld + cy * g.nz + cz);
@@ -381,7 +382,7 @@ k_gather(BodyArrays B, int n, const uint32_t* keysA, const uint32_t* keysB, cons
     smax[j] = b;
     srow[j] = k;  // the whole sorted key: row = k >> 12, qx = k & 4095
     uint32_t prev = j ? (keys[j - 1] >> 12) : 0xffffffffu;
-    const uint32_t lastRow = (uint32_t)grid->nrows + 2u;
+    const uint32_t lastRow = (uint32_t)(grid->nrows + grid->numWorlds) + 1u;
     if (j == 0) {
         for (uint32_t r = 0; r <= row; r++) rowStart[r] = 0;
     } else if (prev != row) {
@@ -528,19 +529,20 @@ k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
     PairStager st;
     st.init(stage[threadIdx.x >> 5], rowCnt, uidBits);
     const int nrows = grid->nrows, rpw = grid->rowsPerWorld;
-    const uint32_t l0 = rowStart[nrows], l1 = rowStart[nrows + 1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->largeCount = l1 - l0;
+    const uint32_t l0 = rowStart[nrows], l1 = rowStart[nrows + numWorlds];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctr->largeCount = l1 - l0;
     for (uint32_t l = l0 + blockIdx.y; l < l1; l += gridDim.y) {
         float4 amin = __ldg(smin + l), amax = __ldg(smax + l);
         uint32_t bodyA = __float_as_uint(amin.w);
-        uint32_t lo = 0, hi = l0;
+        uint32_t lo = 0, hi = l0, lend = l1;
         if (numWorlds > 1) {
             int w = world[bodyA];
             lo = rowStart[w * rpw];
             hi = rowStart[(w + 1) * rpw];
+            lend = rowStart[nrows + w + 1];
         }
-        // gridded proxies of the same world, then the large ones after l
-        uint32_t total = (hi - lo) + (l1 - (l + 1));
+        // gridded proxies of the same world, then the large ones of the same world after l
+        uint32_t total = (hi - lo) + (lend - (l + 1));
         for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < total; t0 += gridDim.x * blockDim.x) {
             uint32_t t = t0 + threadIdx.x;
             bool hit = false;

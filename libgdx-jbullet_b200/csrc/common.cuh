@@ -134,7 +134,8 @@ struct GridParams {
     float invCellY, invCellZ;
     int ny, nz;            // cells per world
     int rowsPerWorld;      // ny*nz
-    int nrows;             // numWorlds*ny*nz ; row nrows = large proxies, row nrows+1 = dead slots
+    int nrows;             // numWorlds*ny*nz ; rows nrows + w = large proxies of world w, row nrows + numWorlds = dead slots
+    int numWorlds;
     float cellY, cellZ;
     float x0, invX;        // sweep-axis quantisation: qx = clamp(floor((min.x - x0) * invX), 0, 4095)
 };
@@ -153,7 +154,8 @@ struct StepCounters {
     uint32_t largeCount;
     uint32_t epaRetry;
     uint32_t minXKey, maxXKey;  // sweep-axis bounds of the gridded proxies (min kept complemented)
-    uint32_t pad[11];
+    uint32_t migrateOverflow;   // partitioned world: a migration slot was too small
+    uint32_t pad[10];
 };
 
 // monotone float <-> uint key (total order matching float compare for non-NaN; -0 canonicalised to +0)

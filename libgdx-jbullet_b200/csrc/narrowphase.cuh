@@ -259,7 +259,9 @@ k_export_departed(const uint64_t* __restrict__ prevKeys, const uint32_t* __restr
     const uint32_t pn = *prevNum, n = *numPairs;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pn; p += gridDim.x * blockDim.x) {
         ManifoldHdr h = prevH[p];
-        if (h.algorithm == 0) continue;
+        // an empty manifold carries no state its next owner would not recreate identically (body order follows from the
+        // pair and the shape types), so only touching manifolds travel
+        if (h.algorithm == 0 || h.num_contacts == 0) continue;
         uint64_t k = prevKeys[p];
         if (findPairIndex(keys, n, first, k, uidBits) >= 0) continue;  // still ours: k_carry took care of it
         uint32_t slot = atomicAdd(outCount, 1u);
@@ -284,6 +286,36 @@ k_import_arrivals(const uint64_t* __restrict__ inKeys, const ManifoldHdr* __rest
         H[idx] = h;
         for (int q = 0; q < h.num_contacts && q < 4; q++) P[4 * (size_t)idx + q] = inP[4 * (size_t)s + q];
         atomicAdd(&ctr->numManifolds, 1u);
+    }
+}
+
+// Slot variant of the import: `nslots` fixed-size slots (one per rank, as an all-gather leaves them), each
+// { count, pad[3], keys[cap], headers[cap], points[4*cap] }; counts are read on the device.
+__host__ __device__ __forceinline__ size_t mgpuSlotBytes(uint32_t cap) {
+    return 16 + (size_t)cap * (sizeof(uint64_t) + sizeof(ManifoldHdr) + 4 * sizeof(b2c_manifold_point));
+}
+__global__ void __launch_bounds__(256)
+k_import_arrival_slots(const unsigned char* __restrict__ slots, uint32_t nslots, uint32_t cap, const uint64_t* __restrict__ keys,
+                       const uint32_t* __restrict__ numPairs, const uint32_t* __restrict__ first, int uidBits, ManifoldHdr* __restrict__ H,
+                       b2c_manifold_point* __restrict__ P, StepCounters* ctr) {
+    const uint32_t n = *numPairs;
+    const size_t slotBytes = mgpuSlotBytes(cap);
+    for (uint32_t r = blockIdx.y; r < nslots; r += gridDim.y) {
+        const unsigned char* slot = slots + (size_t)r * slotBytes;
+        uint32_t count = *reinterpret_cast<const uint32_t*>(slot);
+        if (count > cap) { if (threadIdx.x == 0 && blockIdx.x == 0) ctr->migrateOverflow = 1; count = cap; }
+        const uint64_t* inKeys = reinterpret_cast<const uint64_t*>(slot + 16);
+        const ManifoldHdr* inH = reinterpret_cast<const ManifoldHdr*>(slot + 16 + (size_t)cap * 8);
+        const b2c_manifold_point* inP = reinterpret_cast<const b2c_manifold_point*>(slot + 16 + (size_t)cap * (8 + sizeof(ManifoldHdr)));
+        for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += gridDim.x * blockDim.x) {
+            int idx = findPairIndex(keys, n, first, inKeys[s], uidBits);
+            if (idx < 0) continue;
+            ManifoldHdr h = inH[s];
+            if (H[idx].algorithm != 0) continue;
+            H[idx] = h;
+            for (int q = 0; q < h.num_contacts && q < 4; q++) P[4 * (size_t)idx + q] = inP[4 * (size_t)s + q];
+            atomicAdd(&ctr->numManifolds, 1u);
+        }
     }
 }
 

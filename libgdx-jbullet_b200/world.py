@@ -221,6 +221,15 @@ class GpuCollisionWorld:
     def mgpu_import_arrivals(self, keys_ptr, hdr_ptr, pts_ptr, count):
         self._ck(self.L.b2c_mgpu_import_arrivals(self.h, C.c_void_p(keys_ptr), C.c_void_p(hdr_ptr), C.c_void_p(pts_ptr), count))
 
+    def mgpu_slot_bytes(self, cap):
+        return int(self.L.b2c_mgpu_slot_bytes(cap))
+
+    def mgpu_export_departed_slot(self, slot_ptr, cap):
+        self._ck(self.L.b2c_mgpu_export_departed_slot(self.h, C.c_void_p(slot_ptr), cap))
+
+    def mgpu_import_arrival_slots(self, slots_ptr, nslots, cap):
+        self._ck(self.L.b2c_mgpu_import_arrival_slots(self.h, C.c_void_p(slots_ptr), nslots, cap))
+
     def mgpu_narrowphase(self):
         self._ck(self.L.b2c_mgpu_narrowphase(self.h))
 

@@ -11,7 +11,7 @@ import scenes
 pytestmark = pytest.mark.gpu
 
 
-def run_partitioned(pkg, sc, R, steps, mode=1):
+def run_partitioned(pkg, sc, R, steps, mode=1, slots=False):
     import torch
     single = scenes.build_gpu(pkg, sc, mode=mode)
     ranks = [scenes.build_gpu(pkg, sc, mode=mode) for _ in range(R)]
@@ -20,25 +20,39 @@ def run_partitioned(pkg, sc, R, steps, mode=1):
     cap = 1 << 16
     bufs = [(torch.zeros(cap, dtype=torch.int64, device="cuda"), torch.zeros(cap * 8, dtype=torch.int32, device="cuda"),
              torch.zeros(cap * 4 * 24, dtype=torch.int32, device="cuda")) for _ in range(R)]
+    scap = 1 << 14
+    sbytes = single.mgpu_slot_bytes(scap)
+    allslots = torch.zeros(sbytes * R, dtype=torch.uint8, device="cuda")
     migrated_total = 0
     for step in range(steps):
         xf = sc.transforms(step)
         single.setWorldTransforms(xf)
         single.performDiscreteCollisionDetection()
-        counts = []
-        for r, w in enumerate(ranks):
+        for w in ranks:
             w.setWorldTransforms(xf)
             w.mgpu_broadphase()
-            k, h, p = bufs[r]
-            counts.append(w.mgpu_export_departed(k.data_ptr(), h.data_ptr(), p.data_ptr(), cap))
-        # "all-gather": concatenate every rank's departed manifolds
-        keys = torch.cat([bufs[r][0][:counts[r]] for r in range(R)])
-        hdrs = torch.cat([bufs[r][1][:counts[r] * 8] for r in range(R)])
-        pts = torch.cat([bufs[r][2][:counts[r] * 96] for r in range(R)])
-        torch.cuda.synchronize()
-        tot = int(sum(counts))
+        if slots:
+            # sync-free variant: every rank packs its slot straight into the "gathered" buffer, then all ranks scan it
+            for r, w in enumerate(ranks):
+                w.mgpu_export_departed_slot(allslots.data_ptr() + r * sbytes, scap)
+                w.sync_counts()
+            tot = int(sum(int(allslots[r * sbytes:r * sbytes + 4].view(torch.int32)[0]) for r in range(R)))
+            for w in ranks:
+                w.mgpu_import_arrival_slots(allslots.data_ptr(), R, scap)
+        else:
+            counts = []
+            for r, w in enumerate(ranks):
+                k, h, p = bufs[r]
+                counts.append(w.mgpu_export_departed(k.data_ptr(), h.data_ptr(), p.data_ptr(), cap))
+            # "all-gather": concatenate every rank's departed manifolds
+            keys = torch.cat([bufs[r][0][:counts[r]] for r in range(R)])
+            hdrs = torch.cat([bufs[r][1][:counts[r] * 8] for r in range(R)])
+            pts = torch.cat([bufs[r][2][:counts[r] * 96] for r in range(R)])
+            torch.cuda.synchronize()
+            tot = int(sum(counts))
+            for w in ranks:
+                w.mgpu_import_arrivals(keys.data_ptr(), hdrs.data_ptr(), pts.data_ptr(), tot)
         for w in ranks:
-            w.mgpu_import_arrivals(keys.data_ptr(), hdrs.data_ptr(), pts.data_ptr(), tot)
             w.mgpu_narrowphase()
             w.sync_counts()
         # union of the ranks == the single world
@@ -62,6 +76,13 @@ def test_partitioned_spheres_world_matches_single(gpu_pkg):
     sc.vel *= 6.0  # enough motion that the sorted order (and with it pair ownership) changes every step
     migrated = run_partitioned(gpu_pkg, sc, R=2, steps=6)
     assert migrated > 0, "no manifold ever departed: the migration path was not exercised"
+
+
+def test_partitioned_spheres_world_slot_exchange(gpu_pkg):
+    sc = scenes.spheres_scene(n=20000, seed=8)
+    sc.vel *= 6.0
+    migrated = run_partitioned(gpu_pkg, sc, R=4, steps=5, slots=True)
+    assert migrated > 0
 
 
 def test_partitioned_bin_world_with_large_statics(gpu_pkg):
