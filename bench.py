@@ -38,6 +38,9 @@ def make_scene(n_bodies, seed, workload="c2", worlds=4096):
     import scenes
     if workload == "c4":   # independent 64-body dice worlds
         return scenes.worlds_scene(num_worlds=worlds, seed=seed)
+    if workload == "c3":   # 708 x 708 cells = 1 002 528 triangles, 50 % hull-16 / 50 % spheres r=0.4
+        cells = max(8, int(round(708 * (n_bodies / 10000.0) ** 0.5)))
+        return scenes.terrain_scene(cells=cells, n=n_bodies, seed=seed, mix=(0.5, 0.5, 0.0))
     if workload == "c5":   # spheres r=0.5 at 40 % packing, one world
         return scenes.spheres_scene(n=n_bodies, seed=seed)
     # 49 x 49 footprint at 0.82 spacing = the 40 x 40 bin of SURVEY §8d C2
@@ -223,7 +226,7 @@ def run_ours(args):
         # strong scaling: ONE world, every rank holds all proxies and owns a slice of the sorted-AABB list
         sc = make_scene(N, seed=100, workload="c5")
     else:
-        sc = make_scene(N, seed=100 + rank)
+        sc = make_scene(N, seed=100 + rank, workload=wl)
     import scenes
     if args.settle > 0 and wl == "c2":
         if args.save_settled or not load_settled(sc, N, 100 + rank, args.settle):
@@ -384,6 +387,8 @@ def run_ours(args):
     strong = wl in ("c4", "c5")
     wl_name = {"c2": f"C2: {N} mixed boxes/spheres/16-pt hulls in a closed bin of 5 static boxes, single world per GPU, "
                      "DbvtBroadphase pair semantics, seeded transform trace",
+               "c3": f"C3: {N} convex hulls (16 pts) and spheres on a {2 * max(8, int(round(708 * (N / 10000.0) ** 0.5))) ** 2}-triangle "
+                     "BvhTriangleMeshShape heightfield (quantized BVH), one world per GPU",
                "c4": f"C4: {args.worlds} independent 64-body dice worlds, split by world over the GPUs",
                "c5": f"C5: {N} spheres r=0.5 at 40% packing, ONE world partitioned by sorted-AABB slices over the GPUs, "
                      "departed manifolds all-gathered with NCCL"}[wl]
@@ -403,7 +408,7 @@ def run_ours(args):
                    "deep_penetration_checks_per_step": st["deep_penetration_checks"],
                    "proxies": nb, "l2": "flushed between timed iterations (192 MiB write)",
                    "parallelism": ("1 GPU" if ngpu == 1 else
-                                   {"c2": "1 world per GPU, no collective", "c4": f"{args.worlds // world} worlds per GPU, no collective",
+                                   {"c2": "1 world per GPU, no collective", "c3": "1 world per GPU, no collective", "c4": f"{args.worlds // world} worlds per GPU, no collective",
                                     "c5": f"every GPU sorts all proxies, sweeps and dispatches 1/{world} of the sorted list; one "
                                           f"all-gather of {args.migrate_cap}-manifold migration slots per step"}[wl])},
         "pairs_per_s": pairs_all / args.steps / (ms_max * 1e-3),
@@ -494,8 +499,9 @@ def main():
     ap.add_argument("--max-pairs", type=int, default=3 << 20)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
-                    help="c2 = BASELINE headline (default); c4 = batched worlds split by world; c5 = one partitioned world")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = BASELINE headline (default); c3 = convex bodies on a 1M-triangle BVH mesh (use --bodies 10000); "
+                         "c4 = batched worlds split by world; c5 = one partitioned world")
     ap.add_argument("--worlds", type=int, default=4096)
     ap.add_argument("--migrate-cap", type=int, default=8192, help="c5, N>1: manifolds per migration slot")
     ap.add_argument("--profile-step", action="store_true",

@@ -188,7 +188,8 @@ typedef struct {
     int32_t kernel_launches;          /* kernels launched by the last b2c_step */
     int32_t grid_rows;
     float ms_aabb, ms_broadphase, ms_narrowphase, ms_total; /* CUDA-event times of the last b2c_step */
-    int32_t pad[2];
+    int32_t epa_retries;              /* penetration-bin items redone with the large pools */
+    int32_t pad[1];
 } b2c_stats;
 int32_t b2c_get_stats(b2c_ctx*, b2c_stats* out);
 
@@ -214,6 +215,18 @@ int32_t b2c_transforms_written(b2c_ctx*, int32_t n);
  * synchronise and does not copy results to the host.  Counters are read later with b2c_sync_counts. */
 int32_t b2c_step_device(b2c_ctx*);
 int32_t b2c_sync_counts(b2c_ctx*, int32_t* num_pairs_out, int32_t* num_manifolds_out, int32_t* num_contacts_added_out);
+
+/* ---- consumers directly behind the pair list ------------------------------------------------- */
+/* Pairs that entered / left the pair cache in the last b2c_calculate_overlapping_pairs (or b2c_step): what
+ * bp/HashedOverlappingPairCache.java:323-325 and :135-137 report to OverlappingPairCallback / GhostPairCallback
+ * (disp/GhostPairCallback.java:40-68).  Rows of (uid0 < uid1); order unspecified.  Either output may be NULL to only
+ * count.  Valid until the next pair calculation. */
+int32_t b2c_get_pair_deltas(b2c_ctx*, int32_t* added_out, int32_t cap_added, int32_t* removed_out, int32_t cap_removed,
+                            int32_t* num_added_out, int32_t* num_removed_out);
+/* SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110):
+ * union-find over every broadphase pair whose two objects merge islands (non-static).  tags_out[i] = island tag of body
+ * uid i+1 (the smallest body index of its island), -1 for static bodies; n = number of bodies to report. */
+int32_t b2c_compute_islands(b2c_ctx*, int32_t* tags_out, int32_t n, int32_t* num_islands_out);
 
 /* ---- one world partitioned over several GPUs -------------------------------------
  * Every rank holds all proxies (their state is small) and owns a contiguous slice of the SORTED proxy list: it

@@ -33,7 +33,7 @@ class Stats(C.Structure):
         ("gjk_checks", C.c_int32), ("deep_penetration_checks", C.c_int32), ("epa_failed", C.c_int32),
         ("mesh_items", C.c_int32), ("large_proxies", C.c_int32), ("kernel_launches", C.c_int32), ("grid_rows", C.c_int32),
         ("ms_aabb", C.c_float), ("ms_broadphase", C.c_float), ("ms_narrowphase", C.c_float), ("ms_total", C.c_float),
-        ("pad", C.c_int32 * 2),
+        ("epa_retries", C.c_int32), ("pad", C.c_int32 * 1),
     ]
 
 
@@ -64,7 +64,7 @@ EXPORTS = [
     "b2c_device_transforms", "b2c_transforms_written", "b2c_step_device", "b2c_sync_counts", "b2c_get_contacts",
     "b2c_set_profiling", "b2c_get_stage_times", "b2c_stage_name", "b2c_set_transforms_device", "b2c_set_partition", "b2c_mgpu_broadphase", "b2c_mgpu_export_departed",
     "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase", "b2c_mgpu_slot_bytes", "b2c_mgpu_export_departed_slot",
-    "b2c_mgpu_import_arrival_slots",
+    "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands",
 ]
 NUM_STAGES = 12
 CONTACT_HEADER_DTYPE = np.dtype([
@@ -131,6 +131,8 @@ def load():
     L.b2c_mgpu_export_departed.argtypes = [vp, vp, vp, vp, i32, pi32]
     L.b2c_mgpu_import_arrivals.argtypes = [vp, vp, vp, vp, i32]
     L.b2c_mgpu_narrowphase.argtypes = [vp]
+    L.b2c_get_pair_deltas.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
+    L.b2c_compute_islands.argtypes = [vp, vp, i32, pi32]
     L.b2c_mgpu_slot_bytes.argtypes = [i32]
     L.b2c_mgpu_slot_bytes.restype = C.c_int64
     L.b2c_mgpu_export_departed_slot.argtypes = [vp, vp, i32]

@@ -13,6 +13,7 @@
 #include "broadphase.cuh"
 #include "bvh_build.h"
 #include "common.cuh"
+#include "islands.cuh"
 #include "narrowphase.cuh"
 #include "pair_rows.cuh"
 #include "radix_sort.cuh"
@@ -23,7 +24,7 @@ namespace {
 
 constexpr int EPA_GRID = 148 * 2, EPA_BLOCK = 32;      // tier 0: one warp per block, per-lane pools in shared memory (2 blocks/SM)
 constexpr int EPA_GRID3 = 148 * 16, EPA_BLOCK3 = 64;   // tier 2: pools in local memory, throughput variant
-constexpr int EPA_GRID2 = 148, EPA_BLOCK2 = 64;        // tier 1: large pools in global memory
+constexpr int EPA_GRID2 = 148 * 3, EPA_BLOCK2 = 64;    // tier 1: one item per warp, large pools in shared memory (2 x 34 KB per block)
 
 struct HostMesh {
     int4* nodes = nullptr;
@@ -112,7 +113,6 @@ struct b2c_ctx {
     RadixSorter sortBins;
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
-    EpaScratch* dEpaScratch = nullptr;
     uint32_t* dEpaRetry = nullptr;
     uint32_t maxEpaRetry = 0;
     uint32_t* dMeshPair = nullptr;
@@ -131,6 +131,12 @@ struct b2c_ctx {
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
     bool stageValid = false;
+
+    // islands + pair deltas (allocated on first use)
+    int* dIslandPar = nullptr;
+    int* dIslandTags = nullptr;
+    int2* dDelta[2] = {nullptr, nullptr};
+    uint32_t* dDeltaCounts = nullptr;  // [3]: added, removed, islands
 
     // compact contact stream
     b2c_contact_header* dContactHdr = nullptr;
@@ -379,7 +385,6 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     GjkArgs g;
     g.epaItems = ctx->dEpaItems;
     g.maxEpa = ctx->maxEpa;
-    g.scratch = ctx->dEpaScratch;
     g.epaRetry = ctx->dEpaRetry;
     g.maxEpaRetry = ctx->maxEpaRetry;
     g.meshPair = ctx->dMeshPair;
@@ -443,7 +448,11 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         if (ctx->timeline) cudaEventRecord(ctx->tl[1], se);
         if (hint != 0) { k_epa<2><<<EPA_GRID3, EPA_BLOCK3, 0, se>>>(a, g, hint < 0 ? 0 : 1); ctx->launches++; }
     }
-    k_epa<1><<<EPA_GRID2, EPA_BLOCK2, 0, se>>>(a, g, 0);  // retry tier + the manifolds of the whole bin
+    {
+        const int smem1 = (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch);
+        cudaFuncSetAttribute(k_epa<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+        k_epa<1><<<EPA_GRID2, EPA_BLOCK2, smem1, se>>>(a, g, 0);  // retry tier + the manifolds of the whole bin
+    }
     if (ctx->timeline) cudaEventRecord(ctx->tl[2], se);
     if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[1], se));
     if (ctx->timeline) cudaEventRecord(ctx->tl[3], s);
@@ -473,6 +482,7 @@ int32_t readCounters(b2c_ctx* ctx) {
     ctx->stats.deep_penetration_checks = (int32_t)c.deepChecks;
     ctx->epaHint = c.epaCount > EPA_SMEM_LANES ? 1 : 0;
     ctx->stats.epa_failed = (int32_t)(c.epaFailed & 0x3fffffffu);
+    ctx->stats.epa_retries = (int32_t)c.epaRetry;
     ctx->stats.mesh_items = (int32_t)c.meshItems;
     ctx->stats.large_proxies = (int32_t)c.largeCount;
     ctx->lastPairs = ctx->stats.num_pairs;
@@ -633,7 +643,6 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dSurvivors, P));
     ctx->maxEpa = (uint32_t)(P / 4 + 1024);
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
-    CKC(dalloc(&ctx->dEpaScratch, (size_t)EPA_GRID2 * EPA_BLOCK2));
     ctx->maxEpaRetry = ctx->maxEpa;
     CKC(dalloc(&ctx->dEpaRetry, (size_t)ctx->maxEpaRetry));
     const size_t MI = (size_t)(cfg->max_mesh_items > 0 ? cfg->max_mesh_items : 1);
@@ -673,11 +682,12 @@ void b2c_destroy(b2c_ctx* ctx) {
     ctx->sortBodies.destroy();
     cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dRowZero); cudaFree(ctx->dBigRows);
     cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
-    cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaScratch); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
+    cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
+    cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
     for (int i = 0; i < 2; i++) {
         if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
         if (ctx->evJoin[i]) cudaEventDestroy(ctx->evJoin[i]);
@@ -1249,6 +1259,61 @@ int32_t b2c_get_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b
     if (hOut && counts[0]) CK(cudaMemcpyAsync(hOut, ctx->dContactHdr, (size_t)counts[0] * sizeof(b2c_contact_header), cudaMemcpyDeviceToHost, s));
     if (pOut && counts[1]) CK(cudaMemcpyAsync(pOut, ctx->dContactPts, (size_t)counts[1] * sizeof(b2c_manifold_point), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return B2C_OK;
+}
+
+int32_t b2c_get_pair_deltas(b2c_ctx* ctx, int32_t* addedOut, int32_t capA, int32_t* removedOut, int32_t capR, int32_t* nA, int32_t* nR) {
+    if (!ctx || capA < 0 || capR < 0) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const size_t P = (size_t)ctx->cfg.max_pairs;
+    if (!ctx->dDeltaCounts) CK(dalloc(&ctx->dDeltaCounts, (size_t)4));
+    for (int i = 0; i < 2; i++)
+        if (!ctx->dDelta[i]) CK(dalloc(&ctx->dDelta[i], P));
+    const int cur = ctx->cur, prev = cur ^ 1;
+    CK(cudaMemsetAsync(ctx->dDeltaCounts, 0, 2 * sizeof(uint32_t), s));
+    const unsigned g = gridFor((uint32_t)P, 256);
+    k_pair_delta<<<g, 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur], ctx->dSortedKeys[prev], ctx->dNumPairs[prev],
+                                   ctx->dPairFirst[prev], ctx->uidBits, ctx->dDelta[0], (uint32_t)P, ctx->dDeltaCounts);
+    k_pair_delta<<<g, 256, 0, s>>>(ctx->dSortedKeys[prev], ctx->dNumPairs[prev], ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
+                                   ctx->dPairFirst[cur], ctx->uidBits, ctx->dDelta[1], (uint32_t)P, ctx->dDeltaCounts + 1);
+    uint32_t c[2] = {0, 0};
+    CK(cudaMemcpyAsync(c, ctx->dDeltaCounts, sizeof(c), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (nA) *nA = (int32_t)c[0];
+    if (nR) *nR = (int32_t)c[1];
+    if ((addedOut && (uint32_t)capA < c[0]) || (removedOut && (uint32_t)capR < c[1])) {
+        ctx->err = "pair delta output buffer too small";
+        return B2C_ERR_CAPACITY;
+    }
+    if (addedOut && c[0]) CK(cudaMemcpyAsync(addedOut, ctx->dDelta[0], (size_t)c[0] * sizeof(int2), cudaMemcpyDeviceToHost, s));
+    if (removedOut && c[1]) CK(cudaMemcpyAsync(removedOut, ctx->dDelta[1], (size_t)c[1] * sizeof(int2), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2C_OK;
+}
+
+int32_t b2c_compute_islands(b2c_ctx* ctx, int32_t* tagsOut, int32_t n, int32_t* numIslands) {
+    if (!ctx || n < 0 || n > ctx->nBodies) return B2C_ERR_BAD_ARG;
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const size_t N = (size_t)ctx->cfg.max_bodies;
+    if (!ctx->dDeltaCounts) CK(dalloc(&ctx->dDeltaCounts, (size_t)4));
+    if (!ctx->dIslandPar) CK(dalloc(&ctx->dIslandPar, N));
+    if (!ctx->dIslandTags) CK(dalloc(&ctx->dIslandTags, N));
+    const int nb = ctx->nBodies;
+    if (nb == 0) { if (numIslands) *numIslands = 0; return B2C_OK; }
+    CK(cudaMemsetAsync(ctx->dDeltaCounts + 2, 0, sizeof(uint32_t), s));
+    k_island_init<<<(nb + 255) / 256, 256, 0, s>>>(ctx->dIslandPar, nb);
+    k_island_unite<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairs, ctx->dNumPairs[ctx->cur], ctx->B.flags,
+                                                                            ctx->dIslandPar);
+    k_island_flatten<<<(nb + 255) / 256, 256, 0, s>>>(ctx->dIslandPar, ctx->B.flags, nb, ctx->dIslandTags, ctx->dDeltaCounts + 2);
+    uint32_t c = 0;
+    CK(cudaMemcpyAsync(&c, ctx->dDeltaCounts + 2, sizeof(c), cudaMemcpyDeviceToHost, s));
+    if (tagsOut && n) CK(cudaMemcpyAsync(tagsOut, ctx->dIslandTags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (numIslands) *numIslands = (int32_t)c;
     return B2C_OK;
 }
 

@@ -452,7 +452,6 @@ struct GjkArgs {
     uint32_t maxEpa;
     uint32_t* epaRetry;      // items whose small pool overflowed
     uint32_t maxEpaRetry;
-    EpaScratch* scratch;     // [tier-1 threads] large pools
     // mesh work items
     uint32_t* meshPair;      // [maxMeshItems] pair index
     int* meshTri;            // [maxMeshItems] triangle index
@@ -924,7 +923,12 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g, int solo) {
     uint32_t failed = 0;
     extern __shared__ __align__(16) unsigned char epaSmem[];
     const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
-    for (uint32_t it0 = first; it0 < nItems; it0 += step) {
+    // TIER 1: one item per WARP (lane 0), its large pool in this warp's slice of shared memory — a retried item is a long
+    // run (up to 256 polytope expansions), and in global memory every one of its dependent accesses would cost ~1 us
+    const uint32_t warpsPerBlock = blockDim.x >> 5;
+    const uint32_t itFirst = TIER != 1 ? first : ((threadIdx.x & 31) == 0 ? blockIdx.x * warpsPerBlock + (threadIdx.x >> 5) : 0xffffffffu);
+    const uint32_t itStep = TIER != 1 ? step : gridDim.x * warpsPerBlock;
+    for (uint32_t it0 = itFirst; it0 < nItems; it0 += itStep) {
         const uint32_t it = TIER != 1 ? it0 : g.epaRetry[it0];
         EpaItem item = g.epaItems[it];
         uint32_t p = item.pair & ~EPA_RETRY_BIT;
@@ -971,7 +975,7 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g, int solo) {
                 epaFail = true;  // retry list full: report as failure below
             }
         } else {
-            EpaScratch* sc = g.scratch + (blockIdx.x * blockDim.x + threadIdx.x);
+            EpaScratch* sc = reinterpret_cast<EpaScratch*>(epaSmem + (size_t)(threadIdx.x >> 5) * sizeof(EpaScratch));
             ok = epaPenetration(A, B, la, lb, sc, wA, wB, epaFail, poolOverflow);
             if (poolOverflow) epaFail = true;
         }

@@ -256,6 +256,27 @@ class GpuCollisionWorld:
             self._ck(self.L.b2c_get_manifolds(self.h, _vp(out), n.value, int(only_touching), C.byref(n)))
         return out
 
+    def pair_deltas(self):
+        """(added, removed) pairs of the last pair calculation as sorted (n,2) arrays — the events the reference's pair cache
+        sends to its ghost pair callback (bp/HashedOverlappingPairCache.java:135-137, 323-325)."""
+        na, nr = C.c_int32(), C.c_int32()
+        self._ck(self.L.b2c_get_pair_deltas(self.h, None, 0, None, 0, C.byref(na), C.byref(nr)))
+        a = np.zeros((na.value, 2), dtype=np.int32)
+        r = np.zeros((nr.value, 2), dtype=np.int32)
+        self._ck(self.L.b2c_get_pair_deltas(self.h, _vp(a) if na.value else None, na.value, _vp(r) if nr.value else None, nr.value,
+                                            C.byref(na), C.byref(nr)))
+        a = a[np.lexsort((a[:, 1], a[:, 0]))] if len(a) else a
+        r = r[np.lexsort((r[:, 1], r[:, 0]))] if len(r) else r
+        return a, r
+
+    def islands(self):
+        """Island tag per body (index = uid-1; -1 = static) and the island count
+        (disp/SimulationIslandManager.java:57-110)."""
+        t = np.zeros(max(self.num_bodies, 1), dtype=np.int32)
+        n = C.c_int32()
+        self._ck(self.L.b2c_compute_islands(self.h, _vp(t), self.num_bodies, C.byref(n)))
+        return t[: self.num_bodies], n.value
+
     def raw_contacts(self):
         n = C.c_int32()
         self._ck(self.L.b2c_get_raw_contacts(self.h, None, 0, C.byref(n)))

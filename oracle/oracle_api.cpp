@@ -4,6 +4,9 @@
 #include <chrono>
 #include <cstring>
 #include "world.h"
+#include "islands.h"
+#include <algorithm>
+#include <iterator>
 
 using namespace orc;
 
@@ -113,6 +116,26 @@ void orc_get_pairs(void* h, int* out) {
         out[2 * i] = w->pairs[i].first;
         out[2 * i + 1] = w->pairs[i].second;
     }
+}
+// Pairs added to / removed from the cache by the last calculateOverlappingPairs: what
+// bp/HashedOverlappingPairCache.java:323-325 (add) and :135-137 (remove) report to the ghost pair callback.
+// out arrays hold (uid0, uid1) rows, sorted; returns the counts through n2.
+void orc_pair_deltas(void* h, int* addedOut, int capA, int* removedOut, int capR, int* n2) {
+    World* w = (World*)h;
+    std::vector<std::pair<int, int>> added, removed;
+    std::set_difference(w->pairs.begin(), w->pairs.end(), w->prevPairs.begin(), w->prevPairs.end(), std::back_inserter(added));
+    std::set_difference(w->prevPairs.begin(), w->prevPairs.end(), w->pairs.begin(), w->pairs.end(), std::back_inserter(removed));
+    for (int i = 0; i < (int)added.size() && i < capA; i++) { addedOut[2 * i] = added[i].first; addedOut[2 * i + 1] = added[i].second; }
+    for (int i = 0; i < (int)removed.size() && i < capR; i++) { removedOut[2 * i] = removed[i].first; removedOut[2 * i + 1] = removed[i].second; }
+    n2[0] = (int)added.size();
+    n2[1] = (int)removed.size();
+}
+// disp/SimulationIslandManager.java:57-110 over the current pair list; tags[i] for object i (uid i+1), -1 = static.
+int orc_islands(void* h, int* tagsOut) {
+    World* w = (World*)h;
+    std::vector<char> merges(w->bodies.size());
+    for (size_t i = 0; i < w->bodies.size(); i++) merges[i] = (w->bodies[i].alive && !w->bodies[i].isStatic) ? 1 : 0;
+    return islandTags(w->pairs, merges, tagsOut);
 }
 int orc_dispatch_all_pairs(void* h) { return ((World*)h)->dispatchAllPairs(); }
 int orc_num_raw(void* h) { return (int)((World*)h)->raw.size(); }

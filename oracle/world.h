@@ -75,6 +75,7 @@ struct World {
     std::vector<Body> bodies;  // index = uid-1
     int step = 0;
     std::vector<std::pair<int, int>> pairs;  // sorted (uid0<uid1)
+    std::vector<std::pair<int, int>> prevPairs;  // the list before the last calculateOverlappingPairs (pair add/remove deltas)
     std::map<std::pair<int, int>, PairState> pairState;
     std::vector<RawContact> raw;
     LDbvtBroadphase literal;
@@ -220,6 +221,7 @@ struct World {
 
     // BroadphaseInterface.calculateOverlappingPairs: resulting pair set
     int calculateOverlappingPairs() {
+        prevPairs = pairs;
         if (mode == BP_DBVT_LITERAL) {
             literal.collide();
             pairs.clear();

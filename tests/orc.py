@@ -55,6 +55,8 @@ def lib():
     L.orc_calculate_overlapping_pairs.argtypes = [C.c_void_p]
     L.orc_get_pairs.argtypes = [C.c_void_p, i32p]
     L.orc_dispatch_all_pairs.argtypes = [C.c_void_p]
+    L.orc_pair_deltas.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, i32p]
+    L.orc_islands.argtypes = [C.c_void_p, i32p]
     L.orc_num_raw.argtypes = [C.c_void_p]
     L.orc_get_raw.argtypes = [C.c_void_p, i32p, f32p]
     L.orc_get_manifolds.argtypes = [C.c_void_p, C.c_int, i32p, f32p, i32p]
@@ -164,6 +166,20 @@ class OracleWorld:
         if n:
             self.L.orc_get_pairs(self.h, out)
         return out
+
+    def pair_deltas(self, cap=1 << 22):
+        """(added, removed) pair lists of the last calculate_overlapping_pairs, each sorted (n,2)."""
+        a = np.zeros((cap, 2), dtype=np.int32)
+        r = np.zeros((cap, 2), dtype=np.int32)
+        n2 = np.zeros(2, dtype=np.int32)
+        self.L.orc_pair_deltas(self.h, a, cap, r, cap, n2)
+        return a[: n2[0]].copy(), r[: n2[1]].copy()
+
+    def islands(self):
+        """Island tag per object (index = uid-1), -1 for statics; and the number of islands."""
+        t = np.zeros(max(self.num_bodies, 1), dtype=np.int32)
+        n = self.L.orc_islands(self.h, t)
+        return t[: self.num_bodies], n
 
     def dispatch_all_pairs(self):
         return self.L.orc_dispatch_all_pairs(self.h)

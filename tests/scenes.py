@@ -196,7 +196,7 @@ def heightfield(cells, cell=0.5, amp=3.0, seed=3):
     return verts, tris.astype(np.int32), h.astype(np.float32)
 
 
-def terrain_scene(cells=64, n=200, seed=4, cell=0.5):
+def terrain_scene(cells=64, n=200, seed=4, cell=0.5, mix=(0.45, 0.45, 0.10)):
     """C3: hulls and spheres resting on a BVH triangle-mesh heightfield."""
     rng = np.random.default_rng(SEED + seed)
     sc = Scene()
@@ -211,7 +211,7 @@ def terrain_scene(cells=64, n=200, seed=4, cell=0.5):
     xz = rng.uniform(1.0, size - 1.0, size=(n, 2))
     gi = np.clip((xz / cell).astype(int), 0, cells - 1)
     ground = h[gi[:, 0], gi[:, 1]]
-    kind = rng.choice(3, size=n, p=[0.45, 0.45, 0.10])
+    kind = rng.choice(3, size=n, p=list(mix))   # hull / sphere / box shares
     y = ground + np.where(kind == 1, 0.4, 0.45) + rng.uniform(-0.05, 0.25, size=n)
     pos = np.stack([xz[:, 0], y, xz[:, 1]], axis=1)
     for k in range(n):

@@ -1,0 +1,62 @@
+"""-m gpu: the two consumers right behind the pair list against the CPU oracle:
+pair add/remove deltas (ghost pair callback events) and simulation islands (union-find partition)."""
+import numpy as np
+import pytest
+
+import parity
+import scenes
+from test_oracle_islands import canon_partition
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(gw, ow, sc, steps, active_fn=None):
+    seen_added = seen_removed = 0
+    for step in range(steps):
+        parity.step_and_compare(gw, ow, sc.transforms(step), sc.extent)
+        ga, gr = gw.pair_deltas()
+        oa, orm = ow.pair_deltas()
+        assert np.array_equal(ga, oa), f"added pairs differ at step {step}: gpu {len(ga)} oracle {len(oa)}"
+        assert np.array_equal(gr, orm), f"removed pairs differ at step {step}: gpu {len(gr)} oracle {len(orm)}"
+        seen_added += len(ga)
+        seen_removed += len(gr)
+        gt, gn = gw.islands()
+        ot, on = ow.islands()
+        assert gn == on, f"island count differs at step {step}: {gn} vs {on}"
+        assert np.array_equal(gt, canon_partition(ot)), f"island partition differs at step {step}"
+        assert np.array_equal(gt, canon_partition(gt)), "device tags are not the smallest member index"
+    return seen_added, seen_removed
+
+
+def test_deltas_and_islands_bin(gpu_pkg):
+    sc = scenes.bin_scene(n=3000, seed=21)
+    sc.vel *= 3.0
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    a, r = _check(gw, ow, sc, 6)
+    assert a > 3000 and r > 0   # step 0 adds everything; later steps must both add and remove
+
+
+def test_deltas_and_islands_tight_mode_stack(gpu_pkg):
+    sc = scenes.stack_scene(n_side=4, extra=True, seed=5)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=0)
+    _check(gw, ow, sc, 5)
+
+
+def test_islands_batched_worlds(gpu_pkg):
+    sc = scenes.worlds_scene(num_worlds=48, seed=3)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    _check(gw, ow, sc, 3)
+    gt, gn = gw.islands()
+    world = np.asarray(sc.world)
+    dyn = gt >= 0
+    # an island never spans two worlds
+    assert np.array_equal(world[dyn], world[gt[dyn]])
+    assert gn >= sc.num_worlds
+
+
+def test_islands_sparse_spheres_many_islands(gpu_pkg):
+    sc = scenes.spheres_scene(n=6000, seed=2, fill=0.12)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=0)
+    _check(gw, ow, sc, 2)
+    _, gn = gw.islands()
+    assert gn > 100
