@@ -40,6 +40,8 @@ struct b2c_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     // side streams of the narrowphase (forked from / joined to `stream` with events inside one step):
+    cudaStream_t streamCopy = nullptr;    // D2H of the pair list while the narrowphase is still running on `stream`
+    cudaEvent_t evPairsReady = nullptr;   // recorded on `stream` when the broadphase of the current step is enqueued
     cudaStream_t streamClosed = nullptr;  // sphere-sphere / convex-plane bins, beside the GJK kernels
     cudaStream_t streamEpa = nullptr;     // penetration bin (few long-latency lanes), beside k_manifold_cc; high priority
     cudaEvent_t evFork[2] = {nullptr, nullptr}, evJoin[2] = {nullptr, nullptr};
@@ -107,10 +109,13 @@ struct b2c_ctx {
     // narrowphase
     b2c_raw_contact* dRaw = nullptr;
     int8_t* dRawFlag = nullptr;
-    uint32_t* dBinKeys[2] = {nullptr, nullptr};
+    uint8_t* dBinOf = nullptr;
+    uint32_t* dBinItems = nullptr;
+    uint32_t* dBinStart = nullptr;   // [17]
+    uint32_t* dBinZero = nullptr;    // hist[16] | ticket | pad | status[binTiles][16]
+    uint32_t binTiles = 0;
     uint32_t* dCursors = nullptr;
     uint32_t* dSurvivors = nullptr;
-    RadixSorter sortBins;
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
     uint32_t* dEpaRetry = nullptr;
@@ -288,6 +293,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     if (n == 0) {
         CK(cudaMemsetAsync(ctx->dNumPairs[cur], 0, sizeof(uint32_t), s));
+        CK(cudaEventRecord(ctx->evPairsReady, s));
         ctx->step++;
         ctx->pairsValid = true;
         return B2C_OK;
@@ -341,6 +347,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
                                                                       ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr);
     ctx->launches += 10 + ctx->sortBodies.launches;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->evPairsReady, s));
     ctx->step++;
     ctx->pairsValid = true;
     return B2C_OK;
@@ -365,10 +372,10 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.mpts = ctx->dMPts[ctx->cur];
     a.raw = ctx->dRaw;
     a.rawFlag = ctx->dRawFlag;
-    a.binKeys[0] = ctx->dBinKeys[0];
-    a.binKeys[1] = ctx->dBinKeys[1];
-    a.binSide = ctx->dSide + 2;
-    a.binStart = &ctx->sortBins.st->hist[3][0];
+    a.binOf = ctx->dBinOf;
+    a.binItems = ctx->dBinItems;
+    a.binStart = ctx->dBinStart;
+    a.binZero = ctx->dBinZero;
     a.ctr = ctx->dCtr;
     a.threshold = ctx->cfg.contact_breaking_threshold;
     a.maxPairs = (uint32_t)ctx->cfg.max_pairs;
@@ -396,12 +403,14 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     const unsigned pg = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
     mark(ctx, 8);
     k_clear_np_counters<<<1, 32, 0, s>>>(ctx->dCtr);
+    CK(cudaMemsetAsync(ctx->dBinZero, 0, (32 + (size_t)ctx->binTiles * 16) * sizeof(uint32_t), s));
     k_classify<<<pg, 256, 0, s>>>(a);
-    // stable partition of the pair indices by bin: one radix pass over the bin digit (bits 24-31)
-    ctx->sortBins.launches = 0;
-    ctx->sortBins.sort<uint32_t, false>(ctx->dBinKeys[0], ctx->dBinKeys[1], nullptr, nullptr, ctx->dNumPairs[ctx->cur], 0, 32,
-                                        ctx->dSide + 2, s, 3);
-    ctx->launches += ctx->sortBins.launches - 2;
+    // stable partition of the pair indices by bin, one pass (k_bin_scatter)
+    {
+        unsigned bg = ctx->binTiles < 148u * 4u ? ctx->binTiles : 148u * 4u;
+        k_bin_scatter<<<bg ? bg : 1, 256, 0, s>>>(a);
+    }
+    ctx->launches += 1;
     mark(ctx, 9);
     // the closed-form bins touch only their own pairs' records: they run beside the GJK kernels
     cudaStream_t sc = s;
@@ -571,6 +580,8 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     {
         int prLo = 0, prHi = 0;
         CKC(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+        CKC(cudaStreamCreateWithFlags(&ctx->streamCopy, cudaStreamNonBlocking));
+        CKC(cudaEventCreateWithFlags(&ctx->evPairsReady, cudaEventDisableTiming));
         CKC(cudaStreamCreateWithPriority(&ctx->streamClosed, cudaStreamNonBlocking, prLo));
         CKC(cudaStreamCreateWithPriority(&ctx->streamEpa, cudaStreamNonBlocking, prHi));
         for (int i = 0; i < 2; i++) {
@@ -635,9 +646,11 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dRaw, P));
     CKC(dalloc(&ctx->dRawFlag, P));
     if (P > (size_t)(1u << 24)) return fail(B2C_ERR_BAD_ARG);  // pair index must fit 24 bits next to the bin byte
-    CKC(dalloc(&ctx->dBinKeys[0], P));
-    CKC(dalloc(&ctx->dBinKeys[1], P));
-    CKC(ctx->sortBins.init((uint32_t)P));
+    CKC(dalloc(&ctx->dBinOf, P));
+    CKC(dalloc(&ctx->dBinItems, P));
+    CKC(dalloc(&ctx->dBinStart, (size_t)32));
+    ctx->binTiles = (uint32_t)((P + BIN_TILE - 1) / BIN_TILE);
+    CKC(dalloc(&ctx->dBinZero, 32 + (size_t)ctx->binTiles * 16));
     CKC(dalloc(&ctx->dCursors, (size_t)4));
     CKC(dalloc(&ctx->dExportCount, (size_t)1));
     CKC(dalloc(&ctx->dSurvivors, P));
@@ -681,7 +694,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
     cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dRowZero); cudaFree(ctx->dBigRows);
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinKeys[0]); cudaFree(ctx->dBinKeys[1]); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); ctx->sortBins.destroy();
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dBinZero); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors);
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -692,6 +705,8 @@ void b2c_destroy(b2c_ctx* ctx) {
         if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
         if (ctx->evJoin[i]) cudaEventDestroy(ctx->evJoin[i]);
     }
+    if (ctx->streamCopy) { cudaStreamSynchronize(ctx->streamCopy); cudaStreamDestroy(ctx->streamCopy); }
+    if (ctx->evPairsReady) cudaEventDestroy(ctx->evPairsReady);
     if (ctx->streamClosed) cudaStreamDestroy(ctx->streamClosed);
     if (ctx->streamEpa) cudaStreamDestroy(ctx->streamEpa);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1041,15 +1056,19 @@ int32_t b2c_get_pairs(b2c_ctx* ctx, int32_t* out, int32_t cap, int32_t* numOut) 
     if (!ctx) return B2C_ERR_BAD_ARG;
     if (!ctx->pairsValid) return B2C_ERR_STATE;
     cudaSetDevice(ctx->device);
+    // The pair list is final once the broadphase has run: copy it on a second stream that only waits for that point,
+    // so after b2c_step_device the download overlaps the narrowphase still running on the ctx stream.
+    cudaStream_t cs = ctx->streamCopy;
+    CK(cudaStreamWaitEvent(cs, ctx->evPairsReady, 0));
     uint32_t n = 0;
-    CK(cudaMemcpyAsync(&n, ctx->dNumPairs[ctx->cur], sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(&n, ctx->dNumPairs[ctx->cur], sizeof(n), cudaMemcpyDeviceToHost, cs));
+    CK(cudaStreamSynchronize(cs));
     if (numOut) *numOut = (int32_t)n;
     if (!out) return B2C_OK;
     if ((uint32_t)cap < n) { ctx->err = "pair output buffer too small"; return B2C_ERR_CAPACITY; }
     if (n) {
-        CK(cudaMemcpyAsync(out, ctx->dPairs, (size_t)n * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyAsync(out, ctx->dPairs, (size_t)n * sizeof(int2), cudaMemcpyDeviceToHost, cs));
+        CK(cudaStreamSynchronize(cs));
     }
     return B2C_OK;
 }
@@ -1170,8 +1189,10 @@ int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, in
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<b2c_raw_contact> raw(n);
     std::vector<uint32_t> ms(n), mc(n);
+    std::vector<uint8_t> binOf(n);
     if (n) {
         CK(cudaMemcpyAsync(raw.data(), ctx->dRaw, (size_t)n * sizeof(b2c_raw_contact), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(binOf.data(), ctx->dBinOf, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->hasMesh) {
             CK(cudaMemcpyAsync(ms.data(), ctx->dMeshStart, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(mc.data(), ctx->dMeshCount, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1191,7 +1212,7 @@ int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, in
     }
     int32_t k = 0;
     for (uint32_t p = 0; p < n; p++) {
-        if (raw[p].has_contact == -1) continue;  // not dispatched
+        if (binOf[p] == BIN_SKIP) continue;  // not dispatched (both bodies inactive, or no algorithm for the type pair)
         if (raw[p].has_contact == -3) {
             for (uint32_t q = ms[p]; q < ms[p] + mc[p] && q < nItems; q++) {
                 if (out && k < cap) out[k] = rawMesh[q];

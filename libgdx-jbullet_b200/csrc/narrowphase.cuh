@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "epa.cuh"
 #include "gjk.cuh"
+#include "radix_sort.cuh"
 
 namespace b2c {
 
@@ -47,9 +48,10 @@ struct NpArgs {
     b2c_manifold_point* mpts;     // [4*maxPairs] this step: the 4 point slots of each manifold
     b2c_raw_contact* raw;         // [maxPairs]
     int8_t* rawFlag;              // [maxPairs] copy of raw[p].has_contact for the kernels that only need the flag
-    uint32_t* binKeys[2];         // [maxPairs] (bin << 24) | pairIndex, stably partitioned by bin (radix pass)
-    const uint32_t* binSide;      // which of binKeys holds the partitioned list
-    const uint32_t* binStart;     // exclusive bin offsets (the partition's digit histogram); [b+1] = end of bin b
+    uint8_t* binOf;               // [maxPairs] bin of every pair (k_classify)
+    uint32_t* binItems;           // [maxPairs] pair indices, stably partitioned by bin (k_bin_scatter)
+    uint32_t* binStart;           // [17] exclusive bin offsets; [b+1] = end of bin b
+    uint32_t* binZero;            // cleared per dispatch: hist[16] | ticket | pad[15] | status[tiles][16]
     StepCounters* ctr;
     float threshold;
     uint32_t maxPairs;
@@ -324,6 +326,9 @@ __device__ __forceinline__ bool isConvexType(int t) { return t == SH_BOX || t ==
 
 __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
     const uint32_t n = *a.numPairs;
+    __shared__ uint32_t hist[16];
+    if (threadIdx.x < 16) hist[threadIdx.x] = 0;
+    __syncthreads();
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
@@ -337,13 +342,115 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
             else if (isConvexType(t0) && isConvexType(t1)) bin = BIN_GJK0 + t0 * 3 + t1;
             else if ((isConvexType(t0) && t1 == SH_MESH) || (isConvexType(t1) && t0 == SH_MESH)) bin = BIN_MESH;
         }
-        a.binKeys[0][p] = ((uint32_t)bin << 24) | p;
-        a.raw[p].has_contact = -1;  // not processed
+        a.binOf[p] = (uint8_t)bin;  // BIN_SKIP pairs are not dispatched: their raw record is not written this step
+        // per-block histogram: one shared-memory atomic per group of lanes with the same bin
+        uint32_t m = __match_any_sync(__activemask(), bin);
+        if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(m));
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && hist[threadIdx.x]) atomicAdd(&a.binZero[threadIdx.x], hist[threadIdx.x]);
+}
+
+// k_bin_scatter: stable partition of the pair indices by bin in ONE pass: tiles are taken in ticket order, every tile
+// ranks its pairs per bin (match-any inside a warp, exclusive scan over the warps), publishes its 16 counts and resolves
+// its offsets by decoupled look-back over the preceding tiles (the scheme of radix_sort.cuh with a 4-bit digit).
+constexpr int BIN_ITEMS = 8, BIN_TILE = 256 * BIN_ITEMS, BIN_LOOKBACK = 8;
+__global__ void __launch_bounds__(256) k_bin_scatter(NpArgs a) {
+    const uint32_t n = *a.numPairs;
+    const uint32_t numTiles = (n + BIN_TILE - 1) / BIN_TILE;
+    const uint32_t* hist = a.binZero;
+    uint32_t* ticket = a.binZero + 16;
+    uint32_t* status = a.binZero + 32;
+    __shared__ uint32_t warpCnt[8][16];
+    __shared__ uint32_t base[16];
+    __shared__ uint32_t sTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltmask = (1u << lane) - 1u;
+    uint32_t myStart = 0;  // threads 0..15: exclusive offset of bin threadIdx.x
+    if (threadIdx.x < 16)
+        for (int j = 0; j < (int)threadIdx.x; j++) myStart += hist[j];
+    if (blockIdx.x == 0 && threadIdx.x <= 16) {
+        uint32_t e = 0;
+        for (int j = 0; j < (int)threadIdx.x; j++) e += hist[j];
+        a.binStart[threadIdx.x] = e;
+    }
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+        if (threadIdx.x < 128) (&warpCnt[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if (tile >= numTiles) return;
+        const uint32_t tileStart = tile * BIN_TILE + warp * (BIN_ITEMS * 32) + lane;
+        uint32_t bin[BIN_ITEMS], rank[BIN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < BIN_ITEMS; k++) {
+            uint32_t idx = tileStart + k * 32;
+            bin[k] = idx < n ? (uint32_t)a.binOf[idx] : 0x100u + lane;
+        }
+#pragma unroll
+        for (int k = 0; k < BIN_ITEMS; k++) {
+            const bool valid = bin[k] < 16u;
+            uint32_t m = __match_any_sync(0xffffffffu, bin[k]);
+            uint32_t lower = __popc(m & ltmask);
+            uint32_t pre = 0;
+            if (valid && lower == 0) {
+                pre = warpCnt[warp][bin[k]];
+                warpCnt[warp][bin[k]] = pre + __popc(m);
+            }
+            __syncwarp();
+            pre = __shfl_sync(0xffffffffu, pre, __ffs(m) - 1);
+            rank[k] = pre + lower;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            const int d = threadIdx.x;
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                uint32_t c = warpCnt[w][d];
+                warpCnt[w][d] = run;
+                run += c;
+            }
+            uint32_t* my = status + (size_t)tile * 16 + d;
+            uint32_t excl = 0;
+            if (tile == 0) {
+                rs_store_release(my, run | RS_FLAG_INC);
+            } else {
+                rs_store_release(my, run | RS_FLAG_AGG);
+                int t = (int)tile - 1;
+                bool done = false;
+                while (!done && t >= 0) {
+                    uint32_t sv[BIN_LOOKBACK];
+#pragma unroll
+                    for (int k = 0; k < BIN_LOOKBACK; k++)
+                        sv[k] = (t - k >= 0) ? rs_load_relaxed(status + (size_t)(t - k) * 16 + d) : RS_FLAG_INC;
+                    int used = 0;
+#pragma unroll
+                    for (int k = 0; k < BIN_LOOKBACK; k++) {
+                        if (!done && used == k) {
+                            uint32_t f = sv[k] & ~RS_VAL_MASK;
+                            if (f != 0) {
+                                excl += sv[k] & RS_VAL_MASK;
+                                used = k + 1;
+                                if (f == RS_FLAG_INC) done = true;
+                            }
+                        }
+                    }
+                    t -= used;
+                }
+                rs_store_release(my, (excl + run) | RS_FLAG_INC);
+            }
+            base[d] = myStart + excl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BIN_ITEMS; k++) {
+            if (bin[k] < 16u) a.binItems[base[bin[k]] + warpCnt[warp][bin[k]] + rank[k]] = tileStart + k * 32;
+        }
     }
 }
-__device__ __forceinline__ uint32_t binItem(const NpArgs& a, uint32_t it) {
-    return (*a.binSide ? a.binKeys[1] : a.binKeys[0])[it] & 0xFFFFFFu;
-}
+__device__ __forceinline__ uint32_t binItem(const NpArgs& a, uint32_t it) { return a.binItems[it]; }
 
 __device__ __forceinline__ void writeRaw(b2c_raw_contact* r, int2 pr, int tri, int has, f3 n, f3 pt, float depth, int method,
                                          int iters) {
