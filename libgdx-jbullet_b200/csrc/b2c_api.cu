@@ -337,8 +337,11 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     k_row_scan<<<ctx->rowTiles, 256, 0, s>>>(rowCnt, ctx->nRows, rowStart, rowStatus, rowMisc, ctx->dBigRows, ctx->dNumPairs[cur]);
     k_row_scatter<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys, ctx->dCtr, (uint32_t)ctx->cfg.max_pairs,
                                                                              ctx->uidBits, rowStart, ctx->dCsr);
-    k_row_sort<<<gridFor(ctx->nRows, 256), 256, 0, s>>>(rowStart, ctx->nRows, ctx->dCsr, ctx->uidBits, ctx->dPairs, ctx->dSortedKeys[cur]);
-    k_row_sort_big<<<148 * 4, 256, 0, s>>>(rowStart, ctx->dBigRows, rowMisc, ctx->dCsr, ctx->uidBits, ctx->dPairs, ctx->dSortedKeys[cur]);
+    k_row_rank<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys, ctx->dCtr, (uint32_t)ctx->cfg.max_pairs,
+                                                                          ctx->uidBits, rowStart, ctx->dCsr, ctx->dPairs,
+                                                                          ctx->dSortedKeys[cur]);
+    k_row_sort_big<<<148, BIG_THREADS, 0, s>>>(rowStart, ctx->dBigRows, rowMisc, ctx->dCsr, ctx->uidBits, ctx->dPairs,
+                                               ctx->dSortedKeys[cur]);
     mark(ctx, 7);
     // manifolds follow their pair into the new list (done here so a step without dispatch keeps them too)
     k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
@@ -627,7 +630,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dCsr, P));
     ctx->nRows = (uint32_t)N + 2u;
     ctx->rowTiles = (ctx->nRows + RSCAN_TILE - 1) / RSCAN_TILE;
-    CKC(dalloc(&ctx->dRowZero, (size_t)ctx->nRows + ctx->rowTiles + sizeof(RowMisc) / sizeof(uint32_t)));
+    CKC(dalloc(&ctx->dRowZero, (size_t)ctx->nRows + ctx->rowTiles + sizeof(RowMisc) / sizeof(uint32_t) + 8));
     CKC(dalloc(&ctx->dBigRows, (size_t)ctx->nRows));
     CKC(dalloc(&ctx->dSide, (size_t)4));
     CKC(dalloc(&ctx->dSmin, N));

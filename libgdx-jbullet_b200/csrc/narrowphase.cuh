@@ -222,16 +222,17 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
         }
         uint32_t cm = __ballot_sync(0xffffffffu, carriedManifold);
         if (lane == 0 && cm) atomicAdd(&ctr->numManifolds, (uint32_t)__popc(cm));
-        // live points: the warp copies them with 16-byte accesses (6 int4 per point)
-        uint32_t m = __ballot_sync(0xffffffffu, nc > 0);
-        while (m) {
-            int q = __ffs(m) - 1;
-            m &= m - 1;
-            int fq = __shfl_sync(0xffffffffu, found, q);
-            int nq = __shfl_sync(0xffffffffu, nc, q);
-            const int4* src = reinterpret_cast<const int4*>(prevP + 4 * (size_t)fq);
-            int4* dst = reinterpret_cast<int4*>(P + 4 * (size_t)(base + q));
-            if (lane < 6 * nq) dst[lane] = src[lane];
+        // live points: every lane copies its own manifold's points (96-byte records = 6 x int4, all loads of a point
+        // in flight before its stores), so the lanes of a warp work in parallel instead of taking turns
+        if (nc > 0) {
+            const int4* src = reinterpret_cast<const int4*>(prevP + 4 * (size_t)found);
+            int4* dst = reinterpret_cast<int4*>(P + 4 * (size_t)p);
+            for (int q = 0; q < nc; q++) {
+                int4 v0 = src[6 * q], v1 = src[6 * q + 1], v2 = src[6 * q + 2], v3 = src[6 * q + 3], v4 = src[6 * q + 4],
+                     v5 = src[6 * q + 5];
+                dst[6 * q] = v0; dst[6 * q + 1] = v1; dst[6 * q + 2] = v2; dst[6 * q + 3] = v3; dst[6 * q + 4] = v4;
+                dst[6 * q + 5] = v5;
+            }
         }
     }
 }

@@ -8,7 +8,7 @@
 //   k_row_scan     exclusive scan of rowCnt -> rowStart (single pass, decoupled look-back); rows longer than
 //                  ROW_SMALL go on the big-row list; rowStart doubles as next step's "first pair of uid0" table
 //   k_row_scatter  uid1 of every emitted pair -> csr[rowStart[uid0] + slot]
-//   k_row_sort     one thread per short row: insertion sort of <= ROW_SMALL uid1 values, writes (uid0,uid1) + key
+//   k_row_rank     one thread per pair of a short row (<= ROW_SMALL): its place is the count of smaller uid1 in the row
 //   k_row_sort_big one block per long row (large statics, meshes): the row is a SET of uids, so it is sorted by
 //                  setting bits in a shared-memory bitmap over [min uid1, max uid1] and enumerating them in order
 // All of it is integer/byte work bound by L2/HBM traffic: ~8 P read + 4 P write + 4 P read + 16 P write bytes.
@@ -17,8 +17,8 @@
 
 namespace b2c {
 
-constexpr int ROW_SMALL = 32;
-constexpr int RSCAN_TILE = 1024;           // 256 threads x 4 rows
+constexpr int ROW_SMALL = 48;
+constexpr int RSCAN_PER = 16, RSCAN_TILE = 256 * RSCAN_PER;  // rows per thread, rows per tile
 constexpr uint32_t RS2_AGG = 1u << 30, RS2_INC = 2u << 30, RS2_VAL = (1u << 30) - 1u;
 constexpr int BIG_WORDS = 8192;            // shared-memory bitmap of k_row_sort_big: 262 144 uids per chunk
 
@@ -44,11 +44,16 @@ k_row_scan(const uint32_t* __restrict__ rowCnt, uint32_t nRows, uint32_t* __rest
     if (threadIdx.x == 0) sTile = atomicAdd(&misc->ticket, 1u);
     __syncthreads();
     const uint32_t tile = sTile;
-    const uint32_t base = tile * RSCAN_TILE + threadIdx.x * 4;
-    uint32_t c[4];
+    const uint32_t base = tile * RSCAN_TILE + threadIdx.x * RSCAN_PER;
+    uint32_t c[RSCAN_PER];
+    uint32_t sum = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) c[k] = (base + k < nRows) ? rowCnt[base + k] : 0u;
-    const uint32_t sum = c[0] + c[1] + c[2] + c[3];
+    for (int k = 0; k < RSCAN_PER; k += 4) {  // rowCnt is 16-byte aligned and padded to a multiple of 4
+        uint4 v = (base + k < nRows) ? *reinterpret_cast<const uint4*>(rowCnt + base + k) : make_uint4(0, 0, 0, 0);
+        c[k] = v.x; c[k + 1] = (base + k + 1 < nRows) ? v.y : 0u; c[k + 2] = (base + k + 2 < nRows) ? v.z : 0u;
+        c[k + 3] = (base + k + 3 < nRows) ? v.w : 0u;
+        sum += c[k] + c[k + 1] + c[k + 2] + c[k + 3];
+    }
     uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -100,7 +105,7 @@ k_row_scan(const uint32_t* __restrict__ rowCnt, uint32_t nRows, uint32_t* __rest
     __syncthreads();
     uint32_t run = sExcl + warpSum[warp] + (incl - sum);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < RSCAN_PER; k++) {
         if (base + k < nRows) {
             rowStart[base + k] = run;
             if (c[k] > (uint32_t)ROW_SMALL) bigRows[atomicAdd(&misc->bigCount, 1u)] = base + k;
@@ -122,32 +127,33 @@ k_row_scatter(const uint64_t* __restrict__ pairKeys, const StepCounters* __restr
     }
 }
 
+// One thread per EMITTED pair: its place inside its (short) row is the number of row members smaller than its uid1 —
+// the row is a set, so ranks are distinct.  O(row length) independent L1-resident loads per pair, no local arrays.
 __global__ void __launch_bounds__(256)
-k_row_sort(const uint32_t* __restrict__ rowStart, uint32_t nRows, const uint32_t* __restrict__ csr, int uidBits,
-           int2* __restrict__ pairs, uint64_t* __restrict__ sortedKeys) {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nRows; r += gridDim.x * blockDim.x) {
-        const uint32_t s = rowStart[r], cnt = rowStart[r + 1] - s;
-        if (cnt == 0 || cnt > (uint32_t)ROW_SMALL) continue;
-        uint32_t v[ROW_SMALL];
-        for (uint32_t k = 0; k < cnt; k++) {  // insertion sort while loading
-            uint32_t x = csr[s + k];
-            int j = (int)k - 1;
-            while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; j--; }
-            v[j + 1] = x;
-        }
-        for (uint32_t k = 0; k < cnt; k++) {
-            pairs[s + k] = make_int2((int)r, (int)v[k]);
-            sortedKeys[s + k] = ((uint64_t)r << uidBits) | v[k];
-        }
+k_row_rank(const uint64_t* __restrict__ pairKeys, const StepCounters* __restrict__ ctr, uint32_t maxPairs, int uidBits,
+           const uint32_t* __restrict__ rowStart, const uint32_t* __restrict__ csr, int2* __restrict__ pairs,
+           uint64_t* __restrict__ sortedKeys) {
+    const uint32_t n = ctr->pairCount < maxPairs ? ctr->pairCount : maxPairs;
+    const uint64_t mask = (1ull << uidBits) - 1ull;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint64_t k = pairKeys[p];
+        const uint32_t hi = (uint32_t)(k & mask), lo = (uint32_t)((k >> uidBits) & mask);
+        const uint32_t s = rowStart[lo], cnt = rowStart[lo + 1] - s;
+        if (cnt > (uint32_t)ROW_SMALL) continue;  // long rows: k_row_sort_big
+        uint32_t pos = 0;
+        for (uint32_t e = 0; e < cnt; e++) pos += (__ldg(csr + s + e) < hi) ? 1u : 0u;
+        pairs[s + pos] = make_int2((int)lo, (int)hi);
+        sortedKeys[s + pos] = ((uint64_t)lo << uidBits) | hi;
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int BIG_THREADS = 1024;
+__global__ void __launch_bounds__(BIG_THREADS)
 k_row_sort_big(const uint32_t* __restrict__ rowStart, const uint32_t* __restrict__ bigRows, const RowMisc* __restrict__ misc,
                const uint32_t* __restrict__ csr, int uidBits, int2* __restrict__ pairs, uint64_t* __restrict__ sortedKeys) {
     __shared__ uint32_t bm[BIG_WORDS];
-    __shared__ uint32_t red[2][8];
-    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t red[2][32];
+    __shared__ uint32_t wsum[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nBig = misc->bigCount;
     for (uint32_t b = blockIdx.x; b < nBig; b += gridDim.x) {
@@ -165,7 +171,7 @@ k_row_sort_big(const uint32_t* __restrict__ rowStart, const uint32_t* __restrict
         __syncthreads();  // previous row's use of red/bm is over
         if (lane == 0) { red[0][warp] = mn; red[1][warp] = mx; }
         __syncthreads();
-        for (int w = 0; w < 8; w++) { mn = min(mn, red[0][w]); mx = max(mx, red[1][w]); }
+        for (int w = 0; w < BIG_THREADS / 32; w++) { mn = min(mn, red[0][w]); mx = max(mx, red[1][w]); }
         uint32_t outBase = s;
         for (uint32_t c0 = mn; c0 <= mx; c0 += (uint32_t)BIG_WORDS * 32u) {
             const uint32_t span = min(mx - c0 + 1u, (uint32_t)BIG_WORDS * 32u);
@@ -189,7 +195,7 @@ k_row_sort_big(const uint32_t* __restrict__ rowStart, const uint32_t* __restrict
             if (lane == 31) wsum[warp] = incl;
             __syncthreads();
             uint32_t before = 0, total = 0;
-            for (int w = 0; w < 8; w++) { if (w < warp) before += wsum[w]; total += wsum[w]; }
+            for (int w = 0; w < BIG_THREADS / 32; w++) { if (w < warp) before += wsum[w]; total += wsum[w]; }
             uint32_t pos = outBase + before + (incl - mine);
             for (uint32_t w = w0; w < w1; w++) {
                 uint32_t bits = bm[w];
