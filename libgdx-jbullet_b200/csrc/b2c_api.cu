@@ -46,6 +46,7 @@ struct b2c_ctx {
     cudaStream_t streamEpa = nullptr;     // penetration bin (few long-latency lanes), beside k_manifold_cc; high priority
     cudaEvent_t evFork[2] = {nullptr, nullptr}, evJoin[2] = {nullptr, nullptr};
     bool overlap = true;
+    int epaLpw = 8;                       // active lanes per warp in the shared-memory EPA tier (B2C_EPA_LPW: 32/16/8/4)
     int epaHint = -1;                     // -1 unknown, 0 small penetration bin (shared-memory tier), 1 large (local-memory tier)
     bool timeline = false;                // B2C_TIMELINE=1: print where the side-stream kernels ran (debug)
     cudaEvent_t tl[6] = {};
@@ -456,14 +457,14 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         // which variant: the host knows the size of the previous step's bin (when it has read the counters); the kernels
         // handle any count either way, so a stale hint only costs time.  Without a hint both are launched and the device decides.
         const int hint = ctx->epaHint;
-        if (hint <= 0) { k_epa<0><<<EPA_GRID, EPA_BLOCK, smem, se>>>(a, g, hint < 0 ? 0 : 1); ctx->launches++; }
+        if (hint <= 0) { k_epa<0><<<EPA_GRID, 32 * (32 / ctx->epaLpw), smem, se>>>(a, g, hint < 0 ? 0 : 1, ctx->epaLpw); ctx->launches++; }
         if (ctx->timeline) cudaEventRecord(ctx->tl[1], se);
-        if (hint != 0) { k_epa<2><<<EPA_GRID3, EPA_BLOCK3, 0, se>>>(a, g, hint < 0 ? 0 : 1); ctx->launches++; }
+        if (hint != 0) { k_epa<2><<<EPA_GRID3, EPA_BLOCK3, 0, se>>>(a, g, hint < 0 ? 0 : 1, 32); ctx->launches++; }
     }
     {
         const int smem1 = (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch);
         cudaFuncSetAttribute(k_epa<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-        k_epa<1><<<EPA_GRID2, EPA_BLOCK2, smem1, se>>>(a, g, 0);  // retry tier + the manifolds of the whole bin
+        k_epa<1><<<EPA_GRID2, EPA_BLOCK2, smem1, se>>>(a, g, 0, 32);  // retry tier + the manifolds of the whole bin
     }
     if (ctx->timeline) cudaEventRecord(ctx->tl[2], se);
     if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[1], se));
@@ -593,13 +594,15 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         }
         const char* e = getenv("B2C_OVERLAP");  // measurement knob: 0 = everything on one stream
         ctx->overlap = !(e && e[0] == '0');
+        const char* l = getenv("B2C_EPA_LPW");
+        if (l) { int v = atoi(l); if (v == 32 || v == 16 || v == 8 || v == 4) ctx->epaLpw = v; }
         const char* t = getenv("B2C_TIMELINE");
         ctx->timeline = t && t[0] == '1';
         for (int i = 0; i < 6; i++) CKC(cudaEventCreate(&ctx->tl[i]));
     }
     const size_t N = (size_t)cfg->max_bodies, P = (size_t)cfg->max_pairs;
     CKC(dalloc(&ctx->dShapes, (size_t)cfg->max_shapes));
-    CKC(dalloc(&ctx->dHullPts, (size_t)(cfg->max_hull_points > 0 ? cfg->max_hull_points : 1)));
+    CKC(dalloc(&ctx->dHullPts, (size_t)(cfg->max_hull_points > 0 ? cfg->max_hull_points : 1) + 4));  // + 4: HullS::support reads in fours
     CKC(dalloc(&ctx->dMeshes, (size_t)cfg->max_shapes));
     CKC(dalloc(&ctx->B.xf4, 3 * N));
     CKC(dalloc(&ctx->B.shape, N));

@@ -48,20 +48,39 @@ struct HullS {  // sh/ConvexHullShape.java:75-102,142-157; points are pre-multip
     const float4* __restrict__ pts;
     int n;
     float margin;
-    __device__ __forceinline__ f3 support(f3 v0) const {
+    template <bool WIDE>
+    __device__ __forceinline__ f3 supportT(f3 v0) const {
         f3 sup = mk3(0.f, 0.f, 0.f);
         float maxDot = -1e30f;
         f3 v = v0;
         float l2 = len2_3(v);
         if (l2 < 0.0001f) v = mk3(1.f, 0.f, 0.f);
         else v = scl3(v, 1.0f / jsqrtf(l2));
-        for (int i = 0; i < n; i++) {
-            float4 p = __ldg(pts + i);
-            float d = v.x * p.x + v.y * p.y + v.z * p.z;
-            if (d > maxDot) { maxDot = d; sup = mk3(p.x, p.y, p.z); }  // first strict max
+        if (!WIDE) {
+            for (int i = 0; i < n; i++) {
+                float4 p = __ldg(pts + i);
+                float d = v.x * p.x + v.y * p.y + v.z * p.z;
+                if (d > maxDot) { maxDot = d; sup = mk3(p.x, p.y, p.z); }  // first strict max
+            }
+            return sup;
+        }
+        // WIDE (straight-line callers with registers to spare): four vertex loads in flight per round (the pool is
+        // padded, so reading up to 3 entries past n is safe); the comparisons still run in vertex order, so the first
+        // strict maximum wins exactly as in the reference loop
+        for (int i = 0; i < n; i += 4) {
+            const float4 p0 = __ldg(pts + i), p1 = __ldg(pts + i + 1), p2 = __ldg(pts + i + 2), p3 = __ldg(pts + i + 3);
+            const float d0 = v.x * p0.x + v.y * p0.y + v.z * p0.z;
+            const float d1 = v.x * p1.x + v.y * p1.y + v.z * p1.z;
+            const float d2 = v.x * p2.x + v.y * p2.y + v.z * p2.z;
+            const float d3 = v.x * p3.x + v.y * p3.y + v.z * p3.z;
+            if (d0 > maxDot) { maxDot = d0; sup = mk3(p0.x, p0.y, p0.z); }
+            if (i + 1 < n && d1 > maxDot) { maxDot = d1; sup = mk3(p1.x, p1.y, p1.z); }
+            if (i + 2 < n && d2 > maxDot) { maxDot = d2; sup = mk3(p2.x, p2.y, p2.z); }
+            if (i + 3 < n && d3 > maxDot) { maxDot = d3; sup = mk3(p3.x, p3.y, p3.z); }
         }
         return sup;
     }
+    __device__ __forceinline__ f3 support(f3 v0) const { return supportT<false>(v0); }
     __device__ __forceinline__ f3 supportMargin(f3 v) const { return addMarginDir(support(v), v, margin); }
 };
 struct TriS {  // sh/TriangleShape.java:93-100 with lm/VectorUtil.java:41-58 maxAxis

@@ -587,6 +587,11 @@ struct LaneShape {
         if (type == SH_HULL) { HullS hs; hs.pts = pts; hs.n = n; hs.margin = 0.f; return hs.support(v); }
         return mk3(0.f, 0.f, 0.f);  // sphere
     }
+    __device__ __forceinline__ f3 supportWide(f3 v) const {  // same values; hull vertices fetched four at a time
+        if (type == SH_BOX) return mk3(fsel(v.x, h.x, -h.x), fsel(v.y, h.y, -h.y), fsel(v.z, h.z, -h.z));
+        if (type == SH_HULL) { HullS hs; hs.pts = pts; hs.n = n; hs.margin = 0.f; return hs.supportT<true>(v); }
+        return mk3(0.f, 0.f, 0.f);
+    }
 };
 
 // Warp-level refill: idle lanes take the next items of [0, end).  The warp reserves CHUNK items at a time from
@@ -654,8 +659,8 @@ __global__ void __launch_bounds__(256) k_gjk_prefilter(NpArgs a, uint32_t* __res
             f3 laO = sub3(ta.o, positionOffset), lbO = sub3(tb.o, positionOffset);
             // trip 1 (axis (0,1,0), empty simplex)
             f3 axis = mk3(0.f, 1.f, 0.f);
-            f3 pW = add3(mulMV(ta.m, A.support(mulMtV(ta.m, neg3(axis)))), laO);
-            f3 qW = add3(mulMV(tb.m, B.support(mulMtV(tb.m, axis))), lbO);
+            f3 pW = add3(mulMV(ta.m, A.supportWide(mulMtV(ta.m, neg3(axis)))), laO);
+            f3 qW = add3(mulMV(tb.m, B.supportWide(mulMtV(tb.m, axis))), lbO);
             f3 w = sub3(pW, qW);
             float delta = dot3(axis, w);
             float sq = B2C_SIMD_INFINITY;
@@ -667,8 +672,8 @@ __global__ void __launch_bounds__(256) k_gjk_prefilter(NpArgs a, uint32_t* __res
             normal1 = normal1 && !(sq1 < GJK_REL_ERROR2);
             normal1 = normal1 && !((sq - sq1) <= B2C_FLT_EPSILON * sq);
             // trip 2
-            pW = add3(mulMV(ta.m, A.support(mulMtV(ta.m, neg3(axis)))), laO);
-            qW = add3(mulMV(tb.m, B.support(mulMtV(tb.m, axis))), lbO);
+            pW = add3(mulMV(ta.m, A.supportWide(mulMtV(ta.m, neg3(axis)))), laO);
+            qW = add3(mulMV(tb.m, B.supportWide(mulMtV(tb.m, axis))), lbO);
             w = sub3(pW, qW);
             delta = dot3(axis, w);
             bool done = normal1 && (delta > 0.f) && (delta * delta > sq1 * maxDistSq);
@@ -1018,7 +1023,7 @@ constexpr uint32_t EPA_SMEM_LANES = 148u * 2u * 32u;
 constexpr uint32_t EPA_RETRY_BIT = 0x80000000u;  // set in EpaItem.pair while the item waits for the retry tier
 
 template <int TIER>
-__global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g, int solo) {
+__global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs g, int solo, int lpw) {
     uint32_t nItems;
     if (TIER != 1) {
         nItems = a.ctr->epaCount < g.maxEpa ? a.ctr->epaCount : g.maxEpa;
@@ -1034,8 +1039,14 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g, int solo) {
     // TIER 1: one item per WARP (lane 0), its large pool in this warp's slice of shared memory — a retried item is a long
     // run (up to 256 polytope expansions), and in global memory every one of its dependent accesses would cost ~1 us
     const uint32_t warpsPerBlock = blockDim.x >> 5;
-    const uint32_t itFirst = TIER != 1 ? first : ((threadIdx.x & 31) == 0 ? blockIdx.x * warpsPerBlock + (threadIdx.x >> 5) : 0xffffffffu);
-    const uint32_t itStep = TIER != 1 ? step : gridDim.x * warpsPerBlock;
+    // TIER 0: `lpw` active lanes per warp (32 pool slices per block whatever the block size): the fewer lanes share a
+    // warp, the less one item's iterations wait behind the divergent paths of its neighbours
+    const uint32_t slot0 = (threadIdx.x >> 5) * (uint32_t)lpw + (threadIdx.x & 31);
+    const bool active0 = (int)(threadIdx.x & 31) < lpw;
+    const uint32_t itFirst = TIER == 2 ? first
+                           : TIER == 0 ? (active0 ? blockIdx.x * 32u + slot0 : 0xffffffffu)
+                           : ((threadIdx.x & 31) == 0 ? blockIdx.x * warpsPerBlock + (threadIdx.x >> 5) : 0xffffffffu);
+    const uint32_t itStep = TIER == 2 ? step : TIER == 0 ? gridDim.x * 32u : gridDim.x * warpsPerBlock;
     for (uint32_t it0 = itFirst; it0 < nItems; it0 += itStep) {
         const uint32_t it = TIER != 1 ? it0 : g.epaRetry[it0];
         EpaItem item = g.epaItems[it];
@@ -1070,7 +1081,7 @@ __global__ void __launch_bounds__(64) k_epa(NpArgs a, GjkArgs g, int solo) {
         bool epaFail = false, poolOverflow = false;
         bool ok;
         if (TIER == 0) {
-            EpaScratchSmall* sc = reinterpret_cast<EpaScratchSmall*>(epaSmem + (size_t)threadIdx.x * EPA_SMALL_STRIDE);
+            EpaScratchSmall* sc = reinterpret_cast<EpaScratchSmall*>(epaSmem + (size_t)slot0 * EPA_SMALL_STRIDE);
             ok = epaPenetration(A, B, la, lb, sc, wA, wB, epaFail, poolOverflow);
         } else if (TIER == 2) {
             EpaScratchLocal sc;
