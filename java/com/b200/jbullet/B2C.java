@@ -52,6 +52,15 @@ final class B2C {
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle getManifolds = h("b2c_get_manifolds", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 
+    // device-resident stepping: enqueue, download the pair list while the narrowphase runs, then wait for the counts
+    static final MethodHandle stepDevice = h("b2c_step_device", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle syncCounts = h("b2c_sync_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    // OverlappingPairCallback / GhostPairCallback events (bp/HashedOverlappingPairCache.java:135-137,323-325)
+    static final MethodHandle getPairDeltas = h("b2c_get_pair_deltas",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    // SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110)
+    static final MethodHandle computeIslands = h("b2c_compute_islands", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+
     static void check(int rc, MemorySegment ctx) {
         if (rc != 0) {
             String msg;
