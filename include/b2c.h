@@ -164,6 +164,17 @@ typedef struct {
 int32_t b2c_get_contacts(b2c_ctx*, b2c_contact_header* headers_out, int32_t cap_headers, b2c_manifold_point* points_out,
                          int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
 
+/* The same stream with 64-byte points that carry only what the constraint solver reads (world points, normal, distance,
+ * combined friction / restitution, lifetime, src_slot, triangle ids) — the manifold cache itself (local points, refresh)
+ * stays on the device.  One third fewer bytes over PCIe than b2c_get_contacts. */
+typedef struct {
+    float world_a[3], world_b[3], normal_on_b[3];
+    float distance, combined_friction, combined_restitution;
+    int32_t life_time, src_slot, part_id1, index1;
+} b2c_solver_point; /* 64 bytes */
+int32_t b2c_get_solver_contacts(b2c_ctx*, b2c_contact_header* headers_out, int32_t cap_headers, b2c_solver_point* points_out,
+                                int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
+
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
 typedef struct {

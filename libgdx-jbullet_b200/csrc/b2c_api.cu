@@ -1264,17 +1264,22 @@ int32_t b2c_get_stats(b2c_ctx* ctx, b2c_stats* out) {
     return B2C_OK;
 }
 
-int32_t b2c_get_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b2c_manifold_point* pOut, int32_t capP,
-                         int32_t* nH, int32_t* nP) {
+static int32_t getContactsImpl(b2c_ctx* ctx, bool slim, b2c_contact_header* hOut, int32_t capH, void* pOut, int32_t capP, int32_t* nH,
+                               int32_t* nP) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     if (!ctx->pairsValid) return B2C_ERR_STATE;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     NpArgs a = makeNpArgs(ctx);
+    const size_t ptSize = slim ? sizeof(b2c_solver_point) : sizeof(b2c_manifold_point);
     CK(cudaMemsetAsync(ctx->dContactCounts, 0, 2 * sizeof(uint32_t), s));
-    k_compact_contacts<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(a, ctx->dContactHdr, ctx->dContactPts,
-                                                                                  ctx->capContactHdr, ctx->capContactPts,
-                                                                                  ctx->dContactCounts);
+    const unsigned grid = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
+    if (slim)
+        k_compact_contacts<true><<<grid, 256, 0, s>>>(a, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                      ctx->dContactCounts);
+    else
+        k_compact_contacts<false><<<grid, 256, 0, s>>>(a, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts);
     uint32_t counts[2] = {0, 0};
     CK(cudaMemcpyAsync(counts, ctx->dContactCounts, sizeof(counts), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -1284,9 +1289,19 @@ int32_t b2c_get_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b
     if (!hOut && !pOut) return B2C_OK;
     if ((uint32_t)capH < counts[0] || (uint32_t)capP < counts[1]) { ctx->err = "contact output buffers too small"; return B2C_ERR_CAPACITY; }
     if (hOut && counts[0]) CK(cudaMemcpyAsync(hOut, ctx->dContactHdr, (size_t)counts[0] * sizeof(b2c_contact_header), cudaMemcpyDeviceToHost, s));
-    if (pOut && counts[1]) CK(cudaMemcpyAsync(pOut, ctx->dContactPts, (size_t)counts[1] * sizeof(b2c_manifold_point), cudaMemcpyDeviceToHost, s));
+    if (pOut && counts[1]) CK(cudaMemcpyAsync(pOut, ctx->dContactPts, (size_t)counts[1] * ptSize, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B2C_OK;
+}
+
+int32_t b2c_get_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b2c_manifold_point* pOut, int32_t capP,
+                         int32_t* nH, int32_t* nP) {
+    return getContactsImpl(ctx, false, hOut, capH, pOut, capP, nH, nP);
+}
+
+int32_t b2c_get_solver_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b2c_solver_point* pOut, int32_t capP,
+                                int32_t* nH, int32_t* nP) {
+    return getContactsImpl(ctx, true, hOut, capH, pOut, capP, nH, nP);
 }
 
 int32_t b2c_get_pair_deltas(b2c_ctx* ctx, int32_t* addedOut, int32_t capA, int32_t* removedOut, int32_t capR, int32_t* nA, int32_t* nR) {

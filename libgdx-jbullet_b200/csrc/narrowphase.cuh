@@ -1179,9 +1179,12 @@ __global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
 }
 
 // Compact the touching manifolds (header + live points) for the D2H contact stream.
+// SLIM: points are written as 64-byte b2c_solver_point records (what the constraint solver reads).
+template <bool SLIM>
 __global__ void __launch_bounds__(256)
-k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, b2c_manifold_point* __restrict__ pts, uint32_t capH,
+k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restrict__ ptsOut, uint32_t capH,
                    uint32_t capP, uint32_t* __restrict__ counts /*[2]: headers, points*/) {
+    b2c_manifold_point* __restrict__ pts = reinterpret_cast<b2c_manifold_point*>(ptsOut);
     const uint32_t n = *a.numPairs;
     const int lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
@@ -1215,8 +1218,19 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, b2c_manifold_
                 hdr[h] = hh;
                 for (int k = 0; k < nc; k++) {
                     const int4* src = reinterpret_cast<const int4*>(a.mpts + 4 * (size_t)p + k);
-                    int4* dst = reinterpret_cast<int4*>(pts + fp + k);
-                    for (int q = 0; q < 6; q++) dst[q] = src[q];
+                    if (!SLIM) {
+                        int4* dst = reinterpret_cast<int4*>(pts + fp + k);
+                        for (int q = 0; q < 6; q++) dst[q] = src[q];
+                    } else {
+                        // 96-byte record words: 0-2 local_a, 3-5 local_b, 6-8 world_a, 9-11 world_b, 12-14 normal, 15 distance,
+                        // 16 friction, 17 restitution, 18 life, 19 src_slot, 20 part_id1, 21 index1, 22-23 pad
+                        const int4 v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4], v5 = src[5];
+                        int4* dst = reinterpret_cast<int4*>(reinterpret_cast<b2c_solver_point*>(ptsOut) + fp + k);
+                        dst[0] = make_int4(v1.z, v1.w, v2.x, v2.y);  // world_a xyz, world_b x
+                        dst[1] = make_int4(v2.z, v2.w, v3.x, v3.y);  // world_b yz, normal xy
+                        dst[2] = make_int4(v3.z, v3.w, v4.x, v4.y);  // normal z, distance, friction, restitution
+                        dst[3] = make_int4(v4.z, v4.w, v5.x, v5.y);  // life, src_slot, part_id1, index1
+                    }
                 }
             }
         }

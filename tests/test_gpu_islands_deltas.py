@@ -60,3 +60,26 @@ def test_islands_sparse_spheres_many_islands(gpu_pkg):
     _check(gw, ow, sc, 2)
     _, gn = gw.islands()
     assert gn > 100
+
+
+def test_solver_contact_stream_matches_full_stream(gpu_pkg):
+    """b2c_get_solver_contacts is a 64-byte projection of b2c_get_contacts: same manifolds, same field bits."""
+    sc = scenes.bin_scene(n=2500, seed=17)
+    gw = scenes.build_gpu(gpu_pkg, sc, mode=1)
+    for step in range(3):
+        gw.setWorldTransforms(sc.transforms(step))
+        gw.step()
+    h1, p1 = gw.contacts()
+    h2, p2 = gw.solver_contacts()
+    assert len(h1) == len(h2) > 100 and len(p1) == len(p2)
+    o1 = np.lexsort((h1["pair_uid1"], h1["pair_uid0"]))
+    o2 = np.lexsort((h2["pair_uid1"], h2["pair_uid0"]))
+    for f in ("pair_uid0", "pair_uid1", "body0", "body1", "num_contacts", "algorithm", "pair_index"):
+        assert np.array_equal(h1[f][o1], h2[f][o2]), f
+    for a, b in zip(o1, o2):
+        n = h1["num_contacts"][a]
+        q1 = p1[h1["first_point"][a]:h1["first_point"][a] + n]
+        q2 = p2[h2["first_point"][b]:h2["first_point"][b] + n]
+        for f in ("world_a", "world_b", "normal_on_b", "distance", "combined_friction", "combined_restitution", "life_time",
+                  "src_slot", "part_id1", "index1"):
+            assert q1[f].tobytes() == q2[f].tobytes(), f
