@@ -46,6 +46,7 @@ struct b2c_ctx {
     cudaStream_t streamEpa = nullptr;     // penetration bin (few long-latency lanes), beside k_manifold_cc; high priority
     cudaEvent_t evFork[2] = {nullptr, nullptr}, evJoin[2] = {nullptr, nullptr};
     bool overlap = true;
+    int mccBlocks = 8;                    // k_manifold_cc blocks per SM (B2C_MCC_BLOCKS)
     int epaLpw = 8;                       // active lanes per warp in the shared-memory EPA tier (B2C_EPA_LPW: 32/16/8/4)
     int epaHint = -1;                     // -1 unknown, 0 small penetration bin (shared-memory tier), 1 large (local-memory tier)
     bool timeline = false;                // B2C_TIMELINE=1: print where the side-stream kernels ran (debug)
@@ -469,7 +470,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     if (ctx->timeline) cudaEventRecord(ctx->tl[2], se);
     if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[1], se));
     if (ctx->timeline) cudaEventRecord(ctx->tl[3], s);
-    k_manifold_cc<<<148 * 8, 256, 0, s>>>(a);
+    k_manifold_cc<<<148 * ctx->mccBlocks, 256, 0, s>>>(a);
     if (ctx->timeline) cudaEventRecord(ctx->tl[4], s);
     ctx->launches += 2;
     if (ctx->overlap) {
@@ -594,6 +595,8 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         }
         const char* e = getenv("B2C_OVERLAP");  // measurement knob: 0 = everything on one stream
         ctx->overlap = !(e && e[0] == '0');
+        const char* mb = getenv("B2C_MCC_BLOCKS");
+        if (mb) { int v = atoi(mb); if (v >= 1 && v <= 8) ctx->mccBlocks = v; }
         const char* l = getenv("B2C_EPA_LPW");
         if (l) { int v = atoi(l); if (v == 32 || v == 16 || v == 8 || v == 4) ctx->epaLpw = v; }
         const char* t = getenv("B2C_TIMELINE");

@@ -182,6 +182,160 @@ __device__ __forceinline__ float combinedFriction(float f0, float f1) {
     return f;
 }
 
+// ---- the same manifold step with 128-bit accesses (single addContactPoint + refresh callers) ------------------
+// One 96-byte point = six int4: q0 = (localA.xyz, localB.x) q1 = (localB.yz, worldA.xy) q2 = (worldA.z, worldB.xyz)
+// q3 = (normal.xyz, distance) q4 = (friction, restitution, lifeTime, src_slot) q5 = (partId1, index1, pad, pad).
+// manifoldStepV does exactly what "mark src_slot; manifoldAdd; resultRefresh" does above — same float operations in
+// the same order — but reads the header once, fetches whole points with independent 16-byte loads and writes them
+// back the same way, so a thread issues a handful of memory round trips instead of dozens of scalar ones.
+struct PtV {
+    int4 q0, q1, q2, q3, q4, q5;
+};
+__device__ __forceinline__ float i2f(int v) { return __int_as_float(v); }
+__device__ __forceinline__ int f2i(float v) { return __float_as_int(v); }
+__device__ __forceinline__ PtV ldPtV(const b2c_manifold_point* p) {
+    const int4* s = reinterpret_cast<const int4*>(p);
+    PtV r;
+    r.q0 = s[0]; r.q1 = s[1]; r.q2 = s[2]; r.q3 = s[3]; r.q4 = s[4]; r.q5 = s[5];
+    return r;
+}
+__device__ __forceinline__ void stPtV(b2c_manifold_point* p, const PtV& r) {
+    int4* d = reinterpret_cast<int4*>(p);
+    d[0] = r.q0; d[1] = r.q1; d[2] = r.q2; d[3] = r.q3; d[4] = r.q4; d[5] = r.q5;
+}
+
+// hdr0/hdr1: the manifold header already in registers (hdr1.x = num_contacts, hdr1.y = algorithm); the caller has set
+// algorithm / bodies for a new manifold.  Returns true when a contact was added.  Writes the header back.
+__device__ __forceinline__ bool manifoldStepV(ManifoldHdr* H, b2c_manifold_point* P, int4 hdr0, int4 hdr1, int pairBody0,
+                                              const Xf& rootA, const Xf& rootB, bool has, f3 normal, f3 point, float depth,
+                                              float threshold, float friction, float restitution) {
+    int nc = hdr1.x;
+    const bool isSwapped = hdr0.z != pairBody0;
+    int newSlot = -1;      // slot that holds a point created this step (src_slot -1); replaced points keep their slot
+    bool added = false;
+    if (has && !(depth > threshold)) {  // disp/ManifoldResult.java:96
+        added = true;
+        f3 pointA = add3(scl3(normal, depth), point);
+        f3 localA, localB;
+        if (isSwapped) { localA = invXfPoint(rootB, pointA); localB = invXfPoint(rootA, point); }
+        else { localA = invXfPoint(rootA, pointA); localB = invXfPoint(rootB, point); }
+        // getCacheEntry (np/PersistentManifold.java:214-233): the first 16 bytes of every live point
+        int4 a0 = make_int4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+        if (nc > 0) a0 = *reinterpret_cast<const int4*>(P);
+        if (nc > 1) a1 = *reinterpret_cast<const int4*>(P + 1);
+        if (nc > 2) a2 = *reinterpret_cast<const int4*>(P + 2);
+        if (nc > 3) a3 = *reinterpret_cast<const int4*>(P + 3);
+        float shortest = threshold * threshold;
+        int nearest = -1;
+        {
+            f3 d;
+            float dd;
+            if (nc > 0) { d = sub3(mk3(i2f(a0.x), i2f(a0.y), i2f(a0.z)), localA); dd = dot3(d, d); if (dd < shortest) { shortest = dd; nearest = 0; } }
+            if (nc > 1) { d = sub3(mk3(i2f(a1.x), i2f(a1.y), i2f(a1.z)), localA); dd = dot3(d, d); if (dd < shortest) { shortest = dd; nearest = 1; } }
+            if (nc > 2) { d = sub3(mk3(i2f(a2.x), i2f(a2.y), i2f(a2.z)), localA); dd = dot3(d, d); if (dd < shortest) { shortest = dd; nearest = 2; } }
+            if (nc > 3) { d = sub3(mk3(i2f(a3.x), i2f(a3.y), i2f(a3.z)), localA); dd = dot3(d, d); if (dd < shortest) { shortest = dd; nearest = 3; } }
+        }
+        int life = 0, src = -1, idx;
+        if (nearest >= 0) {  // replaceContactPoint keeps the lifetime (:280-305); src_slot = the slot it continues
+            idx = nearest;
+            life = reinterpret_cast<const int4*>(P + idx)[4].z;
+            src = idx;
+        } else {
+            idx = nc;
+            if (idx == 4) {  // sortCachedPoints (:83-156) + closestAxis4 (lm/VectorUtil.java:60-90)
+                const float d0 = i2f(reinterpret_cast<const int4*>(P)[3].w), d1 = i2f(reinterpret_cast<const int4*>(P + 1)[3].w);
+                const float d2 = i2f(reinterpret_cast<const int4*>(P + 2)[3].w), d3 = i2f(reinterpret_cast<const int4*>(P + 3)[3].w);
+                int maxPenetrationIndex = -1;
+                float maxPenetration = depth;
+                if (d0 < maxPenetration) { maxPenetrationIndex = 0; maxPenetration = d0; }
+                if (d1 < maxPenetration) { maxPenetrationIndex = 1; maxPenetration = d1; }
+                if (d2 < maxPenetration) { maxPenetrationIndex = 2; maxPenetration = d2; }
+                if (d3 < maxPenetration) { maxPenetrationIndex = 3; maxPenetration = d3; }
+                const f3 p0 = mk3(i2f(a0.x), i2f(a0.y), i2f(a0.z)), p1 = mk3(i2f(a1.x), i2f(a1.y), i2f(a1.z));
+                const f3 p2 = mk3(i2f(a2.x), i2f(a2.y), i2f(a2.z)), p3 = mk3(i2f(a3.x), i2f(a3.y), i2f(a3.z));
+                float res0 = 0.f, res1 = 0.f, res2 = 0.f, res3 = 0.f;
+                if (maxPenetrationIndex != 0) res0 = len2_3(crs3(sub3(localA, p1), sub3(p3, p2)));
+                if (maxPenetrationIndex != 1) res1 = len2_3(crs3(sub3(localA, p0), sub3(p3, p2)));
+                if (maxPenetrationIndex != 2) res2 = len2_3(crs3(sub3(localA, p0), sub3(p3, p1)));
+                if (maxPenetrationIndex != 3) res3 = len2_3(crs3(sub3(localA, p0), sub3(p2, p1)));
+                res0 = fabsf(res0); res1 = fabsf(res1); res2 = fabsf(res2); res3 = fabsf(res3);
+                int maxIndex = -1;
+                float maxVal = -1e30f;
+                if (res0 > maxVal) { maxIndex = 0; maxVal = res0; }
+                if (res1 > maxVal) { maxIndex = 1; maxVal = res1; }
+                if (res2 > maxVal) { maxIndex = 2; maxVal = res2; }
+                if (res3 > maxVal) { maxIndex = 3; maxVal = res3; }
+                idx = maxIndex < 0 ? 0 : maxIndex;
+            } else {
+                nc = nc + 1;
+            }
+            newSlot = idx;
+        }
+        PtV n;
+        n.q0 = make_int4(f2i(localA.x), f2i(localA.y), f2i(localA.z), f2i(localB.x));
+        n.q1 = make_int4(f2i(localB.y), f2i(localB.z), f2i(pointA.x), f2i(pointA.y));
+        n.q2 = make_int4(f2i(pointA.z), f2i(point.x), f2i(point.y), f2i(point.z));
+        n.q3 = make_int4(f2i(normal.x), f2i(normal.y), f2i(normal.z), f2i(depth));
+        n.q4 = make_int4(f2i(friction), f2i(restitution), life, src);
+        n.q5 = make_int4(0, 0, 0, 0);
+        stPtV(P + idx, n);
+    }
+    // refreshContactPoints(trA, trB) (np/PersistentManifold.java:312-372) incl. removeContactPoint (:259-278); the
+    // reference's two loops fused per point: point i is updated, then tested; everything above i is already final
+    if (nc > 0) {
+        const Xf& trA = isSwapped ? rootB : rootA;
+        const Xf& trB = isSwapped ? rootA : rootB;
+        const float thr2 = threshold * threshold;
+        for (int i = nc - 1; i >= 0; i--) {
+            PtV v = ldPtV(P + i);
+            const f3 la = mk3(i2f(v.q0.x), i2f(v.q0.y), i2f(v.q0.z)), lb = mk3(i2f(v.q0.w), i2f(v.q1.x), i2f(v.q1.y));
+            const f3 nrm = mk3(i2f(v.q3.x), i2f(v.q3.y), i2f(v.q3.z));
+            const f3 wa = xfPoint(trA, la);
+            const f3 wb = xfPoint(trB, lb);
+            const float dist = dot3(sub3(wa, wb), nrm);
+            bool remove = false;
+            if (!(dist <= threshold)) {
+                remove = true;
+            } else {
+                f3 projected = sub3(wa, scl3(nrm, dist));
+                f3 diff = sub3(wb, projected);
+                if (dot3(diff, diff) > thr2) remove = true;
+            }
+            if (!remove) {
+                v.q1.z = f2i(wa.x); v.q1.w = f2i(wa.y); v.q2.x = f2i(wa.z);
+                v.q2.y = f2i(wb.x); v.q2.z = f2i(wb.y); v.q2.w = f2i(wb.z);
+                v.q3.w = f2i(dist);
+                v.q4.z = v.q4.z + 1;                       // lifeTime++
+                v.q4.w = (i == newSlot) ? -1 : i;          // src_slot: the slot this point held at the start of the step
+                stPtV(P + i, v);
+            } else {
+                const int last = nc - 1;
+                if (i != last) {
+                    // p[i] = p[last] (already refreshed and kept); p[last].lifeTime = 0, src_slot = -1
+                    PtV l = ldPtV(P + last);
+                    stPtV(P + i, l);
+                    l.q4.z = 0; l.q4.w = -1;
+                    stPtV(P + last, l);
+                } else {
+                    // the reference leaves the refreshed values in the dead slot; keep the record identical
+                    v.q1.z = f2i(wa.x); v.q1.w = f2i(wa.y); v.q2.x = f2i(wa.z);
+                    v.q2.y = f2i(wb.x); v.q2.z = f2i(wb.y); v.q2.w = f2i(wb.z);
+                    v.q3.w = f2i(dist);
+                    v.q4.z = v.q4.z + 1;
+                    v.q4.w = (i == newSlot) ? -1 : i;
+                    stPtV(P + i, v);
+                }
+                nc = last;
+            }
+        }
+    }
+    hdr1.x = nc;
+    int4* hd = reinterpret_cast<int4*>(H);
+    hd[0] = hdr0;
+    hd[1] = hdr1;
+    return added;
+}
+
 // ---- k_carry: bring manifolds over from the previous step by pair key --------------------------------
 // A pair that stayed in the cache keeps its algorithm and manifold (bp/BroadphasePair.java:37-40); a pair
 // that left and came back starts empty (bp/HashedOverlappingPairCache.java:129-174 cleanOverlappingPair).
@@ -471,14 +625,16 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
         int b0 = pr.x - 1, b1 = pr.y - 1;
         Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
         float r0 = a.shapes[a.shape[b0]].dims[0], r1 = a.shapes[a.shape[b1]].dims[0];
-        MView m = mview(a, p);
-        if (m.h->algorithm == 0) { m.h->algorithm = 1; m.h->body0 = pr.x; m.h->body1 = pr.y; created++; }
-        for (int k = 0; k < m.h->num_contacts; k++) m.p[k].src_slot = k;
+        ManifoldHdr* H = a.mhdr + p;
+        int4 h0 = reinterpret_cast<const int4*>(H)[0], h1 = reinterpret_cast<const int4*>(H)[1];
+        bool fresh = false;
+        if (h1.y == 0) { h1.y = 1; h0.z = pr.x; h0.w = pr.y; created++; fresh = true; }
         f3 diff = sub3(t0.o, t1.o);
         float len = len3(diff);
         if (len > (r0 + r1)) {
             writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, 10, 0);
-            resultRefresh(m, pr.x, t0, t1, a.threshold);
+            if (h1.x != 0) manifoldStepV(H, a.mpts + 4 * (size_t)p, h0, h1, pr.x, t0, t1, false, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, a.threshold, 0.f, 0.f);
+            else if (fresh) { reinterpret_cast<int4*>(H)[0] = h0; reinterpret_cast<int4*>(H)[1] = h1; }
             continue;
         }
         float dist = len - (r0 + r1);
@@ -487,8 +643,9 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
         f3 pos1 = add3(t1.o, scl3(n, r1));
         writeRaw(a.raw + p, pr, -1, 1, n, pos1, dist, 10, 0);
         float2 m0 = a.material[b0], m1 = a.material[b1];
-        if (manifoldAdd(m, pr.x, t0, t1, n, pos1, dist, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
-        resultRefresh(m, pr.x, t0, t1, a.threshold);
+        if (manifoldStepV(H, a.mpts + 4 * (size_t)p, h0, h1, pr.x, t0, t1, true, n, pos1, dist, a.threshold, combinedFriction(m0.x, m1.x),
+                          m0.y * m1.y))
+            added++;
     }
     if (created) atomicAdd(&a.ctr->numManifolds, created);
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
@@ -782,22 +939,29 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
 // record: getNewManifold on first use (disp/ConvexConvexAlgorithm.java:92-96), ManifoldResult.addContactPoint,
 // refreshContactPoints (:136-138).
 __device__ __forceinline__ void manifoldCcOne(const NpArgs& a, uint32_t p, bool has, uint32_t& added, uint32_t& created) {
-    int2 pr = a.pairs[p];
-    MView m = mview(a, p);
-    if (m.h->algorithm == 0) { m.h->algorithm = 3; m.h->body0 = pr.x; m.h->body1 = pr.y; created++; }
-    const int nc = m.h->num_contacts;
-    if (nc == 0 && !has) return;  // nothing to add, nothing to refresh
-    const b2c_raw_contact* r = a.raw + p;
-    for (int k = 0; k < nc; k++) m.p[k].src_slot = k;
-    int b0 = pr.x - 1, b1 = pr.y - 1;
-    Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
-    if (has) {
-        float2 m0 = a.material[b0], m1 = a.material[b1];
-        if (manifoldAdd(m, pr.x, t0, t1, mk3(r->normal[0], r->normal[1], r->normal[2]), mk3(r->point[0], r->point[1], r->point[2]),
-                        r->depth, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0))
-            added++;
+    const int2 pr = a.pairs[p];
+    ManifoldHdr* H = a.mhdr + p;
+    int4 h0 = reinterpret_cast<const int4*>(H)[0], h1 = reinterpret_cast<const int4*>(H)[1];
+    bool fresh = false;
+    if (h1.y == 0) { h1.y = 3; h0.z = pr.x; h0.w = pr.y; created++; fresh = true; }
+    if (h1.x == 0 && !has) {  // nothing to add, nothing to refresh
+        if (fresh) { reinterpret_cast<int4*>(H)[0] = h0; reinterpret_cast<int4*>(H)[1] = h1; }
+        return;
     }
-    resultRefresh(m, pr.x, t0, t1, a.threshold);
+    const int b0 = pr.x - 1, b1 = pr.y - 1;
+    const Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+    f3 n = mk3(0.f, 0.f, 0.f), pt = n;
+    float depth = 0.f, fr = 0.f, re = 0.f;
+    if (has) {
+        const b2c_raw_contact* r = a.raw + p;
+        n = mk3(r->normal[0], r->normal[1], r->normal[2]);
+        pt = mk3(r->point[0], r->point[1], r->point[2]);
+        depth = r->depth;
+        const float2 m0 = a.material[b0], m1 = a.material[b1];
+        fr = combinedFriction(m0.x, m1.x);
+        re = m0.y * m1.y;
+    }
+    if (manifoldStepV(H, a.mpts + 4 * (size_t)p, h0, h1, pr.x, t0, t1, has, n, pt, depth, a.threshold, fr, re)) added++;
 }
 
 // k_manifold_cc: every pair of the GJK bins whose detector finished in k_gjk / k_gjk_prefilter.  Pairs waiting in the
