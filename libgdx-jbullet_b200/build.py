@@ -39,17 +39,20 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra=()):
+    """extra / B2C_NVCC_EXTRA: additional nvcc flags for tuning experiments (e.g. -DGJK_MINB=5), never used by default."""
+    out = out or OUT
+    extra = list(extra) + os.environ.get("B2C_NVCC_EXTRA", "").split()
+    if not force and not extra and out == OUT and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libb2c.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
