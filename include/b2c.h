@@ -35,7 +35,14 @@ typedef enum {
 /* Which reference broadphase defines the exact pair set. */
 typedef enum {
     B2C_BP_TIGHT = 0, /* bp/SimpleBroadphase.java:81-110: overlaps of the AABBs last passed to setAabb */
-    B2C_BP_DBVT = 1   /* bp/DbvtBroadphase.java:89-228: overlaps of the per-proxy effective (possibly fattened) AABB */
+    B2C_BP_DBVT = 1,  /* bp/DbvtBroadphase.java:89-228: overlaps of the per-proxy effective (possibly fattened) AABB */
+    /* bp/AxisSweep3.java (16-bit) / bp/AxisSweep3_32.java (31-bit): overlaps of the AABBs QUANTISED over the world box as
+     * bp/AxisSweep3Internal.java:201-216 does (min edges even, max edges odd).  The incremental edge sort ends every step
+     * with exactly that set (oracle/sap_literal.h + tests/test_oracle_sap.py), so no edge lists are kept.  Set the world box
+     * with b2c_set_world_aabb before creating proxies (default +-1000).  Reference uids are handle indices, which it
+     * reuses after a removal; here uids are never reused. */
+    B2C_BP_SAP16 = 2,
+    B2C_BP_SAP32 = 3
 } b2c_broadphase_mode;
 
 /* Shape kinds (subset of bp/BroadphaseNativeType.java on the hot path). */
@@ -62,6 +69,8 @@ void b2c_default_config(b2c_config* cfg);
 int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out);
 void b2c_destroy(b2c_ctx* ctx);
 const char* b2c_last_error_string(const b2c_ctx* ctx);
+/* AxisSweep3(worldAabbMin, worldAabbMax, ...) bounds (bp/AxisSweep3.java:43-58) for the SAP modes; before any proxy. */
+int32_t b2c_set_world_aabb(b2c_ctx* ctx, const float world_min[3], const float world_max[3]);
 /* Library-level check usable without a ctx: number of visible sm_100 devices (0 on a CPU box). */
 int32_t b2c_device_count(void);
 

@@ -64,6 +64,8 @@ struct b2c_ctx {
     bool shapesDirty = false;
     bool hasPlane = false, hasMesh = false;
 
+    SapParams sap{};   // AxisSweep3 modes (broadphase_mode 2 / 3)
+
     // bodies
     int nBodies = 0;  // slots in use (uids 1..nBodies)
     BodyArrays B{};
@@ -197,7 +199,7 @@ int32_t uploadShapes(b2c_ctx* ctx) {
 
 // host copy of the shape AABB for createProxy (disp/CollisionWorld.java:113-119): computed on the device
 // by a one-thread launch of the same code path, so the bits are identical to the per-step kernel.
-__global__ void k_initial_aabb(BodyArrays B, const ShapeDev* shapes, int i) {
+__global__ void k_initial_aabb(BodyArrays B, const ShapeDev* shapes, int i, SapParams sp) {
     Xf t;
     float4 r0 = B.xf4[3 * (size_t)i], r1 = B.xf4[3 * (size_t)i + 1], r2 = B.xf4[3 * (size_t)i + 2];
     t.m[0][0] = r0.x; t.m[0][1] = r0.y; t.m[0][2] = r0.z;
@@ -206,6 +208,7 @@ __global__ void k_initial_aabb(BodyArrays B, const ShapeDev* shapes, int i) {
     t.o = mk3(r0.w, r1.w, r2.w);
     f3 mn, mx;
     shapeAabb(shapes[B.shape[i]], t, mn, mx);
+    if (sp.enabled) { sapSetAabb(B, i, mn, mx, sp); return; }  // createProxy -> addHandle: quantised creation AABB
     B.effMin[i] = make_float4(mn.x, mn.y, mn.z, 0.f);
     B.effMax[i] = make_float4(mx.x, mx.y, mx.z, 0.f);
     B.leafMin[i] = B.effMin[i];
@@ -213,7 +216,7 @@ __global__ void k_initial_aabb(BodyArrays B, const ShapeDev* shapes, int i) {
 }
 
 // batched variant used when many proxies are created before the first step
-__global__ void k_initial_aabb_range(BodyArrays B, const ShapeDev* shapes, int first, int count) {
+__global__ void k_initial_aabb_range(BodyArrays B, const ShapeDev* shapes, int first, int count, SapParams sp) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     int i = first + k;
@@ -225,6 +228,7 @@ __global__ void k_initial_aabb_range(BodyArrays B, const ShapeDev* shapes, int f
     t.o = mk3(r0.w, r1.w, r2.w);
     f3 mn, mx;
     shapeAabb(shapes[B.shape[i]], t, mn, mx);
+    if (sp.enabled) { sapSetAabb(B, i, mn, mx, sp); return; }  // createProxy -> addHandle: quantised creation AABB
     B.effMin[i] = make_float4(mn.x, mn.y, mn.z, 0.f);
     B.effMax[i] = make_float4(mx.x, mx.y, mx.z, 0.f);
     B.leafMin[i] = B.effMin[i];
@@ -271,7 +275,7 @@ int32_t runAabbKernel(b2c_ctx* ctx, bool forPairs) {
     k_aabb<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
         ctx->B, ctx->dShapes, n, staging, ctx->cfg.max_bodies, ctx->stagingCount, ctx->extPending ? ctx->dExtAabb : nullptr,
         ctx->dExtMask, ctx->cfg.max_bodies, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.contact_breaking_threshold,
-        ctx->cfg.dbvt_margin, ctx->cfg.dbvt_predicted_frames, ctx->aabbPending ? 1 : 0, ctx->dCtr);
+        ctx->cfg.dbvt_margin, ctx->cfg.dbvt_predicted_frames, ctx->aabbPending ? 1 : 0, ctx->dCtr, ctx->sap);
     ctx->launches++;
     ctx->stagingCount = 0;
     if (ctx->extPending) {
@@ -323,7 +327,8 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     RowMisc* rowMisc = reinterpret_cast<RowMisc*>(ctx->dRowZero + ctx->nRows + ctx->rowTiles);
     CK(cudaMemsetAsync(ctx->dRowZero, 0, ((size_t)ctx->nRows + ctx->rowTiles) * sizeof(uint32_t) + sizeof(RowMisc), s));
     k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys, rowCnt,
-                               (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi);
+                               (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi, ctx->sap.enabled ? ctx->B.leafMin : nullptr,
+                               ctx->sap.enabled ? ctx->B.leafMax : nullptr);
     // one block column per large proxy (static planes, meshes, big statics; one floor per world in batched scenes): the
     // host sizes the grid from the last count it has read, the kernel strides over whatever there is
     const unsigned perWorld = (unsigned)(n / ctx->cfg.num_worlds + 1);
@@ -332,7 +337,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     mark(ctx, 5);
     k_large<<<lg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
                                ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi,
-                               ctx->partRank);
+                               ctx->partRank, ctx->sap.enabled ? ctx->B.leafMin : nullptr, ctx->sap.enabled ? ctx->B.leafMax : nullptr);
     mark(ctx, 6);
     // canonical (uid0, uid1) order: rows keyed by uid0 (pair_rows.cuh); rowStart is also the "first pair of uid0" table
     uint32_t* rowStart = ctx->dPairFirst[cur];
@@ -527,6 +532,21 @@ int32_t readCounters(b2c_ctx* ctx) {
 
 }  // namespace
 
+static void sapConfigure(b2c_ctx* ctx, const float mn[3], const float mx[3]) {
+    const bool wide = ctx->cfg.broadphase_mode == B2C_BP_SAP32;
+    const int sentinel = wide ? 0x7fffffff : 0xffff;  // bp/AxisSweep3_32.java:49, bp/AxisSweep3.java:52
+    ctx->sap.handleMask = wide ? (int)0xfffffffe : 0xfffe;
+    ctx->sap.mask = wide ? 0xffffffffu : 0xffffu;
+    for (int c = 0; c < 3; c++) {
+        ctx->sap.wmin[c] = mn[c];
+        ctx->sap.wmax[c] = mx[c];
+        const float size = mx[c] - mn[c];
+        ctx->sap.quant[c] = (float)sentinel / size;  // bp/AxisSweep3Internal.java:103-105: maxInt / aabbSize
+    }
+    ctx->sap.enabled = 1;
+}
+
+
 extern "C" {
 
 void b2c_default_config(b2c_config* cfg) {
@@ -569,9 +589,14 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) return B2C_ERR_CUDA;
+    if (cfg->broadphase_mode < B2C_BP_TIGHT || cfg->broadphase_mode > B2C_BP_SAP32) return B2C_ERR_BAD_ARG;
     b2c_ctx* ctx = new b2c_ctx();
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
+    if (cfg->broadphase_mode >= B2C_BP_SAP16) {
+        const float mn[3] = {-1000.f, -1000.f, -1000.f}, mx[3] = {1000.f, 1000.f, 1000.f};
+        sapConfigure(ctx, mn, mx);
+    }
     auto fail = [&](int32_t rc) { b2c_destroy(ctx); return rc; };
 #define CKC(call)                                  \
     do {                                           \
@@ -724,6 +749,16 @@ void b2c_destroy(b2c_ctx* ctx) {
 
 const char* b2c_last_error_string(const b2c_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
+int32_t b2c_set_world_aabb(b2c_ctx* ctx, const float mn[3], const float mx[3]) {
+    if (!ctx || !mn || !mx) return B2C_ERR_BAD_ARG;
+    for (int c = 0; c < 3; c++)
+        if (!(mx[c] > mn[c])) return B2C_ERR_BAD_ARG;
+    if (ctx->cfg.broadphase_mode != B2C_BP_SAP16 && ctx->cfg.broadphase_mode != B2C_BP_SAP32) return B2C_OK;  // only the SAP modes quantise
+    if (ctx->nBodies > 0) { ctx->err = "b2c_set_world_aabb after proxies were created"; return B2C_ERR_STATE; }
+    sapConfigure(ctx, mn, mx);
+    return B2C_OK;
+}
+
 // ---- shapes ------------------------------------------------------------------------------------------
 static int32_t addShape(b2c_ctx* ctx, const ShapeDev& s, int32_t* out) {
     if ((int)ctx->hShapes.size() >= ctx->cfg.max_shapes) { ctx->err = "shape table full"; return B2C_ERR_CAPACITY; }
@@ -875,7 +910,7 @@ int32_t b2c_proxy_create(b2c_ctx* ctx, int32_t shape, const float t[12], int16_t
     CK(cudaMemcpyAsync(ctx->B.material + i, &mat, sizeof(float2), cudaMemcpyHostToDevice, s));
     int ls = ctx->step;  // createProxy counts as a setAabb in the current window (bp/DbvtBroadphase.java:177-180)
     CK(cudaMemcpyAsync(ctx->B.lastSet + i, &ls, sizeof(int), cudaMemcpyHostToDevice, s));
-    k_initial_aabb<<<1, 1, 0, s>>>(ctx->B, ctx->dShapes, i);
+    k_initial_aabb<<<1, 1, 0, s>>>(ctx->B, ctx->dShapes, i, ctx->sap);
     CK(cudaStreamSynchronize(s));  // host temporaries above go out of scope
     ctx->hFlags.push_back(fl);
     ctx->hShapeOf.push_back(shape);
@@ -921,7 +956,7 @@ int32_t b2c_proxy_create_batch(b2c_ctx* ctx, int32_t n, const int32_t* shapes, c
     CK(cudaMemcpyAsync(ctx->B.world + first, wl.data(), S * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->B.material + first, mat.data(), S * sizeof(float2), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->B.lastSet + first, ls.data(), S * sizeof(int), cudaMemcpyHostToDevice, s));
-    k_initial_aabb_range<<<(n + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, first, n);
+    k_initial_aabb_range<<<(n + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, first, n, ctx->sap);
     CK(cudaStreamSynchronize(s));
     for (int k = 0; k < n; k++) { ctx->hFlags.push_back(fl[k]); ctx->hShapeOf.push_back(shapes[k]); }
     ctx->nBodies += n;
@@ -1256,8 +1291,12 @@ int32_t b2c_get_aabbs(b2c_ctx* ctx, float* out, int32_t n) {
 
 int32_t b2c_get_broadphase_aabb(b2c_ctx* ctx, float mn[3], float mx[3]) {
     if (!ctx || !mn || !mx) return B2C_ERR_BAD_ARG;
-    // bp/SimpleBroadphase.java:118-121 and bp/DbvtBroadphase.java getBroadphaseAabb: unbounded
-    for (int c = 0; c < 3; c++) { mn[c] = -1e30f; mx[c] = 1e30f; }
+    // bp/SimpleBroadphase.java:118-121 and bp/DbvtBroadphase.java getBroadphaseAabb: unbounded;
+    // bp/AxisSweep3Internal.java:622-627: the world box
+    for (int c = 0; c < 3; c++) {
+        mn[c] = ctx->sap.enabled ? ctx->sap.wmin[c] : -1e30f;
+        mx[c] = ctx->sap.enabled ? ctx->sap.wmax[c] : 1e30f;
+    }
     return B2C_OK;
 }
 

@@ -93,10 +93,41 @@ __device__ __forceinline__ bool aabbIntersect(f3 amin, f3 amax, f3 bmin, f3 bmax
            (amax.z >= bmin.z);
 }
 
+// bp/AxisSweep3Internal.java:201-216 quantize (Java's (int) cast == cvt.rzi: toward zero, saturating, NaN -> 0)
+__device__ __forceinline__ uint32_t sapQuantize1(float p, int axis, int isMax, const SapParams& sp) {
+    float c = jminf(jmaxf(p, sp.wmin[axis]), sp.wmax[axis]);
+    float v = (c - sp.wmin[axis]) * sp.quant[axis];
+    return (uint32_t)((__float2int_rz(v) & sp.handleMask) | isMax) & sp.mask;
+}
+// monotone float image of a quantised coordinate: the box the grid and the sweep windows work on
+__device__ __forceinline__ float sapDequant(uint32_t q, int axis, const SapParams& sp) {
+    return __uint2float_rn(q) / sp.quant[axis] + sp.wmin[axis];
+}
+// SAP modes: leafMin/leafMax hold the quantised bounds (bit patterns), effMin/effMax their float image
+__device__ __forceinline__ void sapSetAabb(const BodyArrays& B, int i, f3 mn, f3 mx, const SapParams& sp) {
+    uint32_t q0 = sapQuantize1(mn.x, 0, 0, sp), q1 = sapQuantize1(mn.y, 1, 0, sp), q2 = sapQuantize1(mn.z, 2, 0, sp);
+    uint32_t r0 = sapQuantize1(mx.x, 0, 1, sp), r1 = sapQuantize1(mx.y, 1, 1, sp), r2 = sapQuantize1(mx.z, 2, 1, sp);
+    B.leafMin[i] = make_float4(__uint_as_float(q0), __uint_as_float(q1), __uint_as_float(q2), 0.f);
+    B.leafMax[i] = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), 0.f);
+    B.effMin[i] = make_float4(sapDequant(q0, 0, sp), sapDequant(q1, 1, sp), sapDequant(q2, 2, sp), 0.f);
+    B.effMax[i] = make_float4(sapDequant(r0, 0, sp), sapDequant(r1, 1, sp), sapDequant(r2, 2, sp), 0.f);
+}
+// overlap of the quantised boxes (the index-order test of bp/AxisSweep3Internal.java:174-195 in value form)
+__device__ __forceinline__ bool sapOverlap(float4 aqmin, float4 aqmax, float4 bqmin, float4 bqmax) {
+    return !(__float_as_uint(aqmax.x) < __float_as_uint(bqmin.x) || __float_as_uint(bqmax.x) < __float_as_uint(aqmin.x) ||
+             __float_as_uint(aqmax.y) < __float_as_uint(bqmin.y) || __float_as_uint(bqmax.y) < __float_as_uint(aqmin.y) ||
+             __float_as_uint(aqmax.z) < __float_as_uint(bqmin.z) || __float_as_uint(bqmax.z) < __float_as_uint(aqmin.z));
+}
+
 // BroadphaseInterface.setAabb for one proxy.  mode 0: bp/SimpleBroadphase.java:112-116;
 // mode 1: bp/DbvtBroadphase.java:196-228 with the in-place Expand/SignedExpand of bp/Dbvt.java:157-169.
 __device__ __forceinline__ void setAabbState(const BodyArrays& B, int i, f3 mn, f3 mx, int mode, int step, float dbvtMargin,
-                                             float predicted, uint8_t& flags) {
+                                             float predicted, uint8_t& flags, const SapParams& sp) {
+    if (mode >= 2) {  // bp/AxisSweep3Internal.java:591-594 setAabb -> updateHandle: new quantised bounds
+        sapSetAabb(B, i, mn, mx, sp);
+        B.lastSet[i] = step;
+        return;
+    }
     if (mode == 1) {
         f3 lmin = mk3(B.leafMin[i].x, B.leafMin[i].y, B.leafMin[i].z);
         f3 lmax = mk3(B.leafMax[i].x, B.leafMax[i].y, B.leafMax[i].z);
@@ -142,7 +173,7 @@ __device__ __forceinline__ void setAabbState(const BodyArrays& B, int i, f3 mn, 
 __global__ void __launch_bounds__(256)
 k_aabb(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, const float* __restrict__ staging, int stagingStride,
        int stagingCount, const float* __restrict__ extAabb, const uint8_t* __restrict__ extMask, int extStride, int mode,
-       int step, float threshold, float dbvtMargin, float predicted, int doUpdate, StepCounters* ctr) {
+       int step, float threshold, float dbvtMargin, float predicted, int doUpdate, StepCounters* ctr, SapParams sp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float extY = 0.f, extZ = 0.f;
     if (i < n) {
@@ -164,7 +195,7 @@ k_aabb(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, const float* __
                     f3 mn = mk3(extAabb[i], extAabb[i + (size_t)extStride], extAabb[i + 2 * (size_t)extStride]);
                     f3 mx = mk3(extAabb[i + 3 * (size_t)extStride], extAabb[i + 4 * (size_t)extStride],
                                 extAabb[i + 5 * (size_t)extStride]);
-                    setAabbState(B, i, mn, mx, mode, step, dbvtMargin, predicted, flags);
+                    setAabbState(B, i, mn, mx, mode, step, dbvtMargin, predicted, flags, sp);
                 }
             } else if (doUpdate && (flags & BF_ACTIVE)) {
                 Xf t;
@@ -183,7 +214,7 @@ k_aabb(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, const float* __
                 mx = add3(mx, ct);
                 f3 d = sub3(mx, mn);
                 if ((flags & BF_STATIC) || (len2_3(d) < 1e12f)) {  // disp/CollisionWorld.java:212-214
-                    setAabbState(B, i, mn, mx, mode, step, dbvtMargin, predicted, flags);
+                    setAabbState(B, i, mn, mx, mode, step, dbvtMargin, predicted, flags, sp);
                 } else {
                     flags = (uint8_t)((flags | BF_OVERFLOW) & ~BF_ACTIVE);  // reference: DISABLE_SIMULATION (:217)
                 }
@@ -454,7 +485,8 @@ struct PairStager {
 __global__ void __launch_bounds__(256)
 k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ srow,
         const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
-        uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi) {
+        uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi,
+        const float4* __restrict__ qmin, const float4* __restrict__ qmax /* SAP modes: quantised bounds per body, else null */) {
     __shared__ uint64_t stage[8][PAIR_STAGE];
     PairStager st;
     st.init(stage[threadIdx.x >> 5], rowCnt, uidBits);
@@ -509,6 +541,12 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                           (amin.z <= bmax.z) && (amax.z >= bmin.z) &&
                           filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
                     bodyB = __float_as_uint(bmin.w);
+                    // AxisSweep3 modes: the float boxes are a monotone image of the quantised ones (necessary condition);
+                    // the pair predicate itself is on the quantised values
+                    if (hit && qmin) {
+                        const uint32_t bodyA = __float_as_uint(amin.w);
+                        hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
+                    }
                 }
                 j++;
             }
@@ -524,7 +562,7 @@ __global__ void __launch_bounds__(256)
 k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ rowStart,
         const GridParams* __restrict__ grid, const int* __restrict__ world, int numWorlds, int uidBits,
         uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi,
-        int partRank) {
+        int partRank, const float4* __restrict__ qmin, const float4* __restrict__ qmax) {
     __shared__ uint64_t stage[8][PAIR_STAGE];
     PairStager st;
     st.init(stage[threadIdx.x >> 5], rowCnt, uidBits);
@@ -553,6 +591,7 @@ k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
                 bodyB = __float_as_uint(bmin.w);
                 hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
                       (amin.z <= bmax.z) && (amax.z >= bmin.z) && filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
+                if (hit && qmin) hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
                 if (hit && numWorlds > 1 && j >= l0) hit = world[bodyB] == world[bodyA];
                 // partitioned world: a (large, gridded) pair belongs to the rank whose slice holds the gridded member;
                 // (large, large) pairs belong to rank 0

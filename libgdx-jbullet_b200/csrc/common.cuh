@@ -126,6 +126,14 @@ struct MeshDev {
     int pad;
 };
 
+// AxisSweep3 quantisation (bp/AxisSweep3Internal.java:87-105, 201-216)
+struct SapParams {
+    float wmin[3], wmax[3], quant[3];
+    int handleMask;      // 0xfffe / 0xfffffffe
+    uint32_t mask;       // 0xffff / 0xffffffff
+    int enabled;
+};
+
 enum { BF_STATIC = 1, BF_ALIVE = 2, BF_ACTIVE = 4, BF_OVERFLOW = 8, BF_INFIXED = 16 };
 
 // Grid over the two non-sweep axes, chosen on the device each step (no host sync).

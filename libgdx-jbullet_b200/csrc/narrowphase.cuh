@@ -791,7 +791,11 @@ struct WarpQueue {
 // those the detector result is final here (no contact, lastUsedMethod -1, curIter 1).  Every other pair —
 // including anything unusual in trip 1 — goes to the survivor list and is run from scratch by k_gjk, so this
 // kernel only has to be exact when it says "done".
-__global__ void __launch_bounds__(256) k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict__ survCount) {
+#ifndef PREF_MINB
+#define PREF_MINB 3
+#endif
+__global__ void __launch_bounds__(256, PREF_MINB)
+k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict__ survCount) {
     const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
     __shared__ uint32_t warpCnt[8];
     __shared__ uint32_t blockBase;

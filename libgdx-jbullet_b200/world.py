@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib
 from ._lib import B2CError, Config, MANIFOLD_DTYPE, RAW_DTYPE, Stats
 
-TIGHT, DBVT = 0, 1
+TIGHT, DBVT, SAP16, SAP32 = 0, 1, 2, 3
 DEFAULT_FILTER, STATIC_FILTER, ALL_FILTER = 1, 2, -1  # bp/CollisionFilterGroups.java:33-39
 
 
@@ -38,7 +38,7 @@ def transforms_to_planes(xf):
 
 class GpuCollisionWorld:
     def __init__(self, mode=DBVT, max_bodies=131072, max_pairs=2 << 20, num_worlds=1, device=0, max_mesh_items=1 << 20,
-                 max_hull_points=1 << 20, max_shapes=4096, contact_breaking_threshold=0.02):
+                 max_hull_points=1 << 20, max_shapes=4096, contact_breaking_threshold=0.02, world_aabb=None):
         self.L = _lib.load()
         cfg = Config()
         self.L.b2c_default_config(C.byref(cfg))
@@ -57,6 +57,10 @@ class GpuCollisionWorld:
         if rc != 0:
             raise B2CError(rc, "b2c_create failed (no sm_100 device? there is no CPU fallback)")
         self.h = h
+        if world_aabb is not None:   # AxisSweep3(worldAabbMin, worldAabbMax) for the SAP modes
+            mn = np.ascontiguousarray(world_aabb[0], dtype=np.float32)
+            mx = np.ascontiguousarray(world_aabb[1], dtype=np.float32)
+            self._ck(self.L.b2c_set_world_aabb(self.h, _vp(mn), _vp(mx)))
         self.num_bodies = 0
         self._broadphase = GpuBroadphase(self)
         self._dispatcher = GpuDispatcher(self)

@@ -26,6 +26,18 @@ void* orc_create(int mode) {
     return w;
 }
 void orc_destroy(void* h) { delete (World*)h; }
+// AxisSweep3(worldAabbMin, worldAabbMax) bounds; call before the first body (bp/AxisSweep3.java:43-58)
+void orc_set_world_aabb(void* h, const float* mn, const float* mx) {
+    World* w = (World*)h;
+    w->worldAabbMin.set(mn[0], mn[1], mn[2]);
+    w->worldAabbMax.set(mx[0], mx[1], mx[2]);
+}
+// bp/AxisSweep3Internal.java:201-216 for one point: 3 quantised coordinates
+void orc_sap_quantize(void* h, const float* p, int isMax, unsigned* out3) {
+    World* w = (World*)h;
+    w->sapInit();
+    w->sapQ.quantize(out3, V3(p[0], p[1], p[2]), isMax);
+}
 void orc_set_brute_force(void* h, int on) { ((World*)h)->bruteForcePairs = on != 0; }
 void orc_set_params(void* h, float breaking, float dbvtMargin, float predictedFrames) {
     World* w = (World*)h;

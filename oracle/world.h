@@ -17,6 +17,7 @@
 #include <vector>
 #include "bvh.h"
 #include "dbvt_literal.h"
+#include "sap_literal.h"
 #include "gjk.h"
 #include "jmath.h"
 #include "manifold.h"
@@ -24,7 +25,9 @@
 
 namespace orc {
 
-enum BroadphaseMode { BP_TIGHT = 0, BP_DBVT = 1, BP_DBVT_LITERAL = 2 };  // 2: the reference's tree, literally (dbvt_literal.h)
+enum BroadphaseMode { BP_TIGHT = 0, BP_DBVT = 1, BP_DBVT_LITERAL = 2,
+                      BP_SAP16 = 3, BP_SAP32 = 4,                     // AxisSweep3 / AxisSweep3_32 as a stateless predicate on quantised AABBs
+                      BP_SAP16_LITERAL = 5, BP_SAP32_LITERAL = 6 };  // 2: the reference's tree, literally (dbvt_literal.h)
 
 struct Body {
     int shape = -1;
@@ -43,6 +46,8 @@ struct Body {
     bool aabbOverflow = false;
     LProxy* lit = nullptr; // BP_DBVT_LITERAL proxy
     int world = 0;        // batched independent worlds: each is its own CollisionWorld in the reference
+    unsigned qmin[3] = {0, 0, 0}, qmax[3] = {1, 1, 1};  // SAP modes: quantised bounds (bp/AxisSweep3Internal.java:201-216)
+    int sapHandle = 0;    // literal SAP handle (== uid while no handle is ever reused)
 };
 
 struct RawContact {  // one detector result, before ManifoldResult
@@ -79,6 +84,33 @@ struct World {
     std::map<std::pair<int, int>, PairState> pairState;
     std::vector<RawContact> raw;
     LDbvtBroadphase literal;
+    // AxisSweep3 modes
+    V3 worldAabbMin = V3(-1000.f, -1000.f, -1000.f), worldAabbMax = V3(1000.f, 1000.f, 1000.f);
+    SapQuantizer sapQ;
+    LSap sapLit;
+    bool sapReady = false;
+    std::vector<int> sapHandleUid;
+    bool isSap() const { return mode >= BP_SAP16 && mode <= BP_SAP32_LITERAL; }
+    bool isSapLiteral() const { return mode == BP_SAP16_LITERAL || mode == BP_SAP32_LITERAL; }
+    void sapInit() {
+        if (sapReady) return;
+        const bool wide = (mode == BP_SAP32 || mode == BP_SAP32_LITERAL);
+        sapQ.init(worldAabbMin, worldAabbMax, wide);
+        if (isSapLiteral()) sapLit.init(worldAabbMin, worldAabbMax, wide, 1 << 16);
+        sapReady = true;
+    }
+    // quantise, and keep the monotone float image of the quantised box as the "effective" AABB
+    void sapSet(Body& b, const V3& mn, const V3& mx) {
+        sapQ.quantize(b.qmin, mn, 0);
+        sapQ.quantize(b.qmax, mx, 1);
+        b.effMin.set(sapQ.dequant(b.qmin[0], 0), sapQ.dequant(b.qmin[1], 1), sapQ.dequant(b.qmin[2], 2));
+        b.effMax.set(sapQ.dequant(b.qmax[0], 0), sapQ.dequant(b.qmax[1], 1), sapQ.dequant(b.qmax[2], 2));
+    }
+    static bool sapOverlap(const Body& a, const Body& b) {
+        for (int k = 0; k < 3; k++)
+            if (a.qmax[k] < b.qmin[k] || b.qmax[k] < a.qmin[k]) return false;
+        return true;
+    }
     // counters
     long gjkChecks = 0, deepPenetrationChecks = 0, addedContacts = 0, bvhNodesVisited = 0, trianglesTested = 0;
 
@@ -135,12 +167,23 @@ struct World {
             literal.predictedframes = predictedFrames;
             b.lit = literal.createProxy(b.effMin, b.effMax, group, mask, world);
         }
+        if (isSap()) {  // bp/AxisSweep3Internal.java:576-584 createProxy -> addHandle with the shape's AABB
+            sapInit();
+            V3 mn = b.effMin, mx = b.effMax;
+            if (isSapLiteral()) {
+                b.sapHandle = sapLit.addHandle(mn, mx, group, mask, world);
+                if ((int)sapHandleUid.size() <= b.sapHandle) sapHandleUid.resize(b.sapHandle + 1, 0);
+                sapHandleUid[b.sapHandle] = b.uid;
+            }
+            sapSet(b, mn, mx);
+        }
         bodies.push_back(b);
         return b.uid;
     }
     void removeBody(int uid) {
         Body& b = bodies[uid - 1];
         if (b.alive && mode == BP_DBVT_LITERAL) literal.destroyProxy(b.lit);
+        if (b.alive && isSapLiteral()) sapLit.removeHandle(b.sapHandle);
         b.alive = false;
     }
 
@@ -159,6 +202,12 @@ struct World {
         if (mode == BP_DBVT_LITERAL) {
             literal.setAabb(b.lit, mn, mx);
             b.effMin = b.lit->aabb.mi; b.effMax = b.lit->aabb.mx;
+            b.lastSetStep = step;
+            return;
+        }
+        if (isSap()) {  // bp/AxisSweep3Internal.java:591-594 setAabb -> updateHandle
+            if (isSapLiteral()) sapLit.updateHandle(b.sapHandle, mn, mx);
+            sapSet(b, mn, mx);
             b.lastSetStep = step;
             return;
         }
@@ -230,6 +279,18 @@ struct World {
             step++;
             return (int)pairs.size();
         }
+        if (isSapLiteral()) {
+            // the reference's proxy uid IS the handle index (bp/AxisSweep3Internal.java:461), and freed handles are reused;
+            // this oracle numbers bodies by creation, so handles are mapped back to its uids
+            pairs.clear();
+            for (auto& pr : sapLit.pairs) {
+                int a = sapHandleUid[pr.first], c = sapHandleUid[pr.second];
+                pairs.push_back(std::make_pair(std::min(a, c), std::max(a, c)));
+            }
+            std::sort(pairs.begin(), pairs.end());
+            step++;
+            return (int)pairs.size();
+        }
         if (mode == BP_DBVT) {
             // bp/DbvtBroadphase.java:96-111: proxies not updated during this step (but updated the step
             // before) move to the fixed set; eff is kept, leaf volume becomes eff.
@@ -250,7 +311,7 @@ struct World {
                 for (size_t c = a + 1; c < order.size(); c++) {
                     const Body& A = bodies[order[a]];
                     const Body& B = bodies[order[c]];
-                    if (filter(A, B) && intersect(A.effMin, A.effMax, B.effMin, B.effMax))
+                    if (filter(A, B) && (isSap() ? sapOverlap(A, B) : intersect(A.effMin, A.effMax, B.effMin, B.effMax)))
                         pairs.push_back(std::make_pair(A.uid, B.uid));
                 }
         } else {
@@ -263,7 +324,8 @@ struct World {
                 for (size_t c = a + 1; c < order.size(); c++) {
                     const Body& B = bodies[order[c]];
                     if (B.effMin.x > A.effMax.x) break;
-                    if (filter(A, B) && intersect(A.effMin, A.effMax, B.effMin, B.effMax))
+                    // SAP modes: eff is a monotone image of the quantised box, so the float window is conservative
+                    if (filter(A, B) && (isSap() ? sapOverlap(A, B) : intersect(A.effMin, A.effMax, B.effMin, B.effMax)))
                         pairs.push_back(std::make_pair(std::min(A.uid, B.uid), std::max(A.uid, B.uid)));
                 }
             }

@@ -34,6 +34,8 @@ def lib():
     L.orc_create.argtypes = [C.c_int]
     L.orc_destroy.argtypes = [C.c_void_p]
     L.orc_set_brute_force.argtypes = [C.c_void_p, C.c_int]
+    L.orc_set_world_aabb.argtypes = [C.c_void_p, f32p, f32p]
+    L.orc_sap_quantize.argtypes = [C.c_void_p, f32p, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
     L.orc_set_params.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
     L.orc_shape_box.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
     L.orc_shape_sphere.argtypes = [C.c_void_p, C.c_float]
@@ -79,14 +81,22 @@ def xf12(basis=None, origin=(0, 0, 0)):
 
 
 TIGHT, DBVT, DBVT_LITERAL = 0, 1, 2
+SAP16, SAP32, SAP16_LITERAL, SAP32_LITERAL = 3, 4, 5, 6
 
 
 class OracleWorld:
-    def __init__(self, mode=TIGHT, brute_force=False):
+    def __init__(self, mode=TIGHT, brute_force=False, world_aabb=None):
         self.L = lib()
         self.h = self.L.orc_create(mode)
         if brute_force:
             self.L.orc_set_brute_force(self.h, 1)
+        if world_aabb is not None:
+            self.L.orc_set_world_aabb(self.h, np.asarray(world_aabb[0], np.float32), np.asarray(world_aabb[1], np.float32))
+
+    def sap_quantize(self, p, is_max):
+        out = np.zeros(3, dtype=np.uint32)
+        self.L.orc_sap_quantize(self.h, np.asarray(p, np.float32), int(is_max), out)
+        return out
 
     def __del__(self):
         try:

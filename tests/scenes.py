@@ -295,9 +295,9 @@ def build_gpu(pkg, sc, mode, max_pairs=None, **kw):
     return gw
 
 
-def build_oracle(sc, mode, brute_force=False):
+def build_oracle(sc, mode, brute_force=False, world_aabb=None):
     import orc
-    ow = orc.OracleWorld(mode=mode, brute_force=brute_force)
+    ow = orc.OracleWorld(mode=mode, brute_force=brute_force, world_aabb=world_aabb)
     ids = []
     for s in sc.shapes:
         if s[0] == "box":
@@ -315,5 +315,8 @@ def build_oracle(sc, mode, brute_force=False):
     return ow
 
 
-def build_both(pkg, sc, mode, **kw):
-    return build_gpu(pkg, sc, mode, **kw), build_oracle(sc, mode)
+def build_both(pkg, sc, mode, world_aabb=None, **kw):
+    if world_aabb is not None:
+        kw["world_aabb"] = world_aabb
+    # device modes 2/3 are AxisSweep3 / AxisSweep3_32 = oracle modes 3/4
+    return build_gpu(pkg, sc, mode, **kw), build_oracle(sc, {2: 3, 3: 4}.get(mode, mode), world_aabb=world_aabb)
