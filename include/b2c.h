@@ -115,6 +115,10 @@ int32_t b2c_proxy_set_material(b2c_ctx*, int32_t uid, float friction, float rest
 int32_t b2c_set_transforms(b2c_ctx*, int32_t n, const int32_t* uids, const float* planes12);
 /* CollisionObject.isActive() per body (disp/CollisionObject.java:178-180); 1 = active */
 int32_t b2c_set_activation(b2c_ctx*, int32_t n, const int32_t* uids, const uint8_t* active);
+/* CollisionObject.checkCollideWith / RigidBody.checkCollideWithOverride (dynamics/RigidBody.java:624-639): bodies linked by
+ * a constraint with disableCollisionsBetweenLinkedBodies stay in the pair cache but are not dispatched
+ * (disp/CollisionDispatcher.java:216-218).  uid_pairs = 2*n uids, any order; replaces the previous list; n = 0 clears. */
+int32_t b2c_set_no_collide_pairs(b2c_ctx*, int32_t n, const int32_t* uid_pairs);
 /* BroadphaseInterface.setAabb (bp/BroadphaseInterface.java:39) in bulk, for hosts that compute
  * AABBs themselves: minmax6 = 6 SoA planes of n floats (minx miny minz maxx maxy maxz). */
 int32_t b2c_set_aabbs(b2c_ctx*, int32_t n, const int32_t* uids, const float* minmax6);

@@ -54,6 +54,8 @@ final class B2C {
 
     // AxisSweep3(worldAabbMin, worldAabbMax): world box of the SAP broadphase modes
     static final MethodHandle setWorldAabb = h("b2c_set_world_aabb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    // RigidBody.checkCollideWithOverride: constraint-linked body pairs are not dispatched
+    static final MethodHandle setNoCollidePairs = h("b2c_set_no_collide_pairs", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
     // device-resident stepping: enqueue, download the pair list while the narrowphase runs, then wait for the counts
     static final MethodHandle stepDevice = h("b2c_step_device", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle syncCounts = h("b2c_sync_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -140,6 +141,9 @@ struct b2c_ctx {
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
     bool stageValid = false;
+
+    uint64_t* dNoCollide = nullptr;   // sorted keys of never-dispatched body pairs (b2c_set_no_collide_pairs)
+    uint32_t numNoCollide = 0, capNoCollide = 0;
 
     // islands + pair deltas (allocated on first use)
     int* dIslandPar = nullptr;
@@ -389,6 +393,9 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.ctr = ctx->dCtr;
     a.threshold = ctx->cfg.contact_breaking_threshold;
     a.maxPairs = (uint32_t)ctx->cfg.max_pairs;
+    a.noCollide = ctx->dNoCollide;
+    a.numNoCollide = ctx->numNoCollide;
+    a.uidBits = ctx->uidBits;
     return a;
 }
 
@@ -734,6 +741,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
+    cudaFree(ctx->dNoCollide);
     cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
     for (int i = 0; i < 2; i++) {
         if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
@@ -1042,6 +1050,31 @@ int32_t b2c_set_activation(b2c_ctx* ctx, int32_t n, const int32_t* uids, const u
         CK(cudaMemcpyAsync(ctx->B.flags, dev.data(), (size_t)ctx->nBodies, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return B2C_OK;
+}
+
+int32_t b2c_set_no_collide_pairs(b2c_ctx* ctx, int32_t n, const int32_t* uidPairs) {
+    if (!ctx || n < 0 || (n > 0 && !uidPairs)) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    std::vector<uint64_t> keys((size_t)n);
+    for (int i = 0; i < n; i++) {
+        int a = uidPairs[2 * i], b = uidPairs[2 * i + 1];
+        if (a < 1 || b < 1 || a > ctx->cfg.max_bodies || b > ctx->cfg.max_bodies || a == b) return B2C_ERR_BAD_HANDLE;
+        uint32_t lo = (uint32_t)(a < b ? a : b), hi = (uint32_t)(a < b ? b : a);
+        keys[i] = ((uint64_t)lo << ctx->uidBits) | hi;
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    CK(cudaStreamSynchronize(ctx->stream));  // a step in flight may still be reading the old list
+    if (keys.size() > ctx->capNoCollide) {
+        cudaFree(ctx->dNoCollide);
+        ctx->dNoCollide = nullptr;
+        ctx->capNoCollide = 0;
+        CK(cudaMalloc((void**)&ctx->dNoCollide, keys.size() * sizeof(uint64_t)));
+        ctx->capNoCollide = (uint32_t)keys.size();
+    }
+    if (!keys.empty()) CK(cudaMemcpy(ctx->dNoCollide, keys.data(), keys.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    ctx->numNoCollide = (uint32_t)keys.size();
     return B2C_OK;
 }
 

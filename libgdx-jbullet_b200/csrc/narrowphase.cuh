@@ -55,6 +55,9 @@ struct NpArgs {
     StepCounters* ctr;
     float threshold;
     uint32_t maxPairs;
+    const uint64_t* noCollide;    // sorted (uid0 << uidBits | uid1) keys of body pairs that are never dispatched, or null
+    uint32_t numNoCollide;
+    int uidBits;
 };
 
 __device__ __forceinline__ MView mview(const NpArgs& a, uint32_t p) {
@@ -490,7 +493,17 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
         uint8_t f0 = a.flags[b0], f1 = a.flags[b1];
         int bin = BIN_SKIP;
         // disp/CollisionDispatcher.java:198-223: skip when both are inactive
-        if ((f0 & BF_ACTIVE) || (f1 & BF_ACTIVE)) {
+        bool dispatch = (f0 & BF_ACTIVE) || (f1 & BF_ACTIVE);
+        if (dispatch && a.numNoCollide) {  // :216-218 checkCollideWith: constraint-linked bodies
+            const uint64_t k = ((uint64_t)(uint32_t)pr.x << a.uidBits) | (uint32_t)pr.y;
+            uint32_t lo = 0, hi = a.numNoCollide;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (a.noCollide[mid] < k) lo = mid + 1; else hi = mid;
+            }
+            if (lo < a.numNoCollide && a.noCollide[lo] == k) dispatch = false;
+        }
+        if (dispatch) {
             int t0 = a.shapes[a.shape[b0]].type, t1 = a.shapes[a.shape[b1]].type;
             if (t0 == SH_SPHERE && t1 == SH_SPHERE) bin = BIN_SS;
             else if ((isConvexType(t0) && t1 == SH_PLANE) || (isConvexType(t1) && t0 == SH_PLANE)) bin = BIN_CP;

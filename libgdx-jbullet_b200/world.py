@@ -202,6 +202,12 @@ class GpuCollisionWorld:
     def step_device(self):
         self._ck(self.L.b2c_step_device(self.h))
 
+    def setNoCollidePairs(self, pairs):
+        """Body pairs linked by a collision-disabling constraint (dynamics/RigidBody.java:624-639): kept in the pair cache,
+        never dispatched."""
+        p = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        self._ck(self.L.b2c_set_no_collide_pairs(self.h, len(p), _vp(p) if len(p) else None))
+
     def sync_counts(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self._ck(self.L.b2c_sync_counts(self.h, C.byref(a), C.byref(b), C.byref(c)))

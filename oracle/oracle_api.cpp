@@ -38,6 +38,15 @@ void orc_sap_quantize(void* h, const float* p, int isMax, unsigned* out3) {
     w->sapInit();
     w->sapQ.quantize(out3, V3(p[0], p[1], p[2]), isMax);
 }
+// RigidBody.checkCollideWithOverride (dynamics/RigidBody.java:624-639): body pairs that must not be dispatched
+void orc_set_no_collide_pairs(void* h, int n, const int* uidPairs) {
+    World* w = (World*)h;
+    w->noCollide.clear();
+    for (int i = 0; i < n; i++) {
+        int a = uidPairs[2 * i], b = uidPairs[2 * i + 1];
+        w->noCollide.insert(std::make_pair(a < b ? a : b, a < b ? b : a));
+    }
+}
 void orc_set_brute_force(void* h, int on) { ((World*)h)->bruteForcePairs = on != 0; }
 void orc_set_params(void* h, float breaking, float dbvtMargin, float predictedFrames) {
     World* w = (World*)h;

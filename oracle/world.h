@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <set>
 #include <vector>
 #include "bvh.h"
 #include "dbvt_literal.h"
@@ -83,6 +84,7 @@ struct World {
     std::vector<std::pair<int, int>> prevPairs;  // the list before the last calculateOverlappingPairs (pair add/remove deltas)
     std::map<std::pair<int, int>, PairState> pairState;
     std::vector<RawContact> raw;
+    std::set<std::pair<int, int>> noCollide;  // (uid0 < uid1) pairs whose bodies are linked by a collision-disabling constraint
     LDbvtBroadphase literal;
     // AxisSweep3 modes
     V3 worldAabbMin = V3(-1000.f, -1000.f, -1000.f), worldAabbMax = V3(1000.f, 1000.f, 1000.f);
@@ -494,6 +496,9 @@ struct World {
             const Body& b1 = bodies[p.second - 1];
             // disp/CollisionDispatcher.java:198-223 needsCollision
             if (!b0.active && !b1.active) continue;
+            // ... else if (!body0.checkCollideWith(body1)): bodies linked by a constraint that disables their collision
+            // (dynamics/RigidBody.java:624-639; the constraint is registered on both bodies, so the relation is symmetric)
+            if (!noCollide.empty() && noCollide.count(p)) continue;
             const Shape* s0 = &shapes[b0.shape];
             const Shape* s1 = &shapes[b1.shape];
             PairState& ps = pairState[p];

@@ -34,6 +34,7 @@ def lib():
     L.orc_create.argtypes = [C.c_int]
     L.orc_destroy.argtypes = [C.c_void_p]
     L.orc_set_brute_force.argtypes = [C.c_void_p, C.c_int]
+    L.orc_set_no_collide_pairs.argtypes = [C.c_void_p, C.c_int, i32p]
     L.orc_set_world_aabb.argtypes = [C.c_void_p, f32p, f32p]
     L.orc_sap_quantize.argtypes = [C.c_void_p, f32p, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
     L.orc_set_params.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
@@ -92,6 +93,10 @@ class OracleWorld:
             self.L.orc_set_brute_force(self.h, 1)
         if world_aabb is not None:
             self.L.orc_set_world_aabb(self.h, np.asarray(world_aabb[0], np.float32), np.asarray(world_aabb[1], np.float32))
+
+    def set_no_collide_pairs(self, pairs):
+        p = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        self.L.orc_set_no_collide_pairs(self.h, len(p), p if len(p) else np.zeros((1, 2), np.int32))
 
     def sap_quantize(self, p, is_max):
         out = np.zeros(3, dtype=np.uint32)

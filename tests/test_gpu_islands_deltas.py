@@ -83,3 +83,27 @@ def test_solver_contact_stream_matches_full_stream(gpu_pkg):
         for f in ("world_a", "world_b", "normal_on_b", "distance", "combined_friction", "combined_restitution", "life_time",
                   "src_slot", "part_id1", "index1"):
             assert q1[f].tobytes() == q2[f].tobytes(), f
+
+
+def test_constraint_linked_pairs_are_not_dispatched(gpu_pkg):
+    """disp/CollisionDispatcher.java:216-218 + dynamics/RigidBody.java:624-639: linked bodies stay in the pair cache but
+    get no algorithm; an existing manifold is left as it is (never refreshed)."""
+    sc = scenes.bin_scene(n=1500, seed=23)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    r = parity.step_and_compare(gw, ow, sc.transforms(0), sc.extent)
+    pairs = gw.pairs()
+    hdr, _ = gw.contacts()
+    touching = np.stack([hdr["pair_uid0"], hdr["pair_uid1"]], axis=1)
+    # link 40 touching pairs (reversed order on purpose) and 40 arbitrary overlapping pairs
+    rng = np.random.default_rng(1)
+    link = np.concatenate([touching[rng.choice(len(touching), 40, replace=False)][:, ::-1],
+                           pairs[rng.choice(len(pairs), 40, replace=False)]])
+    gw.setNoCollidePairs(link)
+    ow.set_no_collide_pairs(link)
+    for step in range(1, 4):
+        r2 = parity.step_and_compare(gw, ow, sc.transforms(step), sc.extent)
+    assert r2["records"] < r["records"]          # fewer detector runs than with everything dispatched
+    gw.setNoCollidePairs(np.zeros((0, 2), np.int32))
+    ow.set_no_collide_pairs(np.zeros((0, 2), np.int32))
+    r3 = parity.step_and_compare(gw, ow, sc.transforms(4), sc.extent)
+    assert r3["records"] > r2["records"]
