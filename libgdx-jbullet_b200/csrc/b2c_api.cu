@@ -45,7 +45,7 @@ struct b2c_ctx {
     cudaEvent_t evPairsReady = nullptr;   // recorded on `stream` when the broadphase of the current step is enqueued
     cudaStream_t streamClosed = nullptr;  // sphere-sphere / convex-plane bins, beside the GJK kernels
     cudaStream_t streamEpa = nullptr;     // penetration bin (few long-latency lanes), beside k_manifold_cc; high priority
-    cudaEvent_t evFork[2] = {nullptr, nullptr}, evJoin[2] = {nullptr, nullptr};
+    cudaEvent_t evFork[4] = {nullptr, nullptr, nullptr, nullptr}, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
     bool overlap = true;
     int mccBlocks = 8;                    // k_manifold_cc blocks per SM (B2C_MCC_BLOCKS)
     int epaLpw = 8;                       // active lanes per warp in the shared-memory EPA tier (B2C_EPA_LPW: 32/16/8/4)
@@ -325,11 +325,18 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     const int partLo = (int)((long long)n * ctx->partRank / ctx->partRanks);
     const int partHi = (int)((long long)n * (ctx->partRank + 1) / ctx->partRanks);
     dim3 sg((unsigned)((partHi - partLo + 255) / 256 > 0 ? (partHi - partLo + 255) / 256 : 1), 9);
-    mark(ctx, 4);
     uint32_t* rowCnt = ctx->dRowZero;
     uint32_t* rowStatus = ctx->dRowZero + ctx->nRows;
     RowMisc* rowMisc = reinterpret_cast<RowMisc*>(ctx->dRowZero + ctx->nRows + ctx->rowTiles);
     CK(cudaMemsetAsync(ctx->dRowZero, 0, ((size_t)ctx->nRows + ctx->rowTiles) * sizeof(uint32_t) + sizeof(RowMisc), s));
+    mark(ctx, 4);
+    // k_large (a few proxies against everything, latency-bound) runs beside k_sweep: both only append pairs
+    cudaStream_t sl = s;
+    if (ctx->overlap) {
+        sl = ctx->streamClosed;
+        CK(cudaEventRecord(ctx->evFork[2], s));
+        CK(cudaStreamWaitEvent(sl, ctx->evFork[2], 0));
+    }
     k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys, rowCnt,
                                (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi, ctx->sap.enabled ? ctx->B.leafMin : nullptr,
                                ctx->sap.enabled ? ctx->B.leafMax : nullptr);
@@ -339,20 +346,35 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     const int lhint = ctx->stats.large_proxies > 16 ? ctx->stats.large_proxies : 16;
     dim3 lg(gridFor(perWorld, 256, 64), (unsigned)(lhint < 8192 ? lhint : 8192));
     mark(ctx, 5);
-    k_large<<<lg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
+    k_large<<<lg, 256, 0, sl>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
                                ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi,
                                ctx->partRank, ctx->sap.enabled ? ctx->B.leafMin : nullptr, ctx->sap.enabled ? ctx->B.leafMax : nullptr);
+    if (ctx->overlap) {
+        CK(cudaEventRecord(ctx->evJoin[2], sl));
+        CK(cudaStreamWaitEvent(s, ctx->evJoin[2], 0));
+    }
     mark(ctx, 6);
     // canonical (uid0, uid1) order: rows keyed by uid0 (pair_rows.cuh); rowStart is also the "first pair of uid0" table
     uint32_t* rowStart = ctx->dPairFirst[cur];
     k_row_scan<<<ctx->rowTiles, 256, 0, s>>>(rowCnt, ctx->nRows, rowStart, rowStatus, rowMisc, ctx->dBigRows, ctx->dNumPairs[cur]);
     k_row_scatter<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys, ctx->dCtr, (uint32_t)ctx->cfg.max_pairs,
                                                                              ctx->uidBits, rowStart, ctx->dCsr);
+    // the long rows (a handful of blocks with serial phases) are ordered beside the short ones
+    cudaStream_t sb = s;
+    if (ctx->overlap) {
+        sb = ctx->streamClosed;
+        CK(cudaEventRecord(ctx->evFork[3], s));
+        CK(cudaStreamWaitEvent(sb, ctx->evFork[3], 0));
+    }
+    k_row_sort_big<<<148, BIG_THREADS, 0, sb>>>(rowStart, ctx->dBigRows, rowMisc, ctx->dCsr, ctx->uidBits, ctx->dPairs,
+                                                ctx->dSortedKeys[cur]);
     k_row_rank<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dPairKeys, ctx->dCtr, (uint32_t)ctx->cfg.max_pairs,
                                                                           ctx->uidBits, rowStart, ctx->dCsr, ctx->dPairs,
                                                                           ctx->dSortedKeys[cur]);
-    k_row_sort_big<<<148, BIG_THREADS, 0, s>>>(rowStart, ctx->dBigRows, rowMisc, ctx->dCsr, ctx->uidBits, ctx->dPairs,
-                                               ctx->dSortedKeys[cur]);
+    if (ctx->overlap) {
+        CK(cudaEventRecord(ctx->evJoin[3], sb));
+        CK(cudaStreamWaitEvent(s, ctx->evJoin[3], 0));
+    }
     mark(ctx, 7);
     // manifolds follow their pair into the new list (done here so a step without dispatch keeps them too)
     k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
@@ -427,7 +449,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         unsigned bg = ctx->binTiles < 148u * 4u ? ctx->binTiles : 148u * 4u;
         k_bin_scatter<<<bg ? bg : 1, 256, 0, s>>>(a);
     }
-    ctx->launches += 1;
+    ctx->launches += 3;  // k_clear_np_counters, k_classify, k_bin_scatter (kernels only; memsets are not counted)
     mark(ctx, 9);
     // the closed-form bins touch only their own pairs' records: they run beside the GJK kernels
     cudaStream_t sc = s;
@@ -437,7 +459,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         CK(cudaStreamWaitEvent(sc, ctx->evFork[0], 0));
     }
     k_sphere_sphere<<<148 * 4, 256, 0, sc>>>(a);
-    ctx->launches += 5;
+    ctx->launches += 1;  // k_sphere_sphere
     if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, sc>>>(a); ctx->launches++; }
     if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[0], sc));
     mark(ctx, 10);
@@ -621,7 +643,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         CKC(cudaEventCreateWithFlags(&ctx->evPairsReady, cudaEventDisableTiming));
         CKC(cudaStreamCreateWithPriority(&ctx->streamClosed, cudaStreamNonBlocking, prLo));
         CKC(cudaStreamCreateWithPriority(&ctx->streamEpa, cudaStreamNonBlocking, prHi));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 4; i++) {
             CKC(cudaEventCreateWithFlags(&ctx->evFork[i], cudaEventDisableTiming));
             CKC(cudaEventCreateWithFlags(&ctx->evJoin[i], cudaEventDisableTiming));
         }
@@ -743,7 +765,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
     cudaFree(ctx->dNoCollide);
     cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 4; i++) {
         if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
         if (ctx->evJoin[i]) cudaEventDestroy(ctx->evJoin[i]);
     }

@@ -1,0 +1,11 @@
+#!/bin/bash
+# compute-sanitizer over a small slice of the GPU parity tests (run under gpurun): memcheck (out-of-bounds / misaligned
+# accesses), then racecheck (shared-memory hazards in the radix, row, bin and stager kernels).
+set -u
+mkdir -p gpurun_out
+T="tests/test_gpu_parity.py::test_c1_stack_parity tests/test_gpu_parity.py::test_c3_terrain_mesh_parity tests/test_gpu_pair_rows.py::test_rows_around_the_short_long_threshold tests/test_gpu_sap.py::test_sap_default_world_box_and_batched_worlds tests/test_gpu_islands_deltas.py::test_deltas_and_islands_tight_mode_stack tests/test_gpu_partitioned.py::test_partitioned_bin_world_with_large_statics"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest $T -m gpu -x -q > gpurun_out/sanitize_memcheck.log 2>&1
+echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|Misaligned" gpurun_out/sanitize_memcheck.log | head -20
+T2="tests/test_gpu_parity.py::test_c1_stack_parity tests/test_gpu_pair_rows.py::test_rows_around_the_short_long_threshold"
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 --print-limit 20 python -m pytest $T2 -m gpu -x -q > gpurun_out/sanitize_racecheck.log 2>&1
+echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed|hazard" gpurun_out/sanitize_racecheck.log | head -20
