@@ -40,6 +40,16 @@ public:
         if (n) check(b2c_get_pairs(ctx, reinterpret_cast<int32_t*>(pairs.data()), n, &n), ctx);
         return pairs;
     }
+    // The add / remove events the reference's cache sends to OverlappingPairCallback / GhostPairCallback
+    // (bp/HashedOverlappingPairCache.java:135-137, 323-325) for the last calculateOverlappingPairs.
+    void getPairDeltas(std::vector<BroadphasePair>& added, std::vector<BroadphasePair>& removed) {
+        int32_t na = 0, nr = 0;
+        check(b2c_get_pair_deltas(ctx, nullptr, 0, nullptr, 0, &na, &nr), ctx);
+        added.resize((size_t)na);
+        removed.resize((size_t)nr);
+        check(b2c_get_pair_deltas(ctx, na ? reinterpret_cast<int32_t*>(added.data()) : nullptr, na,
+                                  nr ? reinterpret_cast<int32_t*>(removed.data()) : nullptr, nr, &na, &nr), ctx);
+    }
     int num = 0;
 private:
     b2c_ctx* ctx;
@@ -136,6 +146,17 @@ public:
         updateAabbs();
         broadphase->calculateOverlappingPairs(dispatcher);
         dispatcher->dispatchAllCollisionPairs(broadphase->getOverlappingPairCache(), nullptr, dispatcher);
+    }
+    // SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110)
+    int32_t computeIslands(std::vector<int32_t>& tags) {
+        int32_t n = 0;
+        tags.resize((size_t)numBodies);
+        check(b2c_compute_islands(ctx, tags.data(), numBodies, &n), ctx);
+        return n;
+    }
+    // RigidBody.checkCollideWithOverride (dynamics/RigidBody.java:624-639): constraint-linked bodies are not dispatched
+    void setNoCollidePairs(const std::vector<BroadphasePair>& links) {
+        check(b2c_set_no_collide_pairs(ctx, (int32_t)links.size(), links.empty() ? nullptr : &links[0].proxy0), ctx);
     }
     GpuBroadphase* getBroadphase() { return broadphase; }
     GpuPairCache* getPairCache() { return broadphase->getOverlappingPairCache(); }

@@ -26,5 +26,11 @@ int main() {
     const b2c_manifold& m = world.getDispatcher()->getManifoldByIndexInternal(0);
     std::printf("m0 bodies %d %d contacts %d normal %.3f %.3f %.3f depth %.6f\n", m.body0, m.body1, m.num_contacts,
                 m.points[0].normal_on_b[0], m.points[0].normal_on_b[1], m.points[0].normal_on_b[2], m.points[0].distance);
+    std::vector<BroadphasePair> added, removed;
+    world.getPairCache()->getPairDeltas(added, removed);
+    std::vector<int32_t> tags;
+    int islands = world.computeIslands(tags);
+    std::printf("deltas +%d -%d islands %d tags %d %d %d %d\n", (int)added.size(), (int)removed.size(), islands, tags[0], tags[1], tags[2],
+                tags[3]);
     return 0;
 }

@@ -33,3 +33,5 @@ def test_host_mirror_runs_reference_call_sequence(gpu_pkg):
     assert lines[1:4] == ["pair 1 2", "pair 2 3", "pair 3 4"]
     # ground (uid 1) vs lowest box (uid 2): normal on B points from the box (B) down to the ground (A)
     assert "contacts 1 normal 0.000 -1.000 0.000" in lines[4]
+    # first step: all three pairs are new; the three stacked boxes form one island (tag = smallest body index), ground is static
+    assert lines[5] == "deltas +3 -0 islands 1 tags -1 1 1 1"
