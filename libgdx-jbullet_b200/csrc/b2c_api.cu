@@ -50,6 +50,15 @@ struct b2c_ctx {
     int mccBlocks = 8;                    // k_manifold_cc blocks per SM (B2C_MCC_BLOCKS)
     int epaLpw = 8;                       // active lanes per warp in the shared-memory EPA tier (B2C_EPA_LPW: 32/16/8/4)
     int epaHint = -1;                     // -1 unknown, 0 small penetration bin (shared-memory tier), 1 large (local-memory tier)
+    // CUDA graphs of the whole step (b2c_step_device), one per launch signature
+    struct StepGraph {
+        uint64_t sig[4];
+        cudaGraphExec_t exec;
+        int launches;
+    };
+    std::vector<StepGraph> graphs;
+    bool useGraphs = true;                // B2C_GRAPH=0 disables
+    bool capturing = false;
     bool timeline = false;                // B2C_TIMELINE=1: print where the side-stream kernels ran (debug)
     cudaEvent_t tl[6] = {};
     std::string err;
@@ -79,7 +88,8 @@ struct b2c_ctx {
     uint8_t* dExtMask = nullptr;
     bool extPending = false;
     bool aabbPending = false;
-    int step = 0;
+    int step = 0;                // host mirror of *dStep (the kernels read the device copy)
+    int* dStep = nullptr;
 
     // broadphase
     uint32_t* dKeys[2] = {nullptr, nullptr};
@@ -278,7 +288,7 @@ int32_t runAabbKernel(b2c_ctx* ctx, bool forPairs) {
     const float* staging = ctx->stagingCount > 0 ? ctx->dStaging : nullptr;
     k_aabb<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
         ctx->B, ctx->dShapes, n, staging, ctx->cfg.max_bodies, ctx->stagingCount, ctx->extPending ? ctx->dExtAabb : nullptr,
-        ctx->dExtMask, ctx->cfg.max_bodies, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.contact_breaking_threshold,
+        ctx->dExtMask, ctx->cfg.max_bodies, ctx->cfg.broadphase_mode, ctx->dStep, ctx->cfg.contact_breaking_threshold,
         ctx->cfg.dbvt_margin, ctx->cfg.dbvt_predicted_frames, ctx->aabbPending ? 1 : 0, ctx->dCtr, ctx->sap);
     ctx->launches++;
     ctx->stagingCount = 0;
@@ -305,14 +315,16 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
         CK(cudaMemsetAsync(ctx->dNumPairs[cur], 0, sizeof(uint32_t), s));
         CK(cudaEventRecord(ctx->evPairsReady, s));
         ctx->step++;
+        CK(cudaMemcpyAsync(ctx->dStep, &ctx->step, sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
         ctx->pairsValid = true;
         return B2C_OK;
     }
     unsigned nb = (n + 255) / 256;
     mark(ctx, 1);
-    k_bounds<<<nb, 256, 0, s>>>(ctx->B, n, ctx->cfg.broadphase_mode, ctx->step, ctx->cfg.num_worlds,
+    k_bounds<<<nb, 256, 0, s>>>(ctx->B, n, ctx->cfg.broadphase_mode, ctx->dStep, ctx->cfg.num_worlds,
                                 ctx->maxRows - ctx->cfg.num_worlds, ctx->dCtr, ctx->dGrid);
-    k_keys<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0]);
+    k_keys<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dStep);
     int rowBits = bitsFor((uint32_t)ctx->maxRows + 2u);
     mark(ctx, 2);
     ctx->sortBodies.launches = 0;
@@ -383,7 +395,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
                                                                       ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr);
     ctx->launches += 10 + ctx->sortBodies.launches;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->evPairsReady, s));
+    CK(cudaEventRecordWithFlags(ctx->evPairsReady, s, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     ctx->step++;
     ctx->pairsValid = true;
     return B2C_OK;
@@ -484,10 +496,8 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     {
         static_assert(EPA_SMALL_STRIDE % 8 == 4, "lane chunks need an odd word stride");
         const int smem = EPA_BLOCK * EPA_SMALL_STRIDE;
-        cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         // blocks of two kernels share an SM only when both run with the same L1/shared split: k_manifold_cc has to ask for
         // the split the shared-memory EPA pools force, or it would wait for every EPA block to retire
-        if (ctx->overlap) cudaFuncSetAttribute(k_manifold_cc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (ctx->timeline) cudaEventRecord(ctx->tl[0], se);
         // which variant: the host knows the size of the previous step's bin (when it has read the counters); the kernels
         // handle any count either way, so a stale hint only costs time.  Without a hint both are launched and the device decides.
@@ -498,7 +508,6 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     }
     {
         const int smem1 = (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch);
-        cudaFuncSetAttribute(k_epa<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
         k_epa<1><<<EPA_GRID2, EPA_BLOCK2, smem1, se>>>(a, g, 0, 32);  // retry tier + the manifolds of the whole bin
     }
     if (ctx->timeline) cudaEventRecord(ctx->tl[2], se);
@@ -647,6 +656,11 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
             CKC(cudaEventCreateWithFlags(&ctx->evFork[i], cudaEventDisableTiming));
             CKC(cudaEventCreateWithFlags(&ctx->evJoin[i], cudaEventDisableTiming));
         }
+        // one-time kernel attributes (kept out of the per-step path so that it can be captured into a graph)
+        cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPA_BLOCK * EPA_SMALL_STRIDE);
+        cudaFuncSetAttribute(k_epa<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch));
+        const char* gr = getenv("B2C_GRAPH");
+        ctx->useGraphs = !(gr && gr[0] == '0');
         const char* e = getenv("B2C_OVERLAP");  // measurement knob: 0 = everything on one stream
         ctx->overlap = !(e && e[0] == '0');
         const char* mb = getenv("B2C_MCC_BLOCKS");
@@ -672,6 +686,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->B.leafMax, N));
     CKC(dalloc(&ctx->B.lastSet, N));
     CKC(dalloc(&ctx->B.material, N));
+    CKC(dalloc(&ctx->dStep, (size_t)1));
     CKC(dalloc(&ctx->dStaging, 12 * N));
     CKC(cudaMallocHost((void**)&ctx->hStagingPinned, 12 * N * sizeof(float)));
     CKC(dalloc(&ctx->dExtAabb, 6 * N));
@@ -743,11 +758,14 @@ void b2c_destroy(b2c_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
     cudaFree(ctx->dShapes); cudaFree(ctx->dHullPts); cudaFree(ctx->dMeshes);
     for (auto& m : ctx->meshes) { cudaFree(m.nodes); cudaFree(m.verts); cudaFree(m.idx); }
     cudaFree(ctx->B.xf4); cudaFree(ctx->B.shape); cudaFree(ctx->B.filt); cudaFree(ctx->B.flags); cudaFree(ctx->B.world);
     cudaFree(ctx->B.effMin); cudaFree(ctx->B.effMax); cudaFree(ctx->B.leafMin); cudaFree(ctx->B.leafMax);
     cudaFree(ctx->B.lastSet); cudaFree(ctx->B.material);
+    cudaFree(ctx->dStep);
     cudaFree(ctx->dStaging); cudaFreeHost(ctx->hStagingPinned); cudaFree(ctx->dExtAabb); cudaFree(ctx->dExtMask);
     for (int i = 0; i < 2; i++) {
         cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dSortedKeys[i]);
@@ -1202,18 +1220,88 @@ int32_t b2c_transforms_written(b2c_ctx* ctx, int32_t n) {
     return B2C_OK;
 }
 
+// Everything that decides WHAT enqueueBroadphase + enqueueNarrowphase launch (pointers that ping-pong, launch shapes that
+// follow host hints, optional kernels).  Two steps with the same signature enqueue identical work, so the captured graph
+// of the first serves the second.
+static void stepSignature(const b2c_ctx* ctx, uint64_t sig[4]) {
+    const int lhint = ctx->stats.large_proxies > 16 ? ctx->stats.large_proxies : 16;
+    sig[0] = ((uint64_t)(uint32_t)ctx->nBodies << 32) | (uint32_t)ctx->stagingCount;
+    sig[1] = ((uint64_t)(uint32_t)(ctx->cur & 1)) | ((uint64_t)(ctx->extPending ? 1 : 0) << 1) | ((uint64_t)(ctx->hasPlane ? 1 : 0) << 2) |
+             ((uint64_t)(ctx->hasMesh ? 1 : 0) << 3) | ((uint64_t)(ctx->overlap ? 1 : 0) << 4) | ((uint64_t)(uint32_t)(ctx->epaHint + 1) << 8) |
+             ((uint64_t)(uint32_t)lhint << 16) | ((uint64_t)(uint32_t)ctx->partRank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
+    sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide;
+    sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8);
+}
+
+static void dropStepGraphs(b2c_ctx* ctx) {
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
+// One full collision step on the ctx stream.  The step is ~28 short kernels plus memsets and side-stream joins; issued one
+// by one the host falls behind the device in the broadphase (5-15 us kernels), so the sequence is captured once per
+// launch signature into a CUDA graph and replayed with a single cudaGraphLaunch.
 int32_t b2c_step_device(b2c_ctx* ctx) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     ctx->launches = 0;
     ctx->aabbPending = true;
     cudaStream_t s = ctx->stream;
+    const bool graphable = ctx->useGraphs && !ctx->prof && !ctx->timeline && ctx->nBodies > 0;
+    if (!graphable) {
+        CK(cudaEventRecord(ctx->ev[0], s));
+        int32_t rc = enqueueBroadphase(ctx);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev[2], s));
+        rc = enqueueNarrowphase(ctx);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev[3], s));
+        ctx->stats.kernel_launches = ctx->launches;
+        return B2C_OK;
+    }
+    int32_t rc = uploadShapes(ctx);  // not capturable (synchronous copy); a no-op unless shapes were registered since
+    if (rc) return rc;
+    uint64_t sig[4];
+    stepSignature(ctx, sig);
+    b2c_ctx::StepGraph* hit = nullptr;
+    for (auto& g : ctx->graphs)
+        if (g.sig[0] == sig[0] && g.sig[1] == sig[1] && g.sig[2] == sig[2] && g.sig[3] == sig[3]) { hit = &g; break; }
     CK(cudaEventRecord(ctx->ev[0], s));
-    int32_t rc = enqueueBroadphase(ctx);
-    if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[2], s));
-    rc = enqueueNarrowphase(ctx);
-    if (rc) return rc;
+    if (hit) {
+        // the host-side state transitions enqueueBroadphase / enqueueNarrowphase would have made
+        ctx->stagingCount = 0;
+        ctx->extPending = false;
+        ctx->aabbPending = false;
+        ctx->cur ^= 1;
+        ctx->step++;
+        ctx->pairsValid = true;
+        ctx->stageValid = false;
+        ctx->launches = hit->launches;
+        CK(cudaGraphLaunch(hit->exec, s));
+    } else {
+        if (ctx->graphs.size() >= 16) dropStepGraphs(ctx);
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        ctx->capturing = true;
+        rc = enqueueBroadphase(ctx);
+        if (rc == B2C_OK) {
+            cudaEventRecordWithFlags(ctx->ev[2], s, cudaEventRecordExternal);
+            rc = enqueueNarrowphase(ctx);
+        }
+        ctx->capturing = false;
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return B2C_ERR_CUDA; }
+        b2c_ctx::StepGraph g;
+        memcpy(g.sig, sig, sizeof(sig));
+        g.launches = ctx->launches;
+        g.exec = nullptr;
+        ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return B2C_ERR_CUDA; }
+        ctx->graphs.push_back(g);
+        CK(cudaGraphLaunch(g.exec, s));
+    }
     CK(cudaEventRecord(ctx->ev[3], s));
     ctx->stats.kernel_launches = ctx->launches;
     return B2C_OK;

@@ -173,7 +173,9 @@ __device__ __forceinline__ void setAabbState(const BodyArrays& B, int i, f3 mn, 
 __global__ void __launch_bounds__(256)
 k_aabb(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, const float* __restrict__ staging, int stagingStride,
        int stagingCount, const float* __restrict__ extAabb, const uint8_t* __restrict__ extMask, int extStride, int mode,
-       int step, float threshold, float dbvtMargin, float predicted, int doUpdate, StepCounters* ctr, SapParams sp) {
+       const int* __restrict__ stepPtr, float threshold, float dbvtMargin, float predicted, int doUpdate, StepCounters* ctr,
+       SapParams sp) {
+    const int step = *stepPtr;  // device-resident step index: the same captured launch serves every step
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float extY = 0.f, extZ = 0.f;
     if (i < n) {
@@ -250,7 +252,9 @@ k_aabb(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, const float* __
 // k_bounds: classify large proxies (static and larger than the dynamic cell, or non-finite), reduce the
 // min-corner bounds of the gridded ones; the last block to finish derives the grid.
 __global__ void __launch_bounds__(256)
-k_bounds(BodyArrays B, int n, int mode, int step, int numWorlds, int maxRows, StepCounters* ctr, GridParams* grid) {
+k_bounds(BodyArrays B, int n, int mode, const int* __restrict__ stepPtr, int numWorlds, int maxRows, StepCounters* ctr,
+         GridParams* grid) {
+    const int step = *stepPtr;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     // gridded proxies have extents <= the largest dynamic extent (limit); the cell is 5 % larger, which
     // absorbs the rounding of the row computation so overlapping proxies always sit in adjacent rows
@@ -365,8 +369,9 @@ __device__ __forceinline__ uint32_t quantX(float x, float x0, float invX) {
 // k_keys: 32-bit key and payload for every slot.
 __global__ void __launch_bounds__(256)
 k_keys(BodyArrays B, int n, const StepCounters* __restrict__ ctr, const GridParams* __restrict__ grid,
-       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* stepPtr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *stepPtr = *stepPtr + 1;  // k_aabb and k_bounds of this step have read it (stream order); next step sees +1
     if (i >= n) return;
     GridParams g = *grid;
     // same large criterion as k_bounds

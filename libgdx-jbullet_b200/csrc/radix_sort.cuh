@@ -275,6 +275,9 @@ struct RadixSorter {
         uint32_t tile = RS_THREADS * items;
         uint32_t numTiles = (cap + tile - 1) / tile + 1;
         statusWordsPerPass = (size_t)numTiles * 256;
+        // dynamic shared memory of the wide tiles (> 48 KB needs the opt-in), set once so that sort() only launches
+        cudaFuncSetAttribute(rs_pass<uint32_t, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * RS_THREADS * 16);
+        cudaFuncSetAttribute(rs_pass<uint32_t, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * RS_THREADS * 8);
         cudaError_t e = cudaMalloc(&st, sizeof(RadixState));
         if (e != cudaSuccess) return e;
         return cudaMalloc(&status, statusWordsPerPass * RS_MAX_PASSES * sizeof(uint32_t));
@@ -313,10 +316,8 @@ struct RadixSorter {
         for (int p = firstPass; p < npass; p++) {
             uint32_t* stp = status + statusWordsPerPass * p;
             if (items == 16) {
-                cudaFuncSetAttribute(rs_pass<K, HAS_VAL, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
                 rs_pass<K, HAS_VAL, 16><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
             } else if (items == 8) {
-                cudaFuncSetAttribute(rs_pass<K, HAS_VAL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
                 rs_pass<K, HAS_VAL, 8><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
             } else {
                 rs_pass<K, HAS_VAL, 4><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
