@@ -570,6 +570,90 @@ int32_t readCounters(b2c_ctx* ctx) {
 
 }  // namespace
 
+// Everything that decides WHAT enqueueBroadphase / enqueueNarrowphase launch (pointers that ping-pong, launch shapes that
+// follow host hints, optional kernels).  Two calls with the same signature enqueue identical work, so the captured graph
+// of the first serves the second.  kind: 0 = broadphase + narrowphase (one step), 1 = broadphase, 2 = narrowphase.
+static void stepSignature(const b2c_ctx* ctx, int kind, uint64_t sig[4]) {
+    const int lhint = ctx->stats.large_proxies > 16 ? ctx->stats.large_proxies : 16;
+    sig[0] = ((uint64_t)(uint32_t)ctx->nBodies << 32) | (uint32_t)ctx->stagingCount;
+    sig[1] = ((uint64_t)(uint32_t)(ctx->cur & 1)) | ((uint64_t)(ctx->extPending ? 1 : 0) << 1) | ((uint64_t)(ctx->hasPlane ? 1 : 0) << 2) |
+             ((uint64_t)(ctx->hasMesh ? 1 : 0) << 3) | ((uint64_t)(ctx->overlap ? 1 : 0) << 4) | ((uint64_t)(ctx->aabbPending ? 1 : 0) << 5) |
+             ((uint64_t)(uint32_t)kind << 6) | ((uint64_t)(uint32_t)(ctx->epaHint + 1) << 8) | ((uint64_t)(uint32_t)lhint << 16) |
+             ((uint64_t)(uint32_t)ctx->partRank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
+    sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide;
+    sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8);
+}
+
+static void dropStepGraphs(b2c_ctx* ctx) {
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
+// Enqueue the broadphase and/or the narrowphase on the ctx stream.  A step is ~28 short kernels plus memsets and
+// side-stream joins; issued one by one the host falls behind the device in the broadphase (5-15 us kernels), so the
+// sequence is captured once per launch signature into a CUDA graph and replayed with a single cudaGraphLaunch.
+static int32_t enqueuePhases(b2c_ctx* ctx, int kind) {
+    cudaStream_t s = ctx->stream;
+    const bool broad = kind != 2, narrow = kind != 1;
+    if (narrow && !broad && !ctx->pairsValid) {
+        ctx->err = "dispatch_all_pairs before calculate_overlapping_pairs";
+        return B2C_ERR_STATE;
+    }
+    const bool graphable = ctx->useGraphs && !ctx->prof && !ctx->timeline && ctx->nBodies > 0;
+    if (!graphable) {
+        int32_t rc = B2C_OK;
+        if (broad) rc = enqueueBroadphase(ctx);
+        if (rc) return rc;
+        if (kind == 0) CK(cudaEventRecord(ctx->ev[2], s));
+        if (narrow) rc = enqueueNarrowphase(ctx);
+        return rc;
+    }
+    int32_t rc = uploadShapes(ctx);  // not capturable (synchronous copy); a no-op unless shapes were registered since
+    if (rc) return rc;
+    uint64_t sig[4];
+    stepSignature(ctx, kind, sig);
+    b2c_ctx::StepGraph* hit = nullptr;
+    for (auto& g : ctx->graphs)
+        if (g.sig[0] == sig[0] && g.sig[1] == sig[1] && g.sig[2] == sig[2] && g.sig[3] == sig[3]) { hit = &g; break; }
+    if (hit) {
+        // the host-side state transitions the enqueue functions would have made
+        if (broad) {
+            ctx->stagingCount = 0;
+            ctx->extPending = false;
+            ctx->aabbPending = false;
+            ctx->cur ^= 1;
+            ctx->step++;
+            ctx->pairsValid = true;
+        }
+        ctx->stageValid = false;
+        ctx->launches += hit->launches;
+        CK(cudaGraphLaunch(hit->exec, s));
+        return B2C_OK;
+    }
+    if (ctx->graphs.size() >= 24) dropStepGraphs(ctx);
+    const int launchesBefore = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    if (broad) rc = enqueueBroadphase(ctx);
+    if (rc == B2C_OK && kind == 0) cudaEventRecordWithFlags(ctx->ev[2], s, cudaEventRecordExternal);
+    if (rc == B2C_OK && narrow) rc = enqueueNarrowphase(ctx);
+    ctx->capturing = false;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return B2C_ERR_CUDA; }
+    b2c_ctx::StepGraph g;
+    memcpy(g.sig, sig, sizeof(sig));
+    g.launches = ctx->launches - launchesBefore;
+    g.exec = nullptr;
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return B2C_ERR_CUDA; }
+    ctx->graphs.push_back(g);
+    CK(cudaGraphLaunch(g.exec, s));
+    return B2C_OK;
+}
+
 static void sapConfigure(b2c_ctx* ctx, const float mn[3], const float mx[3]) {
     const bool wide = ctx->cfg.broadphase_mode == B2C_BP_SAP32;
     const int sentinel = wide ? 0x7fffffff : 0xffff;  // bp/AxisSweep3_32.java:49, bp/AxisSweep3.java:52
@@ -1161,7 +1245,7 @@ int32_t b2c_calculate_overlapping_pairs(b2c_ctx* ctx, int32_t* numPairs) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     ctx->launches = 0;
-    int32_t rc = enqueueBroadphase(ctx);
+    int32_t rc = enqueuePhases(ctx, 1);
     if (rc) return rc;
     rc = readCounters(ctx);
     if (numPairs) *numPairs = ctx->lastPairs;
@@ -1194,7 +1278,7 @@ int32_t b2c_dispatch_all_pairs(b2c_ctx* ctx, int32_t* numManifolds, int32_t* num
     if (!ctx) return B2C_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     int before = ctx->launches;
-    int32_t rc = enqueueNarrowphase(ctx);
+    int32_t rc = enqueuePhases(ctx, 2);
     if (rc) return rc;
     rc = readCounters(ctx);
     if (numManifolds) *numManifolds = ctx->lastManifolds;
@@ -1220,88 +1304,15 @@ int32_t b2c_transforms_written(b2c_ctx* ctx, int32_t n) {
     return B2C_OK;
 }
 
-// Everything that decides WHAT enqueueBroadphase + enqueueNarrowphase launch (pointers that ping-pong, launch shapes that
-// follow host hints, optional kernels).  Two steps with the same signature enqueue identical work, so the captured graph
-// of the first serves the second.
-static void stepSignature(const b2c_ctx* ctx, uint64_t sig[4]) {
-    const int lhint = ctx->stats.large_proxies > 16 ? ctx->stats.large_proxies : 16;
-    sig[0] = ((uint64_t)(uint32_t)ctx->nBodies << 32) | (uint32_t)ctx->stagingCount;
-    sig[1] = ((uint64_t)(uint32_t)(ctx->cur & 1)) | ((uint64_t)(ctx->extPending ? 1 : 0) << 1) | ((uint64_t)(ctx->hasPlane ? 1 : 0) << 2) |
-             ((uint64_t)(ctx->hasMesh ? 1 : 0) << 3) | ((uint64_t)(ctx->overlap ? 1 : 0) << 4) | ((uint64_t)(uint32_t)(ctx->epaHint + 1) << 8) |
-             ((uint64_t)(uint32_t)lhint << 16) | ((uint64_t)(uint32_t)ctx->partRank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
-    sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide;
-    sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8);
-}
-
-static void dropStepGraphs(b2c_ctx* ctx) {
-    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
-    ctx->graphs.clear();
-}
-
-// One full collision step on the ctx stream.  The step is ~28 short kernels plus memsets and side-stream joins; issued one
-// by one the host falls behind the device in the broadphase (5-15 us kernels), so the sequence is captured once per
-// launch signature into a CUDA graph and replayed with a single cudaGraphLaunch.
 int32_t b2c_step_device(b2c_ctx* ctx) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     ctx->launches = 0;
     ctx->aabbPending = true;
     cudaStream_t s = ctx->stream;
-    const bool graphable = ctx->useGraphs && !ctx->prof && !ctx->timeline && ctx->nBodies > 0;
-    if (!graphable) {
-        CK(cudaEventRecord(ctx->ev[0], s));
-        int32_t rc = enqueueBroadphase(ctx);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev[2], s));
-        rc = enqueueNarrowphase(ctx);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev[3], s));
-        ctx->stats.kernel_launches = ctx->launches;
-        return B2C_OK;
-    }
-    int32_t rc = uploadShapes(ctx);  // not capturable (synchronous copy); a no-op unless shapes were registered since
-    if (rc) return rc;
-    uint64_t sig[4];
-    stepSignature(ctx, sig);
-    b2c_ctx::StepGraph* hit = nullptr;
-    for (auto& g : ctx->graphs)
-        if (g.sig[0] == sig[0] && g.sig[1] == sig[1] && g.sig[2] == sig[2] && g.sig[3] == sig[3]) { hit = &g; break; }
     CK(cudaEventRecord(ctx->ev[0], s));
-    if (hit) {
-        // the host-side state transitions enqueueBroadphase / enqueueNarrowphase would have made
-        ctx->stagingCount = 0;
-        ctx->extPending = false;
-        ctx->aabbPending = false;
-        ctx->cur ^= 1;
-        ctx->step++;
-        ctx->pairsValid = true;
-        ctx->stageValid = false;
-        ctx->launches = hit->launches;
-        CK(cudaGraphLaunch(hit->exec, s));
-    } else {
-        if (ctx->graphs.size() >= 16) dropStepGraphs(ctx);
-        cudaGraph_t graph = nullptr;
-        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        ctx->capturing = true;
-        rc = enqueueBroadphase(ctx);
-        if (rc == B2C_OK) {
-            cudaEventRecordWithFlags(ctx->ev[2], s, cudaEventRecordExternal);
-            rc = enqueueNarrowphase(ctx);
-        }
-        ctx->capturing = false;
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return B2C_ERR_CUDA; }
-        b2c_ctx::StepGraph g;
-        memcpy(g.sig, sig, sizeof(sig));
-        g.launches = ctx->launches;
-        g.exec = nullptr;
-        ce = cudaGraphInstantiate(&g.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return B2C_ERR_CUDA; }
-        ctx->graphs.push_back(g);
-        CK(cudaGraphLaunch(g.exec, s));
-    }
+    int32_t rc = enqueuePhases(ctx, 0);
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[3], s));
     ctx->stats.kernel_launches = ctx->launches;
     return B2C_OK;
@@ -1590,7 +1601,7 @@ int32_t b2c_mgpu_broadphase(b2c_ctx* ctx) {
     ctx->launches = 0;
     ctx->aabbPending = true;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int32_t rc = enqueueBroadphase(ctx);
+    int32_t rc = enqueuePhases(ctx, 1);
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     return rc;
 }
@@ -1664,7 +1675,7 @@ int32_t b2c_mgpu_import_arrival_slots(b2c_ctx* ctx, const void* slots, int32_t n
 int32_t b2c_mgpu_narrowphase(b2c_ctx* ctx) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
-    int32_t rc = enqueueNarrowphase(ctx);
+    int32_t rc = enqueuePhases(ctx, 2);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->stats.kernel_launches = ctx->launches;
