@@ -98,6 +98,7 @@ struct b2c_ctx {
     float4* dSmin = nullptr;
     float4* dSmax = nullptr;
     uint32_t* dSrow = nullptr;
+    uint32_t* dScyz = nullptr;        // (cy << 16 | cz) of every sorted proxy's grid row
     uint32_t* dRowStart = nullptr;
     int maxRows = 0;
     GridParams* dGrid = nullptr;
@@ -332,7 +333,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
                                          12 + rowBits, ctx->dSide, s);
     mark(ctx, 3);
     k_gather<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->dSide, ctx->dGrid,
-                                ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart);
+                                ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dScyz);
     // this rank's slice of the sorted proxy list (the whole list when the world is not partitioned)
     const int partLo = (int)((long long)n * ctx->partRank / ctx->partRanks);
     const int partHi = (int)((long long)n * (ctx->partRank + 1) / ctx->partRanks);
@@ -351,7 +352,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     }
     k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys, rowCnt,
                                (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi, ctx->sap.enabled ? ctx->B.leafMin : nullptr,
-                               ctx->sap.enabled ? ctx->B.leafMax : nullptr);
+                               ctx->sap.enabled ? ctx->B.leafMax : nullptr, ctx->dScyz);
     // one block column per large proxy (static planes, meshes, big statics; one floor per world in batched scenes): the
     // host sizes the grid from the last count it has read, the kernel strides over whatever there is
     const unsigned perWorld = (unsigned)(n / ctx->cfg.num_worlds + 1);
@@ -795,6 +796,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dSmin, N));
     CKC(dalloc(&ctx->dSmax, N));
     CKC(dalloc(&ctx->dSrow, N));
+    CKC(dalloc(&ctx->dScyz, N));
     ctx->maxRows = (int)(2 * N + 64 > (size_t)(64 * cfg->num_worlds) ? 2 * N + 64 : (size_t)(64 * cfg->num_worlds));
     if (ctx->maxRows > (1 << 20) - 4) ctx->maxRows = (1 << 20) - 4;  // the row shares a 32-bit key with 12 bits of x
     if ((long long)cfg->num_worlds * 5 > ctx->maxRows) return fail(B2C_ERR_BAD_ARG);
@@ -855,7 +857,7 @@ void b2c_destroy(b2c_ctx* ctx) {
         cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dSortedKeys[i]);
         cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dMHdr[i]); cudaFree(ctx->dMPts[i]); cudaFree(ctx->dPairFirst[i]);
     }
-    cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dRowStart);
+    cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dScyz); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
     cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dRowZero); cudaFree(ctx->dBigRows);

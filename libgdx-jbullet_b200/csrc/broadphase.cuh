@@ -403,7 +403,7 @@ k_keys(BodyArrays B, int n, const StepCounters* __restrict__ ctr, const GridPara
 __global__ void __launch_bounds__(256)
 k_gather(BodyArrays B, int n, const uint32_t* keysA, const uint32_t* keysB, const uint32_t* valsA, const uint32_t* valsB,
          const uint32_t* __restrict__ side, const GridParams* __restrict__ grid, float4* __restrict__ smin,
-         float4* __restrict__ smax, uint32_t* __restrict__ srow, uint32_t* __restrict__ rowStart) {
+         float4* __restrict__ smax, uint32_t* __restrict__ srow, uint32_t* __restrict__ rowStart, uint32_t* __restrict__ scyz) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t* keys = *side ? keysB : keysA;
@@ -417,6 +417,17 @@ k_gather(BodyArrays B, int n, const uint32_t* keysA, const uint32_t* keysB, cons
     smin[j] = a;
     smax[j] = b;
     srow[j] = k;  // the whole sorted key: row = k >> 12, qx = k & 4095
+    {
+        // cell coordinates of the row, once per proxy (the sweep's 9 threads per proxy would each redo the divisions);
+        // 0xffffffff marks the rows that are not part of the grid (large proxies, dead slots)
+        const uint32_t nrows = (uint32_t)grid->nrows, rpw = (uint32_t)grid->rowsPerWorld, nz = (uint32_t)grid->nz;
+        uint32_t c = 0xffffffffu;
+        if (row < nrows) {
+            const uint32_t rem = row % rpw;
+            c = ((rem / nz) << 16) | (rem % nz);
+        }
+        scyz[j] = c;
+    }
     uint32_t prev = j ? (keys[j - 1] >> 12) : 0xffffffffu;
     const uint32_t lastRow = (uint32_t)(grid->nrows + grid->numWorlds) + 1u;
     if (j == 0) {
@@ -467,6 +478,33 @@ struct PairStager {
         __syncwarp();
         count = 0;
     }
+    // Final flush of a 256-thread block: the eight warps reserve their output range with ONE atomic on the shared pair
+    // counter (the per-warp atomics of the plain flush were the top stall of the sweep: ~250 k same-address atomics per
+    // step at 100 k bodies).  Every thread of the block must call it.
+    __device__ __forceinline__ void flushBlock(uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr,
+                                               uint32_t* sCnt /*[8]*/, uint32_t* sBase) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) sCnt[warp] = (uint32_t)count;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { uint32_t c = sCnt[w]; sCnt[w] = tot; tot += c; }
+            *sBase = tot ? atomicAdd(&ctr->pairCount, tot) : 0u;
+        }
+        __syncthreads();
+        const uint32_t base = *sBase + sCnt[warp];
+        for (int k = lane; k < count; k += 32) {
+            uint32_t pos = base + k;
+            if (pos < maxPairs) {
+                uint64_t key = buf[k];
+                uint32_t slot = atomicAdd(&rowCnt[(uint32_t)(key >> uidBits)], 1u);
+                pairKeys[pos] = key | ((uint64_t)slot << (2 * uidBits));
+            } else {
+                ctr->pairOverflow = 1;
+            }
+        }
+        count = 0;
+    }
     // all 32 lanes call this together
     __device__ __forceinline__ void push(bool hit, uint32_t bodyA, uint32_t bodyB, uint64_t* __restrict__ pairKeys,
                                          uint32_t maxPairs, StepCounters* ctr) {
@@ -491,7 +529,8 @@ __global__ void __launch_bounds__(256)
 k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax, const uint32_t* __restrict__ srow,
         const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
         uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, int partLo, int partHi,
-        const float4* __restrict__ qmin, const float4* __restrict__ qmax /* SAP modes: quantised bounds per body, else null */) {
+        const float4* __restrict__ qmin, const float4* __restrict__ qmax /* SAP modes: quantised bounds per body, else null */,
+        const uint32_t* __restrict__ scyz) {
     __shared__ uint64_t stage[8][PAIR_STAGE];
     PairStager st;
     st.init(stage[threadIdx.x >> 5], rowCnt, uidBits);
@@ -499,18 +538,18 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
     n = n < partHi ? n : partHi;
     const int nb = blockIdx.y;  // 0..8
     const int dy = nb / 3 - 1, dz = nb % 3 - 1;
-    const int ny = grid->ny, nz = grid->nz, rpw = grid->rowsPerWorld, nrows = grid->nrows;
+    const int ny = grid->ny, nz = grid->nz;
     uint32_t j = 0, end = 0;
     float4 amin = make_float4(0, 0, 0, 0), amax = amin;
     uint32_t xkI = 0, xkMax = 0;
     if (i < n) {
         const uint32_t keyI = srow[i];
         const uint32_t row = keyI >> 12;
-        if (row < (uint32_t)nrows) {
-            int w = row / rpw, rem = row - w * rpw;
-            int cy = rem / nz + dy, cz = rem % nz + dz;
+        const uint32_t cc = __ldg(scyz + i);
+        if (cc != 0xffffffffu) {
+            int cy = (int)(cc >> 16) + dy, cz = (int)(cc & 0xffffu) + dz;
             if (cy >= 0 && cy < ny && cz >= 0 && cz < nz) {
-                uint32_t r2 = (uint32_t)(w * rpw + cy * nz + cz);
+                uint32_t r2 = (uint32_t)((int)row + dy * nz + dz);  // same world: cy stays inside [0, ny)
                 uint32_t lo = rowStart[r2], hi = rowStart[r2 + 1];
                 amin = __ldg(smin + i);
                 amax = __ldg(smax + i);
@@ -558,7 +597,9 @@ k_sweep(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
         }
         st.push(hit, __float_as_uint(amin.w), bodyB, pairKeys, maxPairs, ctr);
     }
-    st.flush(pairKeys, maxPairs, ctr);
+    __shared__ uint32_t sCnt[8];
+    __shared__ uint32_t sBase;
+    st.flushBlock(pairKeys, maxPairs, ctr, sCnt, &sBase);
 }
 
 // k_large: proxies that do not fit the grid (row == nrows) against every proxy of the same world, and
@@ -605,7 +646,9 @@ k_large(int n, const float4* __restrict__ smin, const float4* __restrict__ smax,
             st.push(hit, bodyA, bodyB, pairKeys, maxPairs, ctr);
         }
     }
-    st.flush(pairKeys, maxPairs, ctr);
+    __shared__ uint32_t sCnt[8];
+    __shared__ uint32_t sBase;
+    st.flushBlock(pairKeys, maxPairs, ctr, sCnt, &sBase);
 }
 
 }  // namespace b2c
