@@ -16,7 +16,7 @@ cat gpurun_out/bench_$TAG.json
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
 cat gpurun_out/bench_ref_$TAG.json
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu --profile-step > gpurun_out/ncu_launch_$TAG.log 2>&1
+    --log-file gpurun_out/launches_$TAG.csv env B2C_GRAPH=0 python bench.py --steps 3 --warmup 3 --no-cpu --profile-step > gpurun_out/ncu_launch_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/prof_$TAG \
-    python bench.py --steps 3 --warmup 3 --no-cpu --profile-step > gpurun_out/ncu_full_$TAG.log 2>&1
+    env B2C_GRAPH=0 B2C_OVERLAP=0 python bench.py --steps 3 --warmup 3 --no-cpu --profile-step > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out | tail -12
