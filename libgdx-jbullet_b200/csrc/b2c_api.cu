@@ -132,6 +132,10 @@ struct b2c_ctx {
     uint32_t binTiles = 0;
     uint32_t* dCursors = nullptr;
     uint32_t* dSurvivors = nullptr;
+    uint32_t* dSurvSorted = nullptr;   // survivors ordered by last step's iteration count
+    uint8_t* dSurvKey = nullptr;
+    uint32_t* dSurvZero = nullptr;     // hist[16] | ticket | pad | status[binTiles][16]
+    uint32_t* dSurvStart = nullptr;    // [17]
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
     uint32_t* dEpaRetry = nullptr;
@@ -460,7 +464,8 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     // stable partition of the pair indices by bin, one pass (k_bin_scatter)
     {
         unsigned bg = ctx->binTiles < 148u * 4u ? ctx->binTiles : 148u * 4u;
-        k_bin_scatter<<<bg ? bg : 1, 256, 0, s>>>(a);
+        k_partition16<<<bg ? bg : 1, 256, 0, s>>>(ctx->dBinOf, ctx->dNumPairs[ctx->cur], ctx->dBinZero, ctx->dBinStart, nullptr,
+                                                  ctx->dBinItems);
     }
     ctx->launches += 3;  // k_clear_np_counters, k_classify, k_bin_scatter (kernels only; memsets are not counted)
     mark(ctx, 9);
@@ -477,9 +482,15 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[0], sc));
     mark(ctx, 10);
     CK(cudaMemsetAsync(ctx->dCursors, 0, 4 * sizeof(uint32_t), s));
-    k_gjk_prefilter<<<148 * 8, 256, 0, s>>>(a, ctx->dSurvivors, ctx->dCursors + 2);
-    k_gjk<<<148 * GJK_MINB, 128, 0, s>>>(a, g, ctx->dCursors, ctx->dSurvivors, ctx->dCursors + 2);
-    ctx->launches += 2;
+    CK(cudaMemsetAsync(ctx->dSurvZero, 0, (32 + (size_t)ctx->binTiles * 16) * sizeof(uint32_t), s));
+    k_gjk_prefilter<<<148 * 8, 256, 0, s>>>(a, ctx->dSurvivors, ctx->dCursors + 2, ctx->dSurvKey, ctx->dSurvZero);
+    {
+        unsigned bg = ctx->binTiles < 148u * 2u ? ctx->binTiles : 148u * 2u;
+        k_partition16<<<bg ? bg : 1, 256, 0, s>>>(ctx->dSurvKey, ctx->dCursors + 2, ctx->dSurvZero, ctx->dSurvStart, ctx->dSurvivors,
+                                                  ctx->dSurvSorted);
+    }
+    k_gjk<<<148 * GJK_MINB, 128, 0, s>>>(a, g, ctx->dCursors, ctx->dSurvSorted, ctx->dCursors + 2);
+    ctx->launches += 3;
     if (ctx->hasMesh) {
         k_mesh_query<<<148 * 4, 128, 0, s>>>(a, g);
         k_gjk_tri<<<148 * 4, 128, 0, s>>>(a, g, ctx->dCursors + 1);
@@ -815,9 +826,13 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dBinStart, (size_t)32));
     ctx->binTiles = (uint32_t)((P + BIN_TILE - 1) / BIN_TILE);
     CKC(dalloc(&ctx->dBinZero, 32 + (size_t)ctx->binTiles * 16));
+    CKC(dalloc(&ctx->dSurvZero, 32 + (size_t)ctx->binTiles * 16));
     CKC(dalloc(&ctx->dCursors, (size_t)4));
     CKC(dalloc(&ctx->dExportCount, (size_t)1));
     CKC(dalloc(&ctx->dSurvivors, P));
+    CKC(dalloc(&ctx->dSurvSorted, P));
+    CKC(dalloc(&ctx->dSurvKey, P));
+    CKC(dalloc(&ctx->dSurvStart, (size_t)32));
     ctx->maxEpa = (uint32_t)(P / 4 + 1024);
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
     ctx->maxEpaRetry = ctx->maxEpa;
@@ -861,7 +876,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
     cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dRowZero); cudaFree(ctx->dBigRows);
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dBinZero); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors);
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dBinZero); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); cudaFree(ctx->dSurvSorted); cudaFree(ctx->dSurvKey); cudaFree(ctx->dSurvZero); cudaFree(ctx->dSurvStart);
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

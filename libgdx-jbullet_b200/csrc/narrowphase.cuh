@@ -519,16 +519,20 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
     if (threadIdx.x < 16 && hist[threadIdx.x]) atomicAdd(&a.binZero[threadIdx.x], hist[threadIdx.x]);
 }
 
-// k_bin_scatter: stable partition of the pair indices by bin in ONE pass: tiles are taken in ticket order, every tile
+// k_partition16: stable partition of an index list by a 4-bit key in ONE pass: tiles are taken in ticket order, every tile
 // ranks its pairs per bin (match-any inside a warp, exclusive scan over the warps), publishes its 16 counts and resolves
 // its offsets by decoupled look-back over the preceding tiles (the scheme of radix_sort.cuh with a 4-bit digit).
 constexpr int BIN_ITEMS = 8, BIN_TILE = 256 * BIN_ITEMS, BIN_LOOKBACK = 8;
-__global__ void __launch_bounds__(256) k_bin_scatter(NpArgs a) {
-    const uint32_t n = *a.numPairs;
+// keys[i] < 16 for i < *nPtr; zero = (hist[16] | ticket | pad[15] | status[tiles][16]) cleared by the caller, hist filled by
+// the producer of the keys; out[...] = payload ? payload[i] : i in stable key order; startOut[0..16] = exclusive offsets.
+__global__ void __launch_bounds__(256)
+k_partition16(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ nPtr, uint32_t* zero, uint32_t* __restrict__ startOut,
+              const uint32_t* __restrict__ payload, uint32_t* __restrict__ out) {
+    const uint32_t n = *nPtr;
     const uint32_t numTiles = (n + BIN_TILE - 1) / BIN_TILE;
-    const uint32_t* hist = a.binZero;
-    uint32_t* ticket = a.binZero + 16;
-    uint32_t* status = a.binZero + 32;
+    const uint32_t* hist = zero;
+    uint32_t* ticket = zero + 16;
+    uint32_t* status = zero + 32;
     __shared__ uint32_t warpCnt[8][16];
     __shared__ uint32_t base[16];
     __shared__ uint32_t sTile;
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(NpArgs a) {
     if (blockIdx.x == 0 && threadIdx.x <= 16) {
         uint32_t e = 0;
         for (int j = 0; j < (int)threadIdx.x; j++) e += hist[j];
-        a.binStart[threadIdx.x] = e;
+        startOut[threadIdx.x] = e;
     }
     for (;;) {
         __syncthreads();
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(NpArgs a) {
 #pragma unroll
         for (int k = 0; k < BIN_ITEMS; k++) {
             uint32_t idx = tileStart + k * 32;
-            bin[k] = idx < n ? (uint32_t)a.binOf[idx] : 0x100u + lane;
+            bin[k] = idx < n ? (uint32_t)keys[idx] : 0x100u + lane;
         }
 #pragma unroll
         for (int k = 0; k < BIN_ITEMS; k++) {
@@ -614,7 +618,10 @@ __global__ void __launch_bounds__(256) k_bin_scatter(NpArgs a) {
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < BIN_ITEMS; k++) {
-            if (bin[k] < 16u) a.binItems[base[bin[k]] + warpCnt[warp][bin[k]] + rank[k]] = tileStart + k * 32;
+            if (bin[k] < 16u) {
+                const uint32_t idx = tileStart + k * 32;
+                out[base[bin[k]] + warpCnt[warp][bin[k]] + rank[k]] = payload ? payload[idx] : idx;
+            }
         }
     }
 }
@@ -808,10 +815,14 @@ struct WarpQueue {
 #define PREF_MINB 3
 #endif
 __global__ void __launch_bounds__(256, PREF_MINB)
-k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict__ survCount) {
+k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict__ survCount, uint8_t* __restrict__ survKey,
+                uint32_t* survHist /*[16], zeroed*/) {
     const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
     __shared__ uint32_t warpCnt[8];
     __shared__ uint32_t blockBase;
+    __shared__ uint32_t sHist[16];
+    if (threadIdx.x < 16) sHist[threadIdx.x] = 0;
+    __syncthreads();
     uint32_t checks = 0;
     for (uint32_t base = s0 + blockIdx.x * blockDim.x; base < e0; base += gridDim.x * blockDim.x) {
         const uint32_t it = base + threadIdx.x;
@@ -869,9 +880,21 @@ k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict
             blockBase = tot ? atomicAdd(survCount, tot) : 0;
         }
         __syncthreads();
-        if (survive) survivors[blockBase + warpCnt[warp] + __popc(m & ((1u << lane) - 1u))] = p;
+        if (survive) {
+            const uint32_t slot = blockBase + warpCnt[warp] + __popc(m & ((1u << lane) - 1u));
+            survivors[slot] = p;
+            // Temporal coherence: the iteration count a pair needed last step (kept in its manifold header by k_gjk) is the
+            // count it needs now for ~95 % of the pairs.  Survivors are ordered by it, longest first, so the lanes of a
+            // warp start, iterate and finish together instead of each being in a different phase of the detector.
+            const int last = a.mhdr[p].pad0;
+            const uint32_t key = last <= 1 ? 15u : (last >= 15 ? 0u : (uint32_t)(15 - last));  // unknown / new pairs last
+            survKey[slot] = (uint8_t)key;
+            const uint32_t same = __match_any_sync(__activemask(), key);  // one shared-memory atomic per key per warp
+            if (lane == __ffs(same) - 1) atomicAdd(&sHist[key], (uint32_t)__popc(same));
+        }
         __syncthreads();
     }
+    if (threadIdx.x < 16 && sHist[threadIdx.x]) atomicAdd(&survHist[threadIdx.x], sHist[threadIdx.x]);
     if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
 }
 
@@ -924,6 +947,7 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
                 GjkResult r;
                 L.finish(r);
                 busy = false;
+                a.mhdr[p].pad0 = r.curIter;  // next step's ordering key (k_gjk_prefilter); travels with the manifold
                 bool queued = false;
                 if (r.needEpa) {
                     deep++;
