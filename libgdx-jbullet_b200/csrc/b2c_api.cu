@@ -489,7 +489,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         k_partition16<<<bg ? bg : 1, 256, 0, s>>>(ctx->dSurvKey, ctx->dCursors + 2, ctx->dSurvZero, ctx->dSurvStart, ctx->dSurvivors,
                                                   ctx->dSurvSorted);
     }
-    k_gjk<<<148 * GJK_MINB, 128, 0, s>>>(a, g, ctx->dCursors, ctx->dSurvSorted, ctx->dCursors + 2);
+    k_gjk<<<148 * GJK_MINB, 128, 0, s>>>(a, g, ctx->dCursors, ctx->dSurvSorted, ctx->dCursors + 2, ctx->dSurvStart);
     ctx->launches += 3;
     if (ctx->hasMesh) {
         k_mesh_query<<<148 * 4, 128, 0, s>>>(a, g);

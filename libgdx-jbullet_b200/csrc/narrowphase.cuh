@@ -905,8 +905,10 @@ k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict
 #define GJK_MINB 4
 #endif
 __global__ void __launch_bounds__(128, GJK_MINB)
-k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ survivors, const uint32_t* __restrict__ survCount) {
+k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ survivors, const uint32_t* __restrict__ survCount,
+      const uint32_t* __restrict__ survStart /*[17] offsets of the 16 history buckets; bucket 15 = no history*/) {
     const uint32_t count = *survCount;
+    const uint32_t unknownStart = survStart[15];
     uint32_t deep = 0, checks = 0;
     GjkLane L;
     LaneShape A, B;
@@ -917,7 +919,13 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
     WarpQueue wq;
     wq.init();
     while (true) {
-        const bool want = !busy && more;
+                // Pairs with a known history come in runs of equal predicted iteration count: the warp takes 32 of them at a time
+        // and refills only when all of its lanes are done, so the lanes stay in phase (same trip, mostly the same simplex
+        // size).  Pairs without history (the tail of the list) have unrelated iteration counts: there every lane refills
+        // as soon as it is free.
+        const bool inKnownPart = wq.next < unknownStart;
+        const bool anyBusy = __any_sync(0xffffffffu, busy);  // every lane votes (never behind a short-circuit)
+        const bool want = !busy && more && (!inKnownPart || !anyBusy);
         const uint32_t it = wq.take(want, cursor, count);  // one convergent call site for the whole warp
         if (want) {
             if (it == 0xffffffffu) {
