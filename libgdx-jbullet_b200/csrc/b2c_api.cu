@@ -125,6 +125,7 @@ struct b2c_ctx {
     // narrowphase
     b2c_raw_contact* dRaw = nullptr;
     int8_t* dRawFlag = nullptr;
+    uint8_t* dHist = nullptr;          // per-pair GJK iteration count of the last step (k_carry)
     uint8_t* dBinOf = nullptr;
     uint32_t* dBinItems = nullptr;
     uint32_t* dBinStart = nullptr;   // [17]
@@ -397,7 +398,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
                                                                       ctx->dSortedKeys[cur ^ 1], ctx->dNumPairs[cur ^ 1],
                                                                       ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
-                                                                      ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr);
+                                                                      ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr, ctx->dHist);
     ctx->launches += 10 + ctx->sortBodies.launches;
     CK(cudaGetLastError());
     CK(cudaEventRecordWithFlags(ctx->evPairsReady, s, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -425,6 +426,7 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.mpts = ctx->dMPts[ctx->cur];
     a.raw = ctx->dRaw;
     a.rawFlag = ctx->dRawFlag;
+    a.hist = ctx->dHist;
     a.binOf = ctx->dBinOf;
     a.binItems = ctx->dBinItems;
     a.binStart = ctx->dBinStart;
@@ -822,6 +824,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dRawFlag, P));
     if (P > (size_t)(1u << 24)) return fail(B2C_ERR_BAD_ARG);  // pair index must fit 24 bits next to the bin byte
     CKC(dalloc(&ctx->dBinOf, P));
+    CKC(dalloc(&ctx->dHist, P));
     CKC(dalloc(&ctx->dBinItems, P));
     CKC(dalloc(&ctx->dBinStart, (size_t)32));
     ctx->binTiles = (uint32_t)((P + BIN_TILE - 1) / BIN_TILE);
@@ -876,7 +879,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
     cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dRowZero); cudaFree(ctx->dBigRows);
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dBinZero); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); cudaFree(ctx->dSurvSorted); cudaFree(ctx->dSurvKey); cudaFree(ctx->dSurvZero); cudaFree(ctx->dSurvStart);
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dHist); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dBinZero); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); cudaFree(ctx->dSurvSorted); cudaFree(ctx->dSurvKey); cudaFree(ctx->dSurvZero); cudaFree(ctx->dSurvStart);
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

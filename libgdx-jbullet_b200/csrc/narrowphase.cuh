@@ -22,7 +22,9 @@
 
 namespace b2c {
 
-enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_GJK0 = 3, BIN_MESH = 12, BIN_COUNT = 13 };
+// BIN_GJK0 + 3*typeA + typeB: convex-convex pairs the prefilter looks at; BIN_PS0 + (number of hulls): convex-convex pairs
+// that went past the prefilter last step (history byte) — they go straight to the survivor list
+enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_MESH = 3, BIN_GJK0 = 4, BIN_PS0 = 13, BIN_COUNT = 16 };
 
 // Device-side split of b2c_manifold: the 32-byte header every kernel streams, and the point slots only the
 // touching pairs read.  The ABI's 416-byte record is assembled when results are copied out.
@@ -48,6 +50,8 @@ struct NpArgs {
     b2c_manifold_point* mpts;     // [4*maxPairs] this step: the 4 point slots of each manifold
     b2c_raw_contact* raw;         // [maxPairs]
     int8_t* rawFlag;              // [maxPairs] copy of raw[p].has_contact for the kernels that only need the flag
+    uint8_t* hist;                // [maxPairs] GJK iterations each pair needed last step (0 = none / new pair, capped at 15):
+                                  //   written by k_carry from the manifold header word k_gjk leaves there
     uint8_t* binOf;               // [maxPairs] bin of every pair (k_classify)
     uint32_t* binItems;           // [maxPairs] pair indices, stably partitioned by bin (k_bin_scatter)
     uint32_t* binStart;           // [17] exclusive bin offsets; [b+1] = end of bin b
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(256)
 k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs, const uint64_t* __restrict__ prevKeys,
         const uint32_t* __restrict__ prevNum, const uint32_t* __restrict__ prevFirst, const ManifoldHdr* __restrict__ prevH,
         const b2c_manifold_point* __restrict__ prevP, ManifoldHdr* __restrict__ H, b2c_manifold_point* __restrict__ P, int uidBits,
-        StepCounters* ctr) {
+        StepCounters* ctr, uint8_t* __restrict__ hist) {
     const uint32_t n = *numPairs, pn = *prevNum;
     const int lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
@@ -376,6 +380,7 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
             }
             int4* dst = reinterpret_cast<int4*>(H + p);   // adjacent lanes -> adjacent 32-byte headers
             dst[0] = h0; dst[1] = h1;
+            hist[p] = (uint8_t)(h1.z > 15 ? 15 : (h1.z < 0 ? 0 : h1.z));  // header word pad0 = last step's GJK iteration count
         }
         uint32_t cm = __ballot_sync(0xffffffffu, carriedManifold);
         if (lane == 0 && cm) atomicAdd(&ctr->numManifolds, (uint32_t)__popc(cm));
@@ -507,7 +512,8 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
             int t0 = a.shapes[a.shape[b0]].type, t1 = a.shapes[a.shape[b1]].type;
             if (t0 == SH_SPHERE && t1 == SH_SPHERE) bin = BIN_SS;
             else if ((isConvexType(t0) && t1 == SH_PLANE) || (isConvexType(t1) && t0 == SH_PLANE)) bin = BIN_CP;
-            else if (isConvexType(t0) && isConvexType(t1)) bin = BIN_GJK0 + t0 * 3 + t1;
+            else if (isConvexType(t0) && isConvexType(t1))
+                bin = a.hist[p] >= 2 ? BIN_PS0 + (t0 == SH_HULL ? 1 : 0) + (t1 == SH_HULL ? 1 : 0) : BIN_GJK0 + t0 * 3 + t1;
             else if ((isConvexType(t0) && t1 == SH_MESH) || (isConvexType(t1) && t0 == SH_MESH)) bin = BIN_MESH;
         }
         a.binOf[p] = (uint8_t)bin;  // BIN_SKIP pairs are not dispatched: their raw record is not written this step
@@ -817,7 +823,9 @@ struct WarpQueue {
 __global__ void __launch_bounds__(256, PREF_MINB)
 k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict__ survCount, uint8_t* __restrict__ survKey,
                 uint32_t* survHist /*[16], zeroed*/) {
-    const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
+    // [s0, mid): pairs to examine; [mid, e0): pairs predicted to survive (~95 % right; k_gjk runs survivors from scratch, so
+    // a wrong prediction just ends there in trip 2) — appended to the survivor list with their history key, no arithmetic
+    const uint32_t s0 = a.binStart[BIN_GJK0], mid = a.binStart[BIN_PS0], e0 = a.binStart[BIN_COUNT];
     __shared__ uint32_t warpCnt[8];
     __shared__ uint32_t blockBase;
     __shared__ uint32_t sHist[16];
@@ -828,7 +836,13 @@ k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict
         const uint32_t it = base + threadIdx.x;
         bool survive = false;
         uint32_t p = 0;
-        if (it < e0) {
+        uint32_t key = 15u;  // examined pairs that survive have no usable history
+        if (it >= mid && it < e0) {
+            p = binItem(a, it);
+            survive = true;
+            const int last = a.hist[p];
+            key = last >= 15 ? 0u : (uint32_t)(15 - last);  // longest first
+        } else if (it < mid) {
             p = binItem(a, it);
             int2 pr = a.pairs[p];
             const int b0 = pr.x - 1, b1 = pr.y - 1;
@@ -886,8 +900,6 @@ k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict
             // Temporal coherence: the iteration count a pair needed last step (kept in its manifold header by k_gjk) is the
             // count it needs now for ~95 % of the pairs.  Survivors are ordered by it, longest first, so the lanes of a
             // warp start, iterate and finish together instead of each being in a different phase of the detector.
-            const int last = a.mhdr[p].pad0;
-            const uint32_t key = last <= 1 ? 15u : (last >= 15 ? 0u : (uint32_t)(15 - last));  // unknown / new pairs last
             survKey[slot] = (uint8_t)key;
             const uint32_t same = __match_any_sync(__activemask(), key);  // one shared-memory atomic per key per warp
             if (lane == __ffs(same) - 1) atomicAdd(&sHist[key], (uint32_t)__popc(same));
@@ -1017,7 +1029,7 @@ __device__ __forceinline__ void manifoldCcOne(const NpArgs& a, uint32_t p, bool 
 // penetration bin (rawFlag == -2, set by k_gjk and never touched by k_epa) are left to k_manifold_epa, so this kernel
 // can run concurrently with the EPA kernels on another stream.
 __global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
-    const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_GJK0 + 9];
+    const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_COUNT];
     uint32_t added = 0, created = 0;
     for (uint32_t it = s0 + blockIdx.x * blockDim.x + threadIdx.x; it < e0; it += gridDim.x * blockDim.x) {
         uint32_t p = binItem(a, it);
