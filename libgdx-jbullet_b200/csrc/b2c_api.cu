@@ -463,13 +463,13 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     k_clear_np_counters<<<1, 32, 0, s>>>(ctx->dCtr);
     CK(cudaMemsetAsync(ctx->dBinZero, 0, (32 + (size_t)ctx->binTiles * 16) * sizeof(uint32_t), s));
     k_classify<<<pg, 256, 0, s>>>(a);
-    // stable partition of the pair indices by bin, one pass (k_bin_scatter)
+    // stable partition of the pair indices by bin, one pass (k_partition16)
     {
         unsigned bg = ctx->binTiles < 148u * 4u ? ctx->binTiles : 148u * 4u;
         k_partition16<<<bg ? bg : 1, 256, 0, s>>>(ctx->dBinOf, ctx->dNumPairs[ctx->cur], ctx->dBinZero, ctx->dBinStart, nullptr,
                                                   ctx->dBinItems);
     }
-    ctx->launches += 3;  // k_clear_np_counters, k_classify, k_bin_scatter (kernels only; memsets are not counted)
+    ctx->launches += 3;  // k_clear_np_counters, k_classify, k_partition16 (kernels only; memsets are not counted)
     mark(ctx, 9);
     // the closed-form bins touch only their own pairs' records: they run beside the GJK kernels
     cudaStream_t sc = s;

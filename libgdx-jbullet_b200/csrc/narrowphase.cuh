@@ -53,7 +53,7 @@ struct NpArgs {
     uint8_t* hist;                // [maxPairs] GJK iterations each pair needed last step (0 = none / new pair, capped at 15):
                                   //   written by k_carry from the manifold header word k_gjk leaves there
     uint8_t* binOf;               // [maxPairs] bin of every pair (k_classify)
-    uint32_t* binItems;           // [maxPairs] pair indices, stably partitioned by bin (k_bin_scatter)
+    uint32_t* binItems;           // [maxPairs] pair indices, stably partitioned by bin (k_partition16)
     uint32_t* binStart;           // [17] exclusive bin offsets; [b+1] = end of bin b
     uint32_t* binZero;            // cleared per dispatch: hist[16] | ticket | pad[15] | status[tiles][16]
     StepCounters* ctr;
@@ -1026,7 +1026,7 @@ __device__ __forceinline__ void manifoldCcOne(const NpArgs& a, uint32_t p, bool 
 }
 
 // k_manifold_cc: every pair of the GJK bins whose detector finished in k_gjk / k_gjk_prefilter.  Pairs waiting in the
-// penetration bin (rawFlag == -2, set by k_gjk and never touched by k_epa) are left to k_manifold_epa, so this kernel
+// penetration bin (rawFlag == -2, set by k_gjk and never touched by k_epa) are left to the manifold loop of k_epa<1>, so this kernel
 // can run concurrently with the EPA kernels on another stream.
 __global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
     const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_COUNT];
