@@ -22,9 +22,10 @@
 
 namespace b2c {
 
-// BIN_GJK0 + 3*typeA + typeB: convex-convex pairs the prefilter looks at; BIN_PS0 + (number of hulls): convex-convex pairs
-// that went past the prefilter last step (history byte) — they go straight to the survivor list
-enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_MESH = 3, BIN_GJK0 = 4, BIN_PS0 = 13, BIN_COUNT = 16 };
+// Convex-convex pairs are binned by which side is a hull (the only support mapping with a loop; box and sphere are a few
+// selects): BIN_GJK0 + 2*(A is hull) + (B is hull) for the pairs the prefilter looks at, BIN_PS0 + the same for the pairs that
+// went past the prefilter last step (history byte) — those go straight to the survivor list.
+enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_MESH = 3, BIN_GJK0 = 4, BIN_PS0 = 8, BIN_COUNT = 12 };
 
 // Device-side split of b2c_manifold: the 32-byte header every kernel streams, and the point slots only the
 // touching pairs read.  The ABI's 416-byte record is assembled when results are copied out.
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
             if (t0 == SH_SPHERE && t1 == SH_SPHERE) bin = BIN_SS;
             else if ((isConvexType(t0) && t1 == SH_PLANE) || (isConvexType(t1) && t0 == SH_PLANE)) bin = BIN_CP;
             else if (isConvexType(t0) && isConvexType(t1))
-                bin = a.hist[p] >= 2 ? BIN_PS0 + (t0 == SH_HULL ? 1 : 0) + (t1 == SH_HULL ? 1 : 0) : BIN_GJK0 + t0 * 3 + t1;
+                bin = (a.hist[p] >= 2 ? BIN_PS0 : BIN_GJK0) + (t0 == SH_HULL ? 2 : 0) + (t1 == SH_HULL ? 1 : 0);
             else if ((isConvexType(t0) && t1 == SH_MESH) || (isConvexType(t1) && t0 == SH_MESH)) bin = BIN_MESH;
         }
         a.binOf[p] = (uint8_t)bin;  // BIN_SKIP pairs are not dispatched: their raw record is not written this step
