@@ -34,6 +34,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so the real
+    stdout is set aside for the result line and fd 1 is pointed at stderr for everything else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def make_scene(n_bodies, seed, workload="c2", worlds=4096):
     import scenes
     if workload == "c4":   # SURVEY §8d C4: independent 64-body dice worlds
@@ -443,7 +465,7 @@ def run_ours(args):
     }
     if ngpu == 1 and not args.no_cpu and wl == "c2":
         out["cpu_baseline"] = cpu_baseline(sc, args)
-    print(json.dumps(out), flush=True)
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -499,7 +521,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -522,6 +544,7 @@ def main():
     ap.add_argument("--save-settled", default="", help="write the settled origins (npz) here; commit it under tests/golden/")
     ap.add_argument("--settle", type=int, default=60, help="relaxation iterations for the settled snapshot (0 = raw lattice)")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
