@@ -252,6 +252,15 @@ int32_t b2c_get_pair_deltas(b2c_ctx*, int32_t* added_out, int32_t cap_added, int
  * uid i+1 (the smallest body index of its island), -1 for static bodies; n = number of bodies to report. */
 int32_t b2c_compute_islands(b2c_ctx*, int32_t* tags_out, int32_t n, int32_t* num_islands_out);
 
+/* CollisionWorld.rayTest with a ClosestRayResultCallback per ray (disp/CollisionWorld.java:553-590, 697-729), batched:
+ * from_xyz / to_xyz = 3 floats per ray (host); group / mask = the callback's collisionFilterGroup / collisionFilterMask
+ * (disp/CollisionWorld.java:655-670, defaults DEFAULT_FILTER = 1 and ALL_FILTER = -1).  Outputs per ray: uid of the closest
+ * body hit (0 = none), closestHitFraction (1 = none), hitNormalWorld, hitPointWorld.  Uses the transforms currently
+ * resident.  Convex bodies (box, sphere, hull) are cast with the reference's SubsimplexConvexCast; static planes and
+ * triangle meshes are not cast yet (the ray passes through them). */
+int32_t b2c_ray_test_closest(b2c_ctx*, int32_t n, const float* from_xyz, const float* to_xyz, int16_t group, int16_t mask,
+                             int32_t* uid_out, float* fraction_out, float* normal_out, float* point_out);
+
 /* ---- one world partitioned over several GPUs -------------------------------------
  * Every rank holds all proxies (their state is small) and owns a contiguous slice of the SORTED proxy list: it
  * emits the pairs whose first member in sweep order lies in its slice (slab partition by sorted-AABB range; reads

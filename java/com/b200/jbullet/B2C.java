@@ -56,6 +56,9 @@ final class B2C {
     static final MethodHandle setWorldAabb = h("b2c_set_world_aabb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     // RigidBody.checkCollideWithOverride: constraint-linked body pairs are not dispatched
     static final MethodHandle setNoCollidePairs = h("b2c_set_no_collide_pairs", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    // CollisionWorld.rayTest + ClosestRayResultCallback, batched
+    static final MethodHandle rayTestClosest = h("b2c_ray_test_closest",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_SHORT, JAVA_SHORT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     // device-resident stepping: enqueue, download the pair list while the narrowphase runs, then wait for the counts
     static final MethodHandle stepDevice = h("b2c_step_device", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle syncCounts = h("b2c_sync_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));

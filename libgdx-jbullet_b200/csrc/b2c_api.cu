@@ -18,6 +18,7 @@
 #include "narrowphase.cuh"
 #include "pair_rows.cuh"
 #include "radix_sort.cuh"
+#include "raycast.cuh"
 
 using namespace b2c;
 
@@ -160,6 +161,14 @@ struct b2c_ctx {
 
     uint64_t* dNoCollide = nullptr;   // sorted keys of never-dispatched body pairs (b2c_set_no_collide_pairs)
     uint32_t numNoCollide = 0, capNoCollide = 0;
+
+    // ray tests (allocated on first use)
+    float4* dRayMin = nullptr;
+    float4* dRayMax = nullptr;
+    float* dRayIn = nullptr;       // from | to, 6 floats per ray
+    RayOut* dRayOut = nullptr;
+    uint32_t* dRayOverflow = nullptr;
+    int rayCap = 0;
 
     // islands + pair deltas (allocated on first use)
     int* dIslandPar = nullptr;
@@ -885,6 +894,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
+    cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
     cudaFree(ctx->dNoCollide);
     cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
     for (int i = 0; i < 4; i++) {
@@ -1211,7 +1221,8 @@ int32_t b2c_set_no_collide_pairs(b2c_ctx* ctx, int32_t n, const int32_t* uidPair
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     CK(cudaStreamSynchronize(ctx->stream));  // a step in flight may still be reading the old list
     if (keys.size() > ctx->capNoCollide) {
-        cudaFree(ctx->dNoCollide);
+        cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
+    cudaFree(ctx->dNoCollide);
         ctx->dNoCollide = nullptr;
         ctx->capNoCollide = 0;
         CK(cudaMalloc((void**)&ctx->dNoCollide, keys.size() * sizeof(uint64_t)));
@@ -1572,6 +1583,58 @@ int32_t b2c_compute_islands(b2c_ctx* ctx, int32_t* tagsOut, int32_t n, int32_t* 
     if (tagsOut && n) CK(cudaMemcpyAsync(tagsOut, ctx->dIslandTags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (numIslands) *numIslands = (int32_t)c;
+    return B2C_OK;
+}
+
+int32_t b2c_ray_test_closest(b2c_ctx* ctx, int32_t n, const float* from, const float* to, int16_t group, int16_t mask, int32_t* uidOut,
+                             float* fracOut, float* nrmOut, float* ptOut) {
+    if (!ctx || n < 0 || (n > 0 && (!from || !to))) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    if (ctx->stagingCount || ctx->extPending) {  // transforms uploaded but not yet repacked: flush them (no AABB update)
+        int32_t rc = runAabbKernel(ctx, false);
+        if (rc) return rc;
+    }
+    int32_t rc = uploadShapes(ctx);
+    if (rc) return rc;
+    const size_t N = (size_t)ctx->cfg.max_bodies;
+    if (!ctx->dRayMin) CK(dalloc(&ctx->dRayMin, N));
+    if (!ctx->dRayMax) CK(dalloc(&ctx->dRayMax, N));
+    if (!ctx->dRayOverflow) CK(dalloc(&ctx->dRayOverflow, (size_t)1));
+    if (n > ctx->rayCap) {
+        cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut);
+        ctx->dRayIn = nullptr; ctx->dRayOut = nullptr; ctx->rayCap = 0;
+        CK(cudaMalloc((void**)&ctx->dRayIn, (size_t)n * 6 * sizeof(float)));
+        CK(cudaMalloc((void**)&ctx->dRayOut, (size_t)n * sizeof(RayOut)));
+        ctx->rayCap = n;
+    }
+    const int nb = ctx->nBodies;
+    CK(cudaMemcpyAsync(ctx->dRayIn, from, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dRayIn + 3 * (size_t)n, to, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->dRayOverflow, 0, sizeof(uint32_t), s));
+    if (nb > 0) k_ray_aabbs<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, nb, ctx->dRayMin, ctx->dRayMax);
+    const uint32_t cbFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
+    const unsigned grid = (unsigned)(n < 148 * 16 ? n : 148 * 16);
+    k_ray_test<<<grid, RAY_THREADS, 0, s>>>(ctx->B, ctx->dShapes, ctx->dHullPts, nb, ctx->dRayMin, ctx->dRayMax, ctx->dRayIn,
+                                            ctx->dRayIn + 3 * (size_t)n, n, cbFilter, ctx->dRayOut, ctx->dRayOverflow);
+    std::vector<RayOut> host((size_t)n);
+    uint32_t ov = 0;
+    CK(cudaMemcpyAsync(host.data(), ctx->dRayOut, (size_t)n * sizeof(RayOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ov, ctx->dRayOverflow, sizeof(ov), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ov) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "ray test: a ray met %u body AABBs, more than the %d candidates a block keeps", ov, RAY_MAX_CAND);
+        ctx->err = buf;
+        return B2C_ERR_CAPACITY;
+    }
+    for (int i = 0; i < n; i++) {
+        if (uidOut) uidOut[i] = host[i].uid;
+        if (fracOut) fracOut[i] = host[i].fraction;
+        if (nrmOut) { nrmOut[3 * i] = host[i].normal[0]; nrmOut[3 * i + 1] = host[i].normal[1]; nrmOut[3 * i + 2] = host[i].normal[2]; }
+        if (ptOut) { ptOut[3 * i] = host[i].point[0]; ptOut[3 * i + 1] = host[i].point[1]; ptOut[3 * i + 2] = host[i].point[2]; }
+    }
     return B2C_OK;
 }
 

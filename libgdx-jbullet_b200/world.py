@@ -202,6 +202,19 @@ class GpuCollisionWorld:
     def step_device(self):
         self._ck(self.L.b2c_step_device(self.h))
 
+    def rayTestClosest(self, ray_from, ray_to, group=1, mask=-1):
+        """CollisionWorld.rayTest + ClosestRayResultCallback for a batch of rays: (uid (0 = miss), fraction, normal, point)."""
+        f = np.ascontiguousarray(ray_from, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(ray_to, dtype=np.float32).reshape(-1, 3)
+        n = len(f)
+        uid = np.zeros(n, dtype=np.int32)
+        frac = np.zeros(n, dtype=np.float32)
+        nrm = np.zeros((n, 3), dtype=np.float32)
+        pt = np.zeros((n, 3), dtype=np.float32)
+        if n:
+            self._ck(self.L.b2c_ray_test_closest(self.h, n, _vp(f), _vp(t), int(group), int(mask), _vp(uid), _vp(frac), _vp(nrm), _vp(pt)))
+        return uid, frac, nrm, pt
+
     def setNoCollidePairs(self, pairs):
         """Body pairs linked by a collision-disabling constraint (dynamics/RigidBody.java:624-639): kept in the pair cache,
         never dispatched."""

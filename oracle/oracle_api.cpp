@@ -158,6 +158,18 @@ int orc_islands(void* h, int* tagsOut) {
     for (size_t i = 0; i < w->bodies.size(); i++) merges[i] = (w->bodies[i].alive && !w->bodies[i].isStatic) ? 1 : 0;
     return islandTags(w->pairs, merges, tagsOut);
 }
+// CollisionWorld.rayTest + ClosestRayResultCallback for n rays: from/to 3 floats each; out: uid (0 = miss), fraction,
+// normal xyz, point xyz
+void orc_ray_test_closest(void* h, int n, const float* from, const float* to, int group, int mask, int* uidOut, float* out7) {
+    World* w = (World*)h;
+    for (int i = 0; i < n; i++) {
+        RayHit r = w->rayTestClosest(V3(from[3 * i], from[3 * i + 1], from[3 * i + 2]), V3(to[3 * i], to[3 * i + 1], to[3 * i + 2]), group, mask);
+        uidOut[i] = r.uid;
+        out7[7 * i] = r.fraction;
+        out7[7 * i + 1] = r.normal.x; out7[7 * i + 2] = r.normal.y; out7[7 * i + 3] = r.normal.z;
+        out7[7 * i + 4] = r.point.x; out7[7 * i + 5] = r.point.y; out7[7 * i + 6] = r.point.z;
+    }
+}
 int orc_dispatch_all_pairs(void* h) { return ((World*)h)->dispatchAllPairs(); }
 int orc_num_raw(void* h) { return (int)((World*)h)->raw.size(); }
 // raw record: 5 ints (uid0, uid1, tri, hasContact, method) + iters ; 7 floats (normal, point, depth)

@@ -20,6 +20,7 @@
 #include "dbvt_literal.h"
 #include "sap_literal.h"
 #include "gjk.h"
+#include "raycast.h"
 #include "jmath.h"
 #include "manifold.h"
 #include "shapes.h"
@@ -335,6 +336,46 @@ struct World {
         std::sort(pairs.begin(), pairs.end());
         step++;
         return (int)pairs.size();
+    }
+
+    // disp/CollisionWorld.java:553-590 rayTest with a ClosestRayResultCallback(group, mask); convex shapes only
+    RayHit rayTestClosest(const V3& from, const V3& to, int group, int mask) const {
+        RayHit hit;
+        float closest = 1.f;  // RayResultCallback.closestHitFraction
+        for (const Body& b : bodies) {
+            if (!b.alive) continue;
+            if (closest == 0.f) break;
+            // RayResultCallback.needsCollision (disp/CollisionWorld.java:664-670)
+            bool collides = ((int)b.group & mask) != 0;
+            collides = collides && (group & (int)b.mask) != 0;
+            if (!collides) continue;
+            const Shape& s = shapes[b.shape];
+            if (s.type != SH_BOX && s.type != SH_SPHERE && s.type != SH_HULL) continue;  // concave: not cast here
+            V3 mn, mx;
+            shapeGetAabb(s, b.xf, mn, mx);
+            float hitLambda = closest;
+            V3 hitNormal;
+            if (!rayAabb(from, to, mn, mx, hitLambda, hitNormal)) continue;
+            CastResult cr;
+            cr.fraction = closest;
+            if (rayConvexCast(from, to, s, b.xf, cr)) {
+                if (cr.normal.len2() > 0.0001f) {
+                    if (cr.fraction < closest) {
+                        // castResult.normal.mul(rayFromTrans.basis) with the identity basis, then nor()
+                        V3 nn(cr.normal.x * 1.f + cr.normal.y * 0.f + cr.normal.z * 0.f, cr.normal.x * 0.f + cr.normal.y * 1.f + cr.normal.z * 0.f,
+                              cr.normal.x * 0.f + cr.normal.y * 0.f + cr.normal.z * 1.f);
+                        nn.nor();
+                        closest = cr.fraction;
+                        hit.uid = b.uid;
+                        hit.fraction = cr.fraction;
+                        hit.normal.set(nn);
+                        float sgl = 1.f - cr.fraction;
+                        hit.point.set(sgl * from.x + cr.fraction * to.x, sgl * from.y + cr.fraction * to.y, sgl * from.z + cr.fraction * to.z);
+                    }
+                }
+            }
+        }
+        return hit;
     }
 
     // ---- narrowphase ------------------------------------------------------------------

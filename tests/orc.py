@@ -58,6 +58,7 @@ def lib():
     L.orc_calculate_overlapping_pairs.argtypes = [C.c_void_p]
     L.orc_get_pairs.argtypes = [C.c_void_p, i32p]
     L.orc_dispatch_all_pairs.argtypes = [C.c_void_p]
+    L.orc_ray_test_closest.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_int, i32p, f32p]
     L.orc_pair_deltas.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, i32p]
     L.orc_islands.argtypes = [C.c_void_p, i32p]
     L.orc_num_raw.argtypes = [C.c_void_p]
@@ -195,6 +196,15 @@ class OracleWorld:
         t = np.zeros(max(self.num_bodies, 1), dtype=np.int32)
         n = self.L.orc_islands(self.h, t)
         return t[: self.num_bodies], n
+
+    def ray_test_closest(self, ray_from, ray_to, group=1, mask=-1):
+        """CollisionWorld.rayTest with a ClosestRayResultCallback per ray: (uid (0 = miss), fraction, normal, point)."""
+        f = np.ascontiguousarray(ray_from, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(ray_to, dtype=np.float32).reshape(-1, 3)
+        uid = np.zeros(len(f), dtype=np.int32)
+        out = np.zeros((len(f), 7), dtype=np.float32)
+        self.L.orc_ray_test_closest(self.h, len(f), f, t, int(group), int(mask), uid, out)
+        return uid, out[:, 0].copy(), out[:, 1:4].copy(), out[:, 4:7].copy()
 
     def dispatch_all_pairs(self):
         return self.L.orc_dispatch_all_pairs(self.h)
