@@ -46,7 +46,8 @@ typedef enum {
 } b2c_broadphase_mode;
 
 /* Shape kinds (subset of bp/BroadphaseNativeType.java on the hot path). */
-typedef enum { B2C_SHAPE_BOX = 0, B2C_SHAPE_SPHERE = 1, B2C_SHAPE_HULL = 2, B2C_SHAPE_PLANE = 4, B2C_SHAPE_MESH = 5 } b2c_shape_kind;
+typedef enum { B2C_SHAPE_BOX = 0, B2C_SHAPE_SPHERE = 1, B2C_SHAPE_HULL = 2, B2C_SHAPE_PLANE = 4, B2C_SHAPE_MESH = 5,
+               B2C_SHAPE_COMPOUND = 6 } b2c_shape_kind;
 
 typedef struct {
     int32_t device;                    /* CUDA device ordinal */
@@ -60,7 +61,8 @@ typedef struct {
     float contact_breaking_threshold;  /* BulletGlobals.java:63, default 0.02 */
     float dbvt_margin;                 /* bp/DbvtBroadphase.java:35 DBVT_BP_MARGIN, default 0.05 */
     float dbvt_predicted_frames;       /* bp/DbvtBroadphase.java:73, default 2 */
-    int32_t reserved[5];
+    int32_t max_compound_items;        /* child work items per step over all CompoundShape pairs (0 = max(65536, max_pairs)) */
+    int32_t reserved[4];
 } b2c_config;
 
 /* Fills cfg with the reference's defaults (thresholds above; capacities for ~128k bodies). */
@@ -90,6 +92,15 @@ int32_t b2c_shape_register_plane(b2c_ctx*, const float normal[3], float constant
 int32_t b2c_shape_register_mesh(b2c_ctx*, const void* vertex_base, int32_t num_vertices, int32_t vertex_stride,
                                 const void* index_base, int32_t num_triangles, int32_t index_stride,
                                 const float scaling[3], int32_t* shape_out);
+/* sh/CompoundShape.java:50-82: new CompoundShape() followed by addChildShape(localTransform_i, child_i) for i = 0..n-1.
+ * child_shapes = ids of box / sphere / hull shapes registered before; child_transforms12 = n x (9 row-major basis floats +
+ * origin).  The local AABB is the running Math.min / Math.max of the children's AABBs (:60-80), collisionMargin stays 0 (:49).
+ * Pairs with a compound on either side run disp/CompoundCollisionAlgorithm.java:83-129: one child algorithm and one
+ * PersistentManifold per child (per child x child for two compounds), reported by b2c_get_manifolds / b2c_get_contacts with
+ * the child indices.  Not built: compound children that are themselves compounds or concave, compound x triangle mesh (the
+ * pair stays in the pair list but generates no contacts), rays against compounds, compounds in a partitioned world. */
+int32_t b2c_shape_register_compound(b2c_ctx*, int32_t num_children, const int32_t* child_shapes, const float* child_transforms12,
+                                    int32_t* shape_out);
 /* Debug/inspection: copy the quantized BVH (16-byte nodes, sh/QuantizedBvhNodes.java:34-48) */
 int32_t b2c_mesh_get_bvh(b2c_ctx*, int32_t shape, void* nodes16_out, int32_t cap_nodes, int32_t* num_nodes, float quant9_out[9]);
 
@@ -158,12 +169,14 @@ typedef struct {
     int32_t body0, body1;             /* PersistentManifold.getBody0/1 (np/PersistentManifold.java:161-167) */
     int32_t num_contacts;             /* getNumContacts */
     int32_t algorithm;                /* 1 sphere-sphere, 2 convex-plane, 3 convex-convex, 4 convex-concave */
-    int32_t pad[2];
+    int32_t child0, child1;           /* child manifold of a compound pair: index of the child in body0's / body1's CompoundShape
+                                         (-1 = that object is not a compound); -1, -1 for every other manifold */
     b2c_manifold_point points[4];
 } b2c_manifold; /* 416 bytes */
 
 /* Dispatcher.getNumManifolds / getManifoldByIndexInternal (bp/Dispatcher.java:62-64): manifolds in pair
- * order.  only_touching != 0 skips manifolds with zero contacts. */
+ * order; a compound pair contributes one manifold per child algorithm, in the order
+ * disp/CompoundCollisionAlgorithm.java:100-125 runs them.  only_touching != 0 skips manifolds with zero contacts. */
 int32_t b2c_get_manifolds(b2c_ctx*, b2c_manifold* out, int32_t cap, int32_t only_touching, int32_t* num_out);
 
 /* Compact contact stream for the solver: only manifolds with >= 1 contact, each a 32-byte header plus its
@@ -172,7 +185,8 @@ typedef struct {
     int32_t pair_uid0, pair_uid1, body0, body1;
     int32_t num_contacts, algorithm;
     int32_t first_point;              /* index of this manifold's first point in the point array */
-    int32_t pair_index;               /* index of the pair in the sorted pair list */
+    int32_t pair_index;               /* index of the pair in the sorted pair list (child manifolds of compound pairs: index
+                                         of the child work item instead; match those by the uids) */
 } b2c_contact_header; /* 32 bytes */
 int32_t b2c_get_contacts(b2c_ctx*, b2c_contact_header* headers_out, int32_t cap_headers, b2c_manifold_point* points_out,
                          int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
@@ -191,7 +205,7 @@ int32_t b2c_get_solver_contacts(b2c_ctx*, b2c_contact_header* headers_out, int32
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
 typedef struct {
-    int32_t uid0, uid1, tri, has_contact;
+    int32_t uid0, uid1, tri, has_contact; /* tri: triangle index for mesh pairs; -2 - k for child algorithm k of a compound pair; else -1 */
     float normal[3], point[3], depth;
     int32_t method; /* GjkPairDetector.lastUsedMethod (np/GjkPairDetector.java:54); 10 sphere-sphere; 11 convex-plane */
     int32_t iters;

@@ -126,6 +126,10 @@ public:
         check(b2c_shape_register_hull(ctx, &pts[0].x, (int32_t)pts.size(), -1.f, &s), ctx);
         return s;
     }
+    // new CompoundShape() + addChildShape(childTransforms12[i], childShapes[i]) in order (sh/CompoundShape.java:50-82)
+    int32_t CompoundShape(int32_t n, const int32_t* childShapes, const float* childTransforms12) {
+        int32_t s; check(b2c_shape_register_compound(ctx, n, childShapes, childTransforms12, &s), ctx); return s;
+    }
     int32_t StaticPlaneShape(const Vector3& n, float c) { int32_t s; float v[3] = {n.x, n.y, n.z}; check(b2c_shape_register_plane(ctx, v, c, &s), ctx); return s; }
 
     // disp/CollisionWorld.java:102-121

@@ -18,13 +18,14 @@ final class B2C {
         return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
     }
 
-    // b2c_config: 8 x int32, 3 x float, 5 x int32 reserved (64 bytes)
+    // b2c_config: 8 x int32, 3 x float, max_compound_items, 4 x int32 reserved (64 bytes)
     static final StructLayout CONFIG = MemoryLayout.structLayout(
         JAVA_INT.withName("device"), JAVA_INT.withName("broadphase_mode"), JAVA_INT.withName("max_bodies"),
         JAVA_INT.withName("max_pairs"), JAVA_INT.withName("max_shapes"), JAVA_INT.withName("max_hull_points"),
         JAVA_INT.withName("max_mesh_items"), JAVA_INT.withName("num_worlds"),
         JAVA_FLOAT.withName("contact_breaking_threshold"), JAVA_FLOAT.withName("dbvt_margin"),
-        JAVA_FLOAT.withName("dbvt_predicted_frames"), MemoryLayout.sequenceLayout(5, JAVA_INT).withName("reserved"));
+        JAVA_FLOAT.withName("dbvt_predicted_frames"), JAVA_INT.withName("max_compound_items"),
+        MemoryLayout.sequenceLayout(4, JAVA_INT).withName("reserved"));
 
     static final MethodHandle defaultConfig = h("b2c_default_config", FunctionDescriptor.ofVoid(ADDRESS));
     static final MethodHandle create = h("b2c_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
@@ -36,6 +37,9 @@ final class B2C {
     static final MethodHandle shapePlane = h("b2c_shape_register_plane", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_FLOAT, ADDRESS));
     static final MethodHandle shapeMesh = h("b2c_shape_register_mesh",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    // new CompoundShape() + addChildShape(localTransform_i, child_i): child shape ids + n x 12 floats
+    static final MethodHandle shapeCompound = h("b2c_shape_register_compound",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle proxyCreate = h("b2c_proxy_create",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_SHORT, JAVA_SHORT, JAVA_INT, JAVA_INT, ADDRESS));
     static final MethodHandle proxyDestroy = h("b2c_proxy_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));

@@ -23,7 +23,7 @@ class Config(C.Structure):
         ("device", C.c_int32), ("broadphase_mode", C.c_int32), ("max_bodies", C.c_int32), ("max_pairs", C.c_int32),
         ("max_shapes", C.c_int32), ("max_hull_points", C.c_int32), ("max_mesh_items", C.c_int32), ("num_worlds", C.c_int32),
         ("contact_breaking_threshold", C.c_float), ("dbvt_margin", C.c_float), ("dbvt_predicted_frames", C.c_float),
-        ("reserved", C.c_int32 * 5),
+        ("max_compound_items", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -45,7 +45,7 @@ MANIFOLD_POINT_DTYPE = np.dtype([
 ])
 MANIFOLD_DTYPE = np.dtype([
     ("pair_uid0", np.int32), ("pair_uid1", np.int32), ("body0", np.int32), ("body1", np.int32), ("num_contacts", np.int32),
-    ("algorithm", np.int32), ("pad", np.int32, 2), ("points", MANIFOLD_POINT_DTYPE, 4),
+    ("algorithm", np.int32), ("child0", np.int32), ("child1", np.int32), ("points", MANIFOLD_POINT_DTYPE, 4),
 ])
 RAW_DTYPE = np.dtype([
     ("uid0", np.int32), ("uid1", np.int32), ("tri", np.int32), ("has_contact", np.int32), ("normal", np.float32, 3),
@@ -65,6 +65,7 @@ EXPORTS = [
     "b2c_set_profiling", "b2c_get_stage_times", "b2c_stage_name", "b2c_set_transforms_device", "b2c_set_partition", "b2c_mgpu_broadphase", "b2c_mgpu_export_departed",
     "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase", "b2c_mgpu_slot_bytes", "b2c_mgpu_export_departed_slot",
     "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest",
+    "b2c_shape_register_compound",
 ]
 NUM_STAGES = 12
 CONTACT_HEADER_DTYPE = np.dtype([
@@ -107,6 +108,7 @@ def load():
     L.b2c_shape_register_plane.argtypes = [vp, vp, f32, pi32]
     L.b2c_shape_register_mesh.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, pi32]
     L.b2c_mesh_get_bvh.argtypes = [vp, i32, vp, i32, pi32, vp]
+    L.b2c_shape_register_compound.argtypes = [vp, i32, vp, vp, pi32]
     L.b2c_proxy_create.argtypes = [vp, i32, vp, C.c_int16, C.c_int16, i32, i32, pi32]
     L.b2c_proxy_create_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, pi32]
     L.b2c_proxy_destroy.argtypes = [vp, i32]

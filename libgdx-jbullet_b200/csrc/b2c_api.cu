@@ -14,6 +14,7 @@
 #include "broadphase.cuh"
 #include "bvh_build.h"
 #include "common.cuh"
+#include "compound.cuh"
 #include "islands.cuh"
 #include "narrowphase.cuh"
 #include "pair_rows.cuh"
@@ -158,6 +159,23 @@ struct b2c_ctx {
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
     bool stageValid = false;
+
+    // compound shapes (compound.cuh) — buffers are allocated when the first one is registered
+    bool hasCompound = false;
+    std::vector<CompoundChildDev> hChildren;
+    CompoundChildDev* dChildren = nullptr;
+    size_t capChildren = 0;
+    uint32_t maxCompoundItems = 0;
+    CompoundCounters* dCompoundCtr = nullptr;
+    uint32_t* dCItemPair = nullptr;
+    uint32_t* dCItemCode = nullptr;
+    int* dCItemPrev = nullptr;
+    b2c_raw_contact* dCRaw = nullptr;
+    uint32_t* dCRetry = nullptr;
+    GjkResult* dCRetryRes = nullptr;
+    ManifoldHdr* dCH[2] = {nullptr, nullptr};          // child manifolds, ping-pong per dispatch
+    b2c_manifold_point* dCP[2] = {nullptr, nullptr};
+    int ccur = 0;                                      // index of the LATEST child-manifold arrays
 
     uint64_t* dNoCollide = nullptr;   // sorted keys of never-dispatched body pairs (b2c_set_no_collide_pairs)
     uint32_t numNoCollide = 0, capNoCollide = 0;
@@ -446,7 +464,26 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.noCollide = ctx->dNoCollide;
     a.numNoCollide = ctx->numNoCollide;
     a.uidBits = ctx->uidBits;
+    a.hasCompound = ctx->hasCompound ? 1 : 0;
     return a;
+}
+
+CompoundArgs makeCompoundArgs(b2c_ctx* ctx) {
+    CompoundArgs c;
+    c.children = ctx->dChildren;
+    c.cc = ctx->dCompoundCtr;
+    c.itemPair = ctx->dCItemPair;
+    c.itemCode = ctx->dCItemCode;
+    c.itemPrev = ctx->dCItemPrev;
+    c.raw = ctx->dCRaw;
+    c.retry = ctx->dCRetry;
+    c.retryRes = ctx->dCRetryRes;
+    c.H = ctx->dCH[ctx->ccur ^ 1];
+    c.P = ctx->dCP[ctx->ccur ^ 1];
+    c.prevH = ctx->dCH[ctx->ccur];
+    c.prevP = ctx->dCP[ctx->ccur];
+    c.maxItems = ctx->maxCompoundItems;
+    return c;
 }
 
 int32_t enqueueNarrowphase(b2c_ctx* ctx) {
@@ -544,6 +581,18 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         CK(cudaStreamWaitEvent(s, ctx->evJoin[0], 0));
     }
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
+    if (ctx->hasCompound) {
+        // CompoundShape pairs: expand into child work items, detect, retry the rare large EPA runs, per-child manifolds
+        CompoundArgs c = makeCompoundArgs(ctx);
+        CK(cudaMemsetAsync(ctx->dCompoundCtr, 0, sizeof(CompoundCounters), s));
+        const unsigned ig = gridFor(ctx->maxCompoundItems, 64, 148 * 8);
+        k_compound_expand<<<148, 128, 0, s>>>(a, c);
+        k_compound_detect<<<ig, 64, 0, s>>>(a, c);
+        k_compound_retry<<<148, 64, 2 * (int)sizeof(EpaScratch), s>>>(a, c);
+        k_compound_manifold<<<gridFor(ctx->maxCompoundItems, 128, 148 * 8), 128, 0, s>>>(a, c);
+        ctx->launches += 4;
+        ctx->ccur ^= 1;
+    }
     mark(ctx, 12);
     ctx->stageValid = ctx->prof;
     CK(cudaGetLastError());
@@ -588,6 +637,18 @@ int32_t readCounters(b2c_ctx* ctx) {
         ctx->err = "penetration-solver work list capacity exceeded";
         return B2C_ERR_CAPACITY;
     }
+    if (ctx->hasCompound) {
+        CompoundCounters cc;
+        CK(cudaMemcpyAsync(&cc, ctx->dCompoundCtr, sizeof(cc), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (cc.overflow) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "compound work-item capacity exceeded: need %u, max_compound_items %u", cc.itemCount,
+                     ctx->maxCompoundItems);
+            ctx->err = buf;
+            return B2C_ERR_CAPACITY;
+        }
+    }
     return B2C_OK;
 }
 
@@ -601,7 +662,8 @@ static void stepSignature(const b2c_ctx* ctx, int kind, uint64_t sig[4]) {
     sig[0] = ((uint64_t)(uint32_t)ctx->nBodies << 32) | (uint32_t)ctx->stagingCount;
     sig[1] = ((uint64_t)(uint32_t)(ctx->cur & 1)) | ((uint64_t)(ctx->extPending ? 1 : 0) << 1) | ((uint64_t)(ctx->hasPlane ? 1 : 0) << 2) |
              ((uint64_t)(ctx->hasMesh ? 1 : 0) << 3) | ((uint64_t)(ctx->overlap ? 1 : 0) << 4) | ((uint64_t)(ctx->aabbPending ? 1 : 0) << 5) |
-             ((uint64_t)(uint32_t)kind << 6) | ((uint64_t)(uint32_t)(ctx->epaHint + 1) << 8) | ((uint64_t)(uint32_t)lhint << 16) |
+             ((uint64_t)(uint32_t)kind << 6) | ((uint64_t)(uint32_t)(ctx->epaHint + 1) << 8) | ((uint64_t)(ctx->hasCompound ? 1 : 0) << 10) |
+             ((uint64_t)(uint32_t)(ctx->ccur & 1) << 11) | ((uint64_t)(uint32_t)lhint << 16) |
              ((uint64_t)(uint32_t)ctx->partRank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
     sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide;
     sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8);
@@ -648,6 +710,7 @@ static int32_t enqueuePhases(b2c_ctx* ctx, int kind) {
             ctx->step++;
             ctx->pairsValid = true;
         }
+        if (narrow && ctx->hasCompound) ctx->ccur ^= 1;
         ctx->stageValid = false;
         ctx->launches += hit->launches;
         CK(cudaGraphLaunch(hit->exec, s));
@@ -766,6 +829,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         // one-time kernel attributes (kept out of the per-step path so that it can be captured into a graph)
         cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPA_BLOCK * EPA_SMALL_STRIDE);
         cudaFuncSetAttribute(k_epa<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch));
+        cudaFuncSetAttribute(k_compound_retry, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(EpaScratch));
         const char* gr = getenv("B2C_GRAPH");
         ctx->useGraphs = !(gr && gr[0] == '0');
         const char* e = getenv("B2C_OVERLAP");  // measurement knob: 0 = everything on one stream
@@ -896,6 +960,9 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
     cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
     cudaFree(ctx->dNoCollide);
+    cudaFree(ctx->dChildren); cudaFree(ctx->dCompoundCtr); cudaFree(ctx->dCItemPair); cudaFree(ctx->dCItemCode); cudaFree(ctx->dCItemPrev);
+    cudaFree(ctx->dCRaw); cudaFree(ctx->dCRetry); cudaFree(ctx->dCRetryRes);
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->dCH[i]); cudaFree(ctx->dCP[i]); }
     cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
     for (int i = 0; i < 4; i++) {
         if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
@@ -1032,6 +1099,73 @@ int32_t b2c_shape_register_mesh(b2c_ctx* ctx, const void* vbase, int32_t nv, int
     ctx->hMeshes.push_back(md);
     ctx->meshes.push_back(std::move(hm));
     ctx->hasMesh = true;
+    return addShape(ctx, s, out);
+}
+// sh/CompoundShape.java:50-82: new CompoundShape() then addChildShape(localTransform_i, child_i) for i = 0..n-1
+int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* childShapes, const float* childXf12, int32_t* out) {
+    if (!ctx || !childShapes || !childXf12 || n < 1 || n > 32767) return B2C_ERR_BAD_ARG;
+    for (int i = 0; i < n; i++) {
+        if (childShapes[i] < 0 || childShapes[i] >= (int)ctx->hShapes.size()) return B2C_ERR_BAD_HANDLE;
+        const int t = ctx->hShapes[childShapes[i]].type;
+        if (t != SH_BOX && t != SH_SPHERE && t != SH_HULL) {
+            ctx->err = "compound children must be box, sphere or convex hull shapes";
+            return B2C_ERR_BAD_ARG;
+        }
+    }
+    if ((int)ctx->hShapes.size() >= ctx->cfg.max_shapes) { ctx->err = "shape table full"; return B2C_ERR_CAPACITY; }
+    cudaSetDevice(ctx->device);
+    if (!ctx->dCompoundCtr) {  // first compound: the child work-item arrays
+        const int want = ctx->cfg.max_compound_items;
+        size_t M = want > 0 ? (size_t)want : std::max<size_t>(65536, (size_t)ctx->cfg.max_pairs);
+        if (M > ((size_t)1 << 26)) M = (size_t)1 << 26;
+        ctx->maxCompoundItems = (uint32_t)M;
+        CK(dalloc(&ctx->dCompoundCtr, (size_t)1));
+        CK(dalloc(&ctx->dCItemPair, M));
+        CK(dalloc(&ctx->dCItemCode, M));
+        CK(dalloc(&ctx->dCItemPrev, M));
+        CK(dalloc(&ctx->dCRaw, M));
+        CK(dalloc(&ctx->dCRetry, M));
+        CK(dalloc(&ctx->dCRetryRes, M));
+        for (int i = 0; i < 2; i++) {
+            CK(dalloc(&ctx->dCH[i], M));
+            CK(dalloc(&ctx->dCP[i], 4 * M));
+        }
+    }
+    const int first = (int)ctx->hChildren.size();
+    for (int i = 0; i < n; i++) {
+        CompoundChildDev ch{};
+        for (int k = 0; k < 9; k++) ch.m[k] = childXf12[12 * i + k];
+        for (int k = 0; k < 3; k++) ch.o[k] = childXf12[12 * i + 9 + k];
+        ch.shape = childShapes[i];
+        ctx->hChildren.push_back(ch);
+    }
+    if (ctx->hChildren.size() > ctx->capChildren) {  // the table moves: graphs that captured the old pointer are stale
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+        ctx->graphs.clear();
+        cudaFree(ctx->dChildren);
+        ctx->dChildren = nullptr;
+        ctx->capChildren = std::max<size_t>(1024, 2 * ctx->hChildren.size());
+        CK(dalloc(&ctx->dChildren, ctx->capChildren));
+    }
+    CK(cudaMemcpy(ctx->dChildren, ctx->hChildren.data(), ctx->hChildren.size() * sizeof(CompoundChildDev), cudaMemcpyHostToDevice));
+    int32_t rc = uploadShapes(ctx);  // the children's records must be on the device for the AABB kernel below
+    if (rc) return rc;
+    float* d6 = nullptr;
+    float h6[6];
+    CK(cudaMalloc((void**)&d6, 6 * sizeof(float)));
+    k_compound_local_aabb<<<1, 1, 0, ctx->stream>>>(ctx->dShapes, ctx->dChildren, first, n, d6);
+    cudaError_t ce = cudaMemcpyAsync(h6, d6, sizeof(h6), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d6);
+    CK(ce);
+    ShapeDev s{};
+    s.type = SH_COMPOUND;
+    s.margin = 0.f;  // sh/CompoundShape.java:49 collisionMargin
+    for (int c = 0; c < 3; c++) { s.aabbMin[c] = h6[c]; s.aabbMax[c] = h6[3 + c]; }
+    s.pointOffset = first;
+    s.numPoints = n;
+    ctx->hasCompound = true;
     return addShape(ctx, s, out);
 }
 int32_t b2c_mesh_get_bvh(b2c_ctx* ctx, int32_t shape, void* nodesOut, int32_t cap, int32_t* numNodes, float quant9[9]) {
@@ -1376,6 +1510,24 @@ int32_t b2c_step(b2c_ctx* ctx, int32_t n, const float* planes, int32_t* numPairs
 }
 
 // ---- results -----------------------------------------------------------------------------------------
+// number of child algorithms of a compound pair: children(body0) x children(body1), a non-compound side counting as one
+static uint32_t hostCompoundCount(const b2c_ctx* ctx, int uid0, int uid1) {
+    const ShapeDev& S0 = ctx->hShapes[ctx->hShapeOf[uid0 - 1]];
+    const ShapeDev& S1 = ctx->hShapes[ctx->hShapeOf[uid1 - 1]];
+    const uint32_t n0 = S0.type == SH_COMPOUND ? (uint32_t)S0.numPoints : 1u;
+    const uint32_t n1 = S1.type == SH_COMPOUND ? (uint32_t)S1.numPoints : 1u;
+    return n0 * n1;
+}
+static int32_t compoundNumItems(b2c_ctx* ctx, uint32_t* nOut) {
+    *nOut = 0;
+    if (!ctx->hasCompound) return B2C_OK;
+    CompoundCounters cc;
+    CK(cudaMemcpyAsync(&cc, ctx->dCompoundCtr, sizeof(cc), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *nOut = cc.numItems <= ctx->maxCompoundItems ? cc.numItems : 0;
+    return B2C_OK;
+}
+
 int32_t b2c_get_manifolds(b2c_ctx* ctx, b2c_manifold* out, int32_t cap, int32_t onlyTouching, int32_t* numOut) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     if (!ctx->pairsValid) return B2C_ERR_STATE;
@@ -1390,19 +1542,40 @@ int32_t b2c_get_manifolds(b2c_ctx* ctx, b2c_manifold* out, int32_t cap, int32_t 
         CK(cudaMemcpyAsync(pts.data(), ctx->dMPts[ctx->cur], 4 * (size_t)n * sizeof(b2c_manifold_point), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    // child manifolds of the compound pairs (compound.cuh): the latest arrays, indexed through the pair's header
+    uint32_t nItems = 0;
+    int32_t rcc = compoundNumItems(ctx, &nItems);
+    if (rcc) return rcc;
+    std::vector<ManifoldHdr> chdr(nItems);
+    std::vector<b2c_manifold_point> cpts(4 * (size_t)nItems);
+    if (nItems) {
+        CK(cudaMemcpyAsync(chdr.data(), ctx->dCH[ctx->ccur], (size_t)nItems * sizeof(ManifoldHdr), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(cpts.data(), ctx->dCP[ctx->ccur], 4 * (size_t)nItems * sizeof(b2c_manifold_point), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     int32_t k = 0;
-    for (uint32_t p = 0; p < n; p++) {
-        const ManifoldHdr& h = hdr[p];
-        if (h.algorithm == 0) continue;
-        if (onlyTouching && h.num_contacts == 0) continue;
+    auto emit = [&](const ManifoldHdr& h, const b2c_manifold_point* pp, int child0, int child1) {
+        if (onlyTouching && h.num_contacts == 0) return;
         if (out && k < cap) {
             b2c_manifold& m = out[k];
             memset(&m, 0, sizeof(m));
             m.pair_uid0 = h.pair_uid0; m.pair_uid1 = h.pair_uid1; m.body0 = h.body0; m.body1 = h.body1;
             m.num_contacts = h.num_contacts; m.algorithm = h.algorithm;
-            for (int q = 0; q < h.num_contacts && q < 4; q++) m.points[q] = pts[4 * (size_t)p + q];
+            m.child0 = child0; m.child1 = child1;
+            for (int q = 0; q < h.num_contacts && q < 4; q++) m.points[q] = pp[q];
         }
         k++;
+    };
+    for (uint32_t p = 0; p < n; p++) {
+        const ManifoldHdr& h = hdr[p];
+        if (h.algorithm == 0) continue;
+        if (h.algorithm == 5) {  // compound pair: one manifold per child algorithm, in the order the reference runs them
+            const uint32_t start = (uint32_t)h.pad1, count = hostCompoundCount(ctx, h.pair_uid0, h.pair_uid1);
+            for (uint32_t q = start; q < start + count && q < nItems; q++)
+                if (chdr[q].algorithm != 0) emit(chdr[q], &cpts[4 * (size_t)q], chdr[q].pad0, chdr[q].pad1);
+            continue;
+        }
+        emit(h, &pts[4 * (size_t)p], -1, -1);
     }
     if (numOut) *numOut = k;
     if (out && k > cap) { ctx->err = "manifold output buffer too small"; return B2C_ERR_CAPACITY; }
@@ -1419,6 +1592,15 @@ int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, in
     std::vector<b2c_raw_contact> raw(n);
     std::vector<uint32_t> ms(n), mc(n);
     std::vector<uint8_t> binOf(n);
+    uint32_t nCItems = 0;
+    int32_t rcc = compoundNumItems(ctx, &nCItems);
+    if (rcc) return rcc;
+    std::vector<ManifoldHdr> hdr(ctx->hasCompound ? n : 0);
+    std::vector<b2c_raw_contact> craw(nCItems);
+    if (ctx->hasCompound && n) {
+        CK(cudaMemcpyAsync(hdr.data(), ctx->dMHdr[ctx->cur], (size_t)n * sizeof(ManifoldHdr), cudaMemcpyDeviceToHost, ctx->stream));
+        if (nCItems) CK(cudaMemcpyAsync(craw.data(), ctx->dCRaw, (size_t)nCItems * sizeof(b2c_raw_contact), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (n) {
         CK(cudaMemcpyAsync(raw.data(), ctx->dRaw, (size_t)n * sizeof(b2c_raw_contact), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(binOf.data(), ctx->dBinOf, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1441,7 +1623,16 @@ int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, in
     }
     int32_t k = 0;
     for (uint32_t p = 0; p < n; p++) {
-        if (binOf[p] == BIN_SKIP) continue;  // not dispatched (both bodies inactive, or no algorithm for the type pair)
+        if (binOf[p] == BIN_SKIP || binOf[p] == BIN_COMPOUND_KEEP) continue;  // not dispatched (both bodies inactive, or no algorithm for the type pair)
+        if (binOf[p] == BIN_COMPOUND) {  // one record per child algorithm (tri = -2 - k)
+            if (hdr[p].algorithm != 5) continue;
+            const uint32_t start = (uint32_t)hdr[p].pad1, count = hostCompoundCount(ctx, hdr[p].pair_uid0, hdr[p].pair_uid1);
+            for (uint32_t q = start; q < start + count && q < nCItems; q++) {
+                if (out && k < cap) out[k] = craw[q];
+                k++;
+            }
+            continue;
+        }
         if (raw[p].has_contact == -3) {
             for (uint32_t q = ms[p]; q < ms[p] + mc[p] && q < nItems; q++) {
                 if (out && k < cap) out[k] = rawMesh[q];
@@ -1507,6 +1698,19 @@ static int32_t getContactsImpl(b2c_ctx* ctx, bool slim, b2c_contact_header* hOut
     else
         k_compact_contacts<false><<<grid, 256, 0, s>>>(a, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
                                                        ctx->dContactCounts);
+    if (ctx->hasCompound) {  // the child manifolds of compound pairs: the same compaction over the latest item arrays
+        NpArgs a2 = a;
+        a2.mhdr = ctx->dCH[ctx->ccur];
+        a2.mpts = ctx->dCP[ctx->ccur];
+        a2.numPairs = &ctx->dCompoundCtr->numItems;
+        const unsigned g2 = gridFor(ctx->maxCompoundItems, 256);
+        if (slim)
+            k_compact_contacts<true><<<g2, 256, 0, s>>>(a2, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                         ctx->dContactCounts);
+        else
+            k_compact_contacts<false><<<g2, 256, 0, s>>>(a2, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                          ctx->dContactCounts);
+    }
     uint32_t counts[2] = {0, 0};
     CK(cudaMemcpyAsync(counts, ctx->dContactCounts, sizeof(counts), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

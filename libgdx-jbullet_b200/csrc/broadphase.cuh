@@ -65,6 +65,7 @@ __device__ __forceinline__ void shapeAabb(const ShapeDev& s, const Xf& t, f3& mn
         mx = add3(t.o, e);
         break;
     }
+    case SH_COMPOUND:  // sh/CompoundShape.java:124-160: the float sequence of lm/AabbUtil2.java:165-209 over the children's box
     case SH_HULL:  // sh/PolyhedralConvexShape.java:169-171 (margin counted twice)
         aabbFromLocalBox(mk3(s.aabbMin[0], s.aabbMin[1], s.aabbMin[2]), mk3(s.aabbMax[0], s.aabbMax[1], s.aabbMax[2]),
                          s.margin, t, mn, mx);

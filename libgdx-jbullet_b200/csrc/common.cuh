@@ -100,7 +100,7 @@ __host__ __device__ __forceinline__ Xf invMul(const Xf& a, const Xf& b) {
     return r;
 }
 
-enum { SH_BOX = 0, SH_SPHERE = 1, SH_HULL = 2, SH_TRIANGLE = 3, SH_PLANE = 4, SH_MESH = 5 };
+enum { SH_BOX = 0, SH_SPHERE = 1, SH_HULL = 2, SH_TRIANGLE = 3, SH_PLANE = 4, SH_MESH = 5, SH_COMPOUND = 6 };
 
 // One registered shape (64 B, read through the read-only path).
 struct ShapeDev {
@@ -109,11 +109,26 @@ struct ShapeDev {
     float dims[3];       // box: implicitShapeDimensions (half extents minus margin); sphere: dims[0] = radius
     float aabbMin[3];    // hull / mesh local AABB (sh/PolyhedralConvexShape.java:177-201, sh/TriangleMeshShape.java:79-93)
     float aabbMax[3];
-    int pointOffset;     // hull: first vertex in the float4 hull-point pool
-    int numPoints;
+    int pointOffset;     // hull: first vertex in the float4 hull-point pool; compound: first child in the child table
+    int numPoints;       // hull: vertices; compound: children
     float plane[4];      // static plane: unit normal, constant
     int mesh;            // index into the mesh table
 };
+
+// One child of a CompoundShape (sh/CompoundShapeChild.java:34-39): local transform + child shape id.  64 B.
+struct CompoundChildDev {
+    float m[9];          // childTransform basis, row-major
+    float o[3];          // childTransform origin
+    int shape;           // index into the shape table (box, sphere or hull)
+    int pad[3];
+};
+// Transform.mul(tr1, tr2) (lm/Transform.java:122-131): origin = tr1.transform(tr2.origin), basis = tr1.basis * tr2.basis
+__host__ __device__ __forceinline__ Xf mulXf(const Xf& a, const Xf& b) {
+    Xf r;
+    r.o = xfPoint(a, b.o);
+    mulMM(a.m, b.m, r.m);
+    return r;
+}
 
 // One registered triangle mesh with its quantized BVH (sh/OptimizedBvh.java, sh/QuantizedBvhNodes.java).
 struct MeshDev {

@@ -25,7 +25,10 @@ namespace b2c {
 // Convex-convex pairs are binned by which side is a hull (the only support mapping with a loop; box and sphere are a few
 // selects): BIN_GJK0 + 2*(A is hull) + (B is hull) for the pairs the prefilter looks at, BIN_PS0 + the same for the pairs that
 // went past the prefilter last step (history byte) — those go straight to the survivor list.
-enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_MESH = 3, BIN_GJK0 = 4, BIN_PS0 = 8, BIN_COUNT = 12 };
+// BIN_COMPOUND: pairs with a CompoundShape on either side (compound.cuh expands them into child work items);
+// BIN_COMPOUND_KEEP: such pairs that are not dispatched this step but own child manifolds that must stay alive.
+enum { BIN_SKIP = 0, BIN_SS = 1, BIN_CP = 2, BIN_MESH = 3, BIN_GJK0 = 4, BIN_PS0 = 8, BIN_COUNT = 12, BIN_COMPOUND = 12,
+       BIN_COMPOUND_KEEP = 13 };
 
 // Device-side split of b2c_manifold: the 32-byte header every kernel streams, and the point slots only the
 // touching pairs read.  The ABI's 416-byte record is assembled when results are copied out.
@@ -63,6 +66,7 @@ struct NpArgs {
     const uint64_t* noCollide;    // sorted (uid0 << uidBits | uid1) keys of body pairs that are never dispatched, or null
     uint32_t numNoCollide;
     int uidBits;
+    int hasCompound;              // a CompoundShape is registered: k_classify also looks at the pairs it does not dispatch
 };
 
 __device__ __forceinline__ MView mview(const NpArgs& a, uint32_t p) {
@@ -374,7 +378,10 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
                 const int4* src = reinterpret_cast<const int4*>(prevH + found);
                 h0 = src[0]; h1 = src[1];
                 nc = h1.x;
-                carriedManifold = h1.y != 0;  // algorithm field: the pair already owns a manifold
+                // algorithm field: the pair already owns a manifold.  5 = compound pair: its child manifolds live in the
+                // compound item arrays and are counted by k_compound_expand (header word pad0 = "counted this step")
+                carriedManifold = h1.y != 0 && h1.y != 5;
+                if (h1.y == 5) h1.z = 0;
             } else {
                 h0 = make_int4((int)uid0, (int)(k & ((1ull << uidBits) - 1ull)), 0, 0);
                 h1 = make_int4(0, 0, 0, 0);
@@ -488,6 +495,14 @@ k_import_arrival_slots(const unsigned char* __restrict__ slots, uint32_t nslots,
 // ---- k_classify: needsCollision + algorithm table --------------------------------------------------
 __device__ __forceinline__ bool isConvexType(int t) { return t == SH_BOX || t == SH_SPHERE || t == SH_HULL; }
 
+// compound x {box, sphere, hull, plane, compound}: children are convex, so every child algorithm is one of sphere-sphere,
+// convex-plane, convex-convex.  compound x triangle mesh (ConvexConcave per child) is not built: the pair is skipped.
+__device__ __forceinline__ bool compoundPairSupported(int t0, int t1) {
+    if (t0 != SH_COMPOUND && t1 != SH_COMPOUND) return false;
+    const int other = t0 == SH_COMPOUND ? t1 : t0;
+    return other == SH_COMPOUND || other == SH_PLANE || isConvexType(other);
+}
+
 __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
     const uint32_t n = *a.numPairs;
     __shared__ uint32_t hist[16];
@@ -516,6 +531,10 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
             else if (isConvexType(t0) && isConvexType(t1))
                 bin = (a.hist[p] >= 2 ? BIN_PS0 : BIN_GJK0) + (t0 == SH_HULL ? 2 : 0) + (t1 == SH_HULL ? 1 : 0);
             else if ((isConvexType(t0) && t1 == SH_MESH) || (isConvexType(t1) && t0 == SH_MESH)) bin = BIN_MESH;
+            else if (compoundPairSupported(t0, t1)) bin = BIN_COMPOUND;  // disp/DefaultCollisionConfiguration.java:198-204
+        } else if (a.hasCompound) {
+            int t0 = a.shapes[a.shape[b0]].type, t1 = a.shapes[a.shape[b1]].type;
+            if (compoundPairSupported(t0, t1)) bin = BIN_COMPOUND_KEEP;
         }
         a.binOf[p] = (uint8_t)bin;  // BIN_SKIP pairs are not dispatched: their raw record is not written this step
         // per-block histogram: one shared-memory atomic per group of lanes with the same bin

@@ -38,7 +38,8 @@ def transforms_to_planes(xf):
 
 class GpuCollisionWorld:
     def __init__(self, mode=DBVT, max_bodies=131072, max_pairs=2 << 20, num_worlds=1, device=0, max_mesh_items=1 << 20,
-                 max_hull_points=1 << 20, max_shapes=4096, contact_breaking_threshold=0.02, world_aabb=None):
+                 max_hull_points=1 << 20, max_shapes=4096, contact_breaking_threshold=0.02, world_aabb=None,
+                 max_compound_items=0):
         self.L = _lib.load()
         cfg = Config()
         self.L.b2c_default_config(C.byref(cfg))
@@ -51,6 +52,7 @@ class GpuCollisionWorld:
         cfg.max_hull_points = max_hull_points
         cfg.max_shapes = max_shapes
         cfg.contact_breaking_threshold = contact_breaking_threshold
+        cfg.max_compound_items = max_compound_items
         self.cfg = cfg
         h = C.c_void_p()
         rc = self.L.b2c_create(C.byref(cfg), C.byref(h))
@@ -110,6 +112,16 @@ class GpuCollisionWorld:
         s = np.asarray(scaling, dtype=np.float32)
         out = C.c_int32()
         self._ck(self.L.b2c_shape_register_mesh(self.h, _vp(v), len(v), 12, _vp(i), len(i), 12, _vp(s), C.byref(out)))
+        return out.value
+
+    def CompoundShape(self, child_shapes, child_transforms):
+        """new CompoundShape() + addChildShape(child_transforms[i], child_shapes[i]) in order (sh/CompoundShape.java:50-82)."""
+        cs = np.ascontiguousarray(child_shapes, dtype=np.int32)
+        xf = np.ascontiguousarray(child_transforms, dtype=np.float32).reshape(-1, 12)
+        if len(cs) != len(xf):
+            raise ValueError("one transform per child")
+        out = C.c_int32()
+        self._ck(self.L.b2c_shape_register_compound(self.h, len(cs), _vp(cs), _vp(xf), C.byref(out)))
         return out.value
 
     def mesh_bvh(self, shape):

@@ -75,6 +75,14 @@ int orc_shape_plane(void* h, float nx, float ny, float nz, float c) {
     initPlane(s, V3(nx, ny, nz), c);
     return ((World*)h)->addShape(s);
 }
+// sh/CompoundShape.java:50-82: n children (shape ids registered before) under local transforms (n x 12 floats)
+int orc_shape_compound(void* h, int n, const int* childShapes, const float* childXf12) {
+    World* w = (World*)h;
+    for (int i = 0; i < n; i++) {
+        if (childShapes[i] < 0 || childShapes[i] >= (int)w->shapes.size() || !w->shapes[childShapes[i]].isConvex()) return -1;
+    }
+    return w->addCompound(n, childShapes, childXf12);
+}
 int orc_shape_mesh(void* h, const float* verts, int nv, const int* idx, int ntri) {
     return ((World*)h)->addMesh(verts, nv, idx, ntri);
 }
@@ -183,38 +191,47 @@ void orc_get_raw(void* h, int* ints6, float* floats7) {
         floats7[7 * i + 6] = r.depth;
     }
 }
-// Manifolds in pair order.  Per manifold: ints[4] = (pairUid0, pairUid1, body0, body1), nContacts;
-// per point (4 slots): 16 floats = localA(3) localB(3) worldA(3) worldB(3) normal(3) distance(1),
-// and 7 ints = lifeTime, srcSlot, partId0, partId1, index0, index1, pad; plus friction/restitution floats.
-int orc_get_manifolds(void* h, int cap, int* hdr5, float* pts /*cap*4*18*/, int* pint /*cap*4*6*/) {
+// Manifolds in pair order (the child manifolds of a compound pair in the order its child algorithms run).  Per manifold:
+// hdr7 = (pairUid0, pairUid1, body0, body1, nContacts, child index in body0's compound shape or -1, the same for body1);
+// per point (4 slots): 18 floats = localA(3) localB(3) worldA(3) worldB(3) normal(3) distance friction restitution,
+// and 6 ints = lifeTime, srcSlot, partId0, partId1, index0, index1.
+static void emitManifold(const std::pair<int, int>& key, const PersistentManifold& m, int child0, int child1, int n, int* hdr7,
+                         float* pts, int* pint) {
+    hdr7[7 * n + 0] = key.first; hdr7[7 * n + 1] = key.second;
+    hdr7[7 * n + 2] = m.body0; hdr7[7 * n + 3] = m.body1; hdr7[7 * n + 4] = m.cachedPoints;
+    hdr7[7 * n + 5] = child0; hdr7[7 * n + 6] = child1;
+    for (int k = 0; k < 4; k++) {
+        const ManifoldPoint& p = m.pointCache[k];
+        float* f = pts + ((size_t)n * 4 + k) * 18;
+        int* ii = pint + ((size_t)n * 4 + k) * 6;
+        if (k >= m.cachedPoints) {
+            for (int q = 0; q < 18; q++) f[q] = 0;
+            for (int q = 0; q < 6; q++) ii[q] = 0;
+            continue;
+        }
+        f[0] = p.localPointA.x; f[1] = p.localPointA.y; f[2] = p.localPointA.z;
+        f[3] = p.localPointB.x; f[4] = p.localPointB.y; f[5] = p.localPointB.z;
+        f[6] = p.positionWorldOnA.x; f[7] = p.positionWorldOnA.y; f[8] = p.positionWorldOnA.z;
+        f[9] = p.positionWorldOnB.x; f[10] = p.positionWorldOnB.y; f[11] = p.positionWorldOnB.z;
+        f[12] = p.normalWorldOnB.x; f[13] = p.normalWorldOnB.y; f[14] = p.normalWorldOnB.z;
+        f[15] = p.distance1; f[16] = p.combinedFriction; f[17] = p.combinedRestitution;
+        ii[0] = p.lifeTime; ii[1] = p.srcSlot; ii[2] = p.partId0; ii[3] = p.partId1;
+        ii[4] = p.index0; ii[5] = p.index1;
+    }
+}
+int orc_get_manifolds(void* h, int cap, int* hdr7, float* pts /*cap*4*18*/, int* pint /*cap*4*6*/) {
     World* w = (World*)h;
     int n = 0;
     for (auto& kv : w->pairState) {
-        if (!kv.second.hasManifold) continue;
-        if (n < cap) {
-            const PersistentManifold& m = kv.second.manifold;
-            hdr5[5 * n + 0] = kv.first.first; hdr5[5 * n + 1] = kv.first.second;
-            hdr5[5 * n + 2] = m.body0; hdr5[5 * n + 3] = m.body1; hdr5[5 * n + 4] = m.cachedPoints;
-            for (int k = 0; k < 4; k++) {
-                const ManifoldPoint& p = m.pointCache[k];
-                float* f = pts + ((size_t)n * 4 + k) * 18;
-                int* ii = pint + ((size_t)n * 4 + k) * 6;
-                if (k >= m.cachedPoints) {
-                    for (int q = 0; q < 18; q++) f[q] = 0;
-                    for (int q = 0; q < 6; q++) ii[q] = 0;
-                    continue;
-                }
-                f[0] = p.localPointA.x; f[1] = p.localPointA.y; f[2] = p.localPointA.z;
-                f[3] = p.localPointB.x; f[4] = p.localPointB.y; f[5] = p.localPointB.z;
-                f[6] = p.positionWorldOnA.x; f[7] = p.positionWorldOnA.y; f[8] = p.positionWorldOnA.z;
-                f[9] = p.positionWorldOnB.x; f[10] = p.positionWorldOnB.y; f[11] = p.positionWorldOnB.z;
-                f[12] = p.normalWorldOnB.x; f[13] = p.normalWorldOnB.y; f[14] = p.normalWorldOnB.z;
-                f[15] = p.distance1; f[16] = p.combinedFriction; f[17] = p.combinedRestitution;
-                ii[0] = p.lifeTime; ii[1] = p.srcSlot; ii[2] = p.partId0; ii[3] = p.partId1;
-                ii[4] = p.index0; ii[5] = p.index1;
-            }
+        if (kv.second.hasManifold) {
+            if (n < cap) emitManifold(kv.first, kv.second.manifold, -1, -1, n, hdr7, pts, pint);
+            n++;
         }
-        n++;
+        for (size_t k = 0; k < kv.second.kids.size(); k++) {
+            if (!kv.second.kids[k].hasManifold) continue;
+            if (n < cap) emitManifold(kv.first, kv.second.kids[k].manifold, kv.second.kidChild[k].first, kv.second.kidChild[k].second, n, hdr7, pts, pint);
+            n++;
+        }
     }
     return n;
 }

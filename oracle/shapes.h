@@ -8,9 +8,14 @@
 
 namespace orc {
 
-enum ShapeType { SH_BOX = 0, SH_SPHERE = 1, SH_HULL = 2, SH_TRIANGLE = 3, SH_PLANE = 4, SH_MESH = 5 };
+enum ShapeType { SH_BOX = 0, SH_SPHERE = 1, SH_HULL = 2, SH_TRIANGLE = 3, SH_PLANE = 4, SH_MESH = 5, SH_COMPOUND = 6 };
 
 struct Bvh;  // bvh.h
+
+struct CompoundChild {  // sh/CompoundShapeChild.java:34-39
+    Xf transform;
+    int shape = -1;      // index of the child shape in World::shapes (childShape)
+};
 
 struct Shape {
     int type = SH_BOX;
@@ -22,9 +27,11 @@ struct Shape {
     V3 tri[3];                     // sh/TriangleShape.java vertices1
     V3 planeNormal; float planeConstant = 0;  // sh/StaticPlaneShape.java:41-42
     Bvh* bvh = nullptr;            // sh/BvhTriangleMeshShape.java:50
+    std::vector<CompoundChild> children;  // sh/CompoundShape.java:43 (localAabbMin/Max above double as :44-45)
 
     bool isConvex() const { return type == SH_BOX || type == SH_SPHERE || type == SH_HULL || type == SH_TRIANGLE; }
     bool isConcave() const { return type == SH_MESH || type == SH_PLANE; }  // bp/BroadphaseNativeType.java:95-98
+    bool isCompound() const { return type == SH_COMPOUND; }                  // bp/BroadphaseNativeType.java:104-106
 
     // sh/SphereShape.java:83-97 ; sh/ConvexInternalShape.java:111 ; sh/ConcaveShape.java:39
     float getMargin() const {
@@ -199,6 +206,9 @@ static inline void shapeGetAabb(const Shape& s, const Xf& t, V3& mn, V3& mx) {
         return;
     }
     case SH_HULL:  // sh/PolyhedralConvexShape.java:169-171 (margin applied a second time: SURVEY Q8)
+        transformAabbMM(s.localAabbMin, s.localAabbMax, s.getMargin(), t, mn, mx);
+        return;
+    case SH_COMPOUND:  // sh/CompoundShape.java:124-160: the same float sequence as lm/AabbUtil2.java:165-209 (margin 0 unless set)
         transformAabbMM(s.localAabbMin, s.localAabbMax, s.getMargin(), t, mn, mx);
         return;
     case SH_PLANE:  // sh/StaticPlaneShape.java:125-128

@@ -64,6 +64,11 @@ struct RawContact {  // one detector result, before ManifoldResult
 struct PairState {
     PersistentManifold manifold;
     bool hasManifold = false;
+    // CompoundCollisionAlgorithm.childCollisionAlgorithms (disp/CompoundCollisionAlgorithm.java:46): one child algorithm, and
+    // so one manifold, per child (per child x child when both shapes are compounds), in the order processCollision visits them
+    std::vector<PairState> kids;
+    std::vector<std::pair<int, int>> kidChild;  // (child index in manifold.body0's shape, in body1's shape), -1 = not a compound
+    bool isCompound = false;
 };
 
 struct MeshShapeData {
@@ -121,6 +126,29 @@ struct World {
         shapes.push_back(s);
         meshes.emplace_back(nullptr);
         return (int)shapes.size() - 1;
+    }
+    // sh/CompoundShape.java:50-82 addChildShape for every child: the local AABB is the running Math.min / Math.max of the
+    // children's AABBs under their local transforms.  Children must be convex here (box, sphere, hull).
+    int addCompound(int n, const int* childShapes, const float* childXf12) {
+        Shape s;
+        s.type = SH_COMPOUND;
+        s.collisionMargin = 0.0f;  // sh/CompoundShape.java:49
+        s.localAabbMin.set(1e30f, 1e30f, 1e30f);     // :44
+        s.localAabbMax.set(-1e30f, -1e30f, -1e30f);  // :45
+        for (int i = 0; i < n; i++) {
+            CompoundChild c;
+            const float* t = childXf12 + 12 * i;
+            for (int r = 0; r < 3; r++)
+                for (int k = 0; k < 3; k++) c.transform.basis.m[r][k] = t[r * 3 + k];
+            c.transform.origin.set(t[9], t[10], t[11]);
+            c.shape = childShapes[i];
+            V3 mn, mx;
+            shapeGetAabb(shapes[c.shape], c.transform, mn, mx);
+            s.localAabbMin.set(jminf(s.localAabbMin.x, mn.x), jminf(s.localAabbMin.y, mn.y), jminf(s.localAabbMin.z, mn.z));  // lm/VectorUtil.java:176-180
+            s.localAabbMax.set(jmaxf(s.localAabbMax.x, mx.x), jmaxf(s.localAabbMax.y, mx.y), jmaxf(s.localAabbMax.z, mx.z));  // :182-186
+            s.children.push_back(c);
+        }
+        return addShape(s);
     }
     int addMesh(const float* verts, int nv, const int* idx, int ntri) {
         std::unique_ptr<MeshShapeData> md(new MeshShapeData());
@@ -518,6 +546,56 @@ struct World {
         if (out.hasContact) res.addContactPoint(out.normalOnBInWorld, out.pointInWorld, out.depth);
     }
 
+    // One child algorithm of a compound pair: findAlgorithm(colObj with its temporary child shape, otherObj) picked from
+    // the table (disp/DefaultCollisionConfiguration.java:149-213), with its own manifold (getNewManifold(body0, body1) of the
+    // child algorithm: disp/SphereSphereCollisionAlgorithm.java:49-60, disp/ConvexPlaneCollisionAlgorithm.java:57-67,
+    // disp/ConvexConvexAlgorithm.java:92-96).  A = the compound's child, B = the other object (or its child).
+    void compoundLeaf(const Shape* sa, int childA, const Body& a, const Shape* sb, int childB, const Body& b, ManifoldResult& res,
+                      PairState& ps, int& k) {
+        if ((int)ps.kids.size() <= k) { ps.kids.resize(k + 1); ps.kidChild.resize(k + 1, std::make_pair(-1, -1)); }
+        PairState& kid = ps.kids[k];
+        ps.kidChild[k] = std::make_pair(childA, childB);
+        const int code = -2 - k;
+        k++;
+        kid.manifold.breakingThreshold = breakingThreshold;
+        for (int q = 0; q < 4; q++) kid.manifold.pointCache[q].srcSlot = (q < kid.manifold.cachedPoints) ? q : -1;
+        res.manifoldPtr = &kid.manifold;
+        size_t rawBefore = raw.size();
+        if (sa->type == SH_SPHERE && sb->type == SH_SPHERE) {
+            if (!kid.hasManifold) { kid.hasManifold = true; kid.manifold.body0 = a.uid; kid.manifold.body1 = b.uid; }
+            sphereSphere(sa, sb, a, b, res);
+        } else if (sa->isConvex() && sb->type == SH_PLANE) {
+            if (!kid.hasManifold) { kid.hasManifold = true; kid.manifold.body0 = a.uid; kid.manifold.body1 = b.uid; }
+            convexPlane(sa, sb, a, b, res);
+        } else if (sa->isConvex() && sb->isConvex()) {
+            if (!kid.hasManifold) { kid.hasManifold = true; kid.manifold.body0 = a.uid; kid.manifold.body1 = b.uid; }
+            convexConvex(sa, sb, a, b, res, true, code);
+        } else {
+            // child x triangle mesh (ConvexConcave per child) is not restated: neither side generates contacts for it
+        }
+        for (size_t r = rawBefore; r < raw.size(); r++) { raw[r].uid0 = res.body0; raw[r].uid1 = res.body1; raw[r].tri = code; }
+    }
+    // disp/CompoundCollisionAlgorithm.java:83-129 processCollision: every child in turn, the compound's object temporarily
+    // carrying the child's shape and orgTrans * childTrans; contact points are still projected with the original transforms
+    // (res keeps rootTransA / rootTransB of the pair's two objects).  `other` may itself be a compound: its child algorithm is
+    // then the swapped compound algorithm over ITS children, against this child (:57-75 init -> findAlgorithm).
+    void compoundProcess(const Body& colObj, const Body& otherObj, const Shape* otherShape, int otherChild, ManifoldResult& res,
+                         PairState& ps, int& k) {
+        const Shape& cs = shapes[colObj.shape];
+        for (size_t i = 0; i < cs.children.size(); i++) {
+            Body tmp = colObj;                 // colObj.setWorldTransform(newChildWorldTrans)
+            tmp.xf.set(colObj.xf);
+            tmp.xf.mul(cs.children[i].transform);  // newChildWorldTrans.mul(orgTrans, childTrans) (lm/Transform.java:122-131)
+            const Shape* childShape = &shapes[cs.children[i].shape];
+            if (otherShape->isCompound()) {
+                // algorithm(child i of colObj, compound other) = swapped CompoundCollisionAlgorithm: its colObj is `other`
+                compoundProcess(otherObj, tmp, childShape, (int)i, res, ps, k);
+            } else {
+                compoundLeaf(childShape, (int)i, tmp, otherShape, otherChild, otherObj, res, ps, k);
+            }
+        }
+    }
+
     // Dispatcher.dispatchAllCollisionPairs over the current pair set.  Returns number of manifolds.
     int dispatchAllPairs() {
         raw.clear();
@@ -570,14 +648,25 @@ struct World {
                 if (!ps.hasManifold) { ps.hasManifold = true; }
                 ps.manifold.body0 = b1.uid; ps.manifold.body1 = b0.uid;
                 convexConcave(s1, s0, b1, b0, res);
+            } else if (s0->isCompound()) {          // compoundCreateFunc (disp/DefaultCollisionConfiguration.java:198-200)
+                ps.isCompound = true;
+                int k = 0;
+                compoundProcess(b0, b1, s1, -1, res, ps, k);
+            } else if (s1->isCompound()) {          // swappedCompoundCreateFunc (:202-204)
+                ps.isCompound = true;
+                int k = 0;
+                compoundProcess(b1, b0, s0, -1, res, ps, k);
             } else {
                 // EmptyAlgorithm: no manifold
             }
             addedContacts += res.addedContacts - before;
         }
         int n = 0;
-        for (auto& kv : pairState)
+        for (auto& kv : pairState) {
             if (kv.second.hasManifold) n++;
+            for (auto& kid : kv.second.kids)
+                if (kid.hasManifold) n++;
+        }
         return n;
     }
 };

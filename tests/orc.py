@@ -43,6 +43,7 @@ def lib():
     L.orc_shape_hull.argtypes = [C.c_void_p, f32p, C.c_int]
     L.orc_shape_plane.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
     L.orc_shape_mesh.argtypes = [C.c_void_p, f32p, C.c_int, i32p, C.c_int]
+    L.orc_shape_compound.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
     L.orc_mesh_num_nodes.argtypes = [C.c_void_p, C.c_int]
     L.orc_mesh_get_nodes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.orc_mesh_get_quant.argtypes = [C.c_void_p, C.c_int, f32p]
@@ -123,6 +124,15 @@ class OracleWorld:
 
     def plane(self, n, c):
         return self.L.orc_shape_plane(self.h, n[0], n[1], n[2], c)
+
+    def compound(self, child_shapes, child_xf):
+        """CompoundShape with addChildShape(child_xf[i], child_shapes[i]) in order (sh/CompoundShape.java:50-82)."""
+        cs = np.ascontiguousarray(child_shapes, dtype=np.int32)
+        xf = np.ascontiguousarray(child_xf, dtype=np.float32).reshape(-1, 12)
+        assert len(cs) == len(xf)
+        sid = self.L.orc_shape_compound(self.h, len(cs), cs, xf)
+        assert sid >= 0, "compound children must be convex shapes registered before"
+        return sid
 
     def mesh(self, verts, idx):
         verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
@@ -218,9 +228,9 @@ class OracleWorld:
         return ints, fl
 
     def manifolds(self):
-        hdr0 = np.zeros((1, 5), dtype=np.int32)
+        hdr0 = np.zeros((1, 7), dtype=np.int32)
         n = self.L.orc_get_manifolds(self.h, 0, hdr0, np.zeros(1, np.float32), np.zeros(1, np.int32))
-        hdr = np.zeros((max(n, 1), 5), dtype=np.int32)
+        hdr = np.zeros((max(n, 1), 7), dtype=np.int32)
         pts = np.zeros((max(n, 1), 4, 18), dtype=np.float32)
         pint = np.zeros((max(n, 1), 4, 6), dtype=np.int32)
         self.L.orc_get_manifolds(self.h, n, hdr, pts, pint)

@@ -70,6 +70,8 @@ def compare_manifolds(gm, om, extent):
         return dict(manifolds=0, points=0)
     assert np.array_equal(gm["pair_uid0"], hdr[:, 0]) and np.array_equal(gm["pair_uid1"], hdr[:, 1]), "manifold pair keys differ"
     assert np.array_equal(gm["body0"], hdr[:, 2]) and np.array_equal(gm["body1"], hdr[:, 3]), "manifold body order differs"
+    if hdr.shape[1] >= 7:  # child manifolds of compound pairs: which child of body0's / body1's CompoundShape
+        assert np.array_equal(gm["child0"], hdr[:, 5]) and np.array_equal(gm["child1"], hdr[:, 6]), "compound child indices differ"
     bad = np.nonzero(gm["num_contacts"] != hdr[:, 4])[0]
     assert len(bad) == 0, f"num_contacts differs at {[(int(hdr[b,0]), int(hdr[b,1]), int(gm['num_contacts'][b]), int(hdr[b,4])) for b in bad[:6]]}"
     total = 0

