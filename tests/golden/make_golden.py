@@ -21,6 +21,8 @@ CASES = {
     "c2_bin_dbvt": (lambda: scenes.bin_scene(n=400, seed=9), orc.DBVT, 4),
     "c3_terrain_dbvt": (lambda: scenes.terrain_scene(cells=24, n=60, seed=4), orc.DBVT, 3),
     "c4_worlds_dbvt": (lambda: scenes.worlds_scene(num_worlds=4, seed=5), orc.DBVT, 3),
+    # CompoundShape pairs (child manifolds carry child indices in mf_hdr columns 5, 6)
+    "c6_compound_dbvt": (lambda: scenes.compound_scene(n=120, seed=8), orc.DBVT, 4),
 }
 
 
@@ -47,7 +49,10 @@ def run_case(make, mode, steps):
 
 
 def main():
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases
     for name, (make, mode, steps) in CASES.items():
+        if only and name not in only:
+            continue
         out = run_case(make, mode, steps)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith("pairs")})

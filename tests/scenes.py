@@ -274,7 +274,7 @@ def spheres_scene(n=20000, seed=6, radius=0.5, fill=0.40):
     return sc
 
 
-def compound_scene(n=300, seed=8, plane_ground=True, spacing=1.15, compound_share=0.5):
+def compound_scene(n=300, seed=8, plane_ground=True, spacing=0.9, compound_share=0.5):
     """compounds (dumbbells, L-brackets, hull+sphere clusters, three-box crosses) mixed with plain boxes,
     spheres and hulls on a jittered lattice over a static plane (or box) floor, close enough that compound x {sphere, box,
     hull, plane / static box, compound} pairs all occur, some of them penetrating."""
