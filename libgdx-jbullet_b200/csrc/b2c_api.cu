@@ -171,8 +171,6 @@ struct b2c_ctx {
     uint32_t* dCItemCode = nullptr;
     int* dCItemPrev = nullptr;
     b2c_raw_contact* dCRaw = nullptr;
-    uint32_t* dCRetry = nullptr;
-    GjkResult* dCRetryRes = nullptr;
     ManifoldHdr* dCH[2] = {nullptr, nullptr};          // child manifolds, ping-pong per dispatch
     b2c_manifold_point* dCP[2] = {nullptr, nullptr};
     int ccur = 0;                                      // index of the LATEST child-manifold arrays
@@ -476,8 +474,6 @@ CompoundArgs makeCompoundArgs(b2c_ctx* ctx) {
     c.itemCode = ctx->dCItemCode;
     c.itemPrev = ctx->dCItemPrev;
     c.raw = ctx->dCRaw;
-    c.retry = ctx->dCRetry;
-    c.retryRes = ctx->dCRetryRes;
     c.H = ctx->dCH[ctx->ccur ^ 1];
     c.P = ctx->dCP[ctx->ccur ^ 1];
     c.prevH = ctx->dCH[ctx->ccur];
@@ -504,6 +500,8 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     g.meshStart = ctx->dMeshStart;
     g.meshCount = ctx->dMeshCount;
     g.maxMeshItems = (uint32_t)ctx->cfg.max_mesh_items;
+    g.comp = CompoundArgs{};
+    if (ctx->hasCompound) g.comp = makeCompoundArgs(ctx);
     const unsigned pg = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
     mark(ctx, 8);
     k_clear_np_counters<<<1, 32, 0, s>>>(ctx->dCtr);
@@ -544,6 +542,14 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         k_gjk_tri<<<148 * 4, 128, 0, s>>>(a, g, ctx->dCursors + 1);
         ctx->launches += 2;
     }
+    if (ctx->hasCompound) {
+        // CompoundShape pairs: expand into child work items, run their detectors; items that need the penetration solver
+        // join the bin below, the per-child manifolds follow at the end of the dispatch
+        CK(cudaMemsetAsync(ctx->dCompoundCtr, 0, sizeof(CompoundCounters), s));
+        k_compound_expand<<<148, 128, 0, s>>>(a, g.comp);
+        k_compound_gjk<<<148 * 4, 128, 0, s>>>(a, g, ctx->dCursors + 3);
+        ctx->launches += 2;
+    }
     mark(ctx, 11);
     // the penetration bin is a handful of long, latency-bound lanes: it runs on its own (high-priority) stream while
     // k_manifold_cc streams through the manifolds of all the other pairs
@@ -582,15 +588,9 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     }
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
     if (ctx->hasCompound) {
-        // CompoundShape pairs: expand into child work items, detect, retry the rare large EPA runs, per-child manifolds
-        CompoundArgs c = makeCompoundArgs(ctx);
-        CK(cudaMemsetAsync(ctx->dCompoundCtr, 0, sizeof(CompoundCounters), s));
-        const unsigned ig = gridFor(ctx->maxCompoundItems, 64, 148 * 8);
-        k_compound_expand<<<148, 128, 0, s>>>(a, c);
-        k_compound_detect<<<ig, 64, 0, s>>>(a, c);
-        k_compound_retry<<<148, 64, 2 * (int)sizeof(EpaScratch), s>>>(a, c);
-        k_compound_manifold<<<gridFor(ctx->maxCompoundItems, 128, 148 * 8), 128, 0, s>>>(a, c);
-        ctx->launches += 4;
+        // per-child manifolds of the compound pairs, once every detector (and the penetration bin) has finished
+        k_compound_manifold<<<gridFor(ctx->maxCompoundItems, 128, 148 * 8), 128, 0, s>>>(a, g.comp);
+        ctx->launches += 1;
         ctx->ccur ^= 1;
     }
     mark(ctx, 12);
@@ -829,7 +829,6 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         // one-time kernel attributes (kept out of the per-step path so that it can be captured into a graph)
         cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPA_BLOCK * EPA_SMALL_STRIDE);
         cudaFuncSetAttribute(k_epa<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch));
-        cudaFuncSetAttribute(k_compound_retry, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(EpaScratch));
         const char* gr = getenv("B2C_GRAPH");
         ctx->useGraphs = !(gr && gr[0] == '0');
         const char* e = getenv("B2C_OVERLAP");  // measurement knob: 0 = everything on one stream
@@ -961,7 +960,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
     cudaFree(ctx->dNoCollide);
     cudaFree(ctx->dChildren); cudaFree(ctx->dCompoundCtr); cudaFree(ctx->dCItemPair); cudaFree(ctx->dCItemCode); cudaFree(ctx->dCItemPrev);
-    cudaFree(ctx->dCRaw); cudaFree(ctx->dCRetry); cudaFree(ctx->dCRetryRes);
+    cudaFree(ctx->dCRaw);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->dCH[i]); cudaFree(ctx->dCP[i]); }
     cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
     for (int i = 0; i < 4; i++) {
@@ -1124,8 +1123,6 @@ int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* chil
         CK(dalloc(&ctx->dCItemCode, M));
         CK(dalloc(&ctx->dCItemPrev, M));
         CK(dalloc(&ctx->dCRaw, M));
-        CK(dalloc(&ctx->dCRetry, M));
-        CK(dalloc(&ctx->dCRetryRes, M));
         for (int i = 0; i < 2; i++) {
             CK(dalloc(&ctx->dCH[i], M));
             CK(dalloc(&ctx->dCP[i], 4 * M));

@@ -12,9 +12,9 @@
 //   k_compound_expand    one thread per compound pair: reserves count = n0 * n1 consecutive items, remembers where the pair's
 //                        items of the previous dispatch start (kept in the pair's manifold header, which k_carry moves with
 //                        the pair), so child manifolds persist exactly as long as the pair stays in the cache
-//   k_compound_detect    one thread per item: the child algorithm's detector — sphere-sphere, convex-plane, or GJK (+ EPA with
-//                        the medium pool in local memory) on (child shape, orgTrans * childTrans) — into a raw record
-//   k_compound_retry     the few items whose EPA overflowed the medium pool: one item per warp, large pool in shared memory
+//   k_compound_gjk       the child algorithm's detector — sphere-sphere, convex-plane, or GJK on (child shape,
+//                        orgTrans * childTrans) — into a raw record; persistent lanes that refill as their item ends
+//   k_epa (narrowphase.cuh) items whose GJK asks for the penetration solver join the pairs' penetration bin: same tiers
 //   k_compound_manifold  one thread per item: manifold of the previous dispatch -> this dispatch's slot, then
 //                        ManifoldResult.addContactPoint / refreshContactPoints against the ORIGINAL transforms of the pair's
 //                        two objects ("the contactpoint is still projected back using the original inverted worldtrans", :112)
@@ -33,80 +33,6 @@
 #include "narrowphase.cuh"
 
 namespace b2c {
-
-struct CompoundCounters {
-    uint32_t itemCount;   // items reserved by k_compound_expand (may exceed the capacity -> overflow)
-    uint32_t overflow;
-    uint32_t numItems;    // items the later kernels and the result calls may touch (0 after an overflow)
-    uint32_t retryCount;
-};
-
-constexpr uint32_t CITEM_KEEP = 0x80000000u;  // itemCode flag: copy the manifold forward, do nothing else
-
-struct CompoundArgs {
-    const CompoundChildDev* children;
-    CompoundCounters* cc;          // cleared per dispatch
-    uint32_t* itemPair;            // [maxItems] pair index
-    uint32_t* itemCode;            // [maxItems] k = i * n1 + j (index of the item inside its pair) | CITEM_KEEP
-    int* itemPrev;                 // [maxItems] the same item in the previous dispatch's arrays, or -1
-    b2c_raw_contact* raw;          // [maxItems] detector output
-    uint32_t* retry;               // [maxItems] items waiting for the large EPA pool
-    GjkResult* retryRes;           // [maxItems] their GJK state
-    ManifoldHdr* H;                // [maxItems] child manifolds of this dispatch (header word pad0 / pad1 = child index in
-    b2c_manifold_point* P;         //            body0's / body1's compound shape, -1 = that object is not a compound)
-    const ManifoldHdr* prevH;      // the previous dispatch's
-    const b2c_manifold_point* prevP;
-    uint32_t maxItems;
-};
-
-struct CompoundItem {
-    int2 pr;            // the broadphase pair (uid0 < uid1)
-    int bodyA, bodyB;   // 0-based body indices of the child algorithm's body0 / body1
-    int shapeA, shapeB; // shape table indices (A: a compound's child; B: the other object's shape or its child)
-    int childA, childB; // child index inside its compound, -1 = not a compound
-    Xf tA, tB;          // world transforms the child algorithm sees
-};
-
-// Which child algorithm item k of pair p is, with its shapes and transforms.
-__device__ __forceinline__ void decodeCompoundItem(const NpArgs& a, const CompoundArgs& c, uint32_t p, uint32_t k, CompoundItem& it) {
-    it.pr = a.pairs[p];
-    const int b0 = it.pr.x - 1, b1 = it.pr.y - 1;
-    const int s0 = a.shape[b0], s1 = a.shape[b1];
-    const ShapeDev& S0 = a.shapes[s0];
-    const ShapeDev& S1 = a.shapes[s1];
-    const bool c0 = S0.type == SH_COMPOUND, c1 = S1.type == SH_COMPOUND;
-    const Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
-    auto childXf = [&](const ShapeDev& S, int i, const Xf& org, int& shapeOut) {
-        const CompoundChildDev& ch = c.children[S.pointOffset + i];
-        Xf l;
-        l.m[0][0] = ch.m[0]; l.m[0][1] = ch.m[1]; l.m[0][2] = ch.m[2];
-        l.m[1][0] = ch.m[3]; l.m[1][1] = ch.m[4]; l.m[1][2] = ch.m[5];
-        l.m[2][0] = ch.m[6]; l.m[2][1] = ch.m[7]; l.m[2][2] = ch.m[8];
-        l.o = mk3(ch.o[0], ch.o[1], ch.o[2]);
-        shapeOut = ch.shape;
-        return mulXf(org, l);  // newChildWorldTrans.mul(orgTrans, childTrans) (disp/CompoundCollisionAlgorithm.java:107)
-    };
-    if (c0 && c1) {
-        const int n1 = S1.numPoints;
-        const int i = (int)k / n1, j = (int)k % n1;
-        it.bodyA = b1; it.childA = j; it.tA = childXf(S1, j, t1, it.shapeA);
-        it.bodyB = b0; it.childB = i; it.tB = childXf(S0, i, t0, it.shapeB);
-    } else if (c0) {
-        it.bodyA = b0; it.childA = (int)k; it.tA = childXf(S0, (int)k, t0, it.shapeA);
-        it.bodyB = b1; it.childB = -1; it.tB = t1; it.shapeB = s1;
-    } else {
-        it.bodyA = b1; it.childA = (int)k; it.tA = childXf(S1, (int)k, t1, it.shapeA);
-        it.bodyB = b0; it.childB = -1; it.tB = t0; it.shapeB = s0;
-    }
-}
-
-__device__ __forceinline__ uint32_t compoundItemCount(const NpArgs& a, int2 pr) {
-    const ShapeDev& S0 = a.shapes[a.shape[pr.x - 1]];
-    const ShapeDev& S1 = a.shapes[a.shape[pr.y - 1]];
-    const uint32_t n0 = S0.type == SH_COMPOUND ? (uint32_t)S0.numPoints : 1u;
-    const uint32_t n1 = S1.type == SH_COMPOUND ? (uint32_t)S1.numPoints : 1u;
-    return n0 * n1;
-}
 
 __global__ void __launch_bounds__(128) k_compound_expand(NpArgs a, CompoundArgs c) {
     const uint32_t s = a.binStart[BIN_COMPOUND], mid = a.binStart[BIN_COMPOUND_KEEP], e = a.binStart[BIN_COMPOUND_KEEP + 1];
@@ -142,165 +68,124 @@ __global__ void __launch_bounds__(128) k_compound_expand(NpArgs a, CompoundArgs 
     if (counted) atomicAdd(&a.ctr->numManifolds, counted);
 }
 
-// np/GjkPairDetector.java:265-303: fold the penetration solver's answer into the detector result
-__device__ __forceinline__ void mergeEpaResult(const GjkResult& r, bool ok, f3 wA, f3 wB, bool& isValid, float& distance, f3& pointOnB,
-                                               f3& normalInB, int& method) {
-    isValid = r.isValid;
-    distance = r.distance;
-    pointOnB = r.pointOnB;
-    normalInB = r.normalInB;
-    method = r.lastUsedMethod;
-    if (ok) {
-        f3 nrm = sub3(wB, wA);
-        float lenSqr = len2_3(nrm);
-        if (lenSqr > (B2C_FLT_EPSILON * B2C_FLT_EPSILON)) {
-            nrm = scl3(nrm, 1.f / jsqrtf(lenSqr));
-            float distance2 = -len3(sub3(wA, wB));
-            if (!isValid || (distance2 < distance)) {
-                distance = distance2;
-                pointOnB = wB;
-                normalInB = nrm;
-                isValid = true;
-                method = 3;
-            }
-        } else {
-            method = 4;
-        }
-    } else {
-        method = 5;
-    }
-}
-
-__device__ __forceinline__ void writeCompoundGjkRaw(b2c_raw_contact* rw, int2 pr, int code, const GjkResult& r, bool isValid, float distance,
-                                                    f3 pointOnB, f3 normalInB, int method) {
-    const f3 pt = add3(pointOnB, r.positionOffset);
-    writeRaw(rw, pr, code, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0), isValid ? pt : mk3(0, 0, 0), isValid ? distance : 0.f,
-             method, r.curIter);
-}
-
-__global__ void __launch_bounds__(64) k_compound_detect(NpArgs a, CompoundArgs c) {
+// k_compound_gjk: the detector of every child algorithm.  Persistent warps as in k_gjk: a lane owns one item at a time and
+// refills from the work list as soon as its item ends (most (child, other) combinations are far apart and end in trip 2);
+// the closed-form child algorithms (sphere-sphere, convex-plane) are finished inside the refill.  Items whose detector asks
+// for the penetration solver join the pairs' penetration bin (EpaItem.meshItem = -2 - item) and are finished by k_epa.
+__global__ void __launch_bounds__(128, 4) k_compound_gjk(NpArgs a, GjkArgs g, uint32_t* cursor) {
+    const CompoundArgs& c = g.comp;
     const uint32_t total = c.cc->itemCount;
     const uint32_t n = (c.cc->overflow || total > c.maxItems) ? 0u : total;
     if (blockIdx.x == 0 && threadIdx.x == 0) c.cc->numItems = n;
-    uint32_t checks = 0, deep = 0, failed = 0;
-    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
-        const uint32_t code = c.itemCode[item];
-        if (code & CITEM_KEEP) continue;
-        CompoundItem it;
-        decodeCompoundItem(a, c, c.itemPair[item], code, it);
-        const ShapeDev& sa = a.shapes[it.shapeA];
-        const ShapeDev& sb = a.shapes[it.shapeB];
-        b2c_raw_contact* rw = c.raw + item;
-        const int tag = -2 - (int)code;  // raw-record key of a child algorithm: -2 - k
-        if (sa.type == SH_SPHERE && sb.type == SH_SPHERE) {
-            // disp/SphereSphereCollisionAlgorithm.java:73-134 on (child, other)
-            const float r0 = sa.dims[0], r1 = sb.dims[0];
-            f3 diff = sub3(it.tA.o, it.tB.o);
-            float len = len3(diff);
-            if (len > (r0 + r1)) {
-                writeRaw(rw, it.pr, tag, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, 10, 0);
+    uint32_t checks = 0, deep = 0;
+    GjkLane L;
+    LaneShape A, B;
+    Xf ta, tb;
+    uint32_t item = 0, p = 0;
+    int tag = 0;
+    int2 pr = make_int2(0, 0);
+    bool busy = false, more = true;
+    WarpQueue wq;
+    wq.init();
+    while (true) {
+        const bool want = !busy && more;
+        const uint32_t idx = wq.take(want, cursor, n);
+        if (want) {
+            if (idx == 0xffffffffu) {
+                more = false;
             } else {
-                float dist = len - (r0 + r1);
-                f3 nrm = mk3(1.f, 0.f, 0.f);
-                if (len > B2C_FLT_EPSILON) nrm = scl3(diff, 1.f / len);
-                f3 pos1 = add3(it.tB.o, scl3(nrm, r1));
-                writeRaw(rw, it.pr, tag, 1, nrm, pos1, dist, 10, 0);
-            }
-        } else if (sb.type == SH_PLANE) {
-            // disp/ConvexPlaneCollisionAlgorithm.java:75-136, convex = the child (convexPlaneCF, never swapped here)
-            const f3 planeNormal = mk3(sb.plane[0], sb.plane[1], sb.plane[2]);
-            const float planeConstant = sb.plane[3];
-            Xf planeInConvex = invMul(it.tA, it.tB);
-            Xf convexInPlane = invMul(it.tB, it.tA);
-            f3 dir = mulMV(planeInConvex.m, neg3(planeNormal));
-            AnyS shp = makeAnyS(sa, a.hullPts);
-            f3 vtx = shp.supportMargin(dir);
-            f3 vtxInPlane = xfPoint(convexInPlane, vtx);
-            float distance = dot3(planeNormal, vtxInPlane) - planeConstant;
-            f3 projected = sub3(vtxInPlane, scl3(planeNormal, distance));
-            f3 world = xfPoint(it.tB, projected);
-            bool has = distance < a.threshold;
-            f3 nW = mulMV(it.tB.m, planeNormal);
-            writeRaw(rw, it.pr, tag, has ? 1 : 0, nW, world, distance, 11, 0);
-        } else {
-            // disp/ConvexConvexAlgorithm.java:90-139: GjkPairDetector on (child, other), then the penetration solver
-            LaneShape A, B;
-            A.load(sa, a.hullPts);
-            B.load(sb, a.hullPts);
-            const float mA = sa.margin, mB = sb.margin;
-            const float maxd = mA + mB + a.threshold;
-            GjkLane L;
-            L.begin(it.tA, it.tB, mA, mB, maxd * maxd);
-            checks++;
-            for (;;) {
-                f3 pW = add3(mulMV(it.tA.m, A.support(L.dirA(it.tA))), L.laO);
-                f3 qW = add3(mulMV(it.tB.m, B.support(L.dirB(it.tB))), L.lbO);
-                if (L.iterate(pW, qW)) break;
-            }
-            GjkResult r;
-            L.finish(r);
-            if (!r.needEpa) {
-                writeCompoundGjkRaw(rw, it.pr, tag, r, r.isValid, r.distance, r.pointOnB, r.normalInB, r.lastUsedMethod);
-            } else {
-                deep++;
-                AnyS EA = makeAnyS(sa, a.hullPts), EB = makeAnyS(sb, a.hullPts);
-                Xf la = it.tA, lb = it.tB;
-                la.o = sub3(it.tA.o, r.positionOffset);
-                lb.o = sub3(it.tB.o, r.positionOffset);
-                f3 wA, wB;
-                bool epaFail = false, poolOverflow = false;
-                EpaScratchLocal sc;
-                bool ok = epaPenetration(EA, EB, la, lb, &sc, wA, wB, epaFail, poolOverflow);
-                if (poolOverflow) {
-                    const uint32_t slot = atomicAdd(&c.cc->retryCount, 1u);  // < maxItems: at most one entry per item
-                    c.retry[slot] = item;
-                    c.retryRes[slot] = r;
-                    rw->has_contact = -2;
-                    continue;
+                const uint32_t code = c.itemCode[idx];
+                if (!(code & CITEM_KEEP)) {
+                    item = idx;
+                    p = c.itemPair[idx];
+                    CompoundItem it;
+                    decodeCompoundItem(a, c, p, code, it);
+                    pr = it.pr;
+                    tag = -2 - (int)code;  // raw-record key of a child algorithm: -2 - k
+                    const ShapeDev& sa = a.shapes[it.shapeA];
+                    const ShapeDev& sb = a.shapes[it.shapeB];
+                    b2c_raw_contact* rw = c.raw + item;
+                    if (sa.type == SH_SPHERE && sb.type == SH_SPHERE) {
+                        // disp/SphereSphereCollisionAlgorithm.java:73-134 on (child, other)
+                        const float r0 = sa.dims[0], r1 = sb.dims[0];
+                        f3 diff = sub3(it.tA.o, it.tB.o);
+                        float len = len3(diff);
+                        if (len > (r0 + r1)) {
+                            writeRaw(rw, pr, tag, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, 10, 0);
+                        } else {
+                            float dist = len - (r0 + r1);
+                            f3 nrm = mk3(1.f, 0.f, 0.f);
+                            if (len > B2C_FLT_EPSILON) nrm = scl3(diff, 1.f / len);
+                            f3 pos1 = add3(it.tB.o, scl3(nrm, r1));
+                            writeRaw(rw, pr, tag, 1, nrm, pos1, dist, 10, 0);
+                        }
+                    } else if (sb.type == SH_PLANE) {
+                        // disp/ConvexPlaneCollisionAlgorithm.java:75-136, convex = the child (convexPlaneCF, never swapped here)
+                        const f3 planeNormal = mk3(sb.plane[0], sb.plane[1], sb.plane[2]);
+                        const float planeConstant = sb.plane[3];
+                        Xf planeInConvex = invMul(it.tA, it.tB);
+                        Xf convexInPlane = invMul(it.tB, it.tA);
+                        f3 dir = mulMV(planeInConvex.m, neg3(planeNormal));
+                        AnyS shp = makeAnyS(sa, a.hullPts);
+                        f3 vtx = shp.supportMargin(dir);
+                        f3 vtxInPlane = xfPoint(convexInPlane, vtx);
+                        float distance = dot3(planeNormal, vtxInPlane) - planeConstant;
+                        f3 projected = sub3(vtxInPlane, scl3(planeNormal, distance));
+                        f3 world = xfPoint(it.tB, projected);
+                        bool has = distance < a.threshold;
+                        f3 nW = mulMV(it.tB.m, planeNormal);
+                        writeRaw(rw, pr, tag, has ? 1 : 0, nW, world, distance, 11, 0);
+                    } else {
+                        // disp/ConvexConvexAlgorithm.java:90-139: GjkPairDetector on (child, other)
+                        A.load(sa, a.hullPts);
+                        B.load(sb, a.hullPts);
+                        ta = it.tA;
+                        tb = it.tB;
+                        const float mA = sa.margin, mB = sb.margin;
+                        const float maxd = mA + mB + a.threshold;
+                        L.begin(ta, tb, mA, mB, maxd * maxd);
+                        busy = true;
+                        checks++;
+                    }
                 }
-                if (epaFail) failed++;
-                bool isValid; float distance; f3 pointOnB, normalInB; int method;
-                mergeEpaResult(r, ok, wA, wB, isValid, distance, pointOnB, normalInB, method);
-                writeCompoundGjkRaw(rw, it.pr, tag, r, isValid, distance, pointOnB, normalInB, method);
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy)) {
+            if (!__any_sync(0xffffffffu, more)) break;
+            continue;
+        }
+        if (busy) {
+            f3 pW = add3(mulMV(ta.m, A.support(L.dirA(ta))), L.laO);
+            f3 qW = add3(mulMV(tb.m, B.support(L.dirB(tb))), L.lbO);
+            if (L.iterate(pW, qW)) {
+                GjkResult r;
+                L.finish(r);
+                busy = false;
+                b2c_raw_contact* rw = c.raw + item;
+                bool queued = false;
+                if (r.needEpa) {
+                    deep++;
+                    uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
+                    if (slot < g.maxEpa) {
+                        g.epaItems[slot].pair = p;
+                        g.epaItems[slot].meshItem = -2 - (int)item;
+                        g.epaItems[slot].g = r;
+                        rw->has_contact = -2;  // pending in the penetration bin
+                        queued = true;
+                    } else {
+                        a.ctr->epaFailed = 0x7fffffffu;  // capacity: reported by the host as B2C_ERR_CAPACITY
+                    }
+                }
+                if (!queued) {
+                    f3 pt = add3(r.pointOnB, r.positionOffset);
+                    writeRaw(rw, pr, tag, r.isValid ? 1 : 0, r.isValid ? r.normalInB : mk3(0, 0, 0), r.isValid ? pt : mk3(0, 0, 0),
+                             r.isValid ? r.distance : 0.f, r.lastUsedMethod, r.curIter);
+                }
             }
         }
     }
     if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
     if (deep) atomicAdd(&a.ctr->deepChecks, deep);
-    if (failed) atomicAdd(&a.ctr->epaFailed, failed);
-}
-
-// Items whose polytope outgrew the medium pool: one item per warp (lane 0), the full-size pool in this warp's slice of
-// shared memory — the same arrangement as the retry tier of k_epa.
-__global__ void __launch_bounds__(64) k_compound_retry(NpArgs a, CompoundArgs c) {
-    extern __shared__ __align__(16) unsigned char compoundSmem[];
-    const uint32_t n = c.cc->retryCount < c.maxItems ? c.cc->retryCount : c.maxItems;
-    const uint32_t warpsPerBlock = blockDim.x >> 5;
-    if ((threadIdx.x & 31) != 0) return;
-    uint32_t failed = 0;
-    for (uint32_t q = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); q < n; q += gridDim.x * warpsPerBlock) {
-        const uint32_t item = c.retry[q];
-        const GjkResult r = c.retryRes[q];
-        const uint32_t code = c.itemCode[item];
-        CompoundItem it;
-        decodeCompoundItem(a, c, c.itemPair[item], code, it);
-        const ShapeDev& sa = a.shapes[it.shapeA];
-        const ShapeDev& sb = a.shapes[it.shapeB];
-        AnyS EA = makeAnyS(sa, a.hullPts), EB = makeAnyS(sb, a.hullPts);
-        Xf la = it.tA, lb = it.tB;
-        la.o = sub3(it.tA.o, r.positionOffset);
-        lb.o = sub3(it.tB.o, r.positionOffset);
-        f3 wA, wB;
-        bool epaFail = false, poolOverflow = false;
-        EpaScratch* sc = reinterpret_cast<EpaScratch*>(compoundSmem + (size_t)(threadIdx.x >> 5) * sizeof(EpaScratch));
-        bool ok = epaPenetration(EA, EB, la, lb, sc, wA, wB, epaFail, poolOverflow);
-        if (poolOverflow) epaFail = true;
-        if (epaFail) failed++;
-        bool isValid; float distance; f3 pointOnB, normalInB; int method;
-        mergeEpaResult(r, ok, wA, wB, isValid, distance, pointOnB, normalInB, method);
-        writeCompoundGjkRaw(c.raw + item, it.pr, -2 - (int)code, r, isValid, distance, pointOnB, normalInB, method);
-    }
-    if (failed) atomicAdd(&a.ctr->epaFailed, failed);
 }
 
 __global__ void __launch_bounds__(128) k_compound_manifold(NpArgs a, CompoundArgs c) {

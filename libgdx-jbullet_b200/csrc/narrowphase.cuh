@@ -751,10 +751,83 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
 }
 
+// ---- CompoundShape work items (the kernels are in compound.cuh; the penetration bin below also serves them) ----------
+struct CompoundCounters {
+    uint32_t itemCount;   // items reserved by k_compound_expand (may exceed the capacity -> overflow)
+    uint32_t overflow;
+    uint32_t numItems;    // items the later kernels and the result calls may touch (0 after an overflow)
+    uint32_t pad;
+};
+
+constexpr uint32_t CITEM_KEEP = 0x80000000u;  // itemCode flag: copy the manifold forward, do nothing else
+
+struct CompoundArgs {
+    const CompoundChildDev* children;
+    CompoundCounters* cc;          // cleared per dispatch
+    uint32_t* itemPair;            // [maxItems] pair index
+    uint32_t* itemCode;            // [maxItems] k = i * n1 + j (index of the item inside its pair) | CITEM_KEEP
+    int* itemPrev;                 // [maxItems] the same item in the previous dispatch's arrays, or -1
+    b2c_raw_contact* raw;          // [maxItems] detector output
+    ManifoldHdr* H;                // [maxItems] child manifolds of this dispatch (header word pad0 / pad1 = child index in
+    b2c_manifold_point* P;         //            body0's / body1's compound shape, -1 = that object is not a compound)
+    const ManifoldHdr* prevH;      // the previous dispatch's
+    const b2c_manifold_point* prevP;
+    uint32_t maxItems;
+};
+
+struct CompoundItem {
+    int2 pr;            // the broadphase pair (uid0 < uid1)
+    int bodyA, bodyB;   // 0-based body indices of the child algorithm's body0 / body1
+    int shapeA, shapeB; // shape table indices (A: a compound's child; B: the other object's shape or its child)
+    int childA, childB; // child index inside its compound, -1 = not a compound
+    Xf tA, tB;          // world transforms the child algorithm sees
+};
+
+// Which child algorithm item k of pair p is, with its shapes and transforms.
+__device__ __forceinline__ void decodeCompoundItem(const NpArgs& a, const CompoundArgs& c, uint32_t p, uint32_t k, CompoundItem& it) {
+    it.pr = a.pairs[p];
+    const int b0 = it.pr.x - 1, b1 = it.pr.y - 1;
+    const int s0 = a.shape[b0], s1 = a.shape[b1];
+    const ShapeDev& S0 = a.shapes[s0];
+    const ShapeDev& S1 = a.shapes[s1];
+    const bool c0 = S0.type == SH_COMPOUND, c1 = S1.type == SH_COMPOUND;
+    const Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+    auto childXf = [&](const ShapeDev& S, int i, const Xf& org, int& shapeOut) {
+        const CompoundChildDev& ch = c.children[S.pointOffset + i];
+        Xf l;
+        l.m[0][0] = ch.m[0]; l.m[0][1] = ch.m[1]; l.m[0][2] = ch.m[2];
+        l.m[1][0] = ch.m[3]; l.m[1][1] = ch.m[4]; l.m[1][2] = ch.m[5];
+        l.m[2][0] = ch.m[6]; l.m[2][1] = ch.m[7]; l.m[2][2] = ch.m[8];
+        l.o = mk3(ch.o[0], ch.o[1], ch.o[2]);
+        shapeOut = ch.shape;
+        return mulXf(org, l);  // newChildWorldTrans.mul(orgTrans, childTrans) (disp/CompoundCollisionAlgorithm.java:107)
+    };
+    if (c0 && c1) {
+        const int n1 = S1.numPoints;
+        const int i = (int)k / n1, j = (int)k % n1;
+        it.bodyA = b1; it.childA = j; it.tA = childXf(S1, j, t1, it.shapeA);
+        it.bodyB = b0; it.childB = i; it.tB = childXf(S0, i, t0, it.shapeB);
+    } else if (c0) {
+        it.bodyA = b0; it.childA = (int)k; it.tA = childXf(S0, (int)k, t0, it.shapeA);
+        it.bodyB = b1; it.childB = -1; it.tB = t1; it.shapeB = s1;
+    } else {
+        it.bodyA = b1; it.childA = (int)k; it.tA = childXf(S1, (int)k, t1, it.shapeA);
+        it.bodyB = b0; it.childB = -1; it.tB = t0; it.shapeB = s0;
+    }
+}
+
+__device__ __forceinline__ uint32_t compoundItemCount(const NpArgs& a, int2 pr) {
+    const ShapeDev& S0 = a.shapes[a.shape[pr.x - 1]];
+    const ShapeDev& S1 = a.shapes[a.shape[pr.y - 1]];
+    const uint32_t n0 = S0.type == SH_COMPOUND ? (uint32_t)S0.numPoints : 1u;
+    const uint32_t n1 = S1.type == SH_COMPOUND ? (uint32_t)S1.numPoints : 1u;
+    return n0 * n1;
+}
+
 // ---- GJK bins + EPA --------------------------------------------------------------------------------
 struct EpaItem {        // a pair (or pair/triangle) whose detector asked for the penetration solver
     uint32_t pair;      // pair index
-    int meshItem;       // index into the mesh item arrays, or -1
+    int meshItem;       // index into the mesh item arrays, or -1; <= -2: compound child work item -2 - meshItem
     GjkResult g;
 };
 
@@ -770,6 +843,7 @@ struct GjkArgs {
     uint32_t* meshStart;     // [maxPairs] first item of a mesh pair (indexed by pair)
     uint32_t* meshCount;     // [maxPairs]
     uint32_t maxMeshItems;
+    CompoundArgs comp;       // compound child work items (EpaItem.meshItem <= -2 names item -2 - meshItem)
 };
 
 // A lane's convex shape, chosen at run time inside ONE code path (the whole bin shares the loop body; only
@@ -1313,6 +1387,15 @@ __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs 
             TriS T = loadTri(a.meshes[ms.mesh], tri, ms.margin);
             A = makeAnyS(cs, a.hullPts);
             B.type = SH_TRIANGLE; B.h = mk3(0, 0, 0); B.ta = T.a; B.tb = T.b; B.tc = T.c; B.pts = nullptr; B.n = 0; B.margin = ms.margin;
+        } else if (item.meshItem <= -2) {  // a child algorithm of a compound pair (compound.cuh)
+            const uint32_t ci = (uint32_t)(-2 - item.meshItem);
+            const uint32_t code = g.comp.itemCode[ci];
+            CompoundItem cit;
+            decodeCompoundItem(a, g.comp, p, code, cit);
+            A = makeAnyS(a.shapes[cit.shapeA], a.hullPts);
+            B = makeAnyS(a.shapes[cit.shapeB], a.hullPts);
+            ta = cit.tA; tb = cit.tB;
+            tri = -2 - (int)code;
         } else {
             A = makeAnyS(s0, a.hullPts);
             B = makeAnyS(s1, a.hullPts);
@@ -1368,10 +1451,10 @@ __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs 
             method = 5;
         }
         f3 pt = add3(pointOnB, r.positionOffset);
-        b2c_raw_contact* rw = item.meshItem >= 0 ? g.rawMesh + item.meshItem : a.raw + p;
+        b2c_raw_contact* rw = item.meshItem >= 0 ? g.rawMesh + item.meshItem : (item.meshItem <= -2 ? g.comp.raw + (-2 - item.meshItem) : a.raw + p);
         writeRaw(rw, pr, tri, isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0), isValid ? pt : mk3(0, 0, 0),
                  isValid ? distance : 0.f, method, r.curIter);
-        if (TIER == 1 && item.meshItem < 0) {  // the retried pair's manifold, by the thread that finished its detector
+        if (TIER == 1 && item.meshItem == -1) {  // the retried pair's manifold, by the thread that finished its detector
             uint32_t added = 0, created = 0;
             manifoldCcOne(a, p, isValid, added, created);
             if (created) atomicAdd(&a.ctr->numManifolds, created);
@@ -1387,7 +1470,7 @@ __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs 
         uint32_t added = 0, created = 0;
         for (uint32_t it = first; it < nAll; it += step) {
             const uint32_t pp = g.epaItems[it].pair;
-            if ((pp & EPA_RETRY_BIT) || g.epaItems[it].meshItem >= 0) continue;
+            if ((pp & EPA_RETRY_BIT) || g.epaItems[it].meshItem != -1) continue;
             manifoldCcOne(a, pp, a.raw[pp].has_contact == 1, added, created);
         }
         if (created) atomicAdd(&a.ctr->numManifolds, created);

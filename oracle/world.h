@@ -366,27 +366,13 @@ struct World {
         return (int)pairs.size();
     }
 
-    // disp/CollisionWorld.java:553-590 rayTest with a ClosestRayResultCallback(group, mask); convex shapes only
-    RayHit rayTestClosest(const V3& from, const V3& to, int group, int mask) const {
-        RayHit hit;
-        float closest = 1.f;  // RayResultCallback.closestHitFraction
-        for (const Body& b : bodies) {
-            if (!b.alive) continue;
-            if (closest == 0.f) break;
-            // RayResultCallback.needsCollision (disp/CollisionWorld.java:664-670)
-            bool collides = ((int)b.group & mask) != 0;
-            collides = collides && (group & (int)b.mask) != 0;
-            if (!collides) continue;
-            const Shape& s = shapes[b.shape];
-            if (s.type != SH_BOX && s.type != SH_SPHERE && s.type != SH_HULL) continue;  // concave: not cast here
-            V3 mn, mx;
-            shapeGetAabb(s, b.xf, mn, mx);
-            float hitLambda = closest;
-            V3 hitNormal;
-            if (!rayAabb(from, to, mn, mx, hitLambda, hitNormal)) continue;
+    // disp/CollisionWorld.java:260-356 rayTestSingle for one (object, shape, transform) against the running callback state
+    void rayTestSingle(const V3& from, const V3& to, const Body& b, int shapeIndex, const Xf& xf, float& closest, RayHit& hit) const {
+        const Shape& s = shapes[shapeIndex];
+        if (s.isConvex()) {
             CastResult cr;
             cr.fraction = closest;
-            if (rayConvexCast(from, to, s, b.xf, cr)) {
+            if (rayConvexCast(from, to, s, xf, cr)) {
                 if (cr.normal.len2() > 0.0001f) {
                     if (cr.fraction < closest) {
                         // castResult.normal.mul(rayFromTrans.basis) with the identity basis, then nor()
@@ -402,6 +388,61 @@ struct World {
                     }
                 }
             }
+        } else if (s.isConcave()) {
+            Xf worldToObj; worldToObj.set(xf);
+            worldToObj.inverse();
+            TriangleRaycast rcb;
+            rcb.from = from; worldToObj.transform(rcb.from);
+            rcb.to = to; worldToObj.transform(rcb.to);
+            rcb.hitFraction = closest;
+            if (s.type == SH_MESH) {
+                const MeshShapeData* md = meshes[shapeIndex].get();
+                bvhReportRayOverlappingNodex(md->bvh, rcb.from, rcb.to, [&](int part, int tri) {
+                    V3 t[3];
+                    md->mesh.getTriangle(tri, t);
+                    rcb.processTriangle(t, part, tri);
+                });
+            } else {
+                V3 mn(jminf(rcb.from.x, rcb.to.x), jminf(rcb.from.y, rcb.to.y), jminf(rcb.from.z, rcb.to.z));
+                V3 mx(jmaxf(rcb.from.x, rcb.to.x), jmaxf(rcb.from.y, rcb.to.y), jmaxf(rcb.from.z, rcb.to.z));
+                planeProcessAllTriangles(s.planeNormal, s.planeConstant, mn, mx, [&](const V3* t, int part, int tri) { rcb.processTriangle(t, part, tri); });
+            }
+            if (rcb.hit) {  // ClosestRayResultCallback.addSingleResult of the last reported triangle (:708-729)
+                closest = rcb.hitFraction;
+                hit.uid = b.uid;
+                hit.fraction = rcb.hitFraction;
+                hit.normal.set(rcb.hitNormalLocal);
+                v3mul(hit.normal, b.xf.basis);  // collisionObject.getWorldTransform().basis (the OBJECT's, also for compound children)
+                float sgl = 1.f - rcb.hitFraction;
+                hit.point.set(sgl * from.x + rcb.hitFraction * to.x, sgl * from.y + rcb.hitFraction * to.y, sgl * from.z + rcb.hitFraction * to.z);
+            }
+        } else if (s.isCompound()) {
+            for (size_t i = 0; i < s.children.size(); i++) {
+                Xf childWorld; childWorld.set(xf);
+                childWorld.mul(s.children[i].transform);
+                rayTestSingle(from, to, b, s.children[i].shape, childWorld, closest, hit);
+            }
+        }
+    }
+
+    // disp/CollisionWorld.java:553-590 rayTest with a ClosestRayResultCallback(group, mask)
+    RayHit rayTestClosest(const V3& from, const V3& to, int group, int mask) const {
+        RayHit hit;
+        float closest = 1.f;  // RayResultCallback.closestHitFraction
+        for (const Body& b : bodies) {
+            if (!b.alive) continue;
+            if (closest == 0.f) break;
+            // RayResultCallback.needsCollision (disp/CollisionWorld.java:664-670)
+            bool collides = ((int)b.group & mask) != 0;
+            collides = collides && (group & (int)b.mask) != 0;
+            if (!collides) continue;
+            const Shape& s = shapes[b.shape];
+            V3 mn, mx;
+            shapeGetAabb(s, b.xf, mn, mx);
+            float hitLambda = closest;
+            V3 hitNormal;
+            if (!rayAabb(from, to, mn, mx, hitLambda, hitNormal)) continue;
+            rayTestSingle(from, to, b, b.shape, b.xf, closest, hit);
         }
         return hit;
     }
