@@ -98,7 +98,7 @@ int32_t b2c_shape_register_mesh(b2c_ctx*, const void* vertex_base, int32_t num_v
  * Pairs with a compound on either side run disp/CompoundCollisionAlgorithm.java:83-129: one child algorithm and one
  * PersistentManifold per child (per child x child for two compounds), reported by b2c_get_manifolds / b2c_get_contacts with
  * the child indices.  Not built: compound children that are themselves compounds or concave, compound x triangle mesh (the
- * pair stays in the pair list but generates no contacts), rays against compounds, compounds in a partitioned world. */
+ * pair stays in the pair list but generates no contacts), compounds in a partitioned world. */
 int32_t b2c_shape_register_compound(b2c_ctx*, int32_t num_children, const int32_t* child_shapes, const float* child_transforms12,
                                     int32_t* shape_out);
 /* Debug/inspection: copy the quantized BVH (16-byte nodes, sh/QuantizedBvhNodes.java:34-48) */
@@ -270,8 +270,11 @@ int32_t b2c_compute_islands(b2c_ctx*, int32_t* tags_out, int32_t n, int32_t* num
  * from_xyz / to_xyz = 3 floats per ray (host); group / mask = the callback's collisionFilterGroup / collisionFilterMask
  * (disp/CollisionWorld.java:655-670, defaults DEFAULT_FILTER = 1 and ALL_FILTER = -1).  Outputs per ray: uid of the closest
  * body hit (0 = none), closestHitFraction (1 = none), hitNormalWorld, hitPointWorld.  Uses the transforms currently
- * resident.  Convex bodies (box, sphere, hull) are cast with the reference's SubsimplexConvexCast; static planes and
- * triangle meshes are not cast yet (the ray passes through them). */
+ * resident.  Every branch of rayTestSingle (disp/CollisionWorld.java:260-356) is covered: convex bodies (box, sphere, hull)
+ * are cast with the reference's SubsimplexConvexCast, triangle meshes with the quantised-BVH ray walk
+ * (sh/OptimizedBvh.java:817-931) + np/TriangleRaycastCallback.java:46-117, static planes with the two triangles
+ * sh/StaticPlaneShape.java:60-122 generates, compounds child by child.  For meshes and planes the normal is the reference's
+ * unnormalised triangle normal rotated into world space. */
 int32_t b2c_ray_test_closest(b2c_ctx*, int32_t n, const float* from_xyz, const float* to_xyz, int16_t group, int16_t mask,
                              int32_t* uid_out, float* fraction_out, float* normal_out, float* point_out);
 

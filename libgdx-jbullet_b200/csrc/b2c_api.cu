@@ -1817,7 +1817,7 @@ int32_t b2c_ray_test_closest(b2c_ctx* ctx, int32_t n, const float* from, const f
     if (nb > 0) k_ray_aabbs<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, nb, ctx->dRayMin, ctx->dRayMax);
     const uint32_t cbFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
     const unsigned grid = (unsigned)(n < 148 * 16 ? n : 148 * 16);
-    k_ray_test<<<grid, RAY_THREADS, 0, s>>>(ctx->B, ctx->dShapes, ctx->dHullPts, nb, ctx->dRayMin, ctx->dRayMax, ctx->dRayIn,
+    k_ray_test<<<grid, RAY_THREADS, 0, s>>>(ctx->B, ctx->dShapes, ctx->dHullPts, ctx->dMeshes, ctx->dChildren, nb, ctx->dRayMin, ctx->dRayMax, ctx->dRayIn,
                                             ctx->dRayIn + 3 * (size_t)n, n, cbFilter, ctx->dRayOut, ctx->dRayOverflow);
     std::vector<RayOut> host((size_t)n);
     uint32_t ov = 0;

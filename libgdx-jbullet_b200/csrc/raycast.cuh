@@ -1,4 +1,4 @@
-// raycast.cuh — batched closest-hit ray tests against the convex bodies of the world.
+// raycast.cuh — batched closest-hit ray tests against the bodies of the world.
 //
 // Replaces, per ray: CollisionWorld.rayTest with a ClosestRayResultCallback (disp/CollisionWorld.java:553-590, 697-729):
 //   objects in world order, needsCollision filter (:664-670), AabbUtil2.rayAabb (lm/AabbUtil2.java:40-108) with the running
@@ -8,15 +8,25 @@
 // an object's cast result does not depend on that bound, so: (1) all threads test the ray against every body's AABB with
 // the widest bound and collect the candidates, (2) the candidates are cast in parallel, (3) one thread replays the
 // reference's loop over the candidates in body order with the stored cast results — the same accept/reject decisions, in
-// the same order.  Concave shapes (planes, meshes) are not cast (the ray passes through them); that path is next.
+// the same order.
+// rayTestSingle's other branches (disp/CollisionWorld.java:301-356) follow the same scheme, because what an object reports
+// under the widest bound decides what it reports under any bound b: a triangle mesh / static plane ends on the FIRST
+// triangle (in traversal order) that attains its smallest hit distance m (np/TriangleRaycastCallback.java:46-117 accepts
+// only distance < hitFraction, and the BVH ray walk, sh/OptimizedBvh.java:817-931, never looks at the bound), a compound on
+// the first child attaining its smallest cast fraction (:333-352) — and under bound b it reports exactly that if m < b and
+// nothing otherwise.  So step (2) stores one (valid, fraction, world normal) per candidate whatever its shape type.
 #pragma once
 #include "broadphase.cuh"
 #include "epa.cuh"
 #include "gjk.cuh"
+#include "narrowphase.cuh"
 
 namespace b2c {
 
-constexpr int RAY_THREADS = 128;
+#ifndef B2C_RAY_THREADS
+#define B2C_RAY_THREADS 128
+#endif
+constexpr int RAY_THREADS = B2C_RAY_THREADS;
 constexpr int RAY_MAX_CAND = 1024;
 
 __device__ __forceinline__ int rayOutcode(f3 p, f3 h) {  // lm/AabbUtil2.java:40-43
@@ -104,6 +114,115 @@ __device__ __forceinline__ bool rayConvexCast(f3 rayFrom, f3 rayTo, const AnyS& 
     return true;
 }
 
+// np/TriangleRaycastCallback.java:46-117 processTriangle with BridgeTriangleRaycastCallback.reportHit ->
+// ClosestRayResultCallback.addSingleResult folded in: hitFraction / normal of the last reported triangle
+struct TriRay {
+    f3 from, to;        // in the concave object's local space
+    float hitFraction;
+    bool hit;
+    f3 normalLocal;     // not normalised, as in the reference
+    __device__ __forceinline__ void processTriangle(f3 vert0, f3 vert1, f3 vert2) {
+        const f3 v10 = sub3(vert1, vert0), v20 = sub3(vert2, vert0);
+        const f3 triangleNormal = crs3(v10, v20);
+        const float dist = dot3(vert0, triangleNormal);
+        float dist_a = dot3(triangleNormal, from);
+        dist_a -= dist;
+        float dist_b = dot3(triangleNormal, to);
+        dist_b -= dist;
+        if (dist_a * dist_b >= 0.f) return;  // same sign
+        const float proj_length = dist_a - dist_b;
+        const float distance = dist_a / proj_length;
+        if (distance < hitFraction) {
+            float edge_tolerance = len2_3(triangleNormal);
+            edge_tolerance *= -0.0001f;
+            const float s = 1.f - distance;  // lm/VectorUtil.java:137-141 setInterpolate3
+            const f3 point = mk3(s * from.x + distance * to.x, s * from.y + distance * to.y, s * from.z + distance * to.z);
+            const f3 v0p = sub3(vert0, point), v1p = sub3(vert1, point);
+            const f3 cp0 = crs3(v0p, v1p);
+            if (dot3(cp0, triangleNormal) >= edge_tolerance) {
+                const f3 v2p = sub3(vert2, point);
+                const f3 cp1 = crs3(v1p, v2p);
+                if (dot3(cp1, triangleNormal) >= edge_tolerance) {
+                    const f3 cp2 = crs3(v2p, v0p);
+                    if (dot3(cp2, triangleNormal) >= edge_tolerance) {
+                        hit = true;
+                        normalLocal = dist_a > 0.f ? triangleNormal : neg3(triangleNormal);
+                        hitFraction = distance;
+                    }
+                }
+            }
+        }
+    }
+};
+
+// sh/BvhTriangleMeshShape.java:135-142 performRaycast -> sh/OptimizedBvh.java:817-931 walkStacklessQuantizedTreeAgainstRay
+// with zero box-cast extents: quantised box prune, then rayAabb (exit bound 1) on the unquantised node box
+__device__ __forceinline__ void rayMeshWalk(const MeshDev& md, TriRay& tr) {
+    f3 rmin = mk3(jminf(tr.from.x, tr.to.x), jminf(tr.from.y, tr.to.y), jminf(tr.from.z, tr.to.z));
+    f3 rmax = mk3(jmaxf(tr.from.x, tr.to.x), jmaxf(tr.from.y, tr.to.y), jmaxf(tr.from.z, tr.to.z));
+    const f3 zero = mk3(0.f, 0.f, 0.f);
+    rmin = add3(rmin, zero);
+    rmax = add3(rmax, zero);
+    uint32_t qmin[3], qmax[3];
+    quantizeClamp(md, rmin, qmin);
+    quantizeClamp(md, rmax, qmax);
+    int cur = 0;
+    const int end = md.numNodes;
+    while (cur < end) {
+        const int4 nd = __ldg(md.nodes + cur);
+        const uint32_t nminx = (uint32_t)nd.x & 0xFFFFu, nminy = ((uint32_t)nd.x >> 16) & 0xFFFFu, nminz = (uint32_t)nd.y & 0xFFFFu;
+        const uint32_t nmaxx = ((uint32_t)nd.y >> 16) & 0xFFFFu, nmaxy = (uint32_t)nd.z & 0xFFFFu, nmaxz = ((uint32_t)nd.z >> 16) & 0xFFFFu;
+        const bool boxBox = !(qmin[0] > nmaxx || qmax[0] < nminx) && !(qmin[2] > nmaxz || qmax[2] < nminz) &&
+                            !(qmin[1] > nmaxy || qmax[1] < nminy);
+        const bool leaf = nd.w >= 0;
+        bool rayBox = false;
+        if (boxBox) {  // unQuantize (:1058-1068) + the zero extents
+            f3 b0 = add3(mk3(__uint2float_rn(nminx) / md.quant[0], __uint2float_rn(nminy) / md.quant[1], __uint2float_rn(nminz) / md.quant[2]),
+                         mk3(md.qmin[0], md.qmin[1], md.qmin[2]));
+            f3 b1 = add3(mk3(__uint2float_rn(nmaxx) / md.quant[0], __uint2float_rn(nmaxy) / md.quant[1], __uint2float_rn(nmaxz) / md.quant[2]),
+                         mk3(md.qmin[0], md.qmin[1], md.qmin[2]));
+            b0 = add3(b0, zero);
+            b1 = add3(b1, zero);
+            rayBox = rayAabb(tr.from, tr.to, b0, b1, 1.f);
+        }
+        if (leaf && rayBox) {
+            const TriS t = loadTri(md, nd.w & 0x1FFFFF, 0.f);
+            tr.processTriangle(t.a, t.b, t.c);
+        }
+        if (rayBox || leaf) cur++;
+        else cur += -nd.w;
+    }
+}
+
+// sh/StaticPlaneShape.java:60-122 processAllTriangles over the ray's local AABB (including the `set(aabbMax).set(aabbMin)`
+// half-extent line, :67) with lm/TransformUtil.java:45-61 planeSpace1
+__device__ __forceinline__ void rayPlaneTriangles(f3 planeNormal, float planeConstant, TriRay& tr) {
+    const f3 aabbMin = mk3(jminf(tr.from.x, tr.to.x), jminf(tr.from.y, tr.to.y), jminf(tr.from.z, tr.to.z));
+    const f3 aabbMax = mk3(jmaxf(tr.from.x, tr.to.x), jmaxf(tr.from.y, tr.to.y), jmaxf(tr.from.z, tr.to.z));
+    const f3 halfExtents = scl3(aabbMin, 0.5f);  // (sic)
+    const float radius = len3(halfExtents);
+    const f3 center = scl3(add3(aabbMax, aabbMin), 0.5f);
+    f3 t0, t1;
+    const f3 n = planeNormal;
+    if (fabsf(n.z) > 0.7071067811865475244008443621048490f) {
+        const float a = n.y * n.y + n.z * n.z;
+        const float k = 1.f / jsqrtf(a);
+        t0 = mk3(0.f, -n.z * k, n.y * k);
+        t1 = mk3(a * k, -n.x * t0.z, n.x * t0.y);
+    } else {
+        const float a = n.x * n.x + n.y * n.y;
+        const float k = 1.f / jsqrtf(a);
+        t0 = mk3(-n.y * k, n.x * k, 0.f);
+        t1 = mk3(-n.z * t0.y, n.z * t0.x, a * k);
+    }
+    const f3 projectedCenter = sub3(center, scl3(planeNormal, dot3(planeNormal, center) - planeConstant));
+    const f3 tmp1 = scl3(t0, radius), tmp2 = scl3(t1, radius);
+    const f3 both = mk3(projectedCenter.x + tmp1.x + tmp2.x, projectedCenter.y + tmp1.y + tmp2.y, projectedCenter.z + tmp1.z + tmp2.z);
+    const f3 diff = sub3(tmp1, tmp2);
+    tr.processTriangle(both, add3(projectedCenter, diff), sub3(projectedCenter, diff));
+    tr.processTriangle(sub3(projectedCenter, diff), sub3(projectedCenter, add3(tmp1, tmp2)), both);
+}
+
 // tight shape AABBs (shape.getAabb(worldTransform), no contact threshold) of the bodies a ray can hit; others get an empty box
 __global__ void __launch_bounds__(256)
 k_ray_aabbs(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, float4* __restrict__ rmin, float4* __restrict__ rmax) {
@@ -113,7 +232,7 @@ k_ray_aabbs(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, float4* __
     const uint8_t fl = B.flags[i];
     if (fl & BF_ALIVE) {
         const ShapeDev s = shapes[B.shape[i]];
-        if (s.type == SH_BOX || s.type == SH_SPHERE || s.type == SH_HULL) {
+        {
             Xf t = loadXf(B.xf4, i);
             f3 a, b;
             shapeAabb(s, t, a, b);
@@ -133,7 +252,8 @@ struct RayOut {
 };
 
 __global__ void __launch_bounds__(RAY_THREADS)
-k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __restrict__ hullPts, int n,
+k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __restrict__ hullPts, const MeshDev* __restrict__ meshes,
+           const CompoundChildDev* __restrict__ children, int n,
            const float4* __restrict__ rmin, const float4* __restrict__ rmax, const float* __restrict__ rayFrom,
            const float* __restrict__ rayTo, int numRays, uint32_t cbFilter /* group | mask << 16 */, RayOut* __restrict__ out,
            uint32_t* __restrict__ overflow) {
@@ -169,18 +289,61 @@ k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __re
         for (uint32_t k = threadIdx.x; k < cnt; k += RAY_THREADS) {
             const int i = (int)sCand[k];
             const ShapeDev s = shapes[B.shape[i]];
-            AnyS shp;
-            shp.type = s.type;
-            shp.h = mk3(s.dims[0], s.dims[1], s.dims[2]);
-            shp.ta = shp.tb = shp.tc = mk3(0.f, 0.f, 0.f);
-            shp.pts = hullPts + s.pointOffset;
-            shp.n = s.numPoints;
-            shp.margin = s.margin;
             const Xf t = loadXf(B.xf4, i);
             float fr = 1.f;
             f3 nn = mk3(0.f, 0.f, 0.f);
-            const bool hit = rayConvexCast(from, to, shp, t, fr, nn);
-            sValid[k] = (hit && len2_3(nn) > 0.0001f) ? 1 : 0;
+            bool valid = false;
+            auto castConvex = [&](const ShapeDev& cs, const Xf& cx, float bound) {
+                AnyS shp;
+                shp.type = cs.type;
+                shp.h = mk3(cs.dims[0], cs.dims[1], cs.dims[2]);
+                shp.ta = shp.tb = shp.tc = mk3(0.f, 0.f, 0.f);
+                shp.pts = hullPts + cs.pointOffset;
+                shp.n = cs.numPoints;
+                shp.margin = cs.margin;
+                float f = 1.f;
+                f3 c = mk3(0.f, 0.f, 0.f);
+                const bool hit = rayConvexCast(from, to, shp, cx, f, c);
+                if (hit && len2_3(c) > 0.0001f && f < bound) {
+                    // castResult.normal.mul(rayFromTrans.basis) with the identity basis, then nor()
+                    nn = nor3(mk3(c.x * 1.f + c.y * 0.f + c.z * 0.f, c.x * 0.f + c.y * 1.f + c.z * 0.f, c.x * 0.f + c.y * 0.f + c.z * 1.f));
+                    fr = f;
+                    valid = true;
+                }
+            };
+            if (s.type == SH_BOX || s.type == SH_SPHERE || s.type == SH_HULL) {
+                castConvex(s, t, 1.f);
+                if (!valid) fr = 1.f;
+            } else if (s.type == SH_COMPOUND) {  // :333-352: the children in order, each against the bound its predecessors left
+                for (int ch = 0; ch < s.numPoints; ch++) {
+                    const CompoundChildDev& cd = children[s.pointOffset + ch];
+                    Xf l;
+                    l.m[0][0] = cd.m[0]; l.m[0][1] = cd.m[1]; l.m[0][2] = cd.m[2];
+                    l.m[1][0] = cd.m[3]; l.m[1][1] = cd.m[4]; l.m[1][2] = cd.m[5];
+                    l.m[2][0] = cd.m[6]; l.m[2][1] = cd.m[7]; l.m[2][2] = cd.m[8];
+                    l.o = mk3(cd.o[0], cd.o[1], cd.o[2]);
+                    castConvex(shapes[cd.shape], mulXf(t, l), fr);
+                }
+            } else {  // :301-331: static plane / triangle mesh in the object's local space
+                Xf inv;  // Transform.inverse (lm/Transform.java:101-105)
+                for (int r = 0; r < 3; r++)
+                    for (int c = 0; c < 3; c++) inv.m[r][c] = t.m[c][r];
+                inv.o = mulMV(inv.m, neg3(t.o));
+                TriRay tr;
+                tr.from = xfPoint(inv, from);
+                tr.to = xfPoint(inv, to);
+                tr.hitFraction = 1.f;
+                tr.hit = false;
+                tr.normalLocal = mk3(0.f, 0.f, 0.f);
+                if (s.type == SH_MESH) rayMeshWalk(meshes[s.mesh], tr);
+                else rayPlaneTriangles(mk3(s.plane[0], s.plane[1], s.plane[2]), s.plane[3], tr);
+                if (tr.hit) {
+                    valid = true;
+                    fr = tr.hitFraction;
+                    nn = mulMV(t.m, tr.normalLocal);  // hitNormalWorld.mul(collisionObject.getWorldTransform().basis), not normalised
+                }
+            }
+            sValid[k] = valid ? 1 : 0;
             sFrac[k] = fr;
             sNrm[k][0] = nn.x; sNrm[k][1] = nn.y; sNrm[k][2] = nn.z;
         }
@@ -208,9 +371,7 @@ k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __re
                 if (sValid[bk] && sFrac[bk] < closest) {
                     closest = sFrac[bk];
                     hitBody = best;
-                    // castResult.normal.mul(rayFromTrans.basis) with the identity basis, then nor()
-                    f3 c = mk3(sNrm[bk][0], sNrm[bk][1], sNrm[bk][2]);
-                    hn = nor3(mk3(c.x * 1.f + c.y * 0.f + c.z * 0.f, c.x * 0.f + c.y * 1.f + c.z * 0.f, c.x * 0.f + c.y * 0.f + c.z * 1.f));
+                    hn = mk3(sNrm[bk][0], sNrm[bk][1], sNrm[bk][2]);
                 }
             }
             RayOut o;

@@ -70,3 +70,51 @@ def test_ray_kats(gpu_pkg):
     assert abs(frac[0] - (10.0 - (c[1] + 1.0)) / 20.0) < 1e-3 and abs(frac[1] - 0.5) < 1e-3 and frac[2] == 1.0
     assert np.allclose(nrm[:2], [[0, 1, 0], [0, 1, 0]], atol=1e-2)
     assert abs(pt[1][1]) < 1e-2
+
+
+def test_rays_against_terrain_mesh_plane_and_compounds(gpu_pkg):
+    """rayTestSingle's concave and compound branches (disp/CollisionWorld.java:301-356): BVH ray walk + triangle test for the
+    mesh, the two generated triangles for a static plane, every child of a compound — bit-identical to the oracle."""
+    sc = scenes.terrain_scene(cells=48, n=300, seed=14)
+    # add a static plane far below the terrain and a layer of compounds above it
+    rng = np.random.default_rng(21)
+    pl = sc.add_shape("plane", (0.1, 1.0, -0.05), -6.0)
+    sph = sc.add_shape("sphere", 0.35)
+    bar = sc.add_shape("box", (0.5, 0.12, 0.12))
+    eye = np.eye(3)
+    dumb = sc.add_shape("compound", [sph, bar, sph], scenes.make_xf(np.stack([eye] * 3), np.asarray([(-0.5, 0, 0), (0, 0, 0), (0.5, 0, 0)])))
+    extra_pos, extra_rot, extra_shape = [(0.0, 0.0, 0.0)], [eye], [pl]
+    for _ in range(80):
+        extra_pos.append(tuple(rng.uniform((1, 5, 1), (23, 8, 23))))
+        extra_rot.append(scenes.random_rotations(rng, 1)[0])
+        extra_shape.append(dumb)
+    for k, sid in enumerate(extra_shape):
+        sc.body_shape.append(sid); sc.static.append(k == 0); sc.group.append(2 if k == 0 else 1); sc.mask.append(-1 ^ 2 if k == 0 else -1); sc.world.append(0)
+    sc.base = np.concatenate([sc.base, scenes.make_xf(np.asarray(extra_rot), np.asarray(extra_pos))], axis=0)
+    sc.vel = None
+    sc.spin = None
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    f, t = _rays(rng, 1500, -2.0, 26.0)
+    f[:, 1] = rng.uniform(4.0, 12.0, size=len(f))
+    t[:, 1] = rng.uniform(-9.0, 2.0, size=len(t))
+    f[::7] = t[::7] + np.asarray([0.0, 15.0, 0.0], np.float32)     # some rays straight down
+    hits = _compare(gw, ow, f, t)
+    gu = gw.rayTestClosest(f, t)[0]
+    kinds = np.asarray([sc.shapes[sc.body_shape[u - 1]][0] for u in gu[gu > 0]])
+    assert hits > 1000 and (kinds == "mesh").sum() > 300 and (kinds == "plane").sum() > 10 and (kinds == "compound").sum() > 50
+    # rays from below the terrain: the mesh reports the flipped triangle normal
+    hits_up = _compare(gw, ow, t, f)
+    assert hits_up > 1000
+    # only the dynamic bodies answer (callback mask 1): compounds and convex bodies, no mesh / plane
+    _compare(gw, ow, f, t, group=1, mask=1)
+
+
+def test_rays_against_a_compound_heavy_scene(gpu_pkg):
+    sc = scenes.compound_scene(n=400, seed=17)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    rng = np.random.default_rng(5)
+    ext = float(sc.extent)
+    f, t = _rays(rng, 800, -1.0, ext)
+    f[:, 1] = rng.uniform(2.0, 8.0, size=len(f))
+    t[:, 1] = rng.uniform(-3.0, 1.0, size=len(t))
+    assert _compare(gw, ow, f, t) > 600
