@@ -358,8 +358,8 @@ def run_ours(args):
     # ---------------- end-to-end arm through the C ABI with HOST buffers: `e2e` ----------------
     P_cap = args.max_pairs
     pairs_host = torch.empty((P_cap, 2), dtype=torch.int32).pin_memory()
-    hdr_host = torch.empty((P_cap, 8), dtype=torch.int32).pin_memory()
-    pts_host = torch.empty((2 * P_cap, 24), dtype=torch.int32).pin_memory()
+    hdr_host = torch.empty((P_cap, 4), dtype=torch.int32).pin_memory()
+    pts_host = torch.empty((2 * P_cap, 12), dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
     nP, nH, nPt = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     e2e_ms = []
@@ -374,13 +374,13 @@ def run_ours(args):
         one_step()                                                                        # enqueue only, no host sync
         gw._ck(L.b2c_get_pairs(gw.h, ctypes.c_void_p(pairs_host.data_ptr()), P_cap, ctypes.byref(nP)))   # D2H pair list (while the narrowphase runs)
         gw.sync_counts()
-        gw._ck(L.b2c_get_solver_contacts(gw.h, ctypes.c_void_p(hdr_host.data_ptr()), P_cap, ctypes.c_void_p(pts_host.data_ptr()),
-                                         2 * P_cap, ctypes.byref(nH), ctypes.byref(nPt)))  # D2H contact stream (64-B solver points)
+        gw._ck(L.b2c_get_packed_contacts(gw.h, ctypes.c_void_p(hdr_host.data_ptr()), P_cap, ctypes.c_void_p(pts_host.data_ptr()),
+                                         2 * P_cap, ctypes.byref(nH), ctypes.byref(nPt)))  # D2H contact stream (16-B headers, 48-B points)
         t_end = time.perf_counter()
         step_no += 1
         if k >= 2:
             e2e_ms.append((t_end - t_start) * 1e3)
-            d2h = nP.value * 8 + nH.value * 32 + nPt.value * 64 + 128
+            d2h = nP.value * 8 + nH.value * 16 + nPt.value * 48 + 128
     barrier()
     e2e_ms_per_step = float(np.mean(e2e_ms))
     clocks = sampler.stop() if rank == 0 else None
@@ -455,7 +455,7 @@ def run_ours(args):
         "gpu_launches": int(launches_all),
         "e2e": {"value": (1000.0 / e2e_max) if strong else ngpu * 1000.0 / e2e_max, "unit": "steps/s", "ms_per_step": e2e_max,
                 "h2d_bytes_per_step": nb * 48, "d2h_bytes_per_step": int(d2h),
-                "what": "b2c_set_transforms(pinned host planes) + b2c_step_device + b2c_get_pairs (overlaps the narrowphase) + b2c_sync_counts + b2c_get_solver_contacts (32-B manifold headers + 64-B solver points), all into pinned host buffers"},
+                "what": "b2c_set_transforms(pinned host planes) + b2c_step_device + b2c_get_pairs (overlaps the narrowphase) + b2c_sync_counts + b2c_get_packed_contacts (16-B manifold headers + 48-B solver points: world points on A and B, normal, distance, lifetime, warm-start slot, triangle index), all into pinned host buffers"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": abytes[dom],

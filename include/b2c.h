@@ -202,6 +202,25 @@ typedef struct {
 int32_t b2c_get_solver_contacts(b2c_ctx*, b2c_contact_header* headers_out, int32_t cap_headers, b2c_solver_point* points_out,
                                 int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
 
+/* The same stream with nothing in it that the host can derive itself (bench.py's `e2e` uses this one): 16-byte headers
+ * and 48-byte points, one quarter fewer bytes over PCIe than b2c_get_solver_contacts.  The host already holds the pair list
+ * (b2c_get_pairs: uid0, uid1 = pairs[pair_index]), the bodies' materials (combined friction = clamp(f0 * f1, +-10),
+ * restitution = r0 * r1, disp/ManifoldResult.java:160-175) and positionWorldOnA/B are both kept (the solver reads both). */
+typedef struct {
+    int32_t pair_index;               /* index of the pair in the sorted pair list (also for child manifolds of compound pairs) */
+    int32_t first_point;              /* index of this manifold's first point in the point array */
+    int32_t info;                     /* num_contacts | algorithm << 8 | swapped << 16 (swapped: manifold body0 is pairs[pair_index].uid1) */
+    int32_t children;                 /* compound child manifold: (uint16)child0 | child1 << 16 (int16 each, -1 = not a compound); else -1 */
+} b2c_packed_header; /* 16 bytes */
+typedef struct {
+    float world_a[3], world_b[3], normal_on_b[3];
+    float distance;
+    int32_t life_src;                 /* life_time << 8 | (src_slot + 1)  (life_time saturates at 2^24 - 1) */
+    int32_t index1;                   /* triangle index for mesh pairs, else 0 */
+} b2c_packed_point; /* 48 bytes */
+int32_t b2c_get_packed_contacts(b2c_ctx*, b2c_packed_header* headers_out, int32_t cap_headers, b2c_packed_point* points_out,
+                                int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
+
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
 typedef struct {

@@ -54,6 +54,9 @@ final class B2C {
     static final MethodHandle step = h("b2c_step", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle getContacts = h("b2c_get_contacts",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    // 16-byte headers + 48-byte points: the contact stream with nothing the host can derive itself
+    static final MethodHandle getPackedContacts = h("b2c_get_packed_contacts",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle getManifolds = h("b2c_get_manifolds", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 
     // AxisSweep3(worldAabbMin, worldAabbMax): world box of the SAP broadphase modes

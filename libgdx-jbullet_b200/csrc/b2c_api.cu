@@ -1679,34 +1679,34 @@ int32_t b2c_get_stats(b2c_ctx* ctx, b2c_stats* out) {
     return B2C_OK;
 }
 
-static int32_t getContactsImpl(b2c_ctx* ctx, bool slim, b2c_contact_header* hOut, int32_t capH, void* pOut, int32_t capP, int32_t* nH,
+static int32_t getContactsImpl(b2c_ctx* ctx, int mode, void* hOut, int32_t capH, void* pOut, int32_t capP, int32_t* nH,
                                int32_t* nP) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     if (!ctx->pairsValid) return B2C_ERR_STATE;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     NpArgs a = makeNpArgs(ctx);
-    const size_t ptSize = slim ? sizeof(b2c_solver_point) : sizeof(b2c_manifold_point);
+    const size_t ptSize = mode == 2 ? sizeof(b2c_packed_point) : (mode == 1 ? sizeof(b2c_solver_point) : sizeof(b2c_manifold_point));
+    const size_t hdSize = mode == 2 ? sizeof(b2c_packed_header) : sizeof(b2c_contact_header);
     CK(cudaMemsetAsync(ctx->dContactCounts, 0, 2 * sizeof(uint32_t), s));
-    const unsigned grid = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
-    if (slim)
-        k_compact_contacts<true><<<grid, 256, 0, s>>>(a, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                      ctx->dContactCounts);
-    else
-        k_compact_contacts<false><<<grid, 256, 0, s>>>(a, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                       ctx->dContactCounts);
+    auto launch = [&](const NpArgs& na, unsigned grid, const uint32_t* itemPair) {
+        if (mode == 2)
+            k_compact_contacts<2><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts, itemPair);
+        else if (mode == 1)
+            k_compact_contacts<1><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts, itemPair);
+        else
+            k_compact_contacts<0><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts, itemPair);
+    };
+    launch(a, gridFor((uint32_t)ctx->cfg.max_pairs, 256), nullptr);
     if (ctx->hasCompound) {  // the child manifolds of compound pairs: the same compaction over the latest item arrays
         NpArgs a2 = a;
         a2.mhdr = ctx->dCH[ctx->ccur];
         a2.mpts = ctx->dCP[ctx->ccur];
         a2.numPairs = &ctx->dCompoundCtr->numItems;
-        const unsigned g2 = gridFor(ctx->maxCompoundItems, 256);
-        if (slim)
-            k_compact_contacts<true><<<g2, 256, 0, s>>>(a2, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                         ctx->dContactCounts);
-        else
-            k_compact_contacts<false><<<g2, 256, 0, s>>>(a2, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                          ctx->dContactCounts);
+        launch(a2, gridFor(ctx->maxCompoundItems, 256), ctx->dCItemPair);
     }
     uint32_t counts[2] = {0, 0};
     CK(cudaMemcpyAsync(counts, ctx->dContactCounts, sizeof(counts), cudaMemcpyDeviceToHost, s));
@@ -1716,7 +1716,7 @@ static int32_t getContactsImpl(b2c_ctx* ctx, bool slim, b2c_contact_header* hOut
     if (counts[0] > ctx->capContactHdr || counts[1] > ctx->capContactPts) { ctx->err = "contact stream capacity exceeded"; return B2C_ERR_CAPACITY; }
     if (!hOut && !pOut) return B2C_OK;
     if ((uint32_t)capH < counts[0] || (uint32_t)capP < counts[1]) { ctx->err = "contact output buffers too small"; return B2C_ERR_CAPACITY; }
-    if (hOut && counts[0]) CK(cudaMemcpyAsync(hOut, ctx->dContactHdr, (size_t)counts[0] * sizeof(b2c_contact_header), cudaMemcpyDeviceToHost, s));
+    if (hOut && counts[0]) CK(cudaMemcpyAsync(hOut, ctx->dContactHdr, (size_t)counts[0] * hdSize, cudaMemcpyDeviceToHost, s));
     if (pOut && counts[1]) CK(cudaMemcpyAsync(pOut, ctx->dContactPts, (size_t)counts[1] * ptSize, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B2C_OK;
@@ -1724,12 +1724,17 @@ static int32_t getContactsImpl(b2c_ctx* ctx, bool slim, b2c_contact_header* hOut
 
 int32_t b2c_get_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b2c_manifold_point* pOut, int32_t capP,
                          int32_t* nH, int32_t* nP) {
-    return getContactsImpl(ctx, false, hOut, capH, pOut, capP, nH, nP);
+    return getContactsImpl(ctx, 0, hOut, capH, pOut, capP, nH, nP);
 }
 
 int32_t b2c_get_solver_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t capH, b2c_solver_point* pOut, int32_t capP,
                                 int32_t* nH, int32_t* nP) {
-    return getContactsImpl(ctx, true, hOut, capH, pOut, capP, nH, nP);
+    return getContactsImpl(ctx, 1, hOut, capH, pOut, capP, nH, nP);
+}
+
+int32_t b2c_get_packed_contacts(b2c_ctx* ctx, b2c_packed_header* hOut, int32_t capH, b2c_packed_point* pOut, int32_t capP,
+                                int32_t* nH, int32_t* nP) {
+    return getContactsImpl(ctx, 2, hOut, capH, pOut, capP, nH, nP);
 }
 
 int32_t b2c_get_pair_deltas(b2c_ctx* ctx, int32_t* addedOut, int32_t capA, int32_t* removedOut, int32_t capR, int32_t* nA, int32_t* nR) {

@@ -1507,11 +1507,14 @@ __global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
 }
 
 // Compact the touching manifolds (header + live points) for the D2H contact stream.
-// SLIM: points are written as 64-byte b2c_solver_point records (what the constraint solver reads).
-template <bool SLIM>
+// MODE 0: 96-byte b2c_manifold_point records; MODE 1: 64-byte b2c_solver_point records (what the constraint solver reads);
+// MODE 2: 16-byte b2c_packed_header + 48-byte b2c_packed_point (nothing the host can derive itself crosses PCIe).
+// itemPair: null for the pair manifolds; for the child manifolds of compound pairs the pair index of every work item.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restrict__ ptsOut, uint32_t capH,
-                   uint32_t capP, uint32_t* __restrict__ counts /*[2]: headers, points*/) {
+                   uint32_t capP, uint32_t* __restrict__ counts /*[2]: headers, points*/, const uint32_t* __restrict__ itemPair) {
+    constexpr bool SLIM = MODE == 1;
     b2c_manifold_point* __restrict__ pts = reinterpret_cast<b2c_manifold_point*>(ptsOut);
     const uint32_t n = *a.numPairs;
     const int lane = threadIdx.x & 31;
@@ -1540,13 +1543,30 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restr
             uint32_t fp = baseP + (uint32_t)(incl - nc);
             if (h < capH && fp + nc <= capP) {
                 const ManifoldHdr* mf = a.mhdr + p;
-                b2c_contact_header hh;
-                hh.pair_uid0 = mf->pair_uid0; hh.pair_uid1 = mf->pair_uid1; hh.body0 = mf->body0; hh.body1 = mf->body1;
-                hh.num_contacts = nc; hh.algorithm = mf->algorithm; hh.first_point = (int)fp; hh.pair_index = (int)p;
-                hdr[h] = hh;
+                if (MODE == 2) {
+                    int4 ph;
+                    ph.x = itemPair ? (int)itemPair[p] : (int)p;
+                    ph.y = (int)fp;
+                    ph.z = nc | (mf->algorithm << 8) | ((mf->body0 != mf->pair_uid0) ? 0x10000 : 0);
+                    ph.w = itemPair ? ((mf->pad0 & 0xffff) | (mf->pad1 << 16)) : -1;  // child0 | child1 << 16 (int16 each, -1 = none)
+                    reinterpret_cast<int4*>(hdr)[h] = ph;
+                } else {
+                    b2c_contact_header hh;
+                    hh.pair_uid0 = mf->pair_uid0; hh.pair_uid1 = mf->pair_uid1; hh.body0 = mf->body0; hh.body1 = mf->body1;
+                    hh.num_contacts = nc; hh.algorithm = mf->algorithm; hh.first_point = (int)fp; hh.pair_index = (int)p;
+                    hdr[h] = hh;
+                }
                 for (int k = 0; k < nc; k++) {
                     const int4* src = reinterpret_cast<const int4*>(a.mpts + 4 * (size_t)p + k);
-                    if (!SLIM) {
+                    if (MODE == 2) {
+                        // words of the 96-byte record: 6-8 world_a, 9-11 world_b, 12-14 normal, 15 distance, 18 life, 19 src_slot, 21 index1
+                        const int4 v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4], v5 = src[5];
+                        int4* dst = reinterpret_cast<int4*>(reinterpret_cast<b2c_packed_point*>(ptsOut) + fp + k);
+                        dst[0] = make_int4(v1.z, v1.w, v2.x, v2.y);  // world_a xyz, world_b x
+                        dst[1] = make_int4(v2.z, v2.w, v3.x, v3.y);  // world_b yz, normal xy
+                        const int life = v4.z > 0xffffff ? 0xffffff : v4.z;
+                        dst[2] = make_int4(v3.z, v3.w, (life << 8) | ((v4.w + 1) & 0xff), v5.y);  // normal z, distance, life | src_slot+1, index1
+                    } else if (!SLIM) {
                         int4* dst = reinterpret_cast<int4*>(pts + fp + k);
                         for (int q = 0; q < 6; q++) dst[q] = src[q];
                     } else {

@@ -340,6 +340,16 @@ class GpuCollisionWorld:
             self._ck(self.L.b2c_get_solver_contacts(self.h, _vp(hdr), nh.value, _vp(pts), npt.value, C.byref(nh), C.byref(npt)))
         return hdr, pts
 
+    def packed_contacts(self):
+        """The contact stream with 16-byte headers and 48-byte points (include/b2c.h b2c_packed_header / b2c_packed_point)."""
+        nh, npt = C.c_int32(), C.c_int32()
+        self._ck(self.L.b2c_get_packed_contacts(self.h, None, 0, None, 0, C.byref(nh), C.byref(npt)))
+        hdr = np.zeros(nh.value, dtype=_lib.PACKED_HEADER_DTYPE)
+        pts = np.zeros(npt.value, dtype=_lib.PACKED_POINT_DTYPE)
+        if nh.value:
+            self._ck(self.L.b2c_get_packed_contacts(self.h, _vp(hdr), nh.value, _vp(pts), npt.value, C.byref(nh), C.byref(npt)))
+        return hdr, pts
+
     def set_profiling(self, on=True):
         self._ck(self.L.b2c_set_profiling(self.h, int(on)))
 

@@ -148,6 +148,58 @@ def test_contact_stream_matches_manifolds(gpu_pkg):
     assert np.array_equal(pts[first]["world_b"], m["points"][k, 0]["world_b"])
 
 
+def _check_packed_stream(gw):
+    """b2c_get_packed_contacts carries exactly the touching manifolds: every field bit-identical to b2c_get_manifolds."""
+    m = gw.manifolds(only_touching=True)
+    pairs = gw.pairs()
+    hdr, pts = gw.packed_contacts()
+    assert len(hdr) == len(m) and len(pts) == int(m["num_contacts"].sum())
+    nc = hdr["info"] & 0xff
+    alg = (hdr["info"] >> 8) & 0xff
+    swapped = (hdr["info"] >> 16) & 1
+    c0 = (hdr["children"] & 0xffff).astype(np.int16).astype(np.int32)
+    c1 = (hdr["children"] >> 16).astype(np.int32)
+    uid0, uid1 = pairs[hdr["pair_index"], 0], pairs[hdr["pair_index"], 1]
+    order = np.lexsort((c1, c0, uid1, uid0))
+    morder = np.lexsort((m["child1"], m["child0"], m["pair_uid1"], m["pair_uid0"]))
+    mm = m[morder]
+    assert np.array_equal(uid0[order], mm["pair_uid0"]) and np.array_equal(uid1[order], mm["pair_uid1"])
+    assert np.array_equal(c0[order], mm["child0"]) and np.array_equal(c1[order], mm["child1"])
+    assert np.array_equal(nc[order], mm["num_contacts"]) and np.array_equal(alg[order], mm["algorithm"])
+    assert np.array_equal(swapped[order] == 1, mm["body0"] != mm["pair_uid0"])
+    for k in range(4):
+        sel = nc[order] > k
+        pp = pts[hdr["first_point"][order][sel] + k]
+        ref = mm["points"][sel, k]
+        for f in ("world_a", "world_b", "normal_on_b", "distance"):
+            assert np.array_equal(pp[f].view(np.uint32), ref[f].view(np.uint32)), f
+        assert np.array_equal(pp["life_src"] >> 8, ref["life_time"]) and np.array_equal((pp["life_src"] & 0xff) - 1, ref["src_slot"])
+        assert np.array_equal(pp["index1"], ref["index1"])
+    return len(hdr)
+
+
+def test_packed_contact_stream(gpu_pkg):
+    sc = scenes.bin_scene(n=2000, seed=12)
+    gw = scenes.build_gpu(gpu_pkg, sc, mode=1)
+    for step in range(4):
+        gw.setWorldTransforms(sc.transforms(step))
+        gw.performDiscreteCollisionDetection()
+    assert _check_packed_stream(gw) > 500
+    # mesh pairs (triangle index) and compound pairs (child indices, pair index of the child manifolds)
+    sc = scenes.terrain_scene(cells=32, n=150, seed=6)
+    gw = scenes.build_gpu(gpu_pkg, sc, mode=1)
+    for step in range(3):
+        gw.setWorldTransforms(sc.transforms(step))
+        gw.performDiscreteCollisionDetection()
+    assert _check_packed_stream(gw) > 50
+    sc = scenes.compound_scene(n=250, seed=10)
+    gw = scenes.build_gpu(gpu_pkg, sc, mode=1)
+    for step in range(3):
+        gw.setWorldTransforms(sc.transforms(step))
+        gw.performDiscreteCollisionDetection()
+    assert _check_packed_stream(gw) > 100
+
+
 def test_c2_full_size_properties(gpu_pkg):
     """BASELINE size (100k bodies): size-independent properties instead of a full oracle run."""
     import bench
