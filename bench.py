@@ -360,6 +360,7 @@ def run_ours(args):
     pairs_host = torch.empty((P_cap, 2), dtype=torch.int32).pin_memory()
     hdr_host = torch.empty((P_cap, 4), dtype=torch.int32).pin_memory()
     pts_host = torch.empty((2 * P_cap, 12), dtype=torch.int32).pin_memory()
+    gw.set_contact_prefetch(2)   # the packed contact stream is compacted at the end of the step's graph
     e2e_steps = max(3, min(args.steps, 20))
     nP, nH, nPt = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     e2e_ms = []

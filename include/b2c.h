@@ -221,6 +221,11 @@ typedef struct {
 int32_t b2c_get_packed_contacts(b2c_ctx*, b2c_packed_header* headers_out, int32_t cap_headers, b2c_packed_point* points_out,
                                 int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
 
+/* Compact the contact stream behind every dispatch instead of inside its getter: format 0 = b2c_get_contacts, 1 =
+ * b2c_get_solver_contacts, 2 = b2c_get_packed_contacts, -1 = off (default).  The compaction then rides in the step's CUDA
+ * graph, its counts come back with b2c_sync_counts, and the getter of that format only issues the two exact-size copies. */
+int32_t b2c_set_contact_prefetch(b2c_ctx*, int32_t format);
+
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
 typedef struct {

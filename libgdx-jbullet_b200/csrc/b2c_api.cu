@@ -197,6 +197,10 @@ struct b2c_ctx {
     b2c_manifold_point* dContactPts = nullptr;
     uint32_t* dContactCounts = nullptr;
     uint32_t capContactHdr = 0, capContactPts = 0;
+    int contactPrefetch = -1;          // b2c_set_contact_prefetch: -1 off, else the stream format compacted at the end of every dispatch
+    int contactReady = -1;             // format of the stream sitting in dContactHdr / dContactPts for the last dispatch, or -1
+    uint32_t contactCounts[2] = {0, 0};
+    bool contactCountsValid = false;   // contactCounts came back with the step counters of the dispatch that compacted
 };
 
 namespace {
@@ -482,6 +486,34 @@ CompoundArgs makeCompoundArgs(b2c_ctx* ctx) {
     return c;
 }
 
+// Compaction of the touching manifolds into dContactHdr / dContactPts (format `mode`, see getContactsImpl)
+int32_t enqueueContactCompaction(b2c_ctx* ctx, int mode) {
+    cudaStream_t s = ctx->stream;
+    NpArgs a = makeNpArgs(ctx);
+    CK(cudaMemsetAsync(ctx->dContactCounts, 0, 2 * sizeof(uint32_t), s));
+    auto launch = [&](const NpArgs& na, unsigned grid, const uint32_t* itemPair) {
+        if (mode == 2)
+            k_compact_contacts<2><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts, itemPair);
+        else if (mode == 1)
+            k_compact_contacts<1><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts, itemPair);
+        else
+            k_compact_contacts<0><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts, itemPair);
+    };
+    launch(a, gridFor((uint32_t)ctx->cfg.max_pairs, 256), nullptr);
+    if (ctx->hasCompound) {  // the child manifolds of compound pairs: the same compaction over the latest item arrays
+        NpArgs a2 = a;
+        a2.mhdr = ctx->dCH[ctx->ccur];
+        a2.mpts = ctx->dCP[ctx->ccur];
+        a2.numPairs = &ctx->dCompoundCtr->numItems;
+        launch(a2, gridFor(ctx->maxCompoundItems, 256), ctx->dCItemPair);
+    }
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
 int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     if (!ctx->pairsValid) {
         ctx->err = "dispatch_all_pairs before calculate_overlapping_pairs";
@@ -596,12 +628,20 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     mark(ctx, 12);
     ctx->stageValid = ctx->prof;
     CK(cudaGetLastError());
+    if (ctx->contactPrefetch >= 0) {  // the contact stream is compacted behind the dispatch: its getter only copies
+        int32_t rc = enqueueContactCompaction(ctx, ctx->contactPrefetch);
+        if (rc) return rc;
+        ctx->launches += ctx->hasCompound ? 2 : 1;
+    }
     return B2C_OK;
 }
 
 int32_t readCounters(b2c_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->hCtrPinned, ctx->dCtr, sizeof(StepCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->contactReady >= 0)
+        CK(cudaMemcpyAsync(ctx->hCtrPinned + 1, ctx->dContactCounts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->contactReady >= 0) { memcpy(ctx->contactCounts, ctx->hCtrPinned + 1, sizeof(ctx->contactCounts)); ctx->contactCountsValid = true; }
     const StepCounters& c = *ctx->hCtrPinned;
     uint32_t np = c.pairCount;
     ctx->stats.num_pairs = (int32_t)(np < (uint32_t)ctx->cfg.max_pairs ? np : (uint32_t)ctx->cfg.max_pairs);
@@ -663,7 +703,7 @@ static void stepSignature(const b2c_ctx* ctx, int kind, uint64_t sig[4]) {
     sig[1] = ((uint64_t)(uint32_t)(ctx->cur & 1)) | ((uint64_t)(ctx->extPending ? 1 : 0) << 1) | ((uint64_t)(ctx->hasPlane ? 1 : 0) << 2) |
              ((uint64_t)(ctx->hasMesh ? 1 : 0) << 3) | ((uint64_t)(ctx->overlap ? 1 : 0) << 4) | ((uint64_t)(ctx->aabbPending ? 1 : 0) << 5) |
              ((uint64_t)(uint32_t)kind << 6) | ((uint64_t)(uint32_t)(ctx->epaHint + 1) << 8) | ((uint64_t)(ctx->hasCompound ? 1 : 0) << 10) |
-             ((uint64_t)(uint32_t)(ctx->ccur & 1) << 11) | ((uint64_t)(uint32_t)lhint << 16) |
+             ((uint64_t)(uint32_t)(ctx->ccur & 1) << 11) | ((uint64_t)(uint32_t)(ctx->contactPrefetch + 1) << 12) | ((uint64_t)(uint32_t)lhint << 16) |
              ((uint64_t)(uint32_t)ctx->partRank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
     sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide;
     sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8);
@@ -677,7 +717,15 @@ static void dropStepGraphs(b2c_ctx* ctx) {
 // Enqueue the broadphase and/or the narrowphase on the ctx stream.  A step is ~28 short kernels plus memsets and
 // side-stream joins; issued one by one the host falls behind the device in the broadphase (5-15 us kernels), so the
 // sequence is captured once per launch signature into a CUDA graph and replayed with a single cudaGraphLaunch.
+static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind);
 static int32_t enqueuePhases(b2c_ctx* ctx, int kind) {
+    ctx->contactReady = -1;  // whatever sat in the contact buffers belongs to an older pair list / dispatch
+    ctx->contactCountsValid = false;
+    int32_t rc = enqueuePhasesImpl(ctx, kind);
+    if (rc == B2C_OK && kind != 1) ctx->contactReady = ctx->contactPrefetch;
+    return rc;
+}
+static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind) {
     cudaStream_t s = ctx->stream;
     const bool broad = kind != 2, narrow = kind != 1;
     if (narrow && !broad && !ctx->pairsValid) {
@@ -888,7 +936,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dRowStart, (size_t)ctx->maxRows + 8));
     CKC(dalloc(&ctx->dGrid, (size_t)1));
     CKC(dalloc(&ctx->dCtr, (size_t)1));
-    CKC(cudaMallocHost((void**)&ctx->hCtrPinned, sizeof(StepCounters)));
+    CKC(cudaMallocHost((void**)&ctx->hCtrPinned, 2 * sizeof(StepCounters)));  // [1]: the prefetched contact-stream counts
     CKC(ctx->sortBodies.init((uint32_t)N));
     ctx->uidBits = bitsFor((uint32_t)N + 1u);
     CKC(dalloc(&ctx->dPairs, P));
@@ -1685,32 +1733,28 @@ static int32_t getContactsImpl(b2c_ctx* ctx, int mode, void* hOut, int32_t capH,
     if (!ctx->pairsValid) return B2C_ERR_STATE;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
-    NpArgs a = makeNpArgs(ctx);
     const size_t ptSize = mode == 2 ? sizeof(b2c_packed_point) : (mode == 1 ? sizeof(b2c_solver_point) : sizeof(b2c_manifold_point));
     const size_t hdSize = mode == 2 ? sizeof(b2c_packed_header) : sizeof(b2c_contact_header);
-    CK(cudaMemsetAsync(ctx->dContactCounts, 0, 2 * sizeof(uint32_t), s));
-    auto launch = [&](const NpArgs& na, unsigned grid, const uint32_t* itemPair) {
-        if (mode == 2)
-            k_compact_contacts<2><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                       ctx->dContactCounts, itemPair);
-        else if (mode == 1)
-            k_compact_contacts<1><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                       ctx->dContactCounts, itemPair);
-        else
-            k_compact_contacts<0><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                       ctx->dContactCounts, itemPair);
-    };
-    launch(a, gridFor((uint32_t)ctx->cfg.max_pairs, 256), nullptr);
-    if (ctx->hasCompound) {  // the child manifolds of compound pairs: the same compaction over the latest item arrays
-        NpArgs a2 = a;
-        a2.mhdr = ctx->dCH[ctx->ccur];
-        a2.mpts = ctx->dCP[ctx->ccur];
-        a2.numPairs = &ctx->dCompoundCtr->numItems;
-        launch(a2, gridFor(ctx->maxCompoundItems, 256), ctx->dCItemPair);
-    }
     uint32_t counts[2] = {0, 0};
-    CK(cudaMemcpyAsync(counts, ctx->dContactCounts, sizeof(counts), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    if (ctx->contactReady == mode && ctx->contactCountsValid) {
+        // compacted behind the dispatch (b2c_set_contact_prefetch) and the counts came back with the step counters
+        // (b2c_sync_counts / b2c_dispatch_all_pairs): nothing to launch, nothing to wait for
+        counts[0] = ctx->contactCounts[0];
+        counts[1] = ctx->contactCounts[1];
+    } else if (ctx->contactReady == mode) {
+        CK(cudaMemcpyAsync(counts, ctx->dContactCounts, sizeof(counts), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ctx->contactCounts[0] = counts[0]; ctx->contactCounts[1] = counts[1];
+        ctx->contactCountsValid = true;
+    } else {
+        int32_t rc = enqueueContactCompaction(ctx, mode);
+        if (rc) return rc;
+        ctx->contactReady = mode;
+        CK(cudaMemcpyAsync(counts, ctx->dContactCounts, sizeof(counts), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ctx->contactCounts[0] = counts[0]; ctx->contactCounts[1] = counts[1];
+        ctx->contactCountsValid = true;
+    }
     if (nH) *nH = (int32_t)counts[0];
     if (nP) *nP = (int32_t)counts[1];
     if (counts[0] > ctx->capContactHdr || counts[1] > ctx->capContactPts) { ctx->err = "contact stream capacity exceeded"; return B2C_ERR_CAPACITY; }
@@ -1735,6 +1779,12 @@ int32_t b2c_get_solver_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t 
 int32_t b2c_get_packed_contacts(b2c_ctx* ctx, b2c_packed_header* hOut, int32_t capH, b2c_packed_point* pOut, int32_t capP,
                                 int32_t* nH, int32_t* nP) {
     return getContactsImpl(ctx, 2, hOut, capH, pOut, capP, nH, nP);
+}
+
+int32_t b2c_set_contact_prefetch(b2c_ctx* ctx, int32_t format) {
+    if (!ctx || format < -1 || format > 2) return B2C_ERR_BAD_ARG;
+    ctx->contactPrefetch = format;
+    return B2C_OK;
 }
 
 int32_t b2c_get_pair_deltas(b2c_ctx* ctx, int32_t* addedOut, int32_t capA, int32_t* removedOut, int32_t capR, int32_t* nA, int32_t* nR) {

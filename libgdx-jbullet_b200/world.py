@@ -350,6 +350,10 @@ class GpuCollisionWorld:
             self._ck(self.L.b2c_get_packed_contacts(self.h, _vp(hdr), nh.value, _vp(pts), npt.value, C.byref(nh), C.byref(npt)))
         return hdr, pts
 
+    def set_contact_prefetch(self, fmt):
+        """Compact the contact stream (0 full / 1 solver / 2 packed points, -1 off) behind every dispatch."""
+        self._ck(self.L.b2c_set_contact_prefetch(self.h, int(fmt)))
+
     def set_profiling(self, on=True):
         self._ck(self.L.b2c_set_profiling(self.h, int(on)))
 

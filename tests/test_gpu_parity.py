@@ -198,6 +198,17 @@ def test_packed_contact_stream(gpu_pkg):
         gw.setWorldTransforms(sc.transforms(step))
         gw.performDiscreteCollisionDetection()
     assert _check_packed_stream(gw) > 100
+    # compaction behind the dispatch (b2c_set_contact_prefetch): the getter only copies; another format still works
+    gw.set_contact_prefetch(2)
+    for step in range(3, 7):
+        gw.step(np.ascontiguousarray(sc.transforms(step).T))
+        assert _check_packed_stream(gw) > 100
+        h1, p1 = gw.solver_contacts()
+        h2, p2 = gw.packed_contacts()
+        assert len(h1) == len(h2) and len(p1) == len(p2)
+    gw.set_contact_prefetch(-1)
+    gw.step(np.ascontiguousarray(sc.transforms(7).T))
+    assert _check_packed_stream(gw) > 100
 
 
 def test_c2_full_size_properties(gpu_pkg):
