@@ -97,8 +97,8 @@ int32_t b2c_shape_register_mesh(b2c_ctx*, const void* vertex_base, int32_t num_v
  * origin).  The local AABB is the running Math.min / Math.max of the children's AABBs (:60-80), collisionMargin stays 0 (:49).
  * Pairs with a compound on either side run disp/CompoundCollisionAlgorithm.java:83-129: one child algorithm and one
  * PersistentManifold per child (per child x child for two compounds), reported by b2c_get_manifolds / b2c_get_contacts with
- * the child indices.  Not built: compound children that are themselves compounds or concave, compound x triangle mesh (the
- * pair stays in the pair list but generates no contacts), compounds in a partitioned world. */
+ * the child indices.  The other object may be a box, sphere, hull, static plane, triangle mesh (ConvexConcave per child) or
+ * another compound.  Not built: compound children that are themselves compounds or concave, compounds in a partitioned world. */
 int32_t b2c_shape_register_compound(b2c_ctx*, int32_t num_children, const int32_t* child_shapes, const float* child_transforms12,
                                     int32_t* shape_out);
 /* Debug/inspection: copy the quantized BVH (16-byte nodes, sh/QuantizedBvhNodes.java:34-48) */
@@ -229,7 +229,8 @@ int32_t b2c_set_contact_prefetch(b2c_ctx*, int32_t format);
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
 typedef struct {
-    int32_t uid0, uid1, tri, has_contact; /* tri: triangle index for mesh pairs; -2 - k for child algorithm k of a compound pair; else -1 */
+    int32_t uid0, uid1, tri, has_contact; /* tri: triangle index for mesh pairs; -2 - k for child algorithm k of a compound
+                                             pair (-2 - (k << 21 | triangle) when the other object is a mesh); else -1 */
     float normal[3], point[3], depth;
     int32_t method; /* GjkPairDetector.lastUsedMethod (np/GjkPairDetector.java:54); 10 sphere-sphere; 11 convex-plane */
     int32_t iters;

@@ -27,6 +27,7 @@ namespace {
 
 constexpr int EPA_GRID = 148 * 2, EPA_BLOCK = 32;      // tier 0: one warp per block, per-lane pools in shared memory (2 blocks/SM)
 constexpr int EPA_GRID3 = 148 * 16, EPA_BLOCK3 = 64;   // tier 2: pools in local memory, throughput variant
+constexpr int COMPOUND_MESH_GRID = 148, COMPOUND_MESH_BLOCK = 64;  // k_compound_mesh: one full-size EPA pool per thread in global memory
 constexpr int EPA_GRID2 = 148 * 3, EPA_BLOCK2 = 64;    // tier 1: one item per warp, large pools in shared memory (2 x 34 KB per block)
 
 struct HostMesh {
@@ -171,6 +172,10 @@ struct b2c_ctx {
     uint32_t* dCItemCode = nullptr;
     int* dCItemPrev = nullptr;
     b2c_raw_contact* dCRaw = nullptr;
+    uint32_t* dCMeshStart = nullptr;                   // child x mesh items: their per-triangle records in dRawMesh
+    uint32_t* dCMeshCount = nullptr;
+    EpaScratch* dCBigScratch = nullptr;                // full-size EPA pools for k_compound_mesh (allocated when a world has both
+    uint32_t numCBigScratch = 0;                       //   compounds and meshes)
     ManifoldHdr* dCH[2] = {nullptr, nullptr};          // child manifolds, ping-pong per dispatch
     b2c_manifold_point* dCP[2] = {nullptr, nullptr};
     int ccur = 0;                                      // index of the LATEST child-manifold arrays
@@ -478,6 +483,10 @@ CompoundArgs makeCompoundArgs(b2c_ctx* ctx) {
     c.itemCode = ctx->dCItemCode;
     c.itemPrev = ctx->dCItemPrev;
     c.raw = ctx->dCRaw;
+    c.meshStart = ctx->dCMeshStart;
+    c.meshCount = ctx->dCMeshCount;
+    c.bigScratch = ctx->dCBigScratch;
+    c.numBigScratch = ctx->numCBigScratch;
     c.H = ctx->dCH[ctx->ccur ^ 1];
     c.P = ctx->dCP[ctx->ccur ^ 1];
     c.prevH = ctx->dCH[ctx->ccur];
@@ -623,6 +632,10 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         // per-child manifolds of the compound pairs, once every detector (and the penetration bin) has finished
         k_compound_manifold<<<gridFor(ctx->maxCompoundItems, 128, 148 * 8), 128, 0, s>>>(a, g.comp);
         ctx->launches += 1;
+        if (ctx->hasMesh) {  // child x triangle mesh: BVH query + per-triangle detector + fold, one thread per child work item
+            k_compound_mesh<<<COMPOUND_MESH_GRID, COMPOUND_MESH_BLOCK, 0, s>>>(a, g);
+            ctx->launches += 1;
+        }
         ctx->ccur ^= 1;
     }
     mark(ctx, 12);
@@ -1008,7 +1021,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
     cudaFree(ctx->dNoCollide);
     cudaFree(ctx->dChildren); cudaFree(ctx->dCompoundCtr); cudaFree(ctx->dCItemPair); cudaFree(ctx->dCItemCode); cudaFree(ctx->dCItemPrev);
-    cudaFree(ctx->dCRaw);
+    cudaFree(ctx->dCRaw); cudaFree(ctx->dCMeshStart); cudaFree(ctx->dCMeshCount); cudaFree(ctx->dCBigScratch);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->dCH[i]); cudaFree(ctx->dCP[i]); }
     cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
     for (int i = 0; i < 4; i++) {
@@ -1036,6 +1049,20 @@ int32_t b2c_set_world_aabb(b2c_ctx* ctx, const float mn[3], const float mx[3]) {
 }
 
 // ---- shapes ------------------------------------------------------------------------------------------
+// A world with both compounds and triangle meshes: k_compound_mesh finishes deep (child, triangle) penetrations in the thread,
+// its rare large polytopes in one full-size pool per thread (global memory)
+static int32_t ensureCompoundMeshScratch(b2c_ctx* ctx) {
+    if (!ctx->hasCompound || !ctx->hasMesh || ctx->dCBigScratch) return B2C_OK;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);  // graphs captured a null scratch pointer
+    ctx->graphs.clear();
+    const uint32_t n = (uint32_t)(COMPOUND_MESH_GRID * COMPOUND_MESH_BLOCK);
+    CK(cudaMalloc((void**)&ctx->dCBigScratch, (size_t)n * sizeof(EpaScratch)));
+    ctx->numCBigScratch = n;
+    return B2C_OK;
+}
+
 static int32_t addShape(b2c_ctx* ctx, const ShapeDev& s, int32_t* out) {
     if ((int)ctx->hShapes.size() >= ctx->cfg.max_shapes) { ctx->err = "shape table full"; return B2C_ERR_CAPACITY; }
     ctx->hShapes.push_back(s);
@@ -1146,6 +1173,8 @@ int32_t b2c_shape_register_mesh(b2c_ctx* ctx, const void* vbase, int32_t nv, int
     ctx->hMeshes.push_back(md);
     ctx->meshes.push_back(std::move(hm));
     ctx->hasMesh = true;
+    int32_t rcs = ensureCompoundMeshScratch(ctx);
+    if (rcs) return rcs;
     return addShape(ctx, s, out);
 }
 // sh/CompoundShape.java:50-82: new CompoundShape() then addChildShape(localTransform_i, child_i) for i = 0..n-1
@@ -1171,6 +1200,8 @@ int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* chil
         CK(dalloc(&ctx->dCItemCode, M));
         CK(dalloc(&ctx->dCItemPrev, M));
         CK(dalloc(&ctx->dCRaw, M));
+        CK(dalloc(&ctx->dCMeshStart, M));
+        CK(dalloc(&ctx->dCMeshCount, M));
         for (int i = 0; i < 2; i++) {
             CK(dalloc(&ctx->dCH[i], M));
             CK(dalloc(&ctx->dCP[i], 4 * M));
@@ -1211,6 +1242,8 @@ int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* chil
     s.pointOffset = first;
     s.numPoints = n;
     ctx->hasCompound = true;
+    int32_t rcs = ensureCompoundMeshScratch(ctx);
+    if (rcs) return rcs;
     return addShape(ctx, s, out);
 }
 int32_t b2c_mesh_get_bvh(b2c_ctx* ctx, int32_t shape, void* nodesOut, int32_t cap, int32_t* numNodes, float quant9[9]) {
@@ -1642,9 +1675,14 @@ int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, in
     if (rcc) return rcc;
     std::vector<ManifoldHdr> hdr(ctx->hasCompound ? n : 0);
     std::vector<b2c_raw_contact> craw(nCItems);
+    std::vector<uint32_t> cms(nCItems), cmc(nCItems);
     if (ctx->hasCompound && n) {
         CK(cudaMemcpyAsync(hdr.data(), ctx->dMHdr[ctx->cur], (size_t)n * sizeof(ManifoldHdr), cudaMemcpyDeviceToHost, ctx->stream));
         if (nCItems) CK(cudaMemcpyAsync(craw.data(), ctx->dCRaw, (size_t)nCItems * sizeof(b2c_raw_contact), cudaMemcpyDeviceToHost, ctx->stream));
+        if (nCItems && ctx->hasMesh) {
+            CK(cudaMemcpyAsync(cms.data(), ctx->dCMeshStart, (size_t)nCItems * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(cmc.data(), ctx->dCMeshCount, (size_t)nCItems * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
     }
     if (n) {
         CK(cudaMemcpyAsync(raw.data(), ctx->dRaw, (size_t)n * sizeof(b2c_raw_contact), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1673,6 +1711,13 @@ int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, in
             if (hdr[p].algorithm != 5) continue;
             const uint32_t start = (uint32_t)hdr[p].pad1, count = hostCompoundCount(ctx, hdr[p].pair_uid0, hdr[p].pair_uid1);
             for (uint32_t q = start; q < start + count && q < nCItems; q++) {
+                if (craw[q].has_contact == -3) {  // child x mesh: one record per (child, triangle) in the mesh item array
+                    for (uint32_t t = cms[q]; t < cms[q] + cmc[q] && t < nItems; t++) {
+                        if (out && k < cap) out[k] = rawMesh[t];
+                        k++;
+                    }
+                    continue;
+                }
                 if (out && k < cap) out[k] = craw[q];
                 k++;
             }

@@ -18,6 +18,8 @@
 //   k_compound_manifold  one thread per item: manifold of the previous dispatch -> this dispatch's slot, then
 //                        ManifoldResult.addContactPoint / refreshContactPoints against the ORIGINAL transforms of the pair's
 //                        two objects ("the contactpoint is still projected back using the original inverted worldtrans", :112)
+//   k_compound_mesh      child x BvhTriangleMeshShape (ConvexConcave per child): BVH query, per-triangle detector and the
+//                        order-dependent fold into the child's manifold, one thread per child work item
 // Pairs that are in the cache but not dispatched this step (both objects asleep, or linked by a constraint) keep their child
 // manifolds untouched: their items are copied forward and nothing else (BIN_COMPOUND_KEEP).
 //
@@ -105,7 +107,9 @@ __global__ void __launch_bounds__(128, 4) k_compound_gjk(NpArgs a, GjkArgs g, ui
                     const ShapeDev& sa = a.shapes[it.shapeA];
                     const ShapeDev& sb = a.shapes[it.shapeB];
                     b2c_raw_contact* rw = c.raw + item;
-                    if (sa.type == SH_SPHERE && sb.type == SH_SPHERE) {
+                    if (sb.type == SH_MESH) {
+                        rw->has_contact = -3;  // child x mesh: k_compound_mesh walks the BVH and writes per-triangle records
+                    } else if (sa.type == SH_SPHERE && sb.type == SH_SPHERE) {
                         // disp/SphereSphereCollisionAlgorithm.java:73-134 on (child, other)
                         const float r0 = sa.dims[0], r1 = sb.dims[0];
                         f3 diff = sub3(it.tA.o, it.tB.o);
@@ -218,10 +222,11 @@ __global__ void __launch_bounds__(128) k_compound_manifold(NpArgs a, CompoundArg
             m.h->pair_uid0 = it.pr.x; m.h->pair_uid1 = it.pr.y;
             m.h->body0 = it.bodyA + 1; m.h->body1 = it.bodyB + 1;
             m.h->num_contacts = 0;
-            m.h->algorithm = (ta == SH_SPHERE && tb == SH_SPHERE) ? 1 : (tb == SH_PLANE ? 2 : 3);
+            m.h->algorithm = (ta == SH_SPHERE && tb == SH_SPHERE) ? 1 : (tb == SH_PLANE ? 2 : (tb == SH_MESH ? 4 : 3));
             m.h->pad0 = it.childA; m.h->pad1 = it.childB;
         }
         for (int q = 0; q < m.h->num_contacts; q++) m.p[q].src_slot = q;
+        if (a.shapes[it.shapeB].type == SH_MESH) continue;  // contacts are folded in by k_compound_mesh
         // ManifoldResult of the PAIR (disp/ManifoldResult.java:70-75): root transforms and materials of its two objects
         const int b0 = it.pr.x - 1, b1 = it.pr.y - 1;
         const Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
@@ -234,6 +239,143 @@ __global__ void __launch_bounds__(128) k_compound_manifold(NpArgs a, CompoundArg
         }
         resultRefresh(m, it.pr.x, t0, t1, a.threshold);
     }
+    if (added) atomicAdd(&a.ctr->contactsAdded, added);
+}
+
+// np/GjkPairDetector.java:265-303: fold the penetration solver's answer into the detector result
+__device__ __forceinline__ void mergeEpaResult(const GjkResult& r, bool ok, f3 wA, f3 wB, bool& isValid, float& distance, f3& pointOnB,
+                                               f3& normalInB, int& method) {
+    isValid = r.isValid;
+    distance = r.distance;
+    pointOnB = r.pointOnB;
+    normalInB = r.normalInB;
+    method = r.lastUsedMethod;
+    if (ok) {
+        f3 nrm = sub3(wB, wA);
+        float lenSqr = len2_3(nrm);
+        if (lenSqr > (B2C_FLT_EPSILON * B2C_FLT_EPSILON)) {
+            nrm = scl3(nrm, 1.f / jsqrtf(lenSqr));
+            float distance2 = -len3(sub3(wA, wB));
+            if (!isValid || (distance2 < distance)) {
+                distance = distance2;
+                pointOnB = wB;
+                normalInB = nrm;
+                isValid = true;
+                method = 3;
+            }
+        } else {
+            method = 4;
+        }
+    } else {
+        method = 5;
+    }
+}
+
+// k_compound_mesh: child x BvhTriangleMeshShape = ConvexConcaveCollisionAlgorithm per child with the child's own manifold
+// (disp/ConvexConcaveCollisionAlgorithm.java:65-93, disp/ConvexTriangleCallback.java:83-172).  One thread per child work item:
+// the BVH query with the child's box in mesh space, then for every triangle in BVH order the convex-convex detector
+// (child, TriangleShape) and ManifoldResult.addContactPoint into the shared manifold (order-dependent 4-point reduction), one
+// refresh at the end.  Sequential per item — compounds resting on a mesh touch a handful of triangles per child — with the
+// penetration solver in the thread (medium pool in local memory, full-size pool in this thread's global-memory slot on overflow).
+__global__ void __launch_bounds__(64) k_compound_mesh(NpArgs a, GjkArgs g) {
+    const CompoundArgs& c = g.comp;
+    const uint32_t n = c.cc->numItems;
+    uint32_t checks = 0, deep = 0, failed = 0, added = 0;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t item = tid; item < n; item += gridDim.x * blockDim.x) {
+        const uint32_t code = c.itemCode[item];
+        if (code & CITEM_KEEP) continue;
+        CompoundItem it;
+        decodeCompoundItem(a, c, c.itemPair[item], code, it);
+        const ShapeDev& ms = a.shapes[it.shapeB];
+        if (ms.type != SH_MESH) continue;
+        const ShapeDev& cs = a.shapes[it.shapeA];
+        const MeshDev md = a.meshes[ms.mesh];
+        const Xf convexInTri = invMul(it.tB, it.tA);
+        f3 mn, mx;
+        convexAabbIn(cs, convexInTri, mn, mx);
+        const f3 extra = mk3(ms.margin, ms.margin, ms.margin);
+        mx = add3(mx, extra);
+        mn = sub3(mn, extra);
+        uint32_t qmin[3], qmax[3];
+        quantizeClamp(md, mn, qmin);
+        quantizeClamp(md, mx, qmax);
+        uint32_t count = 0;
+        walkBvh(md, qmin, qmax, [&](int) { count++; });
+        const uint32_t start = atomicAdd(&a.ctr->meshItems, count);
+        if (start + count > g.maxMeshItems) {
+            a.ctr->meshOverflow = 1;
+            c.meshStart[item] = 0;
+            c.meshCount[item] = 0;
+            continue;
+        }
+        c.meshStart[item] = start;
+        c.meshCount[item] = count;
+        MView m;
+        m.h = c.H + item;
+        m.p = c.P + 4 * (size_t)item;
+        const int b0 = it.pr.x - 1, b1 = it.pr.y - 1;
+        const Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
+        const float2 m0 = a.material[b0], m1 = a.material[b1];
+        const float fr = combinedFriction(m0.x, m1.x), re = m0.y * m1.y;
+        LaneShape A;
+        A.load(cs, a.hullPts);
+        const float mA = cs.margin, mB = ms.margin;
+        const float maxd = mA + mB + a.threshold;
+        uint32_t k = start;
+        walkBvh(md, qmin, qmax, [&](int tri) {
+            const TriS T = loadTri(md, tri, ms.margin);
+            GjkLane L;
+            L.begin(it.tA, it.tB, mA, mB, maxd * maxd);
+            checks++;
+            for (;;) {
+                f3 pW = add3(mulMV(it.tA.m, A.support(L.dirA(it.tA))), L.laO);
+                f3 qW = add3(mulMV(it.tB.m, T.support(L.dirB(it.tB))), L.lbO);
+                if (L.iterate(pW, qW)) break;
+            }
+            GjkResult r;
+            L.finish(r);
+            bool isValid = r.isValid;
+            float distance = r.distance;
+            f3 pointOnB = r.pointOnB, normalInB = r.normalInB;
+            int method = r.lastUsedMethod;
+            if (r.needEpa) {
+                deep++;
+                AnyS EA = makeAnyS(cs, a.hullPts), EB;
+                EB.type = SH_TRIANGLE; EB.h = mk3(0, 0, 0); EB.ta = T.a; EB.tb = T.b; EB.tc = T.c; EB.pts = nullptr; EB.n = 0; EB.margin = ms.margin;
+                Xf la = it.tA, lb = it.tB;
+                la.o = sub3(it.tA.o, r.positionOffset);
+                lb.o = sub3(it.tB.o, r.positionOffset);
+                f3 wA, wB;
+                bool epaFail = false, poolOverflow = false, ok;
+                {
+                    EpaScratchLocal sc;
+                    ok = epaPenetration(EA, EB, la, lb, &sc, wA, wB, epaFail, poolOverflow);
+                }
+                if (poolOverflow) {
+                    if (c.bigScratch && tid < c.numBigScratch) {
+                        EpaScratch* big = reinterpret_cast<EpaScratch*>(c.bigScratch) + tid;
+                        ok = epaPenetration(EA, EB, la, lb, big, wA, wB, epaFail, poolOverflow);
+                    }
+                    if (poolOverflow) { epaFail = true; ok = false; }
+                }
+                if (epaFail) failed++;
+                mergeEpaResult(r, ok, wA, wB, isValid, distance, pointOnB, normalInB, method);
+            }
+            const f3 pt = add3(pointOnB, r.positionOffset);
+            // raw-record key of (child algorithm, triangle): -2 - (k << 21 | t)
+            writeRaw(g.rawMesh + k, it.pr, -2 - (int)((code << 21) | (uint32_t)tri), isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0),
+                     isValid ? pt : mk3(0, 0, 0), isValid ? distance : 0.f, method, r.curIter);
+            if (isValid) {
+                if (manifoldAdd(m, it.pr.x, t0, t1, normalInB, pt, distance, a.threshold, fr, re, 0, tri)) added++;
+            }
+            k++;
+        });
+        resultRefresh(m, it.pr.x, t0, t1, a.threshold);
+    }
+    if (checks) atomicAdd(&a.ctr->gjkChecks, checks);
+    if (deep) atomicAdd(&a.ctr->deepChecks, deep);
+    if (failed) atomicAdd(&a.ctr->epaFailed, failed);
     if (added) atomicAdd(&a.ctr->contactsAdded, added);
 }
 

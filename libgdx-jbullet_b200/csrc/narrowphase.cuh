@@ -495,12 +495,12 @@ k_import_arrival_slots(const unsigned char* __restrict__ slots, uint32_t nslots,
 // ---- k_classify: needsCollision + algorithm table --------------------------------------------------
 __device__ __forceinline__ bool isConvexType(int t) { return t == SH_BOX || t == SH_SPHERE || t == SH_HULL; }
 
-// compound x {box, sphere, hull, plane, compound}: children are convex, so every child algorithm is one of sphere-sphere,
-// convex-plane, convex-convex.  compound x triangle mesh (ConvexConcave per child) is not built: the pair is skipped.
+// compound x {box, sphere, hull, plane, mesh, compound}: children are convex, so every child algorithm is one of
+// sphere-sphere, convex-plane, convex-convex, convex-concave.
 __device__ __forceinline__ bool compoundPairSupported(int t0, int t1) {
     if (t0 != SH_COMPOUND && t1 != SH_COMPOUND) return false;
     const int other = t0 == SH_COMPOUND ? t1 : t0;
-    return other == SH_COMPOUND || other == SH_PLANE || isConvexType(other);
+    return other == SH_COMPOUND || other == SH_PLANE || other == SH_MESH || isConvexType(other);
 }
 
 __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
@@ -767,7 +767,11 @@ struct CompoundArgs {
     uint32_t* itemPair;            // [maxItems] pair index
     uint32_t* itemCode;            // [maxItems] k = i * n1 + j (index of the item inside its pair) | CITEM_KEEP
     int* itemPrev;                 // [maxItems] the same item in the previous dispatch's arrays, or -1
-    b2c_raw_contact* raw;          // [maxItems] detector output
+    b2c_raw_contact* raw;          // [maxItems] detector output (has_contact -3: child x mesh, records are in the mesh item array)
+    uint32_t* meshStart;           // [maxItems] child x mesh items: first (child, triangle) record in GjkArgs.rawMesh
+    uint32_t* meshCount;           // [maxItems]
+    void* bigScratch;              // EpaScratch per thread of k_compound_mesh (global memory), or null
+    uint32_t numBigScratch;
     ManifoldHdr* H;                // [maxItems] child manifolds of this dispatch (header word pad0 / pad1 = child index in
     b2c_manifold_point* P;         //            body0's / body1's compound shape, -1 = that object is not a compound)
     const ManifoldHdr* prevH;      // the previous dispatch's

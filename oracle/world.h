@@ -611,8 +611,16 @@ struct World {
         } else if (sa->isConvex() && sb->isConvex()) {
             if (!kid.hasManifold) { kid.hasManifold = true; kid.manifold.body0 = a.uid; kid.manifold.body1 = b.uid; }
             convexConvex(sa, sb, a, b, res, true, code);
-        } else {
-            // child x triangle mesh (ConvexConcave per child) is not restated: neither side generates contacts for it
+        } else if (sa->isConvex() && sb->type == SH_MESH) {
+            // ConvexConcaveCollisionAlgorithm(child, mesh) with the child algorithm's own ConvexTriangleCallback manifold
+            // (disp/ConvexConcaveCollisionAlgorithm.java:47-93, disp/ConvexTriangleCallback.java:58-66): setBodies(convex, tri)
+            kid.hasManifold = true;
+            kid.manifold.body0 = a.uid; kid.manifold.body1 = b.uid;
+            convexConcave(sa, sb, a, b, res);
+            res.partId0 = res.partId1 = res.index0 = res.index1 = 0;
+            // raw-record key of (child algorithm k, triangle t): -2 - (k << 21 | t)   (t < 2^21, sh/OptimizedBvh.java:65)
+            for (size_t r = rawBefore; r < raw.size(); r++) { raw[r].uid0 = res.body0; raw[r].uid1 = res.body1; raw[r].tri = -2 - (((k - 1) << 21) | raw[r].tri); }
+            return;
         }
         for (size_t r = rawBefore; r < raw.size(); r++) { raw[r].uid0 = res.body0; raw[r].uid1 = res.body1; raw[r].tri = code; }
     }

@@ -326,6 +326,39 @@ def compound_scene(n=300, seed=8, plane_ground=True, spacing=0.9, compound_share
     return sc
 
 
+def terrain_compound_scene(cells=32, n=150, seed=15, cell=0.5):
+    """Compounds (and a few plain convex bodies) resting on a BVH triangle-mesh heightfield: compound x mesh runs
+    ConvexConcave per child (SURVEY §8f rank 3 with §8a N10)."""
+    rng = np.random.default_rng(SEED + seed)
+    sc = Scene()
+    verts, tris, h = heightfield(cells, cell=cell, amp=1.5, seed=seed)
+    m = sc.add_shape("mesh", verts, tris)
+    sc.body_shape.append(m); sc.static.append(True); sc.group.append(2); sc.mask.append(-1 ^ 2); sc.world.append(0)
+    eye = np.eye(3)
+    sph = sc.add_shape("sphere", 0.3)
+    bar = sc.add_shape("box", (0.45, 0.12, 0.12))
+    slab = sc.add_shape("box", (0.35, 0.12, 0.3))
+    hl = sc.add_shape("hull", hull_points(rng, 0.3))
+    compounds = [
+        sc.add_shape("compound", [sph, bar, sph], make_xf(np.stack([eye] * 3), np.asarray([(-0.5, 0, 0), (0, 0, 0), (0.5, 0, 0)]))),
+        sc.add_shape("compound", [slab, hl], make_xf(np.stack([eye, small_rotation(rng, 1, 0.6)[0]]), np.asarray([(0, -0.1, 0), (0.2, 0.25, 0.1)]))),
+    ]
+    plain = [sph, slab, hl]
+    size = cells * cell
+    xz = rng.uniform(1.0, size - 1.0, size=(n, 2))
+    gi = np.clip((xz / cell).astype(int), 0, cells - 1)
+    y = h[gi[:, 0], gi[:, 1]] + 0.3 + rng.uniform(-0.1, 0.25, size=n)
+    pos = np.stack([xz[:, 0], y, xz[:, 1]], axis=1)
+    for k in range(n):
+        sid = compounds[rng.integers(2)] if rng.uniform() < 0.7 else plain[rng.integers(3)]
+        sc.body_shape.append(sid); sc.static.append(False); sc.group.append(1); sc.mask.append(-1); sc.world.append(0)
+    sc.base = make_xf(np.concatenate([eye[None], random_rotations(rng, n)], axis=0), np.concatenate([np.zeros((1, 3)), pos], axis=0))
+    sc.vel = rng.uniform(-0.004, 0.004, size=(n + 1, 3))
+    sc.spin = small_rotation(rng, n + 1, 0.003)
+    sc.extent = float(size)
+    return sc
+
+
 # ---- build the same scene on both sides ---------------------------------------------------------------
 def build_gpu(pkg, sc, mode, max_pairs=None, **kw):
     n = sc.n

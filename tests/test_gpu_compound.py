@@ -112,3 +112,19 @@ def test_compound_registered_after_first_steps_and_capacity(gpu_pkg):
     assert e.value.code == -3
     with pytest.raises(gpu_pkg.B2CError):          # children must be convex
         gw.CompoundShape([c], np.stack([xf((0, 0, 0))]))
+
+
+def test_compounds_on_a_triangle_mesh(gpu_pkg):
+    """compound x BvhTriangleMeshShape: ConvexConcave per child, per-triangle raw records keyed -2 - (child << 21 | triangle),
+    the child manifolds folded in BVH order with the triangle index in index1."""
+    sc = scenes.terrain_compound_scene(cells=32, n=150, seed=15)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    touching = 0
+    for step in range(5):
+        r = parity.step_and_compare(gw, ow, sc.transforms(step), sc.extent)
+        m = gw.manifolds()
+        kid_mesh = (m["child0"] >= 0) & (m["algorithm"] == 4)
+        touching += int((m["num_contacts"][kid_mesh] > 0).sum())
+        assert gw.getDispatcher().getNumManifolds() == len(m)
+        assert gw.stats()["epa_failed"] == 0
+    assert kid_mesh.sum() > 150 and touching > 100
