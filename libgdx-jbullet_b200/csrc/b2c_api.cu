@@ -1189,6 +1189,7 @@ int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* chil
         }
     }
     if ((int)ctx->hShapes.size() >= ctx->cfg.max_shapes) { ctx->err = "shape table full"; return B2C_ERR_CAPACITY; }
+    if (ctx->partRanks > 1) { ctx->err = "compound shapes are not supported in a partitioned world"; return B2C_ERR_STATE; }
     cudaSetDevice(ctx->device);
     if (!ctx->dCompoundCtr) {  // first compound: the child work-item arrays
         const int want = ctx->cfg.max_compound_items;
@@ -1974,6 +1975,10 @@ const char* b2c_stage_name(int32_t k) {
 
 int32_t b2c_set_partition(b2c_ctx* ctx, int32_t rank, int32_t nranks) {
     if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return B2C_ERR_BAD_ARG;
+    if (nranks > 1 && ctx->hasCompound) {  // child manifolds do not migrate between ranks (compound.cuh)
+        ctx->err = "compound shapes are not supported in a partitioned world";
+        return B2C_ERR_STATE;
+    }
     ctx->partRank = rank;
     ctx->partRanks = nranks;
     return B2C_OK;
