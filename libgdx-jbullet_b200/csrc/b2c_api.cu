@@ -188,6 +188,9 @@ struct b2c_ctx {
     float4* dRayMax = nullptr;
     float* dRayIn = nullptr;       // from | to, 6 floats per ray
     RayOut* dRayOut = nullptr;
+    float4* dRayChunkMin = nullptr;   // boxes of RAY_CHUNK consecutive bodies in the last broadphase's sorted order
+    float4* dRayChunkMax = nullptr;
+    int nSortedBodies = 0;            // bodies covered by dSmin's sorted order (0: no broadphase has run)
     uint32_t* dRayOverflow = nullptr;
     int rayCap = 0;
 
@@ -434,6 +437,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
                                                                       ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
                                                                       ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr, ctx->dHist);
     ctx->launches += 10 + ctx->sortBodies.launches;
+    ctx->nSortedBodies = n;  // dSmin.w = proxy index of every sorted position: the ray tests reuse the order
     CK(cudaGetLastError());
     CK(cudaEventRecordWithFlags(ctx->evPairsReady, s, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     ctx->step++;
@@ -770,6 +774,7 @@ static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind) {
             ctx->cur ^= 1;
             ctx->step++;
             ctx->pairsValid = true;
+            ctx->nSortedBodies = ctx->nBodies;
         }
         if (narrow && ctx->hasCompound) ctx->ccur ^= 1;
         ctx->stageValid = false;
@@ -1018,7 +1023,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
-    cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
+    cudaFree(ctx->dRayChunkMin); cudaFree(ctx->dRayChunkMax); cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
     cudaFree(ctx->dNoCollide);
     cudaFree(ctx->dChildren); cudaFree(ctx->dCompoundCtr); cudaFree(ctx->dCItemPair); cudaFree(ctx->dCItemCode); cudaFree(ctx->dCItemPrev);
     cudaFree(ctx->dCRaw); cudaFree(ctx->dCMeshStart); cudaFree(ctx->dCMeshCount); cudaFree(ctx->dCBigScratch);
@@ -1434,8 +1439,7 @@ int32_t b2c_set_no_collide_pairs(b2c_ctx* ctx, int32_t n, const int32_t* uidPair
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     CK(cudaStreamSynchronize(ctx->stream));  // a step in flight may still be reading the old list
     if (keys.size() > ctx->capNoCollide) {
-        cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
-    cudaFree(ctx->dNoCollide);
+        cudaFree(ctx->dNoCollide);
         ctx->dNoCollide = nullptr;
         ctx->capNoCollide = 0;
         CK(cudaMalloc((void**)&ctx->dNoCollide, keys.size() * sizeof(uint64_t)));
@@ -1904,6 +1908,8 @@ int32_t b2c_ray_test_closest(b2c_ctx* ctx, int32_t n, const float* from, const f
     if (!ctx->dRayMin) CK(dalloc(&ctx->dRayMin, N));
     if (!ctx->dRayMax) CK(dalloc(&ctx->dRayMax, N));
     if (!ctx->dRayOverflow) CK(dalloc(&ctx->dRayOverflow, (size_t)1));
+    if (!ctx->dRayChunkMin) CK(dalloc(&ctx->dRayChunkMin, N / RAY_CHUNK + 2));
+    if (!ctx->dRayChunkMax) CK(dalloc(&ctx->dRayChunkMax, N / RAY_CHUNK + 2));
     if (n > ctx->rayCap) {
         cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut);
         ctx->dRayIn = nullptr; ctx->dRayOut = nullptr; ctx->rayCap = 0;
@@ -1915,10 +1921,16 @@ int32_t b2c_ray_test_closest(b2c_ctx* ctx, int32_t n, const float* from, const f
     CK(cudaMemcpyAsync(ctx->dRayIn, from, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->dRayIn + 3 * (size_t)n, to, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->dRayOverflow, 0, sizeof(uint32_t), s));
-    if (nb > 0) k_ray_aabbs<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, nb, ctx->dRayMin, ctx->dRayMax);
+    const int nSorted = ctx->nSortedBodies < nb ? ctx->nSortedBodies : nb;
+    if (nb > 0) {
+        k_ray_aabbs<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, nb, ctx->dRayMin, ctx->dRayMax);
+        const int nChunks = (nb + RAY_CHUNK - 1) / RAY_CHUNK;
+        k_ray_chunks<<<(nChunks + 127) / 128, 128, 0, s>>>(ctx->dRayMin, ctx->dRayMax, ctx->dSmin, nSorted, nb, ctx->dRayChunkMin,
+                                                          ctx->dRayChunkMax);
+    }
     const uint32_t cbFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
     const unsigned grid = (unsigned)(n < 148 * 16 ? n : 148 * 16);
-    k_ray_test<<<grid, RAY_THREADS, 0, s>>>(ctx->B, ctx->dShapes, ctx->dHullPts, ctx->dMeshes, ctx->dChildren, nb, ctx->dRayMin, ctx->dRayMax, ctx->dRayIn,
+    k_ray_test<<<grid, RAY_THREADS, 0, s>>>(ctx->B, ctx->dShapes, ctx->dHullPts, ctx->dMeshes, ctx->dChildren, ctx->dSmin, nSorted, ctx->dRayChunkMin, ctx->dRayChunkMax, nb, ctx->dRayMin, ctx->dRayMax, ctx->dRayIn,
                                             ctx->dRayIn + 3 * (size_t)n, n, cbFilter, ctx->dRayOut, ctx->dRayOverflow);
     std::vector<RayOut> host((size_t)n);
     uint32_t ov = 0;

@@ -244,6 +244,43 @@ k_ray_aabbs(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, float4* __
     rmax[i] = mx;
 }
 
+// Culling of the body loop.  Bodies are taken in the order the last broadphase sorted them (grid row, then x: consecutive
+// positions are neighbours in space; bodies created since follow in index order) and grouped into chunks of RAY_CHUNK; a chunk
+// box is the union of its members' boxes, inflated a little so that a segment touching a member box can never miss the union
+// through rounding.  A ray tests the chunk boxes first and only the members of the chunks it meets: the candidate set stays a
+// superset of "bodies whose box the ray meets", so the results are unchanged.
+constexpr int RAY_CHUNK = 64;
+__device__ __forceinline__ int rayBodyAt(const float4* __restrict__ sortedMin, int nSorted, int pos) {
+    return pos < nSorted ? (int)__float_as_uint(__ldg(&sortedMin[pos].w)) : pos;
+}
+__global__ void __launch_bounds__(128)
+k_ray_chunks(const float4* __restrict__ rmin, const float4* __restrict__ rmax, const float4* __restrict__ sortedMin, int nSorted, int n,
+             float4* __restrict__ cmin, float4* __restrict__ cmax) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nChunks = (n + RAY_CHUNK - 1) / RAY_CHUNK;
+    if (c >= nChunks) return;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    int members = 0;
+    for (int k = 0; k < RAY_CHUNK; k++) {
+        const int pos = c * RAY_CHUNK + k;
+        if (pos >= n) break;
+        const int i = rayBodyAt(sortedMin, nSorted, pos);
+        if (i < 0 || i >= n) continue;
+        const float4 a = __ldg(rmin + i);
+        if (a.w == 0.f) continue;
+        const float4 b = __ldg(rmax + i);
+        lo[0] = fminf(lo[0], a.x); lo[1] = fminf(lo[1], a.y); lo[2] = fminf(lo[2], a.z);
+        hi[0] = fmaxf(hi[0], b.x); hi[1] = fmaxf(hi[1], b.y); hi[2] = fmaxf(hi[2], b.z);
+        members++;
+    }
+    for (int d = 0; d < 3; d++) {  // conservative inflation: absolute + relative
+        lo[d] = lo[d] - (1e-3f + 1e-5f * fabsf(lo[d]));
+        hi[d] = hi[d] + (1e-3f + 1e-5f * fabsf(hi[d]));
+    }
+    cmin[c] = make_float4(lo[0], lo[1], lo[2], members ? 1.f : 0.f);
+    cmax[c] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
 struct RayOut {
     int uid;          // 0 = no hit
     float fraction;   // closestHitFraction (1 = no hit)
@@ -253,7 +290,8 @@ struct RayOut {
 
 __global__ void __launch_bounds__(RAY_THREADS)
 k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __restrict__ hullPts, const MeshDev* __restrict__ meshes,
-           const CompoundChildDev* __restrict__ children, int n,
+           const CompoundChildDev* __restrict__ children, const float4* __restrict__ sortedMin, int nSorted,
+           const float4* __restrict__ cmin, const float4* __restrict__ cmax, int n,
            const float4* __restrict__ rmin, const float4* __restrict__ rmax, const float* __restrict__ rayFrom,
            const float* __restrict__ rayTo, int numRays, uint32_t cbFilter /* group | mask << 16 */, RayOut* __restrict__ out,
            uint32_t* __restrict__ overflow) {
@@ -269,14 +307,25 @@ k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __re
         if (threadIdx.x == 0) sCount = 0;
         __syncthreads();
         // (1) every body whose AABB the ray meets under the widest bound (closestHitFraction = 1)
-        for (int i = threadIdx.x; i < n; i += RAY_THREADS) {
-            const float4 mn = __ldg(rmin + i);
-            if (mn.w == 0.f) continue;
-            if (!filterPass(cbFilter, B.filt[i])) continue;  // RayResultCallback.needsCollision (disp/CollisionWorld.java:664-670)
-            const float4 mx = __ldg(rmax + i);
-            if (rayAabb(from, to, mk3(mn.x, mn.y, mn.z), mk3(mx.x, mx.y, mx.z), 1.f)) {
-                uint32_t k = atomicAdd(&sCount, 1u);
-                if (k < RAY_MAX_CAND) sCand[k] = (uint32_t)i;
+        const int nChunks = (n + RAY_CHUNK - 1) / RAY_CHUNK;
+        for (int c = threadIdx.x; c < nChunks; c += RAY_THREADS) {
+            const float4 cn = __ldg(cmin + c);
+            if (cn.w == 0.f) continue;
+            const float4 cx = __ldg(cmax + c);
+            if (!rayAabb(from, to, mk3(cn.x, cn.y, cn.z), mk3(cx.x, cx.y, cx.z), 1.f)) continue;
+            for (int m = 0; m < RAY_CHUNK; m++) {
+                const int pos = c * RAY_CHUNK + m;
+                if (pos >= n) break;
+                const int i = rayBodyAt(sortedMin, nSorted, pos);
+                if (i < 0 || i >= n) continue;
+                const float4 mn = __ldg(rmin + i);
+                if (mn.w == 0.f) continue;
+                if (!filterPass(cbFilter, B.filt[i])) continue;  // RayResultCallback.needsCollision (disp/CollisionWorld.java:664-670)
+                const float4 mx = __ldg(rmax + i);
+                if (rayAabb(from, to, mk3(mn.x, mn.y, mn.z), mk3(mx.x, mx.y, mx.z), 1.f)) {
+                    uint32_t k = atomicAdd(&sCount, 1u);
+                    if (k < RAY_MAX_CAND) sCand[k] = (uint32_t)i;
+                }
             }
         }
         __syncthreads();
