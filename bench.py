@@ -374,6 +374,8 @@ def run_ours(args):
         gw.setWorldTransformsHostPtr(nb, hframes[frame_index(step_no)].data_ptr())       # H2D of this step's inputs
         one_step()                                                                        # enqueue only, no host sync
         gw._ck(L.b2c_get_pairs(gw.h, ctypes.c_void_p(pairs_host.data_ptr()), P_cap, ctypes.byref(nP)))   # D2H pair list (while the narrowphase runs)
+        gw._ck(L.b2c_begin_contact_download(gw.h, ctypes.c_void_p(hdr_host.data_ptr()), P_cap, ctypes.c_void_p(pts_host.data_ptr()),
+                                            2 * P_cap))                                   # D2H of the manifolds that are final before the EPA tail
         gw.sync_counts()
         gw._ck(L.b2c_get_packed_contacts(gw.h, ctypes.c_void_p(hdr_host.data_ptr()), P_cap, ctypes.c_void_p(pts_host.data_ptr()),
                                          2 * P_cap, ctypes.byref(nH), ctypes.byref(nPt)))  # D2H contact stream (16-B headers, 48-B points)
@@ -456,7 +458,7 @@ def run_ours(args):
         "gpu_launches": int(launches_all),
         "e2e": {"value": (1000.0 / e2e_max) if strong else ngpu * 1000.0 / e2e_max, "unit": "steps/s", "ms_per_step": e2e_max,
                 "h2d_bytes_per_step": nb * 48, "d2h_bytes_per_step": int(d2h),
-                "what": "b2c_set_transforms(pinned host planes) + b2c_step_device + b2c_get_pairs (overlaps the narrowphase) + b2c_sync_counts + b2c_get_packed_contacts (16-B manifold headers + 48-B solver points: world points on A and B, normal, distance, lifetime, warm-start slot, triangle index), all into pinned host buffers"},
+                "what": "b2c_set_transforms(pinned host planes) + b2c_step_device + b2c_get_pairs (overlaps the narrowphase) + b2c_begin_contact_download (overlaps the penetration bin) + b2c_sync_counts + b2c_get_packed_contacts (16-B manifold headers + 48-B solver points: world points on A and B, normal, distance, lifetime, warm-start slot, triangle index), all into pinned host buffers"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": abytes[dom],

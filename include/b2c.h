@@ -225,6 +225,13 @@ int32_t b2c_get_packed_contacts(b2c_ctx*, b2c_packed_header* headers_out, int32_
  * b2c_get_solver_contacts, 2 = b2c_get_packed_contacts, -1 = off (default).  The compaction then rides in the step's CUDA
  * graph, its counts come back with b2c_sync_counts, and the getter of that format only issues the two exact-size copies. */
 int32_t b2c_set_contact_prefetch(b2c_ctx*, int32_t format);
+/* With prefetch format 2: start the download of the packed stream while the step is still running.  Everything outside the
+ * penetration bin (and the mesh bin) is final before the EPA kernels end, is compacted there, and this call — issued after
+ * b2c_step_device — waits for that point and starts copying that part into the caller's (pinned) buffers on the copy
+ * stream.  The following b2c_get_packed_contacts with the SAME buffers only adds what the end of the dispatch appended and
+ * waits for both copies.  Optional: without it the getter copies everything. */
+int32_t b2c_begin_contact_download(b2c_ctx*, b2c_packed_header* headers_out, int32_t cap_headers, b2c_packed_point* points_out,
+                                   int32_t cap_points);
 
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */

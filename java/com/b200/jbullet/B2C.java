@@ -58,6 +58,8 @@ final class B2C {
     static final MethodHandle getPackedContacts = h("b2c_get_packed_contacts",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle setContactPrefetch = h("b2c_set_contact_prefetch", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    static final MethodHandle beginContactDownload = h("b2c_begin_contact_download",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT));
     static final MethodHandle getManifolds = h("b2c_get_manifolds", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 
     // AxisSweep3(worldAabbMin, worldAabbMax): world box of the SAP broadphase modes

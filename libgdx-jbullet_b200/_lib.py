@@ -65,7 +65,7 @@ EXPORTS = [
     "b2c_set_profiling", "b2c_get_stage_times", "b2c_stage_name", "b2c_set_transforms_device", "b2c_set_partition", "b2c_mgpu_broadphase", "b2c_mgpu_export_departed",
     "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase", "b2c_mgpu_slot_bytes", "b2c_mgpu_export_departed_slot",
     "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest",
-    "b2c_shape_register_compound", "b2c_get_packed_contacts", "b2c_set_contact_prefetch",
+    "b2c_shape_register_compound", "b2c_get_packed_contacts", "b2c_set_contact_prefetch", "b2c_begin_contact_download",
 ]
 NUM_STAGES = 12
 CONTACT_HEADER_DTYPE = np.dtype([
@@ -158,6 +158,7 @@ def load():
     L.b2c_get_solver_contacts.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
     L.b2c_get_packed_contacts.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
     L.b2c_set_contact_prefetch.argtypes = [vp, i32]
+    L.b2c_begin_contact_download.argtypes = [vp, vp, i32, vp, i32]
     L.b2c_set_profiling.argtypes = [vp, i32]
     L.b2c_get_stage_times.argtypes = [vp, vp]
     L.b2c_stage_name.argtypes = [i32]

@@ -209,6 +209,12 @@ struct b2c_ctx {
     int contactReady = -1;             // format of the stream sitting in dContactHdr / dContactPts for the last dispatch, or -1
     uint32_t contactCounts[2] = {0, 0};
     bool contactCountsValid = false;   // contactCounts came back with the step counters of the dispatch that compacted
+    // two-phase packed stream (prefetch format 2): the manifolds that are final before the penetration bin ends are compacted
+    // early and can be downloaded while it runs (b2c_begin_contact_download)
+    cudaEvent_t evContactsEarly = nullptr;
+    bool earlyRecorded = false;        // the last dispatch recorded evContactsEarly
+    struct { bool active; void* hdr; void* pts; uint32_t nH, nP; } earlyDl = {false, nullptr, nullptr, 0, 0};
+    uint32_t* hEarlyCountsPinned = nullptr;
 };
 
 namespace {
@@ -500,22 +506,29 @@ CompoundArgs makeCompoundArgs(b2c_ctx* ctx) {
 }
 
 // Compaction of the touching manifolds into dContactHdr / dContactPts (format `mode`, see getContactsImpl)
-int32_t enqueueContactCompaction(b2c_ctx* ctx, int mode) {
+// phase 0: everything (counts cleared first); 1: early part of the pair manifolds (counts cleared first, then snapshot into
+// counts[2..3]); 2: the rest of the pair manifolds + the compound child manifolds, appended behind the early part
+int32_t enqueueContactCompaction(b2c_ctx* ctx, int mode, int phase = 0) {
     cudaStream_t s = ctx->stream;
     NpArgs a = makeNpArgs(ctx);
-    CK(cudaMemsetAsync(ctx->dContactCounts, 0, 2 * sizeof(uint32_t), s));
+    if (phase != 2) CK(cudaMemsetAsync(ctx->dContactCounts, 0, 4 * sizeof(uint32_t), s));
     auto launch = [&](const NpArgs& na, unsigned grid, const uint32_t* itemPair) {
         if (mode == 2)
             k_compact_contacts<2><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                       ctx->dContactCounts, itemPair);
+                                                       ctx->dContactCounts, itemPair, itemPair ? 0 : phase);
         else if (mode == 1)
             k_compact_contacts<1><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                       ctx->dContactCounts, itemPair);
+                                                       ctx->dContactCounts, itemPair, itemPair ? 0 : phase);
         else
             k_compact_contacts<0><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
-                                                       ctx->dContactCounts, itemPair);
+                                                       ctx->dContactCounts, itemPair, itemPair ? 0 : phase);
     };
     launch(a, gridFor((uint32_t)ctx->cfg.max_pairs, 256), nullptr);
+    if (phase == 1) {
+        CK(cudaMemcpyAsync(ctx->dContactCounts + 2, ctx->dContactCounts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        CK(cudaGetLastError());
+        return B2C_OK;
+    }
     if (ctx->hasCompound) {  // the child manifolds of compound pairs: the same compaction over the latest item arrays
         NpArgs a2 = a;
         a2.mhdr = ctx->dCH[ctx->ccur];
@@ -627,6 +640,17 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     k_manifold_cc<<<148 * ctx->mccBlocks, 256, 0, s>>>(a);
     if (ctx->timeline) cudaEventRecord(ctx->tl[4], s);
     ctx->launches += 2;
+    ctx->earlyRecorded = false;
+    if (ctx->contactPrefetch == 2) {
+        // every manifold outside the penetration bin and the mesh bin is final now: compact those and let the host start their
+        // download (b2c_begin_contact_download) while the penetration bin is still running on its stream
+        if (ctx->overlap) CK(cudaStreamWaitEvent(s, ctx->evJoin[0], 0));
+        int32_t rce = enqueueContactCompaction(ctx, 2, 1);
+        if (rce) return rce;
+        ctx->launches += 1;
+        CK(cudaEventRecordWithFlags(ctx->evContactsEarly, s, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+        ctx->earlyRecorded = true;
+    }
     if (ctx->overlap) {
         CK(cudaStreamWaitEvent(s, ctx->evJoin[1], 0));
         CK(cudaStreamWaitEvent(s, ctx->evJoin[0], 0));
@@ -646,7 +670,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     ctx->stageValid = ctx->prof;
     CK(cudaGetLastError());
     if (ctx->contactPrefetch >= 0) {  // the contact stream is compacted behind the dispatch: its getter only copies
-        int32_t rc = enqueueContactCompaction(ctx, ctx->contactPrefetch);
+        int32_t rc = enqueueContactCompaction(ctx, ctx->contactPrefetch, ctx->contactPrefetch == 2 ? 2 : 0);
         if (rc) return rc;
         ctx->launches += ctx->hasCompound ? 2 : 1;
     }
@@ -738,6 +762,8 @@ static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind);
 static int32_t enqueuePhases(b2c_ctx* ctx, int kind) {
     ctx->contactReady = -1;  // whatever sat in the contact buffers belongs to an older pair list / dispatch
     ctx->contactCountsValid = false;
+    ctx->earlyDl.active = false;
+    if (kind != 1) ctx->earlyRecorded = false;
     int32_t rc = enqueuePhasesImpl(ctx, kind);
     if (rc == B2C_OK && kind != 1) ctx->contactReady = ctx->contactPrefetch;
     return rc;
@@ -777,6 +803,7 @@ static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind) {
             ctx->nSortedBodies = ctx->nBodies;
         }
         if (narrow && ctx->hasCompound) ctx->ccur ^= 1;
+        if (narrow) ctx->earlyRecorded = ctx->contactPrefetch == 2;
         ctx->stageValid = false;
         ctx->launches += hit->launches;
         CK(cudaGraphLaunch(hit->exec, s));
@@ -990,7 +1017,9 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     ctx->capContactPts = (uint32_t)(2 * P);
     CKC(dalloc(&ctx->dContactHdr, (size_t)ctx->capContactHdr));
     CKC(dalloc(&ctx->dContactPts, (size_t)ctx->capContactPts));
-    CKC(dalloc(&ctx->dContactCounts, (size_t)2));
+    CKC(dalloc(&ctx->dContactCounts, (size_t)4));
+    CKC(cudaEventCreateWithFlags(&ctx->evContactsEarly, cudaEventDisableTiming));
+    CKC(cudaMallocHost((void**)&ctx->hEarlyCountsPinned, 2 * sizeof(uint32_t)));
 #undef CKC
     *out = ctx;
     return B2C_OK;
@@ -1035,6 +1064,8 @@ void b2c_destroy(b2c_ctx* ctx) {
     }
     if (ctx->streamCopy) { cudaStreamSynchronize(ctx->streamCopy); cudaStreamDestroy(ctx->streamCopy); }
     if (ctx->evPairsReady) cudaEventDestroy(ctx->evPairsReady);
+    if (ctx->evContactsEarly) cudaEventDestroy(ctx->evContactsEarly);
+    cudaFreeHost(ctx->hEarlyCountsPinned);
     if (ctx->streamClosed) cudaStreamDestroy(ctx->streamClosed);
     if (ctx->streamEpa) cudaStreamDestroy(ctx->streamEpa);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1810,9 +1841,21 @@ static int32_t getContactsImpl(b2c_ctx* ctx, int mode, void* hOut, int32_t capH,
     if (counts[0] > ctx->capContactHdr || counts[1] > ctx->capContactPts) { ctx->err = "contact stream capacity exceeded"; return B2C_ERR_CAPACITY; }
     if (!hOut && !pOut) return B2C_OK;
     if ((uint32_t)capH < counts[0] || (uint32_t)capP < counts[1]) { ctx->err = "contact output buffers too small"; return B2C_ERR_CAPACITY; }
-    if (hOut && counts[0]) CK(cudaMemcpyAsync(hOut, ctx->dContactHdr, (size_t)counts[0] * hdSize, cudaMemcpyDeviceToHost, s));
-    if (pOut && counts[1]) CK(cudaMemcpyAsync(pOut, ctx->dContactPts, (size_t)counts[1] * ptSize, cudaMemcpyDeviceToHost, s));
+    uint32_t h0 = 0, p0 = 0;
+    if (mode == 2 && ctx->earlyDl.active && ctx->earlyDl.hdr == hOut && ctx->earlyDl.pts == pOut && ctx->earlyDl.nH <= counts[0] &&
+        ctx->earlyDl.nP <= counts[1]) {
+        h0 = ctx->earlyDl.nH;  // the first part is already on its way (b2c_begin_contact_download): copy only what the
+        p0 = ctx->earlyDl.nP;  // end of the dispatch appended behind it
+    }
+    if (hOut && counts[0] > h0)
+        CK(cudaMemcpyAsync((char*)hOut + (size_t)h0 * hdSize, (const char*)ctx->dContactHdr + (size_t)h0 * hdSize,
+                           (size_t)(counts[0] - h0) * hdSize, cudaMemcpyDeviceToHost, s));
+    if (pOut && counts[1] > p0)
+        CK(cudaMemcpyAsync((char*)pOut + (size_t)p0 * ptSize, (const char*)ctx->dContactPts + (size_t)p0 * ptSize,
+                           (size_t)(counts[1] - p0) * ptSize, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (h0 || p0) CK(cudaStreamSynchronize(ctx->streamCopy));
+    ctx->earlyDl.active = false;
     return B2C_OK;
 }
 
@@ -1829,6 +1872,30 @@ int32_t b2c_get_solver_contacts(b2c_ctx* ctx, b2c_contact_header* hOut, int32_t 
 int32_t b2c_get_packed_contacts(b2c_ctx* ctx, b2c_packed_header* hOut, int32_t capH, b2c_packed_point* pOut, int32_t capP,
                                 int32_t* nH, int32_t* nP) {
     return getContactsImpl(ctx, 2, hOut, capH, pOut, capP, nH, nP);
+}
+
+int32_t b2c_begin_contact_download(b2c_ctx* ctx, b2c_packed_header* hOut, int32_t capH, b2c_packed_point* pOut, int32_t capP) {
+    if (!ctx || !hOut || !pOut || capH < 0 || capP < 0) return B2C_ERR_BAD_ARG;
+    if (ctx->contactPrefetch != 2 || !ctx->earlyRecorded) {
+        ctx->err = "b2c_begin_contact_download needs b2c_set_contact_prefetch(ctx, 2) and an enqueued dispatch";
+        return B2C_ERR_STATE;
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t cs = ctx->streamCopy;
+    CK(cudaStreamWaitEvent(cs, ctx->evContactsEarly, 0));
+    CK(cudaMemcpyAsync(ctx->hEarlyCountsPinned, ctx->dContactCounts + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    CK(cudaStreamSynchronize(cs));  // returns when k_manifold_cc has finished; the penetration bin may still be running
+    const uint32_t nH = ctx->hEarlyCountsPinned[0], nP = ctx->hEarlyCountsPinned[1];
+    if (nH > ctx->capContactHdr || nP > ctx->capContactPts) { ctx->err = "contact stream capacity exceeded"; return B2C_ERR_CAPACITY; }
+    if ((uint32_t)capH < nH || (uint32_t)capP < nP) { ctx->err = "contact output buffers too small"; return B2C_ERR_CAPACITY; }
+    if (nH) CK(cudaMemcpyAsync(hOut, ctx->dContactHdr, (size_t)nH * sizeof(b2c_packed_header), cudaMemcpyDeviceToHost, cs));
+    if (nP) CK(cudaMemcpyAsync(pOut, ctx->dContactPts, (size_t)nP * sizeof(b2c_packed_point), cudaMemcpyDeviceToHost, cs));
+    ctx->earlyDl.active = true;
+    ctx->earlyDl.hdr = hOut;
+    ctx->earlyDl.pts = pOut;
+    ctx->earlyDl.nH = nH;
+    ctx->earlyDl.nP = nP;
+    return B2C_OK;
 }
 
 int32_t b2c_set_contact_prefetch(b2c_ctx* ctx, int32_t format) {

@@ -1517,7 +1517,10 @@ __global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restrict__ ptsOut, uint32_t capH,
-                   uint32_t capP, uint32_t* __restrict__ counts /*[2]: headers, points*/, const uint32_t* __restrict__ itemPair) {
+                   uint32_t capP, uint32_t* __restrict__ counts /*[2]: headers, points*/, const uint32_t* __restrict__ itemPair, int phase) {
+    // phase 0: every touching manifold.  phase 1 / 2 split the pair manifolds in two so that the download of the first part can
+    // start while the penetration bin is still running: 1 = manifolds that are final once k_manifold_cc and the closed-form bins
+    // are done (everything but 2), 2 = pairs waiting in the penetration bin (rawFlag -2) and mesh pairs (folded at the very end).
     constexpr bool SLIM = MODE == 1;
     b2c_manifold_point* __restrict__ pts = reinterpret_cast<b2c_manifold_point*>(ptsOut);
     const uint32_t n = *a.numPairs;
@@ -1526,6 +1529,11 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restr
         uint32_t p = base + lane;
         int nc = 0;
         if (p < n && a.mhdr[p].algorithm != 0) nc = a.mhdr[p].num_contacts;
+        if (phase != 0 && nc > 0) {
+            const int bin = a.binOf[p];
+            const bool late = bin == BIN_MESH || (bin >= BIN_GJK0 && bin < BIN_COUNT && a.rawFlag[p] == -2);
+            if (late != (phase == 2)) nc = 0;
+        }
         uint32_t m = __ballot_sync(0xffffffffu, nc > 0);
         if (m == 0) continue;
         // warp totals: headers = popc(m), points = sum nc (inclusive scan by shuffles)

@@ -148,11 +148,11 @@ def test_contact_stream_matches_manifolds(gpu_pkg):
     assert np.array_equal(pts[first]["world_b"], m["points"][k, 0]["world_b"])
 
 
-def _check_packed_stream(gw):
+def _check_packed_stream(gw, stream=None):
     """b2c_get_packed_contacts carries exactly the touching manifolds: every field bit-identical to b2c_get_manifolds."""
     m = gw.manifolds(only_touching=True)
     pairs = gw.pairs()
-    hdr, pts = gw.packed_contacts()
+    hdr, pts = gw.packed_contacts() if stream is None else stream
     assert len(hdr) == len(m) and len(pts) == int(m["num_contacts"].sum())
     nc = hdr["info"] & 0xff
     alg = (hdr["info"] >> 8) & 0xff
@@ -206,8 +206,26 @@ def test_packed_contact_stream(gpu_pkg):
         h1, p1 = gw.solver_contacts()
         h2, p2 = gw.packed_contacts()
         assert len(h1) == len(h2) and len(p1) == len(p2)
+    # the two-part download: the manifolds that are final before the penetration bin ends start travelling early
+    import ctypes as C
+    _lib = gpu_pkg._lib
+    hbuf = np.zeros(1 << 16, dtype=_lib.PACKED_HEADER_DTYPE)
+    pbuf = np.zeros(1 << 17, dtype=_lib.PACKED_POINT_DTYPE)
+    for step in range(7, 10):
+        gw.setWorldTransforms(sc.transforms(step))
+        gw.step_device()
+        gw._ck(gw.L.b2c_begin_contact_download(gw.h, hbuf.ctypes.data_as(C.c_void_p), len(hbuf), pbuf.ctypes.data_as(C.c_void_p), len(pbuf)))
+        gw.sync_counts()
+        nh, npt = C.c_int32(), C.c_int32()
+        gw._ck(gw.L.b2c_get_packed_contacts(gw.h, hbuf.ctypes.data_as(C.c_void_p), len(hbuf), pbuf.ctypes.data_as(C.c_void_p), len(pbuf),
+                                            C.byref(nh), C.byref(npt)))
+        assert _check_packed_stream(gw, (hbuf[: nh.value].copy(), pbuf[: npt.value].copy())) > 100
     gw.set_contact_prefetch(-1)
-    gw.step(np.ascontiguousarray(sc.transforms(7).T))
+    with pytest.raises(gpu_pkg.B2CError):
+        gw.step_device()
+        gw._ck(gw.L.b2c_begin_contact_download(gw.h, hbuf.ctypes.data_as(C.c_void_p), len(hbuf), pbuf.ctypes.data_as(C.c_void_p), len(pbuf)))
+    gw.sync_counts()
+    gw.step(np.ascontiguousarray(sc.transforms(10).T))
     assert _check_packed_stream(gw) > 100
 
 
