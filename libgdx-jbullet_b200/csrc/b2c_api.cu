@@ -441,7 +441,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     k_carry<<<gridFor((uint32_t)ctx->cfg.max_pairs, 256), 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
                                                                       ctx->dSortedKeys[cur ^ 1], ctx->dNumPairs[cur ^ 1],
                                                                       ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
-                                                                      ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr, ctx->dHist);
+                                                                      ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr, ctx->dHist, ctx->dPairFirst[cur]);
     ctx->launches += 10 + ctx->sortBodies.launches;
     ctx->nSortedBodies = n;  // dSmin.w = proxy index of every sorted position: the ray tests reuse the order
     CK(cudaGetLastError());

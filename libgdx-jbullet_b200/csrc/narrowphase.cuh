@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256)
 k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs, const uint64_t* __restrict__ prevKeys,
         const uint32_t* __restrict__ prevNum, const uint32_t* __restrict__ prevFirst, const ManifoldHdr* __restrict__ prevH,
         const b2c_manifold_point* __restrict__ prevP, ManifoldHdr* __restrict__ H, b2c_manifold_point* __restrict__ P, int uidBits,
-        StepCounters* ctr, uint8_t* __restrict__ hist) {
+        StepCounters* ctr, uint8_t* __restrict__ hist, const uint32_t* __restrict__ curFirst) {
     const uint32_t n = *numPairs, pn = *prevNum;
     const int lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
@@ -368,11 +368,18 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
             uint64_t k = keys[p];
             uint32_t uid0 = (uint32_t)(k >> uidBits);
             uint32_t a = pn ? prevFirst[uid0] : 0, b = pn ? prevFirst[uid0 + 1] : 0;
-            while (a < b) {
-                uint32_t mid = (a + b) >> 1;
-                if (prevKeys[mid] < k) a = mid + 1; else b = mid;
+            // most rows are unchanged from one step to the next: the pair usually sits at the same rank in last step's row,
+            // so one probe replaces the dependent loads of the binary search (which stays as the fallback)
+            const uint32_t guess = a + (p - curFirst[uid0]);
+            if (guess < b && prevKeys[guess] == k) {
+                found = (int)guess;
+            } else {
+                while (a < b) {
+                    uint32_t mid = (a + b) >> 1;
+                    if (prevKeys[mid] < k) a = mid + 1; else b = mid;
+                }
+                if (a < pn && prevKeys[a] == k) found = (int)a;
             }
-            if (a < pn && prevKeys[a] == k) found = (int)a;
             int4 h0, h1;
             if (found >= 0) {
                 const int4* src = reinterpret_cast<const int4*>(prevH + found);
