@@ -1133,7 +1133,10 @@ __device__ __forceinline__ void manifoldCcOne(const NpArgs& a, uint32_t p, bool 
 // k_manifold_cc: every pair of the GJK bins whose detector finished in k_gjk / k_gjk_prefilter.  Pairs waiting in the
 // penetration bin (rawFlag == -2, set by k_gjk and never touched by k_epa) are left to the manifold loop of k_epa<1>, so this kernel
 // can run concurrently with the EPA kernels on another stream.
-__global__ void __launch_bounds__(256) k_manifold_cc(NpArgs a) {
+#ifndef MCC_MINB
+#define MCC_MINB 4
+#endif
+__global__ void __launch_bounds__(256, MCC_MINB) k_manifold_cc(NpArgs a) {
     const uint32_t s0 = a.binStart[BIN_GJK0], e0 = a.binStart[BIN_COUNT];
     uint32_t added = 0, created = 0;
     for (uint32_t it = s0 + blockIdx.x * blockDim.x + threadIdx.x; it < e0; it += gridDim.x * blockDim.x) {
