@@ -74,6 +74,15 @@ public:
         }
         return manifolds.at((size_t)i);
     }
+    // The touching manifolds as the packed contact stream (16-byte headers, 48-byte points): what a solver-side host reads
+    // every step instead of walking getManifoldByIndexInternal.  uid0 / uid1 of a record = pairs[header.pair_index].
+    void getPackedContacts(std::vector<b2c_packed_header>& headers, std::vector<b2c_packed_point>& points) {
+        int32_t nh = 0, np = 0;
+        check(b2c_get_packed_contacts(ctx, nullptr, 0, nullptr, 0, &nh, &np), ctx);
+        headers.resize((size_t)nh);
+        points.resize((size_t)np);
+        if (nh) check(b2c_get_packed_contacts(ctx, headers.data(), nh, points.data(), np, &nh, &np), ctx);
+    }
     int32_t numManifolds = 0, numContactsAdded = 0;
 private:
     b2c_ctx* ctx;
@@ -150,6 +159,11 @@ public:
         updateAabbs();
         broadphase->calculateOverlappingPairs(dispatcher);
         dispatcher->dispatchAllCollisionPairs(broadphase->getOverlappingPairCache(), nullptr, dispatcher);
+    }
+    // CollisionWorld.rayTest + ClosestRayResultCallback for n rays (disp/CollisionWorld.java:553-590, 697-729)
+    void rayTestClosest(int32_t n, const float* fromXyz, const float* toXyz, int32_t* uidOut, float* fractionOut, float* normalOut,
+                        float* pointOut, int16_t group = 1, int16_t mask = -1) {
+        check(b2c_ray_test_closest(ctx, n, fromXyz, toXyz, group, mask, uidOut, fractionOut, normalOut, pointOut), ctx);
     }
     // SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110)
     int32_t computeIslands(std::vector<int32_t>& tags) {

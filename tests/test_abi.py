@@ -32,8 +32,32 @@ def test_struct_sizes_match_header(pkg):
     assert pkg.MANIFOLD_DTYPE["points"].base.itemsize == 96
     assert pkg.RAW_DTYPE.itemsize == 56
     assert pkg._lib.CONTACT_HEADER_DTYPE.itemsize == 32
+    assert pkg._lib.PACKED_HEADER_DTYPE.itemsize == 16 and pkg._lib.PACKED_POINT_DTYPE.itemsize == 48
     assert C.sizeof(pkg._lib.Config) == 64
     assert C.sizeof(pkg._lib.Stats) == 64
+
+
+def test_header_compiles_as_plain_c_with_the_documented_sizes(tmp_path):
+    """include/b2c.h is the FFI contract: it must be valid C (no C++-isms) and every record must have the size its comment
+    states — the Java StructLayouts and the numpy dtypes are written against those numbers."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    src.write_text("""
+#include "b2c.h"
+_Static_assert(sizeof(b2c_config) == 64, "b2c_config");
+_Static_assert(sizeof(b2c_manifold_point) == 96, "b2c_manifold_point");
+_Static_assert(sizeof(b2c_manifold) == 416, "b2c_manifold");
+_Static_assert(sizeof(b2c_contact_header) == 32, "b2c_contact_header");
+_Static_assert(sizeof(b2c_solver_point) == 64, "b2c_solver_point");
+_Static_assert(sizeof(b2c_packed_header) == 16, "b2c_packed_header");
+_Static_assert(sizeof(b2c_packed_point) == 48, "b2c_packed_point");
+_Static_assert(sizeof(b2c_raw_contact) == 56, "b2c_raw_contact");
+_Static_assert(sizeof(b2c_stats) == 64, "b2c_stats");
+int main(void) { return 0; }
+""")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)])
 
 
 def test_default_config_matches_reference_constants(pkg):
