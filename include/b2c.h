@@ -185,8 +185,9 @@ typedef struct {
     int32_t pair_uid0, pair_uid1, body0, body1;
     int32_t num_contacts, algorithm;
     int32_t first_point;              /* index of this manifold's first point in the point array */
-    int32_t pair_index;               /* index of the pair in the sorted pair list (child manifolds of compound pairs: index
-                                         of the child work item instead; match those by the uids) */
+    int32_t pair_index;               /* >= 0: index of the pair in the sorted pair list.  < 0: child manifold of a compound pair;
+                                         v = -1 - pair_index, child0 = (v & 0x7fff) - 1, child1 = (v >> 15) - 1 (the child's index in
+                                         body0's / body1's CompoundShape, -1 = that object is not a compound) */
 } b2c_contact_header; /* 32 bytes */
 int32_t b2c_get_contacts(b2c_ctx*, b2c_contact_header* headers_out, int32_t cap_headers, b2c_manifold_point* points_out,
                          int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);

@@ -14,7 +14,8 @@ import static java.lang.foreign.ValueLayout.*;
 /**
  * Drop-in for {@code CollisionDispatcher} behind {@link Dispatcher} (bp/Dispatcher.java:38-68).
  * NOT COMPILED IN THIS REPOSITORY'S IMAGE.  dispatchAllCollisionPairs runs the whole narrowphase on the device
- * (b2c_dispatch_all_pairs) and pulls back only the touching manifolds (b2c_get_contacts); the Java
+ * (b2c_dispatch_all_pairs) and pulls back only the touching manifolds (b2c_get_contacts; a solver-only host would take
+ * b2c_get_packed_contacts: 16-byte headers, 48-byte points); the Java
  * PersistentManifold / ManifoldPoint objects the island manager and the solver read are refreshed from that
  * stream.  {@code src_slot} says which slot of the same manifold a point continues, so the solver's warm-start
  * fields (appliedImpulse, appliedImpulseLateral1/2, lateralFrictionInitialized, userPersistentData) stay attached
@@ -53,7 +54,12 @@ public class GpuDispatcher extends Dispatcher {
             int uid0 = headers.get(JAVA_INT, o), uid1 = headers.get(JAVA_INT, o + 4);
             int body0 = headers.get(JAVA_INT, o + 8), body1 = headers.get(JAVA_INT, o + 12);
             int n = headers.get(JAVA_INT, o + 16), first = headers.get(JAVA_INT, o + 24);
-            long key = ((long) uid0 << 32) | (uid1 & 0xffffffffL);
+            // pair_index < 0: child manifold of a compound pair (disp/CompoundCollisionAlgorithm.java:49-75 keeps one child
+            // algorithm, hence one manifold, per child): v = -1 - pair_index carries (child0 + 1) | (child1 + 1) << 15
+            int pairIndex = headers.get(JAVA_INT, o + 28);
+            long child = pairIndex < 0 ? (-1L - pairIndex) : 0L;          // 30 bits, 0 for every plain pair
+            long key = (((long) uid0 << 21) | (uid1 & 0x1fffffL)) << 22 ^ child;   // uids < 2^21 (b2c_create), 22 spare bits + xor of the child code
+            key = key * 0x9E3779B97F4A7C15L + child;                    // (uid0, uid1, child0, child1) -> map key
             PersistentManifold m = byPair.get(key);
             ManifoldPoint[] old = null;
             if (m == null) {

@@ -1575,7 +1575,9 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restr
                 } else {
                     b2c_contact_header hh;
                     hh.pair_uid0 = mf->pair_uid0; hh.pair_uid1 = mf->pair_uid1; hh.body0 = mf->body0; hh.body1 = mf->body1;
-                    hh.num_contacts = nc; hh.algorithm = mf->algorithm; hh.first_point = (int)fp; hh.pair_index = (int)p;
+                    hh.num_contacts = nc; hh.algorithm = mf->algorithm; hh.first_point = (int)fp;
+                    // child manifold of a compound pair: which child algorithm it is, as a negative pair_index
+                    hh.pair_index = itemPair ? -1 - (((mf->pad0 + 1) & 0x7fff) | (((mf->pad1 + 1) & 0x7fff) << 15)) : (int)p;
                     hdr[h] = hh;
                 }
                 for (int k = 0; k < nc; k++) {

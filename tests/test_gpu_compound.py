@@ -65,6 +65,13 @@ def test_compound_contact_stream_and_fused_step(gpu_pkg):
         assert len(hdr) == len(m) and hdr["num_contacts"].sum() == len(pts) == m["num_contacts"].sum()
         key = lambda a: sorted(zip(a["pair_uid0"].tolist(), a["pair_uid1"].tolist(), a["body0"].tolist(), a["num_contacts"].tolist()))
         assert key(hdr) == key(m)
+        # child manifolds carry their child indices in a negative pair_index
+        v = -1 - hdr["pair_index"]
+        c0 = np.where(hdr["pair_index"] < 0, (v & 0x7fff) - 1, -1)
+        c1 = np.where(hdr["pair_index"] < 0, (v >> 15) - 1, -1)
+        full = lambda u0, u1, a, b: sorted(zip(u0.tolist(), u1.tolist(), a.tolist(), b.tolist()))
+        assert full(hdr["pair_uid0"], hdr["pair_uid1"], c0, c1) == full(m["pair_uid0"], m["pair_uid1"], m["child0"], m["child1"])
+        assert (hdr["pair_index"] < 0).sum() == (m["child0"] >= 0).sum() > 0
         # points of one child manifold: world_a / distance identical to the manifold record
         k = int(np.nonzero(m["child0"] >= 0)[0][0])
         cand = np.nonzero((hdr["pair_uid0"] == m["pair_uid0"][k]) & (hdr["pair_uid1"] == m["pair_uid1"][k]))[0]
