@@ -28,7 +28,9 @@ public class GpuDispatcher extends Dispatcher {
     final MemorySegment points;    // b2c_manifold_point[2*maxPairs] (96 B)
     final MemorySegment out = arena.allocate(JAVA_INT, 4);
     final ObjectArrayList<PersistentManifold> manifolds = new ObjectArrayList<PersistentManifold>();
-    final java.util.HashMap<Long, PersistentManifold> byPair = new java.util.HashMap<Long, PersistentManifold>();
+    /** (pair, child code): a plain pair owns one manifold, a compound pair one per child algorithm. */
+    record ManifoldKey(int uid0, int uid1, int childCode) { }
+    final java.util.HashMap<ManifoldKey, PersistentManifold> byPair = new java.util.HashMap<ManifoldKey, PersistentManifold>();
     final GpuBroadphase broadphase;
 
     public GpuDispatcher(MemorySegment ctx, GpuBroadphase bp, int maxPairs) {
@@ -48,7 +50,7 @@ public class GpuDispatcher extends Dispatcher {
         } catch (Throwable t) { throw new RuntimeException(t); }
         int nh = out.get(JAVA_INT, 8);
         manifolds.clear();
-        java.util.HashMap<Long, PersistentManifold> next = new java.util.HashMap<Long, PersistentManifold>();
+        java.util.HashMap<ManifoldKey, PersistentManifold> next = new java.util.HashMap<ManifoldKey, PersistentManifold>();
         for (int h = 0; h < nh; h++) {
             long o = 32L * h;
             int uid0 = headers.get(JAVA_INT, o), uid1 = headers.get(JAVA_INT, o + 4);
@@ -57,9 +59,7 @@ public class GpuDispatcher extends Dispatcher {
             // pair_index < 0: child manifold of a compound pair (disp/CompoundCollisionAlgorithm.java:49-75 keeps one child
             // algorithm, hence one manifold, per child): v = -1 - pair_index carries (child0 + 1) | (child1 + 1) << 15
             int pairIndex = headers.get(JAVA_INT, o + 28);
-            long child = pairIndex < 0 ? (-1L - pairIndex) : 0L;          // 30 bits, 0 for every plain pair
-            long key = (((long) uid0 << 21) | (uid1 & 0x1fffffL)) << 22 ^ child;   // uids < 2^21 (b2c_create), 22 spare bits + xor of the child code
-            key = key * 0x9E3779B97F4A7C15L + child;                    // (uid0, uid1, child0, child1) -> map key
+            ManifoldKey key = new ManifoldKey(uid0, uid1, pairIndex < 0 ? -1 - pairIndex : 0);   // 0 for every plain pair
             PersistentManifold m = byPair.get(key);
             ManifoldPoint[] old = null;
             if (m == null) {
