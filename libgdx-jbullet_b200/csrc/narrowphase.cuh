@@ -18,7 +18,17 @@
 #include "common.cuh"
 #include "epa.cuh"
 #include "gjk.cuh"
+#ifndef B2C_HOST_EMULATION
 #include "radix_sort.cuh"
+#else
+// tests/emu compiles this header for the HOST (one emulated lane, test infrastructure only): the look-back primitives of the
+// sorter become plain loads and stores there, and its launch code is not needed
+namespace b2c {
+constexpr uint32_t RS_FLAG_AGG = 0x40000000u, RS_FLAG_INC = 0x80000000u, RS_VAL_MASK = 0x3fffffffu;
+inline void rs_store_release(uint32_t* p, uint32_t v) { *p = v; }
+inline uint32_t rs_load_relaxed(const uint32_t* p) { return *p; }
+}
+#endif
 
 namespace b2c {
 
