@@ -23,6 +23,8 @@ CASES = {
     "c4_worlds_dbvt": (lambda: scenes.worlds_scene(num_worlds=4, seed=5), orc.DBVT, 3),
     # CompoundShape pairs (child manifolds carry child indices in mf_hdr columns 5, 6)
     "c6_compound_dbvt": (lambda: scenes.compound_scene(n=120, seed=8), orc.DBVT, 4),
+    # compounds on a triangle mesh: ConvexConcave per child, raw keys -2 - (child << 21 | triangle)
+    "c7_terrain_compound_dbvt": (lambda: scenes.terrain_compound_scene(cells=24, n=60, seed=15), orc.DBVT, 3),
 }
 
 
