@@ -72,3 +72,26 @@ def test_deltas_compose_to_the_pair_set():
         a, r = ow.pair_deltas()
         cur = (cur - set(map(tuple, r.tolist()))) | set(map(tuple, a.tolist()))
         assert cur == set(map(tuple, pairs.tolist()))
+
+
+def test_island_partition_equals_scipy_connected_components():
+    """Independent check: the island partition over the pairs of non-static bodies is the connected-component partition of
+    that graph (scipy), on a scene with thousands of pairs."""
+    import scenes
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    sc = scenes.bin_scene(n=1500, seed=33, spacing=1.05)
+    ow = scenes.build_oracle(sc, orc.DBVT)
+    pairs = ow.step(sc.transforms(0))
+    tags, n_islands = ow.islands()
+    static = np.asarray(sc.static, dtype=bool)
+    dyn = ~static
+    u, v = pairs[:, 0] - 1, pairs[:, 1] - 1
+    keep = dyn[u] & dyn[v]
+    g = coo_matrix((np.ones(keep.sum()), (u[keep], v[keep])), shape=(sc.n, sc.n))
+    ncomp, lab = connected_components(g, directed=False)
+    assert (tags[static] == -1).all() and (tags[dyn] >= 0).all()
+    # same partition: the map tag -> scipy label is a bijection on the dynamic bodies
+    pairs_tl = set(zip(tags[dyn].tolist(), lab[dyn].tolist()))
+    assert len(pairs_tl) == len(set(tags[dyn].tolist())) == len(set(lab[dyn].tolist()))
+    assert n_islands == len(set(tags[dyn].tolist()))
