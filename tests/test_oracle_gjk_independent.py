@@ -98,3 +98,46 @@ def test_gjk_and_epa_depth_match_the_support_function_distance():
         along = -(_support(*A, -n[None])[0] + _support(*B, n[None])[0])
         assert along > sep - 5e-3, (trial, along, sep)
     assert checked_sep >= 5 and checked_pen >= 5 and quirks <= 6, (checked_sep, checked_pen, quirks)
+
+
+def test_convex_plane_distance_matches_the_support_function():
+    """disp/ConvexPlaneCollisionAlgorithm.java:75-136: the reported distance is the signed distance of the deepest point of the
+    shape (support mapping WITH margin along -normal: sharp full-size box, rounded hull, sphere) to the plane."""
+    global SHARP_BOX
+    rng = np.random.default_rng(7)
+    hp = scenes.hull_points(rng, 0.5)
+    checked = 0
+    for trial in range(40):
+        w = orc.OracleWorld(orc.TIGHT)
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        n32 = n.astype(np.float32)
+        cst = float(np.float32(rng.uniform(-1, 1)))
+        plane = w.plane([float(v) for v in n32], cst)
+        k = trial % 3
+        if k == 0:
+            he = rng.uniform(0.3, 0.6, size=3).astype(np.float32)
+            shp = ("box", he, w.box(*[float(v) for v in he]), 0.04)
+        elif k == 1:
+            r = float(np.float32(rng.uniform(0.3, 0.6)))
+            shp = ("sphere", r, w.sphere(r), r)
+        else:
+            pts = (hp * rng.uniform(0.7, 1.2)).astype(np.float32)
+            shp = ("hull", pts, w.hull(pts), 0.04)
+        rot = scenes.random_rotations(rng, 1)
+        nn = n32.astype(np.float64) / np.linalg.norm(n32.astype(np.float64))   # StaticPlaneShape normalises its normal
+        pos = nn * (cst + rng.uniform(0.2, 0.7)) + rng.normal(size=3) * 0.01
+        xf = scenes.make_xf(rot, pos[None])[0]
+        w.body(plane, orc.xf12(origin=(0, 0, 0)), group=2, mask=-1 ^ 2, static=True)
+        w.body(shp[2], xf)
+        w.step()
+        ri, rf = w.raw()
+        assert len(ri) == 1 and ri[0, 4] == 11
+        SHARP_BOX = True
+        A = (shp[0], shp[1], xf[:9].reshape(3, 3).astype(np.float64), xf[9:].astype(np.float64), shp[3])
+        expected = -_support(*A, -nn[None])[0] - cst
+        assert abs(rf[0, 6] - expected) < 1e-5, (trial, rf[0, 6], expected)
+        assert bool(ri[0, 3]) == (rf[0, 6] < 0.02)
+        checked += 1
+    SHARP_BOX = False
+    assert checked == 40
