@@ -103,7 +103,7 @@ static void app(std::vector<float>& a, const std::vector<float>& b) { a.insert(a
 
 int main(int argc, char** argv) {
     const int N = argc > 1 ? atoi(argv[1]) : 150;
-    const int STEPS = 8; const float SP = argc > 2 ? atof(argv[2]) : 1.0f;
+    const int STEPS = 8; const float SP = argc > 2 ? atof(argv[2]) : 1.0f; const float YOFF = argc > 4 ? atof(argv[4]) : 0.f;
     Sc sc;
     sc.W.mode = orc::BP_DBVT;
     const bool useMesh = argc > 3;
@@ -157,7 +157,7 @@ int main(int argc, char** argv) {
         float xf[12];
         randRot(xf);
         xf[9] = (i % m) * SP + uf(-0.12f, 0.12f);
-        xf[10] = (i / (m * m)) * SP * 0.8f + (useMesh ? 0.45f : 0.5f) + uf(-0.12f, 0.12f);
+        xf[10] = (i / (m * m)) * SP * 0.8f + (useMesh ? 0.45f : 0.5f) + YOFF + uf(-0.12f, 0.12f);
         xf[11] = ((i / m) % m) * SP + uf(-0.12f, 0.12f);
         int shape = (uf(0, 1) < 0.5f) ? comps[rng() % comps.size()] : plain[rng() % plain.size()];
         addBody(shape, xf, false);
@@ -180,7 +180,7 @@ int main(int argc, char** argv) {
     std::map<std::pair<int, int>, ManifoldHdr> prevHdr;
     StepCounters ctr{};
     CompoundCounters cc{};
-    long totalItems = 0, totalTouch = 0, totalRetry = 0, totalDeep = 0, keepItems = 0;
+    long totalItems = 0, totalTouch = 0, totalRetry = 0, totalDeep = 0, keepItems = 0, bigUsed = 0;
     for (int step = 0; step < STEPS; step++) {
         // transforms + activity
         for (int b = 0; b < NB; b++) {
@@ -244,7 +244,13 @@ int main(int argc, char** argv) {
         threadIdx.x = 0;
         blockDim = {1, 1, 1};
         k_compound_manifold(a, c);
-        if (useMesh) { g.comp = c; k_compound_mesh(a, g); }
+        if (useMesh) {
+            memset((void*)big.data(), 0xAB, sizeof(EpaScratch));
+            g.comp = c;
+            k_compound_mesh(a, g);
+            const unsigned char* bytes = reinterpret_cast<const unsigned char*>(big.data());
+            for (size_t q = 0; q < sizeof(EpaScratch); q++) if (bytes[q] != 0xAB) { bigUsed++; break; }
+        }
         ccur ^= 1;
         prevHdr.clear();
         for (uint32_t p = 0; p < P; p++) prevHdr[sc.W.pairs[p]] = mhdr[p];
@@ -329,6 +335,7 @@ int main(int argc, char** argv) {
         printf("step %d ok: pairs %u compound items %u retry %u deep %u kid manifolds %ld contactsAdded %u\n", step, P, cc.numItems, ctr.epaRetry, ctr.deepChecks,
                oracleKidManifolds, ctr.contactsAdded);
     }
-    printf("ALL OK items %ld touching points %ld retries %ld deep %ld keepItems %ld\n", totalItems, totalTouch, totalRetry, totalDeep, keepItems);
+    printf("ALL OK items %ld touching points %ld retries %ld deep %ld keepItems %ld steps-with-large-pool-in-mesh-kernel %ld\n", totalItems, totalTouch, totalRetry, totalDeep,
+           keepItems, bigUsed);
     return 0;
 }

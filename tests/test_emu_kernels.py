@@ -23,7 +23,7 @@ def binaries(tmp_path_factory):
     return bins
 
 
-@pytest.mark.parametrize("args", [("150", "1.0"), ("200", "0.45"), ("120", "0.8", "mesh")])
+@pytest.mark.parametrize("args", [("150", "1.0"), ("200", "0.45"), ("120", "0.8", "mesh"), ("150", "0.7", "mesh", "-0.5")])
 def test_compound_kernels_match_the_oracle_on_the_host(binaries, args):
     """k_compound_expand / k_compound_gjk / k_epa<2>,<1> / k_compound_manifold / k_compound_mesh over 8 steps with bodies going
     to sleep and waking up: child manifold headers, points, raw records and counters, bit for bit."""
