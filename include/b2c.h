@@ -52,7 +52,7 @@ typedef enum { B2C_SHAPE_BOX = 0, B2C_SHAPE_SPHERE = 1, B2C_SHAPE_HULL = 2, B2C_
 typedef struct {
     int32_t device;                    /* CUDA device ordinal */
     int32_t broadphase_mode;           /* b2c_broadphase_mode */
-    int32_t max_bodies;                /* proxy capacity (uids 1..max_bodies) */
+    int32_t max_bodies;                /* LIVE proxy capacity (uids 1..max_bodies; see b2c_proxy_destroy for slot reuse) */
     int32_t max_pairs;                 /* overlapping-pair capacity */
     int32_t max_shapes;                /* shape table capacity */
     int32_t max_hull_points;           /* total hull vertices over all hull shapes */
@@ -115,7 +115,11 @@ int32_t b2c_proxy_create(b2c_ctx*, int32_t shape, const float transform12[12], i
  * uids are assigned consecutively; the first one is returned. */
 int32_t b2c_proxy_create_batch(b2c_ctx*, int32_t n, const int32_t* shapes, const float* planes12, const int16_t* groups,
                                const int16_t* masks, const int32_t* flags, const int32_t* worlds, int32_t* first_uid_out);
-/* destroyProxy (bp/BroadphaseInterface.java:37): pairs containing it disappear at the next calculate */
+/* destroyProxy (bp/BroadphaseInterface.java:37): pairs containing it disappear at the next calculate.  uids are handed out
+ * increasingly (DbvtBroadphase's ++gid) until max_bodies have been created; from then on b2c_proxy_create reuses the slot and
+ * uid of a proxy destroyed BEFORE the last pair calculation, lowest first (as AxisSweep3 reuses handles,
+ * bp/AxisSweep3Internal.java:380-395), so max_bodies bounds the live proxies, not the creations.  b2c_proxy_create_batch
+ * only appends. */
 int32_t b2c_proxy_destroy(b2c_ctx*, int32_t uid);
 /* CollisionObject friction / restitution (disp/CollisionObject.java:95,71) used by ManifoldResult */
 int32_t b2c_proxy_set_material(b2c_ctx*, int32_t uid, float friction, float restitution);
@@ -222,17 +226,28 @@ typedef struct {
 int32_t b2c_get_packed_contacts(b2c_ctx*, b2c_packed_header* headers_out, int32_t cap_headers, b2c_packed_point* points_out,
                                 int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
 
+/* The packed stream keyed by uids instead of pair indices, for hosts that follow the pair cache through its add / remove
+ * events (b2c_get_pair_deltas) and never download the pair list: same 48-byte points; the points of consecutive headers are
+ * consecutive, so a manifold's first point is the running sum of num_contacts over the headers before it. */
+typedef struct {
+    int32_t pair_uid0, pair_uid1;     /* the broadphase pair (uid0 < uid1) */
+    int32_t info;                     /* num_contacts | algorithm << 8 | swapped << 16 (swapped: manifold body0 is pair_uid1) */
+    int32_t children;                 /* compound child manifold: (uint16)child0 | child1 << 16; else -1 */
+} b2c_packed_uid_header; /* 16 bytes */
+int32_t b2c_get_packed_contacts_uid(b2c_ctx*, b2c_packed_uid_header* headers_out, int32_t cap_headers, b2c_packed_point* points_out,
+                                    int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);
+
 /* Compact the contact stream behind every dispatch instead of inside its getter: format 0 = b2c_get_contacts, 1 =
- * b2c_get_solver_contacts, 2 = b2c_get_packed_contacts, -1 = off (default).  The compaction then rides in the step's CUDA
+ * b2c_get_solver_contacts, 2 = b2c_get_packed_contacts, 3 = b2c_get_packed_contacts_uid, -1 = off (default).  The compaction then rides in the step's CUDA
  * graph, its counts come back with b2c_sync_counts, and the getter of that format only issues the two exact-size copies. */
 int32_t b2c_set_contact_prefetch(b2c_ctx*, int32_t format);
-/* With prefetch format 2: start the download of the packed stream while the step is still running.  Everything outside the
+/* With prefetch format 2 or 3: start the download of the packed stream while the step is still running.  Everything outside the
  * penetration bin (and the mesh bin) is final before the EPA kernels end, is compacted there, and this call — issued after
  * b2c_step_device — waits for that point and starts copying that part into the caller's (pinned) buffers on the copy
  * stream.  The following b2c_get_packed_contacts with the SAME buffers only adds what the end of the dispatch appended and
  * waits for both copies.  Optional: without it the getter copies everything. */
-int32_t b2c_begin_contact_download(b2c_ctx*, b2c_packed_header* headers_out, int32_t cap_headers, b2c_packed_point* points_out,
-                                   int32_t cap_points);
+int32_t b2c_begin_contact_download(b2c_ctx*, void* headers_out /* b2c_packed_header* or b2c_packed_uid_header* */, int32_t cap_headers,
+                                   b2c_packed_point* points_out, int32_t cap_points);
 
 /* Raw detector output per processed pair (or per (pair, triangle)), before ManifoldResult: what
  * DiscreteCollisionDetectorInterface.Result.addContactPoint received. */
@@ -294,6 +309,9 @@ int32_t b2c_sync_counts(b2c_ctx*, int32_t* num_pairs_out, int32_t* num_manifolds
  * count.  Valid until the next pair calculation. */
 int32_t b2c_get_pair_deltas(b2c_ctx*, int32_t* added_out, int32_t cap_added, int32_t* removed_out, int32_t cap_removed,
                             int32_t* num_added_out, int32_t* num_removed_out);
+/* Compute the deltas inside every pair calculation (two more kernels behind the pair ordering): b2c_get_pair_deltas then
+ * only waits for the broadphase and copies, i.e. after b2c_step_device its download overlaps the narrowphase. */
+int32_t b2c_set_pair_delta_prefetch(b2c_ctx*, int32_t on);
 /* SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110):
  * union-find over every broadphase pair whose two objects merge islands (non-static).  tags_out[i] = island tag of body
  * uid i+1 (the smallest body index of its island), -1 for static bodies; n = number of bodies to report. */

@@ -12,9 +12,10 @@ The directory name carries a hyphen (repo convention), so import it by path:
 """
 from . import _lib
 from ._lib import B2CError, EXPORTS, LIB_PATH, MANIFOLD_DTYPE, RAW_DTYPE
+from .partitioned import PartitionedStepper, partition_check, world_digest
 from .world import (ALL_FILTER, DBVT, DEFAULT_FILTER, SAP16, SAP32, STATIC_FILTER, TIGHT, GpuBroadphase, GpuCollisionWorld, GpuDispatcher,
                     GpuPairCache, transforms_to_planes)
 
 __all__ = ["GpuCollisionWorld", "GpuBroadphase", "GpuDispatcher", "GpuPairCache", "B2CError", "TIGHT", "DBVT", "SAP16", "SAP32",
            "DEFAULT_FILTER", "STATIC_FILTER", "ALL_FILTER", "transforms_to_planes", "EXPORTS", "LIB_PATH",
-           "MANIFOLD_DTYPE", "RAW_DTYPE"]
+           "MANIFOLD_DTYPE", "RAW_DTYPE", "PartitionedStepper", "partition_check", "world_digest"]

@@ -66,6 +66,7 @@ EXPORTS = [
     "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase", "b2c_mgpu_slot_bytes", "b2c_mgpu_export_departed_slot",
     "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest",
     "b2c_shape_register_compound", "b2c_get_packed_contacts", "b2c_set_contact_prefetch", "b2c_begin_contact_download",
+    "b2c_get_packed_contacts_uid", "b2c_set_pair_delta_prefetch",
 ]
 NUM_STAGES = 12
 CONTACT_HEADER_DTYPE = np.dtype([
@@ -84,7 +85,8 @@ PACKED_POINT_DTYPE = np.dtype([
     ("world_a", np.float32, 3), ("world_b", np.float32, 3), ("normal_on_b", np.float32, 3), ("distance", np.float32),
     ("life_src", np.int32), ("index1", np.int32),
 ])
-assert PACKED_HEADER_DTYPE.itemsize == 16 and PACKED_POINT_DTYPE.itemsize == 48
+PACKED_UID_HEADER_DTYPE = np.dtype([("pair_uid0", np.int32), ("pair_uid1", np.int32), ("info", np.int32), ("children", np.int32)])
+assert PACKED_HEADER_DTYPE.itemsize == 16 and PACKED_POINT_DTYPE.itemsize == 48 and PACKED_UID_HEADER_DTYPE.itemsize == 16
 
 _lib = None
 
@@ -157,6 +159,8 @@ def load():
     L.b2c_get_contacts.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
     L.b2c_get_solver_contacts.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
     L.b2c_get_packed_contacts.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
+    L.b2c_get_packed_contacts_uid.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]
+    L.b2c_set_pair_delta_prefetch.argtypes = [vp, i32]
     L.b2c_set_contact_prefetch.argtypes = [vp, i32]
     L.b2c_begin_contact_download.argtypes = [vp, vp, i32, vp, i32]
     L.b2c_set_profiling.argtypes = [vp, i32]

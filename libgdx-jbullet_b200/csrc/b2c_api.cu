@@ -84,6 +84,9 @@ struct b2c_ctx {
     BodyArrays B{};
     std::vector<uint8_t> hFlags;
     std::vector<int> hShapeOf;
+    // destroyed slots: `freePending` until a pair calculation has dropped their pairs (so the manifold carry can never hand a
+    // dead proxy's manifolds to its successor), then `freeSlots`, which b2c_proxy_create reuses once the table is full
+    std::vector<int> freePending, freeSlots;
     float* dStaging = nullptr;   // 12 planes x max_bodies
     float* hStagingPinned = nullptr;
     int stagingCount = 0;        // >0: planes uploaded for bodies 1..stagingCount, to be repacked by k_aabb
@@ -199,6 +202,9 @@ struct b2c_ctx {
     int* dIslandTags = nullptr;
     int2* dDelta[2] = {nullptr, nullptr};
     uint32_t* dDeltaCounts = nullptr;  // [3]: added, removed, islands
+    bool deltaPrefetch = false;        // b2c_set_pair_delta_prefetch: the deltas are computed inside every pair calculation
+    bool deltaReady = false;           // dDelta / dDeltaCounts belong to the current pair list
+    uint32_t* hDeltaCountsPinned = nullptr;
 
     // compact contact stream
     b2c_contact_header* dContactHdr = nullptr;
@@ -443,6 +449,18 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
                                                                       ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
                                                                       ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr, ctx->dHist, ctx->dPairFirst[cur]);
     ctx->launches += 10 + ctx->sortBodies.launches;
+    if (ctx->deltaPrefetch) {
+        // pair-cache events of this calculation (added / removed pairs), ready together with the pair list so that their
+        // download overlaps the narrowphase
+        const unsigned dg = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
+        const int prev = cur ^ 1;
+        CK(cudaMemsetAsync(ctx->dDeltaCounts, 0, 2 * sizeof(uint32_t), s));
+        k_pair_delta<<<dg, 256, 0, s>>>(ctx->dSortedKeys[cur], ctx->dNumPairs[cur], ctx->dSortedKeys[prev], ctx->dNumPairs[prev],
+                                        ctx->dPairFirst[prev], ctx->uidBits, ctx->dDelta[0], (uint32_t)ctx->cfg.max_pairs, ctx->dDeltaCounts);
+        k_pair_delta<<<dg, 256, 0, s>>>(ctx->dSortedKeys[prev], ctx->dNumPairs[prev], ctx->dSortedKeys[cur], ctx->dNumPairs[cur],
+                                        ctx->dPairFirst[cur], ctx->uidBits, ctx->dDelta[1], (uint32_t)ctx->cfg.max_pairs, ctx->dDeltaCounts + 1);
+        ctx->launches += 2;
+    }
     ctx->nSortedBodies = n;  // dSmin.w = proxy index of every sorted position: the ray tests reuse the order
     CK(cudaGetLastError());
     CK(cudaEventRecordWithFlags(ctx->evPairsReady, s, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -513,7 +531,10 @@ int32_t enqueueContactCompaction(b2c_ctx* ctx, int mode, int phase = 0) {
     NpArgs a = makeNpArgs(ctx);
     if (phase != 2) CK(cudaMemsetAsync(ctx->dContactCounts, 0, 4 * sizeof(uint32_t), s));
     auto launch = [&](const NpArgs& na, unsigned grid, const uint32_t* itemPair) {
-        if (mode == 2)
+        if (mode == 3)
+            k_compact_contacts<3><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
+                                                       ctx->dContactCounts, itemPair, itemPair ? 0 : phase);
+        else if (mode == 2)
             k_compact_contacts<2><<<grid, 256, 0, s>>>(na, ctx->dContactHdr, ctx->dContactPts, ctx->capContactHdr, ctx->capContactPts,
                                                        ctx->dContactCounts, itemPair, itemPair ? 0 : phase);
         else if (mode == 1)
@@ -641,11 +662,11 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     if (ctx->timeline) cudaEventRecord(ctx->tl[4], s);
     ctx->launches += 2;
     ctx->earlyRecorded = false;
-    if (ctx->contactPrefetch == 2) {
+    if (ctx->contactPrefetch >= 2) {
         // every manifold outside the penetration bin and the mesh bin is final now: compact those and let the host start their
         // download (b2c_begin_contact_download) while the penetration bin is still running on its stream
         if (ctx->overlap) CK(cudaStreamWaitEvent(s, ctx->evJoin[0], 0));
-        int32_t rce = enqueueContactCompaction(ctx, 2, 1);
+        int32_t rce = enqueueContactCompaction(ctx, ctx->contactPrefetch, 1);
         if (rce) return rce;
         ctx->launches += 1;
         CK(cudaEventRecordWithFlags(ctx->evContactsEarly, s, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -670,7 +691,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     ctx->stageValid = ctx->prof;
     CK(cudaGetLastError());
     if (ctx->contactPrefetch >= 0) {  // the contact stream is compacted behind the dispatch: its getter only copies
-        int32_t rc = enqueueContactCompaction(ctx, ctx->contactPrefetch, ctx->contactPrefetch == 2 ? 2 : 0);
+        int32_t rc = enqueueContactCompaction(ctx, ctx->contactPrefetch, ctx->contactPrefetch >= 2 ? 2 : 0);
         if (rc) return rc;
         ctx->launches += ctx->hasCompound ? 2 : 1;
     }
@@ -747,7 +768,8 @@ static void stepSignature(const b2c_ctx* ctx, int kind, uint64_t sig[4]) {
              ((uint64_t)(uint32_t)(ctx->ccur & 1) << 11) | ((uint64_t)(uint32_t)(ctx->contactPrefetch + 1) << 12) | ((uint64_t)(uint32_t)lhint << 16) |
              ((uint64_t)(uint32_t)ctx->partRank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
     sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide;
-    sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8);
+    sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8) |
+             ((uint32_t)(ctx->deltaPrefetch ? 1 : 0) << 16);
 }
 
 static void dropStepGraphs(b2c_ctx* ctx) {
@@ -764,8 +786,15 @@ static int32_t enqueuePhases(b2c_ctx* ctx, int kind) {
     ctx->contactCountsValid = false;
     ctx->earlyDl.active = false;
     if (kind != 1) ctx->earlyRecorded = false;
+    if (kind != 2) ctx->deltaReady = false;
     int32_t rc = enqueuePhasesImpl(ctx, kind);
     if (rc == B2C_OK && kind != 1) ctx->contactReady = ctx->contactPrefetch;
+    if (rc == B2C_OK && kind != 2) ctx->deltaReady = ctx->deltaPrefetch;
+    if (rc == B2C_OK && kind != 2 && !ctx->freePending.empty()) {
+        // this pair calculation no longer sees the proxies destroyed before it: their slots may be handed out again
+        ctx->freeSlots.insert(ctx->freeSlots.end(), ctx->freePending.begin(), ctx->freePending.end());
+        ctx->freePending.clear();
+    }
     return rc;
 }
 static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind) {
@@ -803,7 +832,7 @@ static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind) {
             ctx->nSortedBodies = ctx->nBodies;
         }
         if (narrow && ctx->hasCompound) ctx->ccur ^= 1;
-        if (narrow) ctx->earlyRecorded = ctx->contactPrefetch == 2;
+        if (narrow) ctx->earlyRecorded = ctx->contactPrefetch >= 2;
         ctx->stageValid = false;
         ctx->launches += hit->launches;
         CK(cudaGraphLaunch(hit->exec, s));
@@ -1014,7 +1043,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     for (int i = 0; i < 5; i++) CKC(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i <= B2C_NUM_STAGES; i++) CKC(cudaEventCreate(&ctx->stageEv[i]));
     ctx->capContactHdr = (uint32_t)P;
-    ctx->capContactPts = (uint32_t)(2 * P);
+    ctx->capContactPts = (uint32_t)std::min<size_t>(4 * P, 0xfffffff0u);  // a manifold holds up to 4 points (np/PersistentManifold.java:47)
     CKC(dalloc(&ctx->dContactHdr, (size_t)ctx->capContactHdr));
     CKC(dalloc(&ctx->dContactPts, (size_t)ctx->capContactPts));
     CKC(dalloc(&ctx->dContactCounts, (size_t)4));
@@ -1066,6 +1095,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     if (ctx->evPairsReady) cudaEventDestroy(ctx->evPairsReady);
     if (ctx->evContactsEarly) cudaEventDestroy(ctx->evContactsEarly);
     cudaFreeHost(ctx->hEarlyCountsPinned);
+    cudaFreeHost(ctx->hDeltaCountsPinned);
     if (ctx->streamClosed) cudaStreamDestroy(ctx->streamClosed);
     if (ctx->streamEpa) cudaStreamDestroy(ctx->streamEpa);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1303,9 +1333,21 @@ int32_t b2c_proxy_create(b2c_ctx* ctx, int32_t shape, const float t[12], int16_t
     if (!ctx || !t) return B2C_ERR_BAD_ARG;
     if (shape < 0 || shape >= (int)ctx->hShapes.size()) return B2C_ERR_BAD_HANDLE;
     if (world < 0 || world >= ctx->cfg.num_worlds) return B2C_ERR_BAD_ARG;
-    if (ctx->nBodies >= ctx->cfg.max_bodies) { ctx->err = "proxy capacity exceeded"; return B2C_ERR_CAPACITY; }
+    // max_bodies caps the LIVE proxies: when every slot has been handed out, the slot (and uid) of a proxy destroyed before the
+    // last pair calculation is reused, lowest first (AxisSweep3 reuses handles the same way, bp/AxisSweep3Internal.java:380-395)
+    const bool reuse = ctx->nBodies >= ctx->cfg.max_bodies;
+    if (reuse && ctx->freeSlots.empty()) {
+        ctx->err = ctx->freePending.empty() ? "proxy capacity exceeded"
+                                            : "proxy capacity exceeded (destroyed slots become reusable after the next pair calculation)";
+        return B2C_ERR_CAPACITY;
+    }
     cudaSetDevice(ctx->device);
     int i = ctx->nBodies;
+    if (reuse) {
+        auto it = std::min_element(ctx->freeSlots.begin(), ctx->freeSlots.end());
+        i = *it;
+        ctx->freeSlots.erase(it);
+    }
     float4 rows[3] = {make_float4(t[0], t[1], t[2], t[9]), make_float4(t[3], t[4], t[5], t[10]), make_float4(t[6], t[7], t[8], t[11])};
     uint32_t filt = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
     uint8_t fl = (uint8_t)(BF_ALIVE | BF_ACTIVE | ((flags & 1) ? BF_STATIC : 0));
@@ -1323,10 +1365,15 @@ int32_t b2c_proxy_create(b2c_ctx* ctx, int32_t shape, const float t[12], int16_t
     CK(cudaMemcpyAsync(ctx->B.lastSet + i, &ls, sizeof(int), cudaMemcpyHostToDevice, s));
     k_initial_aabb<<<1, 1, 0, s>>>(ctx->B, ctx->dShapes, i, ctx->sap);
     CK(cudaStreamSynchronize(s));  // host temporaries above go out of scope
-    ctx->hFlags.push_back(fl);
-    ctx->hShapeOf.push_back(shape);
-    ctx->nBodies++;
-    if (uidOut) *uidOut = ctx->nBodies;  // ++gid
+    if (reuse) {
+        ctx->hFlags[i] = fl;
+        ctx->hShapeOf[i] = shape;
+    } else {
+        ctx->hFlags.push_back(fl);
+        ctx->hShapeOf.push_back(shape);
+        ctx->nBodies++;
+    }
+    if (uidOut) *uidOut = i + 1;  // ++gid (a recycled slot keeps its uid)
     return B2C_OK;
 }
 
@@ -1382,6 +1429,7 @@ int32_t b2c_proxy_destroy(b2c_ctx* ctx, int32_t uid) {
     uint8_t z = 0;
     CK(cudaMemcpyAsync(ctx->B.flags + (uid - 1), &z, 1, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->freePending.push_back(uid - 1);
     return B2C_OK;
 }
 
@@ -1732,7 +1780,9 @@ int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, in
     uint32_t nItems = 0;
     std::vector<b2c_raw_contact> rawMesh;
     if (ctx->hasMesh) {
-        nItems = ctx->hCtrPinned->meshItems;
+        // read the count of THIS dispatch from the device (the pinned mirror is only as fresh as the last readCounters)
+        CK(cudaMemcpyAsync(&nItems, &ctx->dCtr->meshItems, sizeof(nItems), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         if (nItems > (uint32_t)ctx->cfg.max_mesh_items) nItems = 0;
         rawMesh.resize(nItems);
         if (nItems) {
@@ -1814,8 +1864,8 @@ static int32_t getContactsImpl(b2c_ctx* ctx, int mode, void* hOut, int32_t capH,
     if (!ctx->pairsValid) return B2C_ERR_STATE;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
-    const size_t ptSize = mode == 2 ? sizeof(b2c_packed_point) : (mode == 1 ? sizeof(b2c_solver_point) : sizeof(b2c_manifold_point));
-    const size_t hdSize = mode == 2 ? sizeof(b2c_packed_header) : sizeof(b2c_contact_header);
+    const size_t ptSize = mode >= 2 ? sizeof(b2c_packed_point) : (mode == 1 ? sizeof(b2c_solver_point) : sizeof(b2c_manifold_point));
+    const size_t hdSize = mode >= 2 ? sizeof(b2c_packed_header) : sizeof(b2c_contact_header);
     uint32_t counts[2] = {0, 0};
     if (ctx->contactReady == mode && ctx->contactCountsValid) {
         // compacted behind the dispatch (b2c_set_contact_prefetch) and the counts came back with the step counters
@@ -1842,7 +1892,7 @@ static int32_t getContactsImpl(b2c_ctx* ctx, int mode, void* hOut, int32_t capH,
     if (!hOut && !pOut) return B2C_OK;
     if ((uint32_t)capH < counts[0] || (uint32_t)capP < counts[1]) { ctx->err = "contact output buffers too small"; return B2C_ERR_CAPACITY; }
     uint32_t h0 = 0, p0 = 0;
-    if (mode == 2 && ctx->earlyDl.active && ctx->earlyDl.hdr == hOut && ctx->earlyDl.pts == pOut && ctx->earlyDl.nH <= counts[0] &&
+    if (mode >= 2 && ctx->earlyDl.active && ctx->earlyDl.hdr == hOut && ctx->earlyDl.pts == pOut && ctx->earlyDl.nH <= counts[0] &&
         ctx->earlyDl.nP <= counts[1]) {
         h0 = ctx->earlyDl.nH;  // the first part is already on its way (b2c_begin_contact_download): copy only what the
         p0 = ctx->earlyDl.nP;  // end of the dispatch appended behind it
@@ -1874,10 +1924,15 @@ int32_t b2c_get_packed_contacts(b2c_ctx* ctx, b2c_packed_header* hOut, int32_t c
     return getContactsImpl(ctx, 2, hOut, capH, pOut, capP, nH, nP);
 }
 
-int32_t b2c_begin_contact_download(b2c_ctx* ctx, b2c_packed_header* hOut, int32_t capH, b2c_packed_point* pOut, int32_t capP) {
+int32_t b2c_get_packed_contacts_uid(b2c_ctx* ctx, b2c_packed_uid_header* hOut, int32_t capH, b2c_packed_point* pOut, int32_t capP,
+                                    int32_t* nH, int32_t* nP) {
+    return getContactsImpl(ctx, 3, hOut, capH, pOut, capP, nH, nP);
+}
+
+int32_t b2c_begin_contact_download(b2c_ctx* ctx, void* hOut, int32_t capH, b2c_packed_point* pOut, int32_t capP) {
     if (!ctx || !hOut || !pOut || capH < 0 || capP < 0) return B2C_ERR_BAD_ARG;
-    if (ctx->contactPrefetch != 2 || !ctx->earlyRecorded) {
-        ctx->err = "b2c_begin_contact_download needs b2c_set_contact_prefetch(ctx, 2) and an enqueued dispatch";
+    if (ctx->contactPrefetch < 2 || !ctx->earlyRecorded) {
+        ctx->err = "b2c_begin_contact_download needs b2c_set_contact_prefetch(ctx, 2 or 3) and an enqueued dispatch";
         return B2C_ERR_STATE;
     }
     cudaSetDevice(ctx->device);
@@ -1899,7 +1954,7 @@ int32_t b2c_begin_contact_download(b2c_ctx* ctx, b2c_packed_header* hOut, int32_
 }
 
 int32_t b2c_set_contact_prefetch(b2c_ctx* ctx, int32_t format) {
-    if (!ctx || format < -1 || format > 2) return B2C_ERR_BAD_ARG;
+    if (!ctx || format < -1 || format > 3) return B2C_ERR_BAD_ARG;
     ctx->contactPrefetch = format;
     return B2C_OK;
 }
@@ -1913,6 +1968,24 @@ int32_t b2c_get_pair_deltas(b2c_ctx* ctx, int32_t* addedOut, int32_t capA, int32
     if (!ctx->dDeltaCounts) CK(dalloc(&ctx->dDeltaCounts, (size_t)4));
     for (int i = 0; i < 2; i++)
         if (!ctx->dDelta[i]) CK(dalloc(&ctx->dDelta[i], P));
+    if (ctx->deltaReady) {
+        // computed inside the pair calculation: copy on the side stream, which only waits for the broadphase
+        cudaStream_t cs = ctx->streamCopy;
+        CK(cudaStreamWaitEvent(cs, ctx->evPairsReady, 0));
+        CK(cudaMemcpyAsync(ctx->hDeltaCountsPinned, ctx->dDeltaCounts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+        CK(cudaStreamSynchronize(cs));
+        const uint32_t c0 = ctx->hDeltaCountsPinned[0], c1 = ctx->hDeltaCountsPinned[1];
+        if (nA) *nA = (int32_t)c0;
+        if (nR) *nR = (int32_t)c1;
+        if ((addedOut && (uint32_t)capA < c0) || (removedOut && (uint32_t)capR < c1)) {
+            ctx->err = "pair delta output buffer too small";
+            return B2C_ERR_CAPACITY;
+        }
+        if (addedOut && c0) CK(cudaMemcpyAsync(addedOut, ctx->dDelta[0], (size_t)c0 * sizeof(int2), cudaMemcpyDeviceToHost, cs));
+        if (removedOut && c1) CK(cudaMemcpyAsync(removedOut, ctx->dDelta[1], (size_t)c1 * sizeof(int2), cudaMemcpyDeviceToHost, cs));
+        CK(cudaStreamSynchronize(cs));
+        return B2C_OK;
+    }
     const int cur = ctx->cur, prev = cur ^ 1;
     CK(cudaMemsetAsync(ctx->dDeltaCounts, 0, 2 * sizeof(uint32_t), s));
     const unsigned g = gridFor((uint32_t)P, 256);
@@ -1932,6 +2005,21 @@ int32_t b2c_get_pair_deltas(b2c_ctx* ctx, int32_t* addedOut, int32_t capA, int32
     if (addedOut && c[0]) CK(cudaMemcpyAsync(addedOut, ctx->dDelta[0], (size_t)c[0] * sizeof(int2), cudaMemcpyDeviceToHost, s));
     if (removedOut && c[1]) CK(cudaMemcpyAsync(removedOut, ctx->dDelta[1], (size_t)c[1] * sizeof(int2), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return B2C_OK;
+}
+
+int32_t b2c_set_pair_delta_prefetch(b2c_ctx* ctx, int32_t on) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    if (on) {
+        const size_t P = (size_t)ctx->cfg.max_pairs;
+        if (!ctx->dDeltaCounts) CK(dalloc(&ctx->dDeltaCounts, (size_t)4));
+        for (int i = 0; i < 2; i++)
+            if (!ctx->dDelta[i]) CK(dalloc(&ctx->dDelta[i], P));
+        if (!ctx->hDeltaCountsPinned) CK(cudaMallocHost((void**)&ctx->hDeltaCountsPinned, 2 * sizeof(uint32_t)));
+    }
+    ctx->deltaPrefetch = on != 0;
+    ctx->deltaReady = false;
     return B2C_OK;
 }
 

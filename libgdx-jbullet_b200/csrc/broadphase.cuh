@@ -193,13 +193,13 @@ k_aabb(BodyArrays B, const ShapeDev* __restrict__ shapes, int n, const float* __
                 B.xf4[3 * (size_t)i + 1] = r1;
                 B.xf4[3 * (size_t)i + 2] = r2;
             }
-            if (extAabb) {
-                if (extMask[i]) {
-                    f3 mn = mk3(extAabb[i], extAabb[i + (size_t)extStride], extAabb[i + 2 * (size_t)extStride]);
-                    f3 mx = mk3(extAabb[i + 3 * (size_t)extStride], extAabb[i + 4 * (size_t)extStride],
-                                extAabb[i + 5 * (size_t)extStride]);
-                    setAabbState(B, i, mn, mx, mode, step, dbvtMargin, predicted, flags, sp);
-                }
+            // per proxy: a host-supplied AABB (setAabb) wins for the proxies it names; every other active proxy is still
+            // updated from its transform when updateAabbs was asked for (the two are independent in the reference)
+            if (extAabb && extMask[i]) {
+                f3 mn = mk3(extAabb[i], extAabb[i + (size_t)extStride], extAabb[i + 2 * (size_t)extStride]);
+                f3 mx = mk3(extAabb[i + 3 * (size_t)extStride], extAabb[i + 4 * (size_t)extStride],
+                            extAabb[i + 5 * (size_t)extStride]);
+                setAabbState(B, i, mn, mx, mode, step, dbvtMargin, predicted, flags, sp);
             } else if (doUpdate && (flags & BF_ACTIVE)) {
                 Xf t;
                 {

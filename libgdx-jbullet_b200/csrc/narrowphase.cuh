@@ -1565,8 +1565,12 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restr
         int totalP = __shfl_sync(0xffffffffu, incl, 31);
         uint32_t baseH = 0, baseP = 0;
         if (lane == 0) {
-            baseH = atomicAdd(&counts[0], (uint32_t)__popc(m));
-            baseP = atomicAdd(&counts[1], (uint32_t)totalP);
+            // ONE 64-bit atomic reserves headers (low word) and points (high word) together, so the points of consecutive
+            // headers are consecutive: first_point is the running sum of num_contacts in header order (format 3 relies on it)
+            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(counts),
+                                                     (unsigned long long)__popc(m) | ((unsigned long long)(uint32_t)totalP << 32));
+            baseH = (uint32_t)old;
+            baseP = (uint32_t)(old >> 32);
         }
         baseH = __shfl_sync(0xffffffffu, baseH, 0);
         baseP = __shfl_sync(0xffffffffu, baseP, 0);
@@ -1575,7 +1579,15 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restr
             uint32_t fp = baseP + (uint32_t)(incl - nc);
             if (h < capH && fp + nc <= capP) {
                 const ManifoldHdr* mf = a.mhdr + p;
-                if (MODE == 2) {
+                if (MODE == 3) {
+                    // b2c_packed_uid_header: the host needs no pair list to read it
+                    int4 ph;
+                    ph.x = mf->pair_uid0;
+                    ph.y = mf->pair_uid1;
+                    ph.z = nc | (mf->algorithm << 8) | ((mf->body0 != mf->pair_uid0) ? 0x10000 : 0);
+                    ph.w = itemPair ? ((mf->pad0 & 0xffff) | (mf->pad1 << 16)) : -1;
+                    reinterpret_cast<int4*>(hdr)[h] = ph;
+                } else if (MODE == 2) {
                     int4 ph;
                     ph.x = itemPair ? (int)itemPair[p] : (int)p;
                     ph.y = (int)fp;
@@ -1592,7 +1604,7 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restr
                 }
                 for (int k = 0; k < nc; k++) {
                     const int4* src = reinterpret_cast<const int4*>(a.mpts + 4 * (size_t)p + k);
-                    if (MODE == 2) {
+                    if (MODE >= 2) {
                         // words of the 96-byte record: 6-8 world_a, 9-11 world_b, 12-14 normal, 15 distance, 18 life, 19 src_slot, 21 index1
                         const int4 v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4], v5 = src[5];
                         int4* dst = reinterpret_cast<int4*>(reinterpret_cast<b2c_packed_point*>(ptsOut) + fp + k);

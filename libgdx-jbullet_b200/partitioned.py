@@ -1,0 +1,134 @@
+"""One collision world partitioned over several GPUs (BASELINE config C5) — host side.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Every call below is enqueue-only on the world's CUDA stream;
+the NCCL collectives are enqueued on the same stream, so a step never synchronises with the host.  The device work is
+libb2c.so's `b2c_mgpu_*` entry points (include/b2c.h, last section); this module only sequences them and owns the
+exchange buffers.  `partition_check` proves, inside a real multi-rank run, that the union over the ranks equals what one
+GPU computes for the same world (pairs exactly, manifolds bit for bit).
+"""
+import numpy as np
+
+MASK64 = (1 << 64) - 1
+
+
+class PartitionedStepper:
+    """Sequences one partitioned step:  broadphase on this rank's share -> manifolds of pairs that changed owner are packed
+    into a fixed-size slot -> ONE all-gather -> adoption -> narrowphase on the pairs this rank owns."""
+
+    def __init__(self, gw, rank, nranks, dist, torch, dev, migrate_cap=8192):
+        self.gw, self.rank, self.nranks, self.dist, self.torch = gw, rank, nranks, dist, torch
+        self.stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
+        self.mcap = int(migrate_cap)
+        gw.set_partition(rank, nranks)
+        self.slot_bytes = gw.mgpu_slot_bytes(self.mcap)
+        self.my_slot = torch.zeros(self.slot_bytes, dtype=torch.uint8, device=f"cuda:{dev}")
+        self.all_slots = torch.zeros(self.slot_bytes * nranks, dtype=torch.uint8, device=f"cuda:{dev}")
+        self.extra_launches = 0   # kernels outside b2c_stats.kernel_launches are counted by the library itself
+
+    def all_gather(self, out, inp):
+        """One NCCL all-gather on the world's stream; with a single rank (tests on one device) it is a copy."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            if self.dist is not None and self.nranks > 1:
+                self.dist.all_gather_into_tensor(out, inp)
+            else:
+                out.copy_(inp)
+
+    def step(self):
+        gw = self.gw
+        gw.mgpu_broadphase()
+        gw.mgpu_export_departed_slot(self.my_slot.data_ptr(), self.mcap)
+        self.all_gather(self.all_slots, self.my_slot)
+        gw.mgpu_import_arrival_slots(self.all_slots.data_ptr(), self.nranks, self.mcap)
+        gw.mgpu_narrowphase()
+
+    def describe(self):
+        return (f"ncclAllGather of one {self.slot_bytes}-byte migration slot per rank per step ({self.mcap} manifolds of pairs "
+                f"that changed owner; {self.slot_bytes * self.nranks} bytes gathered per rank)")
+
+    def close(self):
+        self.my_slot = self.all_slots = None
+
+
+def _mix(h):
+    h = (h ^ (h >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    h = (h ^ (h >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return h ^ (h >> np.uint64(31))
+
+
+def multiset_hash(rows_u64):
+    """Order-independent 64-bit digest of the rows of a (n, w) uint64 array: sum of a mixed per-row hash (mod 2^64)."""
+    a = np.ascontiguousarray(rows_u64, dtype=np.uint64)
+    if a.size == 0:
+        return 0
+    with np.errstate(over="ignore"):
+        w = (np.arange(a.shape[1], dtype=np.uint64) * np.uint64(2) + np.uint64(0x9E3779B97F4A7C15))
+        h = _mix((a * w[None, :]).sum(axis=1, dtype=np.uint64) + np.uint64(a.shape[1]))
+        return int(h.sum(dtype=np.uint64)) & MASK64
+
+
+def world_digest(gw):
+    """(pair count, pair hash, touching manifolds, contact points, manifold hash) of the world's last step.  The manifold
+    hash covers the header (pair uids, body order, contact count, algorithm) and all 22 payload words of every live point
+    (local / world positions, normal, distance, friction, restitution, lifetime, warm-start slot, triangle ids) from the
+    compact contact stream, i.e. equality means bit-identical manifolds."""
+    p = gw.pairs().astype(np.uint64)
+    ph = multiset_hash(p)
+    hdr, pts = gw.contacts()
+    rows = np.zeros((len(hdr), 6 + 4 * 11), dtype=np.uint64)
+    if len(hdr):
+        for k, f in enumerate(("pair_uid0", "pair_uid1", "body0", "body1", "num_contacts", "algorithm")):
+            rows[:, k] = hdr[f].astype(np.int64).astype(np.uint64)
+        words = np.ascontiguousarray(pts).view(np.uint64).reshape(len(pts), 12)[:, :11]   # 96-byte records, last 8 bytes padding
+        idx = hdr["first_point"].astype(np.int64)[:, None] + np.arange(4)[None, :]
+        live = np.arange(4)[None, :] < hdr["num_contacts"][:, None]
+        w = words[np.clip(idx, 0, max(len(pts) - 1, 0))]
+        w[~live] = 0
+        rows[:, 6:] = w.reshape(len(hdr), 44)
+    return [int(len(p)), ph, int(len(hdr)), int(len(pts)), multiset_hash(rows)]
+
+
+def partition_check(pkg, make_stepper, build_world, frames, rank, nranks, dist, steps=4):
+    """Run `steps` steps of the same world twice inside this multi-rank job — partitioned over all ranks, and whole on rank
+    0's GPU — and compare after every step: the ranks' pair lists must be disjoint and their union the single-GPU list, the
+    union of their touching manifolds bit-identical to the single-GPU manifolds (order-independent 64-bit digests, summed
+    over the ranks).  Returns a summary dict on rank 0 (raises AssertionError on any mismatch), None elsewhere.
+
+    build_world() -> a fresh GpuCollisionWorld of the scene; make_stepper(gw) -> its PartitionedStepper;
+    frames[k] = (12, n) float32 transform planes of step k."""
+    gw = build_world()
+    mg = make_stepper(gw)
+    single = build_world() if rank == 0 else None
+    report = {"steps": steps, "pairs": [], "touching_manifolds": [], "contact_points": [], "migrated_manifolds": "exercised by the moving trace"}
+    for k in range(steps):
+        planes = frames[k % len(frames)]
+        gw.setWorldTransformPlanes(planes)
+        mg.step()
+        gw.sync_counts()
+        d = world_digest(gw)
+        if dist is not None and nranks > 1:
+            allv = [None] * nranks
+            dist.all_gather_object(allv, d)
+        else:
+            allv = [d]
+        if rank == 0:
+            tot = [sum(v[0] for v in allv), sum(v[1] for v in allv) & MASK64, sum(v[2] for v in allv), sum(v[3] for v in allv),
+                   sum(v[4] for v in allv) & MASK64]
+            single.setWorldTransformPlanes(planes)
+            single.step_device()
+            single.sync_counts()
+            ref = world_digest(single)
+            assert tot[0] == ref[0], f"step {k}: union of the ranks has {tot[0]} pairs, one GPU {ref[0]}"
+            assert tot[1] == ref[1], f"step {k}: pair sets differ (digest)"
+            assert tot[2] == ref[2] and tot[3] == ref[3], f"step {k}: touching manifolds / points {tot[2]}/{tot[3]} vs {ref[2]}/{ref[3]}"
+            assert tot[4] == ref[4], f"step {k}: manifold contents differ (digest)"
+            report["pairs"].append(ref[0]); report["touching_manifolds"].append(ref[2]); report["contact_points"].append(ref[3])
+    mg.close()
+    gw.close()
+    if single is not None:
+        single.close()
+    if rank != 0:
+        return None
+    report["result"] = "union over ranks == single GPU (pairs exact, manifolds bit-identical) at every step"
+    report["per_rank_pairs_last_step"] = [v[0] for v in allv]
+    return report

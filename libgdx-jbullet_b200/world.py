@@ -137,7 +137,7 @@ class GpuCollisionWorld:
         t = np.ascontiguousarray(transform12, dtype=np.float32)
         out = C.c_int32()
         self._ck(self.L.b2c_proxy_create(self.h, shape, _vp(t), group, mask, 1 if static else 0, world, C.byref(out)))
-        self.num_bodies = out.value
+        self.num_bodies = max(self.num_bodies, out.value)  # a recycled slot returns an old uid
         return out.value
 
     def addCollisionObjects(self, shapes, transforms, groups=None, masks=None, static=None, worlds=None):
@@ -350,8 +350,22 @@ class GpuCollisionWorld:
             self._ck(self.L.b2c_get_packed_contacts(self.h, _vp(hdr), nh.value, _vp(pts), npt.value, C.byref(nh), C.byref(npt)))
         return hdr, pts
 
+    def packed_contacts_uid(self):
+        """The packed stream keyed by uids (include/b2c.h b2c_packed_uid_header): needs no pair list on the host."""
+        nh, npt = C.c_int32(), C.c_int32()
+        self._ck(self.L.b2c_get_packed_contacts_uid(self.h, None, 0, None, 0, C.byref(nh), C.byref(npt)))
+        hdr = np.zeros(nh.value, dtype=_lib.PACKED_UID_HEADER_DTYPE)
+        pts = np.zeros(npt.value, dtype=_lib.PACKED_POINT_DTYPE)
+        if nh.value:
+            self._ck(self.L.b2c_get_packed_contacts_uid(self.h, _vp(hdr), nh.value, _vp(pts), npt.value, C.byref(nh), C.byref(npt)))
+        return hdr, pts
+
+    def set_pair_delta_prefetch(self, on=True):
+        """Compute the pair-cache add / remove events inside every pair calculation (b2c_get_pair_deltas then only copies)."""
+        self._ck(self.L.b2c_set_pair_delta_prefetch(self.h, int(on)))
+
     def set_contact_prefetch(self, fmt):
-        """Compact the contact stream (0 full / 1 solver / 2 packed points, -1 off) behind every dispatch."""
+        """Compact the contact stream (0 full / 1 solver / 2 packed / 3 packed uid-keyed points, -1 off) behind every dispatch."""
         self._ck(self.L.b2c_set_contact_prefetch(self.h, int(fmt)))
 
     def set_profiling(self, on=True):

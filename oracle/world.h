@@ -346,7 +346,10 @@ struct World {
                         pairs.push_back(std::make_pair(A.uid, B.uid));
                 }
         } else {
+            // world-major order: separate worlds never share a pair cache (filter() rejects such pairs anyway), so each
+            // world is swept on its own — 4096 batched worlds occupy the same coordinates and would make one sweep quadratic
             std::sort(order.begin(), order.end(), [&](int a, int c) {
+                if (bodies[a].world != bodies[c].world) return bodies[a].world < bodies[c].world;
                 if (bodies[a].effMin.x != bodies[c].effMin.x) return bodies[a].effMin.x < bodies[c].effMin.x;
                 return a < c;
             });
@@ -354,7 +357,7 @@ struct World {
                 const Body& A = bodies[order[a]];
                 for (size_t c = a + 1; c < order.size(); c++) {
                     const Body& B = bodies[order[c]];
-                    if (B.effMin.x > A.effMax.x) break;
+                    if (B.world != A.world || B.effMin.x > A.effMax.x) break;
                     // SAP modes: eff is a monotone image of the quantised box, so the float window is conservative
                     if (filter(A, B) && (isSap() ? sapOverlap(A, B) : intersect(A.effMin, A.effMax, B.effMin, B.effMax)))
                         pairs.push_back(std::make_pair(std::min(A.uid, B.uid), std::max(A.uid, B.uid)));

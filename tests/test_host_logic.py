@@ -55,8 +55,30 @@ def test_frame_index_ping_pong():
 def test_algorithmic_bytes_formula():
     import bench
     st = dict(gjk_checks=1000, deep_penetration_checks=10, large_proxies=5)
-    assert bench.algorithmic_bytes("sweep", 100, 500, st, 7, 5, 0) == 9 * 100 * 4 + 100 * 32 + 8 * 500
-    assert bench.algorithmic_bytes("sort_pairs", 100, 500, st, 7, 5, 0) == 8 * 100 + 500 * (8 + 4 + 4 + 16)
+    assert bench.algorithmic_bytes("sweep", 100, 500, st, 7, 0) == 9 * 100 * 4 + 100 * 32 + 8 * 500
+    assert bench.algorithmic_bytes("sort_pairs", 100, 500, st, 7, 0) == 8 * 100 + 500 * (8 + 4 + 4 + 16)
+    assert bench.algorithmic_bytes("large", 100, 500, st, 7, 0) == 0
+
+
+def test_both_arms_name_the_workload_identically():
+    import bench
+    a = bench.workload_name("c2", 100000, 4096)
+    assert "100000" in a and a == bench.workload_name("c2", 100000, 1)
+    assert bench.max_pairs_for(type("A", (), dict(max_pairs=3 << 20, c5_bodies=1000000, bodies=100000, workload="c2")), "c5") >= 9000000
+
+
+def test_multiset_hash_is_order_independent_and_sensitive(pkg):
+    from libgdx_jbullet_b200.partitioned import MASK64, multiset_hash
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 1 << 40, size=(5000, 7), dtype=np.uint64)
+    h = multiset_hash(a)
+    assert h == multiset_hash(a[rng.permutation(len(a))])
+    # a partition of the rows sums (mod 2^64) to the digest of the whole: what partition_check relies on
+    assert (multiset_hash(a[:1234]) + multiset_hash(a[1234:])) & MASK64 == h
+    b = a.copy(); b[17, 3] ^= np.uint64(1)
+    assert multiset_hash(b) != h
+    assert multiset_hash(np.concatenate([a, a[:1]])) != h     # a duplicated row changes it
+    assert multiset_hash(np.zeros((0, 7), np.uint64)) == 0
 
 
 def test_reference_arm_runs_and_prints_contract_line():
@@ -66,3 +88,16 @@ def test_reference_arm_runs_and_prints_contract_line():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "collision_phase_world_steps_per_s_100k_bodies"
+    assert d["steps"] == 2 and d["warmup"] == 1, "the reference arm must honour --steps / --warmup"
+    assert "java" in d["cpu_baseline"]["jvm"]          # probed at run time, not a constant
+    import bench
+    assert d["config"]["workload"] == bench.workload_name("c2", 1500, 4096)
+
+
+def test_reference_arm_steps_one_world_per_requested_gpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--bodies", "1200",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["n_gpus"] == 2 and d["cpu_baseline"]["cores"] == 2
+    assert abs(d["value"] - 2 * 1000.0 / d["ms_per_step"]) < 1e-6 * d["value"]   # whole-job rate of 2 worlds on 2 cores
