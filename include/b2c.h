@@ -330,26 +330,46 @@ int32_t b2c_ray_test_closest(b2c_ctx*, int32_t n, const float* from_xyz, const f
                              int32_t* uid_out, float* fraction_out, float* normal_out, float* point_out);
 
 /* ---- one world partitioned over several GPUs -------------------------------------
- * Every rank holds all proxies (their state is small) and owns a contiguous slice of the SORTED proxy list: it
- * emits the pairs whose first member in sweep order lies in its slice (slab partition by sorted-AABB range; reads
- * beyond the slice are the halo), and runs the narrowphase for exactly those pairs.  The union over ranks is the
- * single-GPU result.  A pair near a slice boundary can change owner between steps, so its manifold migrates:
- *   b2c_mgpu_broadphase -> b2c_mgpu_export_departed -> [all-gather over NVLink, e.g. ncclAllGather] ->
- *   b2c_mgpu_import_arrivals -> b2c_mgpu_narrowphase.
- * The export/import buffers are DEVICE pointers owned by the caller (so NCCL can use them directly):
- * keys: uint64[cap]; headers: 32-byte records [cap]; points: b2c_manifold_point[4*cap]. */
+ * Space is cut into `nranks` slabs by planes along one axis; rank r owns slab r.  A PROXY is owned by the rank whose slab
+ * held its origin when the partition was set: only that rank runs updateAabbs / setAabb for it.  A PAIR is owned by the slab
+ * that holds max(min_a, min_b) along the axis (a coordinate inside both boxes).  Each step every rank needs the boxes of all
+ * proxies that touch its slab: its own plus the HALO — proxies owned elsewhere whose box reaches into the slab.  Owners publish
+ * their boundary proxies (box not entirely inside the home slab) as 80-byte records (box, proxy index, flags, transform) in
+ * a fixed-size slot, ONE all-gather over NVLink (e.g. ncclAllGather on the ctx stream) hands every rank all slots, and each
+ * rank sorts and sweeps its local list.  The union of the ranks' pair lists is the single-GPU list.  A pair near a plane can
+ * change owner between steps, so its manifold migrates with a second, small all-gather:
+ *   b2c_mgpu_update_export_halo -> [all-gather halo slots] -> b2c_mgpu_import_halo -> b2c_mgpu_broadphase ->
+ *   b2c_mgpu_export_departed_slot -> [all-gather migration slots] -> b2c_mgpu_import_arrival_slots -> b2c_mgpu_narrowphase.
+ * Every call only enqueues on the ctx stream (no host synchronisation); overflowing slots are reported by the next
+ * b2c_sync_counts as B2C_ERR_CAPACITY.  All ranks create the same proxies in the same order (static attributes are
+ * replicated); per-step transforms are only needed for the proxies a rank owns (b2c_get_partition tells which).
+ * Slot buffers are DEVICE pointers owned by the caller, so NCCL can use them directly. */
+/* Slabs along `axis` (0/1/2) cut at planes[0 .. nranks-2] (ascending).  Call on every rank after the proxies exist and while
+ * all ranks hold the same transforms; nranks = 1 removes the partition.  At most 16 ranks. */
+int32_t b2c_set_partition_slabs(b2c_ctx*, int32_t rank, int32_t nranks, int32_t axis, const float* planes);
+/* The same with planes chosen by the library: the axis the origins spread most over, cut at equal-count quantiles. */
 int32_t b2c_set_partition(b2c_ctx*, int32_t rank, int32_t nranks);
+/* The partition in force: axis, nranks-1 planes, and the owning rank of proxies 1..n (any output may be NULL). */
+int32_t b2c_get_partition(b2c_ctx*, int32_t* axis_out, float* planes_out, uint8_t* owner_out, int32_t n);
+/* Halo slot = { uint32 count, uint32 pad[3], 80-byte records[cap] }. */
+int64_t b2c_mgpu_halo_slot_bytes(int32_t cap);
+/* CollisionWorld.updateAabbs for the proxies this rank owns (disp/CollisionWorld.java:231-245), then its boundary proxies
+ * into `slot_dev`. */
+int32_t b2c_mgpu_update_export_halo(b2c_ctx*, void* slot_dev, int32_t cap);
+/* After the all-gather: `slots_dev` = nranks slots in rank order.  Adopts the records that touch this rank's slab. */
+int32_t b2c_mgpu_import_halo(b2c_ctx*, const void* slots_dev, int32_t nslots, int32_t cap);
+/* BroadphaseInterface.calculateOverlappingPairs over the rank's local list; keeps the pairs this rank owns. */
 int32_t b2c_mgpu_broadphase(b2c_ctx*);
+/* Manifold migration with a host round trip (tests): keys: uint64[cap]; headers: 32-byte records [cap]; points:
+ * b2c_manifold_point[4*cap]. */
 int32_t b2c_mgpu_export_departed(b2c_ctx*, uint64_t* keys_dev, void* headers_dev, b2c_manifold_point* points_dev, int32_t cap,
                                  int32_t* count_out);
 int32_t b2c_mgpu_import_arrivals(b2c_ctx*, const uint64_t* keys_dev, const void* headers_dev, const b2c_manifold_point* points_dev,
                                  int32_t count);
 int32_t b2c_mgpu_narrowphase(b2c_ctx*);
-/* The same exchange without any host synchronisation, for a fixed-size all-gather (one NCCL call per step, enqueued
- * right behind the export on the ctx stream): every rank packs its departed manifolds into one SLOT
- *   { uint32 count, uint32 pad[3], uint64 keys[cap], 32-byte headers[cap], b2c_manifold_point points[4*cap] }
- * of b2c_mgpu_slot_bytes(cap) bytes; after the all-gather each rank scans all `nslots` slots on the device.  A slot
- * that would overflow is reported by the next b2c_sync_counts as B2C_ERR_CAPACITY. */
+/* The same exchange without any host synchronisation, for a fixed-size all-gather: every rank packs its departed manifolds
+ * into one SLOT { uint32 count, uint32 pad[3], uint64 keys[cap], 32-byte headers[cap], b2c_manifold_point points[4*cap] }
+ * of b2c_mgpu_slot_bytes(cap) bytes; after the all-gather each rank scans all `nslots` slots on the device. */
 int64_t b2c_mgpu_slot_bytes(int32_t cap);
 int32_t b2c_mgpu_export_departed_slot(b2c_ctx*, void* slot_dev, int32_t cap);
 int32_t b2c_mgpu_import_arrival_slots(b2c_ctx*, const void* slots_dev, int32_t nslots, int32_t cap);

@@ -66,7 +66,8 @@ EXPORTS = [
     "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase", "b2c_mgpu_slot_bytes", "b2c_mgpu_export_departed_slot",
     "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest",
     "b2c_shape_register_compound", "b2c_get_packed_contacts", "b2c_set_contact_prefetch", "b2c_begin_contact_download",
-    "b2c_get_packed_contacts_uid", "b2c_set_pair_delta_prefetch",
+    "b2c_get_packed_contacts_uid", "b2c_set_pair_delta_prefetch", "b2c_set_partition_slabs", "b2c_get_partition",
+    "b2c_mgpu_halo_slot_bytes", "b2c_mgpu_update_export_halo", "b2c_mgpu_import_halo",
 ]
 NUM_STAGES = 12
 CONTACT_HEADER_DTYPE = np.dtype([
@@ -143,6 +144,12 @@ def load():
     L.b2c_sync_counts.argtypes = [vp, pi32, pi32, pi32]
     L.b2c_set_transforms_device.argtypes = [vp, i32, vp]
     L.b2c_set_partition.argtypes = [vp, i32, i32]
+    L.b2c_set_partition_slabs.argtypes = [vp, i32, i32, i32, vp]
+    L.b2c_get_partition.argtypes = [vp, pi32, vp, vp, i32]
+    L.b2c_mgpu_halo_slot_bytes.argtypes = [i32]
+    L.b2c_mgpu_halo_slot_bytes.restype = C.c_int64
+    L.b2c_mgpu_update_export_halo.argtypes = [vp, vp, i32]
+    L.b2c_mgpu_import_halo.argtypes = [vp, vp, i32, i32]
     L.b2c_mgpu_broadphase.argtypes = [vp]
     L.b2c_mgpu_export_departed.argtypes = [vp, vp, vp, vp, i32, pi32]
     L.b2c_mgpu_import_arrivals.argtypes = [vp, vp, vp, vp, i32]

@@ -3,6 +3,7 @@
 // fallback (b2c_create fails without an sm_100 device).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,8 @@
 #include "islands.cuh"
 #include "narrowphase.cuh"
 #include "pair_rows.cuh"
+#include "halo.cuh"
+#include "pairfind.cuh"
 #include "radix_sort.cuh"
 #include "raycast.cuh"
 
@@ -158,7 +161,15 @@ struct b2c_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int launches = 0;
     int32_t lastPairs = 0, lastManifolds = 0, lastContacts = 0;
-    int partRank = 0, partRanks = 1;
+    // one world partitioned over several GPUs by slabs (halo.cuh)
+    SlabFilter slab{};                 // enabled = 0: the whole world lives here
+    int partRanks = 1;
+    uint8_t* dOwner = nullptr;         // [N] owning rank of every proxy
+    uint32_t* dLocalList = nullptr;    // [N] proxies this rank sorts and sweeps this step (owned and touching + imported halo)
+    uint32_t* dNLocal = nullptr;       // device count of dLocalList
+    uint32_t* dNSorted = nullptr;      // device count of the sorted arrays (== nBodies / *dNLocal), written by k_gather
+    uint32_t localHint = 0;            // host's last reading of *dNLocal (launch shapes only; 0 = unknown)
+    bool haloExported = false, haloImported = false;
     uint32_t* dExportCount = nullptr;
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
@@ -341,10 +352,15 @@ int32_t runAabbKernel(b2c_ctx* ctx, bool forPairs) {
     int32_t rc = uploadShapes(ctx);
     if (rc) return rc;
     const float* staging = ctx->stagingCount > 0 ? ctx->dStaging : nullptr;
+    // forPairs: the grid of this step comes out of the same launch (single world: fused bounds reduction; partitioned world: the
+    // reduction runs over the local list once the halo is in, see enqueueBroadphase)
+    const bool slab = ctx->slab.enabled != 0;
     k_aabb<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
         ctx->B, ctx->dShapes, n, staging, ctx->cfg.max_bodies, ctx->stagingCount, ctx->extPending ? ctx->dExtAabb : nullptr,
         ctx->dExtMask, ctx->cfg.max_bodies, ctx->cfg.broadphase_mode, ctx->dStep, ctx->cfg.contact_breaking_threshold,
-        ctx->cfg.dbvt_margin, ctx->cfg.dbvt_predicted_frames, ctx->aabbPending ? 1 : 0, ctx->dCtr, ctx->sap);
+        ctx->cfg.dbvt_margin, ctx->cfg.dbvt_predicted_frames, ctx->aabbPending ? 1 : 0, ctx->dCtr, ctx->sap,
+        forPairs ? 1 : 0, (forPairs && !slab) ? 1 : 0, ctx->dGrid, ctx->cfg.num_worlds, ctx->maxRows - ctx->cfg.num_worlds,
+        slab ? ctx->dOwner : nullptr, ctx->slab.rank);
     ctx->launches++;
     ctx->stagingCount = 0;
     if (ctx->extPending) {
@@ -358,11 +374,26 @@ int32_t runAabbKernel(b2c_ctx* ctx, bool forPairs) {
 
 static inline void mark(b2c_ctx* ctx, int k);
 
+// launch-shape bound of the proxies one pair calculation sorts (the exact count of a partitioned world lives on the device)
+static uint32_t slabUpper(const b2c_ctx* ctx) {
+    const uint32_t n = (uint32_t)ctx->nBodies;
+    if (!ctx->slab.enabled || ctx->localHint == 0) return n;
+    const uint64_t h = (uint64_t)ctx->localHint * 5 / 4 + 4096;
+    return h < n ? (uint32_t)h : n;
+}
+
 int32_t enqueueBroadphase(b2c_ctx* ctx) {
     int n = ctx->nBodies;
+    const bool slab = ctx->slab.enabled != 0;
     mark(ctx, 0);
-    int32_t rc = runAabbKernel(ctx, true);
-    if (rc) return rc;
+    if (!slab) {
+        int32_t rc = runAabbKernel(ctx, true);  // AABB update + (fused) the grid of this step
+        if (rc) return rc;
+    } else if (!ctx->haloImported) {
+        ctx->err = "partitioned world: b2c_mgpu_update_export_halo and b2c_mgpu_import_halo must precede the pair calculation";
+        return B2C_ERR_STATE;
+    }
+    ctx->haloImported = false;
     ctx->cur ^= 1;
     const int cur = ctx->cur;
     cudaStream_t s = ctx->stream;
@@ -375,23 +406,28 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
         ctx->pairsValid = true;
         return B2C_OK;
     }
-    unsigned nb = (n + 255) / 256;
+    // proxies this pair calculation sorts: all slots, or (partitioned world) the local list whose length lives on the device
+    const uint32_t nUpper = slabUpper(ctx);
+    const uint32_t* nPtr = slab ? ctx->dNLocal : nullptr;
+    const uint32_t* list = slab ? ctx->dLocalList : nullptr;
+    const unsigned nb = gridFor(nUpper, 256, 148 * 16);
     mark(ctx, 1);
-    k_bounds<<<nb, 256, 0, s>>>(ctx->B, n, ctx->cfg.broadphase_mode, ctx->dStep, ctx->cfg.num_worlds,
-                                ctx->maxRows - ctx->cfg.num_worlds, ctx->dCtr, ctx->dGrid);
-    k_keys<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dStep);
-    int rowBits = bitsFor((uint32_t)ctx->maxRows + 2u);
+    if (slab) {  // the grid over the local list (the halo arrived after k_aabb)
+        k_bounds<<<gridFor(nUpper, 256, 148 * 4), 256, 0, s>>>(ctx->B, list, nPtr, ctx->cfg.num_worlds, ctx->maxRows - ctx->cfg.num_worlds,
+                                                              ctx->dCtr, ctx->dGrid);
+        ctx->launches++;
+    }
+    int npass = (12 + bitsFor((uint32_t)ctx->maxRows + 2u) + 7) / 8;
+    if (npass > 4) npass = 4;
+    CK(ctx->sortBodies.reset(nUpper, (uint32_t)n, npass, s));
+    k_keys<<<nb, 256, 0, s>>>(ctx->B, n, nPtr, list, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dStep, ctx->sortBodies.st,
+                              npass);
     mark(ctx, 2);
     ctx->sortBodies.launches = 0;
-    ctx->sortBodies.sort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nullptr, (uint32_t)n,
-                                         12 + rowBits, ctx->dSide, s);
+    ctx->sortBodies.passes<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nUpper, npass, s);
     mark(ctx, 3);
-    k_gather<<<nb, 256, 0, s>>>(ctx->B, n, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->dSide, ctx->dGrid,
-                                ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dScyz);
-    // this rank's slice of the sorted proxy list (the whole list when the world is not partitioned)
-    const int partLo = (int)((long long)n * ctx->partRank / ctx->partRanks);
-    const int partHi = (int)((long long)n * (ctx->partRank + 1) / ctx->partRanks);
-    dim3 sg((unsigned)((partHi - partLo + 255) / 256 > 0 ? (partHi - partLo + 255) / 256 : 1), 9);
+    k_gather<<<nb, 256, 0, s>>>(ctx->B, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->sortBodies.st, npass, ctx->dGrid,
+                                ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dScyz, ctx->dNSorted);
     uint32_t* rowCnt = ctx->dRowZero;
     uint32_t* rowStatus = ctx->dRowZero + ctx->nRows;
     RowMisc* rowMisc = reinterpret_cast<RowMisc*>(ctx->dRowZero + ctx->nRows + ctx->rowTiles);
@@ -404,18 +440,19 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
         CK(cudaEventRecord(ctx->evFork[2], s));
         CK(cudaStreamWaitEvent(sl, ctx->evFork[2], 0));
     }
-    k_sweep<<<sg, 256, 0, s>>>(n, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid, ctx->uidBits, ctx->dPairKeys, rowCnt,
-                               (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi, ctx->sap.enabled ? ctx->B.leafMin : nullptr,
-                               ctx->sap.enabled ? ctx->B.leafMax : nullptr, ctx->dScyz);
+    k_sweep<<<gridFor(nUpper, 256, 148 * 8), 256, 0, s>>>(ctx->dNSorted, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid,
+                                                          ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, ctx->slab,
+                                                          ctx->sap.enabled ? ctx->B.leafMin : nullptr,
+                                                          ctx->sap.enabled ? ctx->B.leafMax : nullptr, ctx->dScyz);
     // one block column per large proxy (static planes, meshes, big statics; one floor per world in batched scenes): the
     // host sizes the grid from the last count it has read, the kernel strides over whatever there is
     const unsigned perWorld = (unsigned)(n / ctx->cfg.num_worlds + 1);
     const int lhint = ctx->stats.large_proxies > 16 ? ctx->stats.large_proxies : 16;
     dim3 lg(gridFor(perWorld, 256, 64), (unsigned)(lhint < 8192 ? lhint : 8192));
     mark(ctx, 5);
-    k_large<<<lg, 256, 0, sl>>>(n, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
-                               ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, partLo, partHi,
-                               ctx->partRank, ctx->sap.enabled ? ctx->B.leafMin : nullptr, ctx->sap.enabled ? ctx->B.leafMax : nullptr);
+    k_large<<<lg, 256, 0, sl>>>(ctx->dNSorted, ctx->dSmin, ctx->dSmax, ctx->dRowStart, ctx->dGrid, ctx->B.world, ctx->cfg.num_worlds,
+                               ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, ctx->slab,
+                               ctx->sap.enabled ? ctx->B.leafMin : nullptr, ctx->sap.enabled ? ctx->B.leafMax : nullptr);
     if (ctx->overlap) {
         CK(cudaEventRecord(ctx->evJoin[2], sl));
         CK(cudaStreamWaitEvent(s, ctx->evJoin[2], 0));
@@ -448,7 +485,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
                                                                       ctx->dSortedKeys[cur ^ 1], ctx->dNumPairs[cur ^ 1],
                                                                       ctx->dPairFirst[cur ^ 1], ctx->dMHdr[cur ^ 1], ctx->dMPts[cur ^ 1],
                                                                       ctx->dMHdr[cur], ctx->dMPts[cur], ctx->uidBits, ctx->dCtr, ctx->dHist, ctx->dPairFirst[cur]);
-    ctx->launches += 10 + ctx->sortBodies.launches;
+    ctx->launches += 9 + ctx->sortBodies.launches;  // k_keys, k_gather, k_sweep, k_large, 4 pair-row kernels, k_carry (k_aabb counts itself)
     if (ctx->deltaPrefetch) {
         // pair-cache events of this calculation (added / removed pairs), ready together with the pair list so that their
         // download overlaps the narrowphase
@@ -731,6 +768,18 @@ int32_t readCounters(b2c_ctx* ctx) {
         ctx->err = buf;
         return B2C_ERR_CAPACITY;
     }
+    if (ctx->slab.enabled) {
+        uint32_t nl = 0;
+        CK(cudaMemcpyAsync(&nl, ctx->dNLocal, sizeof(nl), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        // re-shape the launches only when the local list has outgrown the bound or shrunk a lot (a new shape = a new graph)
+        const uint32_t up = slabUpper(ctx);
+        if (ctx->localHint == 0 || nl + 1024 > up || (uint64_t)nl * 2 < up) ctx->localHint = nl ? nl : 1;
+    }
+    if (c.haloOverflow) {
+        ctx->err = "partitioned world: halo slot too small";
+        return B2C_ERR_CAPACITY;
+    }
     if (c.migrateOverflow) {
         ctx->err = "partitioned world: manifold migration slot too small";
         return B2C_ERR_CAPACITY;
@@ -766,8 +815,8 @@ static void stepSignature(const b2c_ctx* ctx, int kind, uint64_t sig[4]) {
              ((uint64_t)(ctx->hasMesh ? 1 : 0) << 3) | ((uint64_t)(ctx->overlap ? 1 : 0) << 4) | ((uint64_t)(ctx->aabbPending ? 1 : 0) << 5) |
              ((uint64_t)(uint32_t)kind << 6) | ((uint64_t)(uint32_t)(ctx->epaHint + 1) << 8) | ((uint64_t)(ctx->hasCompound ? 1 : 0) << 10) |
              ((uint64_t)(uint32_t)(ctx->ccur & 1) << 11) | ((uint64_t)(uint32_t)(ctx->contactPrefetch + 1) << 12) | ((uint64_t)(uint32_t)lhint << 16) |
-             ((uint64_t)(uint32_t)ctx->partRank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
-    sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide;
+             ((uint64_t)(uint32_t)ctx->slab.rank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
+    sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide ^ ((uint64_t)slabUpper(ctx) << 40);
     sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8) |
              ((uint32_t)(ctx->deltaPrefetch ? 1 : 0) << 16);
 }
@@ -804,6 +853,10 @@ static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind) {
         ctx->err = "dispatch_all_pairs before calculate_overlapping_pairs";
         return B2C_ERR_STATE;
     }
+    if (broad && ctx->slab.enabled && !ctx->haloImported) {
+        ctx->err = "partitioned world: b2c_mgpu_update_export_halo and b2c_mgpu_import_halo must precede the pair calculation";
+        return B2C_ERR_STATE;
+    }
     const bool graphable = ctx->useGraphs && !ctx->prof && !ctx->timeline && ctx->nBodies > 0;
     if (!graphable) {
         int32_t rc = B2C_OK;
@@ -830,6 +883,7 @@ static int32_t enqueuePhasesImpl(b2c_ctx* ctx, int kind) {
             ctx->step++;
             ctx->pairsValid = true;
             ctx->nSortedBodies = ctx->nBodies;
+            ctx->haloImported = false;
         }
         if (narrow && ctx->hasCompound) ctx->ccur ^= 1;
         if (narrow) ctx->earlyRecorded = ctx->contactPrefetch >= 2;
@@ -1000,10 +1054,12 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dRowZero, (size_t)ctx->nRows + ctx->rowTiles + sizeof(RowMisc) / sizeof(uint32_t) + 8));
     CKC(dalloc(&ctx->dBigRows, (size_t)ctx->nRows));
     CKC(dalloc(&ctx->dSide, (size_t)4));
-    CKC(dalloc(&ctx->dSmin, N));
-    CKC(dalloc(&ctx->dSmax, N));
-    CKC(dalloc(&ctx->dSrow, N));
+    CKC(dalloc(&ctx->dSmin, N + SW_CH));   // + SW_CH: the sweep stages whole chunks (pairfind.cuh)
+    CKC(dalloc(&ctx->dSmax, N + SW_CH));
+    CKC(dalloc(&ctx->dSrow, N + SW_CH));
     CKC(dalloc(&ctx->dScyz, N));
+    CKC(dalloc(&ctx->dNSorted, (size_t)4));
+    CKC(dalloc(&ctx->dNLocal, (size_t)4));
     ctx->maxRows = (int)(2 * N + 64 > (size_t)(64 * cfg->num_worlds) ? 2 * N + 64 : (size_t)(64 * cfg->num_worlds));
     if (ctx->maxRows > (1 << 20) - 4) ctx->maxRows = (1 << 20) - 4;  // the row shares a 32-bit key with 12 bits of x
     if ((long long)cfg->num_worlds * 5 > ctx->maxRows) return fail(B2C_ERR_BAD_ARG);
@@ -1071,6 +1127,7 @@ void b2c_destroy(b2c_ctx* ctx) {
         cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dSortedKeys[i]);
         cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dMHdr[i]); cudaFree(ctx->dMPts[i]); cudaFree(ctx->dPairFirst[i]);
     }
+    cudaFree(ctx->dNSorted); cudaFree(ctx->dNLocal); cudaFree(ctx->dOwner); cudaFree(ctx->dLocalList);
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dScyz); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
@@ -2140,23 +2197,149 @@ const char* b2c_stage_name(int32_t k) {
     return (k >= 0 && k < B2C_NUM_STAGES) ? names[k] : "";
 }
 
-int32_t b2c_set_partition(b2c_ctx* ctx, int32_t rank, int32_t nranks) {
-    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return B2C_ERR_BAD_ARG;
+// Slab partition along `axis` with explicit planes (ascending, nranks - 1 of them).  Call it on every rank after the proxies
+// exist and while all ranks hold the same transforms: the owner table is derived from the resident origins.
+int32_t b2c_set_partition_slabs(b2c_ctx* ctx, int32_t rank, int32_t nranks, int32_t axis, const float* planes) {
+    if (!ctx || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || axis < 0 || axis > 2) return B2C_ERR_BAD_ARG;
+    if (nranks > 1 && !planes) return B2C_ERR_BAD_ARG;
     if (nranks > 1 && ctx->hasCompound) {  // child manifolds do not migrate between ranks (compound.cuh)
         ctx->err = "compound shapes are not supported in a partitioned world";
         return B2C_ERR_STATE;
     }
-    ctx->partRank = rank;
+    for (int k = 1; k < nranks - 1; k++)
+        if (!(planes[k] >= planes[k - 1])) { ctx->err = "partition planes must ascend"; return B2C_ERR_BAD_ARG; }
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    dropStepGraphs(ctx);
+    ctx->slab = SlabFilter{};
     ctx->partRanks = nranks;
+    ctx->localHint = 0;
+    ctx->haloExported = ctx->haloImported = false;
+    if (nranks == 1) return B2C_OK;
+    if (ctx->stagingCount || ctx->extPending) {  // transforms uploaded but not yet repacked: the owner table reads the rows
+        int32_t rc = runAabbKernel(ctx, false);
+        if (rc) return rc;
+    }
+    const size_t N = (size_t)ctx->cfg.max_bodies;
+    if (!ctx->dOwner) CK(dalloc(&ctx->dOwner, N));
+    if (!ctx->dLocalList) CK(dalloc(&ctx->dLocalList, N));
+    SlabFilter f{};
+    f.enabled = 1; f.axis = axis; f.rank = rank; f.nplanes = nranks - 1;
+    for (int k = 0; k < nranks - 1; k++) f.planes[k] = planes[k];
+    if (ctx->nBodies > 0) {
+        k_assign_owner<<<(ctx->nBodies + 255) / 256, 256, 0, ctx->stream>>>(ctx->B, ctx->nBodies, f, ctx->dOwner);
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->slab = f;
+    return B2C_OK;
+}
+
+// The same with planes chosen here: slabs along the axis the proxy origins spread most over, cut at equal-count quantiles
+// of the origins (identical on every rank, because all ranks hold the same transforms when they call it).
+int32_t b2c_set_partition(b2c_ctx* ctx, int32_t rank, int32_t nranks) {
+    if (!ctx || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) return B2C_ERR_BAD_ARG;
+    if (nranks == 1) return b2c_set_partition_slabs(ctx, 0, 1, 0, nullptr);
+    cudaSetDevice(ctx->device);
+    if (ctx->stagingCount || ctx->extPending) {
+        int32_t rc = runAabbKernel(ctx, false);
+        if (rc) return rc;
+    }
+    const int n = ctx->nBodies;
+    std::vector<float4> rows(3 * (size_t)(n > 0 ? n : 1));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(rows.data(), ctx->B.xf4, 3 * (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    int axis = 0;
+    std::vector<float> best;
+    double bestSpan = -1.0;
+    for (int a = 0; a < 3; a++) {
+        std::vector<float> v;
+        v.reserve((size_t)n);
+        for (int i = 0; i < n; i++)
+            if ((ctx->hFlags[i] & BF_ALIVE) && !(ctx->hFlags[i] & BF_STATIC)) {
+                const float o = rows[3 * (size_t)i + a].w;
+                if (o == o && std::fabs(o) < 1e29f) v.push_back(o);
+            }
+        if (v.empty()) continue;
+        std::sort(v.begin(), v.end());
+        const double span = (double)v.back() - (double)v.front();
+        if (span > bestSpan) { bestSpan = span; axis = a; best.swap(v); }
+    }
+    float planes[15];
+    for (int k = 0; k < nranks - 1; k++) {
+        if (best.empty()) { planes[k] = (float)k; continue; }
+        const size_t idx = (size_t)(((unsigned long long)best.size() * (unsigned)(k + 1)) / (unsigned)nranks);
+        planes[k] = best[idx < best.size() ? idx : best.size() - 1];
+    }
+    return b2c_set_partition_slabs(ctx, rank, nranks, axis, planes);
+}
+
+int32_t b2c_get_partition(b2c_ctx* ctx, int32_t* axis_out, float* planes_out, uint8_t* owner_out, int32_t n) {
+    if (!ctx || n < 0 || n > ctx->nBodies) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled) { ctx->err = "the world is not partitioned"; return B2C_ERR_STATE; }
+    if (axis_out) *axis_out = ctx->slab.axis;
+    if (planes_out) for (int k = 0; k < ctx->slab.nplanes; k++) planes_out[k] = ctx->slab.planes[k];
+    if (owner_out && n) {
+        cudaSetDevice(ctx->device);
+        CK(cudaMemcpyAsync(owner_out, ctx->dOwner, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return B2C_OK;
+}
+
+int64_t b2c_mgpu_halo_slot_bytes(int32_t cap) { return cap < 0 ? 0 : (int64_t)haloSlotBytes((uint32_t)cap); }
+
+// updateAabbs for the proxies this rank owns, then the boundary ones (box not entirely inside the home slab) into `slot`.
+int32_t b2c_mgpu_update_export_halo(b2c_ctx* ctx, void* slot, int32_t cap) {
+    if (!ctx || !slot || cap < 1) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled) { ctx->err = "the world is not partitioned"; return B2C_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    ctx->launches = 0;
+    ctx->aabbPending = true;
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    mark(ctx, 0);
+    int32_t rc = runAabbKernel(ctx, true);  // clears the step counters, k_aabb over the owned proxies
+    if (rc) return rc;
+    CK(cudaMemsetAsync(slot, 0, HALO_HEADER_BYTES, s));
+    if (ctx->nBodies > 0) {
+        k_halo_export<<<(ctx->nBodies + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, (unsigned char*)slot,
+                                                                (uint32_t)cap, ctx->dCtr);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    ctx->haloExported = true;
+    return B2C_OK;
+}
+
+// After the all-gather of the slots: adopt the records that touch this rank's slab and build the step's local list.
+int32_t b2c_mgpu_import_halo(b2c_ctx* ctx, const void* slots, int32_t nslots, int32_t cap) {
+    if (!ctx || !slots || cap < 1 || nslots < 1) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled || nslots != ctx->partRanks) { ctx->err = "halo import: one slot per rank of the partition"; return B2C_ERR_STATE; }
+    if (!ctx->haloExported) { ctx->err = "b2c_mgpu_import_halo before b2c_mgpu_update_export_halo"; return B2C_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->dNLocal, 0, sizeof(uint32_t), s));
+    dim3 grid(gridFor((uint32_t)cap, 256, 148), (unsigned)nslots);
+    k_halo_import<<<grid, 256, 0, s>>>(ctx->B, (const unsigned char*)slots, (uint32_t)cap, ctx->slab, ctx->dLocalList, ctx->dNLocal, ctx->dCtr);
+    if (ctx->nBodies > 0)
+        k_list_owned<<<(ctx->nBodies + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, ctx->dLocalList, ctx->dNLocal);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    ctx->haloExported = false;
+    ctx->haloImported = true;
     return B2C_OK;
 }
 
 int32_t b2c_mgpu_broadphase(b2c_ctx* ctx) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
-    ctx->launches = 0;
-    ctx->aabbPending = true;
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (!ctx->slab.enabled) {  // a partition of one: the plain pair calculation
+        ctx->launches = 0;
+        ctx->aabbPending = true;
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    }
     int32_t rc = enqueuePhases(ctx, 1);
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     return rc;

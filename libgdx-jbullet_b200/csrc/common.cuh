@@ -160,7 +160,10 @@ struct GridParams {
     int nrows;             // numWorlds*ny*nz ; rows nrows + w = large proxies of world w, row nrows + numWorlds = dead slots
     int numWorlds;
     float cellY, cellZ;
-    float x0, invX;        // sweep-axis quantisation: qx = clamp(floor((min.x - x0) * invX), 0, 4095)
+    float x0, invX;        // sweep-axis quantisation: qx = clamp(floor((min.x - x0) * invX), 0, xmaxf)
+    int xbits;             // bits of qx in the sort key (key = row << xbits | qx): 12 when the rows need <= 12 bits, fewer when that
+    uint32_t xmask;        //   keeps the key inside 24 bits (three 8-bit radix passes instead of four)
+    float xmaxf;           // (1 << xbits) - 1 as a float
 };
 
 // Per-step device counters (one 128-byte block, cleared by the first kernel of the step).
@@ -178,7 +181,10 @@ struct StepCounters {
     uint32_t epaRetry;
     uint32_t minXKey, maxXKey;  // sweep-axis bounds of the gridded proxies (min kept complemented)
     uint32_t migrateOverflow;   // partitioned world: a migration slot was too small
-    uint32_t pad[10];
+    uint32_t aabbTicket;        // last-block election in k_aabb (fused bounds -> grid)
+    uint32_t keysTicket;        // last-block election in k_keys (fused radix histograms -> digit offsets)
+    uint32_t haloOverflow;      // partitioned world: a halo slot was too small
+    uint32_t pad[7];
 };
 
 // monotone float <-> uint key (total order matching float compare for non-NaN; -0 canonicalised to +0)

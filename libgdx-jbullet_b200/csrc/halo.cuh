@@ -1,0 +1,134 @@
+// halo.cuh — one world partitioned over several GPUs by slabs of space (BASELINE config C5; device code only).
+//
+// Space is cut by nranks-1 planes along one axis into regions; rank r owns region r.  Two kinds of ownership:
+//   * a PROXY is owned by the rank whose region held its origin when the partition was set (b2c_set_partition_slabs).  Only
+//     the owner runs updateAabbs / the DbvtBroadphase.setAabb state machine for it, so that state never has to move.
+//   * a PAIR is owned by the region that holds max(min_a, min_b) along the axis (SlabFilter::owns) — a coordinate inside both
+//     boxes, so both proxies touch that region.
+// Every step each rank therefore needs the AABBs of all proxies that TOUCH its region: its own, plus the HALO — proxies
+// owned elsewhere whose box reaches into the region.  The owners publish exactly those (box not entirely inside the home
+// region) as 80-byte records {min | proxy, max | flags, 3 transform rows} in a fixed-size slot; ONE all-gather over NVLink
+// (ncclAllGather, enqueued by the host binding on the ctx stream) hands every rank all slots; each rank keeps the records
+// that touch its region (k_halo_import) and sorts / sweeps its local list = owned-and-touching + imported.  The transform
+// travels with the box because the narrowphase of a cross-boundary pair runs on the pair's owner.
+#pragma once
+#include "pairfind.cuh"
+
+namespace b2c {
+
+struct HaloRecord {
+    float4 mn;      // effective AABB min | proxy index
+    float4 mx;      // effective AABB max | flags
+    float4 xf[3];   // world transform rows
+};  // 80 bytes
+constexpr int HALO_HEADER_BYTES = 16;  // { uint32 count, pad[3] }
+
+__host__ __device__ inline size_t haloSlotBytes(uint32_t cap) { return (size_t)HALO_HEADER_BYTES + (size_t)cap * sizeof(HaloRecord); }
+
+__device__ __forceinline__ float axisOf(float4 v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+
+// owner[i] = region of the proxy's origin (all ranks run this on identical transforms -> identical tables)
+__global__ void __launch_bounds__(256)
+k_assign_owner(BodyArrays B, int n, SlabFilter slab, uint8_t* __restrict__ owner) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 r = B.xf4[3 * (size_t)i + slab.axis];  // row `axis` of the transform: .w is the origin coordinate
+    owner[i] = (uint8_t)slab.region(r.w);
+}
+
+// Owned proxies whose box is not entirely inside the home region go into this rank's slot.
+__global__ void __launch_bounds__(256)
+k_halo_export(BodyArrays B, int n, const uint8_t* __restrict__ owner, SlabFilter slab, unsigned char* __restrict__ slot, uint32_t cap,
+              StepCounters* ctr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool send = false;
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    uint8_t flags = 0;
+    if (i < n && owner[i] == (uint8_t)slab.rank) {
+        flags = B.flags[i];
+        if (flags & BF_ALIVE) {
+            a = B.effMin[i];
+            b = B.effMax[i];
+            const int lo = slab.region(axisOf(a, slab.axis)), hi = slab.region(axisOf(b, slab.axis));
+            send = !(lo == slab.rank && hi == slab.rank);
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, send);
+    if (m == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(reinterpret_cast<uint32_t*>(slot), (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (send) {
+        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) {
+            HaloRecord* r = reinterpret_cast<HaloRecord*>(slot + HALO_HEADER_BYTES) + pos;
+            a.w = __uint_as_float((uint32_t)i);
+            b.w = __uint_as_float((uint32_t)flags);
+            r->mn = a;
+            r->mx = b;
+            r->xf[0] = B.xf4[3 * (size_t)i];
+            r->xf[1] = B.xf4[3 * (size_t)i + 1];
+            r->xf[2] = B.xf4[3 * (size_t)i + 2];
+        } else {
+            ctr->haloOverflow = 1;
+        }
+    }
+}
+
+// Every record of the other ranks' slots that touches this rank's region becomes a local (halo) proxy: its box, transform
+// and flags are written into the rank's proxy arrays and its index is appended to the local list.
+__global__ void __launch_bounds__(256)
+k_halo_import(BodyArrays B, const unsigned char* __restrict__ slots, uint32_t cap, SlabFilter slab, uint32_t* __restrict__ list,
+              uint32_t* __restrict__ nLocal, StepCounters* ctr) {
+    const int src = blockIdx.y;
+    if (src == slab.rank) return;  // own slot: those proxies are listed by k_list_owned
+    const unsigned char* slot = slots + (size_t)src * haloSlotBytes(cap);
+    uint32_t cnt = *reinterpret_cast<const uint32_t*>(slot);
+    if (cnt > cap) { if (threadIdx.x == 0 && blockIdx.x == 0) ctr->haloOverflow = 1; cnt = cap; }
+    const HaloRecord* recs = reinterpret_cast<const HaloRecord*>(slot + HALO_HEADER_BYTES);
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < cnt; base += gridDim.x * blockDim.x) {
+        const uint32_t k = base + lane;
+        bool take = false;
+        HaloRecord r;
+        if (k < cnt) {
+            r = recs[k];
+            take = slab.touches(axisOf(r.mn, slab.axis), axisOf(r.mx, slab.axis), slab.rank);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        if (m == 0) continue;
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(nLocal, (uint32_t)__popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+        if (take) {
+            const uint32_t i = __float_as_uint(r.mn.w);
+            B.effMin[i] = make_float4(r.mn.x, r.mn.y, r.mn.z, 0.f);
+            B.effMax[i] = make_float4(r.mx.x, r.mx.y, r.mx.z, 0.f);
+            B.flags[i] = (uint8_t)__float_as_uint(r.mx.w);
+            B.xf4[3 * (size_t)i] = r.xf[0];
+            B.xf4[3 * (size_t)i + 1] = r.xf[1];
+            B.xf4[3 * (size_t)i + 2] = r.xf[2];
+            list[pos] = i;
+        }
+    }
+}
+
+// Owned proxies that touch the home region (all but the ones that have drifted out of it entirely).
+__global__ void __launch_bounds__(256)
+k_list_owned(BodyArrays B, int n, const uint8_t* __restrict__ owner, SlabFilter slab, uint32_t* __restrict__ list,
+             uint32_t* __restrict__ nLocal) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool take = false;
+    if (i < n && owner[i] == (uint8_t)slab.rank && (B.flags[i] & BF_ALIVE))
+        take = slab.touches(axisOf(B.effMin[i], slab.axis), axisOf(B.effMax[i], slab.axis), slab.rank);
+    const uint32_t m = __ballot_sync(0xffffffffu, take);
+    if (m == 0) return;
+    uint32_t pos = 0;
+    if (lane == 0) pos = atomicAdd(nLocal, (uint32_t)__popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+    if (take) list[pos] = (uint32_t)i;
+}
+
+}  // namespace b2c

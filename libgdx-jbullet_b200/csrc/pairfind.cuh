@@ -1,0 +1,475 @@
+// pairfind.cuh — stage 1 of the path, overlap-pair finding over the effective AABBs (device code only).
+//
+// Replaces bp/DbvtBroadphase.java:89-150 collide / bp/SimpleBroadphase.java:81-110 / the AxisSweep3 edge sort: the pair
+// set is "all filtered overlaps of the per-proxy effective AABBs" (DESIGN.md §1), rebuilt from scratch every step:
+//   k_keys     32-bit key = row << xbits | qx per proxy (row = coarse (y, z) grid cell, qx = quantised min.x), the radix
+//              histograms of all digits in the same pass, and (last block) their exclusive scans          [fused rs_hist / rs_scan]
+//   rs_pass    one onesweep pass per 8-bit digit (radix_sort.cuh); constant digits are skipped on the device
+//   k_gather   sorted AABB SoA (float4 min | proxy, float4 max | filter), sorted keys, row start table
+//   k_sweep    each warp takes 32 consecutive sorted proxies; for each of the 9 neighbour rows the UNION of their x-windows
+//              is a contiguous piece of the sorted arrays, staged once per warp in shared memory with 1-D bulk copies (TMA,
+//              cp.async.bulk + mbarrier); every lane then finds and walks its own window in shared memory
+//   k_large    proxies that do not fit the grid (planes, meshes, big statics) against everything in their world
+// Pairs are emitted through PairStager (ballot/popc compaction, one global atomic per block) in arbitrary order and put into
+// canonical (uid0, uid1) order by pair_rows.cuh.
+#pragma once
+#include "broadphase.cuh"
+#include "radix_sort.cuh"
+
+namespace b2c {
+
+// One world partitioned over several GPUs by slabs along `axis`: planes[0..nplanes) ascending, region r is
+// [planes[r-1], planes[r]).  A pair belongs to the region that holds max(min_a[axis], min_b[axis]) — a coordinate that lies
+// inside BOTH boxes, so the owning rank holds both proxies (owned or halo).
+struct SlabFilter {
+    int enabled, axis, rank, nplanes;
+    float planes[15];
+    __device__ __forceinline__ int region(float v) const {
+        int r = 0;
+        for (int k = 0; k < nplanes; k++) r += (v >= planes[k]) ? 1 : 0;
+        return r;
+    }
+    __device__ __forceinline__ bool owns(float4 amin, float4 bmin) const {
+        if (!enabled) return true;
+        const float a = axis == 0 ? amin.x : (axis == 1 ? amin.y : amin.z);
+        const float b = axis == 0 ? bmin.x : (axis == 1 ? bmin.y : bmin.z);
+        return region(fmaxf(a, b)) == rank;
+    }
+    // does the box [mn, mx] touch region r?
+    __device__ __forceinline__ bool touches(float mn, float mx, int r) const {
+        const int lo = region(mn), hi = region(mx);
+        return r >= lo && r <= hi;
+    }
+};
+
+// k_keys: key and payload of every proxy of the step (list == null: slots 0..n-1), with the histograms of the four radix digits.
+// The last block to finish turns the histograms into exclusive digit offsets and the skip flags (a digit with a single
+// non-empty bin is the identity), so no separate histogram / scan launch is needed.  `st` was cleared by a memset node.
+__global__ void __launch_bounds__(256)
+k_keys(BodyArrays B, int nConst, const uint32_t* __restrict__ nPtr, const uint32_t* __restrict__ list, StepCounters* ctr,
+       const GridParams* __restrict__ grid, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* stepPtr, RadixState* st,
+       int npass) {
+    __shared__ uint32_t sh[4][256];
+    __shared__ bool isLast;
+    for (int k = threadIdx.x; k < 4 * 256; k += 256) (&sh[0][0])[k] = 0;
+    __syncthreads();
+    const uint32_t n = nPtr ? *nPtr : (uint32_t)nConst;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *stepPtr = *stepPtr + 1;  // k_aabb of this step has read it (stream order)
+    const GridParams g = *grid;
+    const float limitY = __uint_as_float(ctr->extYBits), limitZ = __uint_as_float(ctr->extZBits);
+    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n; t += gridDim.x * 256) {
+        const uint32_t i = list ? list[t] : t;
+        const uint8_t flags = B.flags[i];
+        uint32_t row, xk = 0;
+        if (!(flags & BF_ALIVE)) {
+            row = (uint32_t)(g.nrows + g.numWorlds);  // dead slots sort behind everything
+        } else {
+            const float4 a = B.effMin[i], b = B.effMax[i];
+            const float ey = b.y - a.y, ez = b.z - a.z;
+            // too large for a cell (only statics can be: the cell is the largest non-static extent) or not finite
+            const bool large = !(ey <= limitY) || !(ez <= limitZ) || !(fabsf(a.y) < 1e29f) || !(fabsf(a.z) < 1e29f) || !(fabsf(a.x) < 1e29f);
+            if (large) {
+                row = (uint32_t)(g.nrows + B.world[i]);  // one row of large proxies per world
+            } else {
+                const int cy = cellOf(a.y, g.y0, g.invCellY, g.ny), cz = cellOf(a.z, g.z0, g.invCellZ, g.nz);
+                row = (uint32_t)(B.world[i] * g.rowsPerWorld + cy * g.nz + cz);
+            }
+            xk = quantX(a.x, g.x0, g.invX, g.xmaxf);
+        }
+        const uint32_t key = (row << g.xbits) | xk;
+        keys[t] = key;
+        vals[t] = i;
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+            if (p < npass) atomicAdd(&sh[p][(key >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < npass * 256; k += 256) {
+        const uint32_t v = (&sh[0][0])[k];
+        if (v) atomicAdd(&(&st->hist[0][0])[k], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) isLast = atomicAdd(&ctr->keysTicket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    // exclusive scan of the 256 bins of every digit (one digit after the other; 256 threads = 256 bins)
+    if (threadIdx.x == 0) st->n = n;
+    for (int p = 0; p < npass; p++) {
+        uint32_t* s = sh[0];
+        const uint32_t v = *(volatile uint32_t*)&st->hist[p][threadIdx.x];
+        s[threadIdx.x] = v;
+        __syncthreads();
+        const bool full = (v == n);  // covers n == 0 as well
+        for (int off = 1; off < 256; off <<= 1) {
+            const uint32_t tv = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
+            __syncthreads();
+            s[threadIdx.x] += tv;
+            __syncthreads();
+        }
+        st->hist[p][threadIdx.x] = s[threadIdx.x] - v;
+        if (__syncthreads_or(full ? 1 : 0) && threadIdx.x == 0) st->skip[p] = 1u;
+        __syncthreads();
+    }
+}
+
+// k_gather: sorted AABB SoA for 128-bit / bulk loads in the sweep, and the row start table.
+//   smin[j] = (min.x, min.y, min.z, bodyIndex) ; smax[j] = (max.x, max.y, max.z, filter)
+// rowStart[r] = first sorted index whose row >= r (rows without proxies get the next row's start).
+__global__ void __launch_bounds__(256)
+k_gather(BodyArrays B, const uint32_t* keysA, const uint32_t* keysB, const uint32_t* valsA, const uint32_t* valsB,
+         const RadixState* __restrict__ st, int npass, const GridParams* __restrict__ grid, float4* __restrict__ smin,
+         float4* __restrict__ smax, uint32_t* __restrict__ skey, uint32_t* __restrict__ rowStart, uint32_t* __restrict__ scyz,
+         uint32_t* __restrict__ nSortedOut) {
+    const uint32_t n = st->n;
+    const int side = rs_side_before(st, npass);  // which ping-pong side the executed passes left the data in
+    const uint32_t* keys = side ? keysB : keysA;
+    const uint32_t* vals = side ? valsB : valsA;
+    const int xbits = grid->xbits;
+    const uint32_t nrows = (uint32_t)grid->nrows, rpw = (uint32_t)grid->rowsPerWorld, nz = (uint32_t)grid->nz;
+    const uint32_t lastRow = (uint32_t)(grid->nrows + grid->numWorlds) + 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *nSortedOut = n;
+        if (n == 0)
+            for (uint32_t r = 0; r <= lastRow; r++) rowStart[r] = 0;
+    }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t k = keys[j];
+        const uint32_t row = k >> xbits;
+        const uint32_t body = vals[j];
+        float4 a = B.effMin[body], b = B.effMax[body];
+        a.w = __uint_as_float(body);
+        b.w = __uint_as_float(B.filt[body]);
+        smin[j] = a;
+        smax[j] = b;
+        skey[j] = k;
+        // cell coordinates of the row, once per proxy; 0xffffffff marks the rows outside the grid (large proxies, dead slots)
+        uint32_t c = 0xffffffffu;
+        if (row < nrows) {
+            const uint32_t rem = row % rpw;
+            c = ((rem / nz) << 16) | (rem % nz);
+        }
+        scyz[j] = c;
+        const uint32_t prev = j ? (keys[j - 1] >> xbits) : 0xffffffffu;
+        if (j == 0) {
+            for (uint32_t r = 0; r <= row; r++) rowStart[r] = 0;
+        } else if (prev != row) {
+            for (uint32_t r = prev + 1; r <= row; r++) rowStart[r] = j;
+        }
+        if (j == n - 1)
+            for (uint32_t r = row + 1; r <= lastRow; r++) rowStart[r] = n;
+    }
+}
+
+// Warp-staged pair append.  A single global counter cannot take one atomic per warp round (same-address
+// atomics serialise in L2), so every warp stages its hits in a private shared-memory buffer (ballot + popc for the slot) and
+// flushes 32+ pairs at a time with ONE global atomic and coalesced 8-byte stores.
+constexpr int PAIR_STAGE = 96;  // per-warp staging capacity (flush when > 64 are waiting)
+
+struct PairStager {
+    uint64_t* buf;      // this warp's shared-memory slice
+    uint32_t* rowCnt;   // pairs per uid0 so far this step: the atomicAdd's return value is the pair's slot in its row
+    int count;          // warp-uniform
+    int uidBits;
+    __device__ __forceinline__ void init(uint64_t* warpBuf, uint32_t* rowCounters, int bits) {
+        buf = warpBuf; rowCnt = rowCounters; count = 0; uidBits = bits;
+    }
+    __device__ __forceinline__ void flush(uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr) {
+        if (count == 0) return;
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->pairCount, (uint32_t)count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int k = lane; k < count; k += 32) {
+            uint32_t pos = base + k;
+            if (pos < maxPairs) {
+                uint64_t key = buf[k];
+                uint32_t slot = atomicAdd(&rowCnt[(uint32_t)(key >> uidBits)], 1u);
+                pairKeys[pos] = key | ((uint64_t)slot << (2 * uidBits));  // pair_rows.cuh: slot | uid0 | uid1
+            } else {
+                ctr->pairOverflow = 1;
+            }
+        }
+        __syncwarp();
+        count = 0;
+    }
+    // Final flush of a 256-thread block: the eight warps reserve their output range with ONE atomic on the shared pair
+    // counter.  Every thread of the block must call it.
+    __device__ __forceinline__ void flushBlock(uint64_t* __restrict__ pairKeys, uint32_t maxPairs, StepCounters* ctr,
+                                               uint32_t* sCnt /*[8]*/, uint32_t* sBase) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) sCnt[warp] = (uint32_t)count;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { uint32_t c = sCnt[w]; sCnt[w] = tot; tot += c; }
+            *sBase = tot ? atomicAdd(&ctr->pairCount, tot) : 0u;
+        }
+        __syncthreads();
+        const uint32_t base = *sBase + sCnt[warp];
+        for (int k = lane; k < count; k += 32) {
+            uint32_t pos = base + k;
+            if (pos < maxPairs) {
+                uint64_t key = buf[k];
+                uint32_t slot = atomicAdd(&rowCnt[(uint32_t)(key >> uidBits)], 1u);
+                pairKeys[pos] = key | ((uint64_t)slot << (2 * uidBits));
+            } else {
+                ctr->pairOverflow = 1;
+            }
+        }
+        count = 0;
+    }
+    // all 32 lanes call this together
+    __device__ __forceinline__ void push(bool hit, uint32_t bodyA, uint32_t bodyB, uint64_t* __restrict__ pairKeys,
+                                         uint32_t maxPairs, StepCounters* ctr) {
+        uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m == 0) return;
+        if (hit) {
+            int lane = threadIdx.x & 31;
+            uint32_t ua = bodyA + 1u, ub = bodyB + 1u;  // uid = slot + 1 (bp/DbvtBroadphase.java:179)
+            uint32_t lo = ua < ub ? ua : ub, hi = ua < ub ? ub : ua;  // bp/HashedOverlappingPairCache.java:292-296
+            buf[count + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)lo << uidBits) | hi;
+        }
+        count += __popc(m);
+        if (count > PAIR_STAGE - 32) flush(pairKeys, maxPairs, ctr);
+    }
+};
+
+// ---- 1-D bulk copies (TMA) into shared memory, completion on an mbarrier --------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smemAddr(bar)), "r"(parity)
+        : "memory");
+}
+// size: multiple of 16 bytes; src and dst 16-byte aligned
+__device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+constexpr int SW_CH = 64;     // sorted entries staged per chunk and warp
+constexpr int SW_WARPS = 8;
+struct __align__(128) SweepStage {
+    float4 mn[SW_CH];
+    float4 mx[SW_CH];
+    uint32_t key[SW_CH];
+};
+
+// k_sweep: every warp owns 32 consecutive SORTED proxies (lane = proxy).  For each of the 9 neighbour rows (dy, dz) a lane's
+// candidates are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)] — its x-window in
+// that row.  The lanes' windows are close together (consecutive proxies of one row, or of a few consecutive rows when the
+// rows are short), so their union [lo, hi) is a short contiguous range of the sorted arrays: it is staged chunk by chunk in
+// the warp's shared-memory buffer with three bulk copies (min, max, key) completing on the warp's mbarrier, and each lane
+// then binary-searches its own start inside the chunk and walks its window from shared memory.  The lanes advance in lock
+// step only for the ballot/popc compaction of hits.  The pair is emitted by the member that comes first in (qx, sorted
+// position) order, so every overlapping pair is produced exactly once; the overlap test is the reference's closed-interval
+// predicate on the original floats (bp/DbvtAabbMm.java:209-212), the keys only select candidates.
+// The sorted arrays are padded by SW_CH entries, so a chunk may read past n (never past the allocation); whatever it stages
+// there is rejected by the key window.
+__global__ void __launch_bounds__(256)
+k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, const float4* __restrict__ smax,
+        const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
+        uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, SlabFilter slab,
+        const float4* __restrict__ qmin, const float4* __restrict__ qmax /* SAP modes: quantised bounds per body, else null */,
+        const uint32_t* __restrict__ scyz) {
+    __shared__ SweepStage stage[SW_WARPS];
+    __shared__ uint64_t bars[SW_WARPS];
+    __shared__ uint64_t pstage[SW_WARPS][PAIR_STAGE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SweepStage& S = stage[warp];
+    uint64_t* bar = &bars[warp];
+    if (lane == 0) {
+        mbarInit(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t parity = 0;
+    PairStager st;
+    st.init(pstage[warp], rowCnt, uidBits);
+    const uint32_t n = *nPtr;
+    const int ny = grid->ny, nz = grid->nz, xbits = grid->xbits;
+    const uint32_t xmask = grid->xmask;
+    const float gx0 = grid->x0, ginvX = grid->invX, gxmax = grid->xmaxf;
+    for (uint32_t wbase = (blockIdx.x * SW_WARPS + warp) * 32u; wbase < n; wbase += gridDim.x * (SW_WARPS * 32u)) {
+        const uint32_t i = wbase + lane;
+        uint32_t keyI = 0, cc = 0xffffffffu;
+        float4 amin = make_float4(0, 0, 0, 0), amax = amin;
+        if (i < n) {
+            keyI = __ldg(skey + i);
+            cc = __ldg(scyz + i);
+            amin = __ldg(smin + i);
+            amax = __ldg(smax + i);
+        }
+        const bool gridded = cc != 0xffffffffu;
+        if (!__any_sync(0xffffffffu, gridded)) continue;  // a warp of large proxies / dead slots: k_large's business
+        const uint32_t row = keyI >> xbits, xkI = keyI & xmask;
+        const uint32_t xkMax = gridded ? quantX(amax.x, gx0, ginvX, gxmax) : 0u;
+        const int cy0 = (int)(cc >> 16), cz0 = (int)(cc & 0xffffu);
+        for (int nb = 0; nb < 9; nb++) {
+            const int dy = nb / 3 - 1, dz = nb % 3 - 1;
+            const int cy = cy0 + dy, cz = cz0 + dz;
+            const bool act = gridded && cy >= 0 && cy < ny && cz >= 0 && cz < nz;
+            const uint32_t tRow = (uint32_t)((int)row + dy * nz + dz);  // same world: cy stays inside [0, ny)
+            const uint32_t startKey = (tRow << xbits) | xkI, endKey = (tRow << xbits) | xkMax;
+            // union of the lanes' windows: from the first position that can matter to the end of the last target row
+            uint32_t minStart = act ? startKey : 0xffffffffu;
+            uint32_t hi = act ? __ldg(rowStart + tRow + 1) : 0u;
+            for (int o = 16; o > 0; o >>= 1) {
+                minStart = min(minStart, __shfl_xor_sync(0xffffffffu, minStart, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (minStart == 0xffffffffu) continue;  // no lane has this neighbour
+            uint32_t lo;
+            if (nb == 4) {
+                lo = wbase + (uint32_t)(__ffs(__ballot_sync(0xffffffffu, act)) - 1) + 1u;  // same row: everything after the proxy itself
+            } else {
+                // warp-cooperative lower bound of minStart inside its row: 32 probes per round
+                const uint32_t r0 = minStart >> xbits;
+                uint32_t a = __ldg(rowStart + r0), b = __ldg(rowStart + r0 + 1);
+                while (b - a > 32u) {
+                    const uint32_t stepw = (b - a + 31u) / 32u;
+                    const uint32_t pos = a + (uint32_t)lane * stepw;
+                    const bool less = pos < b && __ldg(skey + pos) < minStart;
+                    const uint32_t m = __ballot_sync(0xffffffffu, less);  // a prefix of the lanes (keys are sorted)
+                    const int c = __popc(m);
+                    // the answer lies in (a + (c-1)*stepw, a + c*stepw]
+                    const uint32_t na = c ? a + (uint32_t)(c - 1) * stepw + 1u : a;
+                    const uint32_t nbb = min(b, a + (uint32_t)c * stepw);
+                    a = na;
+                    b = nbb;
+                    if (c == 0) break;
+                }
+                {
+                    const uint32_t pos = a + (uint32_t)lane;
+                    const bool less = pos < b && __ldg(skey + pos) < minStart;
+                    a += (uint32_t)__popc(__ballot_sync(0xffffffffu, less));
+                }
+                lo = a;
+            }
+            bool done = !act;
+            for (uint32_t cs = lo & ~3u; cs < hi; cs += SW_CH) {
+                if (__all_sync(0xffffffffu, done)) break;
+                const uint32_t cv = min((uint32_t)SW_CH, hi - cs);          // valid entries of the chunk
+                const uint32_t cnt = (cv + 3u) & ~3u;                       // staged entries: 16-byte multiples
+                __syncwarp();  // every lane has finished reading the previous chunk
+                if (lane == 0) {
+                    mbarExpectTx(bar, cnt * 36u);
+                    bulkLoad(S.mn, smin + cs, cnt * 16u, bar);
+                    bulkLoad(S.mx, smax + cs, cnt * 16u, bar);
+                    bulkLoad(S.key, skey + cs, cnt * 4u, bar);
+                }
+                mbarWait(bar, parity);
+                parity ^= 1u;
+                // this lane's first candidate in the chunk: lower bound of its start key (binary search in shared memory)
+                uint32_t k = cv;
+                if (!done) {
+                    uint32_t a = 0, b = cv;
+                    while (a < b) {
+                        const uint32_t mid = (a + b) >> 1;
+                        if (S.key[mid] < startKey) a = mid + 1; else b = mid;
+                    }
+                    k = a;
+                    if (nb == 4 && i + 1u > cs + k) k = i + 1u - cs;  // same row: only entries behind the proxy itself
+                    if (k > cv) k = cv;
+                }
+                while (__any_sync(0xffffffffu, !done && k < cv)) {
+                    bool hit = false;
+                    uint32_t bodyB = 0;
+                    if (!done && k < cv) {
+                        const uint32_t kj = S.key[k];
+                        if (kj > endKey) {
+                            done = true;  // window closed
+                        } else {
+                            // ties in qx across rows: only the earlier sorted position emits
+                            if ((kj & xmask) != xkI || cs + k > i) {
+                                const float4 bmin = S.mn[k], bmax = S.mx[k];
+                                hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
+                                      (amin.z <= bmax.z) && (amax.z >= bmin.z) &&
+                                      filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
+                                bodyB = __float_as_uint(bmin.w);
+                                // AxisSweep3 modes: the float boxes are a monotone image of the quantised ones (necessary
+                                // condition); the pair predicate itself is on the quantised values
+                                if (hit && qmin) {
+                                    const uint32_t bodyA = __float_as_uint(amin.w);
+                                    hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
+                                }
+                                if (hit) hit = slab.owns(amin, bmin);
+                            }
+                            k++;
+                        }
+                    }
+                    st.push(hit, __float_as_uint(amin.w), bodyB, pairKeys, maxPairs, ctr);
+                }
+            }
+        }
+    }
+    __shared__ uint32_t sCnt[8];
+    __shared__ uint32_t sBase;
+    st.flushBlock(pairKeys, maxPairs, ctr, sCnt, &sBase);
+}
+
+// k_large: proxies that do not fit the grid (rows nrows + world) against every proxy of the same world, and
+// against each other once.
+__global__ void __launch_bounds__(256)
+k_large(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, const float4* __restrict__ smax,
+        const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, const int* __restrict__ world, int numWorlds,
+        int uidBits, uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, SlabFilter slab,
+        const float4* __restrict__ qmin, const float4* __restrict__ qmax) {
+    __shared__ uint64_t stage[8][PAIR_STAGE];
+    PairStager st;
+    st.init(stage[threadIdx.x >> 5], rowCnt, uidBits);
+    const int nrows = grid->nrows, rpw = grid->rowsPerWorld;
+    const uint32_t l0 = rowStart[nrows], l1 = rowStart[nrows + numWorlds];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctr->largeCount = l1 - l0;
+    for (uint32_t l = l0 + blockIdx.y; l < l1; l += gridDim.y) {
+        float4 amin = __ldg(smin + l), amax = __ldg(smax + l);
+        uint32_t bodyA = __float_as_uint(amin.w);
+        uint32_t lo = 0, hi = l0, lend = l1;
+        if (numWorlds > 1) {
+            int w = world[bodyA];
+            lo = rowStart[w * rpw];
+            hi = rowStart[(w + 1) * rpw];
+            lend = rowStart[nrows + w + 1];
+        }
+        // gridded proxies of the same world, then the large ones of the same world after l
+        uint32_t total = (hi - lo) + (lend - (l + 1));
+        for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < total; t0 += gridDim.x * blockDim.x) {
+            uint32_t t = t0 + threadIdx.x;
+            bool hit = false;
+            uint32_t bodyB = 0;
+            if (t < total) {
+                uint32_t j = t < (hi - lo) ? lo + t : (l + 1) + (t - (hi - lo));
+                float4 bmin = __ldg(smin + j), bmax = __ldg(smax + j);
+                bodyB = __float_as_uint(bmin.w);
+                hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
+                      (amin.z <= bmax.z) && (amax.z >= bmin.z) && filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
+                if (hit && qmin) hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
+                if (hit && numWorlds > 1 && j >= l0) hit = world[bodyB] == world[bodyA];
+                if (hit) hit = slab.owns(amin, bmin);  // partitioned world: the pair's region decides the rank
+            }
+            st.push(hit, bodyA, bodyB, pairKeys, maxPairs, ctr);
+        }
+    }
+    __shared__ uint32_t sCnt[8];
+    __shared__ uint32_t sBase;
+    st.flushBlock(pairKeys, maxPairs, ctr, sCnt, &sBase);
+}
+
+}  // namespace b2c

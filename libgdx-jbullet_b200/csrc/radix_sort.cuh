@@ -2,7 +2,8 @@
 // for the canonical pair list (64-bit packed (uidA,uidB) keys).
 //
 // Design (sm_100a, HBM/L2-bound integer work, no tensor cores):
-//   * one upfront histogram kernel builds all digit histograms in a single read of the keys;
+//   * the digit histograms and their exclusive scans come from the kernel that WRITES the keys (k_keys, pairfind.cuh):
+//     no separate histogram / scan launch and no extra read of the keys;
 //   * one kernel per 8-bit digit ("onesweep"): tiles are taken in ticket order, each tile ranks its
 //     keys with warp-level match-any multisplit, publishes its per-digit counts and resolves its
 //     exclusive prefix by decoupled look-back over the preceding tiles, then scatters through shared
@@ -32,59 +33,6 @@ struct RadixState {
     uint32_t n;                         // number of keys (device-resident so it can come from a counter)
     uint32_t pad[7];
 };
-
-__global__ void rs_reset(RadixState* st, uint32_t* status, size_t statusWords, const uint32_t* nPtr, uint32_t nConst,
-                         uint32_t nCap) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t j = i; j < RS_MAX_PASSES * 256; j += stride) (&st->hist[0][0])[j] = 0;
-    if (i < RS_MAX_PASSES) { st->skip[i] = 0; st->ticket[i] = 0; }
-    if (i == 0) {
-        uint32_t n = nPtr ? *nPtr : nConst;
-        st->n = n < nCap ? n : nCap;
-    }
-    for (; i < statusWords; i += stride) status[i] = 0;
-}
-
-template <typename K>
-__global__ void __launch_bounds__(RS_THREADS) rs_hist(const K* __restrict__ keys, RadixState* st, int npass) {
-    __shared__ uint32_t sh[RS_MAX_PASSES][256];
-    for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += RS_THREADS) (&sh[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t n = st->n;
-    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) {
-        K k = keys[i];
-#pragma unroll
-        for (int p = 0; p < RS_MAX_PASSES; p++)
-            if (p < npass) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) {
-        uint32_t v = (&sh[0][0])[i];
-        if (v) atomicAdd(&(&st->hist[0][0])[i], v);
-    }
-}
-
-// one block per pass: exclusive scan of the 256 bins, and the skip flag
-__global__ void __launch_bounds__(256) rs_scan(RadixState* st, int firstPass) {
-    __shared__ uint32_t s[256];
-    __shared__ uint32_t anyFull;
-    const int p = blockIdx.x;
-    const uint32_t n = st->n;
-    uint32_t v = st->hist[p][threadIdx.x];
-    if (threadIdx.x == 0) anyFull = 0;
-    s[threadIdx.x] = v;
-    __syncthreads();
-    if (v == n) anyFull = 1;  // covers n == 0 as well
-    for (int off = 1; off < 256; off <<= 1) {
-        uint32_t t = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
-        __syncthreads();
-        s[threadIdx.x] += t;
-        __syncthreads();
-    }
-    st->hist[p][threadIdx.x] = s[threadIdx.x] - v;
-    if (threadIdx.x == 0) st->skip[p] = (p < firstPass) ? 1u : anyFull;
-}
 
 __device__ __forceinline__ uint32_t rs_load_acquire(const uint32_t* p) {
     uint32_t v;
@@ -248,34 +196,26 @@ rs_pass(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, RadixState* st, ui
     }
 }
 
-// After all passes: which side holds the sorted data (written to *sideOut) — consumers read it on device.
-__global__ void rs_final_side(const RadixState* st, int npass, uint32_t* sideOut) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *sideOut = (uint32_t)rs_side_before(st, npass);
-}
-
 struct RadixSorter {
     RadixState* st = nullptr;
     uint32_t* status = nullptr;
-    size_t statusWordsPerPass = 0;
+    size_t statusWordsPerPass = 0;   // sized for the smallest tile (most tiles)
     uint32_t capacity = 0;
-    int items = 4;
     int launches = 0;
 
-    static int pickItems(uint32_t cap) {
+    static int pickItems(uint32_t n) {
         const char* e = getenv("B2C_RS_ITEMS");  // tuning knob for experiments
         if (e) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) return v; }
         // measured (profiles/): 1 M keys 0.146 / 0.125 / 0.113 ms with 4 / 8 / 16 keys per thread; 262 k keys best at 8;
         // 100 k keys best at 4 (more tiles than SMs matters more than the length of the look-back chain)
-        return cap >= 600000u ? 16 : (cap >= 200000u ? 8 : 4);
+        return n >= 600000u ? 16 : (n >= 200000u ? 8 : 4);
     }
 
     cudaError_t init(uint32_t cap) {
         capacity = cap;
-        items = pickItems(cap);
-        uint32_t tile = RS_THREADS * items;
-        uint32_t numTiles = (cap + tile - 1) / tile + 1;
-        statusWordsPerPass = (size_t)numTiles * 256;
-        // dynamic shared memory of the wide tiles (> 48 KB needs the opt-in), set once so that sort() only launches
+        const uint32_t tile = RS_THREADS * 4;
+        statusWordsPerPass = (size_t)((cap + tile - 1) / tile + 1) * 256;
+        // dynamic shared memory of the wide tiles (> 48 KB needs the opt-in), set once so that passes() only launches
         cudaFuncSetAttribute(rs_pass<uint32_t, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * RS_THREADS * 16);
         cudaFuncSetAttribute(rs_pass<uint32_t, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * RS_THREADS * 8);
         cudaError_t e = cudaMalloc(&st, sizeof(RadixState));
@@ -289,31 +229,30 @@ struct RadixSorter {
         status = nullptr;
     }
 
-    // Sort n keys (n read from *nPtr on the device if nPtr != null, else nConst).  keyBits bounds the
-    // significant bits.  The sorted data ends in side *sideOut (0: keys0/vals0, 1: keys1/vals1).
+    // Clear the histograms / tickets / skip flags and the look-back status of the tiles `nUpper` keys can occupy (memset
+    // nodes of the step graph).  The kernel that writes the keys then fills st->hist, scans it and sets st->n / st->skip.
+    // nUpper shapes the launches (tile size); nMax bounds the count the device may actually hold (>= nUpper).
+    cudaError_t reset(uint32_t nUpper, uint32_t nMax, int npass, cudaStream_t s) {
+        cudaError_t e = cudaMemsetAsync(st, 0, sizeof(RadixState), s);
+        if (e != cudaSuccess) return e;
+        const uint32_t tile = RS_THREADS * pickItems(nUpper);
+        const size_t words = (size_t)((nMax + tile - 1) / tile + 1) * 256;
+        for (int p = 0; p < npass && e == cudaSuccess; p++)
+            e = cudaMemsetAsync(status + statusWordsPerPass * p, 0, words * sizeof(uint32_t), s);
+        return e;
+    }
+
+    // The onesweep passes over at most nUpper keys (the exact count is st->n on the device).  The sorted data ends on the
+    // side rs_side_before(st, npass) names; consumers read that on the device.
     template <typename K, bool HAS_VAL>
-    void sort(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, const uint32_t* nPtr, uint32_t nConst, int keyBits,
-              uint32_t* sideOut, cudaStream_t s, int firstPass = 0) {
-        int npass = (keyBits + 7) / 8;
-        if (npass < 1) npass = 1;
-        if (npass > RS_MAX_PASSES) npass = RS_MAX_PASSES;
+    void passes(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, uint32_t nUpper, int npass, cudaStream_t s) {
+        const int items = pickItems(nUpper);
         const uint32_t tile = RS_THREADS * items;
-        const uint32_t maxTiles = (capacity + tile - 1) / tile;
-        size_t words = statusWordsPerPass * npass;
-        rs_reset<<<(unsigned)((words + 255) / 256 < 1024 ? (words + 255) / 256 : 1024), 256, 0, s>>>(st, status, words, nPtr,
-                                                                                                     nConst, capacity);
-        uint32_t nUpper = nPtr ? capacity : (nConst < capacity ? nConst : capacity);
-        unsigned hgrid = (nUpper + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
-        if (hgrid < 1) hgrid = 1;
-        if (hgrid > 148 * 4) hgrid = 148 * 4;
-        rs_hist<K><<<hgrid, RS_THREADS, 0, s>>>(keys0, st, npass);
-        rs_scan<<<npass, 256, 0, s>>>(st, firstPass);
         unsigned pgrid = (nUpper + tile - 1) / tile;
         if (pgrid < 1) pgrid = 1;
-        if (pgrid > maxTiles) pgrid = maxTiles ? maxTiles : 1;
         if (pgrid > 148 * 4) pgrid = 148 * 4;
-        size_t dyn = (sizeof(K) + (HAS_VAL ? 4 : 0)) * tile;
-        for (int p = firstPass; p < npass; p++) {
+        const size_t dyn = (sizeof(K) + (HAS_VAL ? 4 : 0)) * tile;
+        for (int p = 0; p < npass; p++) {
             uint32_t* stp = status + statusWordsPerPass * p;
             if (items == 16) {
                 rs_pass<K, HAS_VAL, 16><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
@@ -323,8 +262,7 @@ struct RadixSorter {
                 rs_pass<K, HAS_VAL, 4><<<pgrid, RS_THREADS, dyn, s>>>(keys0, keys1, vals0, vals1, st, stp, p);
             }
         }
-        rs_final_side<<<1, 32, 0, s>>>(st, npass, sideOut);
-        launches += 4 + npass - firstPass;
+        launches += npass;
     }
 };
 

@@ -11,22 +11,40 @@ import numpy as np
 MASK64 = (1 << 64) - 1
 
 
-class PartitionedStepper:
-    """Sequences one partitioned step:  broadphase on this rank's share -> manifolds of pairs that changed owner are packed
-    into a fixed-size slot -> ONE all-gather -> adoption -> narrowphase on the pairs this rank owns."""
+def default_halo_cap(n_bodies):
+    """Records per halo slot: the proxies within one box of a slab face — a few N^(2/3) for a compact world."""
+    return max(4096, int(3.5 * float(n_bodies) ** (2.0 / 3.0)))
 
-    def __init__(self, gw, rank, nranks, dist, torch, dev, migrate_cap=8192):
+
+class PartitionedStepper:
+    """Sequences one partitioned step (include/b2c.h, last section):
+        updateAabbs of the owned proxies + boundary proxies into this rank's halo slot
+        -> ONE all-gather of the halo slots (boundary AABBs + transforms, NVLink)
+        -> adoption of the records that touch this rank's slab, pair calculation over the local list
+        -> manifolds of pairs that changed owner into a small migration slot -> ONE all-gather -> adoption
+        -> narrowphase on the pairs this rank owns.
+    planes = None lets the library cut the world at equal-count quantiles along its longest axis."""
+
+    def __init__(self, gw, rank, nranks, dist, torch, dev, migrate_cap=2048, halo_cap=None, axis=None, planes=None):
         self.gw, self.rank, self.nranks, self.dist, self.torch = gw, rank, nranks, dist, torch
         self.stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
         self.mcap = int(migrate_cap)
-        gw.set_partition(rank, nranks)
+        self.hcap = int(halo_cap) if halo_cap else default_halo_cap(gw.num_bodies)
+        if planes is None:
+            gw.set_partition(rank, nranks)
+        else:
+            gw.set_partition_slabs(rank, nranks, axis, planes)
         self.slot_bytes = gw.mgpu_slot_bytes(self.mcap)
-        self.my_slot = torch.zeros(self.slot_bytes, dtype=torch.uint8, device=f"cuda:{dev}")
-        self.all_slots = torch.zeros(self.slot_bytes * nranks, dtype=torch.uint8, device=f"cuda:{dev}")
-        self.extra_launches = 0   # kernels outside b2c_stats.kernel_launches are counted by the library itself
+        self.halo_bytes = gw.mgpu_halo_slot_bytes(self.hcap)
+        d = f"cuda:{dev}"
+        self.my_slot = torch.zeros(self.slot_bytes, dtype=torch.uint8, device=d)
+        self.all_slots = torch.zeros(self.slot_bytes * nranks, dtype=torch.uint8, device=d)
+        self.my_halo = torch.zeros(self.halo_bytes, dtype=torch.uint8, device=d)
+        self.all_halo = torch.zeros(self.halo_bytes * nranks, dtype=torch.uint8, device=d)
+        self.extra_launches = 0   # every kernel of a partitioned step is counted by the library (b2c_stats.kernel_launches)
 
     def all_gather(self, out, inp):
-        """One NCCL all-gather on the world's stream; with a single rank (tests on one device) it is a copy."""
+        """One NCCL all-gather on the world's stream; with a single rank it is a copy."""
         torch = self.torch
         with torch.cuda.stream(self.stream):
             if self.dist is not None and self.nranks > 1:
@@ -36,6 +54,9 @@ class PartitionedStepper:
 
     def step(self):
         gw = self.gw
+        gw.mgpu_update_export_halo(self.my_halo.data_ptr(), self.hcap)
+        self.all_gather(self.all_halo, self.my_halo)
+        gw.mgpu_import_halo(self.all_halo.data_ptr(), self.nranks, self.hcap)
         gw.mgpu_broadphase()
         gw.mgpu_export_departed_slot(self.my_slot.data_ptr(), self.mcap)
         self.all_gather(self.all_slots, self.my_slot)
@@ -43,11 +64,12 @@ class PartitionedStepper:
         gw.mgpu_narrowphase()
 
     def describe(self):
-        return (f"ncclAllGather of one {self.slot_bytes}-byte migration slot per rank per step ({self.mcap} manifolds of pairs "
-                f"that changed owner; {self.slot_bytes * self.nranks} bytes gathered per rank)")
+        return (f"slab partition, 2 ncclAllGather per step: halo slots ({self.hcap} x 80-byte boundary-proxy records = "
+                f"{self.halo_bytes} B per rank, {self.halo_bytes * self.nranks} B gathered) and manifold-migration slots "
+                f"({self.mcap} manifolds = {self.slot_bytes} B per rank, {self.slot_bytes * self.nranks} B gathered)")
 
     def close(self):
-        self.my_slot = self.all_slots = None
+        self.my_slot = self.all_slots = self.my_halo = self.all_halo = None
 
 
 def _mix(h):

@@ -245,6 +245,28 @@ class GpuCollisionWorld:
     def set_partition(self, rank, nranks):
         self._ck(self.L.b2c_set_partition(self.h, rank, nranks))
 
+    def set_partition_slabs(self, rank, nranks, axis, planes):
+        pl = np.ascontiguousarray(planes, dtype=np.float32)
+        assert len(pl) == nranks - 1
+        self._ck(self.L.b2c_set_partition_slabs(self.h, rank, nranks, axis, _vp(pl) if len(pl) else None))
+
+    def partition(self):
+        """(axis, planes, owner rank per proxy) of the slab partition in force."""
+        axis = C.c_int32()
+        planes = np.zeros(15, dtype=np.float32)
+        owner = np.zeros(max(self.num_bodies, 1), dtype=np.uint8)
+        self._ck(self.L.b2c_get_partition(self.h, C.byref(axis), _vp(planes), _vp(owner), self.num_bodies))
+        return axis.value, planes, owner[: self.num_bodies]
+
+    def mgpu_halo_slot_bytes(self, cap):
+        return int(self.L.b2c_mgpu_halo_slot_bytes(cap))
+
+    def mgpu_update_export_halo(self, slot_ptr, cap):
+        self._ck(self.L.b2c_mgpu_update_export_halo(self.h, C.c_void_p(slot_ptr), cap))
+
+    def mgpu_import_halo(self, slots_ptr, nslots, cap):
+        self._ck(self.L.b2c_mgpu_import_halo(self.h, C.c_void_p(slots_ptr), nslots, cap))
+
     def mgpu_broadphase(self):
         self._ck(self.L.b2c_mgpu_broadphase(self.h))
 

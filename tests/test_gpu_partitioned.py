@@ -1,8 +1,10 @@
-"""-m gpu: one world partitioned over R ranks must reproduce the single-GPU result exactly.
+"""-m gpu: one world partitioned over R ranks by slabs with a halo must reproduce the single-GPU result
+exactly.
 
-Run on ONE GPU: R contexts stand in for R ranks and the all-gather is a concatenation of device buffers, so the
-partition logic, the manifold migration and the bit-exact union are covered without a multi-GPU box (bench.py
---workload c5 does the same exchange with NCCL)."""
+Run on ONE GPU: R contexts stand in for R ranks and each all-gather is "every rank writes its slot straight into the
+gathered buffer", so slab ownership, the halo exchange of boundary AABBs, the manifold migration and the bit-exact union
+are covered without a multi-GPU box (bench.py's c5 object does the same exchanges with NCCL and checks the same union
+inside the real multi-rank run, libgdx-jbullet_b200/partitioned.py:partition_check)."""
 import numpy as np
 import pytest
 
@@ -11,12 +13,19 @@ import scenes
 pytestmark = pytest.mark.gpu
 
 
-def run_partitioned(pkg, sc, R, steps, mode=1, slots=False):
+def run_partitioned(pkg, sc, R, steps, mode=1, slots=False, axis=None, planes=None, halo_cap=None, stats=None):
     import torch
     single = scenes.build_gpu(pkg, sc, mode=mode)
     ranks = [scenes.build_gpu(pkg, sc, mode=mode) for _ in range(R)]
     for r, w in enumerate(ranks):
-        w.set_partition(r, R)
+        if planes is None:
+            w.set_partition(r, R)
+        else:
+            w.set_partition_slabs(r, R, axis, planes)
+    hcap = halo_cap or max(4096, sc.n)
+    hbytes = single.mgpu_halo_slot_bytes(hcap)
+    allhalo = torch.zeros(hbytes * R, dtype=torch.uint8, device="cuda")
+    halo_total = 0
     cap = 1 << 16
     bufs = [(torch.zeros(cap, dtype=torch.int64, device="cuda"), torch.zeros(cap * 8, dtype=torch.int32, device="cuda"),
              torch.zeros(cap * 4 * 24, dtype=torch.int32, device="cuda")) for _ in range(R)]
@@ -28,8 +37,14 @@ def run_partitioned(pkg, sc, R, steps, mode=1, slots=False):
         xf = sc.transforms(step)
         single.setWorldTransforms(xf)
         single.performDiscreteCollisionDetection()
-        for w in ranks:
+        # every owner updates its proxies and publishes the boundary ones; "all-gather" = all slots in one buffer
+        for r, w in enumerate(ranks):
             w.setWorldTransforms(xf)
+            w.mgpu_update_export_halo(allhalo.data_ptr() + r * hbytes, hcap)
+        torch.cuda.synchronize()
+        halo_total += int(sum(int(allhalo[r * hbytes:r * hbytes + 4].view(torch.int32)[0]) for r in range(R)))
+        for w in ranks:
+            w.mgpu_import_halo(allhalo.data_ptr(), R, hcap)
             w.mgpu_broadphase()
         if slots:
             # sync-free variant: every rank packs its slot straight into the "gathered" buffer, then all ranks scan it
@@ -68,6 +83,10 @@ def run_partitioned(pkg, sc, R, steps, mode=1, slots=False):
         migrated_total += tot
         sizes = [len(w.pairs()) for w in ranks]
         assert min(sizes) > 0
+    if stats is not None:
+        stats["halo_records"] = halo_total
+        stats["pairs_per_rank"] = sizes
+        stats["owner"] = ranks[0].partition()[2]
     return migrated_total
 
 
@@ -89,3 +108,49 @@ def test_partitioned_bin_world_with_large_statics(gpu_pkg):
     sc = scenes.bin_scene(n=4000, seed=13)
     sc.vel *= 3.0
     run_partitioned(gpu_pkg, sc, R=3, steps=5)
+
+
+def test_slab_ownership_and_halo_size(gpu_pkg):
+    """Explicit planes: proxies are owned by the slab their origin lies in, only boundary proxies travel, and every rank
+    ends up with a share of the pairs."""
+    sc = scenes.spheres_scene(n=27000, seed=9)   # 30^3 lattice
+    lo, hi = float(sc.base[:, 11].min()), float(sc.base[:, 11].max())
+    planes = [lo + (hi - lo) * k / 3.0 for k in (1, 2)]
+    st = {}
+    run_partitioned(gpu_pkg, sc, R=3, steps=4, axis=2, planes=planes, stats=st)
+    owner = st["owner"]
+    z = sc.base[:, 11]
+    expect = (z >= np.float32(planes[0])).astype(np.uint8) + (z >= np.float32(planes[1])).astype(np.uint8)
+    assert np.array_equal(owner, expect)
+    # 2 interior faces x ~900 proxies per lattice layer, both sides, 4 steps: far fewer than all proxies
+    assert 4 * 2 * 900 < st["halo_records"] < 4 * 8 * 900
+    assert min(st["pairs_per_rank"]) > 0.2 * max(st["pairs_per_rank"])
+
+
+def test_halo_slot_overflow_is_reported(gpu_pkg):
+    import torch
+    sc = scenes.spheres_scene(n=8000, seed=10)
+    w = scenes.build_gpu(gpu_pkg, sc, mode=1)
+    w.set_partition(0, 2)
+    hcap = 8
+    hb = w.mgpu_halo_slot_bytes(hcap)
+    buf = torch.zeros(2 * hb, dtype=torch.uint8, device="cuda")
+    w.setWorldTransforms(sc.transforms(0))
+    w.mgpu_update_export_halo(buf.data_ptr(), hcap)
+    w.mgpu_import_halo(buf.data_ptr(), 2, hcap)
+    w.mgpu_broadphase()
+    with pytest.raises(gpu_pkg.B2CError) as e:
+        w.sync_counts()
+    assert e.value.code == -3 and "halo" in str(e.value)
+
+
+def test_pair_calculation_needs_the_halo_first(gpu_pkg):
+    sc = scenes.spheres_scene(n=2000, seed=11)
+    w = scenes.build_gpu(gpu_pkg, sc, mode=1)
+    w.set_partition(1, 2)
+    with pytest.raises(gpu_pkg.B2CError) as e:
+        w.step_device()
+    assert e.value.code == -5
+    w.set_partition(0, 1)      # a partition of one is the plain world again
+    w.step_device()
+    assert w.sync_counts()[0] > 0
