@@ -57,9 +57,12 @@ k_keys(BodyArrays B, int nConst, const uint32_t* __restrict__ nPtr, const uint32
     if (blockIdx.x == 0 && threadIdx.x == 0) *stepPtr = *stepPtr + 1;  // k_aabb of this step has read it (stream order)
     const GridParams g = *grid;
     const float limitY = __uint_as_float(ctr->extYBits), limitZ = __uint_as_float(ctr->extZBits);
-    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n; t += gridDim.x * 256) {
-        const uint32_t i = list ? list[t] : t;
-        const uint8_t flags = B.flags[i];
+    const int lane = threadIdx.x & 31;
+    for (uint32_t t0 = blockIdx.x * 256; t0 < n; t0 += gridDim.x * 256) {
+        const uint32_t t = t0 + threadIdx.x;
+        const bool valid = t < n;
+        const uint32_t i = valid ? (list ? list[t] : t) : 0u;
+        const uint8_t flags = valid ? B.flags[i] : (uint8_t)0;
         uint32_t row, xk = 0;
         if (!(flags & BF_ALIVE)) {
             row = (uint32_t)(g.nrows + g.numWorlds);  // dead slots sort behind everything
@@ -77,11 +80,21 @@ k_keys(BodyArrays B, int nConst, const uint32_t* __restrict__ nPtr, const uint32
             xk = quantX(a.x, g.x0, g.invX, g.xmaxf);
         }
         const uint32_t key = (row << g.xbits) | xk;
-        keys[t] = key;
-        vals[t] = i;
+        if (valid) {
+            keys[t] = key;
+            vals[t] = i;
+            atomicAdd(&sh[0][key & 255u], 1u);  // low bits of qx: spread over the bins
+        }
+        // the upper digits are the same for most lanes of a warp (neighbouring proxies share their row): one shared-memory
+        // atomic per distinct digit instead of a 32-way conflict
 #pragma unroll
-        for (int p = 0; p < 4; p++)
-            if (p < npass) atomicAdd(&sh[p][(key >> (8 * p)) & 255u], 1u);
+        for (int p = 1; p < 4; p++) {
+            if (p < npass) {
+                const uint32_t d = valid ? ((key >> (8 * p)) & 255u) : 0x100u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p][d], (uint32_t)__popc(peers));
+            }
+        }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < npass * 256; k += 256) {
@@ -94,23 +107,31 @@ k_keys(BodyArrays B, int nConst, const uint32_t* __restrict__ nPtr, const uint32
     __syncthreads();
     if (!isLast) return;
     __threadfence();
-    // exclusive scan of the 256 bins of every digit (one digit after the other; 256 threads = 256 bins)
+    // exclusive scan of the 256 bins of every digit: warp p scans digit p (8 consecutive bins per lane, shuffles across lanes)
     if (threadIdx.x == 0) st->n = n;
-    for (int p = 0; p < npass; p++) {
-        uint32_t* s = sh[0];
-        const uint32_t v = *(volatile uint32_t*)&st->hist[p][threadIdx.x];
-        s[threadIdx.x] = v;
-        __syncthreads();
-        const bool full = (v == n);  // covers n == 0 as well
-        for (int off = 1; off < 256; off <<= 1) {
-            const uint32_t tv = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
-            __syncthreads();
-            s[threadIdx.x] += tv;
-            __syncthreads();
+    const int p = threadIdx.x >> 5;
+    if (p < npass) {
+        uint32_t v[8], sum = 0;
+        bool full = false;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = *(volatile uint32_t*)&st->hist[p][lane * 8 + k];
+            full |= (v[k] == n);  // covers n == 0 as well
+            sum += v[k];
         }
-        st->hist[p][threadIdx.x] = s[threadIdx.x] - v;
-        if (__syncthreads_or(full ? 1 : 0) && threadIdx.x == 0) st->skip[p] = 1u;
-        __syncthreads();
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t tv = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tv;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            st->hist[p][lane * 8 + k] = run;
+            run += v[k];
+        }
+        if (__any_sync(0xffffffffu, full) && lane == 0) st->skip[p] = 1u;
     }
 }
 
@@ -272,17 +293,43 @@ struct __align__(128) SweepStage {
     uint32_t key[SW_CH];
 };
 
-// k_sweep: every warp owns 32 consecutive SORTED proxies (lane = proxy).  For each of the 9 neighbour rows (dy, dz) a lane's
-// candidates are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)] — its x-window in
-// that row.  The lanes' windows are close together (consecutive proxies of one row, or of a few consecutive rows when the
-// rows are short), so their union [lo, hi) is a short contiguous range of the sorted arrays: it is staged chunk by chunk in
-// the warp's shared-memory buffer with three bulk copies (min, max, key) completing on the warp's mbarrier, and each lane
-// then binary-searches its own start inside the chunk and walks its window from shared memory.  The lanes advance in lock
-// step only for the ballot/popc compaction of hits.  The pair is emitted by the member that comes first in (qx, sorted
-// position) order, so every overlapping pair is produced exactly once; the overlap test is the reference's closed-interval
-// predicate on the original floats (bp/DbvtAabbMm.java:209-212), the keys only select candidates.
-// The sorted arrays are padded by SW_CH entries, so a chunk may read past n (never past the allocation); whatever it stages
-// there is rejected by the key window.
+// k_sweep: every warp owns 32 consecutive SORTED proxies (lane = proxy) and ONE of the 9 neighbour rows (dy, dz) = blockIdx.y.
+// A lane's candidates are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)] — its
+// x-window in the target row.  The lanes' windows are close together (consecutive proxies of one row, or of a few
+// consecutive rows when rows are short), so their union [lo, hi) is a short contiguous range of the sorted arrays.  The two
+// ends are found by two 16-ary searches that run side by side in the two half-warps (lower bound of the smallest start key,
+// upper bound of the largest end key), then the range is staged chunk by chunk in the warp's shared-memory buffer with
+// three bulk copies (min, max, key) completing on the warp's mbarrier, and each lane binary-searches its own start inside
+// the chunk and walks its window from shared memory.  The lanes advance in lock step only for the ballot/popc compaction of
+// hits.  The pair is emitted by the member that comes first in (qx, sorted position) order, so every overlapping pair is
+// produced exactly once; the overlap test is the reference's closed-interval predicate on the original floats
+// (bp/DbvtAabbMm.java:209-212), the keys only select candidates.
+// The sorted arrays are padded by SW_CH entries, so a chunk may read a few entries past n (never past the allocation);
+// lanes never look at staged entries beyond hi.
+__device__ __forceinline__ uint32_t halfWarpLowerBound(const uint32_t* __restrict__ skey, uint32_t a, uint32_t b, uint32_t target,
+                                                       int lane) {
+    // both half-warps search at once (each its own [a, b) and target): 16 probes per round and half
+    const int sub = lane & 15;
+    const int sh = lane & 16;
+    while (__any_sync(0xffffffffu, b - a > 16u)) {
+        const bool big = b - a > 16u;
+        const uint32_t stepw = big ? (b - a + 15u) / 16u : 1u;
+        const uint32_t pos = a + (uint32_t)sub * stepw;
+        const bool less = big && pos < b && __ldg(skey + pos) < target;
+        const int c = __popc((__ballot_sync(0xffffffffu, less) >> sh) & 0xffffu);  // a prefix of the half (keys are sorted)
+        if (big) {
+            // the answer lies in (a + (c-1)*stepw, a + c*stepw]
+            const uint32_t na = c ? a + (uint32_t)(c - 1) * stepw + 1u : a;
+            const uint32_t nb = c ? min(b, a + (uint32_t)c * stepw) : a;
+            a = na;
+            b = nb;
+        }
+    }
+    const uint32_t pos = a + (uint32_t)sub;
+    const bool less = pos < b && __ldg(skey + pos) < target;
+    return a + (uint32_t)__popc((__ballot_sync(0xffffffffu, less) >> sh) & 0xffffu);
+}
+
 __global__ void __launch_bounds__(256)
 k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, const float4* __restrict__ smax,
         const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
@@ -307,116 +354,94 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
     const int ny = grid->ny, nz = grid->nz, xbits = grid->xbits;
     const uint32_t xmask = grid->xmask;
     const float gx0 = grid->x0, ginvX = grid->invX, gxmax = grid->xmaxf;
+    const int nb = blockIdx.y;  // 0..8
+    const int dy = nb / 3 - 1, dz = nb % 3 - 1;
     for (uint32_t wbase = (blockIdx.x * SW_WARPS + warp) * 32u; wbase < n; wbase += gridDim.x * (SW_WARPS * 32u)) {
         const uint32_t i = wbase + lane;
         uint32_t keyI = 0, cc = 0xffffffffu;
-        float4 amin = make_float4(0, 0, 0, 0), amax = amin;
         if (i < n) {
             keyI = __ldg(skey + i);
             cc = __ldg(scyz + i);
+        }
+        const int cy = (int)(cc >> 16) + dy, cz = (int)(cc & 0xffffu) + dz;
+        const bool act = cc != 0xffffffffu && cy >= 0 && cy < ny && cz >= 0 && cz < nz;
+        if (!__any_sync(0xffffffffu, act)) continue;  // large proxies / dead slots / no such neighbour row
+        float4 amin = make_float4(0, 0, 0, 0), amax = amin;
+        if (act) {
             amin = __ldg(smin + i);
             amax = __ldg(smax + i);
         }
-        const bool gridded = cc != 0xffffffffu;
-        if (!__any_sync(0xffffffffu, gridded)) continue;  // a warp of large proxies / dead slots: k_large's business
         const uint32_t row = keyI >> xbits, xkI = keyI & xmask;
-        const uint32_t xkMax = gridded ? quantX(amax.x, gx0, ginvX, gxmax) : 0u;
-        const int cy0 = (int)(cc >> 16), cz0 = (int)(cc & 0xffffu);
-        for (int nb = 0; nb < 9; nb++) {
-            const int dy = nb / 3 - 1, dz = nb % 3 - 1;
-            const int cy = cy0 + dy, cz = cz0 + dz;
-            const bool act = gridded && cy >= 0 && cy < ny && cz >= 0 && cz < nz;
-            const uint32_t tRow = (uint32_t)((int)row + dy * nz + dz);  // same world: cy stays inside [0, ny)
-            const uint32_t startKey = (tRow << xbits) | xkI, endKey = (tRow << xbits) | xkMax;
-            // union of the lanes' windows: from the first position that can matter to the end of the last target row
-            uint32_t minStart = act ? startKey : 0xffffffffu;
-            uint32_t hi = act ? __ldg(rowStart + tRow + 1) : 0u;
-            for (int o = 16; o > 0; o >>= 1) {
-                minStart = min(minStart, __shfl_xor_sync(0xffffffffu, minStart, o));
-                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        const uint32_t xkMax = act ? quantX(amax.x, gx0, ginvX, gxmax) : 0u;
+        const uint32_t tRow = (uint32_t)((int)row + dy * nz + dz);  // same world: cy stays inside [0, ny)
+        const uint32_t startKey = (tRow << xbits) | xkI, endKey = (tRow << xbits) | xkMax;
+        // union of the lanes' windows: [lower bound of the smallest start key, upper bound of the largest end key)
+        uint32_t loKey = act ? startKey : 0xffffffffu, hiKey = act ? endKey : 0u;
+        for (int o = 16; o > 0; o >>= 1) {
+            loKey = min(loKey, __shfl_xor_sync(0xffffffffu, loKey, o));
+            hiKey = max(hiKey, __shfl_xor_sync(0xffffffffu, hiKey, o));
+        }
+        uint32_t lo, hi;
+        {
+            const bool upper = lane >= 16;
+            const uint32_t r = (upper ? hiKey : loKey) >> xbits;
+            const uint32_t a = __ldg(rowStart + r), b = __ldg(rowStart + r + 1);
+            const uint32_t pos = halfWarpLowerBound(skey, a, b, upper ? hiKey + 1u : loKey, lane);
+            lo = __shfl_sync(0xffffffffu, pos, 0);
+            hi = __shfl_sync(0xffffffffu, pos, 16);
+        }
+        if (nb == 4) lo = wbase + (uint32_t)(__ffs(__ballot_sync(0xffffffffu, act)) - 1) + 1u;  // same row: only entries behind the proxy
+        for (uint32_t cs = lo & ~3u; cs < hi; cs += SW_CH) {
+            const uint32_t cv = min((uint32_t)SW_CH, hi - cs);          // valid entries of the chunk
+            const uint32_t cnt = (cv + 3u) & ~3u;                       // staged entries: 16-byte multiples
+            __syncwarp();  // every lane has finished reading the previous chunk
+            if (lane == 0) {
+                mbarExpectTx(bar, cnt * 36u);
+                bulkLoad(S.mn, smin + cs, cnt * 16u, bar);
+                bulkLoad(S.mx, smax + cs, cnt * 16u, bar);
+                bulkLoad(S.key, skey + cs, cnt * 4u, bar);
             }
-            if (minStart == 0xffffffffu) continue;  // no lane has this neighbour
-            uint32_t lo;
-            if (nb == 4) {
-                lo = wbase + (uint32_t)(__ffs(__ballot_sync(0xffffffffu, act)) - 1) + 1u;  // same row: everything after the proxy itself
-            } else {
-                // warp-cooperative lower bound of minStart inside its row: 32 probes per round
-                const uint32_t r0 = minStart >> xbits;
-                uint32_t a = __ldg(rowStart + r0), b = __ldg(rowStart + r0 + 1);
-                while (b - a > 32u) {
-                    const uint32_t stepw = (b - a + 31u) / 32u;
-                    const uint32_t pos = a + (uint32_t)lane * stepw;
-                    const bool less = pos < b && __ldg(skey + pos) < minStart;
-                    const uint32_t m = __ballot_sync(0xffffffffu, less);  // a prefix of the lanes (keys are sorted)
-                    const int c = __popc(m);
-                    // the answer lies in (a + (c-1)*stepw, a + c*stepw]
-                    const uint32_t na = c ? a + (uint32_t)(c - 1) * stepw + 1u : a;
-                    const uint32_t nbb = min(b, a + (uint32_t)c * stepw);
-                    a = na;
-                    b = nbb;
-                    if (c == 0) break;
-                }
-                {
-                    const uint32_t pos = a + (uint32_t)lane;
-                    const bool less = pos < b && __ldg(skey + pos) < minStart;
-                    a += (uint32_t)__popc(__ballot_sync(0xffffffffu, less));
-                }
-                lo = a;
-            }
+            mbarWait(bar, parity);
+            parity ^= 1u;
+            // this lane's first candidate in the chunk: lower bound of its start key (binary search in shared memory)
+            uint32_t k = cv;
             bool done = !act;
-            for (uint32_t cs = lo & ~3u; cs < hi; cs += SW_CH) {
-                if (__all_sync(0xffffffffu, done)) break;
-                const uint32_t cv = min((uint32_t)SW_CH, hi - cs);          // valid entries of the chunk
-                const uint32_t cnt = (cv + 3u) & ~3u;                       // staged entries: 16-byte multiples
-                __syncwarp();  // every lane has finished reading the previous chunk
-                if (lane == 0) {
-                    mbarExpectTx(bar, cnt * 36u);
-                    bulkLoad(S.mn, smin + cs, cnt * 16u, bar);
-                    bulkLoad(S.mx, smax + cs, cnt * 16u, bar);
-                    bulkLoad(S.key, skey + cs, cnt * 4u, bar);
+            if (act) {
+                uint32_t a = 0, b = cv;
+                while (a < b) {
+                    const uint32_t mid = (a + b) >> 1;
+                    if (S.key[mid] < startKey) a = mid + 1; else b = mid;
                 }
-                mbarWait(bar, parity);
-                parity ^= 1u;
-                // this lane's first candidate in the chunk: lower bound of its start key (binary search in shared memory)
-                uint32_t k = cv;
-                if (!done) {
-                    uint32_t a = 0, b = cv;
-                    while (a < b) {
-                        const uint32_t mid = (a + b) >> 1;
-                        if (S.key[mid] < startKey) a = mid + 1; else b = mid;
-                    }
-                    k = a;
-                    if (nb == 4 && i + 1u > cs + k) k = i + 1u - cs;  // same row: only entries behind the proxy itself
-                    if (k > cv) k = cv;
-                }
-                while (__any_sync(0xffffffffu, !done && k < cv)) {
-                    bool hit = false;
-                    uint32_t bodyB = 0;
-                    if (!done && k < cv) {
-                        const uint32_t kj = S.key[k];
-                        if (kj > endKey) {
-                            done = true;  // window closed
-                        } else {
-                            // ties in qx across rows: only the earlier sorted position emits
-                            if ((kj & xmask) != xkI || cs + k > i) {
-                                const float4 bmin = S.mn[k], bmax = S.mx[k];
-                                hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
-                                      (amin.z <= bmax.z) && (amax.z >= bmin.z) &&
-                                      filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
-                                bodyB = __float_as_uint(bmin.w);
-                                // AxisSweep3 modes: the float boxes are a monotone image of the quantised ones (necessary
-                                // condition); the pair predicate itself is on the quantised values
-                                if (hit && qmin) {
-                                    const uint32_t bodyA = __float_as_uint(amin.w);
-                                    hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
-                                }
-                                if (hit) hit = slab.owns(amin, bmin);
+                k = a;
+                if (nb == 4 && i + 1u > cs + k) k = min(cv, i + 1u - cs);  // same row: only entries behind the proxy itself
+            }
+            while (__any_sync(0xffffffffu, !done && k < cv)) {
+                bool hit = false;
+                uint32_t bodyB = 0;
+                if (!done && k < cv) {
+                    const uint32_t kj = S.key[k];
+                    if (kj > endKey) {
+                        done = true;  // window closed
+                    } else {
+                        // ties in qx across rows: only the earlier sorted position emits
+                        if ((kj & xmask) != xkI || cs + k > i) {
+                            const float4 bmin = S.mn[k], bmax = S.mx[k];
+                            hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
+                                  (amin.z <= bmax.z) && (amax.z >= bmin.z) &&
+                                  filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
+                            bodyB = __float_as_uint(bmin.w);
+                            // AxisSweep3 modes: the float boxes are a monotone image of the quantised ones (necessary
+                            // condition); the pair predicate itself is on the quantised values
+                            if (hit && qmin) {
+                                const uint32_t bodyA = __float_as_uint(amin.w);
+                                hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
                             }
-                            k++;
+                            if (hit) hit = slab.owns(amin, bmin);
                         }
+                        k++;
                     }
-                    st.push(hit, __float_as_uint(amin.w), bodyB, pairKeys, maxPairs, ctr);
                 }
+                st.push(hit, __float_as_uint(amin.w), bodyB, pairKeys, maxPairs, ctr);
             }
         }
     }
