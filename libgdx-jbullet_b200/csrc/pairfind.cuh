@@ -285,30 +285,17 @@ __device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, u
                  : "memory");
 }
 
-constexpr int SW_CH = 64;     // sorted entries staged per chunk and warp
-constexpr int SW_WARPS = 8;
+constexpr int SW_CH = 512;    // sorted entries staged per chunk and block
 struct __align__(128) SweepStage {
     float4 mn[SW_CH];
     float4 mx[SW_CH];
     uint32_t key[SW_CH];
 };
 
-// k_sweep: every warp owns 32 consecutive SORTED proxies (lane = proxy) and ONE of the 9 neighbour rows (dy, dz) = blockIdx.y.
-// A lane's candidates are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)] — its
-// x-window in the target row.  The lanes' windows are close together (consecutive proxies of one row, or of a few
-// consecutive rows when rows are short), so their union [lo, hi) is a short contiguous range of the sorted arrays.  The two
-// ends are found by two 16-ary searches that run side by side in the two half-warps (lower bound of the smallest start key,
-// upper bound of the largest end key), then the range is staged chunk by chunk in the warp's shared-memory buffer with
-// three bulk copies (min, max, key) completing on the warp's mbarrier, and each lane binary-searches its own start inside
-// the chunk and walks its window from shared memory.  The lanes advance in lock step only for the ballot/popc compaction of
-// hits.  The pair is emitted by the member that comes first in (qx, sorted position) order, so every overlapping pair is
-// produced exactly once; the overlap test is the reference's closed-interval predicate on the original floats
-// (bp/DbvtAabbMm.java:209-212), the keys only select candidates.
-// The sorted arrays are padded by SW_CH entries, so a chunk may read a few entries past n (never past the allocation);
-// lanes never look at staged entries beyond hi.
+// Both half-warps search at once (each its own [a, b) and target): 16 probes per round and half.  Returns the lower bound of
+// `target` in skey[a, b).
 __device__ __forceinline__ uint32_t halfWarpLowerBound(const uint32_t* __restrict__ skey, uint32_t a, uint32_t b, uint32_t target,
                                                        int lane) {
-    // both half-warps search at once (each its own [a, b) and target): 16 probes per round and half
     const int sub = lane & 15;
     const int sh = lane & 16;
     while (__any_sync(0xffffffffu, b - a > 16u)) {
@@ -330,23 +317,35 @@ __device__ __forceinline__ uint32_t halfWarpLowerBound(const uint32_t* __restric
     return a + (uint32_t)__popc((__ballot_sync(0xffffffffu, less) >> sh) & 0xffffu);
 }
 
-__global__ void __launch_bounds__(256)
+// k_sweep: a block owns 256 consecutive SORTED proxies (thread = proxy) and ONE of the 9 neighbour rows (dy, dz) = blockIdx.y.
+// A proxy's candidates are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)] — its
+// x-window in the target row.  The windows of consecutive proxies lie next to each other, so their union [lo, hi) is a short
+// contiguous range of the sorted arrays (about the block's own length plus one window).  Warp 0 finds its two ends with two
+// 16-ary searches that run side by side in its half-warps (lower bound of the smallest start key, upper bound of the largest
+// end key); the range is then staged in shared memory with three 1-D bulk copies (TMA: min, max, key) completing on one
+// mbarrier, and every thread binary-searches its own start and walks its own window entirely in shared memory.  Warps
+// advance in lock step only for the ballot/popc compaction of hits.  The pair is emitted by the member that comes first in
+// (qx, sorted position) order, so every overlapping pair is produced exactly once; the overlap test is the reference's
+// closed-interval predicate on the original floats (bp/DbvtAabbMm.java:209-212), the keys only select candidates.
+// The sorted arrays are padded by SW_CH entries: a chunk may read a few entries past n, never past the allocation, and no
+// thread looks at staged entries beyond hi.
+__global__ void __launch_bounds__(256, 5)
 k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, const float4* __restrict__ smax,
         const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
         uint64_t* __restrict__ pairKeys, uint32_t* rowCnt, uint32_t maxPairs, StepCounters* ctr, SlabFilter slab,
         const float4* __restrict__ qmin, const float4* __restrict__ qmax /* SAP modes: quantised bounds per body, else null */,
         const uint32_t* __restrict__ scyz) {
-    __shared__ SweepStage stage[SW_WARPS];
-    __shared__ uint64_t bars[SW_WARPS];
-    __shared__ uint64_t pstage[SW_WARPS][PAIR_STAGE];
+    __shared__ SweepStage S;
+    __shared__ uint64_t bar;
+    __shared__ uint64_t pstage[8][PAIR_STAGE];
+    __shared__ uint32_t sRed[2][8];
+    __shared__ uint32_t sLoHi[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SweepStage& S = stage[warp];
-    uint64_t* bar = &bars[warp];
-    if (lane == 0) {
-        mbarInit(bar, 1);
+    if (threadIdx.x == 0) {
+        mbarInit(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    __syncthreads();
     uint32_t parity = 0;
     PairStager st;
     st.init(pstage[warp], rowCnt, uidBits);
@@ -356,8 +355,8 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
     const float gx0 = grid->x0, ginvX = grid->invX, gxmax = grid->xmaxf;
     const int nb = blockIdx.y;  // 0..8
     const int dy = nb / 3 - 1, dz = nb % 3 - 1;
-    for (uint32_t wbase = (blockIdx.x * SW_WARPS + warp) * 32u; wbase < n; wbase += gridDim.x * (SW_WARPS * 32u)) {
-        const uint32_t i = wbase + lane;
+    for (uint32_t bbase = blockIdx.x * 256u; bbase < n; bbase += gridDim.x * 256u) {
+        const uint32_t i = bbase + threadIdx.x;
         uint32_t keyI = 0, cc = 0xffffffffu;
         if (i < n) {
             keyI = __ldg(skey + i);
@@ -365,7 +364,6 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
         }
         const int cy = (int)(cc >> 16) + dy, cz = (int)(cc & 0xffffu) + dz;
         const bool act = cc != 0xffffffffu && cy >= 0 && cy < ny && cz >= 0 && cz < nz;
-        if (!__any_sync(0xffffffffu, act)) continue;  // large proxies / dead slots / no such neighbour row
         float4 amin = make_float4(0, 0, 0, 0), amax = amin;
         if (act) {
             amin = __ldg(smin + i);
@@ -375,44 +373,57 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
         const uint32_t xkMax = act ? quantX(amax.x, gx0, ginvX, gxmax) : 0u;
         const uint32_t tRow = (uint32_t)((int)row + dy * nz + dz);  // same world: cy stays inside [0, ny)
         const uint32_t startKey = (tRow << xbits) | xkI, endKey = (tRow << xbits) | xkMax;
-        // union of the lanes' windows: [lower bound of the smallest start key, upper bound of the largest end key)
+        // union of the block's windows: [lower bound of the smallest start key, upper bound of the largest end key)
         uint32_t loKey = act ? startKey : 0xffffffffu, hiKey = act ? endKey : 0u;
         for (int o = 16; o > 0; o >>= 1) {
             loKey = min(loKey, __shfl_xor_sync(0xffffffffu, loKey, o));
             hiKey = max(hiKey, __shfl_xor_sync(0xffffffffu, hiKey, o));
         }
-        uint32_t lo, hi;
-        {
-            const bool upper = lane >= 16;
-            const uint32_t r = (upper ? hiKey : loKey) >> xbits;
-            const uint32_t a = __ldg(rowStart + r), b = __ldg(rowStart + r + 1);
-            const uint32_t pos = halfWarpLowerBound(skey, a, b, upper ? hiKey + 1u : loKey, lane);
-            lo = __shfl_sync(0xffffffffu, pos, 0);
-            hi = __shfl_sync(0xffffffffu, pos, 16);
+        __syncthreads();  // the previous iteration's readers of sRed / sLoHi / S are through
+        if (lane == 0) { sRed[0][warp] = loKey; sRed[1][warp] = hiKey; }
+        __syncthreads();
+        if (warp == 0) {
+            loKey = sRed[0][lane & 7];
+            hiKey = sRed[1][lane & 7];
+            for (int o = 4; o > 0; o >>= 1) {
+                loKey = min(loKey, __shfl_xor_sync(0xffffffffu, loKey, o));
+                hiKey = max(hiKey, __shfl_xor_sync(0xffffffffu, hiKey, o));
+            }
+            uint32_t lo = 0, hi = 0;
+            if (loKey != 0xffffffffu) {  // warp-uniform: some proxy of the block has this neighbour row
+                const bool upper = lane >= 16;
+                const uint32_t r = (upper ? hiKey : loKey) >> xbits;
+                const uint32_t a = __ldg(rowStart + r), b = __ldg(rowStart + r + 1);
+                const uint32_t pos = halfWarpLowerBound(skey, a, b, upper ? hiKey + 1u : loKey, lane);
+                lo = __shfl_sync(0xffffffffu, pos, 0);
+                hi = __shfl_sync(0xffffffffu, pos, 16);
+                if (nb == 4) lo = bbase;  // same row: a proxy's candidates start right behind itself
+            }
+            if (lane == 0) { sLoHi[0] = lo; sLoHi[1] = hi; }
         }
-        if (nb == 4) lo = wbase + (uint32_t)(__ffs(__ballot_sync(0xffffffffu, act)) - 1) + 1u;  // same row: only entries behind the proxy
+        __syncthreads();
+        const uint32_t lo = sLoHi[0], hi = sLoHi[1];
+        bool done = !act;
         for (uint32_t cs = lo & ~3u; cs < hi; cs += SW_CH) {
             const uint32_t cv = min((uint32_t)SW_CH, hi - cs);          // valid entries of the chunk
             const uint32_t cnt = (cv + 3u) & ~3u;                       // staged entries: 16-byte multiples
-            __syncwarp();  // every lane has finished reading the previous chunk
-            if (lane == 0) {
-                mbarExpectTx(bar, cnt * 36u);
-                bulkLoad(S.mn, smin + cs, cnt * 16u, bar);
-                bulkLoad(S.mx, smax + cs, cnt * 16u, bar);
-                bulkLoad(S.key, skey + cs, cnt * 4u, bar);
+            if (cs != (lo & ~3u)) __syncthreads();  // every thread has finished reading the previous chunk
+            if (threadIdx.x == 0) {
+                mbarExpectTx(&bar, cnt * 36u);
+                bulkLoad(S.mn, smin + cs, cnt * 16u, &bar);
+                bulkLoad(S.mx, smax + cs, cnt * 16u, &bar);
+                bulkLoad(S.key, skey + cs, cnt * 4u, &bar);
             }
-            mbarWait(bar, parity);
+            mbarWait(&bar, parity);
             parity ^= 1u;
-            // this lane's first candidate in the chunk: lower bound of its start key (binary search in shared memory)
-            uint32_t k = cv;
-            bool done = !act;
-            if (act) {
-                uint32_t a = 0, b = cv;
-                while (a < b) {
-                    const uint32_t mid = (a + b) >> 1;
-                    if (S.key[mid] < startKey) a = mid + 1; else b = mid;
+            // this thread's first candidate in the chunk: lower bound of its start key (branch-free search in shared memory)
+            uint32_t k = 0;
+            if (!done) {
+#pragma unroll
+                for (uint32_t sstep = SW_CH / 2; sstep > 0; sstep >>= 1) {
+                    const uint32_t t = k + sstep;
+                    if (t <= cv && S.key[t - 1] < startKey) k = t;
                 }
-                k = a;
                 if (nb == 4 && i + 1u > cs + k) k = min(cv, i + 1u - cs);  // same row: only entries behind the proxy itself
             }
             while (__any_sync(0xffffffffu, !done && k < cv)) {
