@@ -440,7 +440,7 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
         CK(cudaEventRecord(ctx->evFork[2], s));
         CK(cudaStreamWaitEvent(sl, ctx->evFork[2], 0));
     }
-    k_sweep<<<dim3(gridFor(nUpper, 256, 148 * 8), 9), 256, 0, s>>>(ctx->dNSorted, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid,
+    k_sweep<<<dim3(gridFor(nUpper, 256, 148 * 8), 3), 256, 0, s>>>(ctx->dNSorted, ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dGrid,
                                                           ctx->uidBits, ctx->dPairKeys, rowCnt, (uint32_t)ctx->cfg.max_pairs, ctx->dCtr, ctx->slab,
                                                           ctx->sap.enabled ? ctx->B.leafMin : nullptr,
                                                           ctx->sap.enabled ? ctx->B.leafMax : nullptr, ctx->dScyz);

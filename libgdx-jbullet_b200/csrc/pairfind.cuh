@@ -285,7 +285,7 @@ __device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, u
                  : "memory");
 }
 
-constexpr int SW_CH = 512;    // sorted entries staged per chunk and block
+constexpr int SW_CH = 1024;   // sorted entries staged per chunk and block
 struct __align__(128) SweepStage {
     float4 mn[SW_CH];
     float4 mx[SW_CH];
@@ -317,18 +317,30 @@ __device__ __forceinline__ uint32_t halfWarpLowerBound(const uint32_t* __restric
     return a + (uint32_t)__popc((__ballot_sync(0xffffffffu, less) >> sh) & 0xffffu);
 }
 
-// k_sweep: a block owns 256 consecutive SORTED proxies (thread = proxy) and ONE of the 9 neighbour rows (dy, dz) = blockIdx.y.
-// A proxy's candidates are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)] — its
-// x-window in the target row.  The windows of consecutive proxies lie next to each other, so their union [lo, hi) is a short
-// contiguous range of the sorted arrays (about the block's own length plus one window).  Warp 0 finds its two ends with two
+// k_sweep: a block owns 256 consecutive SORTED proxies (thread = proxy) and one BAND of neighbour rows: dy = blockIdx.y - 1
+// and dz = -1, 0, +1 — three rows that are consecutive in key order (row = ... + cy * nz + cz).  A proxy's candidates in a
+// target row are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)]: its x-window.  The
+// windows of consecutive proxies lie next to each other, so the union [lo, hi) over the block and the band is one short
+// contiguous range of the sorted arrays (about the block's own length plus two rows).  Warp 0 finds its two ends with two
 // 16-ary searches that run side by side in its half-warps (lower bound of the smallest start key, upper bound of the largest
-// end key); the range is then staged in shared memory with three 1-D bulk copies (TMA: min, max, key) completing on one
-// mbarrier, and every thread binary-searches its own start and walks its own window entirely in shared memory.  Warps
-// advance in lock step only for the ballot/popc compaction of hits.  The pair is emitted by the member that comes first in
+// end key); the range is staged in shared memory with three 1-D bulk copies (TMA: min, max, key) completing on one
+// mbarrier, and every thread binary-searches the starts of its three windows and walks them entirely in shared memory, one
+// after the other inside ONE lock-step loop (three short windows per lane even out the loop length across the warp).  The
+// lock step is only needed for the ballot/popc compaction of hits.  The pair is emitted by the member that comes first in
 // (qx, sorted position) order, so every overlapping pair is produced exactly once; the overlap test is the reference's
 // closed-interval predicate on the original floats (bp/DbvtAabbMm.java:209-212), the keys only select candidates.
 // The sorted arrays are padded by SW_CH entries: a chunk may read a few entries past n, never past the allocation, and no
 // thread looks at staged entries beyond hi.
+__device__ __forceinline__ uint32_t smemLowerBound(const uint32_t* __restrict__ key, uint32_t cv, uint32_t target) {
+    uint32_t k = 0;
+#pragma unroll
+    for (uint32_t sstep = SW_CH; sstep > 0; sstep >>= 1) {  // from SW_CH itself: the result may be cv == SW_CH
+        const uint32_t t = k + sstep;
+        if (t <= cv && key[t - 1] < target) k = t;
+    }
+    return k;
+}
+
 __global__ void __launch_bounds__(256, 5)
 k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, const float4* __restrict__ smax,
         const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
@@ -353,8 +365,7 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
     const int ny = grid->ny, nz = grid->nz, xbits = grid->xbits;
     const uint32_t xmask = grid->xmask;
     const float gx0 = grid->x0, ginvX = grid->invX, gxmax = grid->xmaxf;
-    const int nb = blockIdx.y;  // 0..8
-    const int dy = nb / 3 - 1, dz = nb % 3 - 1;
+    const int dy = (int)blockIdx.y - 1;
     for (uint32_t bbase = blockIdx.x * 256u; bbase < n; bbase += gridDim.x * 256u) {
         const uint32_t i = bbase + threadIdx.x;
         uint32_t keyI = 0, cc = 0xffffffffu;
@@ -362,8 +373,8 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
             keyI = __ldg(skey + i);
             cc = __ldg(scyz + i);
         }
-        const int cy = (int)(cc >> 16) + dy, cz = (int)(cc & 0xffffu) + dz;
-        const bool act = cc != 0xffffffffu && cy >= 0 && cy < ny && cz >= 0 && cz < nz;
+        const int cy = (int)(cc >> 16) + dy, cz0 = (int)(cc & 0xffffu);
+        const bool act = cc != 0xffffffffu && cy >= 0 && cy < ny;
         float4 amin = make_float4(0, 0, 0, 0), amax = amin;
         if (act) {
             amin = __ldg(smin + i);
@@ -371,10 +382,11 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
         }
         const uint32_t row = keyI >> xbits, xkI = keyI & xmask;
         const uint32_t xkMax = act ? quantX(amax.x, gx0, ginvX, gxmax) : 0u;
-        const uint32_t tRow = (uint32_t)((int)row + dy * nz + dz);  // same world: cy stays inside [0, ny)
-        const uint32_t startKey = (tRow << xbits) | xkI, endKey = (tRow << xbits) | xkMax;
+        const uint32_t tRow0 = (uint32_t)((int)row + dy * nz);  // the dz = 0 row of the band; same world: cy stays inside [0, ny)
+        const bool vm = act && cz0 > 0, vp = act && cz0 + 1 < nz;  // the dz = -1 / +1 rows exist
         // union of the block's windows: [lower bound of the smallest start key, upper bound of the largest end key)
-        uint32_t loKey = act ? startKey : 0xffffffffu, hiKey = act ? endKey : 0u;
+        uint32_t loKey = act ? (((vm ? tRow0 - 1u : tRow0) << xbits) | xkI) : 0xffffffffu;
+        uint32_t hiKey = act ? (((vp ? tRow0 + 1u : tRow0) << xbits) | xkMax) : 0u;
         for (int o = 16; o > 0; o >>= 1) {
             loKey = min(loKey, __shfl_xor_sync(0xffffffffu, loKey, o));
             hiKey = max(hiKey, __shfl_xor_sync(0xffffffffu, hiKey, o));
@@ -390,20 +402,20 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
                 hiKey = max(hiKey, __shfl_xor_sync(0xffffffffu, hiKey, o));
             }
             uint32_t lo = 0, hi = 0;
-            if (loKey != 0xffffffffu) {  // warp-uniform: some proxy of the block has this neighbour row
+            if (loKey != 0xffffffffu) {  // warp-uniform: some proxy of the block has this band
                 const bool upper = lane >= 16;
                 const uint32_t r = (upper ? hiKey : loKey) >> xbits;
                 const uint32_t a = __ldg(rowStart + r), b = __ldg(rowStart + r + 1);
                 const uint32_t pos = halfWarpLowerBound(skey, a, b, upper ? hiKey + 1u : loKey, lane);
                 lo = __shfl_sync(0xffffffffu, pos, 0);
                 hi = __shfl_sync(0xffffffffu, pos, 16);
-                if (nb == 4) lo = bbase;  // same row: a proxy's candidates start right behind itself
             }
             if (lane == 0) { sLoHi[0] = lo; sLoHi[1] = hi; }
         }
         __syncthreads();
         const uint32_t lo = sLoHi[0], hi = sLoHi[1];
-        bool done = !act;
+        // bit w of `closed`: window w (dz = w - 1) does not exist or has seen its end
+        uint32_t closed = act ? ((vm ? 0u : 1u) | (vp ? 0u : 4u)) : 7u;
         for (uint32_t cs = lo & ~3u; cs < hi; cs += SW_CH) {
             const uint32_t cv = min((uint32_t)SW_CH, hi - cs);          // valid entries of the chunk
             const uint32_t cnt = (cv + 3u) & ~3u;                       // staged entries: 16-byte multiples
@@ -416,24 +428,36 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
             }
             mbarWait(&bar, parity);
             parity ^= 1u;
-            // this thread's first candidate in the chunk: lower bound of its start key (branch-free search in shared memory)
-            uint32_t k = 0;
-            if (!done) {
-#pragma unroll
-                for (uint32_t sstep = SW_CH / 2; sstep > 0; sstep >>= 1) {
-                    const uint32_t t = k + sstep;
-                    if (t <= cv && S.key[t - 1] < startKey) k = t;
-                }
-                if (nb == 4 && i + 1u > cs + k) k = min(cv, i + 1u - cs);  // same row: only entries behind the proxy itself
-            }
-            while (__any_sync(0xffffffffu, !done && k < cv)) {
+            // first candidate of each of the thread's windows in this chunk (branch-free searches in shared memory; a closed
+            // window starts at cv = nothing to do)
+            uint32_t k0 = (closed & 1u) ? cv : smemLowerBound(S.key, cv, ((tRow0 - 1u) << xbits) | xkI);
+            uint32_t k1 = (closed & 2u) ? cv : smemLowerBound(S.key, cv, (tRow0 << xbits) | xkI);
+            const uint32_t k2 = (closed & 4u) ? cv : smemLowerBound(S.key, cv, ((tRow0 + 1u) << xbits) | xkI);
+            if (dy == 0 && !(closed & 2u) && i + 1u > cs + k1) k1 = min(cv, i + 1u - cs);  // own row: only entries behind the proxy
+            int w = 0;
+            uint32_t k = k0;
+            uint32_t endKey = ((tRow0 - 1u) << xbits) | xkMax;
+            while (__any_sync(0xffffffffu, w < 3)) {
                 bool hit = false;
                 uint32_t bodyB = 0;
-                if (!done && k < cv) {
-                    const uint32_t kj = S.key[k];
-                    if (kj > endKey) {
-                        done = true;  // window closed
-                    } else {
+                if (w < 3) {
+                    uint32_t kj = 0;
+                    // move on while the current window has nothing more in this chunk (closed for good when a key beyond its
+                    // end was seen, to be continued in the next chunk when the chunk ran out)
+#pragma unroll
+                    for (int tr = 0; tr < 3; tr++) {
+                        if (w < 3) {
+                            const bool inChunk = k < cv;
+                            if (inChunk) kj = S.key[k];
+                            if (!inChunk || kj > endKey) {
+                                if (inChunk) closed |= 1u << w;
+                                w++;
+                                k = w == 1 ? k1 : k2;
+                                endKey = ((tRow0 + (uint32_t)(w - 1)) << xbits) | xkMax;
+                            }
+                        }
+                    }
+                    if (w < 3) {
                         // ties in qx across rows: only the earlier sorted position emits
                         if ((kj & xmask) != xkI || cs + k > i) {
                             const float4 bmin = S.mn[k], bmax = S.mx[k];
