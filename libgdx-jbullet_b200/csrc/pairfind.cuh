@@ -319,28 +319,21 @@ __device__ __forceinline__ uint32_t halfWarpLowerBound(const uint32_t* __restric
 
 // k_sweep: a block owns 256 consecutive SORTED proxies (thread = proxy) and one BAND of neighbour rows: dy = blockIdx.y - 1
 // and dz = -1, 0, +1 — three rows that are consecutive in key order (row = ... + cy * nz + cz).  A proxy's candidates in a
-// target row are the sorted entries with key in [tRow << xbits | qx(min.x), tRow << xbits | qx(max.x)]: its x-window.  The
-// windows of consecutive proxies lie next to each other, so the union [lo, hi) over the block and the band is one short
-// contiguous range of the sorted arrays (about the block's own length plus two rows).  Warp 0 finds its two ends with two
-// 16-ary searches that run side by side in its half-warps (lower bound of the smallest start key, upper bound of the largest
-// end key); the range is staged in shared memory with three 1-D bulk copies (TMA: min, max, key) completing on one
-// mbarrier, and every thread binary-searches the starts of its three windows and walks them entirely in shared memory, one
-// after the other inside ONE lock-step loop (three short windows per lane even out the loop length across the warp).  The
-// lock step is only needed for the ballot/popc compaction of hits.  The pair is emitted by the member that comes first in
-// (qx, sorted position) order, so every overlapping pair is produced exactly once; the overlap test is the reference's
-// closed-interval predicate on the original floats (bp/DbvtAabbMm.java:209-212), the keys only select candidates.
+// target row are the sorted entries whose qx lies in its x-window [qx(min.x), qx(max.x)].  Every unordered pair is emitted
+// once, by the member that comes first in (qx, sorted position) order; because the list is sorted by row first, that rule
+// folds into the window START: rows behind the proxy's own row take qx >= its qx, rows before it qx > its qx, its own row
+// the entries behind the proxy itself.  So a window is a plain index range [s, e) of the sorted arrays and needs no
+// per-candidate key test.
+// The windows of consecutive proxies lie next to each other: the union [lo, hi) over the block and the band is one short
+// contiguous range (about the block's own length plus two rows).  Warp 0 finds its two ends with two 16-ary searches that run
+// side by side in its half-warps; the range is staged in shared memory with three 1-D bulk copies (TMA: min, max, key)
+// completing on one mbarrier; every thread then finds the six ends of its three windows with interleaved branch-free binary
+// searches in shared memory and walks the three windows back to back in ONE fixed-trip loop (trip count = the warp's longest
+// concatenation, so three short windows per lane even out the length across the warp).  The loop body is the reference's
+// closed-interval overlap predicate on the original floats (bp/DbvtAabbMm.java:209-212) + the group/mask filter + the
+// ballot/popc compaction of hits; the keys only select candidates.
 // The sorted arrays are padded by SW_CH entries: a chunk may read a few entries past n, never past the allocation, and no
 // thread looks at staged entries beyond hi.
-__device__ __forceinline__ uint32_t smemLowerBound(const uint32_t* __restrict__ key, uint32_t cv, uint32_t target) {
-    uint32_t k = 0;
-#pragma unroll
-    for (uint32_t sstep = SW_CH; sstep > 0; sstep >>= 1) {  // from SW_CH itself: the result may be cv == SW_CH
-        const uint32_t t = k + sstep;
-        if (t <= cv && key[t - 1] < target) k = t;
-    }
-    return k;
-}
-
 __global__ void __launch_bounds__(256, 5)
 k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, const float4* __restrict__ smax,
         const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rowStart, const GridParams* __restrict__ grid, int uidBits,
@@ -384,9 +377,16 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
         const uint32_t xkMax = act ? quantX(amax.x, gx0, ginvX, gxmax) : 0u;
         const uint32_t tRow0 = (uint32_t)((int)row + dy * nz);  // the dz = 0 row of the band; same world: cy stays inside [0, ny)
         const bool vm = act && cz0 > 0, vp = act && cz0 + 1 < nz;  // the dz = -1 / +1 rows exist
-        // union of the block's windows: [lower bound of the smallest start key, upper bound of the largest end key)
-        uint32_t loKey = act ? (((vm ? tRow0 - 1u : tRow0) << xbits) | xkI) : 0xffffffffu;
-        uint32_t hiKey = act ? (((vp ? tRow0 + 1u : tRow0) << xbits) | xkMax) : 0u;
+        // window w (dz = w - 1) = sorted entries with key in [a_w, b_w): rows before the proxy's own take qx > xkI (key + 1 runs
+        // into the next row when qx is at its maximum: an empty window, as it must be), rows behind it qx >= xkI
+        const uint32_t a0 = (((tRow0 - 1u) << xbits) | xkI) + (dy <= 0 ? 1u : 0u);
+        const uint32_t a1 = ((tRow0 << xbits) | xkI) + (dy < 0 ? 1u : 0u);
+        const uint32_t a2 = (((tRow0 + 1u) << xbits) | xkI) + (dy < 0 ? 1u : 0u);
+        const uint32_t b0 = (((tRow0 - 1u) << xbits) | xkMax) + 1u, b1 = ((tRow0 << xbits) | xkMax) + 1u,
+                       b2 = (((tRow0 + 1u) << xbits) | xkMax) + 1u;
+        // union of the block's windows: [lower bound of the smallest start key, lower bound of the largest end key)
+        uint32_t loKey = act ? (vm ? a0 : a1) : 0xffffffffu;
+        uint32_t hiKey = act ? (vp ? b2 : b1) : 0u;
         for (int o = 16; o > 0; o >>= 1) {
             loKey = min(loKey, __shfl_xor_sync(0xffffffffu, loKey, o));
             hiKey = max(hiKey, __shfl_xor_sync(0xffffffffu, hiKey, o));
@@ -404,9 +404,11 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
             uint32_t lo = 0, hi = 0;
             if (loKey != 0xffffffffu) {  // warp-uniform: some proxy of the block has this band
                 const bool upper = lane >= 16;
-                const uint32_t r = (upper ? hiKey : loKey) >> xbits;
+                // a start key may have run into the next row (qx + 1 past the maximum): search the row the key names; an end
+                // key's row is the row of its last admissible entry
+                const uint32_t r = upper ? ((hiKey - 1u) >> xbits) : (loKey >> xbits);
                 const uint32_t a = __ldg(rowStart + r), b = __ldg(rowStart + r + 1);
-                const uint32_t pos = halfWarpLowerBound(skey, a, b, upper ? hiKey + 1u : loKey, lane);
+                const uint32_t pos = halfWarpLowerBound(skey, a, b, upper ? hiKey : loKey, lane);
                 lo = __shfl_sync(0xffffffffu, pos, 0);
                 hi = __shfl_sync(0xffffffffu, pos, 16);
             }
@@ -414,8 +416,7 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
         }
         __syncthreads();
         const uint32_t lo = sLoHi[0], hi = sLoHi[1];
-        // bit w of `closed`: window w (dz = w - 1) does not exist or has seen its end
-        uint32_t closed = act ? ((vm ? 0u : 1u) | (vp ? 0u : 4u)) : 7u;
+        const uint32_t fa = __float_as_uint(amax.w);
         for (uint32_t cs = lo & ~3u; cs < hi; cs += SW_CH) {
             const uint32_t cv = min((uint32_t)SW_CH, hi - cs);          // valid entries of the chunk
             const uint32_t cnt = (cv + 3u) & ~3u;                       // staged entries: 16-byte multiples
@@ -428,53 +429,41 @@ k_sweep(const uint32_t* __restrict__ nPtr, const float4* __restrict__ smin, cons
             }
             mbarWait(&bar, parity);
             parity ^= 1u;
-            // first candidate of each of the thread's windows in this chunk (branch-free searches in shared memory; a closed
-            // window starts at cv = nothing to do)
-            uint32_t k0 = (closed & 1u) ? cv : smemLowerBound(S.key, cv, ((tRow0 - 1u) << xbits) | xkI);
-            uint32_t k1 = (closed & 2u) ? cv : smemLowerBound(S.key, cv, (tRow0 << xbits) | xkI);
-            const uint32_t k2 = (closed & 4u) ? cv : smemLowerBound(S.key, cv, ((tRow0 + 1u) << xbits) | xkI);
-            if (dy == 0 && !(closed & 2u) && i + 1u > cs + k1) k1 = min(cv, i + 1u - cs);  // own row: only entries behind the proxy
-            int w = 0;
-            uint32_t k = k0;
-            uint32_t endKey = ((tRow0 - 1u) << xbits) | xkMax;
-            while (__any_sync(0xffffffffu, w < 3)) {
+            // the part of each window that lies in this chunk: six lower bounds, searched side by side
+            uint32_t s0 = 0, s1 = 0, s2 = 0, e0 = 0, e1 = 0, e2 = 0;
+#pragma unroll
+            for (uint32_t sstep = SW_CH; sstep > 0; sstep >>= 1) {  // from SW_CH itself: a result may be cv == SW_CH
+                uint32_t t;
+                t = s0 + sstep; if (t <= cv && S.key[t - 1] < a0) s0 = t;
+                t = s1 + sstep; if (t <= cv && S.key[t - 1] < a1) s1 = t;
+                t = s2 + sstep; if (t <= cv && S.key[t - 1] < a2) s2 = t;
+                t = e0 + sstep; if (t <= cv && S.key[t - 1] < b0) e0 = t;
+                t = e1 + sstep; if (t <= cv && S.key[t - 1] < b1) e1 = t;
+                t = e2 + sstep; if (t <= cv && S.key[t - 1] < b2) e2 = t;
+            }
+            if (dy == 0 && i + 1u > cs) s1 = max(s1, min(cv, i + 1u - cs));  // own row: only the entries behind the proxy itself
+            const uint32_t L0 = (vm && e0 > s0) ? e0 - s0 : 0u;
+            const uint32_t L1 = (act && e1 > s1) ? e1 - s1 : 0u;
+            const uint32_t L2 = (vp && e2 > s2) ? e2 - s2 : 0u;
+            const uint32_t L01 = L0 + L1, L = L01 + L2;
+            uint32_t maxL = L;
+            for (int o = 16; o > 0; o >>= 1) maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, o));
+            for (uint32_t t = 0; t < maxL; t++) {
                 bool hit = false;
                 uint32_t bodyB = 0;
-                if (w < 3) {
-                    uint32_t kj = 0;
-                    // move on while the current window has nothing more in this chunk (closed for good when a key beyond its
-                    // end was seen, to be continued in the next chunk when the chunk ran out)
-#pragma unroll
-                    for (int tr = 0; tr < 3; tr++) {
-                        if (w < 3) {
-                            const bool inChunk = k < cv;
-                            if (inChunk) kj = S.key[k];
-                            if (!inChunk || kj > endKey) {
-                                if (inChunk) closed |= 1u << w;
-                                w++;
-                                k = w == 1 ? k1 : k2;
-                                endKey = ((tRow0 + (uint32_t)(w - 1)) << xbits) | xkMax;
-                            }
-                        }
+                if (t < L) {
+                    const uint32_t k = t < L0 ? s0 + t : (t < L01 ? s1 + (t - L0) : s2 + (t - L01));
+                    const float4 bmin = S.mn[k], bmax = S.mx[k];
+                    hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
+                          (amin.z <= bmax.z) && (amax.z >= bmin.z) && filterPass(fa, __float_as_uint(bmax.w));
+                    bodyB = __float_as_uint(bmin.w);
+                    // AxisSweep3 modes: the float boxes are a monotone image of the quantised ones (necessary condition); the
+                    // pair predicate itself is on the quantised values
+                    if (hit && qmin) {
+                        const uint32_t bodyA = __float_as_uint(amin.w);
+                        hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
                     }
-                    if (w < 3) {
-                        // ties in qx across rows: only the earlier sorted position emits
-                        if ((kj & xmask) != xkI || cs + k > i) {
-                            const float4 bmin = S.mn[k], bmax = S.mx[k];
-                            hit = (amin.x <= bmax.x) && (amax.x >= bmin.x) && (amin.y <= bmax.y) && (amax.y >= bmin.y) &&
-                                  (amin.z <= bmax.z) && (amax.z >= bmin.z) &&
-                                  filterPass(__float_as_uint(amax.w), __float_as_uint(bmax.w));
-                            bodyB = __float_as_uint(bmin.w);
-                            // AxisSweep3 modes: the float boxes are a monotone image of the quantised ones (necessary
-                            // condition); the pair predicate itself is on the quantised values
-                            if (hit && qmin) {
-                                const uint32_t bodyA = __float_as_uint(amin.w);
-                                hit = sapOverlap(__ldg(qmin + bodyA), __ldg(qmax + bodyA), __ldg(qmin + bodyB), __ldg(qmax + bodyB));
-                            }
-                            if (hit) hit = slab.owns(amin, bmin);
-                        }
-                        k++;
-                    }
+                    if (hit) hit = slab.owns(amin, bmin);
                 }
                 st.push(hit, __float_as_uint(amin.w), bodyB, pairKeys, maxPairs, ctr);
             }
