@@ -169,6 +169,12 @@ struct b2c_ctx {
     uint32_t* dNLocal = nullptr;       // device count of dLocalList
     uint32_t* dNSorted = nullptr;      // device count of the sorted arrays (== nBodies / *dNLocal), written by k_gather
     uint32_t localHint = 0;            // host's last reading of *dNLocal (launch shapes only; 0 = unknown)
+    // row-grouped ordering (pairfind.cuh): zeroed block = RowOffsetsMisc | scan status[roTiles + 4] | rowCount[maxRows + 8]
+    uint32_t* dRowOrdZero = nullptr;
+    uint32_t* dSlots = nullptr;        // [N] slot of every proxy inside its row
+    uint32_t roTiles = 0;
+    uint32_t rowLenHint = 0;           // longest row of the last step the host has read
+    bool forceRadix = false;
     bool haloExported = false, haloImported = false;
     uint32_t* dExportCount = nullptr;
     bool prof = false;
@@ -382,6 +388,10 @@ static uint32_t slabUpper(const b2c_ctx* ctx) {
     return h < n ? (uint32_t)h : n;
 }
 
+// Which ordering pipeline the next pair calculation uses: rows grouped and ordered by counting (default), or the radix passes
+// when the longest row seen so far would make the quadratic row ordering matter (B2C_SORT=radix forces them).
+static bool useRowOrder(const b2c_ctx* ctx) { return !ctx->forceRadix && ctx->rowLenHint <= ROW_ORDER_MAX_LEN; }
+
 int32_t enqueueBroadphase(b2c_ctx* ctx) {
     int n = ctx->nBodies;
     const bool slab = ctx->slab.enabled != 0;
@@ -419,15 +429,33 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     }
     int npass = (12 + bitsFor((uint32_t)ctx->maxRows + 2u) + 7) / 8;
     if (npass > 4) npass = 4;
-    CK(ctx->sortBodies.reset(nUpper, (uint32_t)n, npass, s));
-    k_keys<<<nb, 256, 0, s>>>(ctx->B, n, nPtr, list, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dStep, ctx->sortBodies.st,
-                              npass);
-    mark(ctx, 2);
     ctx->sortBodies.launches = 0;
-    ctx->sortBodies.passes<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nUpper, npass, s);
-    mark(ctx, 3);
-    k_gather<<<nb, 256, 0, s>>>(ctx->B, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->sortBodies.st, npass, ctx->dGrid,
-                                ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dScyz, ctx->dNSorted);
+    if (useRowOrder(ctx)) {
+        // rows are short: group by row with one atomic per proxy, order inside the rows by counting (pairfind.cuh)
+        RowOffsetsMisc* misc = reinterpret_cast<RowOffsetsMisc*>(ctx->dRowOrdZero);
+        uint32_t* roStatus = ctx->dRowOrdZero + 4;
+        uint32_t* rowCount = ctx->dRowOrdZero + 4 + ctx->roTiles + 4;
+        CK(cudaMemsetAsync(ctx->dRowOrdZero, 0, (size_t)(4 + ctx->roTiles + 4 + ctx->maxRows + 8) * sizeof(uint32_t), s));
+        k_keys<<<nb, 256, 0, s>>>(ctx->B, n, nPtr, list, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dStep, ctx->sortBodies.st,
+                                  npass, rowCount, ctx->dSlots);
+        mark(ctx, 2);
+        k_row_offsets<<<ctx->roTiles, 256, 0, s>>>(rowCount, ctx->dGrid, ctx->dRowStart, roStatus, misc, ctx->dCtr);
+        k_row_place<<<nb, 256, 0, s>>>(ctx->sortBodies.st, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dSlots, ctx->dRowStart,
+                                       ctx->dKeys[1], ctx->dVals[1]);
+        mark(ctx, 3);
+        k_row_order<<<nb, 256, 0, s>>>(ctx->B, ctx->sortBodies.st, ctx->dGrid, ctx->dKeys[1], ctx->dVals[1], ctx->dRowStart, ctx->dSmin,
+                                       ctx->dSmax, ctx->dSrow, ctx->dScyz, ctx->dNSorted);
+        ctx->launches += 2;  // + k_keys and k_row_order, counted below like k_keys / k_gather of the radix path
+    } else {
+        CK(ctx->sortBodies.reset(nUpper, (uint32_t)n, npass, s));
+        k_keys<<<nb, 256, 0, s>>>(ctx->B, n, nPtr, list, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dStep, ctx->sortBodies.st,
+                                  npass, nullptr, nullptr);
+        mark(ctx, 2);
+        ctx->sortBodies.passes<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], nUpper, npass, s);
+        mark(ctx, 3);
+        k_gather<<<nb, 256, 0, s>>>(ctx->B, ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], ctx->sortBodies.st, npass, ctx->dGrid,
+                                    ctx->dSmin, ctx->dSmax, ctx->dSrow, ctx->dRowStart, ctx->dScyz, ctx->dNSorted);
+    }
     uint32_t* rowCnt = ctx->dRowZero;
     uint32_t* rowStatus = ctx->dRowZero + ctx->nRows;
     RowMisc* rowMisc = reinterpret_cast<RowMisc*>(ctx->dRowZero + ctx->nRows + ctx->rowTiles);
@@ -768,6 +796,7 @@ int32_t readCounters(b2c_ctx* ctx) {
         ctx->err = buf;
         return B2C_ERR_CAPACITY;
     }
+    if (useRowOrder(ctx)) ctx->rowLenHint = c.maxRowLen;  // the radix path does not measure rows: once chosen it stays
     if (ctx->slab.enabled) {
         uint32_t nl = 0;
         CK(cudaMemcpyAsync(&nl, ctx->dNLocal, sizeof(nl), cudaMemcpyDeviceToHost, ctx->stream));
@@ -818,7 +847,7 @@ static void stepSignature(const b2c_ctx* ctx, int kind, uint64_t sig[4]) {
              ((uint64_t)(uint32_t)ctx->slab.rank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
     sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide ^ ((uint64_t)slabUpper(ctx) << 40);
     sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8) |
-             ((uint32_t)(ctx->deltaPrefetch ? 1 : 0) << 16);
+             ((uint32_t)(ctx->deltaPrefetch ? 1 : 0) << 16) | ((uint32_t)(useRowOrder(ctx) ? 1 : 0) << 17);
 }
 
 static void dropStepGraphs(b2c_ctx* ctx) {
@@ -1064,6 +1093,10 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     if (ctx->maxRows > (1 << 20) - 4) ctx->maxRows = (1 << 20) - 4;  // the row shares a 32-bit key with 12 bits of x
     if ((long long)cfg->num_worlds * 5 > ctx->maxRows) return fail(B2C_ERR_BAD_ARG);
     CKC(dalloc(&ctx->dRowStart, (size_t)ctx->maxRows + 8));
+    ctx->roTiles = (uint32_t)((ctx->maxRows + 8 + ROFF_TILE - 1) / ROFF_TILE);
+    CKC(dalloc(&ctx->dRowOrdZero, (size_t)4 + ctx->roTiles + 4 + ctx->maxRows + 8 + 16));
+    CKC(dalloc(&ctx->dSlots, N));
+    { const char* e = getenv("B2C_SORT"); ctx->forceRadix = e && e[0] == 'r'; }
     CKC(dalloc(&ctx->dGrid, (size_t)1));
     CKC(dalloc(&ctx->dCtr, (size_t)1));
     CKC(cudaMallocHost((void**)&ctx->hCtrPinned, 2 * sizeof(StepCounters)));  // [1]: the prefetched contact-stream counts
@@ -1127,6 +1160,7 @@ void b2c_destroy(b2c_ctx* ctx) {
         cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dSortedKeys[i]);
         cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dMHdr[i]); cudaFree(ctx->dMPts[i]); cudaFree(ctx->dPairFirst[i]);
     }
+    cudaFree(ctx->dRowOrdZero); cudaFree(ctx->dSlots);
     cudaFree(ctx->dNSorted); cudaFree(ctx->dNLocal); cudaFree(ctx->dOwner); cudaFree(ctx->dLocalList);
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dScyz); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);

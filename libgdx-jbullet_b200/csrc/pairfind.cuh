@@ -48,7 +48,7 @@ struct SlabFilter {
 __global__ void __launch_bounds__(256)
 k_keys(BodyArrays B, int nConst, const uint32_t* __restrict__ nPtr, const uint32_t* __restrict__ list, StepCounters* ctr,
        const GridParams* __restrict__ grid, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* stepPtr, RadixState* st,
-       int npass) {
+       int npass, uint32_t* __restrict__ rowCount, uint32_t* __restrict__ slots) {
     __shared__ uint32_t sh[4][256];
     __shared__ bool isLast;
     for (int k = threadIdx.x; k < 4 * 256; k += 256) (&sh[0][0])[k] = 0;
@@ -80,6 +80,21 @@ k_keys(BodyArrays B, int nConst, const uint32_t* __restrict__ nPtr, const uint32
             xk = quantX(a.x, g.x0, g.invX, g.xmaxf);
         }
         const uint32_t key = (row << g.xbits) | xk;
+        if (rowCount) {
+            // row-grouped ordering (k_row_order below): the proxy takes a slot in its row; neighbouring proxies mostly share
+            // their row, so one atomic per distinct row of the warp
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? row : 0xffffffffu);
+            uint32_t base = 0;
+            const int leader = __ffs(peers) - 1;
+            if (valid && lane == leader) base = atomicAdd(&rowCount[row], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) {
+                keys[t] = key;
+                vals[t] = i;
+                slots[t] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            }
+            continue;
+        }
         if (valid) {
             keys[t] = key;
             vals[t] = i;
@@ -95,6 +110,10 @@ k_keys(BodyArrays B, int nConst, const uint32_t* __restrict__ nPtr, const uint32
                 if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p][d], (uint32_t)__popc(peers));
             }
         }
+    }
+    if (rowCount) {  // no radix passes follow: only the count is published
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->n = n;
+        return;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < npass * 256; k += 256) {
@@ -180,6 +199,150 @@ k_gather(BodyArrays B, const uint32_t* keysA, const uint32_t* keysB, const uint3
         }
         if (j == n - 1)
             for (uint32_t r = row + 1; r <= lastRow; r++) rowStart[r] = n;
+    }
+}
+
+// ---- row-grouped ordering: the sorted order without radix passes ------------------------------------------------------------
+// The sweep needs the proxies grouped by row and ordered by qx inside a row; the order of equal keys is irrelevant (it only
+// decides WHICH member of a pair emits it).  Rows are short (a few hundred proxies at most in a compact world), so instead of
+// 3-4 stable onesweep passes over all keys:
+//   k_keys          every proxy takes a slot in its row (one atomic per distinct row of a warp)
+//   k_row_offsets   exclusive scan of the row counts = the row start table (single pass, decoupled look-back) + longest row
+//   k_row_place     proxy -> rowStart[row] + slot (grouped by row, arbitrary order inside)
+//   k_row_order     one thread per grouped entry: its place inside the row is the number of row members with a smaller
+//                   (qx, proxy index); writes the sorted AABB SoA / keys / cell coordinates directly (the gather is fused)
+// Work is sum(len^2) key compares on L1-resident rows — a few microseconds for rows of 100-300.  The host switches back to the
+// radix passes when the longest row it has seen makes that quadratic term matter (ROW_ORDER_MAX_LEN).
+constexpr uint32_t ROW_ORDER_MAX_LEN = 4096;
+constexpr int ROFF_PER = 16, ROFF_TILE = 256 * ROFF_PER;
+struct RowOffsetsMisc {
+    uint32_t ticket, pad[3];
+};
+
+__global__ void __launch_bounds__(256)
+k_row_offsets(const uint32_t* __restrict__ rowCount, const GridParams* __restrict__ grid, uint32_t* __restrict__ rowStart,
+              uint32_t* status, RowOffsetsMisc* misc, StepCounters* ctr) {
+    __shared__ uint32_t sTile, sExcl, warpSum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nR = (uint32_t)(grid->nrows + grid->numWorlds) + 2u;  // rowStart[0 .. lastRow] with lastRow = nrows + numWorlds + 1
+    if (threadIdx.x == 0) sTile = atomicAdd(&misc->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sTile;
+    if (tile * ROFF_TILE >= nR) return;  // tiles are taken in ticket order, so every tile before a needed one is needed too
+    const uint32_t base = tile * ROFF_TILE + threadIdx.x * ROFF_PER;
+    uint32_t c[ROFF_PER];
+    uint32_t sum = 0, mx = 0;
+    const uint32_t nGrid = (uint32_t)grid->nrows;  // only grid rows are ordered (and count for the longest row)
+#pragma unroll
+    for (int k = 0; k < ROFF_PER; k += 4) {  // rowCount is 16-byte aligned and padded
+        const uint4 v = (base + k < nR) ? *reinterpret_cast<const uint4*>(rowCount + base + k) : make_uint4(0, 0, 0, 0);
+        c[k] = v.x; c[k + 1] = (base + k + 1 < nR) ? v.y : 0u; c[k + 2] = (base + k + 2 < nR) ? v.z : 0u;
+        c[k + 3] = (base + k + 3 < nR) ? v.w : 0u;
+        sum += c[k] + c[k + 1] + c[k + 2] + c[k + 3];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (base + k + q < nGrid) mx = max(mx, c[k + q]);
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx) atomicMax(&ctr->maxRowLen, mx);
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = lane < 8 ? warpSum[lane] : 0u, vi = v;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += t;
+        }
+        if (lane < 8) warpSum[lane] = vi - v;
+        const uint32_t total = __shfl_sync(0xffffffffu, vi, 7);
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) rs_store_release(status, total | RS_FLAG_INC);
+        } else {
+            if (lane == 0) rs_store_release(status + tile, total | RS_FLAG_AGG);
+            int t = (int)tile - 1;  // decoupled look-back, 32 predecessors per round
+            for (;;) {
+                const uint32_t sv = (t - lane >= 0) ? rs_load_relaxed(status + (t - lane)) : RS_FLAG_INC;
+                const uint32_t notReady = __ballot_sync(0xffffffffu, (sv & ~RS_VAL_MASK) == 0u);
+                const uint32_t incMask = __ballot_sync(0xffffffffu, (sv & ~RS_VAL_MASK) == RS_FLAG_INC);
+                const int firstInc = incMask ? __ffs(incMask) - 1 : 32;
+                const uint32_t need = firstInc >= 31 ? 0xffffffffu : ((2u << firstInc) - 1u);
+                if (notReady & need) continue;  // a predecessor has not published yet
+                uint32_t v2 = (lane <= firstInc) ? (sv & RS_VAL_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+                excl += v2;
+                if (firstInc < 32) break;
+                t -= 32;
+            }
+            if (lane == 0) rs_store_release(status + tile, (excl + total) | RS_FLAG_INC);
+        }
+        if (lane == 0) sExcl = excl;
+    }
+    __syncthreads();
+    uint32_t run = sExcl + warpSum[warp] + (incl - sum);
+#pragma unroll
+    for (int k = 0; k < ROFF_PER; k++) {
+        if (base + k < nR) rowStart[base + k] = run;
+        run += c[k];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_row_place(const RadixState* __restrict__ st, const GridParams* __restrict__ grid, const uint32_t* __restrict__ keys,
+            const uint32_t* __restrict__ vals, const uint32_t* __restrict__ slots, const uint32_t* __restrict__ rowStart,
+            uint32_t* __restrict__ gkey, uint32_t* __restrict__ gval) {
+    const uint32_t n = st->n;
+    const int xbits = grid->xbits;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t k = keys[t];
+        const uint32_t pos = rowStart[k >> xbits] + slots[t];
+        gkey[pos] = k;
+        gval[pos] = vals[t];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_row_order(BodyArrays B, const RadixState* __restrict__ st, const GridParams* __restrict__ grid, const uint32_t* __restrict__ gkey,
+            const uint32_t* __restrict__ gval, const uint32_t* __restrict__ rowStart, float4* __restrict__ smin,
+            float4* __restrict__ smax, uint32_t* __restrict__ skey, uint32_t* __restrict__ scyz, uint32_t* __restrict__ nSortedOut) {
+    const uint32_t n = st->n;
+    const int xbits = grid->xbits;
+    const uint32_t nrows = (uint32_t)grid->nrows, rpw = (uint32_t)grid->rowsPerWorld, nz = (uint32_t)grid->nz;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *nSortedOut = n;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint32_t k = gkey[p];
+        const uint32_t body = gval[p];
+        const uint32_t row = k >> xbits;
+        const uint32_t a = rowStart[row], b = rowStart[row + 1];
+        uint32_t rank = p - a;  // rows outside the grid (large proxies, dead slots) need no order
+        if (row < nrows) {
+            rank = 0;
+            for (uint32_t q = a; q < b; q++) {  // neighbouring threads walk the same row: broadcast loads
+                const uint32_t kq = __ldg(gkey + q);
+                rank += (kq < k || (kq == k && __ldg(gval + q) < body)) ? 1u : 0u;
+            }
+        }
+        const uint32_t j = a + rank;
+        float4 mn = B.effMin[body], mx = B.effMax[body];
+        mn.w = __uint_as_float(body);
+        mx.w = __uint_as_float(B.filt[body]);
+        smin[j] = mn;
+        smax[j] = mx;
+        skey[j] = k;
+        uint32_t c = 0xffffffffu;  // rows outside the grid: large proxies, dead slots
+        if (row < nrows) {
+            const uint32_t rem = row % rpw;
+            c = ((rem / nz) << 16) | (rem % nz);
+        }
+        scyz[j] = c;
     }
 }
 

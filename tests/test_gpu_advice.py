@@ -121,3 +121,25 @@ def test_aabb_overflow_guard_disables_the_object(gpu_pkg):
     parity.step_and_compare(gw, ow, xf, sc.extent)
     assert np.array_equal(gw.aabbs()[-1], created)
     assert r["pairs"] > 300
+
+
+def test_long_rows_switch_to_the_radix_passes(gpu_pkg):
+    """A world strung out along the sweep axis puts thousands of proxies into one grid row: the row-grouped ordering is
+    quadratic there, so the library falls back to the radix passes from the next step on — same pairs either way."""
+    n = 6000
+    sc = scenes.Scene()
+    s = sc.add_shape("sphere", 0.5)
+    rng = np.random.default_rng(5)
+    pos = np.stack([np.arange(n) * 0.9, rng.uniform(-0.05, 0.05, n), rng.uniform(-0.05, 0.05, n)], axis=1)
+    for _ in range(n):
+        sc.body_shape.append(s); sc.static.append(False); sc.group.append(1); sc.mask.append(-1); sc.world.append(0)
+    sc.base = scenes.make_xf(np.tile(np.eye(3), (n, 1, 1)), pos)
+    sc.vel = rng.uniform(-0.01, 0.01, size=(n, 3))
+    sc.extent = float(n)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    launches = []
+    for step in range(4):
+        r = parity.step_and_compare(gw, ow, sc.transforms(step), sc.extent)
+        launches.append(gw.stats()["kernel_launches"])
+    assert r["pairs"] >= n - 1
+    assert launches[-1] != launches[0], "the ordering pipeline did not change after the long row was seen"

@@ -8,6 +8,7 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
 timeout 1500 python -m pytest tests -m gpu -q --durations=15 ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"
 tail -40 gpurun_out/pytest_gpu_$TAG.log
 fi
+if [ "${SKIP_TESTS:-0}" != "1" ]; then B2C_SORT=radix timeout 600 python -m pytest tests -m gpu -q -k "c2_bin or c5_spheres or c4_batched or c1_stack or partitioned_bin" > gpurun_out/pytest_gpu_radix_$TAG.log 2>&1; echo "pytest radix rc=$?"; tail -3 gpurun_out/pytest_gpu_radix_$TAG.log; fi
 timeout 600 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 tail -5 gpurun_out/bench_$TAG.err
 python - <<PY
