@@ -1094,6 +1094,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     if ((long long)cfg->num_worlds * 5 > ctx->maxRows) return fail(B2C_ERR_BAD_ARG);
     CKC(dalloc(&ctx->dRowStart, (size_t)ctx->maxRows + 8));
     ctx->roTiles = (uint32_t)((ctx->maxRows + 8 + ROFF_TILE - 1) / ROFF_TILE);
+    ctx->roTiles = (ctx->roTiles + 3u) & ~3u;  // keeps rowCount (behind misc and status) 16-byte aligned for its 128-bit loads
     CKC(dalloc(&ctx->dRowOrdZero, (size_t)4 + ctx->roTiles + 4 + ctx->maxRows + 8 + 16));
     CKC(dalloc(&ctx->dSlots, N));
     { const char* e = getenv("B2C_SORT"); ctx->forceRadix = e && e[0] == 'r'; }
