@@ -324,11 +324,19 @@ k_row_order(BodyArrays B, const RadixState* __restrict__ st, const GridParams* _
         const uint32_t a = rowStart[row], b = rowStart[row + 1];
         uint32_t rank = p - a;  // rows outside the grid (large proxies, dead slots) need no order
         if (row < nrows) {
-            rank = 0;
-            for (uint32_t q = a; q < b; q++) {  // neighbouring threads walk the same row: broadcast loads
+            // neighbouring threads walk the same row: broadcast loads, eight in flight per thread.  Ties in the key are
+            // broken by the proxy index; they are looked up only when a tie shows (rare: 4096 qx values per row)
+            uint32_t less = 0, ties = 0;
+#pragma unroll 8
+            for (uint32_t q = a; q < b; q++) {
                 const uint32_t kq = __ldg(gkey + q);
-                rank += (kq < k || (kq == k && __ldg(gval + q) < body)) ? 1u : 0u;
+                less += kq < k ? 1u : 0u;
+                ties += kq == k ? 1u : 0u;
             }
+            rank = less;
+            if (ties > 1u)
+                for (uint32_t q = a; q < b; q++)
+                    rank += (__ldg(gkey + q) == k && __ldg(gval + q) < body) ? 1u : 0u;
         }
         const uint32_t j = a + rank;
         float4 mn = B.effMin[body], mx = B.effMax[body];
