@@ -395,8 +395,8 @@ static bool useRowOrder(const b2c_ctx* ctx) { return !ctx->forceRadix && ctx->ro
 int32_t enqueueBroadphase(b2c_ctx* ctx) {
     int n = ctx->nBodies;
     const bool slab = ctx->slab.enabled != 0;
-    mark(ctx, 0);
     if (!slab) {
+        mark(ctx, 0);
         int32_t rc = runAabbKernel(ctx, true);  // AABB update + (fused) the grid of this step
         if (rc) return rc;
     } else if (!ctx->haloImported) {
