@@ -87,11 +87,24 @@ int32_t b2c_shape_register_hull(b2c_ctx*, const float* points_xyz, int32_t num_p
 int32_t b2c_shape_register_plane(b2c_ctx*, const float normal[3], float constant, int32_t* shape_out);
 /* sh/BvhTriangleMeshShape.java:68-90 with useQuantizedAabbCompression=true over one
  * sh/IndexedMesh.java part: vertices with a byte stride, 32-bit indices with a byte stride per
- * triangle (sh/TriangleIndexVertexArray.java:51-94).  The data is copied; the BVH is built on the host
+ * triangle (sh/TriangleIndexVertexArray.java:51-94; use b2c_shape_register_mesh_parts for 16-bit indices / several parts).  The data is copied; the BVH is built on the host
  * exactly as sh/OptimizedBvh.java:283-342 and uploaded. */
 int32_t b2c_shape_register_mesh(b2c_ctx*, const void* vertex_base, int32_t num_vertices, int32_t vertex_stride,
                                 const void* index_base, int32_t num_triangles, int32_t index_stride,
                                 const float scaling[3], int32_t* shape_out);
+/* The same over a sh/TriangleIndexVertexArray.java:72-100 with several parts, each an sh/IndexedMesh.java:35-47 with its own
+ * index type (addIndexedMesh(mesh, ScalarType.SHORT | INTEGER); sh/ByteBufferVertexData.java:75-84 reads SHORT indices as
+ * unsigned).  index_stride is IndexedMesh.triangleIndexStride (bytes per TRIANGLE; the reference steps stride / 3 per index).
+ * Contact points on the mesh report partId1 = the part and index1 = the triangle inside it (b2c_manifold_point); the raw
+ * detector records carry partId << 21 | index in `tri` (sh/OptimizedBvh.java:65,278: at most 1024 parts of 2^21 triangles). */
+typedef enum { B2C_INDEX_INT16 = 2, B2C_INDEX_INT32 = 4 } b2c_index_type;
+typedef struct {
+    const void* vertex_base;  int32_t num_vertices;  int32_t vertex_stride;  /* 3 floats per vertex, stride in bytes */
+    const void* index_base;   int32_t num_triangles; int32_t index_stride;   /* bytes per triangle */
+    int32_t index_type;                                                     /* b2c_index_type */
+} b2c_indexed_mesh;
+int32_t b2c_shape_register_mesh_parts(b2c_ctx*, const b2c_indexed_mesh* parts, int32_t num_parts, const float scaling[3],
+                                      int32_t* shape_out);
 /* sh/CompoundShape.java:50-82: new CompoundShape() followed by addChildShape(localTransform_i, child_i) for i = 0..n-1.
  * child_shapes = ids of box / sphere / hull shapes registered before; child_transforms12 = n x (9 row-major basis floats +
  * origin).  The local AABB is the running Math.min / Math.max of the children's AABBs (:60-80), collisionMargin stays 0 (:49).
@@ -221,7 +234,7 @@ typedef struct {
     float world_a[3], world_b[3], normal_on_b[3];
     float distance;
     int32_t life_src;                 /* life_time << 8 | (src_slot + 1)  (life_time saturates at 2^24 - 1) */
-    int32_t index1;                   /* triangle index for mesh pairs, else 0 */
+    int32_t index1;                   /* mesh pairs: partId1 << 21 | index1 (= the triangle index for a one-part mesh), else 0 */
 } b2c_packed_point; /* 48 bytes */
 int32_t b2c_get_packed_contacts(b2c_ctx*, b2c_packed_header* headers_out, int32_t cap_headers, b2c_packed_point* points_out,
                                 int32_t cap_points, int32_t* num_headers_out, int32_t* num_points_out);

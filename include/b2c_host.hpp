@@ -83,6 +83,14 @@ public:
         points.resize((size_t)np);
         if (nh) check(b2c_get_packed_contacts(ctx, headers.data(), nh, points.data(), np, &nh, &np), ctx);
     }
+    // The same manifolds as full 96-byte points with uid headers: what the Java shim's GpuDispatcher reads (b2c_get_contacts).
+    void getContacts(std::vector<b2c_contact_header>& headers, std::vector<b2c_manifold_point>& points) {
+        int32_t nh = 0, np = 0;
+        check(b2c_get_contacts(ctx, nullptr, 0, nullptr, 0, &nh, &np), ctx);
+        headers.resize((size_t)nh);
+        points.resize((size_t)np);
+        if (nh) check(b2c_get_contacts(ctx, headers.data(), nh, points.data(), np, &nh, &np), ctx);
+    }
     int32_t numManifolds = 0, numContactsAdded = 0;
 private:
     b2c_ctx* ctx;
@@ -175,6 +183,33 @@ public:
     // RigidBody.checkCollideWithOverride (dynamics/RigidBody.java:624-639): constraint-linked bodies are not dispatched
     void setNoCollidePairs(const std::vector<BroadphasePair>& links) {
         check(b2c_set_no_collide_pairs(ctx, (int32_t)links.size(), links.empty() ? nullptr : &links[0].proxy0), ctx);
+    }
+    // ---- the fast path of INTEGRATION.md §4: a host that owns the step loop ---------------------------------------
+    // once: the uid-keyed packed contact stream and the pair-cache events are produced inside the step itself
+    void enableFastPath() {
+        check(b2c_set_contact_prefetch(ctx, 3), ctx);
+        check(b2c_set_pair_delta_prefetch(ctx, 1), ctx);
+    }
+    struct FastStep {
+        int32_t numPairs = 0, numManifolds = 0, numContactsAdded = 0;
+        std::vector<BroadphasePair> added, removed;          // pair-cache events of the step
+        std::vector<b2c_packed_uid_header> headers;          // touching manifolds
+        std::vector<b2c_packed_point> points;
+    };
+    // b2c_set_transforms + b2c_step_device + b2c_get_pair_deltas + b2c_begin_contact_download + b2c_sync_counts +
+    // b2c_get_packed_contacts_uid, with buffers of capacity capPairs pairs (resized to the counts on return)
+    void stepFast(int32_t n, const float* planes12, int32_t capPairs, FastStep& out) {
+        out.added.resize((size_t)capPairs); out.removed.resize((size_t)capPairs);
+        out.headers.resize((size_t)capPairs); out.points.resize((size_t)capPairs * 4);
+        check(b2c_set_transforms(ctx, n, nullptr, planes12), ctx);
+        check(b2c_step_device(ctx), ctx);
+        int32_t na = 0, nr = 0, nh = 0, np = 0;
+        check(b2c_get_pair_deltas(ctx, &out.added[0].proxy0, capPairs, &out.removed[0].proxy0, capPairs, &na, &nr), ctx);
+        check(b2c_begin_contact_download(ctx, out.headers.data(), capPairs, out.points.data(), capPairs * 4), ctx);
+        check(b2c_sync_counts(ctx, &out.numPairs, &out.numManifolds, &out.numContactsAdded), ctx);
+        check(b2c_get_packed_contacts_uid(ctx, out.headers.data(), capPairs, out.points.data(), capPairs * 4, &nh, &np), ctx);
+        out.added.resize((size_t)na); out.removed.resize((size_t)nr);
+        out.headers.resize((size_t)nh); out.points.resize((size_t)np);
     }
     GpuBroadphase* getBroadphase() { return broadphase; }
     GpuPairCache* getPairCache() { return broadphase->getOverlappingPairCache(); }

@@ -27,6 +27,12 @@ final class B2C {
         JAVA_FLOAT.withName("dbvt_predicted_frames"), JAVA_INT.withName("max_compound_items"),
         MemoryLayout.sequenceLayout(4, JAVA_INT).withName("reserved"));
 
+    // b2c_indexed_mesh: one sh/IndexedMesh.java part (40 bytes with the trailing pad of the 8-byte aligned struct)
+    static final StructLayout INDEXED_MESH = MemoryLayout.structLayout(
+        ADDRESS.withName("vertex_base"), JAVA_INT.withName("num_vertices"), JAVA_INT.withName("vertex_stride"),
+        ADDRESS.withName("index_base"), JAVA_INT.withName("num_triangles"), JAVA_INT.withName("index_stride"),
+        JAVA_INT.withName("index_type"), MemoryLayout.paddingLayout(4));
+
     static final MethodHandle defaultConfig = h("b2c_default_config", FunctionDescriptor.ofVoid(ADDRESS));
     static final MethodHandle create = h("b2c_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle destroy = h("b2c_destroy", FunctionDescriptor.ofVoid(ADDRESS));
@@ -37,6 +43,9 @@ final class B2C {
     static final MethodHandle shapePlane = h("b2c_shape_register_plane", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_FLOAT, ADDRESS));
     static final MethodHandle shapeMesh = h("b2c_shape_register_mesh",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    // TriangleIndexVertexArray with several IndexedMesh parts / 16-bit indices
+    static final MethodHandle shapeMeshParts = h("b2c_shape_register_mesh_parts",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     // new CompoundShape() + addChildShape(localTransform_i, child_i): child shape ids + n x 12 floats
     static final MethodHandle shapeCompound = h("b2c_shape_register_compound",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
@@ -77,6 +86,21 @@ final class B2C {
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     // SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110)
     static final MethodHandle computeIslands = h("b2c_compute_islands", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+
+    static final MethodHandle setPairDeltaPrefetch = h("b2c_set_pair_delta_prefetch", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    static final MethodHandle getBroadphaseAabb = h("b2c_get_broadphase_aabb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    // uid-keyed packed contact stream: a host that follows the pair cache through its deltas needs no pair list
+    static final MethodHandle getPackedContactsUid = h("b2c_get_packed_contacts_uid",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    // one world over several GPUs (slabs with a halo): the exchanges between these calls are NCCL all-gathers on b2c_stream
+    static final MethodHandle setPartition = h("b2c_set_partition", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    static final MethodHandle mgpuUpdateExportHalo = h("b2c_mgpu_update_export_halo", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    static final MethodHandle mgpuImportHalo = h("b2c_mgpu_import_halo", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+    static final MethodHandle mgpuBroadphase = h("b2c_mgpu_broadphase", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle mgpuExportDepartedSlot = h("b2c_mgpu_export_departed_slot", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    static final MethodHandle mgpuImportArrivalSlots = h("b2c_mgpu_import_arrival_slots", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+    static final MethodHandle mgpuNarrowphase = h("b2c_mgpu_narrowphase", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle stream = h("b2c_stream", FunctionDescriptor.of(ADDRESS, ADDRESS));
 
     static void check(int rc, MemorySegment ctx) {
         if (rc != 0) {

@@ -23,6 +23,7 @@ public class GpuBroadphase extends BroadphaseInterface {
     final MemorySegment uids;                 // uids touched this step
     int touched = 0;
     final MemorySegment pairBuf;              // 2 x int32 per pair
+    final MemorySegment addedBuf, removedBuf; // the step's pair-cache events (b2c_get_pair_deltas), 2 x int32 per pair
     final MemorySegment scratchInt;
     final ObjectArrayList<GpuProxy> proxies = new ObjectArrayList<GpuProxy>();
     final GpuPairCache pairCache = new GpuPairCache(this);
@@ -39,11 +40,18 @@ public class GpuBroadphase extends BroadphaseInterface {
         this.aabbPlanes = arena.allocate(JAVA_FLOAT, 6L * maxBodies);
         this.uids = arena.allocate(JAVA_INT, maxBodies);
         this.pairBuf = arena.allocate(JAVA_INT, 2L * maxPairs);
+        this.addedBuf = arena.allocate(JAVA_INT, 2L * maxPairs);
+        this.removedBuf = arena.allocate(JAVA_INT, 2L * maxPairs);
         this.scratchInt = arena.allocate(JAVA_INT, 4);
+        try {
+            B2C.check((int) B2C.setPairDeltaPrefetch.invokeExact(ctx, 1), ctx);   // the deltas come out of the pair calculation itself
+        } catch (Throwable t) { throw new RuntimeException(t); }
     }
 
-    /** bp/BroadphaseInterface.java:35.  {@code userPtr} is the CollisionObject; its shape handle and transform are
-     *  registered by GpuCollisionWorld.addCollisionObject, which calls b2c_proxy_create (uid = ++gid like bp/DbvtBroadphase.java:179). */
+    /** bp/BroadphaseInterface.java:35, called by the reference's own CollisionWorld.addCollisionObject
+     *  (disp/CollisionWorld.java:102-121) with {@code userPtr} = the CollisionObject: its shape is registered on first use and
+     *  the proxy created from shape + world transform by GpuShapes.createProxyFor -> b2c_proxy_create (uid = ++gid like
+     *  bp/DbvtBroadphase.java:179; the device recomputes the identical AABB the caller passes in). */
     @Override
     public BroadphaseProxy createProxy(Vector3 aabbMin, Vector3 aabbMax, BroadphaseNativeType shapeType, Object userPtr,
                                        short group, short mask, Dispatcher dispatcher, Object multiSapProxy) {
@@ -86,11 +94,22 @@ public class GpuBroadphase extends BroadphaseInterface {
             B2C.check((int) B2C.calculateOverlappingPairs.invokeExact(ctx, scratchInt), ctx);
             int n = scratchInt.get(JAVA_INT, 0);
             B2C.check((int) B2C.getPairs.invokeExact(ctx, pairBuf, (int) (pairBuf.byteSize() / 8), scratchInt), ctx);
-            pairCache.refresh(pairBuf, n, proxies);   // materialises BroadphasePair views, fires ghost add/remove by diff
+            int cap = (int) (addedBuf.byteSize() / 8);
+            B2C.check((int) B2C.getPairDeltas.invokeExact(ctx, addedBuf, cap, removedBuf, cap, scratchInt.asSlice(4), scratchInt.asSlice(8)), ctx);
+            // keeps the BroadphasePair objects of surviving pairs, creates / drops the others, fires the ghost add / remove events
+            pairCache.refresh(pairBuf, n, addedBuf, scratchInt.get(JAVA_INT, 4), removedBuf, scratchInt.get(JAVA_INT, 8), proxies, dispatcher);
         } catch (Throwable t) { throw new RuntimeException(t); }
     }
 
     @Override public OverlappingPairCache getOverlappingPairCache() { return pairCache; }
-    @Override public void getBroadphaseAabb(Vector3 mn, Vector3 mx) { mn.set(-1e30f, -1e30f, -1e30f); mx.set(1e30f, 1e30f, 1e30f); }
+    /** bp/BroadphaseInterface.java:48: unbounded for Dbvt / Simple, the world box for the AxisSweep3 modes. */
+    @Override public void getBroadphaseAabb(Vector3 mn, Vector3 mx) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment lo = a.allocate(JAVA_FLOAT, 3), hi = a.allocate(JAVA_FLOAT, 3);
+            B2C.check((int) B2C.getBroadphaseAabb.invokeExact(ctx, lo, hi), ctx);
+            mn.set(lo.getAtIndex(JAVA_FLOAT, 0), lo.getAtIndex(JAVA_FLOAT, 1), lo.getAtIndex(JAVA_FLOAT, 2));
+            mx.set(hi.getAtIndex(JAVA_FLOAT, 0), hi.getAtIndex(JAVA_FLOAT, 1), hi.getAtIndex(JAVA_FLOAT, 2));
+        } catch (Throwable t) { throw new RuntimeException(t); }
+    }
     @Override public void printStats() { }
 }

@@ -25,7 +25,7 @@ public class GpuDispatcher extends Dispatcher {
     final MemorySegment ctx;
     final Arena arena = Arena.ofConfined();
     final MemorySegment headers;   // b2c_contact_header[maxPairs]  (32 B)
-    final MemorySegment points;    // b2c_manifold_point[2*maxPairs] (96 B)
+    final MemorySegment points;    // b2c_manifold_point[4*maxPairs] (96 B)
     final MemorySegment out = arena.allocate(JAVA_INT, 4);
     final ObjectArrayList<PersistentManifold> manifolds = new ObjectArrayList<PersistentManifold>();
     /** (pair, child code): a plain pair owns one manifold, a compound pair one per child algorithm. */
@@ -37,7 +37,7 @@ public class GpuDispatcher extends Dispatcher {
         this.ctx = ctx;
         this.broadphase = bp;
         this.headers = arena.allocate(32L * maxPairs);
-        this.points = arena.allocate(96L * 2 * maxPairs);
+        this.points = arena.allocate(96L * 4 * maxPairs);   // a manifold holds up to 4 points
     }
 
     /** bp/Dispatcher.java:58 */
@@ -55,20 +55,20 @@ public class GpuDispatcher extends Dispatcher {
             long o = 32L * h;
             int uid0 = headers.get(JAVA_INT, o), uid1 = headers.get(JAVA_INT, o + 4);
             int body0 = headers.get(JAVA_INT, o + 8), body1 = headers.get(JAVA_INT, o + 12);
-            int n = headers.get(JAVA_INT, o + 16), first = headers.get(JAVA_INT, o + 24);
+            int n = headers.get(JAVA_INT, o + 16), algorithm = headers.get(JAVA_INT, o + 20), first = headers.get(JAVA_INT, o + 24);
             // pair_index < 0: child manifold of a compound pair (disp/CompoundCollisionAlgorithm.java:49-75 keeps one child
             // algorithm, hence one manifold, per child): v = -1 - pair_index carries (child0 + 1) | (child1 + 1) << 15
             int pairIndex = headers.get(JAVA_INT, o + 28);
             ManifoldKey key = new ManifoldKey(uid0, uid1, pairIndex < 0 ? -1 - pairIndex : 0);   // 0 for every plain pair
             PersistentManifold m = byPair.get(key);
-            ManifoldPoint[] old = null;
+            GpuManifolds.SolverState[] old = null;
             if (m == null) {
                 m = new PersistentManifold();
                 m.init(broadphase.proxies.getQuick(body0 - 1).clientObject, broadphase.proxies.getQuick(body1 - 1).clientObject, 0);
             } else {
                 old = GpuManifolds.snapshotSolverState(m);       // copies of the 4 points' warm-start fields
             }
-            GpuManifolds.fill(m, points, first, n, old);         // geometry from the device, solver state via src_slot
+            GpuManifolds.fill(m, points, first, n, old, algorithm);   // geometry from the device, solver state via src_slot
             next.put(key, m);
             manifolds.add(m);
         }
@@ -79,7 +79,12 @@ public class GpuDispatcher extends Dispatcher {
     @Override public int getNumManifolds() { return manifolds.size(); }                               // bp/Dispatcher.java:62
     @Override public PersistentManifold getManifoldByIndexInternal(int i) { return manifolds.getQuick(i); }  // :64
     @Override public ObjectArrayList<PersistentManifold> getInternalManifoldPointer() { return manifolds; }
-    @Override public boolean needsCollision(CollisionObject a, CollisionObject b) { return a.isActive() || b.isActive(); }
+    /** disp/CollisionDispatcher.java:198-223.  On the device the same rule runs in k_classify: activity from
+     *  b2c_set_activation, checkCollideWith from b2c_set_no_collide_pairs (the constraint-linked pairs the shim mirrors). */
+    @Override public boolean needsCollision(CollisionObject a, CollisionObject b) {
+        if (!a.isActive() && !b.isActive()) return false;
+        return a.checkCollideWith(b);
+    }
     @Override public boolean needsResponse(CollisionObject a, CollisionObject b) {
         return a.hasContactResponse() && b.hasContactResponse() && (!a.isStaticOrKinematicObject() || !b.isStaticOrKinematicObject());
     }

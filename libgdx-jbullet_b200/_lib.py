@@ -27,6 +27,12 @@ class Config(C.Structure):
     ]
 
 
+class IndexedMesh(C.Structure):
+    """b2c_indexed_mesh (sh/IndexedMesh.java:35-47 + its ScalarType)."""
+    _fields_ = [("vertex_base", C.c_void_p), ("num_vertices", C.c_int32), ("vertex_stride", C.c_int32),
+                ("index_base", C.c_void_p), ("num_triangles", C.c_int32), ("index_stride", C.c_int32), ("index_type", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("num_pairs", C.c_int32), ("num_manifolds", C.c_int32), ("num_contacts_added", C.c_int32),
@@ -67,7 +73,7 @@ EXPORTS = [
     "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest",
     "b2c_shape_register_compound", "b2c_get_packed_contacts", "b2c_set_contact_prefetch", "b2c_begin_contact_download",
     "b2c_get_packed_contacts_uid", "b2c_set_pair_delta_prefetch", "b2c_set_partition_slabs", "b2c_get_partition",
-    "b2c_mgpu_halo_slot_bytes", "b2c_mgpu_update_export_halo", "b2c_mgpu_import_halo",
+    "b2c_mgpu_halo_slot_bytes", "b2c_mgpu_update_export_halo", "b2c_mgpu_import_halo", "b2c_shape_register_mesh_parts",
 ]
 NUM_STAGES = 12
 CONTACT_HEADER_DTYPE = np.dtype([
@@ -116,6 +122,7 @@ def load():
     L.b2c_shape_register_hull.argtypes = [vp, vp, i32, f32, pi32]
     L.b2c_shape_register_plane.argtypes = [vp, vp, f32, pi32]
     L.b2c_shape_register_mesh.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, pi32]
+    L.b2c_shape_register_mesh_parts.argtypes = [vp, C.POINTER(IndexedMesh), i32, vp, pi32]
     L.b2c_mesh_get_bvh.argtypes = [vp, i32, vp, i32, pi32, vp]
     L.b2c_shape_register_compound.argtypes = [vp, i32, vp, vp, pi32]
     L.b2c_proxy_create.argtypes = [vp, i32, vp, C.c_int16, C.c_int16, i32, i32, pi32]

@@ -37,6 +37,7 @@ struct HostMesh {
     int4* nodes = nullptr;
     float* verts = nullptr;
     int* idx = nullptr;
+    int* partStart = nullptr;
     HostBvh bvh;
 };
 
@@ -1151,7 +1152,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     ctx->graphs.clear();
     cudaFree(ctx->dShapes); cudaFree(ctx->dHullPts); cudaFree(ctx->dMeshes);
-    for (auto& m : ctx->meshes) { cudaFree(m.nodes); cudaFree(m.verts); cudaFree(m.idx); }
+    for (auto& m : ctx->meshes) { cudaFree(m.nodes); cudaFree(m.verts); cudaFree(m.idx); cudaFree(m.partStart); }
     cudaFree(ctx->B.xf4); cudaFree(ctx->B.shape); cudaFree(ctx->B.filt); cudaFree(ctx->B.flags); cudaFree(ctx->B.world);
     cudaFree(ctx->B.effMin); cudaFree(ctx->B.effMax); cudaFree(ctx->B.leafMin); cudaFree(ctx->B.leafMax);
     cudaFree(ctx->B.lastSet); cudaFree(ctx->B.material);
@@ -1292,25 +1293,59 @@ int32_t b2c_shape_register_plane(b2c_ctx* ctx, const float nrm[3], float c, int3
 }
 int32_t b2c_shape_register_mesh(b2c_ctx* ctx, const void* vbase, int32_t nv, int32_t vstride, const void* ibase, int32_t nt,
                                 int32_t istride, const float scaling[3], int32_t* out) {
-    if (!ctx || !vbase || !ibase || nv < 1 || nt < 1 || vstride < 12 || istride < 12) return B2C_ERR_BAD_ARG;
-    if (nt >= (1 << 21)) { ctx->err = "mesh part exceeds 2^21 triangles (sh/OptimizedBvh.java:65)"; return B2C_ERR_BAD_ARG; }
+    b2c_indexed_mesh part{vbase, nv, vstride, ibase, nt, istride, B2C_INDEX_INT32};
+    return b2c_shape_register_mesh_parts(ctx, &part, 1, scaling, out);
+}
+
+// sh/TriangleIndexVertexArray.java:72-100 (a list of IndexedMesh parts, each with its own index type) behind
+// sh/BvhTriangleMeshShape.java:68-90.  The parts are concatenated on the host (vertices pre-multiplied by the scaling,
+// indices rebased), the quantized BVH is built over the triangles in part order with leaf words partId << 21 | index.
+int32_t b2c_shape_register_mesh_parts(b2c_ctx* ctx, const b2c_indexed_mesh* parts, int32_t nparts, const float scaling[3],
+                                      int32_t* out) {
+    if (!ctx || !parts || nparts < 1) return B2C_ERR_BAD_ARG;
+    if (nparts > (1 << 10)) { ctx->err = "more than 1024 mesh parts (sh/OptimizedBvh.java:65 MAX_NUM_PARTS_IN_BITS)"; return B2C_ERR_BAD_ARG; }
     float sc[3] = {1.f, 1.f, 1.f};
     if (scaling) { sc[0] = scaling[0]; sc[1] = scaling[1]; sc[2] = scaling[2]; }
-    std::vector<float> verts(3 * (size_t)nv);
-    std::vector<int32_t> idx(3 * (size_t)nt);
-    for (int i = 0; i < nv; i++) {
-        const float* p = (const float*)((const char*)vbase + (size_t)i * vstride);
-        for (int c = 0; c < 3; c++) verts[3 * (size_t)i + c] = p[c] * sc[c];  // sh/VertexData.java:50-55
+    size_t totalV = 0, totalT = 0;
+    for (int p = 0; p < nparts; p++) {
+        const b2c_indexed_mesh& m = parts[p];
+        if (!m.vertex_base || !m.index_base || m.num_vertices < 1 || m.num_triangles < 1 || m.vertex_stride < 12) return B2C_ERR_BAD_ARG;
+        if (m.index_type != B2C_INDEX_INT16 && m.index_type != B2C_INDEX_INT32) { ctx->err = "mesh index type must be SHORT or INTEGER"; return B2C_ERR_BAD_ARG; }
+        // sh/TriangleIndexVertexArray.java:94: the per-index stride is triangleIndexStride / 3
+        if (m.index_stride / 3 < m.index_type) { ctx->err = "triangle index stride smaller than three indices"; return B2C_ERR_BAD_ARG; }
+        if (m.num_triangles >= (1 << 21)) { ctx->err = "mesh part exceeds 2^21 triangles (sh/OptimizedBvh.java:65)"; return B2C_ERR_BAD_ARG; }
+        totalV += (size_t)m.num_vertices;
+        totalT += (size_t)m.num_triangles;
     }
-    for (int t = 0; t < nt; t++) {
-        const int32_t* p = (const int32_t*)((const char*)ibase + (size_t)t * istride);
-        for (int c = 0; c < 3; c++) {
-            if (p[c] < 0 || p[c] >= nv) { ctx->err = "mesh index out of range"; return B2C_ERR_BAD_ARG; }
-            idx[3 * (size_t)t + c] = p[c];
+    if (totalT > 0x7fffffffu / 3 || totalV > 0x7fffffffu / 3) return B2C_ERR_BAD_ARG;
+    std::vector<float> verts(3 * totalV);
+    std::vector<int32_t> idx(3 * totalT), leafWord(totalT), partStart((size_t)nparts + 1);
+    size_t v0 = 0, t0 = 0;
+    for (int p = 0; p < nparts; p++) {
+        const b2c_indexed_mesh& m = parts[p];
+        for (int i = 0; i < m.num_vertices; i++) {
+            const float* q = (const float*)((const char*)m.vertex_base + (size_t)i * m.vertex_stride);
+            for (int c = 0; c < 3; c++) verts[3 * (v0 + i) + c] = q[c] * sc[c];  // sh/VertexData.java:50-55
         }
+        const size_t istep = (size_t)(m.index_stride / 3);
+        partStart[p] = (int32_t)t0;
+        for (int t = 0; t < m.num_triangles; t++) {
+            for (int c = 0; c < 3; c++) {
+                const char* q = (const char*)m.index_base + ((size_t)3 * t + c) * istep;  // sh/ByteBufferVertexData.java:75-84
+                int32_t v;
+                if (m.index_type == B2C_INDEX_INT16) { uint16_t h; memcpy(&h, q, 2); v = (int32_t)h; }  // getShort & 0xFFFF
+                else memcpy(&v, q, 4);
+                if (v < 0 || v >= m.num_vertices) { ctx->err = "mesh index out of range"; return B2C_ERR_BAD_ARG; }
+                idx[3 * (t0 + t) + c] = v + (int32_t)v0;
+            }
+            leafWord[t0 + t] = (int32_t)(((uint32_t)p << 21) | (uint32_t)t);
+        }
+        v0 += (size_t)m.num_vertices;
+        t0 += (size_t)m.num_triangles;
     }
+    partStart[nparts] = (int32_t)t0;
     HostMesh hm;
-    buildQuantizedBvh(verts.data(), idx.data(), nt, hm.bvh);
+    buildQuantizedBvh(verts.data(), idx.data(), (int)totalT, hm.bvh, nparts > 1 ? leafWord.data() : nullptr);
     cudaSetDevice(ctx->device);
     size_t nn = hm.bvh.nodes.size() / 4;
     CK(cudaMalloc((void**)&hm.nodes, nn * sizeof(int4)));
@@ -1321,7 +1356,14 @@ int32_t b2c_shape_register_mesh(b2c_ctx* ctx, const void* vbase, int32_t nv, int
     CK(cudaMemcpy(hm.idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     MeshDev md{};
     md.nodes = hm.nodes; md.verts = hm.verts; md.idx = hm.idx;
-    md.numNodes = (int)nn; md.numTris = nt;
+    md.numNodes = (int)nn; md.numTris = (int)totalT;
+    md.numParts = nparts;
+    md.partStart = nullptr;
+    if (nparts > 1) {
+        CK(cudaMalloc((void**)&hm.partStart, partStart.size() * sizeof(int)));
+        CK(cudaMemcpy(hm.partStart, partStart.data(), partStart.size() * sizeof(int), cudaMemcpyHostToDevice));
+        md.partStart = hm.partStart;
+    }
     for (int c = 0; c < 3; c++) { md.qmin[c] = hm.bvh.qmin[c]; md.qmax[c] = hm.bvh.qmax[c]; md.quant[c] = hm.bvh.quant[c]; }
     ShapeDev s{};
     s.type = SH_MESH;

@@ -35,8 +35,10 @@ static inline int f2i(float f) {
 struct Q3 { uint16_t v[3]; };
 }  // namespace bvhdetail
 
-// verts: scaled vertex positions xyz; idx: 3 per triangle.
-inline void buildQuantizedBvh(const float* verts, const int32_t* idx, int numTris, HostBvh& out) {
+// verts: scaled vertex positions xyz; idx: 3 per triangle (all sub-parts back to back, in part order — the order
+// sh/StridingMeshInterface.java:40-58 visits them); leafWord[t] = partId << 21 | index inside the part (:278), or null for a
+// one-part mesh.
+inline void buildQuantizedBvh(const float* verts, const int32_t* idx, int numTris, HostBvh& out, const int32_t* leafWord = nullptr) {
     using namespace bvhdetail;
     // mesh bounds over referenced vertices (sh/StridingMeshInterface.java calculateAabbBruteForce)
     float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
@@ -104,7 +106,7 @@ inline void buildQuantizedBvh(const float* verts, const int32_t* idx, int numTri
             int start = fr.start, end = fr.end, num = end - start;
             if (num == 1) {
                 int t = perm[start];
-                putNode(cur, lmin[t].v, lmax[t].v, t);  // (partId 0 << 21) | triangleIndex
+                putNode(cur, lmin[t].v, lmax[t].v, leafWord ? leafWord[t] : t);  // (partId << 21) | triangleIndex
                 cur++;
                 stack.pop_back();
                 continue;

@@ -134,11 +134,12 @@ __host__ __device__ __forceinline__ Xf mulXf(const Xf& a, const Xf& b) {
 struct MeshDev {
     const int4* nodes;   // 16 B: (minx|miny<<16, minz|maxx<<16, maxy|maxz<<16, escapeOrTriangle)
     const float* verts;  // xyz, pre-multiplied by the mesh scaling (sh/VertexData.java:50-55)
-    const int* idx;      // 3 per triangle
+    const int* idx;      // 3 per triangle, all sub-parts back to back, rebased onto the concatenated vertex array
     int numNodes;
     int numTris;
     float qmin[3], qmax[3], quant[3];  // bvhAabbMin, bvhAabbMax, bvhQuantization
-    int pad;
+    int numParts;        // sh/TriangleIndexVertexArray sub-parts; a leaf names its triangle as partId << 21 | index (sh/OptimizedBvh.java:65,278)
+    const int* partStart;  // [numParts + 1] first triangle of every part in the concatenated arrays (null when numParts == 1)
 };
 
 // AxisSweep3 quantisation (bp/AxisSweep3Internal.java:87-105, 201-216)

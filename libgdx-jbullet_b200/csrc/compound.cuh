@@ -364,10 +364,10 @@ __global__ void __launch_bounds__(64) k_compound_mesh(NpArgs a, GjkArgs g) {
             }
             const f3 pt = add3(pointOnB, r.positionOffset);
             // raw-record key of (child algorithm, triangle): -2 - (k << 21 | t)
-            writeRaw(g.rawMesh + k, it.pr, -2 - (int)((code << 21) | (uint32_t)tri), isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0),
+            writeRaw(g.rawMesh + k, it.pr, -2 - (int)((code << 21) | ((uint32_t)tri & 0x1FFFFFu)), isValid ? 1 : 0, isValid ? normalInB : mk3(0, 0, 0),
                      isValid ? pt : mk3(0, 0, 0), isValid ? distance : 0.f, method, r.curIter);
             if (isValid) {
-                if (manifoldAdd(m, it.pr.x, t0, t1, normalInB, pt, distance, a.threshold, fr, re, 0, tri)) added++;
+                if (manifoldAdd(m, it.pr.x, t0, t1, normalInB, pt, distance, a.threshold, fr, re, tri >> 21, tri & 0x1FFFFF)) added++;
             }
             k++;
         });

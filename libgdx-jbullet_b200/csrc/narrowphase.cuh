@@ -1211,7 +1211,7 @@ __device__ __forceinline__ uint32_t walkBvh(const MeshDev& md, const uint32_t qm
         bool overlap = !(qmin[0] > nmaxx || qmax[0] < nminx) && !(qmin[2] > nmaxz || qmax[2] < nminz) &&
                        !(qmin[1] > nmaxy || qmax[1] < nminy);
         bool leaf = nd.w >= 0;
-        if (leaf && overlap) f(nd.w & 0x1FFFFF);  // 21-bit triangle index (sh/QuantizedBvhNodes.java:194-198)
+        if (leaf && overlap) f(nd.w);  // partId << 21 | triangle index (sh/QuantizedBvhNodes.java:186-198)
         if (overlap || leaf) cur++;
         else cur += -nd.w;
     }
@@ -1263,8 +1263,10 @@ __global__ void __launch_bounds__(128) k_mesh_query(NpArgs a, GjkArgs g) {
     if (created) atomicAdd(&a.ctr->numManifolds, created);
 }
 
-__device__ __forceinline__ TriS loadTri(const MeshDev& md, int tri, float margin) {
+// `leaf` is the BVH leaf word partId << 21 | triangleIndex (sh/OptimizedBvh.java:278); for a one-part mesh it IS the index
+__device__ __forceinline__ TriS loadTri(const MeshDev& md, int leaf, float margin) {
     TriS t;
+    const int tri = md.numParts > 1 ? __ldg(md.partStart + (leaf >> 21)) + (leaf & 0x1FFFFF) : leaf;
     int i0 = __ldg(md.idx + 3 * tri), i1 = __ldg(md.idx + 3 * tri + 1), i2 = __ldg(md.idx + 3 * tri + 2);
     t.a = mk3(__ldg(md.verts + 3 * i0), __ldg(md.verts + 3 * i0 + 1), __ldg(md.verts + 3 * i0 + 2));
     t.b = mk3(__ldg(md.verts + 3 * i1), __ldg(md.verts + 3 * i1 + 1), __ldg(md.verts + 3 * i1 + 2));
@@ -1520,7 +1522,7 @@ __global__ void __launch_bounds__(128) k_mesh_manifold(NpArgs a, GjkArgs g) {
             const b2c_raw_contact* r = g.rawMesh + k;
             if (r->has_contact == 1) {
                 if (manifoldAdd(m, pr.x, t0, t1, mk3(r->normal[0], r->normal[1], r->normal[2]), mk3(r->point[0], r->point[1], r->point[2]),
-                                r->depth, a.threshold, fr, re, 0, r->tri))
+                                r->depth, a.threshold, fr, re, r->tri >> 21, r->tri & 0x1FFFFF))  // partId1, index1
                     added++;
             }
         }
@@ -1611,7 +1613,7 @@ k_compact_contacts(NpArgs a, b2c_contact_header* __restrict__ hdr, void* __restr
                         dst[0] = make_int4(v1.z, v1.w, v2.x, v2.y);  // world_a xyz, world_b x
                         dst[1] = make_int4(v2.z, v2.w, v3.x, v3.y);  // world_b yz, normal xy
                         const int life = v4.z > 0xffffff ? 0xffffff : v4.z;
-                        dst[2] = make_int4(v3.z, v3.w, (life << 8) | ((v4.w + 1) & 0xff), v5.y);  // normal z, distance, life | src_slot+1, index1
+                        dst[2] = make_int4(v3.z, v3.w, (life << 8) | ((v4.w + 1) & 0xff), (v5.x << 21) | v5.y);  // normal z, distance, life | src_slot+1, partId1 << 21 | index1
                     } else if (!SLIM) {
                         int4* dst = reinterpret_cast<int4*>(pts + fp + k);
                         for (int q = 0; q < 6; q++) dst[q] = src[q];

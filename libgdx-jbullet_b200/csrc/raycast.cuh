@@ -186,7 +186,7 @@ __device__ __forceinline__ void rayMeshWalk(const MeshDev& md, TriRay& tr) {
             rayBox = rayAabb(tr.from, tr.to, b0, b1, 1.f);
         }
         if (leaf && rayBox) {
-            const TriS t = loadTri(md, nd.w & 0x1FFFFF, 0.f);
+            const TriS t = loadTri(md, nd.w, 0.f);
             tr.processTriangle(t.a, t.b, t.c);
         }
         if (rayBox || leaf) cur++;

@@ -114,6 +114,24 @@ class GpuCollisionWorld:
         self._ck(self.L.b2c_shape_register_mesh(self.h, _vp(v), len(v), 12, _vp(i), len(i), 12, _vp(s), C.byref(out)))
         return out.value
 
+    def BvhTriangleMeshShapeParts(self, parts, scaling=(1.0, 1.0, 1.0)):
+        """BvhTriangleMeshShape over a TriangleIndexVertexArray of several IndexedMesh parts (sh/TriangleIndexVertexArray.java:
+        72-100): parts = [(vertices (n,3) float32, indices (m,3) uint16 -> ScalarType.SHORT | int32 -> INTEGER), ...]."""
+        keep = []
+        arr = (_lib.IndexedMesh * len(parts))()
+        for k, (v, i) in enumerate(parts):
+            v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3)
+            i = np.ascontiguousarray(i)
+            if i.dtype not in (np.uint16, np.int32):
+                i = np.ascontiguousarray(i, dtype=np.int32)
+            i = i.reshape(-1, 3)
+            keep += [v, i]
+            arr[k] = _lib.IndexedMesh(v.ctypes.data, len(v), 12, i.ctypes.data, len(i), 3 * i.itemsize, i.itemsize)
+        s = np.asarray(scaling, dtype=np.float32)
+        out = C.c_int32()
+        self._ck(self.L.b2c_shape_register_mesh_parts(self.h, arr, len(parts), _vp(s), C.byref(out)))
+        return out.value
+
     def CompoundShape(self, child_shapes, child_transforms):
         """new CompoundShape() + addChildShape(child_transforms[i], child_shapes[i]) in order (sh/CompoundShape.java:50-82)."""
         cs = np.ascontiguousarray(child_shapes, dtype=np.int32)

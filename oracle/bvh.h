@@ -9,16 +9,25 @@
 
 namespace orc {
 
-struct MeshData {  // one sub-part (partId 0): sh/IndexedMesh.java:35-47
+struct MeshPart {  // one sub-part: sh/IndexedMesh.java:35-47 (indices already widened to int, sh/ByteBufferVertexData.java:75-84)
     std::vector<float> verts;    // xyz
     std::vector<int32_t> idx;    // 3 per triangle
-    V3 scaling{1, 1, 1};         // sh/StridingMeshInterface.java scaling
     int numTriangles() const { return (int)idx.size() / 3; }
+};
+struct MeshData {  // sh/TriangleIndexVertexArray.java:45-100: a list of sub-parts, partId = position in the list
+    std::vector<MeshPart> parts;
+    V3 scaling{1, 1, 1};         // sh/StridingMeshInterface.java scaling
+    int numTriangles() const {
+        int n = 0;
+        for (const MeshPart& p : parts) n += p.numTriangles();
+        return n;
+    }
     // sh/VertexData.java:50-55 getTriangle (vertex * scaling)
-    void getTriangle(int tri, V3 out[3]) const {
+    void getTriangle(int part, int tri, V3 out[3]) const {
+        const MeshPart& mp = parts[part];
         for (int i = 0; i < 3; i++) {
-            int vi = idx[tri * 3 + i];
-            out[i].set(verts[3 * vi] * scaling.x, verts[3 * vi + 1] * scaling.y, verts[3 * vi + 2] * scaling.z);
+            int vi = mp.idx[tri * 3 + i];
+            out[i].set(mp.verts[3 * vi] * scaling.x, mp.verts[3 * vi + 1] * scaling.y, mp.verts[3 * vi + 2] * scaling.z);
         }
     }
 };
@@ -68,9 +77,12 @@ struct Bvh {
         setQuantizationValues(aabbMin, aabbMax);
         int T = mesh.numTriangles();
         leafNodes.resize(T);
-        for (int t = 0; t < T; t++) {
+        int t = 0;
+        // sh/StridingMeshInterface.java:40-58 internalProcessAllTriangles: part by part, triangle by triangle
+        for (int part = 0; part < (int)mesh.parts.size(); part++)
+        for (int i = 0; i < mesh.parts[part].numTriangles(); i++, t++) {
             V3 tri[3];
-            mesh.getTriangle(t, tri);
+            mesh.getTriangle(part, i, tri);
             V3 mn(1e30f, 1e30f, 1e30f), mx(-1e30f, -1e30f, -1e30f);
             for (int k = 0; k < 3; k++) {
                 mn.x = jminf(mn.x, tri[k].x); mn.y = jminf(mn.y, tri[k].y); mn.z = jminf(mn.z, tri[k].z);
@@ -82,7 +94,7 @@ struct Bvh {
             if (mx.z - mn.z < MIN_AABB_DIMENSION) { mx.z = mx.z + MIN_AABB_HALF_DIMENSION; mn.z = mn.z - MIN_AABB_HALF_DIMENSION; }
             quantizeWithClamp(mn, leafNodes[t].mn);
             quantizeWithClamp(mx, leafNodes[t].mx);
-            leafNodes[t].escapeIndexOrTriangleIndex = (0 << (31 - MAX_NUM_PARTS_IN_BITS)) | t;
+            leafNodes[t].escapeIndexOrTriangleIndex = (part << (31 - MAX_NUM_PARTS_IN_BITS)) | i;  // :278
         }
         nodes.assign(2 * (size_t)T, QNode());
         curNodeIndex = 0;

@@ -86,6 +86,9 @@ int orc_shape_compound(void* h, int n, const int* childShapes, const float* chil
 int orc_shape_mesh(void* h, const float* verts, int nv, const int* idx, int ntri) {
     return ((World*)h)->addMesh(verts, nv, idx, ntri);
 }
+int orc_shape_mesh_parts(void* h, int nparts, const float* verts, const int* nv, const int* idx, const int* ntri) {
+    return ((World*)h)->addMeshParts(nparts, verts, nv, idx, ntri);
+}
 int orc_mesh_num_nodes(void* h, int shape) { return (int)((World*)h)->meshes[shape]->bvh.nodes.size(); }
 void orc_mesh_get_nodes(void* h, int shape, void* out16B) {
     Bvh& b = ((World*)h)->meshes[shape]->bvh;

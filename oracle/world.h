@@ -151,14 +151,25 @@ struct World {
         return addShape(s);
     }
     int addMesh(const float* verts, int nv, const int* idx, int ntri) {
+        return addMeshParts(1, verts, &nv, idx, &ntri);
+    }
+    // sh/TriangleIndexVertexArray.java:72-100: nparts IndexedMesh entries; verts / idx are the parts' arrays back to back
+    // (indices local to their part)
+    int addMeshParts(int nparts, const float* verts, const int* nv, const int* idx, const int* ntri) {
         std::unique_ptr<MeshShapeData> md(new MeshShapeData());
-        md->mesh.verts.assign(verts, verts + 3 * nv);
-        md->mesh.idx.assign(idx, idx + 3 * ntri);
+        md->mesh.parts.resize(nparts);
+        for (int p = 0; p < nparts; p++) {
+            md->mesh.parts[p].verts.assign(verts, verts + 3 * nv[p]);
+            md->mesh.parts[p].idx.assign(idx, idx + 3 * ntri[p]);
+            verts += 3 * nv[p];
+            idx += 3 * ntri[p];
+        }
         // sh/StridingMeshInterface.java calculateAabbBruteForce
         V3 mn(1e30f, 1e30f, 1e30f), mx(-1e30f, -1e30f, -1e30f);
-        for (int t = 0; t < ntri; t++) {
+        for (int p = 0; p < nparts; p++)
+        for (int t = 0; t < ntri[p]; t++) {
             V3 tri[3];
-            md->mesh.getTriangle(t, tri);
+            md->mesh.getTriangle(p, t, tri);
             for (int k = 0; k < 3; k++) {
                 mn.x = jminf(mn.x, tri[k].x); mn.y = jminf(mn.y, tri[k].y); mn.z = jminf(mn.z, tri[k].z);
                 mx.x = jmaxf(mx.x, tri[k].x); mx.y = jmaxf(mx.y, tri[k].y); mx.z = jmaxf(mx.z, tri[k].z);
@@ -402,7 +413,7 @@ struct World {
                 const MeshShapeData* md = meshes[shapeIndex].get();
                 bvhReportRayOverlappingNodex(md->bvh, rcb.from, rcb.to, [&](int part, int tri) {
                     V3 t[3];
-                    md->mesh.getTriangle(tri, t);
+                    md->mesh.getTriangle(part, tri, t);
                     rcb.processTriangle(t, part, tri);
                 });
             } else {
@@ -561,12 +572,12 @@ struct World {
             // sh/BvhTriangleMeshShape.java:265-278 processNode -> ConvexTriangleCallback.processTriangle
             Shape tm;
             tm.type = SH_TRIANGLE;
-            md->mesh.getTriangle(triIndex, tm.tri);
+            md->mesh.getTriangle(part, triIndex, tm.tri);
             tm.collisionMargin = collisionMarginTriangle;
             res.partId0 = -1; res.index0 = -1; res.partId1 = part; res.index1 = triIndex;  // :164
             trianglesTested++;
             // findAlgorithm(convexBody, triBody, sharedManifold): convex-convex with ownManifold=false
-            convexConvexTri(cs, &tm, convexBody, triBody, res, triIndex);
+            convexConvexTri(cs, &tm, convexBody, triBody, res, (part << 21) | triIndex);  // raw-record key: partId << 21 | index
         }, &visited);
         bvhNodesVisited += visited;
         res.refreshContactPoints();

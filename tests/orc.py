@@ -44,6 +44,7 @@ def lib():
     L.orc_shape_plane.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
     L.orc_shape_mesh.argtypes = [C.c_void_p, f32p, C.c_int, i32p, C.c_int]
     L.orc_shape_compound.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
+    L.orc_shape_mesh_parts.argtypes = [C.c_void_p, C.c_int, f32p, i32p, i32p, i32p]
     L.orc_mesh_num_nodes.argtypes = [C.c_void_p, C.c_int]
     L.orc_mesh_get_nodes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.orc_mesh_get_quant.argtypes = [C.c_void_p, C.c_int, f32p]
@@ -138,6 +139,15 @@ class OracleWorld:
         verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
         idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 3)
         return self.L.orc_shape_mesh(self.h, verts, len(verts), idx, len(idx))
+
+    def mesh_parts(self, parts):
+        """BvhTriangleMeshShape over a TriangleIndexVertexArray with several IndexedMesh parts: [(verts, idx), ...]
+        (indices local to their part, any integer dtype)."""
+        v = np.ascontiguousarray(np.concatenate([np.asarray(p[0], np.float32).reshape(-1, 3) for p in parts]))
+        i = np.ascontiguousarray(np.concatenate([np.asarray(p[1]).astype(np.int32).reshape(-1, 3) for p in parts]))
+        nv = np.asarray([len(np.asarray(p[0]).reshape(-1, 3)) for p in parts], dtype=np.int32)
+        nt = np.asarray([len(np.asarray(p[1]).reshape(-1, 3)) for p in parts], dtype=np.int32)
+        return self.L.orc_shape_mesh_parts(self.h, len(parts), v, nv, i, nt)
 
     def mesh_nodes(self, shape):
         n = self.L.orc_mesh_num_nodes(self.h, shape)

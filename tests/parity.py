@@ -95,6 +95,7 @@ def compare_manifolds(gm, om, extent):
         assert np.array_equal(gp["life_time"], oi[:, 0]), f"lifeTime differs in slot {k}"
         assert np.array_equal(gp["src_slot"], oi[:, 1]), f"src_slot differs in slot {k}"
         assert np.array_equal(gp["index1"], oi[:, 5]), f"triangle index differs in slot {k}"
+        assert np.array_equal(gp["part_id1"], oi[:, 3]), f"mesh part id differs in slot {k}"
     return dict(manifolds=int(len(hdr)), points=total)
 
 

@@ -227,6 +227,27 @@ def terrain_scene(cells=64, n=200, seed=4, cell=0.5, mix=(0.45, 0.45, 0.10)):
     return sc
 
 
+def split_mesh_into_parts(sc, nparts=3, short_parts=(1,)):
+    """Replace the scene's one-part mesh (shape 0) by the same triangles split into `nparts` IndexedMesh parts with their own
+    (compacted) vertex arrays; the parts listed in short_parts use 16-bit indices (ScalarType.SHORT)."""
+    kind, verts, tris = sc.shapes[0]
+    assert kind == "mesh"
+    cuts = np.linspace(0, len(tris), nparts + 1).astype(int)
+    parts = []
+    for p in range(nparts):
+        t = tris[cuts[p]:cuts[p + 1]]
+        used, inv = np.unique(t.reshape(-1), return_inverse=True)
+        idx = inv.reshape(-1, 3)
+        if p in short_parts:
+            assert len(used) < 65536
+            idx = idx.astype(np.uint16)
+        else:
+            idx = idx.astype(np.int32)
+        parts.append((np.ascontiguousarray(verts[used]), np.ascontiguousarray(idx)))
+    sc.shapes[0] = ("meshparts", parts)
+    return sc
+
+
 def worlds_scene(num_worlds=32, seed=5):
     """C4: independent worlds of 64 bodies: one static floor box + 63 dice (half extent 0.5) in a jittered 4x4x4 lattice."""
     rng = np.random.default_rng(SEED + seed)
@@ -376,6 +397,8 @@ def build_gpu(pkg, sc, mode, max_pairs=None, **kw):
             ids.append(gw.StaticPlaneShape(s[1], s[2]))
         elif s[0] == "mesh":
             ids.append(gw.BvhTriangleMeshShape(s[1], s[2]))
+        elif s[0] == "meshparts":
+            ids.append(gw.BvhTriangleMeshShapeParts(s[1]))
         elif s[0] == "compound":
             ids.append(gw.CompoundShape([ids[c] for c in s[1]], s[2]))
     shapes = np.asarray([ids[k] for k in sc.body_shape], dtype=np.int32)
@@ -398,6 +421,8 @@ def build_oracle(sc, mode, brute_force=False, world_aabb=None):
             ids.append(ow.plane([float(v) for v in np.asarray(s[1], dtype=np.float32)], float(s[2])))
         elif s[0] == "mesh":
             ids.append(ow.mesh(s[1], s[2]))
+        elif s[0] == "meshparts":
+            ids.append(ow.mesh_parts(s[1]))
         elif s[0] == "compound":
             ids.append(ow.compound([ids[c] for c in s[1]], s[2]))
     for k in range(sc.n):

@@ -55,6 +55,8 @@ _Static_assert(sizeof(b2c_packed_header) == 16, "b2c_packed_header");
 _Static_assert(sizeof(b2c_packed_point) == 48, "b2c_packed_point");
 _Static_assert(sizeof(b2c_raw_contact) == 56, "b2c_raw_contact");
 _Static_assert(sizeof(b2c_stats) == 64, "b2c_stats");
+_Static_assert(sizeof(b2c_packed_uid_header) == 16, "b2c_packed_uid_header");
+_Static_assert(sizeof(b2c_indexed_mesh) == 40, "b2c_indexed_mesh");
 int main(void) { return 0; }
 """)
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)])
@@ -96,3 +98,45 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "import orc" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
+
+
+def test_jni_forwarders_compile():
+    """java/jni/b2c_jni.c (the JNI fallback binding) is valid C against include/b2c.h and the JNI signatures it uses
+    (tests/jni_stub/jni.h stands in for the JDK header this image lacks), and it forwards every native method B2CJni declares."""
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "jni_stub"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "java", "jni", "b2c_jni.c")])
+    java = open(os.path.join(ROOT, "java", "com", "b200", "jbullet", "B2CJni.java")).read()
+    c = open(os.path.join(ROOT, "java", "jni", "b2c_jni.c")).read()
+    natives = re.findall(r"static native \w+(?:\[\])? (\w+)\(", java)
+    assert len(natives) >= 25
+    for n in natives:
+        assert re.search(r"FN\(%s\)" % n, c), f"no JNI forwarder for B2CJni.{n}"
+
+
+def test_java_shim_binds_only_exported_symbols_and_is_complete(pkg):
+    """The FFM binding (java/, not compilable here) must name only symbols libb2c.so exports, with the right arity, and every
+    shim class the sources refer to must exist."""
+    jdir = os.path.join(ROOT, "java", "com", "b200", "jbullet")
+    b2c = open(os.path.join(jdir, "B2C.java")).read()
+    L = pkg._lib.load()
+    bound = re.findall(r'h\("(b2c_\w+)",\s*FunctionDescriptor\.(ofVoid|of)\(([^;]*?)\)\);', b2c, flags=re.S)
+    assert len(bound) >= 40
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "b2c.h")).read(), flags=re.S)
+    for name, kind, args in bound:
+        assert hasattr(L, name), f"B2C.java binds {name}, which libb2c.so does not export"
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, hdr, flags=re.S)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        nargs = len([a for a in args.split(",") if a.strip()]) - (1 if kind == "of" else 0)
+        assert nargs == len(params), f"{name}: B2C.java passes {nargs} arguments, the header declares {len(params)}"
+    sources = {f[:-5]: open(os.path.join(jdir, f)).read() for f in os.listdir(jdir) if f.endswith(".java")}
+    for cls in ("GpuBroadphase", "GpuDispatcher", "GpuPairCache", "GpuShapes", "GpuManifolds", "B2C", "B2CJni"):
+        assert cls in sources, f"java/{cls}.java missing"
+    used = set()
+    for txt in sources.values():
+        used |= set(re.findall(r"\b(Gpu[A-Z]\w+)\.", txt))
+    assert used <= set(sources) | {"GpuBroadphase.GpuProxy"}, used - set(sources)
+    for txt in sources.values():          # every B2C.<handle> the shim calls is declared in B2C.java
+        for hname in re.findall(r"B2C\.(\w+)\.invokeExact", txt):
+            assert re.search(r"static final MethodHandle %s\b" % hname, b2c), f"B2C.{hname} is used but not declared"

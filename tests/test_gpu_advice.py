@@ -143,3 +143,36 @@ def test_long_rows_switch_to_the_radix_passes(gpu_pkg):
         launches.append(gw.stats()["kernel_launches"])
     assert r["pairs"] >= n - 1
     assert launches[-1] != launches[0], "the ordering pipeline did not change after the long row was seen"
+
+
+def test_multi_part_mesh_with_16_bit_indices(gpu_pkg):
+    """N12: a TriangleIndexVertexArray with several IndexedMesh parts, one of them with ScalarType.SHORT indices
+    (sh/ByteBufferVertexData.java:75-84, sh/TriangleIndexVertexArray.java:72-100): the BVH leaves name (partId, index), the node
+    array equals the oracle's bit for bit, and contact points report the part and the triangle inside it."""
+    sc = scenes.terrain_scene(cells=40, n=350, seed=23)
+    scenes.split_mesh_into_parts(sc, nparts=3, short_parts=(1,))
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    gn, gq = gw.mesh_bvh(0)
+    on, oq = ow.mesh_nodes(0)
+    assert np.array_equal(gq.view(np.uint32), oq.view(np.uint32)) and np.array_equal(gn, on), "BVH differs"
+    leaves = gn[gn[:, 3] >= 0, 3]
+    assert set(np.unique(leaves >> 21).tolist()) == {0, 1, 2}
+    parts_seen = set()
+    for step in range(4):
+        r = parity.step_and_compare(gw, ow, sc.transforms(step), sc.extent)
+        m = gw.manifolds(only_touching=True)
+        for k in range(4):
+            sel = (m["algorithm"] == 4) & (m["num_contacts"] > k)
+            parts_seen |= set(np.unique(m["points"][sel, k]["part_id1"]).tolist())
+        hdr, pts = gw.packed_contacts()
+        assert len(pts) == int(m["num_contacts"].sum())
+    assert r["records"] > 800 and r["contacts"] > 40
+    assert parts_seen == {0, 1, 2}, parts_seen
+    # rays against the multi-part mesh decode the leaf word the same way
+    rng = np.random.default_rng(2)
+    size = 40 * 0.5
+    frm = np.stack([rng.uniform(1, size - 1, 200), np.full(200, 30.0), rng.uniform(1, size - 1, 200)], axis=1).astype(np.float32)
+    to = frm.copy(); to[:, 1] = -30.0
+    gu, gf, gnrm, gpt = gw.rayTestClosest(frm, to)
+    ou, of, onrm, opt = ow.ray_test_closest(frm, to)
+    assert np.array_equal(gu, ou) and np.array_equal(gf.view(np.uint32), of.view(np.uint32))

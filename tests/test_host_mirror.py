@@ -35,3 +35,11 @@ def test_host_mirror_runs_reference_call_sequence(gpu_pkg):
     assert "contacts 1 normal 0.000 -1.000 0.000" in lines[4]
     # first step: all three pairs are new; the three stacked boxes form one island (tag = smallest body index), ground is static
     assert lines[5] == "deltas +3 -0 islands 1 tags -1 1 1 1"
+    # the drop-in sequence and the fast path, stepped side by side over a drifting scene, tell the same
+    # story (pair list == mirror maintained from the deltas, same touching manifolds, bit-identical contact points)
+    steps = [l for l in lines if l.startswith("step ")]
+    assert len(steps) == 5 and not any(l.startswith("FAIL") for l in lines), out.stdout
+    counts = [int(l.split()[3]) for l in steps]
+    assert min(counts) > 150
+    assert any(int(l.split()[5]) < 0 for l in steps[1:]) and any(int(l.split()[4]) > 0 for l in steps[1:]), "pairs must come and go"
+    assert lines[-1].startswith("broadphase aabb -1e+30 1e+30")

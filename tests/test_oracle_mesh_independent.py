@@ -85,3 +85,34 @@ def test_sphere_vs_mesh_triangle_contacts_match_point_triangle_distance():
             else:
                 assert d > 0.02 - 2e-3, (trial, k, d)
     assert checked > 20
+
+
+def test_multi_part_mesh_is_the_same_surface():
+    """Splitting one IndexedMesh into several parts changes the ids a contact reports (partId, index inside the part), not
+    the geometry: same pairs, same contact points; and the BVH leaves carry partId << 21 | index (sh/OptimizedBvh.java:278)."""
+    import scenes
+    sc1 = scenes.terrain_scene(cells=24, n=120, seed=31)
+    sc3 = scenes.terrain_scene(cells=24, n=120, seed=31)
+    scenes.split_mesh_into_parts(sc3, nparts=3, short_parts=(0, 2))
+    o1 = scenes.build_oracle(sc1, 1)
+    o3 = scenes.build_oracle(sc3, 1)
+    n1, q1 = o1.mesh_nodes(0)
+    n3, q3 = o3.mesh_nodes(0)
+    assert np.array_equal(q1, q3) and np.array_equal(n1[:, :3], n3[:, :3])       # same boxes, same tree shape
+    leaf = n1[:, 3] >= 0
+    cuts = np.linspace(0, 2 * 24 * 24, 4).astype(int)
+    part = np.searchsorted(cuts, n1[leaf, 3], side="right") - 1
+    assert np.array_equal(n3[leaf, 3], (part << 21) | (n1[leaf, 3] - cuts[part]))
+    for step in range(3):
+        p1 = o1.step(sc1.transforms(step))
+        p3 = o3.step(sc3.transforms(step))
+        assert np.array_equal(p1, p3)
+        h1, pt1, i1 = o1.manifolds()
+        h3, pt3, i3 = o3.manifolds()
+        assert np.array_equal(h1, h3) and np.array_equal(pt1.view(np.uint32), pt3.view(np.uint32))
+        live = np.arange(4)[None, :] < h1[:, 4][:, None]
+        mesh = (i1[:, :, 2] == -1) & live                                          # partId0 == -1 marks a mesh contact
+        g = i1[:, :, 5][mesh]
+        pp = np.searchsorted(cuts, g, side="right") - 1
+        assert np.array_equal(i3[:, :, 3][mesh], pp) and np.array_equal(i3[:, :, 5][mesh], g - cuts[pp])
+    assert mesh.sum() > 20
