@@ -165,8 +165,6 @@ public class DumpGolden {
             uidOf.put(o, b + 1);
         }
         ZipOutputStream z = new ZipOutputStream(new FileOutputStream(outFile));
-        z.setMethod(ZipOutputStream.STORED);   // numpy reads deflated entries too; stored keeps the CRC handling trivial below
-        z.setMethod(ZipOutputStream.DEFLATED);
         Vector3 mn = new Vector3(), mx = new Vector3();
         for (int step = 0; step < steps; step++) {
             float[] xf = s.get("xf" + step).f;
@@ -176,7 +174,7 @@ public class DumpGolden {
             for (int b = 0; b < N; b++) {
                 BroadphaseProxy p = objs[b].getBroadphaseHandle();
                 if (p instanceof DbvtProxy) { mn.set(((DbvtProxy) p).aabb.Mins()); mx.set(((DbvtProxy) p).aabb.Maxs()); }
-                else { worlds[bworld[b]].getBroadphase().getOverlappingPairCache(); SimpleAabb.get(p, mn, mx); }
+                else SimpleAabb.get(p, mn, mx);
                 aabb[6 * b] = mn.x; aabb[6 * b + 1] = mn.y; aabb[6 * b + 2] = mn.z; aabb[6 * b + 3] = mx.x; aabb[6 * b + 4] = mx.y; aabb[6 * b + 5] = mx.z;
             }
             writeNpy(z, "aabb" + step, new int[] {N, 6}, aabb, null);
