@@ -373,6 +373,25 @@ def measure(rig, wl, sc, steps, warmup, e2e_steps, want_stages, partitioned=Fals
         one_step()
         gw.sync_counts()
         step_no += 1
+    if mg is not None:
+        # one full pass over the trace with the worst-case slots, then size them to what this world sends (+50 %)
+        seen_h = seen_m = 0
+        for _ in range(2 * (FRAMES - 1)):
+            gw.setWorldTransformsDevice(nb, dframes[frame_index(step_no)].data_ptr())
+            one_step()
+            gw.sync_counts()
+            torch.cuda.synchronize()
+            seen_h = max(seen_h, int(mg.all_halo.view(torch.int32)[:: mg.halo_bytes // 4][: rig.world].max().item()))
+            seen_m = max(seen_m, int(mg.all_slots.view(torch.int32)[:: mg.slot_bytes // 4][: rig.world].max().item()))
+            step_no += 1
+        mg.all_halo.view(torch.int32)[0] = seen_h      # tune_caps reads the maxima from the gathered slots
+        mg.all_slots.view(torch.int32)[0] = seen_m
+        mg.tune_caps()
+        for _ in range(3):
+            gw.setWorldTransformsDevice(nb, dframes[frame_index(step_no)].data_ptr())
+            one_step()
+            gw.sync_counts()
+            step_no += 1
     rig.barrier()
     if sampler is not None:
         sampler.start()

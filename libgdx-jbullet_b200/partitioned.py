@@ -63,6 +63,31 @@ class PartitionedStepper:
         gw.mgpu_import_arrival_slots(self.all_slots.data_ptr(), self.nranks, self.mcap)
         gw.mgpu_narrowphase()
 
+    def tune_caps(self, headroom=1.5, min_halo=1024, min_migrate=256):
+        """Shrink the exchange slots to what the world actually sends: an all-gather moves whole fixed-size slots, so a slot
+        sized for the worst case costs its full size in NVLink time every step.  Reads the record counts every rank published
+        in the LAST step (first word of each gathered slot — the same values on every rank, so all ranks choose the same new
+        capacities without another collective) and re-allocates the buffers with `headroom`.  A later overflow is still
+        reported by b2c_sync_counts (B2C_ERR_CAPACITY); call this again, or raise the caps, when the world changes."""
+        torch = self.torch
+        torch.cuda.synchronize()
+        halo = self.all_halo.view(torch.int32)[:: self.halo_bytes // 4][: self.nranks]
+        mig = self.all_slots.view(torch.int32)[:: self.slot_bytes // 4][: self.nranks]
+        hmax, mmax = int(halo.max().item()), int(mig.max().item())
+        hcap = max(min_halo, int(hmax * headroom) + 64)
+        mcap = max(min_migrate, int(mmax * headroom) + 64)
+        if hcap >= self.hcap and mcap >= self.mcap:
+            return self.hcap, self.mcap
+        self.hcap, self.mcap = min(hcap, self.hcap), min(mcap, self.mcap)
+        self.slot_bytes = self.gw.mgpu_slot_bytes(self.mcap)
+        self.halo_bytes = self.gw.mgpu_halo_slot_bytes(self.hcap)
+        d = self.my_slot.device
+        self.my_slot = torch.zeros(self.slot_bytes, dtype=torch.uint8, device=d)
+        self.all_slots = torch.zeros(self.slot_bytes * self.nranks, dtype=torch.uint8, device=d)
+        self.my_halo = torch.zeros(self.halo_bytes, dtype=torch.uint8, device=d)
+        self.all_halo = torch.zeros(self.halo_bytes * self.nranks, dtype=torch.uint8, device=d)
+        return self.hcap, self.mcap
+
     def describe(self):
         return (f"slab partition, 2 ncclAllGather per step: halo slots ({self.hcap} x 80-byte boundary-proxy records = "
                 f"{self.halo_bytes} B per rank, {self.halo_bytes * self.nranks} B gathered) and manifold-migration slots "
