@@ -172,6 +172,13 @@ struct b2c_ctx {
     uint32_t localHint = 0;            // host's last reading of *dNLocal (launch shapes only; 0 = unknown)
     // row-grouped ordering (pairfind.cuh): zeroed block = RowOffsetsMisc | scan status[roTiles + 4] | rowCount[maxRows + 8]
     uint32_t* dRowOrdZero = nullptr;
+    // everything a pair calculation needs zeroed lives in ONE allocation cleared by one memset node at the start of the step:
+    // StepCounters | row-order block (dRowOrdZero) | pair-row block (dRowZero); the same for the dispatch: bin partition |
+    // survivor partition | cursors
+    unsigned char* dZeroBp = nullptr;
+    size_t zeroBpBytes = 0;
+    unsigned char* dZeroNp = nullptr;
+    size_t zeroNpBytes = 0;
     uint32_t* dSlots = nullptr;        // [N] slot of every proxy inside its row
     uint32_t roTiles = 0;
     uint32_t rowLenHint = 0;           // longest row of the last step the host has read
@@ -354,7 +361,7 @@ __global__ void k_clear_np_counters(StepCounters* c) {
 // reduction it performs feeds the grid.
 int32_t runAabbKernel(b2c_ctx* ctx, bool forPairs) {
     int n = ctx->nBodies;
-    if (forPairs) CK(cudaMemsetAsync(ctx->dCtr, 0, sizeof(StepCounters), ctx->stream));
+    if (forPairs) CK(cudaMemsetAsync(ctx->dZeroBp, 0, ctx->zeroBpBytes, ctx->stream));  // counters, row counts, scan states of the whole pair calculation
     if (n == 0) return B2C_OK;
     int32_t rc = uploadShapes(ctx);
     if (rc) return rc;
@@ -436,7 +443,6 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
         RowOffsetsMisc* misc = reinterpret_cast<RowOffsetsMisc*>(ctx->dRowOrdZero);
         uint32_t* roStatus = ctx->dRowOrdZero + 4;
         uint32_t* rowCount = ctx->dRowOrdZero + 4 + ctx->roTiles + 4;
-        CK(cudaMemsetAsync(ctx->dRowOrdZero, 0, (size_t)(4 + ctx->roTiles + 4 + ctx->maxRows + 8) * sizeof(uint32_t), s));
         k_keys<<<nb, 256, 0, s>>>(ctx->B, n, nPtr, list, ctx->dCtr, ctx->dGrid, ctx->dKeys[0], ctx->dVals[0], ctx->dStep, ctx->sortBodies.st,
                                   npass, rowCount, ctx->dSlots);
         mark(ctx, 2);
@@ -460,7 +466,6 @@ int32_t enqueueBroadphase(b2c_ctx* ctx) {
     uint32_t* rowCnt = ctx->dRowZero;
     uint32_t* rowStatus = ctx->dRowZero + ctx->nRows;
     RowMisc* rowMisc = reinterpret_cast<RowMisc*>(ctx->dRowZero + ctx->nRows + ctx->rowTiles);
-    CK(cudaMemsetAsync(ctx->dRowZero, 0, ((size_t)ctx->nRows + ctx->rowTiles) * sizeof(uint32_t) + sizeof(RowMisc), s));
     mark(ctx, 4);
     // k_large (a few proxies against everything, latency-bound) runs beside k_sweep: both only append pairs
     cudaStream_t sl = s;
@@ -650,7 +655,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     const unsigned pg = gridFor((uint32_t)ctx->cfg.max_pairs, 256);
     mark(ctx, 8);
     k_clear_np_counters<<<1, 32, 0, s>>>(ctx->dCtr);
-    CK(cudaMemsetAsync(ctx->dBinZero, 0, (32 + (size_t)ctx->binTiles * 16) * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(ctx->dZeroNp, 0, ctx->zeroNpBytes, s));  // bin partition, survivor partition, work cursors
     k_classify<<<pg, 256, 0, s>>>(a);
     // stable partition of the pair indices by bin, one pass (k_partition16)
     {
@@ -672,8 +677,6 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     if (ctx->hasPlane) { k_convex_plane<<<148 * 2, 256, 0, sc>>>(a); ctx->launches++; }
     if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[0], sc));
     mark(ctx, 10);
-    CK(cudaMemsetAsync(ctx->dCursors, 0, 4 * sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(ctx->dSurvZero, 0, (32 + (size_t)ctx->binTiles * 16) * sizeof(uint32_t), s));
     k_gjk_prefilter<<<148 * 8, 256, 0, s>>>(a, ctx->dSurvivors, ctx->dCursors + 2, ctx->dSurvKey, ctx->dSurvZero);
     {
         unsigned bg = ctx->binTiles < 148u * 2u ? ctx->binTiles : 148u * 2u;
@@ -1081,7 +1084,6 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dCsr, P));
     ctx->nRows = (uint32_t)N + 2u;
     ctx->rowTiles = (ctx->nRows + RSCAN_TILE - 1) / RSCAN_TILE;
-    CKC(dalloc(&ctx->dRowZero, (size_t)ctx->nRows + ctx->rowTiles + sizeof(RowMisc) / sizeof(uint32_t) + 8));
     CKC(dalloc(&ctx->dBigRows, (size_t)ctx->nRows));
     CKC(dalloc(&ctx->dSide, (size_t)4));
     CKC(dalloc(&ctx->dSmin, N + SW_CH));   // + SW_CH: the sweep stages whole chunks (pairfind.cuh)
@@ -1096,11 +1098,9 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dRowStart, (size_t)ctx->maxRows + 8));
     ctx->roTiles = (uint32_t)((ctx->maxRows + 8 + ROFF_TILE - 1) / ROFF_TILE);
     ctx->roTiles = (ctx->roTiles + 3u) & ~3u;  // keeps rowCount (behind misc and status) 16-byte aligned for its 128-bit loads
-    CKC(dalloc(&ctx->dRowOrdZero, (size_t)4 + ctx->roTiles + 4 + ctx->maxRows + 8 + 16));
     CKC(dalloc(&ctx->dSlots, N));
     { const char* e = getenv("B2C_SORT"); ctx->forceRadix = e && e[0] == 'r'; }
     CKC(dalloc(&ctx->dGrid, (size_t)1));
-    CKC(dalloc(&ctx->dCtr, (size_t)1));
     CKC(cudaMallocHost((void**)&ctx->hCtrPinned, 2 * sizeof(StepCounters)));  // [1]: the prefetched contact-stream counts
     CKC(ctx->sortBodies.init((uint32_t)N));
     ctx->uidBits = bitsFor((uint32_t)N + 1u);
@@ -1113,9 +1113,23 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dBinItems, P));
     CKC(dalloc(&ctx->dBinStart, (size_t)32));
     ctx->binTiles = (uint32_t)((P + BIN_TILE - 1) / BIN_TILE);
-    CKC(dalloc(&ctx->dBinZero, 32 + (size_t)ctx->binTiles * 16));
-    CKC(dalloc(&ctx->dSurvZero, 32 + (size_t)ctx->binTiles * 16));
-    CKC(dalloc(&ctx->dCursors, (size_t)4));
+    {
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t ctrB = up(sizeof(StepCounters));
+        const size_t ordB = up(((size_t)4 + ctx->roTiles + 4 + ctx->maxRows + 8 + 16) * sizeof(uint32_t));
+        const size_t rowB = up(((size_t)ctx->nRows + ctx->rowTiles + 8) * sizeof(uint32_t) + sizeof(RowMisc));
+        ctx->zeroBpBytes = ctrB + ordB + rowB;
+        CKC(dalloc(&ctx->dZeroBp, ctx->zeroBpBytes));
+        ctx->dCtr = reinterpret_cast<StepCounters*>(ctx->dZeroBp);
+        ctx->dRowOrdZero = reinterpret_cast<uint32_t*>(ctx->dZeroBp + ctrB);
+        ctx->dRowZero = reinterpret_cast<uint32_t*>(ctx->dZeroBp + ctrB + ordB);
+        const size_t binB = up((32 + (size_t)ctx->binTiles * 16) * sizeof(uint32_t));
+        ctx->zeroNpBytes = 2 * binB + 256;
+        CKC(dalloc(&ctx->dZeroNp, ctx->zeroNpBytes));
+        ctx->dBinZero = reinterpret_cast<uint32_t*>(ctx->dZeroNp);
+        ctx->dSurvZero = reinterpret_cast<uint32_t*>(ctx->dZeroNp + binB);
+        ctx->dCursors = reinterpret_cast<uint32_t*>(ctx->dZeroNp + 2 * binB);
+    }
     CKC(dalloc(&ctx->dExportCount, (size_t)1));
     CKC(dalloc(&ctx->dSurvivors, P));
     CKC(dalloc(&ctx->dSurvSorted, P));
@@ -1162,13 +1176,13 @@ void b2c_destroy(b2c_ctx* ctx) {
         cudaFree(ctx->dKeys[i]); cudaFree(ctx->dVals[i]); cudaFree(ctx->dSortedKeys[i]);
         cudaFree(ctx->dNumPairs[i]); cudaFree(ctx->dMHdr[i]); cudaFree(ctx->dMPts[i]); cudaFree(ctx->dPairFirst[i]);
     }
-    cudaFree(ctx->dRowOrdZero); cudaFree(ctx->dSlots);
+    cudaFree(ctx->dZeroBp); cudaFree(ctx->dZeroNp); cudaFree(ctx->dSlots);
     cudaFree(ctx->dNSorted); cudaFree(ctx->dNLocal); cudaFree(ctx->dOwner); cudaFree(ctx->dLocalList);
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dScyz); cudaFree(ctx->dRowStart);
-    cudaFree(ctx->dGrid); cudaFree(ctx->dCtr); cudaFreeHost(ctx->hCtrPinned);
+    cudaFree(ctx->dGrid); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
-    cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dRowZero); cudaFree(ctx->dBigRows);
-    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dHist); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dBinZero); cudaFree(ctx->dCursors); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); cudaFree(ctx->dSurvSorted); cudaFree(ctx->dSurvKey); cudaFree(ctx->dSurvZero); cudaFree(ctx->dSurvStart);
+    cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dBigRows);
+    cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dHist); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); cudaFree(ctx->dSurvSorted); cudaFree(ctx->dSurvKey); cudaFree(ctx->dSurvStart);
     cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
