@@ -342,6 +342,22 @@ int32_t b2c_compute_islands(b2c_ctx*, int32_t* tags_out, int32_t n, int32_t* num
 int32_t b2c_ray_test_closest(b2c_ctx*, int32_t n, const float* from_xyz, const float* to_xyz, int16_t group, int16_t mask,
                              int32_t* uid_out, float* fraction_out, float* normal_out, float* point_out);
 
+/* CollisionWorld.convexSweepTest with a ClosestConvexResultCallback per sweep (disp/CollisionWorld.java:596-651, 765-800),
+ * batched, for TRANSLATIONAL sweeps: sweep i moves the registered convex shape cast_shape_ids[i] (box, sphere or hull) with
+ * the fixed basis basis9[9*i..] (row-major) from from_xyz[3*i..] to to_xyz[3*i..].  group / mask = the callback's
+ * collisionFilterGroup / collisionFilterMask (:752-756); allowed_ccd_penetration = DispatcherInfo.allowedCcdPenetration
+ * (bp/DispatcherInfo.java:44, reference default 0.04).  Outputs per sweep: uid of hitCollisionObject (0 = none),
+ * closestHitFraction (1 = none), hitNormalWorld, hitPointWorld.  Per target objectQuerySingle (:392-551): convex bodies by
+ * np/GjkConvexCast.java:66-196, triangle meshes by the BVH box-cast walk (sh/OptimizedBvh.java:1017-1036) +
+ * np/TriangleConvexcastCallback.java:53-88 (SubsimplexConvexCast per triangle), compounds child by child.  The reference's
+ * static-plane branch dereferences a null caster (:470-477) and throws: a sweep whose expanded segment meets a static plane
+ * that passes the filter reports uid -1 (exclude planes with `mask`).  The cast shape's culling box is
+ * calculateTemporalAabb with zero angular velocity (what equal bases mean up to the reference's quaternion rounding).
+ * Uses the transforms currently resident. */
+int32_t b2c_convex_sweep_closest(b2c_ctx*, int32_t n, const int32_t* cast_shape_ids, const float* basis9, const float* from_xyz,
+                                 const float* to_xyz, int16_t group, int16_t mask, float allowed_ccd_penetration, int32_t* uid_out,
+                                 float* fraction_out, float* normal_out, float* point_out);
+
 /* ---- one world partitioned over several GPUs -------------------------------------
  * Space is cut into `nranks` slabs by planes along one axis; rank r owns slab r.  A PROXY is owned by the rank whose slab
  * held its origin when the partition was set: only that rank runs updateAabbs / setAabb for it.  A PAIR is owned by the slab

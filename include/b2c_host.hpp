@@ -173,6 +173,14 @@ public:
                         float* pointOut, int16_t group = 1, int16_t mask = -1) {
         check(b2c_ray_test_closest(ctx, n, fromXyz, toXyz, group, mask, uidOut, fractionOut, normalOut, pointOut), ctx);
     }
+    // CollisionWorld.convexSweepTest + ClosestConvexResultCallback for n translational sweeps (disp/CollisionWorld.java:596-651,
+    // 765-800); allowedCcdPenetration = getDispatchInfo().allowedCcdPenetration (bp/DispatcherInfo.java:44)
+    void convexSweepTestClosest(int32_t n, const int32_t* castShapeIds, const float* basis9, const float* fromXyz, const float* toXyz,
+                                int32_t* uidOut, float* fractionOut, float* normalOut, float* pointOut, int16_t group = 1,
+                                int16_t mask = -1, float allowedCcdPenetration = 0.04f) {
+        check(b2c_convex_sweep_closest(ctx, n, castShapeIds, basis9, fromXyz, toXyz, group, mask, allowedCcdPenetration, uidOut,
+                                       fractionOut, normalOut, pointOut), ctx);
+    }
     // SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110)
     int32_t computeIslands(std::vector<int32_t>& tags) {
         int32_t n = 0;

@@ -23,6 +23,7 @@
 #include "pairfind.cuh"
 #include "radix_sort.cuh"
 #include "raycast.cuh"
+#include "convexcast.cuh"
 
 using namespace b2c;
 
@@ -221,6 +222,9 @@ struct b2c_ctx {
     int nSortedBodies = 0;            // bodies covered by dSmin's sorted order (0: no broadphase has run)
     uint32_t* dRayOverflow = nullptr;
     int rayCap = 0;
+    float* dSweepIn = nullptr;     // basis 9 | from 3 | to 3 | cast shape id, 16 words per sweep
+    RayOut* dSweepOut = nullptr;
+    int sweepCap = 0;
 
     // islands + pair deltas (allocated on first use)
     int* dIslandPar = nullptr;
@@ -1189,6 +1193,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
     cudaFree(ctx->dRayChunkMin); cudaFree(ctx->dRayChunkMax); cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
+    cudaFree(ctx->dSweepIn); cudaFree(ctx->dSweepOut);
     cudaFree(ctx->dNoCollide);
     cudaFree(ctx->dChildren); cudaFree(ctx->dCompoundCtr); cudaFree(ctx->dCItemPair); cudaFree(ctx->dCItemCode); cudaFree(ctx->dCItemPrev);
     cudaFree(ctx->dCRaw); cudaFree(ctx->dCMeshStart); cudaFree(ctx->dCMeshCount); cudaFree(ctx->dCBigScratch);
@@ -2243,6 +2248,84 @@ int32_t b2c_ray_test_closest(b2c_ctx* ctx, int32_t n, const float* from, const f
     if (ov) {
         char buf[160];
         snprintf(buf, sizeof buf, "ray test: a ray met %u body AABBs, more than the %d candidates a block keeps", ov, RAY_MAX_CAND);
+        ctx->err = buf;
+        return B2C_ERR_CAPACITY;
+    }
+    for (int i = 0; i < n; i++) {
+        if (uidOut) uidOut[i] = host[i].uid;
+        if (fracOut) fracOut[i] = host[i].fraction;
+        if (nrmOut) { nrmOut[3 * i] = host[i].normal[0]; nrmOut[3 * i + 1] = host[i].normal[1]; nrmOut[3 * i + 2] = host[i].normal[2]; }
+        if (ptOut) { ptOut[3 * i] = host[i].point[0]; ptOut[3 * i + 1] = host[i].point[1]; ptOut[3 * i + 2] = host[i].point[2]; }
+    }
+    return B2C_OK;
+}
+
+int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castShapes, const float* basis9, const float* from, const float* to,
+                                 int16_t group, int16_t mask, float allowedPenetration, int32_t* uidOut, float* fracOut, float* nrmOut,
+                                 float* ptOut) {
+    if (!ctx || n < 0 || (n > 0 && (!castShapes || !basis9 || !from || !to))) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    for (int i = 0; i < n; i++) {
+        const int sid = castShapes[i];
+        if (sid < 0 || sid >= (int)ctx->hShapes.size()) { ctx->err = "convex sweep: unknown cast shape id"; return B2C_ERR_BAD_HANDLE; }
+        const int ty = ctx->hShapes[(size_t)sid].type;
+        if (ty != SH_BOX && ty != SH_SPHERE && ty != SH_HULL) {
+            ctx->err = "convex sweep: the cast shape must be convex (box, sphere or hull), as ConvexShape castShape is";
+            return B2C_ERR_BAD_ARG;
+        }
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    if (ctx->stagingCount || ctx->extPending) {
+        int32_t rc = runAabbKernel(ctx, false);
+        if (rc) return rc;
+    }
+    int32_t rc = uploadShapes(ctx);
+    if (rc) return rc;
+    const size_t N = (size_t)ctx->cfg.max_bodies;
+    if (!ctx->dRayMin) CK(dalloc(&ctx->dRayMin, N));
+    if (!ctx->dRayMax) CK(dalloc(&ctx->dRayMax, N));
+    if (!ctx->dRayOverflow) CK(dalloc(&ctx->dRayOverflow, (size_t)1));
+    if (!ctx->dRayChunkMin) CK(dalloc(&ctx->dRayChunkMin, N / RAY_CHUNK + 2));
+    if (!ctx->dRayChunkMax) CK(dalloc(&ctx->dRayChunkMax, N / RAY_CHUNK + 2));
+    if (n > ctx->sweepCap) {
+        cudaFree(ctx->dSweepIn); cudaFree(ctx->dSweepOut);
+        ctx->dSweepIn = nullptr; ctx->dSweepOut = nullptr; ctx->sweepCap = 0;
+        CK(cudaMalloc((void**)&ctx->dSweepIn, (size_t)n * 16 * sizeof(float)));  // shape id, basis 9, from 3, to 3
+        CK(cudaMalloc((void**)&ctx->dSweepOut, (size_t)n * sizeof(RayOut)));
+        ctx->sweepCap = n;
+    }
+    const int nb = ctx->nBodies;
+    float* dBasis = ctx->dSweepIn;
+    float* dFrom = dBasis + 9 * (size_t)n;
+    float* dTo = dFrom + 3 * (size_t)n;
+    int* dShape = reinterpret_cast<int*>(dTo + 3 * (size_t)n);
+    CK(cudaMemcpyAsync(dBasis, basis9, (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dFrom, from, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dTo, to, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dShape, castShapes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->dRayOverflow, 0, sizeof(uint32_t), s));
+    const int nSorted = ctx->nSortedBodies < nb ? ctx->nSortedBodies : nb;
+    if (nb > 0) {
+        k_ray_aabbs<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->dShapes, nb, ctx->dRayMin, ctx->dRayMax);
+        const int nChunks = (nb + RAY_CHUNK - 1) / RAY_CHUNK;
+        k_ray_chunks<<<(nChunks + 127) / 128, 128, 0, s>>>(ctx->dRayMin, ctx->dRayMax, ctx->dSmin, nSorted, nb, ctx->dRayChunkMin,
+                                                          ctx->dRayChunkMax);
+    }
+    const uint32_t cbFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
+    const unsigned grid = (unsigned)(n < 148 * 8 ? n : 148 * 8);
+    k_convex_sweep<<<grid, SWEEP_THREADS, 0, s>>>(ctx->B, ctx->dShapes, ctx->dHullPts, ctx->dMeshes, ctx->dChildren, ctx->dSmin, nSorted,
+                                                  ctx->dRayChunkMin, ctx->dRayChunkMax, nb, ctx->dRayMin, ctx->dRayMax, dShape, dBasis,
+                                                  dFrom, dTo, n, cbFilter, allowedPenetration, ctx->dSweepOut, ctx->dRayOverflow);
+    std::vector<RayOut> host((size_t)n);
+    uint32_t ov = 0;
+    CK(cudaMemcpyAsync(host.data(), ctx->dSweepOut, (size_t)n * sizeof(RayOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ov, ctx->dRayOverflow, sizeof(ov), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ov) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "convex sweep: a sweep met %u expanded body AABBs, more than the %d candidates a block keeps", ov,
+                 SWEEP_MAX_CAND);
         ctx->err = buf;
         return B2C_ERR_CAPACITY;
     }

@@ -245,6 +245,31 @@ class GpuCollisionWorld:
             self._ck(self.L.b2c_ray_test_closest(self.h, n, _vp(f), _vp(t), int(group), int(mask), _vp(uid), _vp(frac), _vp(nrm), _vp(pt)))
         return uid, frac, nrm, pt
 
+    def convexSweepTestClosest(self, cast_shapes, basis, sweep_from, sweep_to, group=1, mask=-1, allowed_ccd_penetration=0.04):
+        """CollisionWorld.convexSweepTest + ClosestConvexResultCallback (disp/CollisionWorld.java:596-651, 765-800) for a batch
+        of translational sweeps: cast_shapes = registered convex shape ids (one, or one per sweep), basis = one 3x3 (shared) or n
+        of them, sweep_from / sweep_to = n x 3 origins.  Returns (uid (0 = miss, -1 = the sweep reached the reference's
+        broken static-plane branch), fraction, normal, point)."""
+        f = np.ascontiguousarray(sweep_from, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(sweep_to, dtype=np.float32).reshape(-1, 3)
+        n = len(f)
+        if len(t) != n:
+            raise ValueError("sweep_from and sweep_to must hold the same number of origins")
+        ids = np.full(n, int(cast_shapes), np.int32) if np.isscalar(cast_shapes) else np.ascontiguousarray(cast_shapes, dtype=np.int32)
+        b = np.ascontiguousarray(basis, dtype=np.float32).reshape(-1, 9)
+        if len(b) == 1 and n != 1:
+            b = np.ascontiguousarray(np.repeat(b, n, axis=0))
+        if len(ids) != n or len(b) != n:
+            raise ValueError("one cast shape and one basis per sweep")
+        uid = np.zeros(n, dtype=np.int32)
+        frac = np.zeros(n, dtype=np.float32)
+        nrm = np.zeros((n, 3), dtype=np.float32)
+        pt = np.zeros((n, 3), dtype=np.float32)
+        if n:
+            self._ck(self.L.b2c_convex_sweep_closest(self.h, n, _vp(ids), _vp(b), _vp(f), _vp(t), int(group), int(mask),
+                                                     float(allowed_ccd_penetration), _vp(uid), _vp(frac), _vp(nrm), _vp(pt)))
+        return uid, frac, nrm, pt
+
     def setNoCollidePairs(self, pairs):
         """Body pairs linked by a collision-disabling constraint (dynamics/RigidBody.java:624-639): kept in the pair cache,
         never dispatched."""

@@ -555,8 +555,10 @@ struct GjkOut {
     int deepPenetrationChecks = 0;  // BulletStats.gNumDeepPenetrationChecks contribution (:270)
 };
 
+// usePenetrationSolver = false: GjkPairDetector.init(..., penetrationDepthSolver = null) as np/GjkConvexCast.java:107 does
 static inline void gjkGetClosestPoints(const Shape* minkowskiA, const Shape* minkowskiB, const Xf& transformA,
-                                       const Xf& transformB, float maximumDistanceSquared, GjkOut& out) {
+                                       const Xf& transformB, float maximumDistanceSquared, GjkOut& out,
+                                       bool usePenetrationSolver = true) {
     static const float REL_ERROR2 = 1.0e-6f;  // :44
     V3 tmp;
     float distance = 0.0f;
@@ -671,7 +673,7 @@ static inline void gjkGetClosestPoints(const Shape* minkowskiA, const Shape* min
         }
 
         bool catchDegeneratePenetrationCase = (degenerateSimplex != 0 && ((distance + margin) < 0.01f));
-        if (checkPenetration && (!isValid || catchDegeneratePenetrationCase)) {
+        if (usePenetrationSolver && checkPenetration && (!isValid || catchDegeneratePenetrationCase)) {  // :266-269
             out.deepPenetrationChecks++;
             bool isValid2 = calcPenDepth(minkowskiA, minkowskiB, localTransA, localTransB, tmpPointOnA, tmpPointOnB);
             if (isValid2) {

@@ -181,6 +181,23 @@ void orc_ray_test_closest(void* h, int n, const float* from, const float* to, in
         out7[7 * i + 4] = r.point.x; out7[7 * i + 5] = r.point.y; out7[7 * i + 6] = r.point.z;
     }
 }
+// CollisionWorld.convexSweepTest + ClosestConvexResultCallback for n translational sweeps of registered convex shapes:
+// basis 9 floats (row-major) per sweep, from / to 3 floats each; out: uid (0 = miss, -1 = the sweep met a static plane),
+// fraction, normal xyz, point xyz
+void orc_convex_sweep_closest(void* h, int n, const int* shapes, const float* basis9, const float* from, const float* to, int group,
+                              int mask, float allowedPenetration, int* uidOut, float* out7) {
+    World* w = (World*)h;
+    for (int i = 0; i < n; i++) {
+        float f12[12], t12[12];
+        for (int k = 0; k < 9; k++) f12[k] = t12[k] = basis9[9 * i + k];
+        for (int k = 0; k < 3; k++) { f12[9 + k] = from[3 * i + k]; t12[9 + k] = to[3 * i + k]; }
+        ConvexSweepHit r = w->convexSweepClosest(shapes[i], xfFrom12(f12), xfFrom12(t12), group, mask, allowedPenetration);
+        uidOut[i] = r.unsupported ? -1 : r.uid;
+        out7[7 * i] = r.fraction;
+        out7[7 * i + 1] = r.normal.x; out7[7 * i + 2] = r.normal.y; out7[7 * i + 3] = r.normal.z;
+        out7[7 * i + 4] = r.point.x; out7[7 * i + 5] = r.point.y; out7[7 * i + 6] = r.point.z;
+    }
+}
 int orc_dispatch_all_pairs(void* h) { return ((World*)h)->dispatchAllPairs(); }
 int orc_num_raw(void* h) { return (int)((World*)h)->raw.size(); }
 // raw record: 5 ints (uid0, uid1, tri, hasContact, method) + iters ; 7 floats (normal, point, depth)

@@ -192,13 +192,22 @@ struct TriangleRaycast {
 };
 
 // sh/OptimizedBvh.java:817-931 walkStacklessQuantizedTreeAgainstRay with zero box-cast extents (:999-1005)
+// and with the box-cast extents of sh/OptimizedBvh.java:1017-1036 reportBoxCastOverlappingNodex
+template <class F>
+static inline void bvhReportBoxCastOverlappingNodex(const Bvh& bvh, const V3& raySource, const V3& rayTarget, const V3& aabbMin,
+                                                    const V3& aabbMax, F cb);
 template <class F>
 static inline void bvhReportRayOverlappingNodex(const Bvh& bvh, const V3& raySource, const V3& rayTarget, F cb) {
     V3 zero(0, 0, 0);
+    bvhReportBoxCastOverlappingNodex(bvh, raySource, rayTarget, zero, zero, cb);
+}
+template <class F>
+static inline void bvhReportBoxCastOverlappingNodex(const Bvh& bvh, const V3& raySource, const V3& rayTarget, const V3& aabbMin,
+                                                    const V3& aabbMax, F cb) {
     V3 rayAabbMin(jminf(raySource.x, rayTarget.x), jminf(raySource.y, rayTarget.y), jminf(raySource.z, rayTarget.z));
     V3 rayAabbMax(jmaxf(raySource.x, rayTarget.x), jmaxf(raySource.y, rayTarget.y), jmaxf(raySource.z, rayTarget.z));
-    rayAabbMin.add(zero);
-    rayAabbMax.add(zero);
+    rayAabbMin.add(aabbMin);  // :856-858 add box cast extents to bounding box
+    rayAabbMax.add(aabbMax);
     uint16_t qmin[3], qmax[3];
     bvh.quantizeWithClamp(rayAabbMin, qmin);
     bvh.quantizeWithClamp(rayAabbMax, qmax);
@@ -215,8 +224,8 @@ static inline void bvhReportRayOverlappingNodex(const Bvh& bvh, const V3& raySou
         const bool isLeaf = n.isLeaf();
         if (boxBoxOverlap) {
             V3 b0 = bvh.unQuantize(n.mn), b1 = bvh.unQuantize(n.mx);
-            b0.add(zero);
-            b1.add(zero);
+            b0.add(aabbMin);  // :901-903 add box cast extents
+            b1.add(aabbMax);
             V3 normal;
             rayBoxOverlap = rayAabb(raySource, rayTarget, b0, b1, param, normal);
         }

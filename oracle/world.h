@@ -20,6 +20,7 @@
 #include "dbvt_literal.h"
 #include "sap_literal.h"
 #include "gjk.h"
+#include "convexcast.h"
 #include "raycast.h"
 #include "jmath.h"
 #include "manifold.h"
@@ -457,6 +458,102 @@ struct World {
             V3 hitNormal;
             if (!rayAabb(from, to, mn, mx, hitLambda, hitNormal)) continue;
             rayTestSingle(from, to, b, b.shape, b.xf, closest, hit);
+        }
+        return hit;
+    }
+
+    // disp/CollisionWorld.java:392-551 objectQuerySingle against the running ClosestConvexResultCallback state
+    void objectQuerySingle(const Shape& cast, const Xf& fromT, const Xf& toT, const Body& b, int shapeIndex, const Xf& xf,
+                           float allowedPenetration, ConvexSweepHit& hit) const {
+        const Shape& s = shapes[shapeIndex];
+        if (s.isConvex()) {
+            ConvexCastResult cr;
+            cr.allowedPenetration = allowedPenetration;
+            cr.fraction = 1.f;
+            if (gjkConvexCast(cast, fromT, toT, s, xf, cr)) {
+                if (cr.normal.len2() > 0.0001f) {
+                    if (cr.fraction < hit.fraction) {
+                        cr.normal.nor();
+                        hit.fraction = cr.fraction;           // ClosestConvexResultCallback.addSingleResult, normalInWorldSpace
+                        hit.uid = b.uid;
+                        hit.normal.set(cr.normal);
+                        hit.point.set(cr.hitPoint);
+                    }
+                }
+            }
+        } else if (s.type == SH_MESH) {
+            Xf worldToObj; worldToObj.set(xf);
+            worldToObj.inverse();
+            V3 fromLocal = fromT.origin; worldToObj.transform(fromLocal);
+            V3 toLocal = toT.origin; worldToObj.transform(toLocal);
+            Xf rotationXform;  // rotation of the cast box in mesh space = MeshRotation^-1 * ConvexToRotation, origin 0
+            rotationXform.basis.set(worldToObj.basis);
+            rotationXform.basis.mul(toT.basis);
+            rotationXform.origin.set(0, 0, 0);
+            V3 boxMin, boxMax;
+            shapeGetAabb(cast, rotationXform, boxMin, boxMax);
+            const MeshShapeData* md = meshes[shapeIndex].get();
+            const float entry = hit.fraction;  // tccb.hitFraction = resultCallback.closestHitFraction, never updated afterwards
+            bvhReportBoxCastOverlappingNodex(md->bvh, fromLocal, toLocal, boxMin, boxMax, [&](int part, int tri) {
+                Shape tm;
+                tm.type = SH_TRIANGLE;
+                md->mesh.getTriangle(part, tri, tm.tri);
+                tm.collisionMargin = s.getMargin();  // triangleMesh.getMargin()
+                ConvexCastResult cr;
+                cr.fraction = 1.f;
+                if (subsimplexConvexCast(cast, fromT, toT, tm, xf, xf, cr)) {
+                    if (cr.normal.len2() > 0.0001f) {
+                        if (cr.fraction < entry) {
+                            cr.normal.nor();
+                            if (cr.fraction <= hit.fraction) {   // reportHit: hitFraction <= closestHitFraction
+                                hit.fraction = cr.fraction;
+                                hit.uid = b.uid;
+                                hit.normal.set(cr.normal);       // normalInWorldSpace = true
+                                hit.point.set(cr.hitPoint);
+                            }
+                        }
+                    }
+                }
+            });
+        } else if (s.type == SH_PLANE) {
+            hit.unsupported = true;  // the reference calls calcTimeOfImpact on a null caster here (:470-477)
+        } else if (s.isCompound()) {
+            for (const CompoundChild& c : s.children) {
+                Xf childWorld; childWorld.set(xf);
+                childWorld.mul(c.transform);
+                objectQuerySingle(cast, fromT, toT, b, c.shape, childWorld, allowedPenetration, hit);
+            }
+        }
+    }
+
+    // disp/CollisionWorld.java:596-651 convexSweepTest with a ClosestConvexResultCallback(group, mask), translational sweep
+    ConvexSweepHit convexSweepClosest(int castShape, const Xf& fromT, const Xf& toT, int group, int mask, float allowedPenetration) const {
+        ConvexSweepHit hit;
+        const Shape& cast = shapes[castShape];
+        // calculateTemporalAabb(R, linVel, angVel = 0, 1): R = the cast shape's rotation with a zero origin
+        Xf R; R.basis.set(fromT.basis); R.origin.set(0, 0, 0);
+        V3 castMin, castMax;
+        shapeGetAabb(cast, R, castMin, castMax);
+        V3 lin; lin.set(toT.origin).sub(fromT.origin);
+        lin.scl(1.f / 1.f);
+        lin.scl(1.f);
+        if (lin.x > 0.f) castMax.x += lin.x; else castMin.x += lin.x;
+        if (lin.y > 0.f) castMax.y += lin.y; else castMin.y += lin.y;
+        if (lin.z > 0.f) castMax.z += lin.z; else castMin.z += lin.z;
+        { V3 am(0, 0, 0); castMin.sub(am); castMax.add(am); }
+        for (const Body& b : bodies) {
+            if (!b.alive) continue;
+            bool collides = ((int)b.group & mask & 0xFFFF) != 0;                     // :752-756
+            collides = collides && ((group & (int)b.mask) & 0xFFFF) != 0;
+            if (!collides) continue;
+            V3 mn, mx;
+            shapeGetAabb(shapes[b.shape], b.xf, mn, mx);
+            mn.add(castMin);                                                         // AabbUtil2.aabbExpand
+            mx.add(castMax);
+            float hitLambda = 1.f;
+            V3 hitNormal;
+            if (!rayAabb(fromT.origin, toT.origin, mn, mx, hitLambda, hitNormal)) continue;
+            objectQuerySingle(cast, fromT, toT, b, b.shape, b.xf, allowedPenetration, hit);
         }
         return hit;
     }

@@ -14,6 +14,7 @@
 #include "../../oracle/world.h"
 #include "../../libgdx-jbullet_b200/csrc/compound.cuh"
 #include "../../libgdx-jbullet_b200/csrc/raycast.cuh"
+#include "../../libgdx-jbullet_b200/csrc/convexcast.cuh"
 namespace b2c { alignas(16) unsigned char epaSmem[2 * sizeof(EpaScratch)]; }
 using namespace b2c;
 static std::mt19937 rng(777);
@@ -83,7 +84,7 @@ int main(int argc, char** argv) {
         for (int r = 0; r < 3; r++) xf4.push_back(make_float4(t[3 * r], t[3 * r + 1], t[3 * r + 2], t[9 + r]));
         filt.push_back(((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16)); flags.push_back(BF_ALIVE | BF_ACTIVE); };
     { float t[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}; addBody(pl, t, 2, -1 ^ 2); }
-    { float t[12]; randRot(t); if (!tiltPlane) { t[0] = 1; t[1] = 0; t[2] = 0; t[3] = 0; t[4] = 1; t[5] = 0; t[6] = 0; t[7] = 0; t[8] = 1; } t[9] = 0.25f; t[10] = 0.5f; t[11] = -0.5f; addBody(meshShape, t, 2, -1 ^ 2); }
+    { float t[12]; randRot(t); if (!tiltPlane) { t[0] = 1; t[1] = 0; t[2] = 0; t[3] = 0; t[4] = 1; t[5] = 0; t[6] = 0; t[7] = 0; t[8] = 1; } t[9] = 0.25f; t[10] = 0.5f; t[11] = -0.5f; addBody(meshShape, t, 8, -1 ^ 2); }
     for (int i = 0; i < NB; i++) { float t[12]; randRot(t); t[9] = uf(0, 12); t[10] = uf(0.5f, 5); t[11] = uf(0, 12); addBody(kinds[rng() % kinds.size()], t, (i % 7 == 0) ? 4 : 1, -1); }
     hull.resize(hull.size() + 8);
     const int N = (int)bodyShape.size();
@@ -124,6 +125,44 @@ int main(int argc, char** argv) {
         }
         if (h.uid) { hits++; int t = shapes[bodyShape[h.uid - 1]].type; hitMesh += t == SH_MESH; hitPlane += t == SH_PLANE; hitComp += t == SH_COMPOUND; }
     }
-    printf("ALL OK rays %d hits %d mesh %d plane %d compound %d overflow %u\n", NR, hits, hitMesh, hitPlane, hitComp, overflow);
+    // ---- convex sweeps (convexcast.cuh): sphere / box / hull casts with random bases; the callback mask leaves the static
+    // plane out (group 2) except for every 50th sweep, which must report the reference's unsupported branch (uid -1)
+    const int NS = NR / 4;
+    int sHits = 0, sMesh = 0, sComp = 0, sUnsup = 0;
+    const int castKinds[3] = {sS, bx, hl};
+    for (int pass = 0; pass < 2; pass++) {
+        const int smask = pass == 0 ? (-1 ^ 2) : -1;
+        const int ns = pass == 0 ? NS : NS / 50 + 1;
+        std::vector<int> castShape(ns); std::vector<float> basis(9 * ns), sf(3 * ns), st(3 * ns);
+        for (int r = 0; r < ns; r++) {
+            castShape[r] = castKinds[rng() % 3];
+            randRot(&basis[9 * r]);
+            if (r % 3 == 0) { float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(&basis[9 * r], I, 36); }
+            for (int c = 0; c < 3; c++) { sf[3 * r + c] = uf(-1, 13); st[3 * r + c] = sf[3 * r + c] + uf(-4, 4); }
+            sf[3 * r + 1] = uf(0, 7); st[3 * r + 1] = sf[3 * r + 1] + uf(-6, 2);
+        }
+        std::vector<RayOut> so(ns); uint32_t sov = 0;
+        const uint32_t sFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)smask << 16);
+        k_convex_sweep(B, shapes.data(), hull.data(), meshes.data(), children.data(), sortedMin.data(), nSorted, cmin.data(), cmax.data(), N, rmin.data(), rmax.data(), castShape.data(), basis.data(), sf.data(), st.data(), ns, sFilter, 0.04f, so.data(), &sov);
+        if (sov) { printf("sweep candidate overflow %u\n", sov); return 1; }
+        for (int r = 0; r < ns; r++) {
+            orc::Xf f, t;
+            for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) f.basis.m[a][c] = t.basis.m[a][c] = basis[9 * r + 3 * a + c];
+            f.origin.set(sf[3 * r], sf[3 * r + 1], sf[3 * r + 2]); t.origin.set(st[3 * r], st[3 * r + 1], st[3 * r + 2]);
+            orc::ConvexSweepHit h = W.convexSweepClosest(castShape[r], f, t, group, smask, 0.04f);
+            const RayOut& g = so[r];
+            const int huid = h.unsupported ? -1 : h.uid;
+            float of[7] = {h.fraction, h.normal.x, h.normal.y, h.normal.z, h.point.x, h.point.y, h.point.z};
+            float gf[7] = {g.fraction, g.normal[0], g.normal[1], g.normal[2], g.point[0], g.point[1], g.point[2]};
+            if (g.uid != huid || (huid > 0 && memcmp(of, gf, 28)) || (huid == 0 && g.fraction != 1.f)) {
+                printf("sweep %d/%d differs: uid %d/%d frac %.9g/%.9g n (%g %g %g)/(%g %g %g) p (%g %g %g)/(%g %g %g)\n", pass, r, g.uid, huid, g.fraction, h.fraction, g.normal[0], g.normal[1], g.normal[2], h.normal.x, h.normal.y, h.normal.z, g.point[0], g.point[1], g.point[2], h.point.x, h.point.y, h.point.z);
+                return 1;
+            }
+            if (huid > 0) { sHits++; int ty = shapes[bodyShape[huid - 1]].type; sMesh += ty == SH_MESH; sComp += ty == SH_COMPOUND; }
+            sUnsup += huid < 0;
+        }
+        if (pass == 1 && sUnsup == 0) { printf("no sweep reached the static plane branch\n"); return 1; }
+    }
+    printf("ALL OK rays %d hits %d mesh %d plane %d compound %d overflow %u | sweeps %d hits %d mesh %d compound %d unsupported %d\n", NR, hits, hitMesh, hitPlane, hitComp, overflow, NS, sHits, sMesh, sComp, sUnsup);
     return 0;
 }

@@ -61,6 +61,7 @@ def lib():
     L.orc_get_pairs.argtypes = [C.c_void_p, i32p]
     L.orc_dispatch_all_pairs.argtypes = [C.c_void_p]
     L.orc_ray_test_closest.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_int, i32p, f32p]
+    L.orc_convex_sweep_closest.argtypes = [C.c_void_p, C.c_int, i32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, i32p, f32p]
     L.orc_pair_deltas.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, i32p]
     L.orc_islands.argtypes = [C.c_void_p, i32p]
     L.orc_num_raw.argtypes = [C.c_void_p]
@@ -224,6 +225,21 @@ class OracleWorld:
         uid = np.zeros(len(f), dtype=np.int32)
         out = np.zeros((len(f), 7), dtype=np.float32)
         self.L.orc_ray_test_closest(self.h, len(f), f, t, int(group), int(mask), uid, out)
+        return uid, out[:, 0].copy(), out[:, 1:4].copy(), out[:, 4:7].copy()
+
+    def convex_sweep_closest(self, cast_shapes, basis, sweep_from, sweep_to, group=1, mask=-1, allowed_ccd_penetration=0.04):
+        """CollisionWorld.convexSweepTest with a ClosestConvexResultCallback per translational sweep: (uid (0 = miss, -1 = the
+        static-plane branch the reference throws in), fraction, normal, point)."""
+        f = np.ascontiguousarray(sweep_from, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(sweep_to, dtype=np.float32).reshape(-1, 3)
+        n = len(f)
+        ids = np.full(n, int(cast_shapes), np.int32) if np.isscalar(cast_shapes) else np.ascontiguousarray(cast_shapes, dtype=np.int32)
+        b = np.ascontiguousarray(basis, dtype=np.float32).reshape(-1, 9)
+        if len(b) == 1 and n != 1:
+            b = np.ascontiguousarray(np.repeat(b, n, axis=0))
+        uid = np.zeros(n, dtype=np.int32)
+        out = np.zeros((n, 7), dtype=np.float32)
+        self.L.orc_convex_sweep_closest(self.h, n, ids, b, f, t, int(group), int(mask), float(allowed_ccd_penetration), uid, out)
         return uid, out[:, 0].copy(), out[:, 1:4].copy(), out[:, 4:7].copy()
 
     def dispatch_all_pairs(self):

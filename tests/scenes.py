@@ -403,6 +403,7 @@ def build_gpu(pkg, sc, mode, max_pairs=None, **kw):
             ids.append(gw.CompoundShape([ids[c] for c in s[1]], s[2]))
     shapes = np.asarray([ids[k] for k in sc.body_shape], dtype=np.int32)
     gw.addCollisionObjects(shapes, sc.base, sc.group, sc.mask, np.asarray(sc.static, dtype=np.int32), sc.world)
+    gw.scene_shape_ids = ids          # scene shape index -> registered shape id
     return gw
 
 
@@ -427,6 +428,7 @@ def build_oracle(sc, mode, brute_force=False, world_aabb=None):
             ids.append(ow.compound([ids[c] for c in s[1]], s[2]))
     for k in range(sc.n):
         ow.body(ids[sc.body_shape[k]], sc.base[k], sc.group[k], sc.mask[k], sc.static[k], sc.world[k])
+    ow.scene_shape_ids = ids
     return ow
 
 

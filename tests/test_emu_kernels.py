@@ -1,4 +1,4 @@
-"""CPU: the device code of narrowphase.cuh / compound.cuh / raycast.cuh (with gjk.cuh, epa.cuh) compiled
+"""CPU: the device code of narrowphase.cuh / compound.cuh / raycast.cuh / convexcast.cuh (with gjk.cuh, epa.cuh) compiled
 for the host with a shim of the CUDA built-ins (tests/emu/) and run against the oracle: every child manifold, raw record and
 ray hit must be bit-identical.  Test infrastructure only — nothing here is a product path; the -m gpu tests remain the parity
 tests proper."""
@@ -34,7 +34,9 @@ def test_compound_kernels_match_the_oracle_on_the_host(binaries, args):
 @pytest.mark.parametrize("args", [("200", "3000"), ("400", "3000", "tilt"), ("300", "2000", "tilt", "mask")])
 def test_ray_kernels_match_the_oracle_on_the_host(binaries, args):
     """k_ray_aabbs / k_ray_chunks / k_ray_test against convex bodies, a rotated triangle mesh, a tilted static plane and
-    compounds, with and without a callback filter: hit body, fraction, normal and point, bit for bit."""
+    compounds, with and without a callback filter: hit body, fraction, normal and point, bit for bit.  Then k_convex_sweep
+    (convexcast.cuh) on the same scene: sphere / box / hull casts with random bases against convex bodies, the mesh and
+    compounds, plus the sweeps that must land in the reference's throwing static-plane branch."""
     r = subprocess.run([binaries["emu_ray"], *args], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 

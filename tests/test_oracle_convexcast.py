@@ -1,0 +1,84 @@
+"""CPU: known answers for the oracle's CollisionWorld.convexSweepTest restatement (oracle/convexcast.h) — the oracle is test
+infrastructure; these pin it against closed-form times of impact before the -m gpu tests compare the device path with it."""
+import numpy as np
+
+import orc
+import scenes
+
+EYE = np.eye(3, dtype=np.float32)
+
+
+def _world():
+    w = orc.OracleWorld(mode=orc.TIGHT)
+    return w
+
+
+def test_sphere_swept_onto_a_sphere_and_a_box():
+    w = _world()
+    big = w.sphere(1.0)
+    small = w.sphere(0.25)
+    bx = w.box(1.0, 0.5, 1.0)
+    w.body(big, orc.xf12(origin=(0, 0, 0)), 1, -1, False, 0)
+    w.body(bx, orc.xf12(origin=(10, 0, 0)), 1, -1, False, 0)
+    # straight down onto the sphere's pole: touching when the centres are 1.25 apart -> travelled 3.75 of 10
+    uid, frac, nrm, pt = w.convex_sweep_closest(small, EYE, [(0, 5, 0), (10, 5, 0), (5, 5, 0)], [(0, -5, 0), (10, -5, 0), (5, -5, 0)])
+    assert uid.tolist() == [1, 2, 0]
+    assert abs(frac[0] - 0.375) < 2e-3 and abs(frac[1] - (5 - 0.75) / 10) < 2e-3 and frac[2] == 1.0
+    assert np.allclose(nrm[:2], [[0, 1, 0], [0, 1, 0]], atol=1e-3)
+    assert np.allclose(pt[0], [0, 1, 0], atol=5e-3) and abs(pt[1][1] - 0.5) < 5e-3
+    # conservative advancement stops within its 0.001 radius BEFORE contact: never past the true time of impact
+    assert frac[0] <= 0.375 + 1e-6 and frac[1] <= 0.425 + 1e-6
+
+
+def test_closest_of_several_targets_filter_and_overlapping_start():
+    w = _world()
+    s = w.sphere(0.5)
+    cast = w.box(0.2, 0.2, 0.2)
+    for k, x in enumerate((6.0, 3.0, 9.0)):
+        w.body(s, orc.xf12(origin=(x, 0, 0)), 1 if k != 1 else 4, -1, False, 0)
+    f, t = [(0, 0, 0)], [(12, 0, 0)]
+    uid, frac, nrm, _ = w.convex_sweep_closest(cast, EYE, f, t)
+    assert uid[0] == 2 and abs(frac[0] - (3 - 0.5 - 0.2) / 12) < 2e-3 and nrm[0][0] < -0.99
+    uid, frac, _, _ = w.convex_sweep_closest(cast, EYE, f, t, group=1, mask=-1 ^ 4)    # the callback ignores group 4
+    assert uid[0] == 1 and abs(frac[0] - (6 - 0.5 - 0.2) / 12) < 2e-3
+    # a sweep that starts in deep overlap: GjkPairDetector without a penetration solver has no valid result -> no hit from it
+    uid, frac, _, _ = w.convex_sweep_closest(cast, EYE, [(3, 0, 0)], [(3, 5, 0)], group=1, mask=4)
+    assert uid[0] == 0 and frac[0] == 1.0
+    # moving away from a body it almost touches: n.r >= -allowedPenetration rejects
+    uid, _, _, _ = w.convex_sweep_closest(cast, EYE, [(3, 0.7004, 0)], [(3, 5, 0)], group=1, mask=4)
+    assert uid[0] == 0
+
+
+def test_sweep_onto_a_mesh_a_compound_and_the_plane_branch():
+    sc = scenes.terrain_scene(cells=16, n=0, seed=3)
+    ow = scenes.build_oracle(sc, orc.TIGHT)
+    sph = ow.sphere(0.3)
+    bar = ow.box(0.5, 0.1, 0.1)
+    comp = ow.compound([sph, bar], scenes.make_xf(np.stack([EYE, EYE]), np.asarray([(0, 0.5, 0), (0, 0, 0)])))
+    ow.body(comp, orc.xf12(origin=(4, 6, 4)), 1, -1, False, 0)
+    cast = ow.sphere(0.2)
+    uid, frac, nrm, pt = ow.convex_sweep_closest(cast, EYE, [(4, 9, 4), (2, 9, 2)], [(4, -3, 4), (2, -3, 2)])
+    # first sweep lands on the compound's upper sphere (top at y = 6.8), second on the terrain
+    assert uid.tolist() == [2, 1]
+    assert abs(frac[0] - (9 - 6.8 - 0.2) / 12) < 2e-3 and nrm[0][1] > 0.99
+    assert 0.3 < frac[1] < 1.0 and nrm[1][1] > 0.5
+    assert abs(pt[0][1] - 6.8) < 5e-3
+    # the mesh reports a point ON the triangle side (hitB of the simplex), within the mesh margin of the surface
+    pl = ow.plane([0.0, 1.0, 0.0], -5.0)
+    ow.body(pl, orc.xf12(), 2, -1 ^ 2, True, 0)
+    uid, _, _, _ = ow.convex_sweep_closest(cast, EYE, [(4, 9, 4)], [(4, -3, 4)])
+    assert uid[0] == -1                       # the reference throws in its static-plane branch
+    uid, _, _, _ = ow.convex_sweep_closest(cast, EYE, [(4, 9, 4)], [(4, -3, 4)], group=1, mask=-1 ^ 2)
+    assert uid[0] == 2
+
+
+def test_rotated_box_cast_uses_its_basis():
+    w = _world()
+    ground = w.box(5, 0.5, 5)
+    w.body(ground, orc.xf12(origin=(0, -0.5, 0)), 1, -1, False, 0)
+    cast = w.box(0.5, 0.5, 0.5)
+    c, s = np.cos(np.pi / 4), np.sin(np.pi / 4)
+    rot = np.asarray([[c, -s, 0], [s, c, 0], [0, 0, 1]], np.float32)    # 45 degrees about z: the lowest corner is sqrt(.5) down
+    uid, frac, _, _ = w.convex_sweep_closest(cast, [EYE, rot], [(0, 5, 0), (1, 5, 0)], [(0, -5, 0), (1, -5, 0)])
+    assert uid.tolist() == [1, 1]
+    assert abs(frac[0] - 0.45) < 2e-3 and abs(frac[1] - (5 - np.sqrt(0.5)) / 10) < 3e-3
