@@ -422,6 +422,7 @@ def measure(rig, wl, sc, steps, warmup, e2e_steps, want_stages, partitioned=Fals
     ms_per_step = float(np.mean([ev0[k].elapsed_time(ev1[k]) for k in range(steps)]))
 
     stage_ms = {}
+    gjk_ms = 0.0
     if want_stages:
         gw.set_profiling(True)
         prof_steps = max(3, min(steps, 10))
@@ -433,6 +434,7 @@ def measure(rig, wl, sc, steps, warmup, e2e_steps, want_stages, partitioned=Fals
             gw.sync_counts()
             for nm, ms in gw.stage_times().items():
                 stage_ms[nm] = stage_ms.get(nm, 0.0) + ms / prof_steps
+            gjk_ms += gw.gjk_kernel_ms() / prof_steps
             step_no += 1
         gw.set_profiling(False)
         rig.barrier()
@@ -473,7 +475,7 @@ def measure(rig, wl, sc, steps, warmup, e2e_steps, want_stages, partitioned=Fals
                 d2h = (nA.value + nR.value) * 8 + nH.value * 16 + nPt.value * 48 + 128
         rig.barrier()
     out = dict(ms=ms_per_step, e2e_ms=float(np.mean(e2e_ms)) if e2e_ms else 0.0, pairs=pairs_tot, contacts=contacts_tot,
-               manifolds=manif_tot, launches=launches, stats=st, stage_ms=stage_ms, d2h=int(d2h), nb=nb, steps=steps,
+               manifolds=manif_tot, launches=launches, stats=st, stage_ms=stage_ms, gjk_ms=gjk_ms, d2h=int(d2h), nb=nb, steps=steps,
                mg=(mg.describe() if mg is not None else None))
     if mg is not None:
         mg.close()
@@ -560,21 +562,56 @@ def run_ours(args):
     body_bits = 12 + min(20, int(np.ceil(np.log2(2 * nb + 66))))
     abytes = {s: algorithmic_bytes(s, nb, P_avg, st, (body_bits + 7) // 8, contacts_live) for s in stage_ms}
     frac = {s: (abytes[s] / (stage_ms[s] * 1e-3) / 1e9) / peak_gbs if stage_ms[s] > 0 else 0.0 for s in stage_ms}
-    # the HBM-shaped part of the step is the broadphase (sort / sweep / pair ordering): its roofline is bytes / time against
-    # the measured copy bandwidth.  The narrowphase stages are FP32-issue / divergence bound (ncu: profiles/), reported below.
+    # Two rooflines.  The DOMINANT kernel of the step is k_gjk (the GJK iterations of every convex-convex pair that
+    # survives the prefilter): FP32-issue / divergence bound, DRAM nearly idle — so its roofline is instruction issue: thread
+    # instructions per launch (a property of the workload, counted once by ncu on this same seeded snapshot:
+    # profiles/kernel_metrics.json) / the launch time measured LIVE here with its own CUDA-event pair, against
+    # 148 SMs x 4 schedulers x 32 lanes x the SM clock sampled during the run.  The HBM-shaped part of the step is the
+    # broadphase (sort / sweep / pair ordering): bytes / time against the measured copy bandwidth, reported beside it.
     bp_ms = sum(stage_ms.get(s, 0.0) for s in BROADPHASE_STAGES)
     bp_bytes = 180 * nb + 8 * P_avg            # 180 B/proxy + 8 B/pair
     dom = max(stage_ms, key=stage_ms.get)
-    ncu = {}
+    km = {}
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "kernel_metrics.json")))
+        km = json.load(open(os.path.join(ROOT, "profiles", "kernel_metrics.json")))
     except Exception:
         pass
-    traffic = None
+    traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("broadphase")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
+    # the counted instructions belong to the default snapshot only (100 000 bodies, settled, seed 100)
+    gk = km.get("kernels", {}).get("k_gjk") if (wl == "c2" and args.bodies == 100000 and settled) else None
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / 1e12          # T thread-instructions / s
+    gjk_ms = r.get("gjk_ms", 0.0)
+    hbm_obj = {"bound": "hbm", "kernel": "broadphase (k_aabb .. pair rows: sort / sweep / pair ordering)",
+               "achieved": bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms > 0 else 0.0, "peak": peak_gbs, "unit": "GB/s",
+               "frac": (bp_bytes / (bp_ms * 1e-3) / 1e9) / peak_gbs if bp_ms > 0 else 0.0,
+               "traffic": traffic.get("broadphase"), "peak_source": peak_src,
+               "algorithmic_bytes_per_launch": bp_bytes, "ms": bp_ms,
+               "formula": "SURVEY 8(d): 180 B/proxy + 8 B/pair over the summed CUDA-event time of the broadphase stages",
+               "all_stages_frac": {s_: round(frac[s_], 5) for s_ in stage_ms},
+               "note": "latency / issue bound at this size: the stages' own DRAM traffic (ncu, `traffic`) would take ~7 us at the HBM peak"}
+    if gk and gjk_ms > 0:
+        achieved = gk["thread_inst_per_step"] / (gjk_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32_issue", "kernel": "k_gjk", "achieved": achieved, "peak": issue_peak, "unit": "T thread-inst/s",
+                    "frac": achieved / issue_peak, "ms": gjk_ms, "share_of_step": gjk_ms / ms_max if ms_max > 0 else None,
+                    "thread_inst_per_launch": gk["thread_inst_per_step"], "warp_inst_per_launch": gk["warp_inst_per_step"],
+                    "lane_efficiency": round(gk["threads_per_inst"] / 32.0, 4), "threads_per_inst": gk["threads_per_inst"],
+                    "issue_active_pct_ncu": gk["issue_active_pct"], "warps_active_pct_ncu": gk["warps_active_pct"],
+                    "regs": gk["regs"], "traffic": gk["dram_bytes_per_step"],
+                    "peak_source": f"148 SMs x 4 schedulers x 32 lanes x {sm_mhz:.0f} MHz (SM clock sampled under load)",
+                    "counts_source": km.get("source"),
+                    "formula": "thread instructions executed per k_gjk launch (ncu, workload property) / live CUDA-event time of the "
+                               "launch; frac = issue-slot utilisation x lane efficiency",
+                    "hbm": hbm_obj}
+    else:
+        roofline = dict(hbm_obj)
+        roofline["dominant_stage"] = {"stage": dom, "ms": stage_ms[dom],
+                                      "bound": "fp32_issue" if dom in ("gjk_mesh", "epa_fold_count") else "hbm",
+                                      "hbm_frac": round(frac[dom], 5)}
     if wl == "c2":
         pl = "1 GPU" if ngpu == 1 else "1 replica of the world per GPU, no collective"
     elif wl == "c4":
@@ -612,16 +649,7 @@ def run_ours(args):
                         "from the pair cache, overlaps the narrowphase) + b2c_begin_contact_download (overlaps the penetration bin) "
                         "+ b2c_sync_counts + b2c_get_packed_contacts_uid (16-B uid-keyed manifold headers + 48-B solver points: world "
                         "points on A and B, normal, distance, lifetime, warm-start slot, triangle index), all into pinned host buffers"},
-        "roofline": {"bound": "hbm", "kernel": "broadphase (k_aabb .. pair rows: sort / sweep / pair ordering)",
-                     "achieved": bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms > 0 else 0.0, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": (bp_bytes / (bp_ms * 1e-3) / 1e9) / peak_gbs if bp_ms > 0 else 0.0,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bp_bytes, "ms": bp_ms,
-                     "formula": "SURVEY 8(d): 180 B/proxy + 8 B/pair over the summed CUDA-event time of the broadphase stages",
-                     "all_stages_frac": {s: round(frac[s], 5) for s in stage_ms},
-                     "dominant_stage": {"stage": dom, "ms": stage_ms[dom], "bound": "fp32_issue" if dom in ("gjk_mesh", "epa_fold_count") else "hbm",
-                                        "hbm_frac": round(frac[dom], 5),
-                                        "ncu": ncu.get(dom, "see profiles/ (issue-active %, threads per instruction)")}},
+        "roofline": roofline,
         "clocks": clocks,
     }
     out.update(extra)

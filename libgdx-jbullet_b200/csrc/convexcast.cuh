@@ -20,7 +20,8 @@
 // Same scheme as raycast.cuh: one block per sweep; (1) all threads collect the bodies whose expanded box the segment
 // meets, (2) the candidates are cast in parallel, (3) the callback's decisions are replayed.  Because the exit bound of the
 // box test is constant and every accept is a strict "fraction < closest" between objects, (3) is: the smallest fraction
-// wins, the lowest body index among equals.  Inside one object: a compound keeps the first child attaining its minimum;
+// wins, the lowest body index among equals — an order-independent reduction, so (1) and (2) alternate in rounds over a
+// fixed-size candidate list and the number of candidates a sweep may have is unbounded.  Inside one object: a compound keeps the first child attaining its minimum;
 // a mesh keeps the LAST triangle (in traversal order) attaining its minimum, since reportHit accepts "<=" — and either
 // reports that minimum m under a bound b exactly when m < b, so one record per candidate is enough.
 #pragma once
@@ -29,7 +30,12 @@
 namespace b2c {
 
 constexpr int SWEEP_THREADS = RAY_THREADS;
-constexpr int SWEEP_MAX_CAND = 1024;
+#ifndef B2C_SWEEP_MAX_CAND
+#define B2C_SWEEP_MAX_CAND 4096
+#define B2C_SWEEP_HIT_CAP 2048
+#endif
+constexpr int SWEEP_MAX_CAND = B2C_SWEEP_MAX_CAND;  // candidate list of one round (>= RAY_CHUNK)
+constexpr int SWEEP_HIT_CAP = B2C_SWEEP_HIT_CAP;    // chunk boxes examined per round = capacity of the hit-chunk list
 
 __device__ __forceinline__ AnyS anyShapeOf(const ShapeDev& cs, const float4* __restrict__ hullPts) {
     AnyS shp;
@@ -233,18 +239,35 @@ __device__ __forceinline__ void sweepMeshWalk(const MeshDev& md, const AnyS& A, 
     }
 }
 
+// One candidate's cast, folded into the thread's running best (smallest fraction, lowest body index among equals).
+struct SweepBest {
+    float fraction;
+    int body;      // -1 = none
+    SweepRec rec;
+    __device__ __forceinline__ void offer(bool valid, int i, const SweepRec& r) {
+        if (!valid) return;
+        if (r.fraction < fraction || (body >= 0 && r.fraction == fraction && i < body)) { fraction = r.fraction; body = i; rec = r; }
+    }
+};
+
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_convex_sweep(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __restrict__ hullPts, const MeshDev* __restrict__ meshes,
                const CompoundChildDev* __restrict__ children, const float4* __restrict__ sortedMin, int nSorted,
                const float4* __restrict__ cmin, const float4* __restrict__ cmax, int n, const float4* __restrict__ rmin,
                const float4* __restrict__ rmax, const int* __restrict__ castShapes, const float* __restrict__ basis9,
                const float* __restrict__ sweepFrom, const float* __restrict__ sweepTo, int numSweeps, uint32_t cbFilter,
-               float allowedPenetration, RayOut* __restrict__ out, uint32_t* __restrict__ overflow) {
-    __shared__ uint32_t sCount;
+               float allowedPenetration, RayOut* __restrict__ out, uint32_t* __restrict__ maxCandidates) {
+    // The candidate set of a sweep has no useful bound (the reference expands every body's box by the cast shape's box
+    // INCLUDING its whole linear motion), so it is produced and consumed in rounds: chunk boxes of a range of SWEEP_HIT_CAP
+    // chunks -> hit-chunk list; members of as many hit chunks as the candidate list has room for (64 each, worst case) ->
+    // candidate list; when it is full, or at the end, all threads cast its entries into their running best.
+    __shared__ uint32_t sHitCount, sCount, sTotal;
     __shared__ int sUnsupported;
+    __shared__ uint32_t sHit[SWEEP_HIT_CAP];
     __shared__ uint32_t sCand[SWEEP_MAX_CAND];
-    __shared__ SweepRec sRec[SWEEP_MAX_CAND];
-    __shared__ uint8_t sValid[SWEEP_MAX_CAND];
+    __shared__ float sBestFrac[SWEEP_THREADS];
+    __shared__ int sBestBody[SWEEP_THREADS];
+    __shared__ SweepRec sBestRec[SWEEP_THREADS];
     for (int sw = blockIdx.x; sw < numSweeps; sw += gridDim.x) {
         Xf fromT;
         for (int r = 0; r < 3; r++)
@@ -270,110 +293,140 @@ k_convex_sweep(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* 
             castMin = sub3(castMin, am);
             castMax = add3(castMax, am);
         }
+        SweepBest best;
+        best.fraction = 1.f;
+        best.body = -1;
+        best.rec.fraction = 1.f;
+        for (int d = 0; d < 3; d++) best.rec.normal[d] = best.rec.point[d] = 0.f;
         __syncthreads();
-        if (threadIdx.x == 0) { sCount = 0; sUnsupported = 0; }
-        __syncthreads();
-        // (1) candidates
-        const int nChunks = (n + RAY_CHUNK - 1) / RAY_CHUNK;
-        for (int c = threadIdx.x; c < nChunks; c += SWEEP_THREADS) {
-            const float4 cn = __ldg(cmin + c);
-            if (cn.w == 0.f) continue;
-            const float4 cx = __ldg(cmax + c);
-            if (!rayAabb(from, to, add3(mk3(cn.x, cn.y, cn.z), castMin), add3(mk3(cx.x, cx.y, cx.z), castMax), 1.f)) continue;
-            for (int m = 0; m < RAY_CHUNK; m++) {
-                const int pos = c * RAY_CHUNK + m;
-                if (pos >= n) break;
-                const int i = rayBodyAt(sortedMin, nSorted, pos);
-                if (i < 0 || i >= n) continue;
-                const float4 mn = __ldg(rmin + i);
-                if (mn.w == 0.f) continue;
-                if (!filterPass(cbFilter, B.filt[i])) continue;  // ConvexResultCallback.needsCollision (:752-756)
-                const float4 mx = __ldg(rmax + i);
-                if (rayAabb(from, to, add3(mk3(mn.x, mn.y, mn.z), castMin), add3(mk3(mx.x, mx.y, mx.z), castMax), 1.f)) {
-                    uint32_t k = atomicAdd(&sCount, 1u);
-                    if (k < SWEEP_MAX_CAND) sCand[k] = (uint32_t)i;
+        if (threadIdx.x == 0) { sCount = 0; sTotal = 0; sUnsupported = 0; }
+
+        // (2) the casts of the listed candidates, strided over the threads
+        auto flush = [&]() {
+            __syncthreads();
+            const uint32_t cnt = sCount;
+            for (uint32_t k = threadIdx.x; k < cnt; k += SWEEP_THREADS) {
+                const int i = (int)sCand[k];
+                const ShapeDev s = shapes[B.shape[i]];
+                const Xf t = loadXf(B.xf4, i);
+                bool valid = false;
+                SweepRec rec;
+                rec.fraction = 1.f;
+                rec.normal[0] = rec.normal[1] = rec.normal[2] = 0.f;
+                rec.point[0] = rec.point[1] = rec.point[2] = 0.f;
+                auto castConvex = [&](const ShapeDev& cs, const Xf& cx) {
+                    const AnyS shp = anyShapeOf(cs, hullPts);
+                    float f = 1.f;
+                    f3 nn, pt;
+                    if (gjkConvexCast(A, fromT, to, shp, cx, allowedPenetration, f, nn, pt)) {
+                        if (len2_3(nn) > 0.0001f && f < rec.fraction) {
+                            nn = nor3(nn);
+                            valid = true;
+                            rec.fraction = f;
+                            rec.normal[0] = nn.x; rec.normal[1] = nn.y; rec.normal[2] = nn.z;
+                            rec.point[0] = pt.x; rec.point[1] = pt.y; rec.point[2] = pt.z;
+                        }
+                    }
+                };
+                if (s.type == SH_BOX || s.type == SH_SPHERE || s.type == SH_HULL) {
+                    castConvex(s, t);
+                } else if (s.type == SH_COMPOUND) {
+                    for (int ch = 0; ch < s.numPoints; ch++) {
+                        const CompoundChildDev& cd = children[s.pointOffset + ch];
+                        Xf l;
+                        l.m[0][0] = cd.m[0]; l.m[0][1] = cd.m[1]; l.m[0][2] = cd.m[2];
+                        l.m[1][0] = cd.m[3]; l.m[1][1] = cd.m[4]; l.m[1][2] = cd.m[5];
+                        l.m[2][0] = cd.m[6]; l.m[2][1] = cd.m[7]; l.m[2][2] = cd.m[8];
+                        l.o = mk3(cd.o[0], cd.o[1], cd.o[2]);
+                        castConvex(shapes[cd.shape], mulXf(t, l));
+                    }
+                } else if (s.type == SH_MESH) {
+                    Xf inv;  // Transform.inverse (lm/Transform.java:101-105)
+                    for (int r = 0; r < 3; r++)
+                        for (int c = 0; c < 3; c++) inv.m[r][c] = t.m[c][r];
+                    inv.o = mulMV(inv.m, neg3(t.o));
+                    Xf rot;  // MeshRotation^-1 * ConvexToRotation, zero origin
+                    mulMM(inv.m, fromT.m, rot.m);
+                    rot.o = mk3(0.f, 0.f, 0.f);
+                    f3 boxMin, boxMax;
+                    shapeAabb(castS, rot, boxMin, boxMax);
+                    sweepMeshWalk(meshes[s.mesh], A, fromT, to, t, s.margin, xfPoint(inv, from), xfPoint(inv, to), boxMin, boxMax, valid, rec);
+                } else if (s.type == SH_PLANE) {
+                    sUnsupported = 1;
                 }
+                best.offer(valid, i, rec);
             }
-        }
-        __syncthreads();
-        uint32_t cnt = sCount;
-        if (cnt > SWEEP_MAX_CAND) {
-            if (threadIdx.x == 0) atomicMax(overflow, cnt);
-            cnt = SWEEP_MAX_CAND;
-        }
-        // (2) the casts, one candidate per thread
-        for (uint32_t k = threadIdx.x; k < cnt; k += SWEEP_THREADS) {
-            const int i = (int)sCand[k];
-            const ShapeDev s = shapes[B.shape[i]];
-            const Xf t = loadXf(B.xf4, i);
-            bool valid = false;
-            SweepRec rec;
-            rec.fraction = 1.f;
-            rec.normal[0] = rec.normal[1] = rec.normal[2] = 0.f;
-            rec.point[0] = rec.point[1] = rec.point[2] = 0.f;
-            auto castConvex = [&](const ShapeDev& cs, const Xf& cx) {
-                const AnyS shp = anyShapeOf(cs, hullPts);
-                float f = 1.f;
-                f3 nn, pt;
-                if (gjkConvexCast(A, fromT, to, shp, cx, allowedPenetration, f, nn, pt)) {
-                    if (len2_3(nn) > 0.0001f && f < rec.fraction) {
-                        nn = nor3(nn);
-                        valid = true;
-                        rec.fraction = f;
-                        rec.normal[0] = nn.x; rec.normal[1] = nn.y; rec.normal[2] = nn.z;
-                        rec.point[0] = pt.x; rec.point[1] = pt.y; rec.point[2] = pt.z;
+            __syncthreads();
+            if (threadIdx.x == 0) sCount = 0;
+            __syncthreads();
+        };
+
+        // (1) candidates, in rounds
+        const int nChunks = (n + RAY_CHUNK - 1) / RAY_CHUNK;
+        for (int c0 = 0; c0 < nChunks; c0 += SWEEP_HIT_CAP) {
+            __syncthreads();
+            if (threadIdx.x == 0) sHitCount = 0;
+            __syncthreads();
+            const int c1 = min(nChunks, c0 + SWEEP_HIT_CAP);
+            for (int c = c0 + threadIdx.x; c < c1; c += SWEEP_THREADS) {
+                const float4 cn = __ldg(cmin + c);
+                if (cn.w == 0.f) continue;
+                const float4 cx = __ldg(cmax + c);
+                if (rayAabb(from, to, add3(mk3(cn.x, cn.y, cn.z), castMin), add3(mk3(cx.x, cx.y, cx.z), castMax), 1.f))
+                    sHit[atomicAdd(&sHitCount, 1u)] = (uint32_t)c;
+            }
+            __syncthreads();
+            const uint32_t nHit = sHitCount;
+            uint32_t h = 0;
+            while (h < nHit) {
+                const uint32_t room = (SWEEP_MAX_CAND - sCount) / RAY_CHUNK;   // hit chunks whose members surely fit
+                if (room == 0) { flush(); continue; }
+                const uint32_t g = min(nHit - h, room);
+                __syncthreads();   // everyone has read sCount
+                for (uint32_t w = threadIdx.x; w < g * RAY_CHUNK; w += SWEEP_THREADS) {
+                    const int pos = (int)sHit[h + w / RAY_CHUNK] * RAY_CHUNK + (int)(w % RAY_CHUNK);
+                    if (pos >= n) continue;
+                    const int i = rayBodyAt(sortedMin, nSorted, pos);
+                    if (i < 0 || i >= n) continue;
+                    const float4 mn = __ldg(rmin + i);
+                    if (mn.w == 0.f) continue;
+                    if (!filterPass(cbFilter, B.filt[i])) continue;  // ConvexResultCallback.needsCollision (:752-756)
+                    const float4 mx = __ldg(rmax + i);
+                    if (rayAabb(from, to, add3(mk3(mn.x, mn.y, mn.z), castMin), add3(mk3(mx.x, mx.y, mx.z), castMax), 1.f)) {
+                        sCand[atomicAdd(&sCount, 1u)] = (uint32_t)i;
+                        atomicAdd(&sTotal, 1u);
                     }
                 }
-            };
-            if (s.type == SH_BOX || s.type == SH_SPHERE || s.type == SH_HULL) {
-                castConvex(s, t);
-            } else if (s.type == SH_COMPOUND) {
-                for (int ch = 0; ch < s.numPoints; ch++) {
-                    const CompoundChildDev& cd = children[s.pointOffset + ch];
-                    Xf l;
-                    l.m[0][0] = cd.m[0]; l.m[0][1] = cd.m[1]; l.m[0][2] = cd.m[2];
-                    l.m[1][0] = cd.m[3]; l.m[1][1] = cd.m[4]; l.m[1][2] = cd.m[5];
-                    l.m[2][0] = cd.m[6]; l.m[2][1] = cd.m[7]; l.m[2][2] = cd.m[8];
-                    l.o = mk3(cd.o[0], cd.o[1], cd.o[2]);
-                    castConvex(shapes[cd.shape], mulXf(t, l));
-                }
-            } else if (s.type == SH_MESH) {
-                Xf inv;  // Transform.inverse (lm/Transform.java:101-105)
-                for (int r = 0; r < 3; r++)
-                    for (int c = 0; c < 3; c++) inv.m[r][c] = t.m[c][r];
-                inv.o = mulMV(inv.m, neg3(t.o));
-                Xf rot;  // MeshRotation^-1 * ConvexToRotation, zero origin
-                mulMM(inv.m, fromT.m, rot.m);
-                rot.o = mk3(0.f, 0.f, 0.f);
-                f3 boxMin, boxMax;
-                shapeAabb(castS, rot, boxMin, boxMax);
-                sweepMeshWalk(meshes[s.mesh], A, fromT, to, t, s.margin, xfPoint(inv, from), xfPoint(inv, to), boxMin, boxMax, valid, rec);
-            } else if (s.type == SH_PLANE) {
-                sUnsupported = 1;
+                __syncthreads();
+                h += g;
             }
-            sValid[k] = valid ? 1 : 0;
-            sRec[k] = rec;
         }
-        __syncthreads();
+        flush();
+
         // (3) smallest fraction, lowest body index among equals
+        sBestFrac[threadIdx.x] = best.fraction;
+        sBestBody[threadIdx.x] = best.body;
+        sBestRec[threadIdx.x] = best.rec;
+        __syncthreads();
         if (threadIdx.x == 0) {
             float closest = 1.f;
             int hitBody = -1;
-            uint32_t bk = 0;
-            for (uint32_t k = 0; k < cnt; k++) {
-                if (!sValid[k]) continue;
-                const float f = sRec[k].fraction;
-                const int i = (int)sCand[k];
+            int bk = 0;
+            for (int k = 0; k < SWEEP_THREADS; k++) {
+                const int i = sBestBody[k];
+                if (i < 0) continue;
+                const float f = sBestFrac[k];
                 if (f < closest || (hitBody >= 0 && f == closest && i < hitBody)) { closest = f; hitBody = i; bk = k; }
             }
             RayOut o;
             o.uid = sUnsupported ? -1 : hitBody + 1;
             o.fraction = closest;
             for (int d = 0; d < 3; d++) {
-                o.normal[d] = hitBody >= 0 ? sRec[bk].normal[d] : 0.f;
-                o.point[d] = hitBody >= 0 ? sRec[bk].point[d] : 0.f;
+                o.normal[d] = hitBody >= 0 ? sBestRec[bk].normal[d] : 0.f;
+                o.point[d] = hitBody >= 0 ? sBestRec[bk].point[d] : 0.f;
             }
             out[sw] = o;
+            atomicMax(maxCandidates, sTotal);
         }
     }
 }

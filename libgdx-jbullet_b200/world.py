@@ -441,6 +441,12 @@ class GpuCollisionWorld:
         self._ck(self.L.b2c_get_stage_times(self.h, _vp(ms)))
         return {self.L.b2c_stage_name(k).decode(): float(ms[k]) for k in range(_lib.NUM_STAGES)}
 
+    def gjk_kernel_ms(self):
+        """Device time of k_gjk alone in the last profiled step (its own CUDA-event pair)."""
+        ms = C.c_float()
+        self._ck(self.L.b2c_get_gjk_kernel_time(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def stats(self):
         s = Stats()
         self._ck(self.L.b2c_get_stats(self.h, C.byref(s)))

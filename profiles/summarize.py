@@ -63,12 +63,16 @@ if __name__ == "__main__" and not (len(sys.argv) > 2 and sys.argv[2] == "--traff
     main(sys.argv[1])
 
 
-STAGE_OF = [  # kernel-name prefix -> bench.py stage (b2c_stage_name); order of launch inside one step disambiguates the sorts
-    ("k_aabb", "aabb"), ("k_bounds", "bounds_keys"), ("k_keys", "bounds_keys"), ("k_gather", "gather"), ("k_sweep", "sweep"),
-    ("k_large", "large"), ("k_row_", "sort_pairs"), ("k_pairs_unpack", "unpack_carry"), ("k_carry", "unpack_carry"),
-    ("k_pair_first", "unpack_carry"), ("k_classify", "classify_bin"), ("k_partition16", "classify_bin"), ("k_sphere_sphere", "closed_form"),
-    ("k_convex_plane", "closed_form"), ("k_gjk", "gjk_mesh"), ("k_mesh_query", "gjk_mesh"), ("k_epa", "epa_fold_count"),
-    ("k_manifold", "epa_fold_count"), ("k_mesh_manifold", "epa_fold_count"),
+STAGE_OF = [  # kernel-name prefix -> bench.py stage (b2c_stage_name); first match wins
+    ("k_aabb", "aabb"), ("k_bounds", "bounds_keys"), ("k_keys", "bounds_keys"),
+    ("k_row_offsets", "sort_proxies"), ("k_row_place", "sort_proxies"), ("k_row_order", "gather"), ("k_gather", "gather"),
+    ("k_sweep", "sweep"), ("k_large", "large"),
+    ("k_row_scan", "sort_pairs"), ("k_row_scatter", "sort_pairs"), ("k_row_sort_big", "sort_pairs"), ("k_row_rank", "sort_pairs"),
+    ("k_pairs_unpack", "unpack_carry"), ("k_carry", "unpack_carry"), ("k_pair_first", "unpack_carry"), ("k_pair_delta", "unpack_carry"),
+    ("k_clear_np", "classify_bin"), ("k_classify", "classify_bin"), ("k_partition16", "classify_bin"),
+    ("k_sphere_sphere", "closed_form"), ("k_convex_plane", "closed_form"),
+    ("k_gjk", "gjk_mesh"), ("k_mesh_query", "gjk_mesh"), ("k_epa", "epa_fold_count"),
+    ("k_manifold", "epa_fold_count"), ("k_mesh_manifold", "epa_fold_count"), ("k_compact", "epa_fold_count"), ("k_count", "epa_fold_count"),
 ]
 
 

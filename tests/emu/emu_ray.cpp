@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <vector>
 #define B2C_RAY_THREADS 1
+#define B2C_SWEEP_MAX_CAND 128   // small lists: the rounds of k_convex_sweep (several flushes per sweep) are exercised
+#define B2C_SWEEP_HIT_CAP 3
 #include "cuda_runtime.h"
 #include "../../oracle/world.h"
 #include "../../libgdx-jbullet_b200/csrc/compound.cuh"
@@ -144,7 +146,7 @@ int main(int argc, char** argv) {
         std::vector<RayOut> so(ns); uint32_t sov = 0;
         const uint32_t sFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)smask << 16);
         k_convex_sweep(B, shapes.data(), hull.data(), meshes.data(), children.data(), sortedMin.data(), nSorted, cmin.data(), cmax.data(), N, rmin.data(), rmax.data(), castShape.data(), basis.data(), sf.data(), st.data(), ns, sFilter, 0.04f, so.data(), &sov);
-        if (sov) { printf("sweep candidate overflow %u\n", sov); return 1; }
+        if (pass == 0 && sov <= 64) { printf("no sweep had more candidates (%u) than fit beside one more chunk (a mid-sweep flush)\n", sov); return 1; }
         for (int r = 0; r < ns; r++) {
             orc::Xf f, t;
             for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) f.basis.m[a][c] = t.basis.m[a][c] = basis[9 * r + 3 * a + c];

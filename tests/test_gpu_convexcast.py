@@ -80,6 +80,27 @@ def test_sweeps_after_a_step_and_with_removed_bodies(gpu_pkg):
     assert (gu > 0).sum() > 50 and not np.isin(gu, (5, 20, 33)).any()
 
 
+def test_long_sweeps_with_more_candidates_than_one_round_holds(gpu_pkg):
+    """The reference expands every body's box by the cast shape's box INCLUDING its whole motion, so a long sweep through a
+    dense scene has thousands of candidates: k_convex_sweep takes them in rounds of SWEEP_MAX_CAND (4096)."""
+    sc = scenes.bin_scene(n=9000, seed=53)
+    cast = sc.add_shape("box", (0.4, 0.4, 0.4))
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1)
+    ext = float(sc.extent)
+    rng = np.random.default_rng(12)
+    n = 12
+    f = rng.uniform(0.0, 0.15 * ext, size=(n, 3)).astype(np.float32)
+    t = rng.uniform(0.85 * ext, ext, size=(n, 3)).astype(np.float32)
+    f[:, 1] += 0.5
+    t[:, 1] = rng.uniform(0.5, 0.9 * ext, size=n)
+    basis = scenes.random_rotations(rng, n).astype(np.float32)
+    sg = np.full(n, gw.scene_shape_ids[cast], np.int32)
+    so = np.full(n, ow.scene_shape_ids[cast], np.int32)
+    gu = _compare(gw, ow, sg, so, basis, f, t, group=1, mask=1)
+    assert (gu > 0).sum() >= n - 2
+    _compare(gw, ow, sg, so, basis, t, f, group=1, mask=1)          # and back
+
+
 def test_sweep_kats(gpu_pkg):
     sc = scenes.stack_scene(n_side=1, extra=False, seed=1)      # ground box (top at y=0) + one unit box resting on it
     cast = sc.add_shape("sphere", 0.25)
@@ -130,7 +151,7 @@ def test_sweeps_against_terrain_mesh_compounds_and_the_plane_branch(gpu_pkg):
     so = np.asarray([ow.scene_shape_ids[casts[k]] for k in which], np.int32)
     gu = _compare(gw, ow, sg, so, basis, f, t, group=1, mask=-1 ^ 2)
     kinds = np.asarray([sc.shapes[sc.body_shape[u - 1]][0] for u in gu[gu > 0]])
-    assert (gu > 0).sum() > 500 and (kinds == "mesh").sum() > 150 and (kinds == "compound").sum() > 30, (len(kinds), (kinds == "mesh").sum(), (kinds == "compound").sum())
+    assert (gu > 0).sum() > 400 and (kinds == "mesh").sum() > 100 and (kinds == "compound").sum() > 30, (len(kinds), (kinds == "mesh").sum(), (kinds == "compound").sum())
     # with the plane inside the filter every sweep whose box reaches it is the unsupported branch
     gu2 = _compare(gw, ow, sg[:100], so[:100], basis[:100], f[:100], t[:100])
     assert (gu2 == -1).all()

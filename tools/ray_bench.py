@@ -37,6 +37,22 @@ def main():
             uid, frac, nrm, pt = gw.rayTestClosest(f, t)
             ms.append((time.perf_counter() - t0) * 1e3)
         out[label] = {"ms": round(min(ms), 3), "rays_per_s": round(nrays / (min(ms) * 1e-3)), "hits": int((uid > 0).sum())}
+    # CCD-like convex sweeps: every sweep moves a small sphere / box 1.5 units (a fast body's step) from a random point of the pile
+    nsw = nrays
+    cast = [gw.SphereShape(0.25), gw.BoxShape((0.3, 0.2, 0.25))]
+    ids = np.asarray([cast[k % 2] for k in range(nsw)], np.int32)
+    sf = rng.uniform(0.0, ext, size=(nsw, 3)).astype(np.float32)
+    d = rng.normal(size=(nsw, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    st = (sf + 1.5 * d).astype(np.float32)
+    basis = scenes.random_rotations(rng, nsw).astype(np.float32)
+    gw.convexSweepTestClosest(ids[:64], basis[:64], sf[:64], st[:64], 1, 1)
+    ms = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        uid, frac, nrm, pt = gw.convexSweepTestClosest(ids, basis, sf, st, 1, 1)       # dynamic bodies only
+        ms.append((time.perf_counter() - t0) * 1e3)
+    out["convex_sweeps"] = {"what": f"{nsw} translational sweeps of 1.5 units (sphere r=0.25 / box 0.3x0.2x0.25, random bases) inside the pile, callback mask 1",
+                            "ms": round(min(ms), 3), "sweeps_per_s": round(nsw / (min(ms) * 1e-3)), "hits": int((uid > 0).sum())}
     print(json.dumps(out))
 
 
