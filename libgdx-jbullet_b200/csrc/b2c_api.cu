@@ -140,13 +140,13 @@ struct b2c_ctx {
     uint8_t* dBinOf = nullptr;
     uint32_t* dBinItems = nullptr;
     uint32_t* dBinStart = nullptr;   // [17]
-    uint32_t* dBinZero = nullptr;    // hist[16] | ticket | pad | status[binTiles][16]
+    uint32_t* dBinZero = nullptr;    // hist[16] | cursor[16] of the bin partition
     uint32_t binTiles = 0;
     uint32_t* dCursors = nullptr;
     uint32_t* dSurvivors = nullptr;
     uint32_t* dSurvSorted = nullptr;   // survivors ordered by last step's iteration count
     uint8_t* dSurvKey = nullptr;
-    uint32_t* dSurvZero = nullptr;     // hist[16] | ticket | pad | status[binTiles][16]
+    uint32_t* dSurvZero = nullptr;     // hist[16] | cursor[16] of the survivor partition
     uint32_t* dSurvStart = nullptr;    // [17]
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
@@ -1130,7 +1130,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         ctx->dCtr = reinterpret_cast<StepCounters*>(ctx->dZeroBp);
         ctx->dRowOrdZero = reinterpret_cast<uint32_t*>(ctx->dZeroBp + ctrB);
         ctx->dRowZero = reinterpret_cast<uint32_t*>(ctx->dZeroBp + ctrB + ordB);
-        const size_t binB = up((32 + (size_t)ctx->binTiles * 16) * sizeof(uint32_t));
+        const size_t binB = up(32 * sizeof(uint32_t));
         ctx->zeroNpBytes = 2 * binB + 256;
         CKC(dalloc(&ctx->dZeroNp, ctx->zeroNpBytes));
         ctx->dBinZero = reinterpret_cast<uint32_t*>(ctx->dZeroNp);

@@ -562,23 +562,25 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
     if (threadIdx.x < 16 && hist[threadIdx.x]) atomicAdd(&a.binZero[threadIdx.x], hist[threadIdx.x]);
 }
 
-// k_partition16: stable partition of an index list by a 4-bit key in ONE pass: tiles are taken in ticket order, every tile
-// ranks its pairs per bin (match-any inside a warp, exclusive scan over the warps), publishes its 16 counts and resolves
-// its offsets by decoupled look-back over the preceding tiles (the scheme of radix_sort.cuh with a 4-bit digit).
-constexpr int BIN_ITEMS = 8, BIN_TILE = 256 * BIN_ITEMS, BIN_LOOKBACK = 8;
-// keys[i] < 16 for i < *nPtr; zero = (hist[16] | ticket | pad[15] | status[tiles][16]) cleared by the caller, hist filled by
-// the producer of the keys; out[...] = payload ? payload[i] : i in stable key order; startOut[0..16] = exclusive offsets.
+// k_partition16: partition of an index list by a 4-bit key in ONE pass.  The producer of the keys has already counted them
+// (hist[16]), so every bin's range is known up front and a tile only has to reserve its share of each bin: it ranks its items
+// per bin (match-any inside a warp, exclusive scan over the warps) and takes `count` consecutive slots with one atomicAdd per
+// bin.  Inside a bin the items of one tile stay together in list order; the tiles themselves land in the order their atomics
+// arrive — nothing downstream depends on the order inside a bin (every consumer works per item), only on items that were
+// neighbours in the list staying neighbours, which a 2048-item tile preserves.  (A stable version with decoupled look-back
+// over the tiles cost 17 us per call at 0.9 M items: the look-back chain, not the data, was the time.)
+constexpr int BIN_ITEMS = 8, BIN_TILE = 256 * BIN_ITEMS;
+// keys[i] < 16 for i < *nPtr; zero = (hist[16] | cursor[16] | ...) cleared by the caller, hist filled by the producer of the
+// keys; out[...] = payload ? payload[i] : i grouped by key; startOut[0..16] = exclusive offsets.
 __global__ void __launch_bounds__(256)
 k_partition16(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ nPtr, uint32_t* zero, uint32_t* __restrict__ startOut,
               const uint32_t* __restrict__ payload, uint32_t* __restrict__ out) {
     const uint32_t n = *nPtr;
     const uint32_t numTiles = (n + BIN_TILE - 1) / BIN_TILE;
     const uint32_t* hist = zero;
-    uint32_t* ticket = zero + 16;
-    uint32_t* status = zero + 32;
+    uint32_t* cursor = zero + 16;
     __shared__ uint32_t warpCnt[8][16];
     __shared__ uint32_t base[16];
-    __shared__ uint32_t sTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = (1u << lane) - 1u;
     uint32_t myStart = 0;  // threads 0..15: exclusive offset of bin threadIdx.x
@@ -589,13 +591,10 @@ k_partition16(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ nPt
         for (int j = 0; j < (int)threadIdx.x; j++) e += hist[j];
         startOut[threadIdx.x] = e;
     }
-    for (;;) {
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
         if (threadIdx.x < 128) (&warpCnt[0][0])[threadIdx.x] = 0;
         __syncthreads();
-        const uint32_t tile = sTile;
-        if (tile >= numTiles) return;
         const uint32_t tileStart = tile * BIN_TILE + warp * (BIN_ITEMS * 32) + lane;
         uint32_t bin[BIN_ITEMS], rank[BIN_ITEMS];
 #pragma unroll
@@ -627,36 +626,7 @@ k_partition16(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ nPt
                 warpCnt[w][d] = run;
                 run += c;
             }
-            uint32_t* my = status + (size_t)tile * 16 + d;
-            uint32_t excl = 0;
-            if (tile == 0) {
-                rs_store_release(my, run | RS_FLAG_INC);
-            } else {
-                rs_store_release(my, run | RS_FLAG_AGG);
-                int t = (int)tile - 1;
-                bool done = false;
-                while (!done && t >= 0) {
-                    uint32_t sv[BIN_LOOKBACK];
-#pragma unroll
-                    for (int k = 0; k < BIN_LOOKBACK; k++)
-                        sv[k] = (t - k >= 0) ? rs_load_relaxed(status + (size_t)(t - k) * 16 + d) : RS_FLAG_INC;
-                    int used = 0;
-#pragma unroll
-                    for (int k = 0; k < BIN_LOOKBACK; k++) {
-                        if (!done && used == k) {
-                            uint32_t f = sv[k] & ~RS_VAL_MASK;
-                            if (f != 0) {
-                                excl += sv[k] & RS_VAL_MASK;
-                                used = k + 1;
-                                if (f == RS_FLAG_INC) done = true;
-                            }
-                        }
-                    }
-                    t -= used;
-                }
-                rs_store_release(my, (excl + run) | RS_FLAG_INC);
-            }
-            base[d] = myStart + excl;
+            base[d] = myStart + (run ? atomicAdd(cursor + d, run) : 0u);
         }
         __syncthreads();
 #pragma unroll
