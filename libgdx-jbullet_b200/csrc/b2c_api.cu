@@ -185,6 +185,14 @@ struct b2c_ctx {
     uint32_t rowLenHint = 0;           // longest row of the last step the host has read
     bool forceRadix = false;
     bool haloExported = false, haloImported = false;
+    // peer-to-peer halo exchange (halo.cuh): this rank's inbox, the peers' inboxes as mapped here, per-step send state
+    unsigned char* dHaloInbox = nullptr;
+    size_t haloSlotBytesP2p = 0;
+    uint32_t haloCapP2p = 0, haloEpoch = 0;
+    HaloPeers haloPeers = {};
+    void* haloIpcOpened[16] = {};
+    bool haloConnected = false;
+    HaloP2pState* dHaloP2p = nullptr;
     uint32_t* dExportCount = nullptr;
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
@@ -816,6 +824,10 @@ int32_t readCounters(b2c_ctx* ctx) {
         const uint32_t up = slabUpper(ctx);
         if (ctx->localHint == 0 || nl + 1024 > up || (uint64_t)nl * 2 < up) ctx->localHint = nl ? nl : 1;
     }
+    if (c.haloOverflow == 2) {
+        ctx->err = "partitioned world: a peer never published its boundary proxies for this step (peer-to-peer halo exchange timed out)";
+        return B2C_ERR_STATE;
+    }
     if (c.haloOverflow) {
         ctx->err = "partitioned world: halo slot too small";
         return B2C_ERR_CAPACITY;
@@ -1186,6 +1198,8 @@ void b2c_destroy(b2c_ctx* ctx) {
     }
     cudaFree(ctx->dZeroBp); cudaFree(ctx->dZeroNp); cudaFree(ctx->dSlots);
     cudaFree(ctx->dNSorted); cudaFree(ctx->dNLocal); cudaFree(ctx->dOwner); cudaFree(ctx->dLocalList);
+    for (int r = 0; r < 16; r++) if (ctx->haloIpcOpened[r]) cudaIpcCloseMemHandle(ctx->haloIpcOpened[r]);
+    cudaFree(ctx->dHaloInbox); cudaFree(ctx->dHaloP2p);
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dScyz); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
@@ -2503,10 +2517,103 @@ int32_t b2c_mgpu_import_halo(b2c_ctx* ctx, const void* slots, int32_t nslots, in
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->dNLocal, 0, sizeof(uint32_t), s));
     dim3 grid(gridFor((uint32_t)cap, 256, 148), (unsigned)nslots);
-    k_halo_import<<<grid, 256, 0, s>>>(ctx->B, (const unsigned char*)slots, (uint32_t)cap, ctx->slab, ctx->dLocalList, ctx->dNLocal, ctx->dCtr);
+    k_halo_import<<<grid, 256, 0, s>>>(ctx->B, (const unsigned char*)slots, (uint32_t)cap, ctx->slab, ctx->dLocalList, ctx->dNLocal, ctx->dCtr,
+                                       haloSlotBytes((uint32_t)cap));
     if (ctx->nBodies > 0)
         k_list_owned<<<(ctx->nBodies + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, ctx->dLocalList, ctx->dNLocal);
     ctx->launches += 2;
+    CK(cudaGetLastError());
+    ctx->haloExported = false;
+    ctx->haloImported = true;
+    return B2C_OK;
+}
+
+// ---- the halo exchange as peer-to-peer stores (no collective) -------------------------------------------------------
+int32_t b2c_mgpu_p2p_init(b2c_ctx* ctx, int32_t cap, void* ipcHandleOut, void** inboxOut) {
+    if (!ctx || cap < 1) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled) { ctx->err = "the world is not partitioned"; return B2C_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < 16; r++) if (ctx->haloIpcOpened[r]) { cudaIpcCloseMemHandle(ctx->haloIpcOpened[r]); ctx->haloIpcOpened[r] = nullptr; }
+    cudaFree(ctx->dHaloInbox); ctx->dHaloInbox = nullptr;
+    ctx->haloConnected = false;
+    ctx->haloCapP2p = (uint32_t)cap;
+    ctx->haloSlotBytesP2p = (haloSlotBytes((uint32_t)cap) + 255) & ~(size_t)255;
+    const size_t bytes = 2 * (size_t)ctx->partRanks * ctx->haloSlotBytesP2p;
+    CK(cudaMalloc((void**)&ctx->dHaloInbox, bytes));   // plain cudaMalloc: the allocation is exported with cudaIpcGetMemHandle
+    CK(cudaMemset(ctx->dHaloInbox, 0, bytes));
+    if (!ctx->dHaloP2p) CK(cudaMalloc((void**)&ctx->dHaloP2p, sizeof(HaloP2pState)));
+    ctx->haloEpoch = 0;
+    if (ipcHandleOut) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->dHaloInbox));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "b2c.h documents a 64-byte handle");
+        memcpy(ipcHandleOut, &h, sizeof h);
+    }
+    if (inboxOut) *inboxOut = ctx->dHaloInbox;
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_p2p_connect(b2c_ctx* ctx, const void* ipcHandles, void* const* inboxPtrs) {
+    if (!ctx || (!ipcHandles && !inboxPtrs)) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled || !ctx->dHaloInbox) { ctx->err = "b2c_mgpu_p2p_connect before b2c_mgpu_p2p_init"; return B2C_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    const int R = ctx->partRanks, me = ctx->slab.rank;
+    for (int r = 0; r < R; r++) {
+        if (r == me) { ctx->haloPeers.inbox[r] = ctx->dHaloInbox; continue; }
+        if (inboxPtrs) { ctx->haloPeers.inbox[r] = (unsigned char*)inboxPtrs[r]; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)ipcHandles + 64 * (size_t)r, sizeof h);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("cudaIpcOpenMemHandle of a peer's halo inbox failed: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return B2C_ERR_CUDA;
+        }
+        ctx->haloIpcOpened[r] = p;
+        ctx->haloPeers.inbox[r] = (unsigned char*)p;
+    }
+    ctx->haloConnected = true;
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_p2p_export_halo(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled || !ctx->haloConnected) { ctx->err = "peer-to-peer halo exchange is not connected"; return B2C_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    ctx->launches = 0;
+    ctx->aabbPending = true;
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    mark(ctx, 0);
+    int32_t rc = runAabbKernel(ctx, true);  // clears the step counters, k_aabb over the owned proxies
+    if (rc) return rc;
+    ctx->haloEpoch++;
+    CK(cudaMemsetAsync(ctx->dHaloP2p, 0, sizeof(HaloP2pState), s));
+    const int nb = ctx->nBodies > 0 ? ctx->nBodies : 1;   // at least one block: the headers must be published
+    k_halo_export_p2p<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, ctx->haloPeers, ctx->partRanks,
+                                                      ctx->haloSlotBytesP2p, ctx->haloCapP2p, ctx->haloEpoch, ctx->dHaloP2p, ctx->dCtr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->haloExported = true;
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_p2p_import_halo(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled || !ctx->haloConnected) { ctx->err = "peer-to-peer halo exchange is not connected"; return B2C_ERR_STATE; }
+    if (!ctx->haloExported) { ctx->err = "b2c_mgpu_p2p_import_halo before b2c_mgpu_p2p_export_halo"; return B2C_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const unsigned char* slots = ctx->dHaloInbox + (size_t)(ctx->haloEpoch & 1u) * (size_t)ctx->partRanks * ctx->haloSlotBytesP2p;
+    CK(cudaMemsetAsync(ctx->dNLocal, 0, sizeof(uint32_t), s));
+    k_halo_wait<<<1, 32, 0, s>>>(slots, ctx->partRanks, ctx->slab.rank, ctx->haloSlotBytesP2p, ctx->haloEpoch, ctx->dCtr);
+    dim3 grid(gridFor(ctx->haloCapP2p, 256, 148), (unsigned)ctx->partRanks);
+    k_halo_import<<<grid, 256, 0, s>>>(ctx->B, slots, ctx->haloCapP2p, ctx->slab, ctx->dLocalList, ctx->dNLocal, ctx->dCtr, ctx->haloSlotBytesP2p);
+    if (ctx->nBodies > 0)
+        k_list_owned<<<(ctx->nBodies + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, ctx->dLocalList, ctx->dNLocal);
+    ctx->launches += 3;
     CK(cudaGetLastError());
     ctx->haloExported = false;
     ctx->haloImported = true;

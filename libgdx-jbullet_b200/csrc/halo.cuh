@@ -76,14 +76,111 @@ k_halo_export(BodyArrays B, int n, const uint8_t* __restrict__ owner, SlabFilter
     }
 }
 
+// ---- the same exchange without a collective: stores into the peers' memory over NVLink -------------------------------
+// Each rank owns an INBOX = 2 parities x nranks slots of the layout above; slot [parity][src] is written only by rank `src`.
+// k_halo_export_p2p sends every boundary record straight into slot [epoch & 1][me] of exactly the ranks whose slab the box
+// reaches (peer pointers from cudaIpcOpenMemHandle, or plain pointers when the "ranks" share a process), so a rank
+// receives only what touches it and nothing is padded to a slot size.  When the last block is done it publishes
+// {count, epoch} in each destination's slot header with one 64-bit release store at system scope; k_halo_wait on the
+// receiving side spins (acquire, system scope) until every source's header carries this step's epoch.  Two parities are
+// enough: a rank can run at most one step ahead of a neighbour, because its next export comes after its own import,
+// which waits for that neighbour's export of the current step.
+struct HaloPeers {
+    unsigned char* inbox[16];   // base of rank r's inbox in THIS process's address space
+};
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct HaloP2pState {
+    uint32_t sendCount[16];   // records sent to each destination this step
+    uint32_t ticket;          // blocks finished
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(256)
+k_halo_export_p2p(BodyArrays B, int n, const uint8_t* __restrict__ owner, SlabFilter slab, HaloPeers peers, int nranks, size_t slotBytes,
+                  uint32_t cap, uint32_t epoch, HaloP2pState* st, StepCounters* ctr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int lo = 1, hi = 0;   // destination regions [lo, hi] (empty: nothing to send)
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    uint8_t flags = 0;
+    if (i < n && owner[i] == (uint8_t)slab.rank) {
+        flags = B.flags[i];
+        if (flags & BF_ALIVE) {
+            a = B.effMin[i];
+            b = B.effMax[i];
+            lo = slab.region(axisOf(a, slab.axis));
+            hi = slab.region(axisOf(b, slab.axis));
+        }
+    }
+    const size_t mySlot = ((size_t)(epoch & 1u) * (size_t)nranks + (size_t)slab.rank) * slotBytes;
+    for (int d = 0; d < nranks; d++) {   // warp-uniform loop: one atomic per destination per warp
+        const bool want = d != slab.rank && lo <= d && d <= hi;
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (m == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&st->sendCount[d], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (want) {
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) {
+                HaloRecord* r = reinterpret_cast<HaloRecord*>(peers.inbox[d] + mySlot + HALO_HEADER_BYTES) + pos;
+                float4 a2 = a, b2 = b;
+                a2.w = __uint_as_float((uint32_t)i);
+                b2.w = __uint_as_float((uint32_t)flags);
+                r->mn = a2;
+                r->mx = b2;
+                r->xf[0] = B.xf4[3 * (size_t)i];
+                r->xf[1] = B.xf4[3 * (size_t)i + 1];
+                r->xf[2] = B.xf4[3 * (size_t)i + 2];
+            } else {
+                ctr->haloOverflow = 1;
+            }
+        }
+    }
+    // publish: every block's stores are fenced at system scope before it takes a ticket; the last block writes the headers
+    __threadfence_system();
+    __syncthreads();
+    __shared__ uint32_t sLast;
+    if (threadIdx.x == 0) sLast = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (sLast && threadIdx.x < (unsigned)nranks && (int)threadIdx.x != slab.rank) {
+        __threadfence_system();
+        const int d = threadIdx.x;
+        uint32_t c = *(volatile uint32_t*)&st->sendCount[d];
+        if (c > cap) c = cap;
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(peers.inbox[d] + mySlot), (unsigned long long)c | ((unsigned long long)epoch << 32));
+    }
+}
+
+// One warp: lane s waits until source s has published this step's epoch in its slot of this rank's inbox.
+__global__ void __launch_bounds__(32)
+k_halo_wait(const unsigned char* __restrict__ inboxParity, int nranks, int rank, size_t slotBytes, uint32_t epoch, StepCounters* ctr) {
+    const int s = threadIdx.x;
+    if (s >= nranks || s == rank) return;
+    const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(inboxParity + (size_t)s * slotBytes);
+    const long long t0 = clock64();
+    while ((uint32_t)(ld_acquire_sys_u64(hdr) >> 32) != epoch) {
+        if (clock64() - t0 > 6000000000ll) { ctr->haloOverflow = 2; break; }   // ~3 s: a peer died; reported by the host as an error
+        __nanosleep(200);
+    }
+}
+
 // Every record of the other ranks' slots that touches this rank's region becomes a local (halo) proxy: its box, transform
 // and flags are written into the rank's proxy arrays and its index is appended to the local list.
 __global__ void __launch_bounds__(256)
 k_halo_import(BodyArrays B, const unsigned char* __restrict__ slots, uint32_t cap, SlabFilter slab, uint32_t* __restrict__ list,
-              uint32_t* __restrict__ nLocal, StepCounters* ctr) {
+              uint32_t* __restrict__ nLocal, StepCounters* ctr, size_t slotStride) {
     const int src = blockIdx.y;
     if (src == slab.rank) return;  // own slot: those proxies are listed by k_list_owned
-    const unsigned char* slot = slots + (size_t)src * haloSlotBytes(cap);
+    const unsigned char* slot = slots + (size_t)src * slotStride;
     uint32_t cnt = *reinterpret_cast<const uint32_t*>(slot);
     if (cnt > cap) { if (threadIdx.x == 0 && blockIdx.x == 0) ctr->haloOverflow = 1; cnt = cap; }
     const HaloRecord* recs = reinterpret_cast<const HaloRecord*>(slot + HALO_HEADER_BYTES);

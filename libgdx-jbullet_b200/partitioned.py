@@ -19,13 +19,14 @@ def default_halo_cap(n_bodies):
 class PartitionedStepper:
     """Sequences one partitioned step (include/b2c.h, last section):
         updateAabbs of the owned proxies + boundary proxies into this rank's halo slot
-        -> ONE all-gather of the halo slots (boundary AABBs + transforms, NVLink)
+        -> the boundary records reach the ranks whose slab they touch: by peer-to-peer stores fused into the export kernel
+           (halo="p2p", default when every rank can map every inbox) or by ONE all-gather of fixed-size halo slots
         -> adoption of the records that touch this rank's slab, pair calculation over the local list
         -> manifolds of pairs that changed owner into a small migration slot -> ONE all-gather -> adoption
         -> narrowphase on the pairs this rank owns.
     planes = None lets the library cut the world at equal-count quantiles along its longest axis."""
 
-    def __init__(self, gw, rank, nranks, dist, torch, dev, migrate_cap=2048, halo_cap=None, axis=None, planes=None):
+    def __init__(self, gw, rank, nranks, dist, torch, dev, migrate_cap=2048, halo_cap=None, axis=None, planes=None, halo="p2p"):
         self.gw, self.rank, self.nranks, self.dist, self.torch = gw, rank, nranks, dist, torch
         self.stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
         self.mcap = int(migrate_cap)
@@ -42,6 +43,35 @@ class PartitionedStepper:
         self.my_halo = torch.zeros(self.halo_bytes, dtype=torch.uint8, device=d)
         self.all_halo = torch.zeros(self.halo_bytes * nranks, dtype=torch.uint8, device=d)
         self.extra_launches = 0   # every kernel of a partitioned step is counted by the library (b2c_stats.kernel_launches)
+        # halo exchange: peer-to-peer stores fused into the export kernel when every rank can map every inbox (CUDA IPC,
+        # one node), else the all-gather.  B2C_HALO=nccl forces the collective (A/B measurements).
+        import os
+        self.halo_mode = "nccl"
+        if halo == "p2p" and os.environ.get("B2C_HALO", "p2p") != "nccl":
+            self.halo_mode = self._connect_p2p(d)
+
+    def _connect_p2p(self, d):
+        """Every rank publishes the IPC handle of its inbox (one small all-gather at set-up), maps the others', and all ranks
+        agree (all-reduce of a success flag) on whether the peer-to-peer path is usable."""
+        torch, gw = self.torch, self.gw
+        ok = 1
+        try:
+            handle, _ptr = gw.mgpu_p2p_init(self.hcap)
+            if self.dist is not None and self.nranks > 1:
+                mine = torch.tensor(list(handle), dtype=torch.uint8, device=d)
+                allh = torch.zeros(64 * self.nranks, dtype=torch.uint8, device=d)
+                self.dist.all_gather_into_tensor(allh, mine)
+                gw.mgpu_p2p_connect(ipc_handles=bytes(allh.cpu().numpy().tobytes()))
+            else:
+                gw.mgpu_p2p_connect(inbox_ptrs=[_ptr] * self.nranks)
+        except Exception as e:  # noqa: BLE001 — any failure means "use the collective", decided by all ranks together
+            self.p2p_error = repr(e)
+            ok = 0
+        if self.dist is not None and self.nranks > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device=d)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        return "p2p" if ok else "nccl"
 
     def all_gather(self, out, inp):
         """One NCCL all-gather on the world's stream; with a single rank it is a copy."""
@@ -54,9 +84,13 @@ class PartitionedStepper:
 
     def step(self):
         gw = self.gw
-        gw.mgpu_update_export_halo(self.my_halo.data_ptr(), self.hcap)
-        self.all_gather(self.all_halo, self.my_halo)
-        gw.mgpu_import_halo(self.all_halo.data_ptr(), self.nranks, self.hcap)
+        if self.halo_mode == "p2p":
+            gw.mgpu_p2p_export_halo()      # k_aabb + boundary records stored straight into the neighbours' inboxes
+            gw.mgpu_p2p_import_halo()      # wait for every source's epoch, adopt
+        else:
+            gw.mgpu_update_export_halo(self.my_halo.data_ptr(), self.hcap)
+            self.all_gather(self.all_halo, self.my_halo)
+            gw.mgpu_import_halo(self.all_halo.data_ptr(), self.nranks, self.hcap)
         gw.mgpu_broadphase()
         gw.mgpu_export_departed_slot(self.my_slot.data_ptr(), self.mcap)
         self.all_gather(self.all_slots, self.my_slot)
@@ -75,6 +109,8 @@ class PartitionedStepper:
         mig = self.all_slots.view(torch.int32)[:: self.slot_bytes // 4][: self.nranks]
         hmax, mmax = int(halo.max().item()), int(mig.max().item())
         hcap = max(min_halo, int(hmax * headroom) + 64)
+        if self.halo_mode == "p2p":
+            hcap = self.hcap          # the peer-to-peer path sends records, not slots: its inbox capacity costs nothing per step
         mcap = max(min_migrate, int(mmax * headroom) + 64)
         if hcap >= self.hcap and mcap >= self.mcap:
             return self.hcap, self.mcap
@@ -89,6 +125,12 @@ class PartitionedStepper:
         return self.hcap, self.mcap
 
     def describe(self):
+        if self.halo_mode == "p2p":
+            return (f"slab partition; halo exchange = peer-to-peer stores over NVLink fused into the export kernel (80-byte "
+                    f"boundary-proxy records written straight into the inboxes of the slabs they reach, release/acquire epoch "
+                    f"flags, no collective; inbox capacity {self.hcap} records per source); 1 ncclAllGather per step for the "
+                    f"manifold-migration slots ({self.mcap} manifolds = {self.slot_bytes} B per rank, "
+                    f"{self.slot_bytes * self.nranks} B gathered)")
         return (f"slab partition, 2 ncclAllGather per step: halo slots ({self.hcap} x 80-byte boundary-proxy records = "
                 f"{self.halo_bytes} B per rank, {self.halo_bytes * self.nranks} B gathered) and manifold-migration slots "
                 f"({self.mcap} manifolds = {self.slot_bytes} B per rank, {self.slot_bytes * self.nranks} B gathered)")

@@ -310,6 +310,29 @@ class GpuCollisionWorld:
     def mgpu_import_halo(self, slots_ptr, nslots, cap):
         self._ck(self.L.b2c_mgpu_import_halo(self.h, C.c_void_p(slots_ptr), nslots, cap))
 
+    def mgpu_p2p_init(self, cap):
+        """Allocate this rank's halo inbox for the peer-to-peer exchange: (64-byte CUDA IPC handle, device pointer)."""
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        self._ck(self.L.b2c_mgpu_p2p_init(self.h, int(cap), handle, C.byref(ptr)))
+        return bytes(handle), int(ptr.value)
+
+    def mgpu_p2p_connect(self, ipc_handles=None, inbox_ptrs=None):
+        """Map the peers' inboxes: ipc_handles = nranks x 64 bytes in rank order (other processes), or inbox_ptrs = nranks
+        device pointers (ranks in this process)."""
+        if inbox_ptrs is not None:
+            arr = (C.c_void_p * len(inbox_ptrs))(*[C.c_void_p(int(p)) for p in inbox_ptrs])
+            self._ck(self.L.b2c_mgpu_p2p_connect(self.h, None, arr))
+        else:
+            buf = (C.c_ubyte * len(ipc_handles)).from_buffer_copy(bytes(ipc_handles))
+            self._ck(self.L.b2c_mgpu_p2p_connect(self.h, buf, None))
+
+    def mgpu_p2p_export_halo(self):
+        self._ck(self.L.b2c_mgpu_p2p_export_halo(self.h))
+
+    def mgpu_p2p_import_halo(self):
+        self._ck(self.L.b2c_mgpu_p2p_import_halo(self.h))
+
     def mgpu_broadphase(self):
         self._ck(self.L.b2c_mgpu_broadphase(self.h))
 

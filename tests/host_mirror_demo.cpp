@@ -128,6 +128,15 @@ int main() {
         int islands = world.computeIslands(tags);
         std::printf("deltas +%d -%d islands %d tags %d %d %d %d\n", (int)added.size(), (int)removed.size(), islands, tags[0], tags[1], tags[2],
                     tags[3]);
+        // the queries a character controller issues: one ray and one convex sweep (a small sphere) straight down onto the stack
+        int32_t probe = world.SphereShape(0.25f);
+        const float from[3] = {0.f, 10.f, 0.f}, to[3] = {0.f, -10.f, 0.f}, basis[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        int32_t ruid = 0, suid = 0;
+        float rfrac = 0.f, sfrac = 0.f, rn[3], rp[3], sn[3], sp[3];
+        world.rayTestClosest(1, from, to, &ruid, &rfrac, rn, rp);
+        world.convexSweepTestClosest(1, &probe, basis, from, to, &suid, &sfrac, sn, sp);
+        std::printf("ray uid %d y %.2f | sweep uid %d fraction %.3f normal %.2f %.2f %.2f\n", ruid, (double)rp[1], suid, (double)sfrac,
+                    (double)sn[0], (double)sn[1], (double)sn[2]);
     }
     return sequences();
 }

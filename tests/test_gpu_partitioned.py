@@ -13,7 +13,7 @@ import scenes
 pytestmark = pytest.mark.gpu
 
 
-def run_partitioned(pkg, sc, R, steps, mode=1, slots=False, axis=None, planes=None, halo_cap=None, stats=None):
+def run_partitioned(pkg, sc, R, steps, mode=1, slots=False, axis=None, planes=None, halo_cap=None, stats=None, p2p=False):
     import torch
     single = scenes.build_gpu(pkg, sc, mode=mode)
     ranks = [scenes.build_gpu(pkg, sc, mode=mode) for _ in range(R)]
@@ -23,6 +23,11 @@ def run_partitioned(pkg, sc, R, steps, mode=1, slots=False, axis=None, planes=No
         else:
             w.set_partition_slabs(r, R, axis, planes)
     hcap = halo_cap or max(4096, sc.n)
+    if p2p:
+        # the halo exchange as peer-to-peer stores: every "rank" maps the others' inboxes by plain device pointer
+        inboxes = [w.mgpu_p2p_init(hcap)[1] for w in ranks]
+        for w in ranks:
+            w.mgpu_p2p_connect(inbox_ptrs=inboxes)
     hbytes = single.mgpu_halo_slot_bytes(hcap)
     allhalo = torch.zeros(hbytes * R, dtype=torch.uint8, device="cuda")
     halo_total = 0
@@ -40,11 +45,18 @@ def run_partitioned(pkg, sc, R, steps, mode=1, slots=False, axis=None, planes=No
         # every owner updates its proxies and publishes the boundary ones; "all-gather" = all slots in one buffer
         for r, w in enumerate(ranks):
             w.setWorldTransforms(xf)
-            w.mgpu_update_export_halo(allhalo.data_ptr() + r * hbytes, hcap)
+            if p2p:
+                w.mgpu_p2p_export_halo()          # all exports are enqueued before any import starts to wait
+            else:
+                w.mgpu_update_export_halo(allhalo.data_ptr() + r * hbytes, hcap)
         torch.cuda.synchronize()
-        halo_total += int(sum(int(allhalo[r * hbytes:r * hbytes + 4].view(torch.int32)[0]) for r in range(R)))
+        if not p2p:
+            halo_total += int(sum(int(allhalo[r * hbytes:r * hbytes + 4].view(torch.int32)[0]) for r in range(R)))
         for w in ranks:
-            w.mgpu_import_halo(allhalo.data_ptr(), R, hcap)
+            if p2p:
+                w.mgpu_p2p_import_halo()
+            else:
+                w.mgpu_import_halo(allhalo.data_ptr(), R, hcap)
             w.mgpu_broadphase()
         if slots:
             # sync-free variant: every rank packs its slot straight into the "gathered" buffer, then all ranks scan it
@@ -108,6 +120,26 @@ def test_partitioned_bin_world_with_large_statics(gpu_pkg):
     sc = scenes.bin_scene(n=4000, seed=13)
     sc.vel *= 3.0
     run_partitioned(gpu_pkg, sc, R=3, steps=5)
+
+
+def test_partitioned_world_with_peer_to_peer_halo(gpu_pkg):
+    """The halo exchange fused into the export kernel (stores into the peers' inboxes, epoch flags) gives the same union as
+    the all-gather path: spheres world over 4 ranks with migration, and the bin with its large statics over 3."""
+    sc = scenes.spheres_scene(n=20000, seed=23)
+    sc.vel *= 6.0
+    moved = run_partitioned(gpu_pkg, sc, R=4, steps=5, slots=True, p2p=True)
+    assert moved > 0
+    sc = scenes.bin_scene(n=4000, seed=29)
+    sc.vel *= 3.0
+    run_partitioned(gpu_pkg, sc, R=3, steps=4, slots=True, p2p=True)
+
+
+def test_peer_to_peer_halo_needs_a_connection(gpu_pkg):
+    sc = scenes.spheres_scene(n=500, seed=3)
+    w = scenes.build_gpu(gpu_pkg, sc, mode=1)
+    w.set_partition(0, 2)
+    with pytest.raises(Exception, match="not connected"):
+        w.mgpu_p2p_export_halo()
 
 
 def test_slab_ownership_and_halo_size(gpu_pkg):

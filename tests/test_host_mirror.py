@@ -35,6 +35,9 @@ def test_host_mirror_runs_reference_call_sequence(gpu_pkg):
     assert "contacts 1 normal 0.000 -1.000 0.000" in lines[4]
     # first step: all three pairs are new; the three stacked boxes form one island (tag = smallest body index), ground is static
     assert lines[5] == "deltas +3 -0 islands 1 tags -1 1 1 1"
+    # ray and convex sweep straight down onto the stack (top of the third box at y = 6): both hit body 4; the sphere of radius
+    # 0.25 touches after (10 - 6.25) / 20 of the way
+    assert lines[6].startswith("ray uid 4 y 6.00 | sweep uid 4 fraction 0.18") and lines[6].endswith("normal 0.00 1.00 0.00"), lines[6]
     # the drop-in sequence and the fast path, stepped side by side over a drifting scene, tell the same
     # story (pair list == mirror maintained from the deltas, same touching manifolds, bit-identical contact points)
     steps = [l for l in lines if l.startswith("step ")]
