@@ -373,7 +373,8 @@ def measure(rig, wl, sc, steps, warmup, e2e_steps, want_stages, partitioned=Fals
         one_step()
         gw.sync_counts()
         step_no += 1
-    if mg is not None:
+    if mg is not None and mg.halo_mode != "p2p":
+        # (all-gather path only: the peer-to-peer path sends records, not fixed-size slots)
         # one full pass over the trace with the worst-case slots, then size them to what this world sends (+50 %)
         seen_h = seen_m = 0
         for _ in range(2 * (FRAMES - 1)):

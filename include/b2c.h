@@ -374,7 +374,8 @@ int32_t b2c_convex_sweep_closest(b2c_ctx*, int32_t n, const int32_t* cast_shape_
  *   b2c_mgpu_update_export_halo -> [all-gather halo slots] -> b2c_mgpu_import_halo -> b2c_mgpu_broadphase ->
  *   b2c_mgpu_export_departed_slot -> [all-gather migration slots] -> b2c_mgpu_import_arrival_slots -> b2c_mgpu_narrowphase.
  * (or, with the halo exchange as peer-to-peer stores — no collective, see b2c_mgpu_p2p_*:
- *   b2c_mgpu_p2p_export_halo -> b2c_mgpu_p2p_import_halo -> b2c_mgpu_broadphase -> ... as above)
+ *   b2c_mgpu_p2p_export_halo -> b2c_mgpu_p2p_import_halo -> b2c_mgpu_broadphase ->
+ *   b2c_mgpu_p2p_export_departed -> b2c_mgpu_p2p_import_arrivals -> b2c_mgpu_narrowphase)
  * Every call only enqueues on the ctx stream (no host synchronisation); overflowing slots are reported by the next
  * b2c_sync_counts as B2C_ERR_CAPACITY.  All ranks create the same proxies in the same order (static attributes are
  * replicated); per-step transforms are only needed for the proxies a rank owns (b2c_get_partition tells which).
@@ -398,18 +399,24 @@ int32_t b2c_mgpu_import_halo(b2c_ctx*, const void* slots_dev, int32_t nslots, in
  * the box reaches (peer memory over NVLink / NVSwitch), then publishes {count, epoch} per destination with one release store
  * at system scope; the import waits (acquire, system scope) for this step's epoch from every source and adopts the records.
  * A rank receives only what touches it and nothing is padded to a slot size; no NCCL call sits between the two kernels.
- *   b2c_mgpu_p2p_init    allocates this rank's inbox for `cap` records per source; returns its 64-byte CUDA IPC handle
- *                        (cudaIpcMemHandle_t) and / or its device pointer (either output may be NULL)
+ *   b2c_mgpu_p2p_init    allocates this rank's inboxes (halo: `cap` records per source; manifold migration: `migrate_cap`
+ *                        manifolds per source; all ranks must pass the same capacities) in ONE allocation; returns its 64-byte
+ *                        CUDA IPC handle (cudaIpcMemHandle_t) and / or its device pointer (either output may be NULL)
  *   b2c_mgpu_p2p_connect maps the peers' inboxes: ipc_handles = nranks x 64 bytes in rank order (ranks in other processes on
  *                        the same node; exchange them once, e.g. with an all-gather), or inbox_ptrs = nranks device pointers
  *                        (ranks that share this process).  The own entry is ignored.
  *   b2c_mgpu_p2p_export_halo = updateAabbs of the owned proxies + the stores into the peers (replaces update_export_halo +
  *                        the all-gather);  b2c_mgpu_p2p_import_halo = wait + adoption (replaces import_halo).
+ *   b2c_mgpu_p2p_export_departed / b2c_mgpu_p2p_import_arrivals: the manifolds of pairs that changed owner, pushed to every
+ *                        other rank the same way (replace export_departed_slot + all-gather + import_arrival_slots).
+ * With both, a partitioned step contains no collective at all — only this library's kernels over peer memory.
  * A source that never publishes (a dead peer) ends the wait after ~3 s; b2c_sync_counts then returns B2C_ERR_STATE. */
-int32_t b2c_mgpu_p2p_init(b2c_ctx*, int32_t cap, void* ipc_handle_out /* 64 bytes */, void** inbox_dev_out);
+int32_t b2c_mgpu_p2p_init(b2c_ctx*, int32_t cap, int32_t migrate_cap, void* ipc_handle_out /* 64 bytes */, void** inbox_dev_out);
 int32_t b2c_mgpu_p2p_connect(b2c_ctx*, const void* ipc_handles, void* const* inbox_ptrs);
 int32_t b2c_mgpu_p2p_export_halo(b2c_ctx*);
 int32_t b2c_mgpu_p2p_import_halo(b2c_ctx*);
+int32_t b2c_mgpu_p2p_export_departed(b2c_ctx*);
+int32_t b2c_mgpu_p2p_import_arrivals(b2c_ctx*);
 /* BroadphaseInterface.calculateOverlappingPairs over the rank's local list; keeps the pairs this rank owns. */
 int32_t b2c_mgpu_broadphase(b2c_ctx*);
 /* Manifold migration with a host round trip (tests): keys: uint64[cap]; headers: 32-byte records [cap]; points:

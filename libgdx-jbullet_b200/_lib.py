@@ -68,7 +68,7 @@ EXPORTS = [
     "b2c_calculate_overlapping_pairs", "b2c_get_pairs", "b2c_dispatch_all_pairs", "b2c_step", "b2c_get_manifolds",
     "b2c_get_raw_contacts", "b2c_get_aabbs", "b2c_get_broadphase_aabb", "b2c_get_stats", "b2c_stream",
     "b2c_device_transforms", "b2c_transforms_written", "b2c_step_device", "b2c_sync_counts", "b2c_get_contacts",
-    "b2c_set_profiling", "b2c_get_stage_times", "b2c_get_gjk_kernel_time", "b2c_mgpu_p2p_init", "b2c_mgpu_p2p_connect", "b2c_mgpu_p2p_export_halo", "b2c_mgpu_p2p_import_halo", "b2c_stage_name", "b2c_set_transforms_device", "b2c_set_partition", "b2c_mgpu_broadphase", "b2c_mgpu_export_departed",
+    "b2c_set_profiling", "b2c_get_stage_times", "b2c_get_gjk_kernel_time", "b2c_mgpu_p2p_init", "b2c_mgpu_p2p_connect", "b2c_mgpu_p2p_export_halo", "b2c_mgpu_p2p_import_halo", "b2c_mgpu_p2p_export_departed", "b2c_mgpu_p2p_import_arrivals", "b2c_stage_name", "b2c_set_transforms_device", "b2c_set_partition", "b2c_mgpu_broadphase", "b2c_mgpu_export_departed",
     "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase", "b2c_mgpu_slot_bytes", "b2c_mgpu_export_departed_slot",
     "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest", "b2c_convex_sweep_closest",
     "b2c_shape_register_compound", "b2c_get_packed_contacts", "b2c_set_contact_prefetch", "b2c_begin_contact_download",
@@ -181,7 +181,9 @@ def load():
     L.b2c_set_profiling.argtypes = [vp, i32]
     L.b2c_get_stage_times.argtypes = [vp, vp]
     L.b2c_get_gjk_kernel_time.argtypes = [vp, vp]
-    L.b2c_mgpu_p2p_init.argtypes = [vp, i32, vp, vp]
+    L.b2c_mgpu_p2p_init.argtypes = [vp, i32, i32, vp, vp]
+    L.b2c_mgpu_p2p_export_departed.argtypes = [vp]
+    L.b2c_mgpu_p2p_import_arrivals.argtypes = [vp]
     L.b2c_mgpu_p2p_connect.argtypes = [vp, vp, vp]
     L.b2c_mgpu_p2p_export_halo.argtypes = [vp]
     L.b2c_mgpu_p2p_import_halo.argtypes = [vp]

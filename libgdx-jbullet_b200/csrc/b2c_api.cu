@@ -193,6 +193,14 @@ struct b2c_ctx {
     void* haloIpcOpened[16] = {};
     bool haloConnected = false;
     HaloP2pState* dHaloP2p = nullptr;
+    HaloRecord* dHaloStage = nullptr;   // two-phase variant: per-destination runs of records before the push
+    unsigned char* dMigInbox = nullptr; // migration inbox (same allocation as the halo inbox, behind it)
+    unsigned char* dMigLocal = nullptr; // this rank's departed-manifold slot before the push
+    HaloPeers migPeers = {};
+    size_t migSlotBytes = 0, haloInboxBytes = 0;
+    uint32_t migCap = 0;
+    bool migExported = false;
+    bool haloTwoPhase = true;
     uint32_t* dExportCount = nullptr;
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
@@ -1199,7 +1207,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dZeroBp); cudaFree(ctx->dZeroNp); cudaFree(ctx->dSlots);
     cudaFree(ctx->dNSorted); cudaFree(ctx->dNLocal); cudaFree(ctx->dOwner); cudaFree(ctx->dLocalList);
     for (int r = 0; r < 16; r++) if (ctx->haloIpcOpened[r]) cudaIpcCloseMemHandle(ctx->haloIpcOpened[r]);
-    cudaFree(ctx->dHaloInbox); cudaFree(ctx->dHaloP2p);
+    cudaFree(ctx->dHaloInbox); cudaFree(ctx->dHaloP2p); cudaFree(ctx->dHaloStage); cudaFree(ctx->dMigLocal);
     cudaFree(ctx->dSide); cudaFree(ctx->dSmin); cudaFree(ctx->dSmax); cudaFree(ctx->dSrow); cudaFree(ctx->dScyz); cudaFree(ctx->dRowStart);
     cudaFree(ctx->dGrid); cudaFreeHost(ctx->hCtrPinned);
     ctx->sortBodies.destroy();
@@ -2529,19 +2537,28 @@ int32_t b2c_mgpu_import_halo(b2c_ctx* ctx, const void* slots, int32_t nslots, in
 }
 
 // ---- the halo exchange as peer-to-peer stores (no collective) -------------------------------------------------------
-int32_t b2c_mgpu_p2p_init(b2c_ctx* ctx, int32_t cap, void* ipcHandleOut, void** inboxOut) {
-    if (!ctx || cap < 1) return B2C_ERR_BAD_ARG;
+int32_t b2c_mgpu_p2p_init(b2c_ctx* ctx, int32_t cap, int32_t migrateCap, void* ipcHandleOut, void** inboxOut) {
+    if (!ctx || cap < 1 || migrateCap < 1) return B2C_ERR_BAD_ARG;
     if (!ctx->slab.enabled) { ctx->err = "the world is not partitioned"; return B2C_ERR_STATE; }
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < 16; r++) if (ctx->haloIpcOpened[r]) { cudaIpcCloseMemHandle(ctx->haloIpcOpened[r]); ctx->haloIpcOpened[r] = nullptr; }
     cudaFree(ctx->dHaloInbox); ctx->dHaloInbox = nullptr;
+    cudaFree(ctx->dHaloStage); ctx->dHaloStage = nullptr;
+    cudaFree(ctx->dMigLocal); ctx->dMigLocal = nullptr;
+    { const char* e = getenv("B2C_HALO_PUSH"); ctx->haloTwoPhase = !(e && e[0] == '0'); }   // 0 = the single fused kernel (A/B)
     ctx->haloConnected = false;
     ctx->haloCapP2p = (uint32_t)cap;
     ctx->haloSlotBytesP2p = (haloSlotBytes((uint32_t)cap) + 255) & ~(size_t)255;
-    const size_t bytes = 2 * (size_t)ctx->partRanks * ctx->haloSlotBytesP2p;
-    CK(cudaMalloc((void**)&ctx->dHaloInbox, bytes));   // plain cudaMalloc: the allocation is exported with cudaIpcGetMemHandle
-    CK(cudaMemset(ctx->dHaloInbox, 0, bytes));
+    ctx->migCap = (uint32_t)migrateCap;
+    ctx->migSlotBytes = mgpuSlotBytes((uint32_t)migrateCap);   // the stride k_import_arrival_slots assumes
+    ctx->haloInboxBytes = 2 * (size_t)ctx->partRanks * ctx->haloSlotBytesP2p;
+    const size_t migBytes = 2 * (size_t)ctx->partRanks * ctx->migSlotBytes;
+    // ONE plain cudaMalloc for both inboxes: the allocation is exported with a single cudaIpcGetMemHandle
+    CK(cudaMalloc((void**)&ctx->dHaloInbox, ctx->haloInboxBytes + migBytes));
+    CK(cudaMemset(ctx->dHaloInbox, 0, ctx->haloInboxBytes + migBytes));
+    ctx->dMigInbox = ctx->dHaloInbox + ctx->haloInboxBytes;
+    CK(cudaMalloc((void**)&ctx->dMigLocal, ctx->migSlotBytes));
     if (!ctx->dHaloP2p) CK(cudaMalloc((void**)&ctx->dHaloP2p, sizeof(HaloP2pState)));
     ctx->haloEpoch = 0;
     if (ipcHandleOut) {
@@ -2574,6 +2591,8 @@ int32_t b2c_mgpu_p2p_connect(b2c_ctx* ctx, const void* ipcHandles, void* const* 
         ctx->haloIpcOpened[r] = p;
         ctx->haloPeers.inbox[r] = (unsigned char*)p;
     }
+    // every rank uses the same capacities, so the migration inbox sits at the same offset in every allocation
+    for (int r = 0; r < R; r++) ctx->migPeers.inbox[r] = ctx->haloPeers.inbox[r] + ctx->haloInboxBytes;
     ctx->haloConnected = true;
     return B2C_OK;
 }
@@ -2592,9 +2611,19 @@ int32_t b2c_mgpu_p2p_export_halo(b2c_ctx* ctx) {
     ctx->haloEpoch++;
     CK(cudaMemsetAsync(ctx->dHaloP2p, 0, sizeof(HaloP2pState), s));
     const int nb = ctx->nBodies > 0 ? ctx->nBodies : 1;   // at least one block: the headers must be published
-    k_halo_export_p2p<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, ctx->haloPeers, ctx->partRanks,
-                                                      ctx->haloSlotBytesP2p, ctx->haloCapP2p, ctx->haloEpoch, ctx->dHaloP2p, ctx->dCtr);
-    ctx->launches++;
+    if (ctx->haloTwoPhase) {
+        if (!ctx->dHaloStage) CK(cudaMalloc((void**)&ctx->dHaloStage, (size_t)ctx->partRanks * ctx->haloCapP2p * sizeof(HaloRecord)));
+        k_halo_stage<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, ctx->partRanks, ctx->dHaloStage,
+                                                     ctx->haloCapP2p, ctx->dHaloP2p, ctx->dCtr);
+        k_halo_push<<<dim3(16, (unsigned)ctx->partRanks), 256, 0, s>>>(ctx->dHaloStage, ctx->haloPeers, ctx->partRanks, ctx->slab.rank,
+                                                                       ctx->haloSlotBytesP2p, ctx->haloCapP2p, ctx->haloEpoch, ctx->dHaloP2p,
+                                                                       reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ctx->dHaloP2p) + offsetof(HaloP2pState, pushTicket)));
+        ctx->launches += 2;
+    } else {
+        k_halo_export_p2p<<<(nb + 255) / 256, 256, 0, s>>>(ctx->B, ctx->nBodies, ctx->dOwner, ctx->slab, ctx->haloPeers, ctx->partRanks,
+                                                          ctx->haloSlotBytesP2p, ctx->haloCapP2p, ctx->haloEpoch, ctx->dHaloP2p, ctx->dCtr);
+        ctx->launches++;
+    }
     CK(cudaGetLastError());
     ctx->haloExported = true;
     return B2C_OK;
@@ -2618,6 +2647,36 @@ int32_t b2c_mgpu_p2p_import_halo(b2c_ctx* ctx) {
     ctx->haloExported = false;
     ctx->haloImported = true;
     return B2C_OK;
+}
+
+// Manifolds of pairs this rank no longer owns -> every other rank's migration inbox (replaces export_departed_slot + the
+// all-gather); then wait + adoption (replaces import_arrival_slots).
+int32_t b2c_mgpu_p2p_export_departed(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled || !ctx->haloConnected) { ctx->err = "peer-to-peer exchange is not connected"; return B2C_ERR_STATE; }
+    if (!ctx->pairsValid) return B2C_ERR_STATE;
+    int32_t rc = b2c_mgpu_export_departed_slot(ctx, ctx->dMigLocal, (int32_t)ctx->migCap);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ctx->dHaloP2p) + offsetof(HaloP2pState, migrateTicket));
+    k_migrate_push<<<dim3(4, (unsigned)ctx->partRanks), 256, 0, s>>>(ctx->dMigLocal, ctx->migPeers, ctx->partRanks, ctx->slab.rank,
+                                                                     ctx->migSlotBytes, ctx->migCap, ctx->haloEpoch, tickets, ctx->dCtr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->migExported = true;
+    return B2C_OK;
+}
+
+int32_t b2c_mgpu_p2p_import_arrivals(b2c_ctx* ctx) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    if (!ctx->slab.enabled || !ctx->haloConnected) { ctx->err = "peer-to-peer exchange is not connected"; return B2C_ERR_STATE; }
+    if (!ctx->migExported) { ctx->err = "b2c_mgpu_p2p_import_arrivals before b2c_mgpu_p2p_export_departed"; return B2C_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    const unsigned char* slots = ctx->dMigInbox + (size_t)(ctx->haloEpoch & 1u) * (size_t)ctx->partRanks * ctx->migSlotBytes;
+    k_halo_wait<<<1, 32, 0, ctx->stream>>>(slots, ctx->partRanks, ctx->slab.rank, ctx->migSlotBytes, ctx->haloEpoch, ctx->dCtr);
+    ctx->launches++;
+    ctx->migExported = false;
+    return b2c_mgpu_import_arrival_slots(ctx, slots, ctx->partRanks, (int32_t)ctx->migCap);
 }
 
 int32_t b2c_mgpu_broadphase(b2c_ctx* ctx) {

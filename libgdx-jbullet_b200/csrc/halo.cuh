@@ -99,8 +99,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 
 struct HaloP2pState {
     uint32_t sendCount[16];   // records sent to each destination this step
-    uint32_t ticket;          // blocks finished
+    uint32_t ticket;          // blocks finished (fused kernel)
     uint32_t pad[3];
+    uint32_t pushTicket[16];  // blocks finished per destination (two-phase variant)
+    uint32_t migrateTicket[16];
 };
 
 __global__ void __launch_bounds__(256)
@@ -145,8 +147,8 @@ k_halo_export_p2p(BodyArrays B, int n, const uint8_t* __restrict__ owner, SlabFi
             }
         }
     }
-    // publish: every block's stores are fenced at system scope before it takes a ticket; the last block writes the headers
-    __threadfence_system();
+    // publish: a block that stored into a peer fences at system scope before it takes a ticket; the last block writes the headers
+    if (__syncthreads_or(lo <= hi && (lo != slab.rank || hi != slab.rank))) __threadfence_system();
     __syncthreads();
     __shared__ uint32_t sLast;
     if (threadIdx.x == 0) sLast = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -157,6 +159,99 @@ k_halo_export_p2p(BodyArrays B, int n, const uint8_t* __restrict__ owner, SlabFi
         uint32_t c = *(volatile uint32_t*)&st->sendCount[d];
         if (c > cap) c = cap;
         st_release_sys_u64(reinterpret_cast<unsigned long long*>(peers.inbox[d] + mySlot), (unsigned long long)c | ((unsigned long long)epoch << 32));
+    }
+}
+
+// Two-phase variant of the same exchange: k_halo_stage compacts the boundary records per destination in LOCAL memory
+// (stage[d] = cap records), k_halo_push copies each destination's run into the peer's inbox with coalesced 16-byte stores
+// (grid.y = destination) and the last block of a destination publishes its header — scattered 16-byte peer stores from
+// one thread per record become full NVLink write packets, and only the push blocks pay a system-scope fence.
+__global__ void __launch_bounds__(256)
+k_halo_stage(BodyArrays B, int n, const uint8_t* __restrict__ owner, SlabFilter slab, int nranks, HaloRecord* __restrict__ stage,
+             uint32_t cap, HaloP2pState* st, StepCounters* ctr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int lo = 1, hi = 0;
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    uint8_t flags = 0;
+    if (i < n && owner[i] == (uint8_t)slab.rank) {
+        flags = B.flags[i];
+        if (flags & BF_ALIVE) {
+            a = B.effMin[i];
+            b = B.effMax[i];
+            lo = slab.region(axisOf(a, slab.axis));
+            hi = slab.region(axisOf(b, slab.axis));
+        }
+    }
+    for (int d = 0; d < nranks; d++) {
+        const bool want = d != slab.rank && lo <= d && d <= hi;
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (m == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&st->sendCount[d], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (want) {
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) {
+                HaloRecord* r = stage + (size_t)d * cap + pos;
+                float4 a2 = a, b2 = b;
+                a2.w = __uint_as_float((uint32_t)i);
+                b2.w = __uint_as_float((uint32_t)flags);
+                r->mn = a2;
+                r->mx = b2;
+                r->xf[0] = B.xf4[3 * (size_t)i];
+                r->xf[1] = B.xf4[3 * (size_t)i + 1];
+                r->xf[2] = B.xf4[3 * (size_t)i + 2];
+            } else {
+                ctr->haloOverflow = 1;
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+k_halo_push(const HaloRecord* __restrict__ stage, HaloPeers peers, int nranks, int rank, size_t slotBytes, uint32_t cap, uint32_t epoch,
+            HaloP2pState* st, uint32_t* __restrict__ pushTicket /*[16], zeroed*/) {
+    const int d = blockIdx.y;
+    if (d == rank) return;
+    uint32_t c = st->sendCount[d];
+    if (c > cap) c = cap;
+    const size_t mySlot = ((size_t)(epoch & 1u) * (size_t)nranks + (size_t)rank) * slotBytes;
+    const float4* src = reinterpret_cast<const float4*>(stage + (size_t)d * cap);
+    float4* dst = reinterpret_cast<float4*>(peers.inbox[d] + mySlot + HALO_HEADER_BYTES);
+    const size_t words = (size_t)c * (sizeof(HaloRecord) / 16);
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) dst[w] = src[w];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&pushTicket[d], 1u) == gridDim.x - 1) {
+        __threadfence_system();
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(peers.inbox[d] + mySlot), (unsigned long long)c | ((unsigned long long)epoch << 32));
+    }
+}
+
+// The manifolds of pairs that changed owner travel the same way: the sender's departed-manifold slot (k_export_departed:
+// { count, keys[cap], headers[cap], points[4 cap] }, narrowphase.cuh) is pushed — only its `count` live records — into slot
+// [parity][me] of EVERY other rank's migration inbox (the sender cannot tell who owns the pair now), then published.
+__global__ void __launch_bounds__(256)
+k_migrate_push(const unsigned char* __restrict__ local, HaloPeers peers, int nranks, int rank, size_t slotBytes, uint32_t cap, uint32_t epoch,
+               uint32_t* __restrict__ pushTicket /*[16], zeroed*/, StepCounters* ctr) {
+    const int d = blockIdx.y;
+    if (d == rank) return;
+    uint32_t c = *reinterpret_cast<const uint32_t*>(local);
+    if (c > cap) { c = cap; if (blockIdx.x == 0 && threadIdx.x == 0) ctr->migrateOverflow = 1; }
+    unsigned char* dst = peers.inbox[d] + ((size_t)(epoch & 1u) * (size_t)nranks + (size_t)rank) * slotBytes;
+    // three runs of 8-byte words: keys (8 B each), headers (32 B), points (4 x 96 B per manifold)
+    const size_t off[3] = {16, 16 + (size_t)cap * 8, 16 + (size_t)cap * (8 + 32)};
+    const size_t words[3] = {(size_t)c, (size_t)c * 4, (size_t)c * 48};
+    for (int k = 0; k < 3; k++) {
+        const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(local + off[k]);
+        unsigned long long* d8 = reinterpret_cast<unsigned long long*>(dst + off[k]);
+        for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words[k]; w += (size_t)gridDim.x * blockDim.x) d8[w] = s8[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&pushTicket[d], 1u) == gridDim.x - 1) {
+        __threadfence_system();
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)c | ((unsigned long long)epoch << 32));
     }
 }
 

@@ -22,7 +22,8 @@ class PartitionedStepper:
         -> the boundary records reach the ranks whose slab they touch: by peer-to-peer stores fused into the export kernel
            (halo="p2p", default when every rank can map every inbox) or by ONE all-gather of fixed-size halo slots
         -> adoption of the records that touch this rank's slab, pair calculation over the local list
-        -> manifolds of pairs that changed owner into a small migration slot -> ONE all-gather -> adoption
+        -> manifolds of pairs that changed owner reach their new owner the same way (peer-to-peer push to every other
+           rank, or a small migration slot + ONE all-gather) -> adoption
         -> narrowphase on the pairs this rank owns.
     planes = None lets the library cut the world at equal-count quantiles along its longest axis."""
 
@@ -56,7 +57,7 @@ class PartitionedStepper:
         torch, gw = self.torch, self.gw
         ok = 1
         try:
-            handle, _ptr = gw.mgpu_p2p_init(self.hcap)
+            handle, _ptr = gw.mgpu_p2p_init(self.hcap, self.mcap)
             if self.dist is not None and self.nranks > 1:
                 mine = torch.tensor(list(handle), dtype=torch.uint8, device=d)
                 allh = torch.zeros(64 * self.nranks, dtype=torch.uint8, device=d)
@@ -92,9 +93,13 @@ class PartitionedStepper:
             self.all_gather(self.all_halo, self.my_halo)
             gw.mgpu_import_halo(self.all_halo.data_ptr(), self.nranks, self.hcap)
         gw.mgpu_broadphase()
-        gw.mgpu_export_departed_slot(self.my_slot.data_ptr(), self.mcap)
-        self.all_gather(self.all_slots, self.my_slot)
-        gw.mgpu_import_arrival_slots(self.all_slots.data_ptr(), self.nranks, self.mcap)
+        if self.halo_mode == "p2p":
+            gw.mgpu_p2p_export_departed()  # manifolds of pairs that changed owner -> every other rank's migration inbox
+            gw.mgpu_p2p_import_arrivals()
+        else:
+            gw.mgpu_export_departed_slot(self.my_slot.data_ptr(), self.mcap)
+            self.all_gather(self.all_slots, self.my_slot)
+            gw.mgpu_import_arrival_slots(self.all_slots.data_ptr(), self.nranks, self.mcap)
         gw.mgpu_narrowphase()
 
     def tune_caps(self, headroom=1.5, min_halo=1024, min_migrate=256):
@@ -104,13 +109,13 @@ class PartitionedStepper:
         capacities without another collective) and re-allocates the buffers with `headroom`.  A later overflow is still
         reported by b2c_sync_counts (B2C_ERR_CAPACITY); call this again, or raise the caps, when the world changes."""
         torch = self.torch
+        if self.halo_mode == "p2p":
+            return self.hcap, self.mcap   # records travel, not slots: the inbox capacities cost nothing per step
         torch.cuda.synchronize()
         halo = self.all_halo.view(torch.int32)[:: self.halo_bytes // 4][: self.nranks]
         mig = self.all_slots.view(torch.int32)[:: self.slot_bytes // 4][: self.nranks]
         hmax, mmax = int(halo.max().item()), int(mig.max().item())
         hcap = max(min_halo, int(hmax * headroom) + 64)
-        if self.halo_mode == "p2p":
-            hcap = self.hcap          # the peer-to-peer path sends records, not slots: its inbox capacity costs nothing per step
         mcap = max(min_migrate, int(mmax * headroom) + 64)
         if hcap >= self.hcap and mcap >= self.mcap:
             return self.hcap, self.mcap
@@ -126,11 +131,10 @@ class PartitionedStepper:
 
     def describe(self):
         if self.halo_mode == "p2p":
-            return (f"slab partition; halo exchange = peer-to-peer stores over NVLink fused into the export kernel (80-byte "
-                    f"boundary-proxy records written straight into the inboxes of the slabs they reach, release/acquire epoch "
-                    f"flags, no collective; inbox capacity {self.hcap} records per source); 1 ncclAllGather per step for the "
-                    f"manifold-migration slots ({self.mcap} manifolds = {self.slot_bytes} B per rank, "
-                    f"{self.slot_bytes * self.nranks} B gathered)")
+            return (f"slab partition; NO collective in the step: boundary proxies (80-byte records, inbox capacity {self.hcap} per "
+                    f"source) and migrating manifolds (capacity {self.mcap} per source) are stored by this library's kernels "
+                    f"straight into the inboxes of the ranks that need them (peer memory over NVLink, CUDA IPC), coalesced, with "
+                    f"release/acquire epoch flags at system scope")
         return (f"slab partition, 2 ncclAllGather per step: halo slots ({self.hcap} x 80-byte boundary-proxy records = "
                 f"{self.halo_bytes} B per rank, {self.halo_bytes * self.nranks} B gathered) and manifold-migration slots "
                 f"({self.mcap} manifolds = {self.slot_bytes} B per rank, {self.slot_bytes * self.nranks} B gathered)")

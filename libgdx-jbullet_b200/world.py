@@ -310,11 +310,12 @@ class GpuCollisionWorld:
     def mgpu_import_halo(self, slots_ptr, nslots, cap):
         self._ck(self.L.b2c_mgpu_import_halo(self.h, C.c_void_p(slots_ptr), nslots, cap))
 
-    def mgpu_p2p_init(self, cap):
-        """Allocate this rank's halo inbox for the peer-to-peer exchange: (64-byte CUDA IPC handle, device pointer)."""
+    def mgpu_p2p_init(self, cap, migrate_cap=2048):
+        """Allocate this rank's inboxes (halo records, migrating manifolds) for the peer-to-peer exchange: (64-byte CUDA IPC
+        handle, device pointer)."""
         handle = (C.c_ubyte * 64)()
         ptr = C.c_void_p()
-        self._ck(self.L.b2c_mgpu_p2p_init(self.h, int(cap), handle, C.byref(ptr)))
+        self._ck(self.L.b2c_mgpu_p2p_init(self.h, int(cap), int(migrate_cap), handle, C.byref(ptr)))
         return bytes(handle), int(ptr.value)
 
     def mgpu_p2p_connect(self, ipc_handles=None, inbox_ptrs=None):
@@ -332,6 +333,12 @@ class GpuCollisionWorld:
 
     def mgpu_p2p_import_halo(self):
         self._ck(self.L.b2c_mgpu_p2p_import_halo(self.h))
+
+    def mgpu_p2p_export_departed(self):
+        self._ck(self.L.b2c_mgpu_p2p_export_departed(self.h))
+
+    def mgpu_p2p_import_arrivals(self):
+        self._ck(self.L.b2c_mgpu_p2p_import_arrivals(self.h))
 
     def mgpu_broadphase(self):
         self._ck(self.L.b2c_mgpu_broadphase(self.h))

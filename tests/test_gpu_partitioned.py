@@ -25,7 +25,7 @@ def run_partitioned(pkg, sc, R, steps, mode=1, slots=False, axis=None, planes=No
     hcap = halo_cap or max(4096, sc.n)
     if p2p:
         # the halo exchange as peer-to-peer stores: every "rank" maps the others' inboxes by plain device pointer
-        inboxes = [w.mgpu_p2p_init(hcap)[1] for w in ranks]
+        inboxes = [w.mgpu_p2p_init(hcap, 1 << 12)[1] for w in ranks]
         for w in ranks:
             w.mgpu_p2p_connect(inbox_ptrs=inboxes)
     hbytes = single.mgpu_halo_slot_bytes(hcap)
@@ -58,7 +58,14 @@ def run_partitioned(pkg, sc, R, steps, mode=1, slots=False, axis=None, planes=No
             else:
                 w.mgpu_import_halo(allhalo.data_ptr(), R, hcap)
             w.mgpu_broadphase()
-        if slots:
+        if p2p:
+            for w in ranks:
+                w.mgpu_p2p_export_departed()      # every rank pushes its departed manifolds into all the others' inboxes
+            torch.cuda.synchronize()
+            tot = 1                               # counted on the device only; the bit-exact union below is the check
+            for w in ranks:
+                w.mgpu_p2p_import_arrivals()
+        elif slots:
             # sync-free variant: every rank packs its slot straight into the "gathered" buffer, then all ranks scan it
             for r, w in enumerate(ranks):
                 w.mgpu_export_departed_slot(allslots.data_ptr() + r * sbytes, scap)
