@@ -103,6 +103,13 @@ final class B2C {
     static final MethodHandle mgpuExportDepartedSlot = h("b2c_mgpu_export_departed_slot", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
     static final MethodHandle mgpuImportArrivalSlots = h("b2c_mgpu_import_arrival_slots", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
     static final MethodHandle mgpuNarrowphase = h("b2c_mgpu_narrowphase", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    // the same exchange as peer-to-peer stores (no collective): inboxes mapped once through CUDA IPC handles
+    static final MethodHandle mgpuP2pInit = h("b2c_mgpu_p2p_init", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle mgpuP2pConnect = h("b2c_mgpu_p2p_connect", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle mgpuP2pExportHalo = h("b2c_mgpu_p2p_export_halo", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle mgpuP2pImportHalo = h("b2c_mgpu_p2p_import_halo", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle mgpuP2pExportDeparted = h("b2c_mgpu_p2p_export_departed", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle mgpuP2pImportArrivals = h("b2c_mgpu_p2p_import_arrivals", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle stream = h("b2c_stream", FunctionDescriptor.of(ADDRESS, ADDRESS));
 
     static void check(int rc, MemorySegment ctx) {

@@ -29,7 +29,9 @@ class PartitionedStepper:
 
     def __init__(self, gw, rank, nranks, dist, torch, dev, migrate_cap=2048, halo_cap=None, axis=None, planes=None, halo="p2p"):
         self.gw, self.rank, self.nranks, self.dist, self.torch = gw, rank, nranks, dist, torch
-        self.stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
+        # dev = "cpu": host-logic tests (gloo, a stand-in world object); everything else is a CUDA device index
+        self.on_gpu = dev != "cpu"
+        self.stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev)) if self.on_gpu else None
         self.mcap = int(migrate_cap)
         self.hcap = int(halo_cap) if halo_cap else default_halo_cap(gw.num_bodies)
         if planes is None:
@@ -38,7 +40,7 @@ class PartitionedStepper:
             gw.set_partition_slabs(rank, nranks, axis, planes)
         self.slot_bytes = gw.mgpu_slot_bytes(self.mcap)
         self.halo_bytes = gw.mgpu_halo_slot_bytes(self.hcap)
-        d = f"cuda:{dev}"
+        d = f"cuda:{dev}" if self.on_gpu else "cpu"
         self.my_slot = torch.zeros(self.slot_bytes, dtype=torch.uint8, device=d)
         self.all_slots = torch.zeros(self.slot_bytes * nranks, dtype=torch.uint8, device=d)
         self.my_halo = torch.zeros(self.halo_bytes, dtype=torch.uint8, device=d)
@@ -55,20 +57,26 @@ class PartitionedStepper:
         """Every rank publishes the IPC handle of its inbox (one small all-gather at set-up), maps the others', and all ranks
         agree (all-reduce of a success flag) on whether the peer-to-peer path is usable."""
         torch, gw = self.torch, self.gw
-        ok = 1
+        ok, handle, ptr = 1, bytes(64), 0
         try:
-            handle, _ptr = gw.mgpu_p2p_init(self.hcap, self.mcap)
-            if self.dist is not None and self.nranks > 1:
-                mine = torch.tensor(list(handle), dtype=torch.uint8, device=d)
-                allh = torch.zeros(64 * self.nranks, dtype=torch.uint8, device=d)
-                self.dist.all_gather_into_tensor(allh, mine)
-                gw.mgpu_p2p_connect(ipc_handles=bytes(allh.cpu().numpy().tobytes()))
-            else:
-                gw.mgpu_p2p_connect(inbox_ptrs=[_ptr] * self.nranks)
+            handle, ptr = gw.mgpu_p2p_init(self.hcap, self.mcap)
         except Exception as e:  # noqa: BLE001 — any failure means "use the collective", decided by all ranks together
-            self.p2p_error = repr(e)
-            ok = 0
-        if self.dist is not None and self.nranks > 1:
+            self.p2p_error, ok = repr(e), 0
+        multi = self.dist is not None and self.nranks > 1
+        # every rank takes part in both collectives below whatever happened to it, so that they always match up
+        if multi:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=d)
+            allh = torch.zeros(64 * self.nranks, dtype=torch.uint8, device=d)
+            self.dist.all_gather_into_tensor(allh, mine)
+        if ok:
+            try:
+                if multi:
+                    gw.mgpu_p2p_connect(ipc_handles=bytes(allh.cpu().numpy().tobytes()))
+                else:
+                    gw.mgpu_p2p_connect(inbox_ptrs=[ptr] * self.nranks)
+            except Exception as e:  # noqa: BLE001
+                self.p2p_error, ok = repr(e), 0
+        if multi:
             flag = torch.tensor([ok], dtype=torch.int32, device=d)
             self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
             ok = int(flag.item())
@@ -77,7 +85,8 @@ class PartitionedStepper:
     def all_gather(self, out, inp):
         """One NCCL all-gather on the world's stream; with a single rank it is a copy."""
         torch = self.torch
-        with torch.cuda.stream(self.stream):
+        import contextlib
+        with (torch.cuda.stream(self.stream) if self.on_gpu else contextlib.nullcontext()):
             if self.dist is not None and self.nranks > 1:
                 self.dist.all_gather_into_tensor(out, inp)
             else:
