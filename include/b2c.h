@@ -341,7 +341,8 @@ int32_t b2c_compute_islands(b2c_ctx*, int32_t* tags_out, int32_t n, int32_t* num
  * are cast with the reference's SubsimplexConvexCast, triangle meshes with the quantised-BVH ray walk
  * (sh/OptimizedBvh.java:817-931) + np/TriangleRaycastCallback.java:46-117, static planes with the two triangles
  * sh/StaticPlaneShape.java:60-122 generates, compounds child by child.  For meshes and planes the normal is the reference's
- * unnormalised triangle normal rotated into world space. */
+ * unnormalised triangle normal rotated into world space.  No limit on the number of bodies a ray may meet: beyond 1024
+ * candidate boxes a ray is evaluated in body-index tiles (exact, but without spatial culling). */
 int32_t b2c_ray_test_closest(b2c_ctx*, int32_t n, const float* from_xyz, const float* to_xyz, int16_t group, int16_t mask,
                              int32_t* uid_out, float* fraction_out, float* normal_out, float* point_out);
 

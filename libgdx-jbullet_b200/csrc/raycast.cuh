@@ -27,7 +27,10 @@ namespace b2c {
 #define B2C_RAY_THREADS 128
 #endif
 constexpr int RAY_THREADS = B2C_RAY_THREADS;
-constexpr int RAY_MAX_CAND = 1024;
+#ifndef B2C_RAY_MAX_CAND
+#define B2C_RAY_MAX_CAND 1024
+#endif
+constexpr int RAY_MAX_CAND = B2C_RAY_MAX_CAND;   // candidates one round keeps in shared memory
 
 __device__ __forceinline__ int rayOutcode(f3 p, f3 h) {  // lm/AabbUtil2.java:40-43
     return (p.x < -h.x ? 0x01 : 0) | (p.x > h.x ? 0x08 : 0) | (p.y < -h.y ? 0x02 : 0) | (p.y > h.y ? 0x10 : 0) |
@@ -328,13 +331,8 @@ k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __re
                 }
             }
         }
-        __syncthreads();
-        uint32_t cnt = sCount;
-        if (cnt > RAY_MAX_CAND) {
-            if (threadIdx.x == 0) atomicMax(overflow, cnt);
-            cnt = RAY_MAX_CAND;
-        }
         // (2) the casts, one candidate per thread
+        auto castAll = [&](uint32_t cnt) {
         for (uint32_t k = threadIdx.x; k < cnt; k += RAY_THREADS) {
             const int i = (int)sCand[k];
             const ShapeDev s = shapes[B.shape[i]];
@@ -396,12 +394,12 @@ k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __re
             sFrac[k] = fr;
             sNrm[k][0] = nn.x; sNrm[k][1] = nn.y; sNrm[k][2] = nn.z;
         }
-        __syncthreads();
-        // (3) the reference's loop over the candidates in body order
-        if (threadIdx.x == 0) {
-            float closest = 1.f;
-            int hitBody = -1;
-            f3 hn = mk3(0.f, 0.f, 0.f);
+        };
+        // (3) the reference's loop over the listed candidates in ascending body index, continuing from (closest, hitBody, hn)
+        float closest = 1.f;
+        int hitBody = -1;
+        f3 hn = mk3(0.f, 0.f, 0.f);
+        auto replay = [&](uint32_t cnt) {
             uint32_t done = 0;
             int lastIdx = -1;
             while (done < cnt) {
@@ -423,6 +421,38 @@ k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __re
                     hn = mk3(sNrm[bk][0], sNrm[bk][1], sNrm[bk][2]);
                 }
             }
+        };
+        __syncthreads();
+        const uint32_t total = sCount;
+        if (total <= RAY_MAX_CAND) {
+            castAll(total);
+            __syncthreads();
+            if (threadIdx.x == 0) replay(total);
+        } else {
+            // A ray that meets more boxes than one round holds (a very long ray through a dense pile) takes the bodies in
+            // INDEX order instead, RAY_MAX_CAND consecutive indices at a time: collect, cast, replay — the replay state carries
+            // over from tile to tile, so the decisions are still the reference's, in its order; only the culling is lost.
+            if (threadIdx.x == 0) atomicMax(overflow, total);   // informational: how many boxes the longest such ray met
+            for (int t0 = 0; t0 < n; t0 += RAY_MAX_CAND) {
+                __syncthreads();
+                if (threadIdx.x == 0) sCount = 0;
+                __syncthreads();
+                const int t1 = min(n, t0 + RAY_MAX_CAND);
+                for (int i = t0 + threadIdx.x; i < t1; i += RAY_THREADS) {
+                    const float4 mn = __ldg(rmin + i);
+                    if (mn.w == 0.f) continue;
+                    if (!filterPass(cbFilter, B.filt[i])) continue;
+                    const float4 mx = __ldg(rmax + i);
+                    if (rayAabb(from, to, mk3(mn.x, mn.y, mn.z), mk3(mx.x, mx.y, mx.z), 1.f)) sCand[atomicAdd(&sCount, 1u)] = (uint32_t)i;
+                }
+                __syncthreads();
+                const uint32_t c2 = sCount;
+                castAll(c2);
+                __syncthreads();
+                if (threadIdx.x == 0) replay(c2);
+            }
+        }
+        if (threadIdx.x == 0) {
             RayOut o;
             o.uid = hitBody + 1;
             o.fraction = closest;

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <vector>
 #define B2C_RAY_THREADS 1
+#define B2C_RAY_MAX_CAND 12    // small: rays that meet more boxes exercise the index-ordered tile path of k_ray_test
 #define B2C_SWEEP_MAX_CAND 128   // small lists: the rounds of k_convex_sweep (several flushes per sweep) are exercised
 #define B2C_SWEEP_HIT_CAP 3
 #include "cuda_runtime.h"
@@ -165,6 +166,7 @@ int main(int argc, char** argv) {
         }
         if (pass == 1 && sUnsup == 0) { printf("no sweep reached the static plane branch\n"); return 1; }
     }
+    if (overflow <= 12) { printf("no ray met more boxes (%u) than one round holds: the tile path was not exercised\n", overflow); return 1; }
     printf("ALL OK rays %d hits %d mesh %d plane %d compound %d overflow %u | sweeps %d hits %d mesh %d compound %d unsupported %d\n", NR, hits, hitMesh, hitPlane, hitComp, overflow, NS, sHits, sMesh, sComp, sUnsup);
     return 0;
 }

@@ -118,3 +118,27 @@ def test_rays_against_a_compound_heavy_scene(gpu_pkg):
     f[:, 1] = rng.uniform(2.0, 8.0, size=len(f))
     t[:, 1] = rng.uniform(-3.0, 1.0, size=len(t))
     assert _compare(gw, ow, f, t) > 600
+
+
+def test_a_ray_through_more_boxes_than_one_round_holds(gpu_pkg):
+    """1500 spheres crowded into one spot: a ray through the cluster meets more than the 1024 candidate boxes a block keeps
+    and takes the index-ordered tile path of k_ray_test; same hits as the oracle's sequential loop, bit for bit."""
+    rng = np.random.default_rng(31)
+    sc = scenes.Scene()
+    sph = sc.add_shape("sphere", 0.5)
+    bx = sc.add_shape("box", (0.3, 0.3, 0.3))
+    n = 1500
+    pos = rng.uniform(-0.2, 0.2, size=(n, 3))
+    pos[::10] += rng.uniform(-6.0, 6.0, size=(len(pos[::10]), 3))      # a few bodies away from the cluster
+    for k in range(n):
+        sc.body_shape.append(sph if k % 3 else bx); sc.static.append(False); sc.group.append(1); sc.mask.append(-1); sc.world.append(0)
+    sc.base = scenes.make_xf(scenes.random_rotations(rng, n), pos)
+    sc.vel = None
+    sc.spin = None
+    sc.extent = 12.0
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=0)
+    f = rng.uniform(-8.0, 8.0, size=(200, 3)).astype(np.float32)
+    t = (-f + rng.uniform(-0.3, 0.3, size=(200, 3))).astype(np.float32)   # through the middle of the cluster
+    f[100:], t[100:] = _rays(rng, 100, -8.0, 8.0)
+    hits = _compare(gw, ow, f, t)
+    assert hits >= 100
