@@ -363,6 +363,19 @@ int32_t b2c_convex_sweep_closest(b2c_ctx*, int32_t n, const int32_t* cast_shape_
                                  const float* to_xyz, int16_t group, int16_t mask, float allowed_ccd_penetration, int32_t* uid_out,
                                  float* fraction_out, float* normal_out, float* point_out);
 
+/* The "CCD motion clamping" query of DiscreteDynamicsWorld.integrateTransforms (dyn/DiscreteDynamicsWorld.java:700-729),
+ * batched: for body_uids[i] a SphereShape(ccd_radius[i]) (the body's ccdSweptSphereRadius) is swept from the body's RESIDENT
+ * world transform to predicted_xyz[i] (predictedTrans.origin) with a ClosestNotMeConvexResultCallback (:1129-1199) whose
+ * filter group / mask are the body's own: the body itself is skipped, so is every object it already has contact points
+ * with (any manifold of their pair's algorithm in the pair cache of the last step, :1181-1196), and a result whose normal
+ * does not oppose the motion (:1157).  Outputs as b2c_convex_sweep_closest; the host applies the reference's clamp
+ * `hasHit && closestHitFraction > 0.0001` (:721) and re-integrates with timeStep * fraction.  The caller lists the bodies
+ * whose squared motion exceeds their ccdSquareMotionThreshold and whose shape is convex (:700-703).  The predicted ROTATION
+ * enters the reference only through the angular term of the swept sphere's culling box (|w| r sqrt 3), taken as 0 here. */
+int32_t b2c_ccd_sweep_not_me(b2c_ctx*, int32_t n, const int32_t* body_uids, const float* ccd_radius, const float* predicted_xyz,
+                             float allowed_ccd_penetration, int32_t* hit_uid_out, float* fraction_out, float* normal_out,
+                             float* point_out);
+
 /* ---- one world partitioned over several GPUs -------------------------------------
  * Space is cut into `nranks` slabs by planes along one axis; rank r owns slab r.  A PROXY is owned by the rank whose slab
  * held its origin when the partition was set: only that rank runs updateAabbs / setAabb for it.  A PAIR is owned by the slab

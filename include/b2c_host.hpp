@@ -181,6 +181,12 @@ public:
         check(b2c_convex_sweep_closest(ctx, n, castShapeIds, basis9, fromXyz, toXyz, group, mask, allowedCcdPenetration, uidOut,
                                        fractionOut, normalOut, pointOut), ctx);
     }
+    // the CCD motion-clamping sweeps of DiscreteDynamicsWorld.integrateTransforms (dyn/DiscreteDynamicsWorld.java:700-729)
+    void ccdSweepNotMe(int32_t n, const int32_t* bodyUids, const float* ccdRadius, const float* predictedXyz, int32_t* hitUidOut,
+                       float* fractionOut, float* normalOut, float* pointOut, float allowedCcdPenetration = 0.04f) {
+        check(b2c_ccd_sweep_not_me(ctx, n, bodyUids, ccdRadius, predictedXyz, allowedCcdPenetration, hitUidOut, fractionOut, normalOut,
+                                   pointOut), ctx);
+    }
     // SimulationIslandManager.updateActivationState + storeIslandActivationState (disp/SimulationIslandManager.java:57-110)
     int32_t computeIslands(std::vector<int32_t>& tags) {
         int32_t n = 0;

@@ -81,6 +81,9 @@ final class B2C {
     // CollisionWorld.convexSweepTest + ClosestConvexResultCallback, batched translational sweeps
     static final MethodHandle convexSweepClosest = h("b2c_convex_sweep_closest",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_SHORT, JAVA_SHORT, JAVA_FLOAT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    // DiscreteDynamicsWorld.integrateTransforms' CCD motion clamping sweeps (ClosestNotMeConvexResultCallback), batched
+    static final MethodHandle ccdSweepNotMe = h("b2c_ccd_sweep_not_me",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_FLOAT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     // device-resident stepping: enqueue, download the pair list while the narrowphase runs, then wait for the counts
     static final MethodHandle stepDevice = h("b2c_step_device", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle syncCounts = h("b2c_sync_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));

@@ -2282,20 +2282,10 @@ int32_t b2c_ray_test_closest(b2c_ctx* ctx, int32_t n, const float* from, const f
     return B2C_OK;
 }
 
-int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castShapes, const float* basis9, const float* from, const float* to,
-                                 int16_t group, int16_t mask, float allowedPenetration, int32_t* uidOut, float* fracOut, float* nrmOut,
-                                 float* ptOut) {
-    if (!ctx || n < 0 || (n > 0 && (!castShapes || !basis9 || !from || !to))) return B2C_ERR_BAD_ARG;
-    if (n == 0) return B2C_OK;
-    for (int i = 0; i < n; i++) {
-        const int sid = castShapes[i];
-        if (sid < 0 || sid >= (int)ctx->hShapes.size()) { ctx->err = "convex sweep: unknown cast shape id"; return B2C_ERR_BAD_HANDLE; }
-        const int ty = ctx->hShapes[(size_t)sid].type;
-        if (ty != SH_BOX && ty != SH_SPHERE && ty != SH_HULL) {
-            ctx->err = "convex sweep: the cast shape must be convex (box, sphere or hull), as ConvexShape castShape is";
-            return B2C_ERR_BAD_ARG;
-        }
-    }
+// Shared body of the two sweep entry points.  me / radius non-null: the CCD motion-clamping sweeps (ClosestNotMe callback).
+static int32_t runConvexSweeps(b2c_ctx* ctx, int32_t n, const int32_t* castShapes, const float* basis9, const float* from, const float* to,
+                               uint32_t cbFilter, float allowedPenetration, const int32_t* meBodies, const float* radius, int32_t* uidOut,
+                               float* fracOut, float* nrmOut, float* ptOut) {
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     if (ctx->stagingCount || ctx->extPending) {
@@ -2313,7 +2303,7 @@ int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castSha
     if (n > ctx->sweepCap) {
         cudaFree(ctx->dSweepIn); cudaFree(ctx->dSweepOut);
         ctx->dSweepIn = nullptr; ctx->dSweepOut = nullptr; ctx->sweepCap = 0;
-        CK(cudaMalloc((void**)&ctx->dSweepIn, (size_t)n * 16 * sizeof(float)));  // shape id, basis 9, from 3, to 3
+        CK(cudaMalloc((void**)&ctx->dSweepIn, (size_t)n * 16 * sizeof(float)));  // basis 9 | from 3 | to 3 | cast shape id (or: me, radius)
         CK(cudaMalloc((void**)&ctx->dSweepOut, (size_t)n * sizeof(RayOut)));
         ctx->sweepCap = n;
     }
@@ -2322,10 +2312,28 @@ int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castSha
     float* dFrom = dBasis + 9 * (size_t)n;
     float* dTo = dFrom + 3 * (size_t)n;
     int* dShape = reinterpret_cast<int*>(dTo + 3 * (size_t)n);
-    CK(cudaMemcpyAsync(dBasis, basis9, (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(dFrom, from, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    SweepNotMe nm{};
     CK(cudaMemcpyAsync(dTo, to, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(dShape, castShapes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (meBodies) {
+        // the basis area holds the radii, the shape-id area the 0-based body indices
+        CK(cudaMemcpyAsync(dBasis, radius, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dShape, meBodies, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+        nm.me = dShape;
+        nm.radius = dBasis;
+        if (ctx->pairsValid) {
+            const int cur = ctx->cur;
+            nm.keys = ctx->dSortedKeys[cur];
+            nm.numPairs = ctx->dNumPairs[cur];
+            nm.first = ctx->dPairFirst[cur];
+            nm.uidBits = ctx->uidBits;
+            nm.mhdr = ctx->dMHdr[cur];
+            nm.compH = ctx->hasCompound ? ctx->dCH[ctx->ccur] : nullptr;
+        }
+    } else {
+        CK(cudaMemcpyAsync(dBasis, basis9, (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dFrom, from, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dShape, castShapes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
     CK(cudaMemsetAsync(ctx->dRayOverflow, 0, sizeof(uint32_t), s));
     const int nSorted = ctx->nSortedBodies < nb ? ctx->nSortedBodies : nb;
     if (nb > 0) {
@@ -2334,11 +2342,10 @@ int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castSha
         k_ray_chunks<<<(nChunks + 127) / 128, 128, 0, s>>>(ctx->dRayMin, ctx->dRayMax, ctx->dSmin, nSorted, nb, ctx->dRayChunkMin,
                                                           ctx->dRayChunkMax);
     }
-    const uint32_t cbFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
     const unsigned grid = (unsigned)(n < 148 * 8 ? n : 148 * 8);
     k_convex_sweep<<<grid, SWEEP_THREADS, 0, s>>>(ctx->B, ctx->dShapes, ctx->dHullPts, ctx->dMeshes, ctx->dChildren, ctx->dSmin, nSorted,
                                                   ctx->dRayChunkMin, ctx->dRayChunkMax, nb, ctx->dRayMin, ctx->dRayMax, dShape, dBasis,
-                                                  dFrom, dTo, n, cbFilter, allowedPenetration, ctx->dSweepOut, ctx->dRayOverflow);
+                                                  dFrom, dTo, n, cbFilter, allowedPenetration, ctx->dSweepOut, ctx->dRayOverflow, nm);
     std::vector<RayOut> host((size_t)n);
     CK(cudaMemcpyAsync(host.data(), ctx->dSweepOut, (size_t)n * sizeof(RayOut), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -2349,6 +2356,38 @@ int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castSha
         if (ptOut) { ptOut[3 * i] = host[i].point[0]; ptOut[3 * i + 1] = host[i].point[1]; ptOut[3 * i + 2] = host[i].point[2]; }
     }
     return B2C_OK;
+}
+
+int32_t b2c_convex_sweep_closest(b2c_ctx* ctx, int32_t n, const int32_t* castShapes, const float* basis9, const float* from, const float* to,
+                                 int16_t group, int16_t mask, float allowedPenetration, int32_t* uidOut, float* fracOut, float* nrmOut,
+                                 float* ptOut) {
+    if (!ctx || n < 0 || (n > 0 && (!castShapes || !basis9 || !from || !to))) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    for (int i = 0; i < n; i++) {
+        const int sid = castShapes[i];
+        if (sid < 0 || sid >= (int)ctx->hShapes.size()) { ctx->err = "convex sweep: unknown cast shape id"; return B2C_ERR_BAD_HANDLE; }
+        const int ty = ctx->hShapes[(size_t)sid].type;
+        if (ty != SH_BOX && ty != SH_SPHERE && ty != SH_HULL) {
+            ctx->err = "convex sweep: the cast shape must be convex (box, sphere or hull), as ConvexShape castShape is";
+            return B2C_ERR_BAD_ARG;
+        }
+    }
+    const uint32_t cbFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)mask << 16);
+    return runConvexSweeps(ctx, n, castShapes, basis9, from, to, cbFilter, allowedPenetration, nullptr, nullptr, uidOut, fracOut, nrmOut, ptOut);
+}
+
+int32_t b2c_ccd_sweep_not_me(b2c_ctx* ctx, int32_t n, const int32_t* bodyUids, const float* radius, const float* predicted, float allowedPenetration,
+                             int32_t* uidOut, float* fracOut, float* nrmOut, float* ptOut) {
+    if (!ctx || n < 0 || (n > 0 && (!bodyUids || !radius || !predicted))) return B2C_ERR_BAD_ARG;
+    if (n == 0) return B2C_OK;
+    std::vector<int32_t> me((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const int u = bodyUids[i];
+        if (u < 1 || u > ctx->nBodies || !(ctx->hFlags[(size_t)u - 1] & BF_ALIVE)) { ctx->err = "ccd sweep: unknown body uid"; return B2C_ERR_BAD_HANDLE; }
+        if (!(radius[i] >= 0.f)) { ctx->err = "ccd sweep: negative swept-sphere radius"; return B2C_ERR_BAD_ARG; }
+        me[(size_t)i] = u - 1;
+    }
+    return runConvexSweeps(ctx, n, nullptr, nullptr, nullptr, predicted, 0u, allowedPenetration, me.data(), radius, uidOut, fracOut, nrmOut, ptOut);
 }
 
 int32_t b2c_set_profiling(b2c_ctx* ctx, int32_t on) {

@@ -182,7 +182,7 @@ struct SweepRec {  // what one candidate reports under the widest bound
 // triangle the walk reports, folded as BridgeTriangleConvexcastCallback does under the entry bound 1
 __device__ __forceinline__ void sweepMeshWalk(const MeshDev& md, const AnyS& A, const Xf& fromA, f3 toOrigin, const Xf& meshXf,
                                               float meshMargin, f3 fromLocal, f3 toLocal, f3 boxMin, f3 boxMax, bool& valid,
-                                              SweepRec& rec) {
+                                              SweepRec& rec, bool notMe, f3 rel) {
     f3 rmin = mk3(jminf(fromLocal.x, toLocal.x), jminf(fromLocal.y, toLocal.y), jminf(fromLocal.z, toLocal.z));
     f3 rmax = mk3(jmaxf(fromLocal.x, toLocal.x), jmaxf(fromLocal.y, toLocal.y), jmaxf(fromLocal.z, toLocal.z));
     rmin = add3(rmin, boxMin);
@@ -224,7 +224,7 @@ __device__ __forceinline__ void sweepMeshWalk(const MeshDev& md, const AnyS& A, 
             if (subsimplexConvexCast(A, fromA, toOrigin, T, meshXf, f, nn, pt)) {
                 if (len2_3(nn) > 0.0001f && f < 1.f) {
                     nn = nor3(nn);
-                    if (f <= closest) {
+                    if (f <= closest && !(notMe && dot3(nn, rel) >= -0.f)) {   // ClosestNotMe...addSingleResult (:1157)
                         closest = f;
                         valid = true;
                         rec.fraction = f;
@@ -237,6 +237,41 @@ __device__ __forceinline__ void sweepMeshWalk(const MeshDev& md, const AnyS& A, 
         if (rayBox || leaf) cur++;
         else cur += -nd.w;
     }
+}
+
+// DiscreteDynamicsWorld's ClosestNotMeConvexResultCallback (dyn/DiscreteDynamicsWorld.java:1129-1199) for the CCD motion
+// clamping sweeps of integrateTransforms (:700-729): per sweep the swept body `me` (its filter group / mask are the
+// callback's), a sphere of its ccdSweptSphereRadius as the cast shape, and the pair cache with its manifolds: an object the
+// body already has contact points with is skipped (needsCollision, :1181-1196), so is a result whose normal does not
+// oppose the motion (addSingleResult, :1157).
+struct SweepNotMe {
+    const int* me;               // [numSweeps] 0-based body index, or null: plain ClosestConvexResultCallback sweeps
+    const float* radius;         // [numSweeps] radius of the swept sphere
+    const uint64_t* keys;        // sorted pair keys of the last pair calculation
+    const uint32_t* numPairs;    // null: no pair cache yet
+    const uint32_t* first;       // first pair of every uid0
+    int uidBits;
+    const ManifoldHdr* mhdr;     // manifold header of every pair
+    const ManifoldHdr* compH;    // child manifolds of compound pairs (or null)
+};
+__device__ __forceinline__ bool sweepAlreadyTouching(const SweepNotMe& nm, const BodyArrays& B, const ShapeDev* __restrict__ shapes, int me,
+                                                     int other) {
+    if (!nm.numPairs) return false;
+    const uint32_t n = *nm.numPairs;
+    const uint32_t u0 = (uint32_t)(me < other ? me : other) + 1u, u1 = (uint32_t)(me < other ? other : me) + 1u;
+    const int p = findPairIndex(nm.keys, n, nm.first, ((uint64_t)u0 << nm.uidBits) | u1, nm.uidBits);
+    if (p < 0) return false;
+    const ManifoldHdr h = nm.mhdr[p];
+    if (h.algorithm == 5) {   // compound pair: any child manifold (getAllContactManifolds of the compound algorithm)
+        if (!nm.compH) return false;
+        const ShapeDev& S0 = shapes[B.shape[u0 - 1]];
+        const ShapeDev& S1 = shapes[B.shape[u1 - 1]];
+        const uint32_t cnt = (S0.type == SH_COMPOUND ? (uint32_t)S0.numPoints : 1u) * (S1.type == SH_COMPOUND ? (uint32_t)S1.numPoints : 1u);
+        for (uint32_t k = 0; k < cnt; k++)
+            if (nm.compH[(uint32_t)h.pad1 + k].num_contacts > 0) return true;
+        return false;
+    }
+    return h.algorithm != 0 && h.num_contacts > 0;
 }
 
 // One candidate's cast, folded into the thread's running best (smallest fraction, lowest body index among equals).
@@ -255,8 +290,8 @@ k_convex_sweep(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* 
                const CompoundChildDev* __restrict__ children, const float4* __restrict__ sortedMin, int nSorted,
                const float4* __restrict__ cmin, const float4* __restrict__ cmax, int n, const float4* __restrict__ rmin,
                const float4* __restrict__ rmax, const int* __restrict__ castShapes, const float* __restrict__ basis9,
-               const float* __restrict__ sweepFrom, const float* __restrict__ sweepTo, int numSweeps, uint32_t cbFilter,
-               float allowedPenetration, RayOut* __restrict__ out, uint32_t* __restrict__ maxCandidates) {
+               const float* __restrict__ sweepFrom, const float* __restrict__ sweepTo, int numSweeps, uint32_t cbFilterIn,
+               float allowedPenetration, RayOut* __restrict__ out, uint32_t* __restrict__ maxCandidates, SweepNotMe nm) {
     // The candidate set of a sweep has no useful bound (the reference expands every body's box by the cast shape's box
     // INCLUDING its whole linear motion), so it is produced and consumed in rounds: chunk boxes of a range of SWEEP_HIT_CAP
     // chunks -> hit-chunk list; members of as many hit chunks as the candidate list has room for (64 each, worst case) ->
@@ -269,14 +304,32 @@ k_convex_sweep(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* 
     __shared__ int sBestBody[SWEEP_THREADS];
     __shared__ SweepRec sBestRec[SWEEP_THREADS];
     for (int sw = blockIdx.x; sw < numSweeps; sw += gridDim.x) {
+        uint32_t cbFilter = cbFilterIn;
         Xf fromT;
         for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) fromT.m[r][c] = basis9[9 * (size_t)sw + 3 * r + c];
-        fromT.o = mk3(sweepFrom[3 * sw], sweepFrom[3 * sw + 1], sweepFrom[3 * sw + 2]);
-        const f3 from = fromT.o;
+            for (int c = 0; c < 3; c++) fromT.m[r][c] = nm.me ? (r == c ? 1.f : 0.f) : basis9[9 * (size_t)sw + 3 * r + c];
+        fromT.o = nm.me ? mk3(0.f, 0.f, 0.f) : mk3(sweepFrom[3 * sw], sweepFrom[3 * sw + 1], sweepFrom[3 * sw + 2]);
         const f3 to = mk3(sweepTo[3 * sw], sweepTo[3 * sw + 1], sweepTo[3 * sw + 2]);
-        const ShapeDev castS = shapes[castShapes[sw]];
+        const int me = nm.me ? nm.me[sw] : -1;
+        ShapeDev castS;
+        if (nm.me) {   // SphereShape(body.getCcdSweptSphereRadius())
+            castS = ShapeDev{};
+            castS.type = SH_SPHERE;
+            castS.dims[0] = nm.radius[sw];
+            castS.margin = nm.radius[sw];
+        } else {
+            castS = shapes[castShapes[sw]];
+        }
         const AnyS A = anyShapeOf(castS, hullPts);
+        if (nm.me) {   // the body's own transform is the start of the sweep; its filter is the callback's
+            const Xf mt = loadXf(B.xf4, me);
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) fromT.m[r][c] = mt.m[r][c];
+            fromT.o = mt.o;
+            cbFilter = B.filt[me];
+        }
+        const f3 from = fromT.o;
+        const f3 rel = sub3(sub3(to, from), mk3(0.f, 0.f, 0.f));   // linVelA - linVelB
         // calculateTemporalAabb(R, linVel, 0, 1)
         f3 castMin, castMax;
         {
@@ -321,6 +374,7 @@ k_convex_sweep(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* 
                     if (gjkConvexCast(A, fromT, to, shp, cx, allowedPenetration, f, nn, pt)) {
                         if (len2_3(nn) > 0.0001f && f < rec.fraction) {
                             nn = nor3(nn);
+                            if (nm.me && dot3(nn, rel) >= -0.f) return;   // ClosestNotMe...addSingleResult (:1157)
                             valid = true;
                             rec.fraction = f;
                             rec.normal[0] = nn.x; rec.normal[1] = nn.y; rec.normal[2] = nn.z;
@@ -350,7 +404,8 @@ k_convex_sweep(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* 
                     rot.o = mk3(0.f, 0.f, 0.f);
                     f3 boxMin, boxMax;
                     shapeAabb(castS, rot, boxMin, boxMax);
-                    sweepMeshWalk(meshes[s.mesh], A, fromT, to, t, s.margin, xfPoint(inv, from), xfPoint(inv, to), boxMin, boxMax, valid, rec);
+                    sweepMeshWalk(meshes[s.mesh], A, fromT, to, t, s.margin, xfPoint(inv, from), xfPoint(inv, to), boxMin, boxMax, valid, rec, nm.me != nullptr,
+                                  rel);
                 } else if (s.type == SH_PLANE) {
                     sUnsupported = 1;
                 }
@@ -390,7 +445,9 @@ k_convex_sweep(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* 
                     if (i < 0 || i >= n) continue;
                     const float4 mn = __ldg(rmin + i);
                     if (mn.w == 0.f) continue;
+                    if (i == me) continue;                           // ClosestNotMe...needsCollision (:1169)
                     if (!filterPass(cbFilter, B.filt[i])) continue;  // ConvexResultCallback.needsCollision (:752-756)
+                    if (nm.me && sweepAlreadyTouching(nm, B, shapes, me, i)) continue;
                     const float4 mx = __ldg(rmax + i);
                     if (rayAabb(from, to, add3(mk3(mn.x, mn.y, mn.z), castMin), add3(mk3(mx.x, mx.y, mx.z), castMax), 1.f)) {
                         sCand[atomicAdd(&sCount, 1u)] = (uint32_t)i;

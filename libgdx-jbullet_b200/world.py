@@ -270,6 +270,25 @@ class GpuCollisionWorld:
                                                      float(allowed_ccd_penetration), _vp(uid), _vp(frac), _vp(nrm), _vp(pt)))
         return uid, frac, nrm, pt
 
+    def ccdSweepNotMe(self, body_uids, ccd_radius, predicted_origins, allowed_ccd_penetration=0.04):
+        """The CCD motion-clamping sweeps of DiscreteDynamicsWorld.integrateTransforms (dyn/DiscreteDynamicsWorld.java:700-729)
+        for the listed bodies: a sphere of ccd_radius swept from each body's resident transform to its predicted origin with a
+        ClosestNotMeConvexResultCallback.  Returns (hit uid (0 = none), closestHitFraction, normal, point)."""
+        u = np.ascontiguousarray(body_uids, dtype=np.int32).reshape(-1)
+        n = len(u)
+        r = np.full(n, float(ccd_radius), np.float32) if np.isscalar(ccd_radius) else np.ascontiguousarray(ccd_radius, dtype=np.float32)
+        t = np.ascontiguousarray(predicted_origins, dtype=np.float32).reshape(-1, 3)
+        if len(r) != n or len(t) != n:
+            raise ValueError("one radius and one predicted origin per body")
+        uid = np.zeros(n, dtype=np.int32)
+        frac = np.zeros(n, dtype=np.float32)
+        nrm = np.zeros((n, 3), dtype=np.float32)
+        pt = np.zeros((n, 3), dtype=np.float32)
+        if n:
+            self._ck(self.L.b2c_ccd_sweep_not_me(self.h, n, _vp(u), _vp(r), _vp(t), float(allowed_ccd_penetration), _vp(uid), _vp(frac),
+                                                 _vp(nrm), _vp(pt)))
+        return uid, frac, nrm, pt
+
     def setNoCollidePairs(self, pairs):
         """Body pairs linked by a collision-disabling constraint (dynamics/RigidBody.java:624-639): kept in the pair cache,
         never dispatched."""

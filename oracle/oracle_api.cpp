@@ -198,6 +198,18 @@ void orc_convex_sweep_closest(void* h, int n, const int* shapes, const float* ba
         out7[7 * i + 4] = r.point.x; out7[7 * i + 5] = r.point.y; out7[7 * i + 6] = r.point.z;
     }
 }
+// The CCD motion-clamping sweeps of DiscreteDynamicsWorld.integrateTransforms for n bodies: out as orc_convex_sweep_closest
+void orc_ccd_sweep_not_me(void* h, int n, const int* uids, const float* radius, const float* to, float allowedPenetration, int* uidOut,
+                          float* out7) {
+    World* w = (World*)h;
+    for (int i = 0; i < n; i++) {
+        ConvexSweepHit r = w->ccdSweepNotMe(uids[i], radius[i], V3(to[3 * i], to[3 * i + 1], to[3 * i + 2]), allowedPenetration);
+        uidOut[i] = r.unsupported ? -1 : r.uid;
+        out7[7 * i] = r.fraction;
+        out7[7 * i + 1] = r.normal.x; out7[7 * i + 2] = r.normal.y; out7[7 * i + 3] = r.normal.z;
+        out7[7 * i + 4] = r.point.x; out7[7 * i + 5] = r.point.y; out7[7 * i + 6] = r.point.z;
+    }
+}
 int orc_dispatch_all_pairs(void* h) { return ((World*)h)->dispatchAllPairs(); }
 int orc_num_raw(void* h) { return (int)((World*)h)->raw.size(); }
 // raw record: 5 ints (uid0, uid1, tri, hasContact, method) + iters ; 7 floats (normal, point, depth)

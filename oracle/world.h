@@ -463,8 +463,10 @@ struct World {
     }
 
     // disp/CollisionWorld.java:392-551 objectQuerySingle against the running ClosestConvexResultCallback state
+    // notMeVel != null: the callback is DiscreteDynamicsWorld's ClosestNotMeConvexResultCallback (dyn/DiscreteDynamicsWorld.java
+    // :1143-1164), whose addSingleResult drops a result whose normal does not oppose the motion (allowedPenetration 0)
     void objectQuerySingle(const Shape& cast, const Xf& fromT, const Xf& toT, const Body& b, int shapeIndex, const Xf& xf,
-                           float allowedPenetration, ConvexSweepHit& hit) const {
+                           float allowedPenetration, ConvexSweepHit& hit, const V3* notMeVel = nullptr) const {
         const Shape& s = shapes[shapeIndex];
         if (s.isConvex()) {
             ConvexCastResult cr;
@@ -474,6 +476,7 @@ struct World {
                 if (cr.normal.len2() > 0.0001f) {
                     if (cr.fraction < hit.fraction) {
                         cr.normal.nor();
+                        if (notMeVel && cr.normal.dot(*notMeVel) >= -0.f) return;
                         hit.fraction = cr.fraction;           // ClosestConvexResultCallback.addSingleResult, normalInWorldSpace
                         hit.uid = b.uid;
                         hit.normal.set(cr.normal);
@@ -506,6 +509,7 @@ struct World {
                         if (cr.fraction < entry) {
                             cr.normal.nor();
                             if (cr.fraction <= hit.fraction) {   // reportHit: hitFraction <= closestHitFraction
+                                if (notMeVel && cr.normal.dot(*notMeVel) >= -0.f) return;
                                 hit.fraction = cr.fraction;
                                 hit.uid = b.uid;
                                 hit.normal.set(cr.normal);       // normalInWorldSpace = true
@@ -521,7 +525,7 @@ struct World {
             for (const CompoundChild& c : s.children) {
                 Xf childWorld; childWorld.set(xf);
                 childWorld.mul(c.transform);
-                objectQuerySingle(cast, fromT, toT, b, c.shape, childWorld, allowedPenetration, hit);
+                objectQuerySingle(cast, fromT, toT, b, c.shape, childWorld, allowedPenetration, hit, notMeVel);
             }
         }
     }
@@ -554,6 +558,57 @@ struct World {
             V3 hitNormal;
             if (!rayAabb(fromT.origin, toT.origin, mn, mx, hitLambda, hitNormal)) continue;
             objectQuerySingle(cast, fromT, toT, b, b.shape, b.xf, allowedPenetration, hit);
+        }
+        return hit;
+    }
+
+    // DiscreteDynamicsWorld.integrateTransforms' "CCD motion clamping" query (dyn/DiscreteDynamicsWorld.java:700-729): a sphere
+    // of the body's ccdSweptSphereRadius swept from its world transform to the predicted origin, ClosestNotMeConvexResultCallback
+    // (:1129-1199) with the body's own filter group / mask: not the body itself, not an object it already has contact points
+    // with (any manifold of their pair's algorithm), not a hit whose normal does not oppose the motion.  The predicted
+    // ROTATION only enters the reference through the angular term of the culling box (|w| * r * sqrt(3)), taken as 0 here.
+    ConvexSweepHit ccdSweepNotMe(int meUid, float radius, const V3& to, float allowedPenetration) const {
+        ConvexSweepHit hit;
+        const Body& me = bodies[meUid - 1];
+        Shape cast;
+        initSphere(cast, radius);
+        Xf fromT; fromT.set(me.xf);
+        Xf toT; toT.set(me.xf); toT.origin.set(to);
+        Xf R; R.basis.set(fromT.basis); R.origin.set(0, 0, 0);
+        V3 castMin, castMax;
+        shapeGetAabb(cast, R, castMin, castMax);
+        V3 lin; lin.set(toT.origin).sub(fromT.origin);
+        lin.scl(1.f / 1.f);
+        lin.scl(1.f);
+        if (lin.x > 0.f) castMax.x += lin.x; else castMin.x += lin.x;
+        if (lin.y > 0.f) castMax.y += lin.y; else castMin.y += lin.y;
+        if (lin.z > 0.f) castMax.z += lin.z; else castMin.z += lin.z;
+        V3 linVelA; linVelA.set(to).sub(fromT.origin);
+        V3 linVelB(0, 0, 0);
+        V3 rel; rel.set(linVelA).sub(linVelB);
+        const int group = me.group, mask = me.mask;
+        for (const Body& b : bodies) {
+            if (!b.alive) continue;
+            if (b.uid == meUid) continue;                                              // :1169
+            bool collides = ((int)b.group & mask & 0xFFFF) != 0;
+            collides = collides && ((group & (int)b.mask) & 0xFFFF) != 0;
+            if (!collides) continue;
+            {   // :1181-1196 needsResponse (me is dynamic) -> skip objects with contact points already
+                auto it = pairState.find(std::make_pair(std::min(meUid, b.uid), std::max(meUid, b.uid)));
+                if (it != pairState.end() && std::binary_search(pairs.begin(), pairs.end(), it->first)) {
+                    bool touching = it->second.hasManifold && it->second.manifold.cachedPoints > 0;
+                    for (const PairState& k : it->second.kids) touching = touching || (k.hasManifold && k.manifold.cachedPoints > 0);
+                    if (touching) continue;
+                }
+            }
+            V3 mn, mx;
+            shapeGetAabb(shapes[b.shape], b.xf, mn, mx);
+            mn.add(castMin);
+            mx.add(castMax);
+            float hitLambda = 1.f;
+            V3 hitNormal;
+            if (!rayAabb(fromT.origin, toT.origin, mn, mx, hitLambda, hitNormal)) continue;
+            objectQuerySingle(cast, fromT, toT, b, b.shape, b.xf, allowedPenetration, hit, &rel);
         }
         return hit;
     }

@@ -146,7 +146,7 @@ int main(int argc, char** argv) {
         }
         std::vector<RayOut> so(ns); uint32_t sov = 0;
         const uint32_t sFilter = ((uint32_t)(uint16_t)group) | ((uint32_t)(uint16_t)smask << 16);
-        k_convex_sweep(B, shapes.data(), hull.data(), meshes.data(), children.data(), sortedMin.data(), nSorted, cmin.data(), cmax.data(), N, rmin.data(), rmax.data(), castShape.data(), basis.data(), sf.data(), st.data(), ns, sFilter, 0.04f, so.data(), &sov);
+        k_convex_sweep(B, shapes.data(), hull.data(), meshes.data(), children.data(), sortedMin.data(), nSorted, cmin.data(), cmax.data(), N, rmin.data(), rmax.data(), castShape.data(), basis.data(), sf.data(), st.data(), ns, sFilter, 0.04f, so.data(), &sov, SweepNotMe{});
         if (pass == 0 && sov <= 64) { printf("no sweep had more candidates (%u) than fit beside one more chunk (a mid-sweep flush)\n", sov); return 1; }
         for (int r = 0; r < ns; r++) {
             orc::Xf f, t;
@@ -167,6 +167,37 @@ int main(int argc, char** argv) {
         if (pass == 1 && sUnsup == 0) { printf("no sweep reached the static plane branch\n"); return 1; }
     }
     if (overflow <= 12) { printf("no ray met more boxes (%u) than one round holds: the tile path was not exercised\n", overflow); return 1; }
+    // ---- CCD motion-clamping sweeps (ClosestNotMeConvexResultCallback): a sphere swept from every 3rd dynamic body's own
+    // transform; the plane is left out by giving those bodies a mask without group 2 on both sides
+    int cHits = 0;
+    {
+        std::vector<int> me; std::vector<float> rad, cto;
+        for (int i = 2; i < N; i += 3) {
+            me.push_back(i); rad.push_back(uf(0.1f, 0.35f));
+            for (int c = 0; c < 3; c++) cto.push_back(xf4[3 * i + c].w + uf(-2.5f, 2.5f));
+        }
+        const int nc = (int)me.size();
+        std::vector<uint32_t> filtSave = filt;
+        for (int i : me) { filt[i] = (filt[i] & 0xffffu) | ((uint32_t)(uint16_t)(-1 ^ 2) << 16); W.bodies[i].mask = (short)(-1 ^ 2); }
+        B.filt = filt.data();
+        std::vector<RayOut> co(nc); uint32_t cov = 0;
+        SweepNotMe nm{}; nm.me = me.data(); nm.radius = rad.data();
+        k_convex_sweep(B, shapes.data(), hull.data(), meshes.data(), children.data(), sortedMin.data(), nSorted, cmin.data(), cmax.data(), N, rmin.data(), rmax.data(), nullptr, nullptr, nullptr, cto.data(), nc, 0u, 0.04f, co.data(), &cov, nm);
+        for (int r = 0; r < nc; r++) {
+            orc::ConvexSweepHit h = W.ccdSweepNotMe(me[r] + 1, rad[r], orc::V3(cto[3 * r], cto[3 * r + 1], cto[3 * r + 2]), 0.04f);
+            const RayOut& g = co[r];
+            const int huid = h.unsupported ? -1 : h.uid;
+            float of[7] = {h.fraction, h.normal.x, h.normal.y, h.normal.z, h.point.x, h.point.y, h.point.z};
+            float gf[7] = {g.fraction, g.normal[0], g.normal[1], g.normal[2], g.point[0], g.point[1], g.point[2]};
+            if (g.uid != huid || (huid > 0 && memcmp(of, gf, 28)) || (huid == 0 && g.fraction != 1.f) || huid == me[r] + 1) {
+                printf("ccd sweep %d (body %d) differs: uid %d/%d frac %.9g/%.9g\n", r, me[r] + 1, g.uid, huid, g.fraction, h.fraction);
+                return 1;
+            }
+            cHits += huid > 0;
+        }
+        if (cHits < nc / 20) { printf("too few CCD sweeps hit anything (%d of %d)\n", cHits, nc); return 1; }
+        printf("ccd sweeps %d hits %d\n", nc, cHits);
+    }
     printf("ALL OK rays %d hits %d mesh %d plane %d compound %d overflow %u | sweeps %d hits %d mesh %d compound %d unsupported %d\n", NR, hits, hitMesh, hitPlane, hitComp, overflow, NS, sHits, sMesh, sComp, sUnsup);
     return 0;
 }

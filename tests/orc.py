@@ -62,6 +62,7 @@ def lib():
     L.orc_dispatch_all_pairs.argtypes = [C.c_void_p]
     L.orc_ray_test_closest.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_int, i32p, f32p]
     L.orc_convex_sweep_closest.argtypes = [C.c_void_p, C.c_int, i32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, i32p, f32p]
+    L.orc_ccd_sweep_not_me.argtypes = [C.c_void_p, C.c_int, i32p, f32p, f32p, C.c_float, i32p, f32p]
     L.orc_pair_deltas.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, i32p]
     L.orc_islands.argtypes = [C.c_void_p, i32p]
     L.orc_num_raw.argtypes = [C.c_void_p]
@@ -240,6 +241,17 @@ class OracleWorld:
         uid = np.zeros(n, dtype=np.int32)
         out = np.zeros((n, 7), dtype=np.float32)
         self.L.orc_convex_sweep_closest(self.h, n, ids, b, f, t, int(group), int(mask), float(allowed_ccd_penetration), uid, out)
+        return uid, out[:, 0].copy(), out[:, 1:4].copy(), out[:, 4:7].copy()
+
+    def ccd_sweep_not_me(self, body_uids, ccd_radius, predicted_origins, allowed_ccd_penetration=0.04):
+        """DiscreteDynamicsWorld.integrateTransforms' CCD motion-clamping sweep per listed body (ClosestNotMeConvexResultCallback)."""
+        u = np.ascontiguousarray(body_uids, dtype=np.int32).reshape(-1)
+        n = len(u)
+        r = np.full(n, float(ccd_radius), np.float32) if np.isscalar(ccd_radius) else np.ascontiguousarray(ccd_radius, dtype=np.float32)
+        t = np.ascontiguousarray(predicted_origins, dtype=np.float32).reshape(-1, 3)
+        uid = np.zeros(n, dtype=np.int32)
+        out = np.zeros((n, 7), dtype=np.float32)
+        self.L.orc_ccd_sweep_not_me(self.h, n, u, r, t, float(allowed_ccd_penetration), uid, out)
         return uid, out[:, 0].copy(), out[:, 1:4].copy(), out[:, 4:7].copy()
 
     def dispatch_all_pairs(self):

@@ -173,3 +173,37 @@ def test_sweeps_against_a_multi_part_mesh(gpu_pkg):
     so = np.full(n, ow.scene_shape_ids[casts[2]], np.int32)
     gu = _compare(gw, ow, sg, so, basis, f, t)
     assert (gu == 1).sum() > 150
+
+
+def test_ccd_motion_clamping_sweeps(gpu_pkg):
+    """b2c_ccd_sweep_not_me == the oracle's DiscreteDynamicsWorld.integrateTransforms CCD query (ClosestNotMeConvexResult-
+    Callback: not the body itself, not objects it already touches, not results whose normal follows the motion), after a real
+    step so that the pair cache and its manifolds exist — bin of mixed shapes, and compounds / convex bodies on a terrain mesh."""
+    rng = np.random.default_rng(41)
+    for sc, mode in ((scenes.bin_scene(n=2500, seed=54), 1), (scenes.terrain_compound_scene(cells=32, n=150, seed=16), 1)):
+        gw, ow = scenes.build_both(gpu_pkg, sc, mode=mode)
+        for step in range(2):
+            xf = sc.transforms(step)
+            gw.setWorldTransforms(xf); gw.step()
+            ow.step(xf)
+        dyn = np.asarray([k + 1 for k in range(sc.n) if not sc.static[k]], np.int32)
+        me = rng.choice(dyn, size=min(400, len(dyn)), replace=False).astype(np.int32)
+        radius = rng.uniform(0.1, 0.3, size=len(me)).astype(np.float32)
+        to = (xf[me - 1, 9:] + rng.uniform(-2.0, 2.0, size=(len(me), 3))).astype(np.float32)
+        to[::2, 1] = xf[me[::2] - 1, 10] - rng.uniform(0.5, 3.0, size=len(me[::2])).astype(np.float32)   # half of them downwards
+        gu, gf, gn, gp = gw.ccdSweepNotMe(me, radius, to)
+        ou, of, on, op = ow.ccd_sweep_not_me(me, radius, to)
+        assert np.array_equal(gu, ou), f"hit bodies differ: {np.nonzero(gu != ou)[0][:8]} gpu {gu[gu != ou][:8]} oracle {ou[gu != ou][:8]}"
+        assert np.array_equal(gf.view(np.uint32), of.view(np.uint32))
+        hit = gu > 0
+        assert np.array_equal(gn[hit].view(np.uint32), on[hit].view(np.uint32)) and np.array_equal(gp[hit].view(np.uint32), op[hit].view(np.uint32))
+        assert hit.sum() > 40 and not (gu == me).any()
+        # the exclusion of touching objects matters: without the pair cache (fresh worlds, no step) more sweeps report a hit
+        g2, o2 = scenes.build_both(gpu_pkg, sc, mode=mode)
+        g2.setWorldTransforms(xf); o2.set_transforms(xf)
+        hu, hf, _, _ = g2.ccdSweepNotMe(me, radius, to)
+        pu, pf, _, _ = o2.ccd_sweep_not_me(me, radius, to)
+        assert np.array_equal(hu, pu) and np.array_equal(hf.view(np.uint32), pf.view(np.uint32))
+        assert (hu > 0).sum() >= hit.sum()
+    with pytest.raises(Exception):
+        gw.ccdSweepNotMe([10 ** 6], 0.2, [(0, 0, 0)])

@@ -82,3 +82,34 @@ def test_rotated_box_cast_uses_its_basis():
     uid, frac, _, _ = w.convex_sweep_closest(cast, [EYE, rot], [(0, 5, 0), (1, 5, 0)], [(0, -5, 0), (1, -5, 0)])
     assert uid.tolist() == [1, 1]
     assert abs(frac[0] - 0.45) < 2e-3 and abs(frac[1] - (5 - np.sqrt(0.5)) / 10) < 3e-3
+
+
+def test_ccd_motion_clamping_sweep_skips_me_and_touching_objects():
+    """DiscreteDynamicsWorld.integrateTransforms' CCD query (dyn/DiscreteDynamicsWorld.java:700-729, 1129-1199)."""
+    w = orc.OracleWorld(mode=orc.DBVT)
+    ground = w.box(20, 0.5, 20)
+    ball = w.sphere(0.5)
+    wall = w.box(0.25, 3, 3)
+    w.body(ground, orc.xf12(origin=(0, -0.5, 0)), 2, -1 ^ 2, True, 0)          # uid 1, top at y = 0
+    w.body(ball, orc.xf12(origin=(0, 0.49, 0)), 1, -1, False, 0)               # uid 2, resting on the ground (touching)
+    w.body(wall, orc.xf12(origin=(5, 3, 0)), 2, -1 ^ 2, True, 0)               # uid 3, face at x = 4.75
+    w.body(ball, orc.xf12(origin=(0, 6, 0)), 1, -1, False, 0)                  # uid 4, free in the air
+    xf = np.stack([orc.xf12(origin=(0, -0.5, 0)), orc.xf12(origin=(0, 0.49, 0)), orc.xf12(origin=(5, 3, 0)), orc.xf12(origin=(0, 6, 0))])
+    w.step(xf)
+    # body 2 flies at the wall: swept sphere of radius 0.2 from x = 0 to x = 10 meets the face at x = 4.75 - 0.2;
+    # the ground it rests on (contact points already) is not reported although the sweep grazes it
+    uid, frac, nrm, _ = w.ccd_sweep_not_me([2], 0.2, [(10, 0.49, 0)])
+    assert uid[0] == 3 and abs(frac[0] - 4.55 / 10) < 2e-3 and nrm[0][0] < -0.99
+    # straight down: the only thing below is the ground, which is excluded -> no hit, full motion allowed
+    uid, frac, _, _ = w.ccd_sweep_not_me([2], 0.2, [(0, -3, 0)])
+    assert uid[0] == 0 and frac[0] == 1.0
+    # body 4 falls onto body 2 (not touching anything yet): top of the ball at y = 0.99
+    uid, frac, nrm, _ = w.ccd_sweep_not_me([4], 0.2, [(0, -4, 0)])
+    assert uid[0] == 2 and abs(frac[0] - (6 - 0.99 - 0.2) / 10) < 2e-3 and nrm[0][1] > 0.99
+    # moving away from everything: nothing
+    uid, _, _, _ = w.ccd_sweep_not_me([4], 0.2, [(0, 16, 0)])
+    assert uid[0] == 0
+    # the plain sweep of the same sphere from body 2's place does see the ground it rests on... unless it starts in contact
+    s02 = w.sphere(0.2)
+    uid, _, _, _ = w.convex_sweep_closest(s02, EYE, [(0, 2.0, 0)], [(0, -3, 0)])
+    assert uid[0] == 2 or uid[0] == 1
