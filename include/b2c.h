@@ -106,12 +106,16 @@ typedef struct {
 int32_t b2c_shape_register_mesh_parts(b2c_ctx*, const b2c_indexed_mesh* parts, int32_t num_parts, const float scaling[3],
                                       int32_t* shape_out);
 /* sh/CompoundShape.java:50-82: new CompoundShape() followed by addChildShape(localTransform_i, child_i) for i = 0..n-1.
- * child_shapes = ids of box / sphere / hull shapes registered before; child_transforms12 = n x (9 row-major basis floats +
- * origin).  The local AABB is the running Math.min / Math.max of the children's AABBs (:60-80), collisionMargin stays 0 (:49).
+ * child_shapes = ids of box / sphere / hull shapes — or of COMPOUND shapes — registered before; child_transforms12 = n x
+ * (9 row-major basis floats + origin).  The local AABB is the running Math.min / Math.max of the children's AABBs (:60-80;
+ * a nested compound counts with CompoundShape.getAabb of its own local box), collisionMargin stays 0 (:49).
  * Pairs with a compound on either side run disp/CompoundCollisionAlgorithm.java:83-129: one child algorithm and one
  * PersistentManifold per child (per child x child for two compounds), reported by b2c_get_manifolds / b2c_get_contacts with
- * the child indices.  The other object may be a box, sphere, hull, static plane, triangle mesh (ConvexConcave per child) or
- * another compound.  Not built: compound children that are themselves compounds or concave, compounds in a partitioned world. */
+ * the child indices.  A child that is itself a compound gets the reference's nested CompoundCollisionAlgorithm: its leaves
+ * are visited depth first with world transforms composed level by level, ((orgTrans * childTrans) * grandChildTrans) ...,
+ * and the child index reported is the leaf's position in that depth-first order.  At most 4 compound levels above a leaf,
+ * at most 32767 leaves.  The other object may be a box, sphere, hull, static plane, triangle mesh (ConvexConcave per leaf)
+ * or another compound.  Not built: concave children, compounds in a partitioned world. */
 int32_t b2c_shape_register_compound(b2c_ctx*, int32_t num_children, const int32_t* child_shapes, const float* child_transforms12,
                                     int32_t* shape_out);
 /* Debug/inspection: copy the quantized BVH (16-byte nodes, sh/QuantizedBvhNodes.java:34-48) */

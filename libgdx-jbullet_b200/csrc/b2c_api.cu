@@ -23,6 +23,7 @@
 #include "pairfind.cuh"
 #include "radix_sort.cuh"
 #include "raycast.cuh"
+#include "compound_flatten.h"
 #include "convexcast.cuh"
 
 using namespace b2c;
@@ -210,6 +211,7 @@ struct b2c_ctx {
     // compound shapes (compound.cuh) — buffers are allocated when the first one is registered
     bool hasCompound = false;
     std::vector<CompoundChildDev> hChildren;
+    std::vector<std::vector<CompoundDirectChild>> compoundDirect;   // per shape id: the addChildShape calls of a compound (else empty)
     CompoundChildDev* dChildren = nullptr;
     size_t capChildren = 0;
     uint32_t maxCompoundItems = 0;
@@ -1429,8 +1431,8 @@ int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* chil
     for (int i = 0; i < n; i++) {
         if (childShapes[i] < 0 || childShapes[i] >= (int)ctx->hShapes.size()) return B2C_ERR_BAD_HANDLE;
         const int t = ctx->hShapes[childShapes[i]].type;
-        if (t != SH_BOX && t != SH_SPHERE && t != SH_HULL) {
-            ctx->err = "compound children must be box, sphere or convex hull shapes";
+        if (t != SH_BOX && t != SH_SPHERE && t != SH_HULL && t != SH_COMPOUND) {
+            ctx->err = "compound children must be box, sphere, convex hull or compound shapes";
             return B2C_ERR_BAD_ARG;
         }
     }
@@ -1454,7 +1456,31 @@ int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* chil
             CK(dalloc(&ctx->dCP[i], 4 * M));
         }
     }
-    const int first = (int)ctx->hChildren.size();
+    // the table gets this compound's frames and leaves (compound_flatten.h); behind them, for the AABB kernel below only, its
+    // DIRECT children (a nested compound counts with its own local AABB, sh/CompoundShape.java:60-80)
+    std::vector<CompoundDirectChild> direct((size_t)n);
+    for (int i = 0; i < n; i++) {
+        direct[(size_t)i].shape = childShapes[i];
+        for (int k = 0; k < 12; k++) direct[(size_t)i].xf12[k] = childXf12[12 * i + k];
+    }
+    int first = 0, numLeaves = 0;
+    const size_t tableBefore = ctx->hChildren.size();
+    if (!flattenCompound(ctx->hChildren, direct,
+                         [&](int sid) -> const std::vector<CompoundDirectChild>* {
+                             return (sid < (int)ctx->compoundDirect.size() && !ctx->compoundDirect[(size_t)sid].empty()) ? &ctx->compoundDirect[(size_t)sid] : nullptr;
+                         },
+                         first, numLeaves)) {
+        ctx->hChildren.resize(tableBefore);
+        ctx->err = "compound shapes nested deeper than 4 levels";
+        return B2C_ERR_CAPACITY;
+    }
+    if (numLeaves < 1 || numLeaves > 32767) {
+        ctx->hChildren.resize(tableBefore);
+        ctx->err = "a compound must have between 1 and 32767 leaf shapes";
+        return B2C_ERR_BAD_ARG;
+    }
+    const size_t tableAfter = ctx->hChildren.size();
+    const int firstDirect = (int)tableAfter;
     for (int i = 0; i < n; i++) {
         CompoundChildDev ch{};
         for (int k = 0; k < 9; k++) ch.m[k] = childXf12[12 * i + k];
@@ -1477,21 +1503,28 @@ int32_t b2c_shape_register_compound(b2c_ctx* ctx, int32_t n, const int32_t* chil
     float* d6 = nullptr;
     float h6[6];
     CK(cudaMalloc((void**)&d6, 6 * sizeof(float)));
-    k_compound_local_aabb<<<1, 1, 0, ctx->stream>>>(ctx->dShapes, ctx->dChildren, first, n, d6);
+    k_compound_local_aabb<<<1, 1, 0, ctx->stream>>>(ctx->dShapes, ctx->dChildren, firstDirect, n, d6);
     cudaError_t ce = cudaMemcpyAsync(h6, d6, sizeof(h6), cudaMemcpyDeviceToHost, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     cudaFree(d6);
+    ctx->hChildren.resize(tableAfter);   // the direct-children scratch entries go again
     CK(ce);
     ShapeDev s{};
     s.type = SH_COMPOUND;
     s.margin = 0.f;  // sh/CompoundShape.java:49 collisionMargin
     for (int c = 0; c < 3; c++) { s.aabbMin[c] = h6[c]; s.aabbMax[c] = h6[3 + c]; }
     s.pointOffset = first;
-    s.numPoints = n;
+    s.numPoints = numLeaves;
     ctx->hasCompound = true;
     int32_t rcs = ensureCompoundMeshScratch(ctx);
     if (rcs) return rcs;
-    return addShape(ctx, s, out);
+    int32_t sid = -1;
+    int32_t rca = addShape(ctx, s, &sid);
+    if (rca) return rca;
+    if ((int)ctx->compoundDirect.size() <= sid) ctx->compoundDirect.resize((size_t)sid + 1);
+    ctx->compoundDirect[(size_t)sid] = direct;
+    if (out) *out = sid;
+    return B2C_OK;
 }
 int32_t b2c_mesh_get_bvh(b2c_ctx* ctx, int32_t shape, void* nodesOut, int32_t cap, int32_t* numNodes, float quant9[9]) {
     if (!ctx || shape < 0 || shape >= (int)ctx->hShapes.size() || ctx->hShapes[shape].type != SH_MESH) return B2C_ERR_BAD_HANDLE;

@@ -116,18 +116,42 @@ struct ShapeDev {
 };
 
 // One child of a CompoundShape (sh/CompoundShapeChild.java:34-39): local transform + child shape id.  64 B.
+// A compound's entries in the child table are its LEAVES (box / sphere / hull) in the depth-first order in which
+// CompoundCollisionAlgorithm visits them; a child that is itself a CompoundShape contributes its own leaves, each chained
+// (parent1) to a FRAME entry that holds the nested compound's local transform, so that a leaf's world transform is composed
+// exactly as the reference's recursion does: ((orgTrans * frame) * ...) * childTrans (disp/CompoundCollisionAlgorithm.java:107).
 struct CompoundChildDev {
     float m[9];          // childTransform basis, row-major
     float o[3];          // childTransform origin
-    int shape;           // index into the shape table (box, sphere or hull)
-    int pad[3];
+    int shape;           // index into the shape table (box, sphere or hull); -1: a frame entry (a nested compound's transform)
+    int parent1;         // 1 + index of the frame entry this entry hangs under, 0 = directly under the compound
+    int pad[2];
 };
+constexpr int COMPOUND_MAX_DEPTH = 4;   // frames above a leaf (nesting depth 5)
 // Transform.mul(tr1, tr2) (lm/Transform.java:122-131): origin = tr1.transform(tr2.origin), basis = tr1.basis * tr2.basis
 __host__ __device__ __forceinline__ Xf mulXf(const Xf& a, const Xf& b) {
     Xf r;
     r.o = xfPoint(a, b.o);
     mulMM(a.m, b.m, r.m);
     return r;
+}
+__host__ __device__ __forceinline__ Xf compoundChildLocal(const CompoundChildDev& ch) {
+    Xf l;
+    l.m[0][0] = ch.m[0]; l.m[0][1] = ch.m[1]; l.m[0][2] = ch.m[2];
+    l.m[1][0] = ch.m[3]; l.m[1][1] = ch.m[4]; l.m[1][2] = ch.m[5];
+    l.m[2][0] = ch.m[6]; l.m[2][1] = ch.m[7]; l.m[2][2] = ch.m[8];
+    l.o = mk3(ch.o[0], ch.o[1], ch.o[2]);
+    return l;
+}
+// world transform of a compound's leaf under the object's transform `org`: the frames from the outermost down, then the leaf
+__host__ __device__ __forceinline__ Xf compoundChildWorld(const Xf& org, const CompoundChildDev* table, const CompoundChildDev& leaf) {
+    if (leaf.parent1 == 0) return mulXf(org, compoundChildLocal(leaf));
+    int chain[COMPOUND_MAX_DEPTH];
+    int d = 0;
+    for (int p = leaf.parent1; p > 0 && d < COMPOUND_MAX_DEPTH; p = table[p - 1].parent1) chain[d++] = p - 1;
+    Xf w = org;
+    for (int k = d - 1; k >= 0; k--) w = mulXf(w, compoundChildLocal(table[chain[k]]));
+    return mulXf(w, compoundChildLocal(leaf));
 }
 
 // One registered triangle mesh with its quantized BVH (sh/OptimizedBvh.java, sh/QuantizedBvhNodes.java).

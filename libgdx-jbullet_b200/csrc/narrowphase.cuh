@@ -785,13 +785,8 @@ __device__ __forceinline__ void decodeCompoundItem(const NpArgs& a, const Compou
     const Xf t0 = loadXf(a.xf4, b0), t1 = loadXf(a.xf4, b1);
     auto childXf = [&](const ShapeDev& S, int i, const Xf& org, int& shapeOut) {
         const CompoundChildDev& ch = c.children[S.pointOffset + i];
-        Xf l;
-        l.m[0][0] = ch.m[0]; l.m[0][1] = ch.m[1]; l.m[0][2] = ch.m[2];
-        l.m[1][0] = ch.m[3]; l.m[1][1] = ch.m[4]; l.m[1][2] = ch.m[5];
-        l.m[2][0] = ch.m[6]; l.m[2][1] = ch.m[7]; l.m[2][2] = ch.m[8];
-        l.o = mk3(ch.o[0], ch.o[1], ch.o[2]);
         shapeOut = ch.shape;
-        return mulXf(org, l);  // newChildWorldTrans.mul(orgTrans, childTrans) (disp/CompoundCollisionAlgorithm.java:107)
+        return compoundChildWorld(org, c.children, ch);  // newChildWorldTrans.mul(orgTrans, childTrans) (disp/CompoundCollisionAlgorithm.java:107), per nesting level
     };
     if (c0 && c1) {
         const int n1 = S1.numPoints;

@@ -364,12 +364,7 @@ k_ray_test(BodyArrays B, const ShapeDev* __restrict__ shapes, const float4* __re
             } else if (s.type == SH_COMPOUND) {  // :333-352: the children in order, each against the bound its predecessors left
                 for (int ch = 0; ch < s.numPoints; ch++) {
                     const CompoundChildDev& cd = children[s.pointOffset + ch];
-                    Xf l;
-                    l.m[0][0] = cd.m[0]; l.m[0][1] = cd.m[1]; l.m[0][2] = cd.m[2];
-                    l.m[1][0] = cd.m[3]; l.m[1][1] = cd.m[4]; l.m[1][2] = cd.m[5];
-                    l.m[2][0] = cd.m[6]; l.m[2][1] = cd.m[7]; l.m[2][2] = cd.m[8];
-                    l.o = mk3(cd.o[0], cd.o[1], cd.o[2]);
-                    castConvex(shapes[cd.shape], mulXf(t, l), fr);
+                    castConvex(shapes[cd.shape], compoundChildWorld(t, children, cd), fr);
                 }
             } else {  // :301-331: static plane / triangle mesh in the object's local space
                 Xf inv;  // Transform.inverse (lm/Transform.java:101-105)

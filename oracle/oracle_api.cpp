@@ -79,7 +79,9 @@ int orc_shape_plane(void* h, float nx, float ny, float nz, float c) {
 int orc_shape_compound(void* h, int n, const int* childShapes, const float* childXf12) {
     World* w = (World*)h;
     for (int i = 0; i < n; i++) {
-        if (childShapes[i] < 0 || childShapes[i] >= (int)w->shapes.size() || !w->shapes[childShapes[i]].isConvex()) return -1;
+        if (childShapes[i] < 0 || childShapes[i] >= (int)w->shapes.size()) return -1;
+        const Shape& c = w->shapes[childShapes[i]];
+        if (!c.isConvex() && !c.isCompound()) return -1;   // a child may itself be a CompoundShape
     }
     return w->addCompound(n, childShapes, childXf12);
 }

@@ -129,7 +129,8 @@ struct World {
         return (int)shapes.size() - 1;
     }
     // sh/CompoundShape.java:50-82 addChildShape for every child: the local AABB is the running Math.min / Math.max of the
-    // children's AABBs under their local transforms.  Children must be convex here (box, sphere, hull).
+    // children's AABBs under their local transforms.  Children are convex (box, sphere, hull) or compounds themselves (their
+    // box is then CompoundShape.getAabb of the nested shape under the child transform).
     int addCompound(int n, const int* childShapes, const float* childXf12) {
         Shape s;
         s.type = SH_COMPOUND;
@@ -794,21 +795,40 @@ struct World {
     // carrying the child's shape and orgTrans * childTrans; contact points are still projected with the original transforms
     // (res keeps rootTransA / rootTransB of the pair's two objects).  `other` may itself be a compound: its child algorithm is
     // then the swapped compound algorithm over ITS children, against this child (:57-75 init -> findAlgorithm).
+    // A child that is itself a CompoundShape gets a nested (never swapped: the compound comes first in findAlgorithm's
+    // arguments, disp/DefaultCollisionConfiguration.java:198-200) CompoundCollisionAlgorithm whose colObj carries
+    // orgTrans * childTrans as its world transform, so the LEAVES are visited depth first with transforms composed level by
+    // level.  leaf(shape, worldTransform, index of the leaf in that depth-first order)
+    template <class F>
+    void visitCompoundLeaves(const Shape& cs, const Xf& org, int& leafIndex, F leaf) const {
+        for (size_t i = 0; i < cs.children.size(); i++) {
+            Xf childWorld;
+            childWorld.set(org);
+            childWorld.mul(cs.children[i].transform);  // newChildWorldTrans.mul(orgTrans, childTrans) (lm/Transform.java:122-131)
+            const Shape& child = shapes[cs.children[i].shape];
+            if (child.isCompound()) visitCompoundLeaves(child, childWorld, leafIndex, leaf);
+            else leaf(&child, childWorld, leafIndex++);
+        }
+    }
     void compoundProcess(const Body& colObj, const Body& otherObj, const Shape* otherShape, int otherChild, ManifoldResult& res,
                          PairState& ps, int& k) {
         const Shape& cs = shapes[colObj.shape];
-        for (size_t i = 0; i < cs.children.size(); i++) {
+        int li = 0;
+        visitCompoundLeaves(cs, colObj.xf, li, [&](const Shape* childShape, const Xf& childWorld, int i) {
             Body tmp = colObj;                 // colObj.setWorldTransform(newChildWorldTrans)
-            tmp.xf.set(colObj.xf);
-            tmp.xf.mul(cs.children[i].transform);  // newChildWorldTrans.mul(orgTrans, childTrans) (lm/Transform.java:122-131)
-            const Shape* childShape = &shapes[cs.children[i].shape];
+            tmp.xf.set(childWorld);
             if (otherShape->isCompound()) {
-                // algorithm(child i of colObj, compound other) = swapped CompoundCollisionAlgorithm: its colObj is `other`
-                compoundProcess(otherObj, tmp, childShape, (int)i, res, ps, k);
+                // algorithm(leaf i of colObj, compound other) = swapped CompoundCollisionAlgorithm: its colObj is `other`
+                int lj = 0;
+                visitCompoundLeaves(*otherShape, otherObj.xf, lj, [&](const Shape* oShape, const Xf& oWorld, int j) {
+                    Body tmpO = otherObj;
+                    tmpO.xf.set(oWorld);
+                    compoundLeaf(oShape, j, tmpO, childShape, i, tmp, res, ps, k);
+                });
             } else {
-                compoundLeaf(childShape, (int)i, tmp, otherShape, otherChild, otherObj, res, ps, k);
+                compoundLeaf(childShape, i, tmp, otherShape, otherChild, otherObj, res, ps, k);
             }
-        }
+        });
     }
 
     // Dispatcher.dispatchAllCollisionPairs over the current pair set.  Returns number of manifolds.

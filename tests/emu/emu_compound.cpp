@@ -12,6 +12,7 @@
 #include "cuda_runtime.h"
 #include "../../oracle/world.h"
 #include "../../libgdx-jbullet_b200/csrc/compound.cuh"
+#include "../../libgdx-jbullet_b200/csrc/compound_flatten.h"
 
 namespace b2c { alignas(16) unsigned char epaSmem[2 * sizeof(EpaScratch)]; }
 
@@ -66,8 +67,19 @@ struct Sc {
         s.plane[0] = W.shapes.back().planeNormal.x; s.plane[1] = W.shapes.back().planeNormal.y; s.plane[2] = W.shapes.back().planeNormal.z; s.plane[3] = c;
         shapes.push_back(s); return (int)shapes.size() - 1;
     }
+    std::vector<std::vector<CompoundDirectChild>> directOfShape;   // per shape id, as b2c_api.cu keeps it
     int addCompound(const std::vector<int>& kids, const std::vector<float>& xf12) {
         int sid = W.addCompound((int)kids.size(), kids.data(), xf12.data());
+        // the same table b2c_shape_register_compound builds: frames + leaves (compound_flatten.h), then the direct children as
+        // scratch entries for the local-AABB kernel
+        std::vector<CompoundDirectChild> direct(kids.size());
+        for (size_t i = 0; i < kids.size(); i++) { direct[i].shape = kids[i]; for (int k = 0; k < 12; k++) direct[i].xf12[k] = xf12[12 * i + k]; }
+        int firstLeaf = 0, numLeaves = 0;
+        if (!flattenCompound(children, direct, [&](int sh) -> const std::vector<CompoundDirectChild>* {
+                return (sh < (int)directOfShape.size() && !directOfShape[sh].empty()) ? &directOfShape[sh] : nullptr; }, firstLeaf, numLeaves)) {
+            printf("compound nesting too deep\n"); exit(1);
+        }
+        const size_t keep = children.size();
         int first = (int)children.size();
         for (size_t i = 0; i < kids.size(); i++) {
             CompoundChildDev ch{};
@@ -81,8 +93,11 @@ struct Sc {
         k_compound_local_aabb(shapes.data(), children.data(), first, (int)kids.size(), out6);
         ShapeDev s{}; s.type = SH_COMPOUND; s.margin = 0;
         for (int c = 0; c < 3; c++) { s.aabbMin[c] = out6[c]; s.aabbMax[c] = out6[3 + c]; }
-        s.pointOffset = first; s.numPoints = (int)kids.size();
+        children.resize(keep);
+        s.pointOffset = firstLeaf; s.numPoints = numLeaves;
         shapes.push_back(s);
+        if (directOfShape.size() < shapes.size()) directOfShape.resize(shapes.size());
+        directOfShape[shapes.size() - 1] = direct;
         const orc::Shape& os = W.shapes[sid];
         float o6[6] = {os.localAabbMin.x, os.localAabbMin.y, os.localAabbMin.z, os.localAabbMax.x, os.localAabbMax.y, os.localAabbMax.z};
         if (memcmp(o6, out6, 24)) { printf("compound local AABB differs\n"); exit(1); }
@@ -136,6 +151,10 @@ int main(int argc, char** argv) {
     { std::vector<float> x(24); randRot(x.data()); x[9] = -0.2f; x[10] = 0; x[11] = 0.1f; randRot(x.data() + 12); x[21] = 0.3f; x[22] = 0.1f; x[23] = -0.1f; comps.push_back(sc.addCompound({hl, sSmall}, x)); }
     { std::vector<float> x; app(x, idXf(0, 0, 0)); app(x, {0, -1, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0}); app(x, {0, 0, 1, 0, 1, 0, -1, 0, 0, 0, 0, 0}); comps.push_back(sc.addCompound({bar, bar, bar}, x)); }
     { std::vector<float> x; app(x, idXf(0, 0.2f, 0)); comps.push_back(sc.addCompound({sBig}, x)); }
+    // nested: children that are CompoundShapes themselves (one and two levels), with rotated frames
+    { std::vector<float> x(24); randRot(x.data()); x[9] = 0.1f; x[10] = 0.35f; x[11] = 0; randRot(x.data() + 12); x[21] = -0.1f; x[22] = -0.3f; x[23] = 0.05f; comps.push_back(sc.addCompound({comps[0], post}, x)); }
+    { std::vector<float> x(24); randRot(x.data()); x[9] = 0; x[10] = 0.2f; x[11] = 0.1f; randRot(x.data() + 12); x[21] = 0.2f; x[22] = -0.4f; x[23] = 0; comps.push_back(sc.addCompound({comps[5], sSmall}, x)); }
+    { std::vector<float> x; app(x, idXf(0, 0, 0)); comps.push_back(sc.addCompound({comps[2]}, x)); }   // identity frame around compound 2
     std::vector<int> plain = {sSmall, sBig, hl, hl2, bx, bar};
     // bodies
     std::vector<int> bodyShape;

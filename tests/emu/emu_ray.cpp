@@ -18,6 +18,7 @@
 #include "../../libgdx-jbullet_b200/csrc/compound.cuh"
 #include "../../libgdx-jbullet_b200/csrc/raycast.cuh"
 #include "../../libgdx-jbullet_b200/csrc/convexcast.cuh"
+#include "../../libgdx-jbullet_b200/csrc/compound_flatten.h"
 namespace b2c { alignas(16) unsigned char epaSmem[2 * sizeof(EpaScratch)]; }
 using namespace b2c;
 static std::mt19937 rng(777);
@@ -52,13 +53,20 @@ int main(int argc, char** argv) {
     auto plane = [&](float nx, float ny, float nz, float c) { W.shapes.emplace_back(); W.meshes.emplace_back(nullptr); orc::initPlane(W.shapes.back(), orc::V3(nx, ny, nz), c);
         ShapeDev s{}; s.type = SH_PLANE; s.plane[0] = W.shapes.back().planeNormal.x; s.plane[1] = W.shapes.back().planeNormal.y; s.plane[2] = W.shapes.back().planeNormal.z; s.plane[3] = c;
         shapes.push_back(s); return (int)shapes.size() - 1; };
+    std::vector<std::vector<CompoundDirectChild>> directOfShape;
     auto compound = [&](const std::vector<int>& kids, const std::vector<float>& xf) { int sid = W.addCompound((int)kids.size(), kids.data(), xf.data());
-        ShapeDev s{}; s.type = SH_COMPOUND; s.pointOffset = (int)children.size(); s.numPoints = (int)kids.size();
-        for (size_t i = 0; i < kids.size(); i++) { CompoundChildDev ch{}; for (int k = 0; k < 9; k++) ch.m[k] = xf[12 * i + k]; for (int k = 0; k < 3; k++) ch.o[k] = xf[12 * i + 9 + k]; ch.shape = kids[i]; children.push_back(ch); }
+        std::vector<CompoundDirectChild> direct(kids.size());
+        for (size_t i = 0; i < kids.size(); i++) { direct[i].shape = kids[i]; for (int k = 0; k < 12; k++) direct[i].xf12[k] = xf[12 * i + k]; }
+        int firstLeaf = 0, numLeaves = 0;
+        flattenCompound(children, direct, [&](int sh) -> const std::vector<CompoundDirectChild>* { return (sh < (int)directOfShape.size() && !directOfShape[sh].empty()) ? &directOfShape[sh] : nullptr; }, firstLeaf, numLeaves);
+        ShapeDev s{}; s.type = SH_COMPOUND; s.pointOffset = firstLeaf; s.numPoints = numLeaves;
         const orc::Shape& os = W.shapes[sid];
         s.aabbMin[0] = os.localAabbMin.x; s.aabbMin[1] = os.localAabbMin.y; s.aabbMin[2] = os.localAabbMin.z;
         s.aabbMax[0] = os.localAabbMax.x; s.aabbMax[1] = os.localAabbMax.y; s.aabbMax[2] = os.localAabbMax.z;
-        shapes.push_back(s); return (int)shapes.size() - 1; };
+        shapes.push_back(s);
+        if (directOfShape.size() < shapes.size()) directOfShape.resize(shapes.size());
+        directOfShape[shapes.size() - 1] = direct;
+        return (int)shapes.size() - 1; };
     // heightfield mesh 24x24 cells over [0,12]^2
     const int C = 24; std::vector<float> verts; std::vector<int> idx;
     for (int i = 0; i <= C; i++) for (int j = 0; j <= C; j++) { verts.push_back(i * 0.5f); verts.push_back(0.6f * sinf(i * 0.7f) * cosf(j * 0.5f) + uf(-0.05f, 0.05f)); verts.push_back(j * 0.5f); }
@@ -79,7 +87,12 @@ int main(int argc, char** argv) {
     int c1 = compound({sS, bar, sB}, x3);
     std::vector<float> x2(24); randRot(x2.data()); x2[9] = -0.2f; x2[10] = 0.1f; x2[11] = 0; randRot(x2.data() + 12); x2[21] = 0.3f; x2[22] = 0; x2[23] = 0.2f;
     int c2 = compound({hl, bx}, x2);
-    std::vector<int> kinds = {sS, sB, bx, bar, hl, c1, c2};
+    // a compound whose children are compounds (rotated frames, two levels): rays and sweeps visit its leaves depth first
+    std::vector<float> x4(24); randRot(x4.data()); x4[9] = 0.2f; x4[10] = 0.3f; x4[11] = 0; randRot(x4.data() + 12); x4[21] = -0.3f; x4[22] = -0.2f; x4[23] = 0.1f;
+    int c3 = compound({c1, c2}, x4);
+    std::vector<float> x5(24); randRot(x5.data()); x5[9] = 0; x5[10] = 0.4f; x5[11] = 0; randRot(x5.data() + 12); x5[21] = 0.1f; x5[22] = -0.5f; x5[23] = 0;
+    int c4 = compound({c3, bar}, x5);
+    std::vector<int> kinds = {sS, sB, bx, bar, hl, c1, c2, c3, c4};
     std::vector<int> bodyShape; std::vector<float4> xf4; std::vector<uint32_t> filt; std::vector<uint8_t> flags;
     auto addBody = [&](int shape, const float* t, int group, int mask) {
         orc::Xf x; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) x.basis.m[r][c] = t[3 * r + c]; x.origin.set(t[9], t[10], t[11]);

@@ -295,7 +295,7 @@ def spheres_scene(n=20000, seed=6, radius=0.5, fill=0.40):
     return sc
 
 
-def compound_scene(n=300, seed=8, plane_ground=True, spacing=0.9, compound_share=0.5):
+def compound_scene(n=300, seed=8, plane_ground=True, spacing=0.9, compound_share=0.5, nested=False):
     """compounds (dumbbells, L-brackets, hull+sphere clusters, three-box crosses) mixed with plain boxes,
     spheres and hulls on a jittered lattice over a static plane (or box) floor, close enough that compound x {sphere, box,
     hull, plane / static box, compound} pairs all occur, some of them penetrating."""
@@ -328,6 +328,16 @@ def compound_scene(n=300, seed=8, plane_ground=True, spacing=0.9, compound_share
                                                       [(0, 0, 0), (0, 0, 0), (0, 0, 0)])),                                  # 3-axis cross
         sc.add_shape("compound", [s_big], cxf([eye], [(0.0, 0.2, 0.0)])),                                                 # single offset child
     ]
+    if nested == "identity":
+        # every compound wrapped in an outer compound with an identity child transform: the same leaves, the same floats
+        compounds = [sc.add_shape("compound", [c], cxf([eye], [(0.0, 0.0, 0.0)])) for c in compounds]
+    elif nested:
+        # children that are CompoundShapes themselves (sh/CompoundShape.java accepts any CollisionShape), one and two levels
+        r1, r2, r3 = small_rotation(rng, 3, 0.9)
+        n1 = sc.add_shape("compound", [compounds[0], post], cxf([r1, eye], [(0.1, 0.35, 0.0), (-0.1, -0.3, 0.05)]))
+        n2 = sc.add_shape("compound", [n1, s_small], cxf([r2, eye], [(0.0, 0.2, 0.1), (0.2, -0.4, 0.0)]))
+        n3 = sc.add_shape("compound", [compounds[2], compounds[1]], cxf([r3, r1], [(-0.2, 0.0, 0.0), (0.25, 0.1, 0.0)]))
+        compounds = compounds + [n1, n2, n3, n2, n3]
     plain = [sc.add_shape("box", tuple(rng.uniform(0.25, 0.45, size=3))) for _ in range(4)]
     plain += [s_small, s_big, hl, sc.add_shape("hull", hull_points(rng, 0.4))]
     m = max(2, int(np.ceil(n ** (1.0 / 3.0))))

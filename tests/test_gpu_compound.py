@@ -117,8 +117,9 @@ def test_compound_registered_after_first_steps_and_capacity(gpu_pkg):
     with pytest.raises(gpu_pkg.B2CError) as e:
         gw.performDiscreteCollisionDetection()
     assert e.value.code == -3
-    with pytest.raises(gpu_pkg.B2CError):          # children must be convex
-        gw.CompoundShape([c], np.stack([xf((0, 0, 0))]))
+    pl = gw.StaticPlaneShape((0.0, 1.0, 0.0), 0.0)
+    with pytest.raises(gpu_pkg.B2CError):          # children must be convex shapes or compounds
+        gw.CompoundShape([pl], np.stack([xf((0, 0, 0))]))
 
 
 def test_compounds_on_a_triangle_mesh(gpu_pkg):
@@ -135,3 +136,58 @@ def test_compounds_on_a_triangle_mesh(gpu_pkg):
         assert gw.getDispatcher().getNumManifolds() == len(m)
         assert gw.stats()["epa_failed"] == 0
     assert kid_mesh.sum() > 150 and touching > 100
+
+
+def test_nested_compounds_parity(gpu_pkg):
+    """Children that are CompoundShapes themselves: the leaves are visited depth first with transforms composed level by level
+    ((org * frame) * child), as the reference's nested CompoundCollisionAlgorithms do — AABBs, pairs, one raw record and one
+    manifold per leaf combination, bit for bit against the oracle; rays and sweeps through them too."""
+    sc = scenes.compound_scene(n=260, seed=9, plane_ground=False, nested=True)
+    gw, ow = scenes.build_both(gpu_pkg, sc, mode=1, max_pairs=1 << 15)
+    kids = 0
+    for step in range(5):
+        parity.step_and_compare(gw, ow, sc.transforms(step), sc.extent)
+        m = gw.manifolds()
+        kids += int((m["child0"] >= 0).sum())
+        assert int(m["child0"].max()) >= 4, "the two-level compound has 5 leaves, more than any flat one of the scene"
+        assert gw.getDispatcher().getNumManifolds() == len(m) == len(ow.manifolds()[0])
+    assert kids > 3000
+    rng = np.random.default_rng(2)
+    ext = float(sc.extent)
+    f = rng.uniform(-1.0, ext, size=(400, 3)).astype(np.float32); f[:, 1] = rng.uniform(2.0, 8.0, size=400)
+    t = rng.uniform(-1.0, ext, size=(400, 3)).astype(np.float32); t[:, 1] = rng.uniform(-1.0, 1.0, size=400)
+    gu, gf, gn, gp = gw.rayTestClosest(f, t)
+    ou, of, on, op = ow.ray_test_closest(f, t)
+    assert np.array_equal(gu, ou) and np.array_equal(gf.view(np.uint32), of.view(np.uint32)) and (gu > 0).sum() > 200
+    cast = gw.SphereShape(0.2), ow.sphere(0.2)
+    eye = np.eye(3, dtype=np.float32)
+    su, sf, _, sp = gw.convexSweepTestClosest(cast[0], eye, f, t, 1, 1)
+    qu, qf, _, qp = ow.convex_sweep_closest(cast[1], eye, f, t, 1, 1)
+    assert np.array_equal(su, qu) and np.array_equal(sf.view(np.uint32), qf.view(np.uint32)) and np.array_equal(sp.view(np.uint32), qp.view(np.uint32))
+
+
+def test_identity_wrapped_compounds_equal_flat_ones(gpu_pkg):
+    """An outer compound with ONE child at the identity transform changes nothing: multiplying by the identity is exact in
+    binary32, so pairs, AABBs and every contact bit must equal the flat scene's — a check that does not involve the oracle."""
+    flat = scenes.compound_scene(n=200, seed=10, plane_ground=True)
+    wrap = scenes.compound_scene(n=200, seed=10, plane_ground=True, nested="identity")
+    assert np.array_equal(flat.base, wrap.base)
+    g0 = scenes.build_gpu(gpu_pkg, flat, mode=1)
+    g1 = scenes.build_gpu(gpu_pkg, wrap, mode=1)
+    for step in range(4):
+        for g, sc in ((g0, flat), (g1, wrap)):
+            g.setWorldTransforms(sc.transforms(step)); g.step()
+        assert np.array_equal(g0.pairs(), g1.pairs())
+        m0, m1 = g0.manifolds(), g1.manifolds()
+        assert m0.tobytes() == m1.tobytes()
+    assert len(m0) > 500
+
+
+def test_compound_nesting_depth_is_limited(gpu_pkg):
+    gw = gpu_pkg.GpuCollisionWorld(mode=1, max_bodies=16, max_pairs=64)
+    sid = gw.SphereShape(0.2)
+    xf = scenes.make_xf(np.eye(3)[None], np.zeros((1, 3)))
+    for level in range(5):                       # leaf -> 5 compounds around it = 4 frames above the leaf: still fine
+        sid = gw.CompoundShape([sid], xf)
+    with pytest.raises(Exception, match="nested deeper"):
+        gw.CompoundShape([sid], xf)

@@ -125,3 +125,44 @@ def test_compound_manifolds_persist_and_die_with_the_pair():
     c = ow.counters()
     assert c["gjk_checks"] > 0 and c["added_contacts"] > 0
     assert counts[-1] > 0
+
+
+def test_nested_compounds_in_the_oracle():
+    """A child that is a CompoundShape: (1) wrapped at the identity it changes no bit (multiplying by the identity is exact);
+    (2) with a real frame transform, every leaf sits where ((org * frame) * child) puts it — checked against a flat compound
+    whose child transforms were composed in float64 and rounded, contact points within 1e-5."""
+    import scenes
+    flat = scenes.compound_scene(n=120, seed=11, plane_ground=True)
+    wrap = scenes.compound_scene(n=120, seed=11, plane_ground=True, nested="identity")
+    w0 = scenes.build_oracle(flat, orc.DBVT)
+    w1 = scenes.build_oracle(wrap, orc.DBVT)
+    for step in range(3):
+        p0 = w0.step(flat.transforms(step))
+        p1 = w1.step(wrap.transforms(step))
+        assert np.array_equal(p0, p1)
+        (h0, f0, i0), (h1, f1, i1) = w0.manifolds(), w1.manifolds()
+        assert np.array_equal(h0, h1) and f0.tobytes() == f1.tobytes() and np.array_equal(i0, i1)
+    assert len(h0) > 300
+    # (2) one nested body above a ground box: dumbbell inside a rotated, shifted frame
+    w = orc.OracleWorld(mode=orc.TIGHT)
+    wf = orc.OracleWorld(mode=orc.TIGHT)
+    c, s = np.cos(0.6), np.sin(0.6)
+    R = np.asarray([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    frame_o = np.asarray([0.1, 0.3, -0.2])
+    offs = [np.asarray([-0.5, 0, 0]), np.asarray([0.5, 0, 0])]
+    for world, nested in ((w, True), (wf, False)):
+        g = world.box(10, 0.5, 10)
+        sp = world.sphere(0.3)
+        world.body(g, orc.xf12(origin=(0, -0.5, 0)), 2, -1 ^ 2, True, 0)
+        if nested:
+            inner = world.compound([sp, sp], np.stack([_xf(tuple(o)) for o in offs]))
+            outer = world.compound([inner], np.stack([orc.xf12(R, frame_o)]))
+        else:
+            outer = world.compound([sp, sp], np.stack([orc.xf12(R, frame_o + R @ o) for o in offs]))
+        world.body(outer, orc.xf12(origin=(0, 0.25, 0)), 1, -1, False, 0)
+    xf = np.stack([orc.xf12(origin=(0, -0.5, 0)), orc.xf12(origin=(0, 0.25, 0))])
+    w.step(xf); wf.step(xf)
+    (h, f, _), (hf, ff, _) = w.manifolds(), wf.manifolds()
+    assert np.array_equal(h[:, :5], hf[:, :5]) and h[:, 4].sum() >= 1
+    live = np.arange(4)[None, :] < h[:, 4][:, None]
+    assert np.allclose(f[live], ff[live], atol=1e-5)
