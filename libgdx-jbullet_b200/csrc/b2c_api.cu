@@ -54,7 +54,7 @@ struct b2c_ctx {
     cudaEvent_t evPairsReady = nullptr;   // recorded on `stream` when the broadphase of the current step is enqueued
     cudaStream_t streamClosed = nullptr;  // sphere-sphere / convex-plane bins, beside the GJK kernels
     cudaStream_t streamEpa = nullptr;     // penetration bin (few long-latency lanes), beside k_manifold_cc; high priority
-    cudaEvent_t evFork[4] = {nullptr, nullptr, nullptr, nullptr}, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evFork[4] = {nullptr, nullptr, nullptr, nullptr}, evJoin[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool overlap = true;
     int mccBlocks = 8;                    // k_manifold_cc blocks per SM (B2C_MCC_BLOCKS)
     int epaLpw = 8;                       // active lanes per warp in the shared-memory EPA tier (B2C_EPA_LPW: 32/16/8/4)
@@ -152,6 +152,7 @@ struct b2c_ctx {
     EpaItem* dEpaItems = nullptr;
     uint32_t maxEpa = 0;
     uint32_t* dEpaRetry = nullptr;
+    uint32_t* dEpaBig = nullptr;      // items routed straight to the large-pool tier (capacity maxEpaRetry)
     uint32_t maxEpaRetry = 0;
     uint32_t* dMeshPair = nullptr;
     int* dMeshTri = nullptr;
@@ -374,7 +375,7 @@ __global__ void k_get_aabbs(BodyArrays B, int n, float* out) {
 __global__ void k_clear_np_counters(StepCounters* c) {
     if (threadIdx.x == 0) {
         c->contactsAdded = c->gjkChecks = c->deepChecks = c->epaFailed = 0;
-        c->meshItems = c->meshOverflow = c->epaCount = c->epaRetry = 0;
+        c->meshItems = c->meshOverflow = c->epaCount = c->epaRetry = c->epaBig = 0;
     }
     if (threadIdx.x < 16) c->binCount[threadIdx.x] = 0;
 }
@@ -666,6 +667,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     g.epaItems = ctx->dEpaItems;
     g.maxEpa = ctx->maxEpa;
     g.epaRetry = ctx->dEpaRetry;
+    g.epaBig = ctx->dEpaBig;
     g.maxEpaRetry = ctx->maxEpaRetry;
     g.meshPair = ctx->dMeshPair;
     g.meshTri = ctx->dMeshTri;
@@ -748,6 +750,13 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     {
         const int smem1 = (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch);
         k_epa<1><<<EPA_GRID2, EPA_BLOCK2, smem1, se>>>(a, g, 0, 32);  // retry tier + the manifolds of the whole bin
+        // the items whose pair overflowed the small pools before (epaRoute) run in the large-pool tier from the start, on a
+        // third stream beside the two kernels above — at C3 this halves the penetration chain (tier 0, THEN tier 1 for ~20 items)
+        cudaStream_t sp = ctx->overlap ? ctx->streamClosed : se;
+        if (ctx->overlap) CK(cudaStreamWaitEvent(sp, ctx->evFork[1], 0));
+        k_epa<1><<<EPA_GRID2, EPA_BLOCK2, smem1, sp>>>(a, g, 1, 32);
+        if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[4], sp));
+        ctx->launches++;
     }
     if (ctx->timeline) cudaEventRecord(ctx->tl[2], se);
     if (ctx->overlap) CK(cudaEventRecord(ctx->evJoin[1], se));
@@ -769,6 +778,7 @@ int32_t enqueueNarrowphase(b2c_ctx* ctx) {
     if (ctx->overlap) {
         CK(cudaStreamWaitEvent(s, ctx->evJoin[1], 0));
         CK(cudaStreamWaitEvent(s, ctx->evJoin[0], 0));
+        CK(cudaStreamWaitEvent(s, ctx->evJoin[4], 0));
     }
     if (ctx->hasMesh) { k_mesh_manifold<<<148 * 4, 128, 0, s>>>(a, g); ctx->launches++; }
     if (ctx->hasCompound) {
@@ -1060,10 +1070,8 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
         CKC(cudaEventCreateWithFlags(&ctx->evPairsReady, cudaEventDisableTiming));
         CKC(cudaStreamCreateWithPriority(&ctx->streamClosed, cudaStreamNonBlocking, prLo));
         CKC(cudaStreamCreateWithPriority(&ctx->streamEpa, cudaStreamNonBlocking, prHi));
-        for (int i = 0; i < 4; i++) {
-            CKC(cudaEventCreateWithFlags(&ctx->evFork[i], cudaEventDisableTiming));
-            CKC(cudaEventCreateWithFlags(&ctx->evJoin[i], cudaEventDisableTiming));
-        }
+        for (int i = 0; i < 4; i++) CKC(cudaEventCreateWithFlags(&ctx->evFork[i], cudaEventDisableTiming));
+        for (int i = 0; i < 5; i++) CKC(cudaEventCreateWithFlags(&ctx->evJoin[i], cudaEventDisableTiming));
         // one-time kernel attributes (kept out of the per-step path so that it can be captured into a graph)
         cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPA_BLOCK * EPA_SMALL_STRIDE);
         cudaFuncSetAttribute(k_epa<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (EPA_BLOCK2 / 32) * (int)sizeof(EpaScratch));
@@ -1168,6 +1176,7 @@ int32_t b2c_create(const b2c_config* cfg, b2c_ctx** out) {
     CKC(dalloc(&ctx->dEpaItems, (size_t)ctx->maxEpa));
     ctx->maxEpaRetry = ctx->maxEpa;
     CKC(dalloc(&ctx->dEpaRetry, (size_t)ctx->maxEpaRetry));
+    CKC(dalloc(&ctx->dEpaBig, (size_t)ctx->maxEpaRetry));
     const size_t MI = (size_t)(cfg->max_mesh_items > 0 ? cfg->max_mesh_items : 1);
     CKC(dalloc(&ctx->dMeshPair, MI));
     CKC(dalloc(&ctx->dMeshTri, MI));
@@ -1215,7 +1224,7 @@ void b2c_destroy(b2c_ctx* ctx) {
     ctx->sortBodies.destroy();
     cudaFree(ctx->dPairKeys); cudaFree(ctx->dCsr); cudaFree(ctx->dBigRows);
     cudaFree(ctx->dPairs); cudaFree(ctx->dRaw); cudaFree(ctx->dRawFlag); cudaFree(ctx->dBinOf); cudaFree(ctx->dHist); cudaFree(ctx->dBinItems); cudaFree(ctx->dBinStart); cudaFree(ctx->dExportCount); cudaFree(ctx->dSurvivors); cudaFree(ctx->dSurvSorted); cudaFree(ctx->dSurvKey); cudaFree(ctx->dSurvStart);
-    cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dMeshPair);
+    cudaFree(ctx->dEpaItems); cudaFree(ctx->dEpaRetry); cudaFree(ctx->dEpaBig); cudaFree(ctx->dMeshPair);
     cudaFree(ctx->dMeshTri); cudaFree(ctx->dRawMesh); cudaFree(ctx->dMeshStart); cudaFree(ctx->dMeshCount);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i <= B2C_NUM_STAGES; i++) if (ctx->stageEv[i]) cudaEventDestroy(ctx->stageEv[i]);
@@ -1228,10 +1237,8 @@ void b2c_destroy(b2c_ctx* ctx) {
     cudaFree(ctx->dCRaw); cudaFree(ctx->dCMeshStart); cudaFree(ctx->dCMeshCount); cudaFree(ctx->dCBigScratch);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->dCH[i]); cudaFree(ctx->dCP[i]); }
     cudaFree(ctx->dIslandPar); cudaFree(ctx->dIslandTags); cudaFree(ctx->dDelta[0]); cudaFree(ctx->dDelta[1]); cudaFree(ctx->dDeltaCounts);
-    for (int i = 0; i < 4; i++) {
-        if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
-        if (ctx->evJoin[i]) cudaEventDestroy(ctx->evJoin[i]);
-    }
+    for (int i = 0; i < 4; i++) if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
+    for (int i = 0; i < 5; i++) if (ctx->evJoin[i]) cudaEventDestroy(ctx->evJoin[i]);
     if (ctx->streamCopy) { cudaStreamSynchronize(ctx->streamCopy); cudaStreamDestroy(ctx->streamCopy); }
     if (ctx->evPairsReady) cudaEventDestroy(ctx->evPairsReady);
     if (ctx->evContactsEarly) cudaEventDestroy(ctx->evContactsEarly);

@@ -210,7 +210,8 @@ struct StepCounters {
     uint32_t keysTicket;        // last-block election in k_keys (fused radix histograms -> digit offsets)
     uint32_t haloOverflow;      // partitioned world: a halo slot was too small
     uint32_t maxRowLen;         // longest grid row of this step (row-grouped ordering, pairfind.cuh)
-    uint32_t pad[6];
+    uint32_t epaBig;            // penetration items sent straight to the large-pool tier (their pair overflowed the small pools before)
+    uint32_t pad[5];
 };
 
 // monotone float <-> uint key (total order matching float compare for non-NaN; -0 canonicalised to +0)

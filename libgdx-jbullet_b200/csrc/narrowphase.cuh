@@ -405,7 +405,10 @@ k_carry(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ numPairs
             }
             int4* dst = reinterpret_cast<int4*>(H + p);   // adjacent lanes -> adjacent 32-byte headers
             dst[0] = h0; dst[1] = h1;
-            hist[p] = (uint8_t)(h1.z > 15 ? 15 : (h1.z < 0 ? 0 : h1.z));  // header word pad0 = last step's GJK iteration count
+            {   // header word pad0 = last step's GJK iteration count | HDR_EPA_BIG
+                const int trips = h1.y == 5 ? 0 : (h1.z & 0xff);
+                hist[p] = (uint8_t)((trips > 15 ? 15 : trips) | ((h1.y != 5 && (h1.z & 0x100)) ? 0x80 : 0));
+            }
         }
         uint32_t cm = __ballot_sync(0xffffffffu, carriedManifold);
         if (lane == 0 && cm) atomicAdd(&ctr->numManifolds, (uint32_t)__popc(cm));
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(256) k_classify(NpArgs a) {
             if (t0 == SH_SPHERE && t1 == SH_SPHERE) bin = BIN_SS;
             else if ((isConvexType(t0) && t1 == SH_PLANE) || (isConvexType(t1) && t0 == SH_PLANE)) bin = BIN_CP;
             else if (isConvexType(t0) && isConvexType(t1))
-                bin = (a.hist[p] >= 2 ? BIN_PS0 : BIN_GJK0) + (t0 == SH_HULL ? 2 : 0) + (t1 == SH_HULL ? 1 : 0);
+                bin = ((a.hist[p] & 0x7f) >= 2 ? BIN_PS0 : BIN_GJK0) + (t0 == SH_HULL ? 2 : 0) + (t1 == SH_HULL ? 1 : 0);
             else if ((isConvexType(t0) && t1 == SH_MESH) || (isConvexType(t1) && t0 == SH_MESH)) bin = BIN_MESH;
             else if (compoundPairSupported(t0, t1)) bin = BIN_COMPOUND;  // disp/DefaultCollisionConfiguration.java:198-204
         } else if (a.hasCompound) {
@@ -817,11 +820,17 @@ struct EpaItem {        // a pair (or pair/triangle) whose detector asked for th
     GjkResult g;
 };
 
+// Temporal coherence of the penetration bin: a pair whose item overflowed the small EPA pools keeps doing so while it stays
+// in deep contact.  The pair remembers it (bit 8 of its manifold header word pad0; k_carry hands it to hist[] bit 7), and its
+// items go straight to the large-pool tier, which then runs BESIDE the small-pool tier instead of after it.
+constexpr int HDR_EPA_BIG = 0x100;      // ManifoldHdr.pad0 (bits 0-7: last step's GJK trip count)
+constexpr uint8_t HIST_EPA_BIG = 0x80;  // NpArgs.hist[] (bits 0-6: trip count clamped to 15)
 struct GjkArgs {
     EpaItem* epaItems;
     uint32_t maxEpa;
     uint32_t* epaRetry;      // items whose small pool overflowed
     uint32_t maxEpaRetry;
+    uint32_t* epaBig;        // items predicted to need the large pools (capacity maxEpaRetry)
     // mesh work items
     uint32_t* meshPair;      // [maxMeshItems] pair index
     int* meshTri;            // [maxMeshItems] triangle index
@@ -831,6 +840,10 @@ struct GjkArgs {
     uint32_t maxMeshItems;
     CompoundArgs comp;       // compound child work items (EpaItem.meshItem <= -2 names item -2 - meshItem)
 };
+
+// The pair word of a new penetration item: an item of a pair that overflowed the small pools before also goes on the
+// large-pool list and carries EPA_RETRY_BIT, so the small-pool tier leaves it alone.
+__device__ __forceinline__ uint32_t epaRoute(const NpArgs& a, const GjkArgs& g, uint32_t p, uint32_t slot, bool big);
 
 // A lane's convex shape, chosen at run time inside ONE code path (the whole bin shares the loop body; only
 // the support mapping switches), so the instruction footprint stays small and every warp runs the same loop.
@@ -920,7 +933,7 @@ k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict
         if (it >= mid && it < e0) {
             p = binItem(a, it);
             survive = true;
-            const int last = a.hist[p];
+            const int last = a.hist[p] & 0x7f;
             key = last >= 15 ? 0u : (uint32_t)(15 - last);  // longest first
         } else if (it < mid) {
             p = binItem(a, it);
@@ -1047,13 +1060,14 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
                 GjkResult r;
                 L.finish(r);
                 busy = false;
-                a.mhdr[p].pad0 = r.curIter;  // next step's ordering key (k_gjk_prefilter); travels with the manifold
+                const bool big = (a.hist[p] & HIST_EPA_BIG) != 0;
+                a.mhdr[p].pad0 = (r.curIter > 255 ? 255 : r.curIter) | (big ? HDR_EPA_BIG : 0);  // next step's ordering key (k_gjk_prefilter); travels with the manifold
                 bool queued = false;
                 if (r.needEpa) {
                     deep++;
                     uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
                     if (slot < g.maxEpa) {
-                        g.epaItems[slot].pair = p;
+                        g.epaItems[slot].pair = epaRoute(a, g, p, slot, big);
                         g.epaItems[slot].meshItem = -1;
                         g.epaItems[slot].g = r;
                         a.raw[p].has_contact = -2;  // pending in the penetration bin
@@ -1298,7 +1312,7 @@ __global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g, uint32_t* 
                     deep++;
                     uint32_t slot = atomicAdd(&a.ctr->epaCount, 1u);
                     if (slot < g.maxEpa) {
-                        g.epaItems[slot].pair = p;
+                        g.epaItems[slot].pair = epaRoute(a, g, p, slot, (a.hist[p] & HIST_EPA_BIG) != 0);
                         g.epaItems[slot].meshItem = (int)item;
                         g.epaItems[slot].g = r;
                         rw->has_contact = -2;  // pending
@@ -1330,7 +1344,14 @@ __global__ void __launch_bounds__(128) k_gjk_tri(NpArgs a, GjkArgs g, uint32_t* 
 //           there = EPA failed, like the reference's EPA_Failed).
 constexpr uint32_t EPA_SMEM_LANES = 148u * 2u * 32u;
 
-constexpr uint32_t EPA_RETRY_BIT = 0x80000000u;  // set in EpaItem.pair while the item waits for the retry tier
+constexpr uint32_t EPA_RETRY_BIT = 0x80000000u;  // set in EpaItem.pair while the item waits for (or belongs to) the large-pool tier
+__device__ __forceinline__ uint32_t epaRoute(const NpArgs& a, const GjkArgs& g, uint32_t p, uint32_t slot, bool big) {
+    if (!big) return p;
+    const uint32_t k = atomicAdd(&a.ctr->epaBig, 1u);
+    if (k >= g.maxEpaRetry) return p;   // list full: an ordinary item (it will overflow and be retried as before)
+    g.epaBig[k] = slot;
+    return p | EPA_RETRY_BIT;
+}
 
 template <int TIER>
 __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs g, int solo, int lpw) {
@@ -1341,7 +1362,10 @@ __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs 
         if (!solo && TIER == 0 && nItems > EPA_SMEM_LANES) return;
         if (!solo && TIER == 2 && nItems <= EPA_SMEM_LANES) return;
     } else {
-        nItems = a.ctr->epaRetry < g.maxEpaRetry ? a.ctr->epaRetry : g.maxEpaRetry;
+        // TIER 1 runs twice: solo = 1 over the PREDICTED list, beside the small-pool tier; solo = 0 afterwards over the items
+        // that overflowed there, followed by the manifold side of the whole bin
+        const uint32_t cnt = solo ? a.ctr->epaBig : a.ctr->epaRetry;
+        nItems = cnt < g.maxEpaRetry ? cnt : g.maxEpaRetry;
     }
     uint32_t failed = 0;
     extern __shared__ __align__(16) unsigned char epaSmem[];
@@ -1358,8 +1382,9 @@ __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs 
                            : ((threadIdx.x & 31) == 0 ? blockIdx.x * warpsPerBlock + (threadIdx.x >> 5) : 0xffffffffu);
     const uint32_t itStep = TIER == 2 ? step : TIER == 0 ? gridDim.x * 32u : gridDim.x * warpsPerBlock;
     for (uint32_t it0 = itFirst; it0 < nItems; it0 += itStep) {
-        const uint32_t it = TIER != 1 ? it0 : g.epaRetry[it0];
+        const uint32_t it = TIER != 1 ? it0 : (solo ? g.epaBig[it0] : g.epaRetry[it0]);
         EpaItem item = g.epaItems[it];
+        if (TIER != 1 && (item.pair & EPA_RETRY_BIT)) continue;   // the large-pool tier has it (epaRoute)
         uint32_t p = item.pair & ~EPA_RETRY_BIT;
         int2 pr = a.pairs[p];
         int b0 = pr.x - 1, b1 = pr.y - 1;
@@ -1409,7 +1434,12 @@ __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs 
         if (TIER != 1) {
             if (poolOverflow) {
                 uint32_t slot = atomicAdd(&a.ctr->epaRetry, 1u);
-                if (slot < g.maxEpaRetry) { g.epaRetry[slot] = it; g.epaItems[it].pair = p | EPA_RETRY_BIT; continue; }
+                if (slot < g.maxEpaRetry) {
+                    g.epaRetry[slot] = it;
+                    g.epaItems[it].pair = p | EPA_RETRY_BIT;
+                    if (item.meshItem > -2) atomicOr(&a.mhdr[p].pad0, HDR_EPA_BIG);   // remembered by the pair (not by compound pairs: their pad0 is a counter flag)
+                    continue;
+                }
                 epaFail = true;  // retry list full: report as failure below
             }
         } else {
@@ -1453,7 +1483,7 @@ __global__ void __launch_bounds__(TIER == 0 ? 256 : 64) k_epa(NpArgs a, GjkArgs 
         }
     }
     if (failed) atomicAdd(&a.ctr->epaFailed, failed);
-    if (TIER == 1) {
+    if (TIER == 1 && !solo) {
         // manifold side of every convex-convex pair that went through the penetration bin (ConvexConvexAlgorithm,
         // disp/ConvexConvexAlgorithm.java:92-139); retried items were done above, (pair, triangle) items are folded by
         // k_mesh_manifold

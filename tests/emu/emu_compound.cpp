@@ -188,7 +188,7 @@ int main(int argc, char** argv) {
     std::vector<float2> material(NB, make_float2(0.5f, 0.0f));
     const uint32_t MAXI = 1 << 18;
     std::vector<uint32_t> itemPair(MAXI), itemCode(MAXI);
-    std::vector<EpaItem> epaItems(MAXI); std::vector<uint32_t> epaRetry(MAXI);
+    std::vector<EpaItem> epaItems(MAXI); std::vector<uint32_t> epaRetry(MAXI), epaBig(MAXI);
     std::vector<int> itemPrev(MAXI);
     std::vector<b2c_raw_contact> craw(MAXI), rawMesh(MAXI);
     std::vector<uint32_t> cMeshStart(MAXI), cMeshCount(MAXI);
@@ -253,12 +253,13 @@ int main(int argc, char** argv) {
         blockIdx = {0, 0, 0}; threadIdx = {0, 0, 0}; blockDim = {1, 1, 1}; gridDim = {1, 1, 1};
         GjkArgs g{};
         g.rawMesh = rawMesh.data(); g.maxMeshItems = MAXI;
-        g.epaItems = epaItems.data(); g.maxEpa = MAXI; g.epaRetry = epaRetry.data(); g.maxEpaRetry = MAXI; g.comp = c;
+        g.epaItems = epaItems.data(); g.maxEpa = MAXI; g.epaRetry = epaRetry.data(); g.maxEpaRetry = MAXI; g.epaBig = epaBig.data(); g.comp = c;
         uint32_t cursor = 0;
         k_compound_expand(a, c);
         k_compound_gjk(a, g, &cursor);
         k_epa<2>(a, g, 1, 32);
         blockDim = {32, 1, 1};
+        for (unsigned t = 0; t < 32; t++) { threadIdx.x = t; k_epa<1>(a, g, 1, 32); }   // items routed straight to the large pools
         for (unsigned t = 0; t < 32; t++) { threadIdx.x = t; k_epa<1>(a, g, 0, 32); }
         threadIdx.x = 0;
         blockDim = {1, 1, 1};

@@ -167,11 +167,11 @@ int main(int argc, char** argv) {
     std::vector<b2c_raw_contact> raw(MAXP), rawMesh(MAXI);
     std::vector<int8_t> rawFlag(MAXP);
     std::vector<uint8_t> hist(MAXP), binOf(MAXP);
-    std::vector<uint32_t> binItems(MAXP), meshPair(MAXI), meshStart(MAXP), meshCount(MAXP), epaRetry(MAXI);
+    std::vector<uint32_t> binItems(MAXP), meshPair(MAXI), meshStart(MAXP), meshCount(MAXP), epaRetry(MAXI), epaBig(MAXI);
     std::vector<int> meshTri(MAXI);
     std::vector<EpaItem> epaItems(MAXI);
     StepCounters ctr{};
-    long totRaw = 0, totPts = 0, totDeep = 0, totMesh = 0, totRetry = 0;
+    long totRaw = 0, totPts = 0, totDeep = 0, totMesh = 0, totRetry = 0, totBig = 0;
     for (int step = 0; step < STEPS; step++) {
         for (int b = 0; b < NB; b++) {
             orc::Body& B = sc.W.bodies[b];
@@ -224,7 +224,7 @@ int main(int argc, char** argv) {
         a.raw = raw.data(); a.rawFlag = rawFlag.data(); a.hist = hist.data(); a.binOf = binOf.data(); a.binItems = binItems.data(); a.binStart = binStart;
         a.ctr = &ctr; a.threshold = 0.02f; a.maxPairs = MAXP; a.uidBits = uidBits;
         GjkArgs g{};
-        g.epaItems = epaItems.data(); g.maxEpa = MAXI; g.epaRetry = epaRetry.data(); g.maxEpaRetry = MAXI;
+        g.epaItems = epaItems.data(); g.maxEpa = MAXI; g.epaRetry = epaRetry.data(); g.maxEpaRetry = MAXI; g.epaBig = epaBig.data();
         g.meshPair = meshPair.data(); g.meshTri = meshTri.data(); g.rawMesh = rawMesh.data(); g.meshStart = meshStart.data(); g.meshCount = meshCount.data();
         g.maxMeshItems = MAXI;
         k_sphere_sphere(a);
@@ -239,12 +239,13 @@ int main(int argc, char** argv) {
         k_gjk_tri(a, g, &cursorTri);
         k_epa<2>(a, g, 1, 32);
         blockDim = {32, 1, 1};
+        for (unsigned t = 0; t < 32; t++) { threadIdx.x = t; k_epa<1>(a, g, 1, 32); }   // items routed straight to the large pools
         for (unsigned t = 0; t < 32; t++) { threadIdx.x = t; k_epa<1>(a, g, 0, 32); }
         threadIdx.x = 0;
         blockDim = {1, 1, 1};
         k_manifold_cc(a);
         k_mesh_manifold(a, g);
-        totDeep += ctr.deepChecks; totMesh += ctr.meshItems; totRetry += ctr.epaRetry;
+        totDeep += ctr.deepChecks; totMesh += ctr.meshItems; totRetry += ctr.epaRetry; totBig += ctr.epaBig;
         // ---- compare raw records
         std::map<std::tuple<int, int, int>, const orc::RawContact*> oraw;
         for (auto& r : sc.W.raw) oraw[std::make_tuple(r.uid0, r.uid1, r.tri)] = &r;
@@ -302,6 +303,6 @@ int main(int argc, char** argv) {
         if ((long)ctr.numManifolds != oracleManifolds) { printf("step %d: numManifolds %u vs oracle %ld\n", step, ctr.numManifolds, oracleManifolds); return 1; }
         printf("step %d ok: pairs %u raw %zu manifolds %ld deep %u mesh items %u contactsAdded %u\n", step, Pn, seen, oracleManifolds, ctr.deepChecks, ctr.meshItems, ctr.contactsAdded);
     }
-    printf("ALL OK raw %ld points %ld deep %ld mesh items %ld retries %ld\n", totRaw, totPts, totDeep, totMesh, totRetry);
+    printf("ALL OK raw %ld points %ld deep %ld mesh items %ld retries %ld routed-to-large-pools %ld\n", totRaw, totPts, totDeep, totMesh, totRetry, totBig);
     return 0;
 }
