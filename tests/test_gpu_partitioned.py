@@ -149,6 +149,25 @@ def test_peer_to_peer_halo_needs_a_connection(gpu_pkg):
         w.mgpu_p2p_export_halo()
 
 
+def test_a_peer_that_never_publishes_is_reported(gpu_pkg):
+    """Failure detection of the peer-to-peer exchange: rank 0 waits for rank 1's epoch flag, rank 1 never exports; after ~3 s
+    the wait gives up and the step's counters come back as an error instead of a hang."""
+    sc = scenes.spheres_scene(n=2000, seed=5)
+    ranks = [scenes.build_gpu(gpu_pkg, sc, mode=1) for _ in range(2)]
+    for r, w in enumerate(ranks):
+        w.set_partition(r, 2)
+    inboxes = [w.mgpu_p2p_init(4096, 256)[1] for w in ranks]
+    for w in ranks:
+        w.mgpu_p2p_connect(inbox_ptrs=inboxes)
+    w0 = ranks[0]
+    w0.setWorldTransforms(sc.transforms(0))
+    w0.mgpu_p2p_export_halo()
+    w0.mgpu_p2p_import_halo()          # rank 1 stays silent
+    w0.mgpu_broadphase()
+    with pytest.raises(gpu_pkg.B2CError, match="timed out"):
+        w0.sync_counts()
+
+
 def test_slab_ownership_and_halo_size(gpu_pkg):
     """Explicit planes: proxies are owned by the slab their origin lies in, only boundary proxies travel, and every rank
     ends up with a share of the pairs."""
