@@ -344,7 +344,7 @@ def measure(rig, wl, sc, steps, warmup, e2e_steps, want_stages, partitioned=Fals
     import scenes
     t0 = time.time()
     P_cap = max_pairs_for(args, wl)
-    gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=P_cap, device=dev)
+    gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=P_cap, device=dev, raw_records=False)
     nb = sc.n
     stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", dev))
     mg = None
@@ -486,7 +486,7 @@ def measure(rig, wl, sc, steps, warmup, e2e_steps, want_stages, partitioned=Fals
     if partitioned and args.check:
         # parity inside the REAL multi-rank run: union over the ranks == one GPU, step by step (fresh worlds, NCCL exchange)
         chk = pkg.partition_check(pkg, lambda g: pkg.PartitionedStepper(g, rig.rank, rig.world, rig.dist, torch, dev),
-                                  lambda: scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=P_cap, device=dev),
+                                  lambda: scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=P_cap, device=dev, raw_records=False),
                                   frames, rig.rank, rig.world, rig.dist, steps=4)
         if chk is not None:
             out["check"] = chk
@@ -636,6 +636,7 @@ def run_ours(args):
                    "snapshot": f"settled ({args.settle} relaxation iterations)" if settled else "raw jittered lattice (deep overlaps)",
                    "deep_penetration_checks_per_step": st["deep_penetration_checks"],
                    "proxies": nb, "l2": "flushed between timed iterations (192 MiB write)",
+                   "raw_detector_records": "off = the library default (b2c_set_raw_records: an inspection channel of this library, not an output of the reference; the tests switch it on)",
                    "parallelism": pl, "cpu_binding_rank0": rig.cpu_binding},
         "pairs_per_s": pairs_all / args.steps / (ms_max * 1e-3),
         "contacts_per_s": contacts_all / args.steps / (ms_max * 1e-3),

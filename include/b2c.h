@@ -277,6 +277,10 @@ typedef struct {
     int32_t pad[1];
 } b2c_raw_contact; /* 56 bytes */
 int32_t b2c_get_raw_contacts(b2c_ctx*, b2c_raw_contact* out, int32_t cap, int32_t* num_out);
+/* The records of pairs whose result nobody on the device reads (no contact; closed-form algorithms that update their manifold
+ * in place) are only written when this inspection channel is on (default off: 64 bytes per dispatched pair per step).
+ * b2c_get_raw_contacts returns B2C_ERR_STATE while it is off.  Takes effect with the next dispatch. */
+int32_t b2c_set_raw_records(b2c_ctx*, int32_t on);
 
 /* Effective broadphase AABBs (DbvtProxy.aabb / SimpleBroadphaseProxy min,max) for bodies 1..n: n x 6 floats */
 int32_t b2c_get_aabbs(b2c_ctx*, float* minmax_out, int32_t n);

@@ -70,7 +70,7 @@ EXPORTS = [
     "b2c_device_transforms", "b2c_transforms_written", "b2c_step_device", "b2c_sync_counts", "b2c_get_contacts",
     "b2c_set_profiling", "b2c_get_stage_times", "b2c_get_gjk_kernel_time", "b2c_mgpu_p2p_init", "b2c_mgpu_p2p_connect", "b2c_mgpu_p2p_export_halo", "b2c_mgpu_p2p_import_halo", "b2c_mgpu_p2p_export_departed", "b2c_mgpu_p2p_import_arrivals", "b2c_stage_name", "b2c_set_transforms_device", "b2c_set_partition", "b2c_mgpu_broadphase", "b2c_mgpu_export_departed",
     "b2c_mgpu_import_arrivals", "b2c_mgpu_narrowphase", "b2c_mgpu_slot_bytes", "b2c_mgpu_export_departed_slot",
-    "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest", "b2c_convex_sweep_closest", "b2c_ccd_sweep_not_me",
+    "b2c_mgpu_import_arrival_slots", "b2c_get_pair_deltas", "b2c_compute_islands", "b2c_get_solver_contacts", "b2c_set_world_aabb", "b2c_set_no_collide_pairs", "b2c_ray_test_closest", "b2c_convex_sweep_closest", "b2c_ccd_sweep_not_me", "b2c_set_raw_records",
     "b2c_shape_register_compound", "b2c_get_packed_contacts", "b2c_set_contact_prefetch", "b2c_begin_contact_download",
     "b2c_get_packed_contacts_uid", "b2c_set_pair_delta_prefetch", "b2c_set_partition_slabs", "b2c_get_partition",
     "b2c_mgpu_halo_slot_bytes", "b2c_mgpu_update_export_halo", "b2c_mgpu_import_halo", "b2c_shape_register_mesh_parts",
@@ -164,6 +164,7 @@ def load():
     L.b2c_set_world_aabb.argtypes = [vp, vp, vp]
     L.b2c_ray_test_closest.argtypes = [vp, i32, vp, vp, C.c_int16, C.c_int16, vp, vp, vp, vp]
     L.b2c_convex_sweep_closest.argtypes = [vp, i32, vp, vp, vp, vp, C.c_int16, C.c_int16, C.c_float, vp, vp, vp, vp]
+    L.b2c_set_raw_records.argtypes = [vp, i32]
     L.b2c_ccd_sweep_not_me.argtypes = [vp, i32, vp, vp, vp, C.c_float, vp, vp, vp, vp]
     L.b2c_set_no_collide_pairs.argtypes = [vp, i32, vp]
     L.b2c_get_pair_deltas.argtypes = [vp, vp, i32, vp, i32, pi32, pi32]

@@ -207,6 +207,7 @@ struct b2c_ctx {
     bool prof = false;
     cudaEvent_t stageEv[B2C_NUM_STAGES + 1] = {};
     cudaEvent_t evGjk[2] = {};     // around k_gjk alone (profiling)
+    bool wantRaw = false;          // b2c_set_raw_records: the inspection records of pairs nobody on the device reads
     bool stageValid = false;
 
     // compound shapes (compound.cuh) — buffers are allocated when the first one is registered
@@ -583,6 +584,7 @@ NpArgs makeNpArgs(b2c_ctx* ctx) {
     a.mpts = ctx->dMPts[ctx->cur];
     a.raw = ctx->dRaw;
     a.rawFlag = ctx->dRawFlag;
+    a.wantRaw = ctx->wantRaw ? 1 : 0;
     a.hist = ctx->dHist;
     a.binOf = ctx->dBinOf;
     a.binItems = ctx->dBinItems;
@@ -890,7 +892,8 @@ static void stepSignature(const b2c_ctx* ctx, int kind, uint64_t sig[4]) {
              ((uint64_t)(uint32_t)ctx->slab.rank << 40) | ((uint64_t)(uint32_t)ctx->partRanks << 52);
     sig[2] = (uint64_t)(uintptr_t)ctx->dNoCollide ^ ((uint64_t)slabUpper(ctx) << 40);
     sig[3] = ((uint64_t)ctx->numNoCollide << 32) | (uint32_t)ctx->epaLpw | ((uint32_t)ctx->mccBlocks << 8) |
-             ((uint32_t)(ctx->deltaPrefetch ? 1 : 0) << 16) | ((uint32_t)(useRowOrder(ctx) ? 1 : 0) << 17);
+             ((uint32_t)(ctx->deltaPrefetch ? 1 : 0) << 16) | ((uint32_t)(useRowOrder(ctx) ? 1 : 0) << 17) |
+             ((uint32_t)(ctx->wantRaw ? 1 : 0) << 18);
 }
 
 static void dropStepGraphs(b2c_ctx* ctx) {
@@ -1964,9 +1967,19 @@ int32_t b2c_get_manifolds(b2c_ctx* ctx, b2c_manifold* out, int32_t cap, int32_t 
     return B2C_OK;
 }
 
+int32_t b2c_set_raw_records(b2c_ctx* ctx, int32_t on) {
+    if (!ctx) return B2C_ERR_BAD_ARG;
+    ctx->wantRaw = on != 0;
+    return B2C_OK;
+}
+
 int32_t b2c_get_raw_contacts(b2c_ctx* ctx, b2c_raw_contact* out, int32_t cap, int32_t* numOut) {
     if (!ctx) return B2C_ERR_BAD_ARG;
     if (!ctx->pairsValid) return B2C_ERR_STATE;
+    if (!ctx->wantRaw) {
+        ctx->err = "raw detector records are an inspection channel and off by default: call b2c_set_raw_records(ctx, 1) before the dispatch";
+        return B2C_ERR_STATE;
+    }
     cudaSetDevice(ctx->device);
     uint32_t n = 0;
     CK(cudaMemcpyAsync(&n, ctx->dNumPairs[ctx->cur], sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));

@@ -64,6 +64,7 @@ struct NpArgs {
     b2c_manifold_point* mpts;     // [4*maxPairs] this step: the 4 point slots of each manifold
     b2c_raw_contact* raw;         // [maxPairs]
     int8_t* rawFlag;              // [maxPairs] copy of raw[p].has_contact for the kernels that only need the flag
+    int wantRaw;                  // b2c_set_raw_records: also write the raw records nobody on the device reads (inspection)
     uint8_t* hist;                // [maxPairs] GJK iterations each pair needed last step (0 = none / new pair, capped at 15):
                                   //   written by k_carry from the manifold header word k_gjk leaves there
     uint8_t* binOf;               // [maxPairs] bin of every pair (k_classify)
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
         f3 diff = sub3(t0.o, t1.o);
         float len = len3(diff);
         if (len > (r0 + r1)) {
-            writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, 10, 0);
+            if (a.wantRaw) writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, 10, 0);
             if (h1.x != 0) manifoldStepV(H, a.mpts + 4 * (size_t)p, h0, h1, pr.x, t0, t1, false, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, a.threshold, 0.f, 0.f);
             else if (fresh) { reinterpret_cast<int4*>(H)[0] = h0; reinterpret_cast<int4*>(H)[1] = h1; }
             continue;
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(256) k_sphere_sphere(NpArgs a) {
         f3 n = mk3(1.f, 0.f, 0.f);
         if (len > B2C_FLT_EPSILON) n = scl3(diff, 1.f / len);
         f3 pos1 = add3(t1.o, scl3(n, r1));
-        writeRaw(a.raw + p, pr, -1, 1, n, pos1, dist, 10, 0);
+        if (a.wantRaw) writeRaw(a.raw + p, pr, -1, 1, n, pos1, dist, 10, 0);   // the manifold is updated right here
         float2 m0 = a.material[b0], m1 = a.material[b1];
         if (manifoldStepV(H, a.mpts + 4 * (size_t)p, h0, h1, pr.x, t0, t1, true, n, pos1, dist, a.threshold, combinedFriction(m0.x, m1.x),
                           m0.y * m1.y))
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(256) k_convex_plane(NpArgs a) {
         f3 world = xfPoint(tp, projected);
         bool has = distance < a.threshold;
         f3 nW = mulMV(tp.m, planeNormal);
-        writeRaw(a.raw + p, pr, -1, has ? 1 : 0, nW, world, distance, 11, 0);
+        if (a.wantRaw) writeRaw(a.raw + p, pr, -1, has ? 1 : 0, nW, world, distance, 11, 0);
         if (has) {
             float2 m0 = a.material[b0], m1 = a.material[b1];
             if (manifoldAdd(m, pr.x, t0, t1, nW, world, distance, a.threshold, combinedFriction(m0.x, m1.x), m0.y * m1.y, 0, 0)) added++;
@@ -970,8 +971,8 @@ k_gjk_prefilter(NpArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict
             delta = dot3(axis, w);
             bool done = normal1 && (delta > 0.f) && (delta * delta > sq1 * maxDistSq);
             if (done) {
-                writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, -1, 1);
-                a.rawFlag[p] = 0;
+                if (a.wantRaw) writeRaw(a.raw + p, pr, -1, 0, mk3(0, 0, 0), mk3(0, 0, 0), 0.f, -1, 1);
+                a.rawFlag[p] = 0;   // all k_manifold_cc needs of a pair without a contact
                 checks++;
             }
             survive = !done;
@@ -1079,6 +1080,7 @@ k_gjk(NpArgs a, GjkArgs g, uint32_t* cursor, const uint32_t* __restrict__ surviv
                 }
                 if (!queued) {
                     f3 pt = add3(r.pointOnB, r.positionOffset);
+                    if (a.wantRaw || r.isValid)   // the record carries the contact to k_manifold_cc; without one the flag is enough
                     writeRaw(a.raw + p, pr, -1, r.isValid ? 1 : 0, r.isValid ? r.normalInB : mk3(0, 0, 0), r.isValid ? pt : mk3(0, 0, 0),
                              r.isValid ? r.distance : 0.f, r.lastUsedMethod, r.curIter);
                     a.rawFlag[p] = r.isValid ? 1 : 0;

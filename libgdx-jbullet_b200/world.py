@@ -39,7 +39,7 @@ def transforms_to_planes(xf):
 class GpuCollisionWorld:
     def __init__(self, mode=DBVT, max_bodies=131072, max_pairs=2 << 20, num_worlds=1, device=0, max_mesh_items=1 << 20,
                  max_hull_points=1 << 20, max_shapes=4096, contact_breaking_threshold=0.02, world_aabb=None,
-                 max_compound_items=0):
+                 max_compound_items=0, raw_records=False):
         self.L = _lib.load()
         cfg = Config()
         self.L.b2c_default_config(C.byref(cfg))
@@ -63,6 +63,8 @@ class GpuCollisionWorld:
             mn = np.ascontiguousarray(world_aabb[0], dtype=np.float32)
             mx = np.ascontiguousarray(world_aabb[1], dtype=np.float32)
             self._ck(self.L.b2c_set_world_aabb(self.h, _vp(mn), _vp(mx)))
+        if raw_records:   # inspection channel: the raw detector record of EVERY dispatched pair (tests, debugging)
+            self._ck(self.L.b2c_set_raw_records(self.h, 1))
         self.num_bodies = 0
         self._broadphase = GpuBroadphase(self)
         self._dispatcher = GpuDispatcher(self)

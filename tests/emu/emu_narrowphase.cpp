@@ -221,7 +221,7 @@ int main(int argc, char** argv) {
         uint32_t nP = Pn;
         a.pairs = pairs.data(); a.numPairs = &nP; a.xf4 = xf4.data(); a.shape = bodyShape.data(); a.flags = flags.data(); a.material = material.data();
         a.shapes = sc.shapes.data(); a.hullPts = sc.hull.data(); a.meshes = meshes.data(); a.mhdr = H[cur].data(); a.mpts = P[cur].data();
-        a.raw = raw.data(); a.rawFlag = rawFlag.data(); a.hist = hist.data(); a.binOf = binOf.data(); a.binItems = binItems.data(); a.binStart = binStart;
+        a.raw = raw.data(); a.rawFlag = rawFlag.data(); a.wantRaw = 1; /* the harness compares every raw detector record */ a.hist = hist.data(); a.binOf = binOf.data(); a.binItems = binItems.data(); a.binStart = binStart;
         a.ctr = &ctr; a.threshold = 0.02f; a.maxPairs = MAXP; a.uidBits = uidBits;
         GjkArgs g{};
         g.epaItems = epaItems.data(); g.maxEpa = MAXI; g.epaRetry = epaRetry.data(); g.maxEpaRetry = MAXI; g.epaBig = epaBig.data();

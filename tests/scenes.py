@@ -393,6 +393,7 @@ def terrain_compound_scene(cells=32, n=150, seed=15, cell=0.5):
 # ---- build the same scene on both sides ---------------------------------------------------------------
 def build_gpu(pkg, sc, mode, max_pairs=None, **kw):
     n = sc.n
+    kw.setdefault("raw_records", True)   # the parity helpers compare the raw detector records too
     gw = pkg.GpuCollisionWorld(mode=mode, max_bodies=max(n, 16), max_pairs=max_pairs or max(16 * n, 4096),
                                num_worlds=sc.num_worlds, **kw)
     ids = []

@@ -176,3 +176,21 @@ def test_multi_part_mesh_with_16_bit_indices(gpu_pkg):
     gu, gf, gnrm, gpt = gw.rayTestClosest(frm, to)
     ou, of, onrm, opt = ow.ray_test_closest(frm, to)
     assert np.array_equal(gu, ou) and np.array_equal(gf.view(np.uint32), of.view(np.uint32))
+
+
+def test_raw_records_are_an_opt_in_inspection_channel(gpu_pkg):
+    """b2c_set_raw_records: off by default — pairs, manifolds and the contact stream do not depend on it, and
+    b2c_get_raw_contacts says why it has nothing to return."""
+    sc = scenes.bin_scene(n=1500, seed=61)
+    on = scenes.build_gpu(gpu_pkg, sc, mode=1)                       # the test helpers switch the channel on
+    off = scenes.build_gpu(gpu_pkg, sc, mode=1, raw_records=False)   # the library default
+    for step in range(3):
+        for w in (on, off):
+            w.setWorldTransforms(sc.transforms(step)); w.step()
+        assert np.array_equal(on.pairs(), off.pairs())
+        assert on.manifolds().tobytes() == off.manifolds().tobytes()
+        h0, p0 = on.contacts(); h1, p1 = off.contacts()
+        assert len(h0) == len(h1) and len(p0) == len(p1)
+    assert len(on.raw_contacts()) == len(on.pairs())
+    with pytest.raises(gpu_pkg.B2CError, match="inspection channel"):
+        off.raw_contacts()

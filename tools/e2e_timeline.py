@@ -21,7 +21,7 @@ def main():
     bench.load_settled(sc, 100000, 100, 60)
     sc.vel *= 0.25
     P_cap = 3 << 20
-    gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=P_cap)
+    gw = scenes.build_gpu(pkg, sc, mode=pkg.DBVT, max_pairs=P_cap, raw_records=False)
     L = gw.L
     nb = sc.n
     frames = [torch.from_numpy(np.ascontiguousarray(pkg.transforms_to_planes(sc.transforms(k)))).pin_memory() for k in range(4)]
