@@ -42,6 +42,44 @@ def test_cuda_matches_golden(gpu_pkg, name):
     parity.compare_gpu_to_golden(gw, sc, gold, steps, sc.extent)
 
 
+# ---- queries behind the pair list: rays, convex sweeps, CCD sweeps on a stepped world ---------------------------------
+def _query_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD_DIR, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg
+
+
+def _compare_queries(out, gold):
+    for q in ("ray", "sweep", "ccd"):
+        assert np.array_equal(out[q + "_uid"], gold[q + "_uid"]), f"{q}: hit bodies differ"
+        assert np.array_equal(out[q + "_frac"].view(np.uint32), gold[q + "_frac"].view(np.uint32)), f"{q}: fractions differ"
+        hit = gold[q + "_uid"] > 0
+        assert np.array_equal(out[q + "_nrm"][hit].view(np.uint32), gold[q + "_nrm"][hit].view(np.uint32)), f"{q}: normals differ"
+        assert np.array_equal(out[q + "_pt"][hit].view(np.uint32), gold[q + "_pt"][hit].view(np.uint32)), f"{q}: points differ"
+        assert hit.sum() >= 5, f"{q}: the fixture should contain hits"
+
+
+@pytest.mark.parametrize("k,name", list(enumerate(sorted(_query_cases().QUERY_CASES))))
+def test_oracle_reproduces_query_golden(k, name):
+    mg = _query_cases()
+    make, mode, steps = mg.QUERY_CASES[name]
+    sc = make()
+    _compare_queries(mg.run_queries(scenes.build_oracle(sc, mode), sc, steps, k, True), np.load(os.path.join(GOLD_DIR, name + ".npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,name", list(enumerate(sorted(_query_cases().QUERY_CASES))))
+def test_cuda_matches_query_golden(gpu_pkg, k, name):
+    """Rays, convex sweeps and CCD sweeps of the CUDA path against stored oracle outputs (nothing under oracle/ runs)."""
+    mg = _query_cases()
+    make, mode, steps = mg.QUERY_CASES[name]
+    sc = make()
+    gw = scenes.build_gpu(gpu_pkg, sc, mode=mode, max_pairs=1 << 15)
+    _compare_queries(mg.run_queries(gw, sc, steps, k, False), np.load(os.path.join(GOLD_DIR, name + ".npz")))
+
+
 # ---- vectors from the REAL reference, when somebody has produced them (tools/javaref/run.sh on a box with a JDK + gdx jar) ----
 JAVA_CASES = sorted(n for n in CASES if os.path.exists(os.path.join(GOLD_DIR, "java_" + n + ".npz")))
 
