@@ -432,7 +432,7 @@ int32_t b2c_mgpu_import_halo(b2c_ctx*, const void* slots_dev, int32_t nslots, in
  *   b2c_mgpu_p2p_export_departed / b2c_mgpu_p2p_import_arrivals: the manifolds of pairs that changed owner, pushed to every
  *                        other rank the same way (replace export_departed_slot + all-gather + import_arrival_slots).
  * With both, a partitioned step contains no collective at all — only this library's kernels over peer memory.
- * A source that never publishes (a dead peer) ends the wait after ~3 s; b2c_sync_counts then returns B2C_ERR_STATE. */
+ * A source that never publishes (a dead peer) ends the wait after ~10 s; b2c_sync_counts then returns B2C_ERR_STATE. */
 int32_t b2c_mgpu_p2p_init(b2c_ctx*, int32_t cap, int32_t migrate_cap, void* ipc_handle_out /* 64 bytes */, void** inbox_dev_out);
 int32_t b2c_mgpu_p2p_connect(b2c_ctx*, const void* ipc_handles, void* const* inbox_ptrs);
 int32_t b2c_mgpu_p2p_export_halo(b2c_ctx*);

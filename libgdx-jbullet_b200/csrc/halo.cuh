@@ -263,7 +263,7 @@ k_halo_wait(const unsigned char* __restrict__ inboxParity, int nranks, int rank,
     const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(inboxParity + (size_t)s * slotBytes);
     const long long t0 = clock64();
     while ((uint32_t)(ld_acquire_sys_u64(hdr) >> 32) != epoch) {
-        if (clock64() - t0 > 6000000000ll) { ctr->haloOverflow = 2; break; }   // ~3 s: a peer died; reported by the host as an error
+        if (clock64() - t0 > 20000000000ll) { ctr->haloOverflow = 2; break; }   // ~10 s: a peer died; reported by the host as an error
         __nanosleep(200);
     }
 }

@@ -225,6 +225,8 @@ def partition_check(pkg, make_stepper, build_world, frames, rank, nranks, dist, 
             assert tot[2] == ref[2] and tot[3] == ref[3], f"step {k}: touching manifolds / points {tot[2]}/{tot[3]} vs {ref[2]}/{ref[3]}"
             assert tot[4] == ref[4], f"step {k}: manifold contents differ (digest)"
             report["pairs"].append(ref[0]); report["touching_manifolds"].append(ref[2]); report["contact_points"].append(ref[3])
+        if dist is not None and nranks > 1:
+            dist.barrier()   # the other ranks wait for rank 0's single-GPU step here, not inside the next step's flag wait
     mg.close()
     gw.close()
     if single is not None:

@@ -150,7 +150,7 @@ def test_peer_to_peer_halo_needs_a_connection(gpu_pkg):
 
 
 def test_a_peer_that_never_publishes_is_reported(gpu_pkg):
-    """Failure detection of the peer-to-peer exchange: rank 0 waits for rank 1's epoch flag, rank 1 never exports; after ~3 s
+    """Failure detection of the peer-to-peer exchange: rank 0 waits for rank 1's epoch flag, rank 1 never exports; after ~10 s
     the wait gives up and the step's counters come back as an error instead of a hang."""
     sc = scenes.spheres_scene(n=2000, seed=5)
     ranks = [scenes.build_gpu(gpu_pkg, sc, mode=1) for _ in range(2)]
