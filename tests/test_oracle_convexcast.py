@@ -113,3 +113,39 @@ def test_ccd_motion_clamping_sweep_skips_me_and_touching_objects():
     s02 = w.sphere(0.2)
     uid, _, _, _ = w.convex_sweep_closest(s02, EYE, [(0, 2.0, 0)], [(0, -3, 0)])
     assert uid[0] == 2 or uid[0] == 1
+
+
+def test_sphere_sweeps_onto_a_box_face_match_the_closed_form_time_of_impact():
+    """Randomised: a sphere of radius r swept onto the top face of a large box from random heights and directions touches when
+    its centre is r above the face: fraction = (y0 - r) / (y0 - y1).  Against a flat face the first conservative-advancement
+    step of GjkConvexCast lands on the contact itself, so the reported fraction equals the closed form to float rounding
+    (positions up to 20 units: ~1e-5); in general it may stop up to its 0.001 radius early."""
+    rng = np.random.default_rng(77)
+    w = orc.OracleWorld(mode=orc.TIGHT)
+    slab = w.box(50.0, 1.0, 50.0)                       # top face at y = 0 (centre at y = -1)
+    w.body(slab, orc.xf12(origin=(0, -1.0, 0)), 1, -1, True, 0)
+    n = 200
+    r = 0.3
+    cast = w.sphere(r)
+    f = np.stack([rng.uniform(-20, 20, n), rng.uniform(1.0, 6.0, n), rng.uniform(-20, 20, n)], axis=1).astype(np.float32)
+    t = np.stack([f[:, 0] + rng.uniform(-5, 5, n), rng.uniform(-4.0, -0.5, n), f[:, 2] + rng.uniform(-5, 5, n)], axis=1).astype(np.float32)
+    uid, frac, nrm, pt = w.convex_sweep_closest(cast, EYE, f, t)
+    assert (uid == 1).all()
+    exact = (f[:, 1].astype(np.float64) - r) / (f[:, 1].astype(np.float64) - t[:, 1].astype(np.float64))
+    slack = 0.0011 / (f[:, 1] - t[:, 1]).astype(np.float64) + 1e-6
+    assert (frac <= exact + 2e-5).all() and (frac >= exact - slack).all(), (np.abs(frac - exact).max(), slack.max())
+    assert np.abs(frac - exact).max() < 2e-5
+    assert np.allclose(nrm, [0, 1, 0], atol=1e-4)
+    # the hit point lies on the face (y = 0) below the sphere centre at the time of impact
+    centre = f + (t - f) * frac[:, None]
+    assert np.abs(pt[:, 1]).max() < 2e-3 and np.abs(pt[:, [0, 2]] - centre[:, [0, 2]]).max() < 2e-3
+    # a rotated box cast (45 degrees about z, lowest edge sqrt(2) * h below the centre) against the same face
+    c, s = np.cos(np.pi / 4), np.sin(np.pi / 4)
+    rot = np.asarray([[c, -s, 0], [s, c, 0], [0, 0, 1]], np.float32)
+    h = 0.25
+    bx = w.box(h, h, h)
+    uid, frac, _, _ = w.convex_sweep_closest(bx, rot, f, t)
+    # GJK works on the margin-less core (half extent h - 0.04) plus a 0.04 margin sphere: the lowest EDGE of the rotated box is rounded
+    low = np.sqrt(2.0) * (h - 0.04) + 0.04
+    exact = (f[:, 1].astype(np.float64) - low) / (f[:, 1].astype(np.float64) - t[:, 1].astype(np.float64))
+    assert (uid == 1).all() and (frac <= exact + 1e-4).all() and (frac >= exact - slack - 1e-4).all()
