@@ -149,3 +149,37 @@ def test_sphere_sweeps_onto_a_box_face_match_the_closed_form_time_of_impact():
     low = np.sqrt(2.0) * (h - 0.04) + 0.04
     exact = (f[:, 1].astype(np.float64) - low) / (f[:, 1].astype(np.float64) - t[:, 1].astype(np.float64))
     assert (uid == 1).all() and (frac <= exact + 1e-4).all() and (frac >= exact - slack - 1e-4).all()
+
+
+def test_sphere_sweeps_onto_a_flat_triangle_mesh_match_the_closed_form():
+    """BVH box-cast walk + SubsimplexConvexCast per triangle on a flat grid mesh at y = 0.5: a sphere of radius r touches the
+    triangles' margin shell when its centre is r + mesh margin above the plane.  SubsimplexConvexCast stops once the squared
+    distance falls under 1e-4, i.e. up to 0.01 early."""
+    rng = np.random.default_rng(5)
+    w = orc.OracleWorld(mode=orc.TIGHT)
+    c = 12
+    xs = np.arange(c + 1, dtype=np.float32)
+    verts = np.asarray([(x, 0.5, z) for x in xs for z in xs], np.float32)
+    tris = []
+    for i in range(c):
+        for j in range(c):
+            v00, v10, v01, v11 = i * (c + 1) + j, (i + 1) * (c + 1) + j, i * (c + 1) + j + 1, (i + 1) * (c + 1) + j + 1
+            tris += [(v00, v01, v10), (v10, v01, v11)]
+    m = w.mesh(verts, np.asarray(tris, np.int32))
+    w.body(m, orc.xf12(), 2, -1 ^ 2, True, 0)
+    r = 0.25
+    cast = w.sphere(r)
+    n = 120
+    f = np.stack([rng.uniform(1, 11, n), rng.uniform(2.0, 5.0, n), rng.uniform(1, 11, n)], axis=1).astype(np.float32)
+    t = np.stack([np.clip(f[:, 0] + rng.uniform(-1.5, 1.5, n), 0.5, 11.5), rng.uniform(-2.0, 0.0, n),
+                  np.clip(f[:, 2] + rng.uniform(-1.5, 1.5, n), 0.5, 11.5)], axis=1).astype(np.float32)
+    uid, frac, nrm, pt = w.convex_sweep_closest(cast, EYE, f, t)
+    assert (uid == 1).all()
+    margin = 0.0   # BvhTriangleMeshShape: collisionMargin 0 (sh/TriangleMeshShape.java), the triangles get the mesh's margin
+    dy = (f[:, 1] - t[:, 1]).astype(np.float64)
+    exact = (f[:, 1].astype(np.float64) - (0.5 + r + margin)) / dy
+    assert (frac <= exact + 1e-5).all() and (frac >= exact - 0.0101 / dy - 1e-5).all(), np.abs(frac - exact).max()
+    # the reported normal is the simplex's separation vector at the LAST advancement (np/SubsimplexConvexCast.java:150), which
+    # for an oblique approach is still a little off the face normal when the cast stops early
+    assert (nrm[:, 1] > 0.95).all() and np.abs(np.linalg.norm(nrm, axis=1) - 1.0).max() < 1e-5
+    assert np.abs(pt[:, 1] - 0.5).max() < 1e-3        # hit point = the simplex's point on the triangle
