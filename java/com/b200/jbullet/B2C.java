@@ -84,6 +84,8 @@ final class B2C {
     // DiscreteDynamicsWorld.integrateTransforms' CCD motion clamping sweeps (ClosestNotMeConvexResultCallback), batched
     static final MethodHandle ccdSweepNotMe = h("b2c_ccd_sweep_not_me",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_FLOAT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    // inspection channel: the raw detector record of every dispatched pair (off by default)
+    static final MethodHandle setRawRecords = h("b2c_set_raw_records", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
     // device-resident stepping: enqueue, download the pair list while the narrowphase runs, then wait for the counts
     static final MethodHandle stepDevice = h("b2c_step_device", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle syncCounts = h("b2c_sync_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));

@@ -101,3 +101,16 @@ def test_reference_arm_steps_one_world_per_requested_gpu():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["n_gpus"] == 2 and d["cpu_baseline"]["cores"] == 2
     assert abs(d["value"] - 2 * 1000.0 / d["ms_per_step"]) < 1e-6 * d["value"]   # whole-job rate of 2 worlds on 2 cores
+
+
+def test_compound_child_table_flattening(tmp_path):
+    """csrc/compound_flatten.h + compoundChildWorld (common.cuh) on the host: depth-first leaf order of nested CompoundShapes,
+    one frame entry per nested occurrence, leaf world transforms equal to the level-by-level composition bit for bit, and the
+    nesting limit (tests/hostcc/flatten_check.cpp; test infrastructure only)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "flatten_check")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-DB2C_HOST_EMULATION", "-I", os.path.join(here, "emu"), "-w",
+                           "-o", exe, os.path.join(here, "hostcc", "flatten_check.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
