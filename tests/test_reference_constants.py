@@ -40,6 +40,16 @@ WHERE = {
                                      ("oracle/convexcast.h", r"const float epsilon\s*=\s*" + NUM), ("oracle/raycast.h", r"const float epsilon\s*=\s*" + NUM)],
     "allowedCcdPenetration": [("include/b2c_host.hpp", r"allowedCcdPenetration\s*=\s*" + NUM), ("libgdx-jbullet_b200/world.py", r"allowed_ccd_penetration=" + NUM)],
     "aabb_overflow_guard_len2": [(CS + "broadphase.cuh", r"len2_3\(d\) < " + NUM), ("oracle/world.h", r"tmp\.len2\(\) < " + NUM)],
+    "GJK_max_iterations": [(CS + "gjk.cuh", r"curIter\+\+ > " + NUM), ("oracle/gjk.h", r"gGjkMaxIter\s*=\s*" + NUM)],
+    "GJK_degenerate5_lenSqr": [(CS + "gjk.cuh", r"if \(lenSqr < " + NUM + r"\) degenerate = 5"), ("oracle/gjk.h", r"if \(lenSqr < " + NUM + r"\) degenerateSimplex = 5")],
+    "GJK_catch_degenerate_distance": [(CS + "gjk.cuh", r"\(distance \+ margin\) < " + NUM), ("oracle/gjk.h", r"\(distance \+ margin\) < " + NUM)],
+    "Voronoi_degenerate_signd": [(CS + "gjk.cuh", r"signd \* signd < \(\(" + NUM), ("oracle/voronoi.h", r"signd \* signd < \(\(" + NUM)],
+    "Hull_tiny_direction_lenSqr": [(CS + "gjk.cuh", r"if \(l2 < " + NUM + r"\) v = mk3\(1"), ("oracle/shapes.h", r"if \(lenSqr < " + NUM)],
+    "Hull_maxDot_init": [(CS + "gjk.cuh", r"float maxDot\s*=\s*" + NUM), ("oracle/shapes.h", r"newDot, maxDot\s*=\s*" + NUM)],
+    "BVH_MAX_NUM_PARTS_IN_BITS": [],   # checked below: leaf word = partId << (31 - bits)
+    "FILTER_DEFAULT": [("libgdx-jbullet_b200/world.py", r"DEFAULT_FILTER, STATIC_FILTER, ALL_FILTER = " + NUM)],
+    "FILTER_STATIC": [("libgdx-jbullet_b200/world.py", r"DEFAULT_FILTER, STATIC_FILTER, ALL_FILTER = [-0-9]+, " + NUM)],
+    "FILTER_ALL": [("libgdx-jbullet_b200/world.py", r"DEFAULT_FILTER, STATIC_FILTER, ALL_FILTER = [-0-9]+, [-0-9]+, " + NUM)],
     "CONVEX_DISTANCE_MARGIN": [(CS + "b2c_api.cu", r"s\.margin = margin >= 0\.f \? margin : " + NUM),
                                ("oracle/jmath.h", r"CONVEX_DISTANCE_MARGIN\s*=\s*" + NUM)],
 }
@@ -54,6 +64,14 @@ def test_constant_matches_the_reference_source(name):
         assert hits, f"{name}: no literal found in {rel} (pattern {rx!r})"
         for h in hits:
             assert float(h) == want, f"{name}: {rel} has {h}, the reference has {want} at {GOLD[name]['source']}"
+
+
+def test_mesh_leaf_word_uses_the_reference_part_bits():
+    """sh/OptimizedBvh.java:65 MAX_NUM_PARTS_IN_BITS = 10: a leaf stores partId << (31 - 10) | triangleIndex."""
+    shift = 31 - int(GOLD["BVH_MAX_NUM_PARTS_IN_BITS"]["value"])
+    assert shift == 21
+    assert f"<< {shift}) | (uint32_t)t" in open(os.path.join(ROOT, CS + "b2c_api.cu")).read()
+    assert f"<< {shift}" in open(os.path.join(ROOT, "oracle", "world.h")).read()
 
 
 def test_every_extracted_constant_is_checked_somewhere_or_documented():

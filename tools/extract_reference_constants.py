@@ -38,6 +38,16 @@ SPEC = {
     "allowedCcdPenetration": ("collision/broadphase/DispatcherInfo.java", r"allowedCcdPenetration\s*=\s*" + NUM),
     "aabb_overflow_guard_len2": ("collision/dispatch/CollisionWorld.java", r"len2\(\)\s*<\s*" + NUM),
     "ccd_min_hit_fraction": ("dynamics/DiscreteDynamicsWorld.java", r"closestHitFraction\s*>\s*" + NUM),
+    "GJK_max_iterations": ("collision/narrowphase/GjkPairDetector.java", r"gGjkMaxIter\s*=\s*" + NUM),
+    "GJK_degenerate5_lenSqr": ("collision/narrowphase/GjkPairDetector.java", r"lenSqr\s*<\s*" + NUM),
+    "GJK_catch_degenerate_distance": ("collision/narrowphase/GjkPairDetector.java", r"\(distance \+ margin\)\s*<\s*" + NUM),
+    "Voronoi_degenerate_signd": ("collision/narrowphase/VoronoiSimplexSolver.java", r"signd \* signd < \(\(" + NUM),
+    "Hull_tiny_direction_lenSqr": ("collision/shapes/ConvexHullShape.java", r"lenSqr\s*<\s*" + NUM),
+    "Hull_maxDot_init": ("collision/shapes/ConvexHullShape.java", r"maxDot\s*=\s*" + NUM),
+    "BVH_MAX_NUM_PARTS_IN_BITS": ("collision/shapes/OptimizedBvh.java", r"MAX_NUM_PARTS_IN_BITS\s*=\s*" + NUM),
+    "FILTER_DEFAULT": ("collision/broadphase/CollisionFilterGroups.java", r"DEFAULT_FILTER\s*=\s*" + NUM),
+    "FILTER_STATIC": ("collision/broadphase/CollisionFilterGroups.java", r"STATIC_FILTER\s*=\s*" + NUM),
+    "FILTER_ALL": ("collision/broadphase/CollisionFilterGroups.java", r"ALL_FILTER\s*=\s*" + NUM),
 }
 
 
