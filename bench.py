@@ -15,9 +15,10 @@ data-path collective, weak scaling); `value` is whole-job world-steps per second
 
 The same line also carries the two SHARDED configs of BASELINE.json (strong scaling, total work fixed as N grows):
   "c4": 4096 independent 64-body worlds split by world over the N GPUs (no collective),
-  "c5": ONE world of 1 M spheres partitioned by sorted-AABB slabs with a halo, boundary AABBs exchanged with ONE NCCL
-        all-gather per step over NVLink; with `check` = the union of the ranks' pair lists / manifolds compared against
-        a single-GPU run of the same step inside this very run.
+  "c5": ONE world of 1 M spheres partitioned by slabs of space with a halo; boundary AABBs + transforms and migrating
+        manifolds are stored by the library's own kernels straight into the peers' inboxes over NVLink (CUDA IPC; no
+        collective in the step — B2C_HALO=nccl selects the two all-gathers instead); with `check` = the union of the
+        ranks' pair lists / manifolds compared against a single-GPU run of the same step inside this very run.
 One JSON line on stdout from rank 0.
 """
 import argparse
